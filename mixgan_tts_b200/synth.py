@@ -1,0 +1,105 @@
+"""Deterministic synthetic weights and inputs for the parity tests and the bench.
+
+There is no network for checkpoints or datasets, so the Denoiser is random-init
+and the inputs are random tensors of the LJSpeech / AISHELL3 shapes
+(SURVEY.md §8d).  Everything is drawn from a ``numpy`` PCG64 stream so that the
+same arrays come out in this container (where the goldens are made with the
+real reference) and on the GPU box (where the reference does not exist).
+
+Weight names and shapes are the reference's ``state_dict`` keys for
+``Denoiser`` (``model/modules.py:385-418``, ``model/blocks.py:1133-1155``):
+conv weights ``[out, in, k]``, linear weights ``[out, in]``.  Init scales follow
+the reference constructors (PyTorch default conv init, xavier-uniform for the
+bias-free ``LinearNorm``), except ``output_projection.conv.weight`` which the
+reference zero-initialises (``model/modules.py:418``) and which is drawn
+N(0, 0.05^2) here so that parity is not vacuous.
+"""
+from __future__ import annotations
+
+import hashlib
+import numpy as np
+
+
+def _rng(seed: int) -> np.random.Generator:
+    return np.random.Generator(np.random.PCG64(seed))
+
+
+def _uniform(g, shape, bound):
+    return ((g.random(shape, dtype=np.float32) * 2.0 - 1.0) * np.float32(bound)).astype(np.float32)
+
+
+def make_denoiser_weights(seed: int = 0, *, n_mel: int = 80, channels: int = 256,
+                          d_encoder: int = 256, layers: int = 20,
+                          multi_speaker: bool = False) -> dict:
+    """Return ``{state_dict key: float32 ndarray}`` for one Denoiser."""
+    g = _rng(seed)
+    C, H, M = channels, d_encoder, n_mel
+    w = {}
+
+    def conv(name, cout, cin, k):
+        bound = 1.0 / np.sqrt(cin * k)
+        w[f"{name}.conv.weight"] = _uniform(g, (cout, cin, k), bound)
+        w[f"{name}.conv.bias"] = _uniform(g, (cout,), bound)
+
+    def linear(name, cout, cin):
+        bound = np.sqrt(6.0 / (cin + cout))
+        w[f"{name}.linear.weight"] = _uniform(g, (cout, cin), bound)
+
+    conv("input_projection.0", C, M, 1)
+    linear("mlp.0", 4 * C, C)
+    linear("mlp.2", C, 4 * C)
+    for l in range(layers):
+        p = f"residual_layers.{l}"
+        conv(f"{p}.conv_layer", 2 * C, C, 3)
+        linear(f"{p}.diffusion_projection", C, C)
+        if multi_speaker:
+            linear(f"{p}.speaker_projection", C, H)
+        conv(f"{p}.conditioner_projection", C, H, 1)
+        conv(f"{p}.output_projection", 2 * C, C, 1)
+    conv("skip_projection", C, C, 1)
+    conv("output_projection", M, C, 1)
+    w["output_projection.conv.weight"] = (
+        g.standard_normal((M, C, 1), dtype=np.float32) * np.float32(0.05))
+    return w
+
+
+def weights_digest(w: dict) -> str:
+    h = hashlib.sha256()
+    for k in sorted(w):
+        h.update(k.encode())
+        h.update(np.ascontiguousarray(w[k]).tobytes())
+    return h.hexdigest()
+
+
+def make_inputs(seed: int, B: int, T: int, K: int, *, n_mel: int = 80, d_encoder: int = 256,
+                multi_speaker: bool = False, shallow: bool = False,
+                min_len_frac: float = 0.5, spec_min: float = -11.5129,
+                spec_max: float = 2.0) -> dict:
+    """Synthetic batch (SURVEY.md §8d draw order).
+
+    Returns float32 arrays: ``cond [B,T,H]``, ``lens [B]`` (int64, ``lens[0]=T``),
+    ``pad_mask [B,T]`` (True = padding, the convention arriving at
+    ``GaussianDiffusion.forward``, model/mixgantts.py:122,137), ``spk [B,H]`` or
+    None, ``coarse_mel [B,T,M]`` and ``start_noise [B,1,M,T]`` (shallow only),
+    ``x_T [B,1,M,T]`` and ``noises [K,B,1,M,T]`` (``noises[t]`` is the draw the
+    reference makes inside ``q_posterior_sample`` at timestep ``t``).
+    """
+    g = _rng(seed)
+    out = {}
+    out["cond"] = g.standard_normal((B, T, d_encoder), dtype=np.float32)
+    lo = max(1, int(T * min_len_frac))
+    lens = g.integers(lo, T + 1, size=(B,), dtype=np.int64)
+    lens[0] = T
+    out["lens"] = lens
+    out["pad_mask"] = np.arange(T)[None, :] >= lens[:, None]
+    out["spk"] = g.standard_normal((B, d_encoder), dtype=np.float32) if multi_speaker else None
+    if shallow:
+        cm = g.standard_normal((B, T, n_mel), dtype=np.float32) * np.float32(2.0) - np.float32(5.0)
+        out["coarse_mel"] = np.clip(cm, spec_min, spec_max).astype(np.float32)
+        out["start_noise"] = g.standard_normal((B, 1, n_mel, T), dtype=np.float32)
+    else:
+        out["coarse_mel"] = None
+        out["start_noise"] = None
+    out["x_T"] = g.standard_normal((B, 1, n_mel, T), dtype=np.float32)
+    out["noises"] = g.standard_normal((K, B, 1, n_mel, T), dtype=np.float32)
+    return out

@@ -1,0 +1,91 @@
+"""Pin the oracle: it must reproduce the golden vectors the REAL reference produced
+(tests/golden/make_golden.py), and the reference's schedule buffers bit for bit."""
+import numpy as np
+import pytest
+import torch
+
+from mixgan_tts_b200 import synth
+from oracle import schedule
+from oracle.denoiser import denoiser_forward
+
+from helpers import GOLDEN_CASES, golden_case, load_golden, rel_l2
+
+# fp32 on a different host CPU may pick different oneDNN kernels: allow rounding-level drift.
+TOL = 2e-5
+
+
+@pytest.mark.parametrize("name", list(GOLDEN_CASES))
+def test_weights_generator_is_stable(name):
+    g = load_golden(name)
+    c = golden_case(name)
+    assert synth.weights_digest(c.W) == str(g["weights_sha256"]), \
+        "synthetic weight generator drifted: regenerate tests/golden with make_golden.py"
+
+
+@pytest.mark.parametrize("name", list(GOLDEN_CASES))
+def test_schedule_buffers_bit_exact(name):
+    g = load_golden(name)
+    c = golden_case(name)
+    assert c.oracle.K == int(g["K"])
+    for k, v in c.oracle.buf.items():
+        ref = g[f"sched_{k}"]
+        assert v.numpy().dtype == np.float32
+        assert np.array_equal(v.numpy().view(np.uint32), ref.view(np.uint32)), k
+
+
+def test_schedule_known_answers_survey_table():
+    # SURVEY.md §8a table, printed from the reference (LJSpeech naive, K=4, vpsde, beta in [0.1, 40])
+    b = schedule.diffusion_buffers(schedule.noise_schedule("vpsde", 4, 0.1, 40, 0.008))
+    np.testing.assert_allclose(b["betas"], [0.7196944356, 0.9768468738, 0.9980875850, 0.9998420477], rtol=2e-7)
+    np.testing.assert_allclose(b["alphas_cumprod"], [0.2803055644, 6.489953026e-3, 1.241165046e-5, 1.960629881e-9], rtol=2e-7)
+    np.testing.assert_allclose(b["posterior_mean_coef1"], [1.0, 0.5205591321, 0.08040717244, 3.522460582e-3], rtol=2e-7)
+    np.testing.assert_allclose(b["posterior_mean_coef2"], [0.0, 0.1102251783, 0.04344818369, 0.01256833225], rtol=2e-7)
+    np.testing.assert_allclose(b["posterior_log_variance_clipped"],
+                               [-46.05170059, -0.3458428085, -8.412964642e-3, -1.703891467e-4], rtol=2e-7)
+    k1 = schedule.diffusion_buffers(schedule.noise_schedule("vpsde", 1, 0.1, 40, 0.008))
+    assert k1["posterior_mean_coef1"][0] == 1.0 and k1["posterior_mean_coef2"][0] == 0.0
+    np.testing.assert_allclose(k1["sqrt_alphas_cumprod"], [4.4279e-5], rtol=1e-4)
+
+
+@pytest.mark.parametrize("mode", ["linear", "cosine", "vpsde"])
+def test_schedule_modes_shapes(mode):
+    # linear: np.linspace(1e-4, max_beta, K) (utils/tools.py:432) — max_beta is the last beta itself
+    b = schedule.noise_schedule(mode, 8, 0.1, 0.06 if mode == "linear" else 40, 0.008)
+    assert b.shape == (8,) and b.dtype == np.float64 and np.all(b > 0) and np.all(b <= 1.0)
+    buf = schedule.diffusion_buffers(b)
+    assert all(v.dtype == np.float32 and v.shape == (8,) for v in buf.values())
+    assert buf["posterior_mean_coef1"][0] == 1.0 and buf["posterior_mean_coef2"][0] == 0.0
+
+
+@pytest.mark.parametrize("name", list(GOLDEN_CASES))
+def test_denoiser_forward_matches_reference_golden(name):
+    g = load_golden(name)
+    c = golden_case(name)
+    out = denoiser_forward(c.oracle.W, c.t("x_T"), torch.from_numpy(g["denoiser_t"]),
+                           c.t("cond").transpose(1, 2), c.t("spk"))
+    assert out.shape == g["denoiser_out"].shape
+    assert rel_l2(out, g["denoiser_out"]) < TOL
+
+
+@pytest.mark.parametrize("name", list(GOLDEN_CASES))
+def test_p_sample_matches_reference_golden(name):
+    g = load_golden(name)
+    c = golden_case(name)
+    K = c.oracle.K
+    t = torch.full((c.B,), K - 1, dtype=torch.long)
+    out, _ = c.oracle.p_sample(c.t("x_T"), t, c.t("cond").transpose(1, 2), c.t("spk"), c.t("noises")[K - 1])
+    assert rel_l2(out, g["p_sample_out"]) < TOL
+
+
+@pytest.mark.parametrize("name", list(GOLDEN_CASES))
+def test_full_inference_matches_reference_golden(name):
+    g = load_golden(name)
+    c = golden_case(name)
+    final, states, x0s, start = c.oracle_forward()
+    assert final.shape == g["final_mel"].shape
+    assert rel_l2(final, g["final_mel"]) < TOL
+    if "state_after_first_step" in g.files:
+        assert rel_l2(states[1], g["state_after_first_step"]) < TOL
+    # padded frames are zeroed by the final mask (model/diffusion.py:200)
+    pad = c.t("pad_mask")
+    assert float(final[pad].abs().max()) == 0.0 if pad.any() else True

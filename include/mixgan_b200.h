@@ -1,0 +1,167 @@
+/*
+ * mixgan_b200.h — C ABI of the B200-native MixGAN-TTS diffusion-decoder reverse process.
+ *
+ * The reference (MaxMax2016/MixGAN-TTS) is pure Python and has no FFI layer; the
+ * boundary it exposes for this path is two torch modules.  Every entry point below
+ * names the reference method it replaces (paths relative to the reference root):
+ *
+ *   mgb_denoiser_forward   Denoiser.forward                      model/modules.py:420-446
+ *                          (ResidualBlock.forward                model/blocks.py:1157-1176,
+ *                           DiffusionEmbedding/Mish/LinearNorm   model/blocks.py:906-913,894-896,278-291)
+ *   mgb_reverse_step       GaussianDiffusion.p_sample            model/diffusion.py:121-129
+ *                          (+ q_posterior / q_posterior_sample   model/diffusion.py:104-119,
+ *                             extract                            model/diffusion.py:26-29)
+ *   mgb_sample             GaussianDiffusion.sampling + the tail of .forward (inference)
+ *                                                                model/diffusion.py:155-165,200
+ *   mgb_shallow_start      GaussianDiffusion.diffuse_fn * mask   model/diffusion.py:177-185,198-199
+ *   mgb_denorm_mask        GaussianDiffusion.denorm_spec * mask  model/diffusion.py:231-232,164,200
+ *   mgb_length_regulate    LengthRegulator.LR / expand / pad     model/linguistic_encoder.py:383-416,
+ *                          get_mask_from_lengths                 utils/tools.py:144-153,374-392
+ *
+ * Conventions
+ *   - Plain pointers and sizes only; no torch types.  All tensors are DEVICE pointers to
+ *     densely packed row-major arrays unless a parameter says "host".
+ *   - The caller owns every buffer (inputs, outputs, packed weights, workspace).  The library
+ *     never allocates or frees caller-visible memory and never synchronises the device; all work
+ *     is enqueued on `stream` (a cudaStream_t passed as void*).
+ *   - Return value: 0 = OK, negative = error (MGB_E_*); mgb_last_error() returns a thread-local
+ *     message.  Nothing throws across the ABI.
+ *   - There is no CPU fallback: on a device that is not sm_100 every compute entry point
+ *     returns MGB_E_ARCH.
+ *
+ * Tensor layouts (fp32 unless noted)
+ *   x_t, noise, x_prev, out : [B][n_mel][T]            (the reference's [B,1,M,T])
+ *   cond                    : [B][T][d_encoder]        (as it arrives at GaussianDiffusion.forward)
+ *   spk                     : [B][d_encoder] or NULL   (required when dims.multi_speaker)
+ *   t                       : int64 [B]
+ *   pad_mask                : uint8 [B][T], 1 = padding (reference convention at .forward) or NULL
+ *   mel / coarse            : [B][T][n_mel]
+ *   sched                   : float [3][K] = posterior_mean_coef1 | posterior_mean_coef2 |
+ *                             sigma, with sigma[t] = (t == 0) ? 0 : exp(0.5*posterior_log_variance_clipped[t])
+ */
+#ifndef MIXGAN_B200_H_
+#define MIXGAN_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MGB_ABI_VERSION 1
+
+enum {
+  MGB_OK = 0,
+  MGB_E_ARG = -1,       /* bad argument (NULL, shape, unsupported dims) */
+  MGB_E_ARCH = -2,      /* device is not sm_100 / library built without sm_100a code */
+  MGB_E_WORKSPACE = -3, /* workspace or packed buffer too small */
+  MGB_E_CUDA = -4,      /* a CUDA call failed; see mgb_last_error() */
+  MGB_E_UNSUPPORTED = -5
+};
+
+/* Arithmetic of the convolution GEMMs. */
+enum {
+  MGB_PREC_FP32 = 0, /* fp32 operands and accumulation on the CUDA cores (parity mode)           */
+  MGB_PREC_BF16 = 1  /* bf16 operands on tcgen05 tensor cores, fp32 accumulation in TMEM,
+                        fp32 residual stream, fp32 posterior update                             */
+};
+
+typedef struct mgb_model_dims {
+  int32_t n_mel;         /* 80  */
+  int32_t channels;      /* 256 residual channels */
+  int32_t d_encoder;     /* 256 conditioner width */
+  int32_t layers;        /* 20  */
+  int32_t multi_speaker; /* 0/1: per-block bias-free speaker projection present */
+} mgb_model_dims;
+
+int mgb_abi_version(void);
+const char* mgb_last_error(void);
+
+/* Instrumentation for bench.py.  mgb_launch_count: kernels this library has enqueued in this
+ * process so far.  mgb_profile_enable(1) makes the library bracket every launch of the path's
+ * dominant kernel with CUDA events on the launching stream; mgb_profile_collect synchronises
+ * those events, returns their summed duration and count, and clears them. */
+long long mgb_launch_count(void);
+void mgb_profile_enable(int on);
+int mgb_profile_collect(float* total_ms, int* count);
+
+/* 0 when `device` can run this library (compute capability 10.x), else MGB_E_ARCH. */
+int mgb_device_check(int device);
+
+/*
+ * Weights.  `flat` is ONE fp32 device array holding the Denoiser's parameters in state_dict
+ * layout ([out][in][k] conv weights, [out][in] linear weights) concatenated in this order:
+ *   input_projection.0.conv.{weight,bias}, mlp.0.linear.weight, mlp.2.linear.weight,
+ *   for each layer l: conv_layer.conv.{weight,bias}, diffusion_projection.linear.weight,
+ *                     [speaker_projection.linear.weight,] conditioner_projection.conv.{weight,bias},
+ *                     output_projection.conv.{weight,bias},
+ *   skip_projection.conv.{weight,bias}, output_projection.conv.{weight,bias}.
+ * mgb_pack_weights rewrites them once (per load_state_dict) into the kernels' layouts.
+ */
+size_t mgb_flat_weight_count(const mgb_model_dims* dims);
+size_t mgb_packed_bytes(const mgb_model_dims* dims, int precision);
+int mgb_pack_weights(const mgb_model_dims* dims, int precision, const float* flat,
+                     void* packed, size_t packed_bytes, void* stream);
+
+size_t mgb_workspace_bytes(const mgb_model_dims* dims, int precision, int B, int T, int K);
+
+/* Denoiser.forward: out = x0 prediction, [B][n_mel][T]. */
+int mgb_denoiser_forward(const mgb_model_dims* dims, int precision, const void* packed,
+                         const float* x, const int64_t* t, const float* cond, const float* spk,
+                         float* out, int B, int T, void* workspace, size_t workspace_bytes,
+                         void* stream);
+
+/* p_sample: x0 = Denoiser(x_t, t, cond, spk); clamp to [-1,1] if clip;
+ * x_prev = coef1[t]*x0 + coef2[t]*x_t + sigma[t]*noise.  x0_out may be NULL. */
+int mgb_reverse_step(const mgb_model_dims* dims, int precision, const void* packed,
+                     const float* x_t, const int64_t* t, const float* cond, const float* spk,
+                     const float* noise, const float* sched, int K, int clip,
+                     float* x_prev, float* x0_out, int B, int T,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
+/* sampling: K reverse steps from x_T with noises[K][B][n_mel][T] (noises[t] used at timestep t),
+ * then mel_out[B][T][n_mel] = denorm_spec(x_0) * (1 - pad_mask).
+ * states_out (optional): [K+1][B][T][n_mel] denormalised states, as sampling() returns them.
+ * x0_norm_out (optional): [B][n_mel][T], the last step's normalised x_0 (== state K before denorm). */
+int mgb_sample(const mgb_model_dims* dims, int precision, const void* packed,
+               const float* x_T, const float* cond, const float* spk, const float* noises,
+               const float* sched, int K, int clip, const float* spec_min, const float* spec_max,
+               const uint8_t* pad_mask, float* states_out, float* mel_out, float* x0_norm_out,
+               int B, int T, void* workspace, size_t workspace_bytes, void* stream);
+
+/* x_T[B][n_mel][T] = (sqrt_acp * norm_spec(coarse)^T + sqrt_1m_acp * noise) * (1 - pad_mask). */
+int mgb_shallow_start(const float* coarse, const float* noise, const float* spec_min,
+                      const float* spec_max, float sqrt_acp, float sqrt_1m_acp,
+                      const uint8_t* pad_mask, float* x_T, int B, int T, int n_mel, void* stream);
+
+/* mel[B][T][n_mel] = denorm_spec(x[B][n_mel][T]^T) * (1 - pad_mask). */
+int mgb_denorm_mask(const float* x, const float* spec_min, const float* spec_max,
+                    const uint8_t* pad_mask, float* mel, int B, int T, int n_mel, void* stream);
+
+/*
+ * LengthRegulator (integer indexing, bit-exact): x[B][S][D] fp32, dur int64 [B][S].
+ * out[B][max_len][D]: each source row s repeated max(dur[b][s],0) times, zero padded;
+ * mel_len[b] = sum_s max(dur[b][s],0) (int64); frames beyond max_len are an error in the
+ * reference (F.pad with a negative size truncates silently) — here they are truncated and the
+ * true length is still reported.  Requires scratch of B*(S+1) int64 in `workspace`.
+ */
+int mgb_length_regulate(const float* x, const int64_t* dur, float* out, int64_t* mel_len,
+                        int B, int S, int D, int max_len, void* workspace, size_t workspace_bytes,
+                        void* stream);
+
+/*
+ * tcgen05 descriptor probe (used by tests/test_umma_probe.py to pin the shared-memory
+ * descriptor conventions the bf16 path relies on).  Copies `a_bytes`/`b_bytes` raw bytes into
+ * shared memory, issues `ksteps` tcgen05.mma (M=128, N=n, K=16, bf16 -> fp32) with the given
+ * descriptor fields (all byte quantities, multiples of 16), and writes D[128][n] fp32.
+ */
+int mgb_probe_umma(const void* a_img, int a_bytes, const void* b_img, int b_bytes,
+                   int a_start, int a_lbo, int a_sbo, int a_kadv,
+                   int b_start, int b_lbo, int b_sbo, int b_kadv,
+                   int n, int ksteps, int use_bulk_copy, float* d_out, int* status_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MIXGAN_B200_H_ */

@@ -1,0 +1,9 @@
+"""B200-native reverse-diffusion decoder of MixGAN-TTS (drop-in ``Denoiser`` / ``GaussianDiffusion``).
+
+Only the hot path lives here: the sm_100a CUDA library (``csrc/`` -> ``libmixgan_b200.so``, C ABI in
+``include/mixgan_b200.h``) and the torch modules that mirror the reference's interface for it.
+"""
+from .modules import Denoiser  # noqa: F401
+from .diffusion import GaussianDiffusion  # noqa: F401
+
+__all__ = ["Denoiser", "GaussianDiffusion"]

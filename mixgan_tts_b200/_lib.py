@@ -1,0 +1,79 @@
+"""ctypes binding of ``libmixgan_b200.so`` (the C ABI declared in ``include/mixgan_b200.h``).
+
+The product path has no CPU fallback: if the shared library is missing, or a call
+returns a non-zero code, a ``RuntimeError`` / ``ValueError`` is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libmixgan_b200.so")
+
+PREC_FP32, PREC_BF16 = 0, 1
+E_ARG, E_ARCH, E_WORKSPACE, E_CUDA, E_UNSUPPORTED = -1, -2, -3, -4, -5
+
+
+class ModelDims(C.Structure):
+    _fields_ = [("n_mel", C.c_int32), ("channels", C.c_int32), ("d_encoder", C.c_int32),
+                ("layers", C.c_int32), ("multi_speaker", C.c_int32)]
+
+
+_P, _I, _Z, _F = C.c_void_p, C.c_int, C.c_size_t, C.c_float
+_D = C.POINTER(ModelDims)
+
+# name -> (restype, argtypes): every symbol include/mixgan_b200.h declares
+SIGNATURES = {
+    "mgb_abi_version": (_I, []),
+    "mgb_last_error": (C.c_char_p, []),
+    "mgb_launch_count": (C.c_longlong, []),
+    "mgb_profile_enable": (None, [_I]),
+    "mgb_profile_collect": (_I, [C.POINTER(C.c_float), C.POINTER(C.c_int)]),
+    "mgb_device_check": (_I, [_I]),
+    "mgb_flat_weight_count": (_Z, [_D]),
+    "mgb_packed_bytes": (_Z, [_D, _I]),
+    "mgb_pack_weights": (_I, [_D, _I, _P, _P, _Z, _P]),
+    "mgb_workspace_bytes": (_Z, [_D, _I, _I, _I, _I]),
+    "mgb_denoiser_forward": (_I, [_D, _I, _P, _P, _P, _P, _P, _P, _I, _I, _P, _Z, _P]),
+    "mgb_reverse_step": (_I, [_D, _I, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _I, _I, _P, _Z, _P]),
+    "mgb_sample": (_I, [_D, _I, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P, _I, _I, _P, _Z, _P]),
+    "mgb_shallow_start": (_I, [_P, _P, _P, _P, _F, _F, _P, _P, _I, _I, _I, _P]),
+    "mgb_denorm_mask": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P]),
+    "mgb_length_regulate": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _Z, _P]),
+    "mgb_probe_umma": (_I, [_P, _I, _P, _I] + [_I] * 11 + [_P, _P, _P]),
+}
+
+_lib = None
+
+
+def load():
+    """Load the shared library (once) and attach the prototypes."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `python -m mixgan_tts_b200.build` "
+            "(there is no CPU fallback for this path)")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype, fn.argtypes = res, args
+    if lib.mgb_abi_version() != 1:
+        raise RuntimeError("libmixgan_b200.so ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str):
+    if rc == 0:
+        return
+    msg = load().mgb_last_error().decode(errors="replace")
+    err = ValueError if rc in (E_ARG, E_WORKSPACE) else RuntimeError
+    raise err(f"{what} failed (code {rc}): {msg}")
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (or NULL for None)."""
+    return None if t is None else C.c_void_p(t.data_ptr())

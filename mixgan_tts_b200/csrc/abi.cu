@@ -1,0 +1,374 @@
+// extern "C" entry points of libmixgan_b200.so (see include/mixgan_b200.h) and the small
+// elementwise kernels either side of the Denoiser: shallow start, denorm + mask, length regulator.
+#include "common.cuh"
+
+#include <atomic>
+#include <mutex>
+#include <vector>
+
+namespace mgb {
+
+static thread_local char g_err[512] = "";
+
+static std::atomic<long long> g_launches{0};
+static std::atomic<int> g_prof_on{0};
+static std::mutex g_prof_mu;
+static std::vector<cudaEvent_t> g_prof_events;  // begin/end pairs
+
+void note_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+static void prof_record(cudaStream_t s) {
+  if (!g_prof_on.load(std::memory_order_relaxed)) return;
+  cudaEvent_t e;
+  if (cudaEventCreate(&e) != cudaSuccess) return;
+  cudaEventRecord(e, s);
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_prof_events.push_back(e);
+}
+void prof_begin(cudaStream_t s) { prof_record(s); }
+void prof_end(cudaStream_t s) { prof_record(s); }
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int check_arch() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) {
+    set_error("no CUDA device is current (this library has no CPU fallback)");
+    return MGB_E_ARCH;
+  }
+  int major = 0;
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  if (major != 10) {
+    set_error("device %d has compute capability %d.x; this library is built for sm_100a only", dev, major);
+    return MGB_E_ARCH;
+  }
+  return MGB_OK;
+}
+
+namespace {
+
+__global__ void fill_i64_kernel(int64_t* p, int n, int64_t v) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+// x_T[b][m][t] = (sa * norm(coarse[b][t][m]) + sn * noise[b][m][t]) * valid[b][t]
+// norm_spec: (x - min) / (max - min) * 2 - 1  (diffusion.py:228-229); q_sample diffusion.py:150-153
+__global__ void shallow_start_kernel(const float* __restrict__ coarse, const float* __restrict__ noise,
+                                     const float* __restrict__ smin, const float* __restrict__ smax,
+                                     float sa, float sn, const uint8_t* __restrict__ pad,
+                                     float* __restrict__ xT, int M, int T) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z, t0 = blockIdx.x * 32, m0 = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {  // read coarse rows t, coalesced over m
+    const int t = t0 + r, m = m0 + threadIdx.x;
+    float v = 0.f;
+    if (t < T && m < M) {
+      const float c = coarse[((size_t)b * T + t) * M + m];
+      v = __fsub_rn(__fmul_rn(__fdiv_rn(__fsub_rn(c, smin[m]), __fsub_rn(smax[m], smin[m])), 2.f), 1.f);
+    }
+    tile[r][threadIdx.x] = v;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {  // write rows m, coalesced over t
+    const int m = m0 + r, t = t0 + threadIdx.x;
+    if (t < T && m < M) {
+      const size_t o = ((size_t)b * M + m) * T + t;
+      const float q = __fadd_rn(__fmul_rn(sa, tile[threadIdx.x][r]), __fmul_rn(sn, noise[o]));
+      const float valid = (pad && pad[(size_t)b * T + t]) ? 0.f : 1.f;
+      xT[o] = q * valid;
+    }
+  }
+}
+
+// mel[b][t][m] = ((x[b][m][t] + 1) / 2 * (max - min) + min) * valid[b][t]   (diffusion.py:231-232)
+__global__ void denorm_mask_kernel(const float* __restrict__ x, const float* __restrict__ smin,
+                                   const float* __restrict__ smax, const uint8_t* __restrict__ pad,
+                                   float* __restrict__ mel, int M, int T) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z, t0 = blockIdx.x * 32, m0 = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int m = m0 + r, t = t0 + threadIdx.x;
+    tile[r][threadIdx.x] = (m < M && t < T) ? x[((size_t)b * M + m) * T + t] : 0.f;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int t = t0 + r, m = m0 + threadIdx.x;
+    if (t < T && m < M) {
+      const float v = tile[threadIdx.x][r];
+      const float dn = __fadd_rn(__fmul_rn(__fdiv_rn(__fadd_rn(v, 1.f), 2.f), __fsub_rn(smax[m], smin[m])), smin[m]);
+      const float valid = (pad && pad[(size_t)b * T + t]) ? 0.f : 1.f;
+      mel[((size_t)b * T + t) * M + m] = dn * valid;
+    }
+  }
+}
+
+// ---- LengthRegulator: exclusive scan of clamped durations, then a gather -----------------------
+__global__ void lr_scan_kernel(const int64_t* __restrict__ dur, int64_t* __restrict__ cum,
+                               int64_t* __restrict__ mel_len, int S) {
+  // one block per utterance; S is small (phonemes/words), a serial scan by thread 0 keeps the
+  // arithmetic identical to the reference's Python loop (linguistic_encoder.py:402-410)
+  const int b = blockIdx.x;
+  if (threadIdx.x == 0) {
+    int64_t acc = 0;
+    for (int s = 0; s < S; ++s) {
+      cum[(size_t)b * (S + 1) + s] = acc;
+      const int64_t dv = dur[(size_t)b * S + s];
+      acc += dv > 0 ? dv : 0;
+    }
+    cum[(size_t)b * (S + 1) + S] = acc;
+    mel_len[b] = acc;
+  }
+}
+
+__global__ void lr_gather_kernel(const float* __restrict__ x, const int64_t* __restrict__ cum,
+                                 float* __restrict__ out, int S, int D, int max_len) {
+  const int b = blockIdx.y, f = blockIdx.x;
+  const int64_t* cb = cum + (size_t)b * (S + 1);
+  // binary search: largest s with cum[s] <= f (and f < cum[s+1])
+  int src = -1;
+  if ((int64_t)f < cb[S]) {
+    int lo = 0, hi = S;  // invariant cb[lo] <= f < cb[hi]
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (cb[mid] <= (int64_t)f) lo = mid; else hi = mid;
+    }
+    src = lo;
+  }
+  float* o = out + ((size_t)b * max_len + f) * D;
+  const float* xi = src >= 0 ? x + ((size_t)b * S + src) * D : nullptr;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) o[d] = xi ? xi[d] : 0.f;
+}
+
+}  // namespace
+
+int launch_fill_t(int64_t* t, int B, int64_t value, cudaStream_t s) {
+  fill_i64_kernel<<<(B + 127) / 128, 128, 0, s>>>(t, B, value);
+  note_launch();
+  MGB_LAUNCH_CHECK();
+  return MGB_OK;
+}
+
+static int denoiser_dispatch(const mgb_model_dims* dims, int precision, const void* packed,
+                             const float* x, const int64_t* t, const float* cond, const float* spk,
+                             const float* noise, const float* sched, int K, int clip, float* x_prev,
+                             float* x0_out, int B, int T, void* ws, size_t ws_bytes, bool cond_ready,
+                             cudaStream_t s) {
+  MGB_REQUIRE(dims_supported(dims), MGB_E_ARG, "unsupported model dims");
+  MGB_REQUIRE(packed && x && t && cond && ws, MGB_E_ARG, "NULL pointer argument");
+  MGB_REQUIRE(B > 0 && T > 0, MGB_E_ARG, "B and T must be positive (got %d, %d)", B, T);
+  MGB_REQUIRE(!dims->multi_speaker || spk, MGB_E_ARG,
+              "multi_speaker model needs a speaker embedding (reference raises TypeError)");
+  if (int rc = check_arch()) return rc;
+  const size_t need = mgb_workspace_bytes(dims, precision, B, T, K > 0 ? K : 1);
+  MGB_REQUIRE(ws_bytes >= need, MGB_E_WORKSPACE, "workspace too small: %zu < %zu", ws_bytes, need);
+  if (precision == MGB_PREC_FP32)
+    return fp32_denoiser(*dims, packed, x, t, cond, spk, noise, sched, K, clip, x_prev, x0_out, B, T, ws, s);
+  if (precision == MGB_PREC_BF16)
+    return bf16_denoiser(*dims, packed, x, t, cond, spk, noise, sched, K, clip, x_prev, x0_out, B, T, ws,
+                         cond_ready, s);
+  set_error("unknown precision %d", precision);
+  return MGB_E_ARG;
+}
+
+}  // namespace mgb
+
+using namespace mgb;
+
+extern "C" {
+
+int mgb_abi_version(void) { return MGB_ABI_VERSION; }
+
+long long mgb_launch_count(void) { return g_launches.load(); }
+
+void mgb_profile_enable(int on) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  for (cudaEvent_t e : g_prof_events) cudaEventDestroy(e);
+  g_prof_events.clear();
+  g_prof_on.store(on ? 1 : 0);
+}
+
+int mgb_profile_collect(float* total_ms, int* count) {
+  MGB_REQUIRE(total_ms && count, MGB_E_ARG, "NULL pointer argument");
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  float total = 0.f;
+  int n = 0;
+  for (size_t i = 0; i + 1 < g_prof_events.size(); i += 2) {
+    MGB_CUDA_CHECK(cudaEventSynchronize(g_prof_events[i + 1]));
+    float ms = 0.f;
+    MGB_CUDA_CHECK(cudaEventElapsedTime(&ms, g_prof_events[i], g_prof_events[i + 1]));
+    total += ms;
+    ++n;
+  }
+  for (cudaEvent_t e : g_prof_events) cudaEventDestroy(e);
+  g_prof_events.clear();
+  *total_ms = total;
+  *count = n;
+  return MGB_OK;
+}
+const char* mgb_last_error(void) { return g_err; }
+
+int mgb_device_check(int device) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n) {
+    set_error("CUDA device %d not available (this library has no CPU fallback)", device);
+    return MGB_E_ARCH;
+  }
+  int major = 0;
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device);
+  if (major != 10) {
+    set_error("device %d has compute capability %d.x; need sm_100", device, major);
+    return MGB_E_ARCH;
+  }
+  return MGB_OK;
+}
+
+size_t mgb_flat_weight_count(const mgb_model_dims* dims) {
+  return dims_supported(dims) ? flat_offsets(*dims).total : 0;
+}
+
+size_t mgb_packed_bytes(const mgb_model_dims* dims, int precision) {
+  if (!dims_supported(dims)) return 0;
+  return precision == MGB_PREC_FP32 ? fp32_packed_bytes(*dims)
+       : precision == MGB_PREC_BF16 ? bf16_packed_bytes(*dims) : 0;
+}
+
+int mgb_pack_weights(const mgb_model_dims* dims, int precision, const float* flat, void* packed,
+                     size_t packed_bytes, void* stream) {
+  MGB_REQUIRE(dims_supported(dims), MGB_E_ARG, "unsupported model dims");
+  MGB_REQUIRE(flat && packed, MGB_E_ARG, "NULL pointer argument");
+  if (int rc = check_arch()) return rc;
+  const size_t need = mgb_packed_bytes(dims, precision);
+  MGB_REQUIRE(need > 0, MGB_E_ARG, "unknown precision %d", precision);
+  MGB_REQUIRE(packed_bytes >= need, MGB_E_WORKSPACE, "packed buffer too small: %zu < %zu", packed_bytes, need);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  return precision == MGB_PREC_FP32 ? fp32_pack(*dims, flat, packed, s) : bf16_pack(*dims, flat, packed, s);
+}
+
+size_t mgb_workspace_bytes(const mgb_model_dims* dims, int precision, int B, int T, int K) {
+  if (!dims_supported(dims) || B <= 0 || T <= 0) return 0;
+  const size_t tail = align_up((size_t)B * sizeof(int64_t), 256) +            // timestep vector
+                      2 * align_up((size_t)B * dims->n_mel * T * sizeof(float), 256);  // x ping-pong
+  const size_t core = precision == MGB_PREC_FP32 ? fp32_workspace_bytes(*dims, B, T)
+                    : precision == MGB_PREC_BF16 ? bf16_workspace_bytes(*dims, B, T, K > 0 ? K : 1) : 0;
+  return core ? align_up(core, 256) + tail : 0;
+}
+
+int mgb_denoiser_forward(const mgb_model_dims* dims, int precision, const void* packed, const float* x,
+                         const int64_t* t, const float* cond, const float* spk, float* out, int B, int T,
+                         void* workspace, size_t workspace_bytes, void* stream) {
+  MGB_REQUIRE(out, MGB_E_ARG, "NULL output");
+  return denoiser_dispatch(dims, precision, packed, x, t, cond, spk, nullptr, nullptr, 0, 0, nullptr, out,
+                           B, T, workspace, workspace_bytes, false, static_cast<cudaStream_t>(stream));
+}
+
+int mgb_reverse_step(const mgb_model_dims* dims, int precision, const void* packed, const float* x_t,
+                     const int64_t* t, const float* cond, const float* spk, const float* noise,
+                     const float* sched, int K, int clip, float* x_prev, float* x0_out, int B, int T,
+                     void* workspace, size_t workspace_bytes, void* stream) {
+  MGB_REQUIRE(noise && sched && x_prev && K > 0, MGB_E_ARG, "reverse_step needs noise, sched, x_prev and K > 0");
+  return denoiser_dispatch(dims, precision, packed, x_t, t, cond, spk, noise, sched, K, clip, x_prev, x0_out,
+                           B, T, workspace, workspace_bytes, false, static_cast<cudaStream_t>(stream));
+}
+
+int mgb_sample(const mgb_model_dims* dims, int precision, const void* packed, const float* x_T,
+               const float* cond, const float* spk, const float* noises, const float* sched, int K, int clip,
+               const float* spec_min, const float* spec_max, const uint8_t* pad_mask, float* states_out,
+               float* mel_out, float* x0_norm_out, int B, int T, void* workspace, size_t workspace_bytes,
+               void* stream) {
+  MGB_REQUIRE(dims_supported(dims), MGB_E_ARG, "unsupported model dims");
+  MGB_REQUIRE(x_T && noises && sched && spec_min && spec_max && mel_out && workspace && K > 0, MGB_E_ARG,
+              "NULL pointer argument or K <= 0");
+  MGB_REQUIRE(B > 0 && T > 0, MGB_E_ARG, "B and T must be positive (got %d, %d)", B, T);
+  const size_t need = mgb_workspace_bytes(dims, precision, B, T, K);
+  MGB_REQUIRE(need > 0 && workspace_bytes >= need, MGB_E_WORKSPACE, "workspace too small: %zu < %zu",
+              workspace_bytes, need);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int M = dims->n_mel;
+  const size_t xbytes = align_up((size_t)B * M * T * sizeof(float), 256);
+  const size_t tbytes = align_up((size_t)B * sizeof(int64_t), 256);
+  char* tail = static_cast<char*>(workspace) + (need - tbytes - 2 * xbytes);
+  int64_t* tvec = reinterpret_cast<int64_t*>(tail);
+  float* xa = reinterpret_cast<float*>(tail + tbytes);
+  float* xb = reinterpret_cast<float*>(tail + tbytes + xbytes);
+  const size_t mel_elems = (size_t)B * T * M;
+  dim3 tgrid((T + 31) / 32, (M + 31) / 32, B), tblock(32, 8);
+
+  if (states_out) {  // sampling() returns the start state too (diffusion.py:160,164)
+    denorm_mask_kernel<<<tgrid, tblock, 0, s>>>(x_T, spec_min, spec_max, nullptr, states_out, M, T);
+    note_launch();
+  }
+  const float* cur = x_T;
+  for (int i = K - 1, n = 0; i >= 0; --i, ++n) {
+    if (int rc = launch_fill_t(tvec, B, i, s)) return rc;
+    float* nxt = (n & 1) ? xb : xa;
+    const int rc = denoiser_dispatch(dims, precision, packed, cur, tvec, cond, spk,
+                                     noises + (size_t)i * B * M * T, sched, K, clip, nxt, nullptr, B, T,
+                                     workspace, workspace_bytes, n > 0, s);
+    if (rc) return rc;
+    cur = nxt;
+    if (states_out) {
+      denorm_mask_kernel<<<tgrid, tblock, 0, s>>>(cur, spec_min, spec_max, nullptr,
+                                                  states_out + (size_t)(n + 1) * mel_elems, M, T);
+      note_launch();
+    }
+  }
+  denorm_mask_kernel<<<tgrid, tblock, 0, s>>>(cur, spec_min, spec_max, pad_mask, mel_out, M, T);
+  note_launch();
+  if (x0_norm_out)
+    MGB_CUDA_CHECK(cudaMemcpyAsync(x0_norm_out, cur, (size_t)B * M * T * sizeof(float),
+                                   cudaMemcpyDeviceToDevice, s));
+  MGB_LAUNCH_CHECK();
+  return MGB_OK;
+}
+
+int mgb_shallow_start(const float* coarse, const float* noise, const float* spec_min, const float* spec_max,
+                      float sqrt_acp, float sqrt_1m_acp, const uint8_t* pad_mask, float* x_T, int B, int T,
+                      int n_mel, void* stream) {
+  MGB_REQUIRE(coarse && noise && spec_min && spec_max && x_T, MGB_E_ARG, "NULL pointer argument");
+  MGB_REQUIRE(B > 0 && T > 0 && n_mel > 0, MGB_E_ARG, "bad shape");
+  if (int rc = check_arch()) return rc;
+  dim3 grid((T + 31) / 32, (n_mel + 31) / 32, B), block(32, 8);
+  shallow_start_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(
+      coarse, noise, spec_min, spec_max, sqrt_acp, sqrt_1m_acp, pad_mask, x_T, n_mel, T);
+  note_launch();
+  MGB_LAUNCH_CHECK();
+  return MGB_OK;
+}
+
+int mgb_denorm_mask(const float* x, const float* spec_min, const float* spec_max, const uint8_t* pad_mask,
+                    float* mel, int B, int T, int n_mel, void* stream) {
+  MGB_REQUIRE(x && spec_min && spec_max && mel, MGB_E_ARG, "NULL pointer argument");
+  MGB_REQUIRE(B > 0 && T > 0 && n_mel > 0, MGB_E_ARG, "bad shape");
+  if (int rc = check_arch()) return rc;
+  dim3 grid((T + 31) / 32, (n_mel + 31) / 32, B), block(32, 8);
+  denorm_mask_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(x, spec_min, spec_max, pad_mask,
+                                                                             mel, n_mel, T);
+  note_launch();
+  MGB_LAUNCH_CHECK();
+  return MGB_OK;
+}
+
+int mgb_length_regulate(const float* x, const int64_t* dur, float* out, int64_t* mel_len, int B, int S, int D,
+                        int max_len, void* workspace, size_t workspace_bytes, void* stream) {
+  MGB_REQUIRE(x && dur && out && mel_len && workspace, MGB_E_ARG, "NULL pointer argument");
+  MGB_REQUIRE(B > 0 && S > 0 && D > 0 && max_len > 0, MGB_E_ARG, "bad shape");
+  MGB_REQUIRE(workspace_bytes >= (size_t)B * (S + 1) * sizeof(int64_t), MGB_E_WORKSPACE,
+              "workspace too small for the duration scan");
+  if (int rc = check_arch()) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  int64_t* cum = static_cast<int64_t*>(workspace);
+  lr_scan_kernel<<<B, 32, 0, s>>>(dur, cum, mel_len, S);
+  dim3 grid(max_len, B);
+  lr_gather_kernel<<<grid, 64, 0, s>>>(x, cum, out, S, D, max_len);
+  note_launch(2);
+  MGB_LAUNCH_CHECK();
+  return MGB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,123 @@
+// Shared host-side helpers: error reporting, canonical flat-weight offsets, packed layouts.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/mixgan_b200.h"
+
+namespace mgb {
+
+void set_error(const char* fmt, ...);
+
+#define MGB_CUDA_CHECK(expr)                                                        \
+  do {                                                                              \
+    cudaError_t _e = (expr);                                                        \
+    if (_e != cudaSuccess) {                                                        \
+      mgb::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),        \
+                     __FILE__, __LINE__);                                           \
+      return MGB_E_CUDA;                                                            \
+    }                                                                               \
+  } while (0)
+
+#define MGB_LAUNCH_CHECK()                                                          \
+  do {                                                                              \
+    cudaError_t _e = cudaGetLastError();                                            \
+    if (_e != cudaSuccess) {                                                        \
+      mgb::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e),    \
+                     __FILE__, __LINE__);                                           \
+      return MGB_E_CUDA;                                                            \
+    }                                                                               \
+  } while (0)
+
+#define MGB_REQUIRE(cond, code, ...)                                                \
+  do {                                                                              \
+    if (!(cond)) {                                                                  \
+      mgb::set_error(__VA_ARGS__);                                                  \
+      return (code);                                                                \
+    }                                                                               \
+  } while (0)
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// ---- canonical flat fp32 weight order (include/mixgan_b200.h) -----------------------------
+struct FlatLayer {
+  size_t conv_w, conv_b, dproj_w, sproj_w, cproj_w, cproj_b, oproj_w, oproj_b;
+};
+struct FlatOffsets {
+  size_t in_w, in_b, mlp0_w, mlp2_w;
+  size_t layer0;        // start of layer 0
+  size_t layer_stride;  // floats per layer
+  FlatLayer rel;        // offsets relative to a layer's start
+  size_t skip_w, skip_b, out_w, out_b;
+  size_t total;
+};
+
+inline FlatOffsets flat_offsets(const mgb_model_dims& d) {
+  const size_t C = d.channels, H = d.d_encoder, M = d.n_mel, L = d.layers;
+  FlatOffsets o{};
+  size_t p = 0;
+  o.in_w = p; p += C * M;
+  o.in_b = p; p += C;
+  o.mlp0_w = p; p += 4 * C * C;
+  o.mlp2_w = p; p += C * 4 * C;
+  o.layer0 = p;
+  size_t q = 0;
+  o.rel.conv_w = q; q += 2 * C * C * 3;
+  o.rel.conv_b = q; q += 2 * C;
+  o.rel.dproj_w = q; q += C * C;
+  o.rel.sproj_w = q; if (d.multi_speaker) q += C * H;
+  o.rel.cproj_w = q; q += C * H;
+  o.rel.cproj_b = q; q += C;
+  o.rel.oproj_w = q; q += 2 * C * C;
+  o.rel.oproj_b = q; q += 2 * C;
+  o.layer_stride = q;
+  p += q * L;
+  o.skip_w = p; p += C * C;
+  o.skip_b = p; p += C;
+  o.out_w = p; p += M * C;
+  o.out_b = p; p += M;
+  o.total = p;
+  return o;
+}
+
+inline bool dims_supported(const mgb_model_dims* d) {
+  return d && d->n_mel > 0 && d->n_mel <= 128 && d->n_mel % 8 == 0 && d->channels == 256 &&
+         d->d_encoder == 256 && d->layers >= 1 && d->layers <= 64 &&
+         (d->multi_speaker == 0 || d->multi_speaker == 1);
+}
+
+int check_arch();  // MGB_OK or MGB_E_ARCH for the current device
+
+// Launch accounting (bench.py's gpu_launches) and optional CUDA-event timing of the dominant
+// kernel on the launching stream (bench.py's roofline.achieved).  See mgb_launch_count / mgb_profile_*.
+void note_launch(int n = 1);
+void prof_begin(cudaStream_t s);  // no-ops unless profiling is enabled
+void prof_end(cudaStream_t s);
+
+// ---- fp32 path (fp32_path.cu) ---------------------------------------------------------------
+size_t fp32_packed_bytes(const mgb_model_dims& d);
+int fp32_pack(const mgb_model_dims& d, const float* flat, void* packed, cudaStream_t s);
+size_t fp32_workspace_bytes(const mgb_model_dims& d, int B, int T);
+// One Denoiser call.  If sched != nullptr the posterior update is fused (writes x_prev); out_x0
+// receives the (optionally clamped) x0 when non-null.
+int fp32_denoiser(const mgb_model_dims& d, const void* packed, const float* x, const int64_t* t,
+                  const float* cond, const float* spk, const float* noise, const float* sched, int K,
+                  int clip, float* x_prev, float* out_x0, int B, int T, void* ws, cudaStream_t s);
+
+// ---- bf16 tcgen05 path (fused_bf16.cu) -------------------------------------------------------
+size_t bf16_packed_bytes(const mgb_model_dims& d);
+int bf16_pack(const mgb_model_dims& d, const float* flat, void* packed, cudaStream_t s);
+size_t bf16_workspace_bytes(const mgb_model_dims& d, int B, int T, int K);
+int bf16_denoiser(const mgb_model_dims& d, const void* packed, const float* x, const int64_t* t,
+                  const float* cond, const float* spk, const float* noise, const float* sched, int K,
+                  int clip, float* x_prev, float* out_x0, int B, int T, void* ws, bool cond_ready,
+                  cudaStream_t s);
+
+// ---- elementwise (elementwise.cu) -------------------------------------------------------------
+int launch_fill_t(int64_t* t, int B, int64_t value, cudaStream_t s);
+
+}  // namespace mgb

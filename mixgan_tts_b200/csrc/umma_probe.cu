@@ -1,0 +1,121 @@
+// tcgen05 descriptor probe: one CTA, raw operand images copied into shared memory, `ksteps`
+// tcgen05.mma (M=128, N=n, K=16, bf16 -> fp32 in TMEM), result read back with tcgen05.ld.
+// tests/test_umma_probe.py uses it to pin the shared-memory descriptor conventions of tc05.cuh
+// (LBO/SBO meaning, +16 B row shift of the start address, K advance) against a host matmul.
+#include "common.cuh"
+#include "tc05.cuh"
+
+namespace mgb {
+namespace {
+
+constexpr long long kProbeTimeout = 200000000LL;  // ~0.1 s of SM cycles
+
+struct ProbeArgs {
+  const uint8_t* a_img; const uint8_t* b_img;
+  int a_bytes, b_bytes, b_off;
+  int a_start, a_lbo, a_sbo, a_kadv;
+  int b_start, b_lbo, b_sbo, b_kadv;
+  int n, ksteps, use_bulk;
+  float* d_out; int* status;
+};
+
+__global__ void __launch_bounds__(128, 1) umma_probe_kernel(const ProbeArgs p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bar_load, bar_mma;
+  __shared__ uint32_t tmem_slot;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  int status = 0;
+
+  if (warp == 0) tc::tmem_alloc<256>(&tmem_slot);
+  if (tid == 32) {
+    tc::mbar_init(&bar_load, 1);
+    tc::mbar_init(&bar_mma, 1);
+    tc::fence_barrier_init();
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+
+  if (p.use_bulk) {
+    if (tid == 0) {
+      tc::mbar_arrive_expect_tx(&bar_load, (uint32_t)(p.a_bytes + p.b_bytes));
+      tc::bulk_g2s(smem, p.a_img, (uint32_t)p.a_bytes, &bar_load);
+      tc::bulk_g2s(smem + p.b_off, p.b_img, (uint32_t)p.b_bytes, &bar_load);
+    }
+    if (!tc::mbar_wait(&bar_load, 0, kProbeTimeout)) status = 1;
+  } else {
+    const uint4* ga = reinterpret_cast<const uint4*>(p.a_img);
+    const uint4* gb = reinterpret_cast<const uint4*>(p.b_img);
+    uint4* sa = reinterpret_cast<uint4*>(smem);
+    uint4* sb = reinterpret_cast<uint4*>(smem + p.b_off);
+    for (int i = tid; i < p.a_bytes / 16; i += blockDim.x) sa[i] = ga[i];
+    for (int i = tid; i < p.b_bytes / 16; i += blockDim.x) sb[i] = gb[i];
+    tc::fence_proxy_async_smem();
+  }
+  __syncthreads();
+
+  if (warp == 0 && status == 0) {
+    tc::tc_fence_after();
+    if (tc::elect_one()) {
+      const uint32_t idesc = tc::make_idesc_bf16(128, p.n);
+      const uint32_t a0 = tc::smem_u32(smem) + p.a_start;
+      const uint32_t b0 = tc::smem_u32(smem + p.b_off) + p.b_start;
+      for (int k = 0; k < p.ksteps; ++k) {
+        const uint64_t ad = tc::make_smem_desc(a0 + k * p.a_kadv, p.a_lbo, p.a_sbo);
+        const uint64_t bd = tc::make_smem_desc(b0 + k * p.b_kadv, p.b_lbo, p.b_sbo);
+        tc::umma_bf16(tmem, ad, bd, idesc, k > 0 ? 1u : 0u);
+      }
+      tc::umma_commit(&bar_mma);
+    }
+    __syncwarp();
+  }
+  if (!tc::mbar_wait(&bar_mma, 0, kProbeTimeout)) status |= 2;
+  tc::tc_fence_after();
+
+  if (status == 0) {
+    const int row = warp * 32 + lane;
+    for (int c0 = 0; c0 < p.n; c0 += 32) {
+      uint32_t r[32];
+      tc::tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, r);
+      tc::tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (c0 + j < p.n) p.d_out[(size_t)row * p.n + c0 + j] = __uint_as_float(r[j]);
+    }
+  }
+  if (status) atomicOr(p.status, status);
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc<256>(tmem);
+}
+
+}  // namespace
+}  // namespace mgb
+
+using namespace mgb;
+
+extern "C" int mgb_probe_umma(const void* a_img, int a_bytes, const void* b_img, int b_bytes, int a_start,
+                              int a_lbo, int a_sbo, int a_kadv, int b_start, int b_lbo, int b_sbo, int b_kadv,
+                              int n, int ksteps, int use_bulk_copy, float* d_out, int* status_out, void* stream) {
+  MGB_REQUIRE(a_img && b_img && d_out && status_out, MGB_E_ARG, "NULL pointer argument");
+  MGB_REQUIRE(a_bytes > 0 && b_bytes > 0 && a_bytes % 16 == 0 && b_bytes % 16 == 0, MGB_E_ARG,
+              "operand images must be positive multiples of 16 bytes");
+  MGB_REQUIRE(n >= 16 && n <= 256 && n % 16 == 0 && ksteps >= 1 && ksteps <= 64, MGB_E_ARG, "bad n/ksteps");
+  MGB_REQUIRE(((a_start | a_lbo | a_sbo | a_kadv | b_start | b_lbo | b_sbo | b_kadv) & 15) == 0, MGB_E_ARG,
+              "descriptor byte fields must be multiples of 16");
+  if (int rc = check_arch()) return rc;
+  ProbeArgs p{};
+  p.a_img = static_cast<const uint8_t*>(a_img); p.b_img = static_cast<const uint8_t*>(b_img);
+  p.a_bytes = a_bytes; p.b_bytes = b_bytes; p.b_off = (int)align_up((size_t)a_bytes, 1024);
+  p.a_start = a_start; p.a_lbo = a_lbo; p.a_sbo = a_sbo; p.a_kadv = a_kadv;
+  p.b_start = b_start; p.b_lbo = b_lbo; p.b_sbo = b_sbo; p.b_kadv = b_kadv;
+  p.n = n; p.ksteps = ksteps; p.use_bulk = use_bulk_copy; p.d_out = d_out; p.status = status_out;
+  const size_t smem = (size_t)p.b_off + align_up((size_t)b_bytes, 1024);
+  MGB_REQUIRE(smem <= 200 * 1024, MGB_E_ARG, "operand images too large for shared memory");
+  MGB_CUDA_CHECK(cudaFuncSetAttribute(umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  umma_probe_kernel<<<1, 128, smem, static_cast<cudaStream_t>(stream)>>>(p);
+  MGB_LAUNCH_CHECK();
+  return MGB_OK;
+}

@@ -1,0 +1,262 @@
+"""Drop-in ``GaussianDiffusion`` (reference: ``model/diffusion.py:38-235``) whose reverse process
+runs in the sm_100a library.
+
+Same constructor, attributes (``denoise_fn``, ``num_timesteps``, ``mel_bins``, ``cond``, ``spk_emb``),
+buffers/``state_dict`` keys and method signatures as the reference.  Every method that draws
+noise additionally accepts the noise as a keyword argument (a superset of the reference API) so
+that parity tests and the bench can inject identical noise; when it is omitted, noise is drawn
+with ``torch.randn`` on the device, as the reference does.
+
+Hot methods (``p_sample``, ``sampling``, inference ``forward``) call the C ABI; the light
+training-time helpers (``q_sample``, ``q_posterior``, ``norm_spec`` ...) are plain torch on the
+registered buffers.  The training branch of ``forward`` is not built yet and raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import torch
+from torch import nn
+
+from . import _lib
+from .modules import PRECISIONS, Denoiser
+from .schedule import noise_schedule_list, posterior_buffers
+
+
+def _extract(a, t, x_shape):
+    b = t.shape[0]
+    return a.gather(-1, t).reshape(b, *((1,) * (len(x_shape) - 1)))
+
+
+class GaussianDiffusion(nn.Module):
+    def __init__(self, args, preprocess_config, model_config, train_config, precision: str | None = None):
+        super().__init__()
+        self.model = args.model
+        self.denoise_fn = Denoiser(preprocess_config, model_config, precision=precision)
+        self.mel_bins = preprocess_config["preprocessing"]["mel"]["n_mel_channels"]
+        den = model_config["denoiser"]
+        betas = noise_schedule_list(
+            schedule_mode=den["noise_schedule_naive"],
+            timesteps=den["timesteps" if self.model == "naive" else "shallow_timesteps"],
+            min_beta=den["min_beta"], max_beta=den["max_beta"], s=den["s"])
+        self.num_timesteps = int(betas.shape[0])
+        self.loss_type = train_config["loss"]["noise_loss"]
+        for name, val in posterior_buffers(betas).items():
+            self.register_buffer(name, torch.tensor(val, dtype=torch.float32))
+        with open(os.path.join(preprocess_config["path"]["preprocessed_path"], "stats.json")) as f:
+            stats = json.load(f)
+        keep = den["keep_bins"]
+        self.register_buffer("spec_min", torch.FloatTensor(stats["spec_min"])[None, None, :keep])
+        self.register_buffer("spec_max", torch.FloatTensor(stats["spec_max"])[None, None, :keep])
+        self.cond = None
+        self.spk_emb = None
+        self._sched_cache = None
+
+    # ------------------------------------------------------------------ light helpers (torch)
+    def q_mean_variance(self, x_start, t):
+        mean = _extract(self.sqrt_alphas_cumprod, t, x_start.shape) * x_start
+        variance = _extract(1. - self.alphas_cumprod, t, x_start.shape)
+        log_variance = _extract(self.log_one_minus_alphas_cumprod, t, x_start.shape)
+        return mean, variance, log_variance
+
+    def predict_start_from_noise(self, x_t, t, noise):
+        return (_extract(self.sqrt_recip_alphas_cumprod, t, x_t.shape) * x_t
+                - _extract(self.sqrt_recipm1_alphas_cumprod, t, x_t.shape) * noise)
+
+    def q_posterior(self, x_start, x_t, t):
+        mean = (_extract(self.posterior_mean_coef1, t, x_t.shape) * x_start
+                + _extract(self.posterior_mean_coef2, t, x_t.shape) * x_t)
+        return (mean, _extract(self.posterior_variance, t, x_t.shape),
+                _extract(self.posterior_log_variance_clipped, t, x_t.shape))
+
+    def q_posterior_sample(self, x_start, x_t, t, repeat_noise=False, noise=None):
+        b = x_start.shape[0]
+        mean, _, logvar = self.q_posterior(x_start=x_start, x_t=x_t, t=t)
+        if noise is None:
+            noise = (torch.randn((1, *x_start.shape[1:]), device=x_start.device).repeat(b, 1, 1, 1)
+                     if repeat_noise else torch.randn(x_start.shape, device=x_start.device))
+        nonzero = (1 - (t == 0).float()).reshape(b, *((1,) * (len(x_start.shape) - 1)))
+        return mean + nonzero * (0.5 * logvar).exp() * noise
+
+    def q_sample(self, x_start, t, noise=None):
+        if noise is None:
+            noise = torch.randn_like(x_start)
+        return (_extract(self.sqrt_alphas_cumprod, t, x_start.shape) * x_start
+                + _extract(self.sqrt_one_minus_alphas_cumprod, t, x_start.shape) * noise)
+
+    def diffuse_fn(self, x_start, t, noise=None):
+        x_start = self.norm_spec(x_start).transpose(1, 2)[:, None, :, :]   # [B,1,M,T]
+        neg = t < 0
+        t[neg] = 0                                                         # in place, as the reference
+        out = self.q_sample(x_start=x_start, t=t, noise=noise)
+        out[neg] = x_start[neg]
+        return out
+
+    def diffuse_trace(self, x_start, mask):
+        b, device = x_start.shape[0], x_start.device
+        trace = [self.norm_spec(x_start).clamp_(-1., 1.) * ~mask.unsqueeze(-1)]
+        for t in range(self.num_timesteps):
+            tt = torch.full((b,), t, device=device, dtype=torch.long)
+            trace.append(self.diffuse_fn(x_start, tt)[:, 0].transpose(1, 2) * ~mask.unsqueeze(-1))
+        return trace
+
+    def norm_spec(self, x):
+        return (x - self.spec_min) / (self.spec_max - self.spec_min) * 2 - 1
+
+    def denorm_spec(self, x):
+        return (x + 1) / 2 * (self.spec_max - self.spec_min) + self.spec_min
+
+    def out2mel(self, x):
+        return x
+
+    # ------------------------------------------------------------------ C-ABI plumbing
+    def _sched(self, device) -> torch.Tensor:
+        """float [3][K]: coef1 | coef2 | sigma (sigma[t] = [t != 0] * exp(0.5 * logvar[t]))."""
+        key = (device, self.posterior_mean_coef1._version, self.posterior_mean_coef1.data_ptr())
+        if self._sched_cache is None or self._sched_cache[0] != key:
+            c1 = self.posterior_mean_coef1.detach().float().cpu()
+            c2 = self.posterior_mean_coef2.detach().float().cpu()
+            sig = (0.5 * self.posterior_log_variance_clipped.detach().float().cpu()).exp()
+            sig[0] = 0.0
+            host = (self.sqrt_alphas_cumprod.detach().float().cpu().tolist(),
+                    self.sqrt_one_minus_alphas_cumprod.detach().float().cpu().tolist())
+            self._sched_cache = (key, torch.stack([c1, c2, sig]).contiguous().to(device), host)
+        return self._sched_cache[1]
+
+    def _call_ctx(self, ref):
+        if ref.device.type != "cuda":
+            raise RuntimeError("mixgan_tts_b200.GaussianDiffusion needs CUDA tensors (no CPU fallback)")
+        den = self.denoise_fn
+        return _lib.load(), den, PRECISIONS[den.precision], C.c_void_p(torch.cuda.current_stream(ref.device).cuda_stream)
+
+    @staticmethod
+    def _f32c(t):
+        return None if t is None else t.detach().float().contiguous()
+
+    def _spk(self, spk_emb):
+        if self.denoise_fn.dims.multi_speaker:
+            if spk_emb is None:
+                raise TypeError("multi_speaker Denoiser needs spk_emb")
+            return self._f32c(spk_emb)
+        return None
+
+    # ------------------------------------------------------------------ hot path
+    @torch.no_grad()
+    def p_sample(self, x_t, t, cond, spk_emb, clip_denoised=True, repeat_noise=False, noise=None,
+                 return_x0=False):
+        """One reverse step (diffusion.py:121-129).  ``cond`` is ``[B,H,T]`` as in the reference."""
+        lib, den, prec, stream = self._call_ctx(x_t)
+        B, _, M, T = x_t.shape
+        with torch.cuda.device(x_t.device):
+            if noise is None:
+                noise = (torch.randn((1, 1, M, T), device=x_t.device).repeat(B, 1, 1, 1) if repeat_noise
+                         else torch.randn(x_t.shape, device=x_t.device))
+            x = self._f32c(x_t)
+            cond_bth = self._f32c(cond.transpose(1, 2))
+            spk = self._spk(spk_emb)
+            tt = t.detach().to(torch.int64).contiguous()
+            nz = self._f32c(noise)
+            out = torch.empty_like(x)
+            x0 = torch.empty_like(x) if return_x0 else None
+            ws = den.workspace(B, T, self.num_timesteps, x.device)
+            _lib.check(lib.mgb_reverse_step(
+                C.byref(den.dims), prec, _lib.ptr(den.packed_weights()), _lib.ptr(x), _lib.ptr(tt),
+                _lib.ptr(cond_bth), _lib.ptr(spk), _lib.ptr(nz), _lib.ptr(self._sched(x.device)),
+                self.num_timesteps, int(bool(clip_denoised)), _lib.ptr(out), _lib.ptr(x0), B, T,
+                _lib.ptr(ws), ws.numel(), stream), "mgb_reverse_step")
+        return (out, x0) if return_x0 else out
+
+    def _sample_core(self, cond_bth, spk, x_T, noises, pad_mask, want_states, clip=True):
+        """Runs K reverse steps + denorm(+mask) in the library.  All tensors fp32 contiguous on one
+        CUDA device: ``cond_bth [B,T,H]``, ``x_T [B,1,M,T]``, ``noises [K,B,1,M,T]``,
+        ``pad_mask`` uint8 ``[B,T]`` (1 = padding) or None."""
+        lib, den, prec, stream = self._call_ctx(x_T)
+        B, _, M, T = x_T.shape
+        K = self.num_timesteps
+        dev = x_T.device
+        mel = torch.empty((B, T, M), dtype=torch.float32, device=dev)
+        states = torch.empty((K + 1, B, T, M), dtype=torch.float32, device=dev) if want_states else None
+        ws = den.workspace(B, T, K, dev)
+        smin = self.spec_min.detach().float().reshape(-1).contiguous()
+        smax = self.spec_max.detach().float().reshape(-1).contiguous()
+        _lib.check(lib.mgb_sample(
+            C.byref(den.dims), prec, _lib.ptr(den.packed_weights()), _lib.ptr(x_T), _lib.ptr(cond_bth),
+            _lib.ptr(spk), _lib.ptr(noises), _lib.ptr(self._sched(dev)), K, int(bool(clip)), _lib.ptr(smin),
+            _lib.ptr(smax), _lib.ptr(pad_mask), _lib.ptr(states), _lib.ptr(mel), None, B, T,
+            _lib.ptr(ws), ws.numel(), stream), "mgb_sample")
+        return mel, states
+
+    def _draw(self, B, T, dev, x_T, noises):
+        M, K = self.mel_bins, self.num_timesteps
+        if x_T is None:
+            x_T = torch.randn((B, 1, M, T), device=dev)
+        if noises is None:
+            noises = torch.randn((K, B, 1, M, T), device=dev)   # the reference draws one per step too
+        if tuple(noises.shape) != (K, B, 1, M, T):
+            raise ValueError(f"noises must be [K,B,1,M,T] = {(K, B, 1, M, T)}, got {tuple(noises.shape)}")
+        return self._f32c(x_T), self._f32c(noises)
+
+    @torch.no_grad()
+    def sampling(self, noise=None, noises=None):
+        """diffusion.py:155-165: returns the K+1 denormalised ``[B,T,M]`` states (start first).
+        ``noise`` is the start state x_T (reference name); ``noises[t]`` the per-step draws."""
+        cond = self.cond                                   # [B,H,T], stashed by forward()
+        B, _, T = cond.shape
+        dev = cond.device
+        with torch.cuda.device(dev):
+            x_T, noises = self._draw(B, T, dev, noise, noises)
+            _, states = self._sample_core(self._f32c(cond.transpose(1, 2)), self._spk(self.spk_emb), x_T, noises,
+                                          None, want_states=True)
+        return list(states.unbind(0))
+
+    @torch.no_grad()
+    def interpolate(self, x1, x2, t, cond, spk_emb, lam=0.5):
+        b, device = x1.shape[0], x1.device
+        t = self.num_timesteps - 1 if t is None else t
+        assert x1.shape == x2.shape
+        tb = torch.full((b,), t, device=device, dtype=torch.long)
+        x = (1 - lam) * self.q_sample(x1, t=tb) + lam * self.q_sample(x2, t=tb)
+        for i in reversed(range(0, t)):
+            x = self.p_sample(x, torch.full((b,), i, device=device, dtype=torch.long), cond, spk_emb)
+        return self.denorm_spec(x[:, 0].transpose(1, 2))
+
+    def forward(self, mel, cond, spk_emb, mel_mask, coarse_mel=None, clip_denoised=True, *,
+                x_T=None, noises=None, start_noise=None):
+        """diffusion.py:187-226.  ``cond [B,T,H]``; ``mel_mask [B,T]`` True = padding.
+        Inference (``mel is None``) returns ``(x_0_pred [B,T,M], None, None, None, t)``."""
+        b, device = cond.shape[0], cond.device
+        t = None
+        self.cond = cond.transpose(1, 2).detach()
+        self.spk_emb = spk_emb.detach() if spk_emb is not None else None
+        if mel is not None:
+            raise NotImplementedError("training branch (mel given) is not built in the B200 path yet")
+        if device.type != "cuda":
+            raise RuntimeError("mixgan_tts_b200.GaussianDiffusion needs CUDA tensors (no CPU fallback)")
+        T = cond.shape[1]
+        with torch.no_grad(), torch.cuda.device(device):
+            lib, den, prec, stream = self._call_ctx(cond)
+            pad = mel_mask.detach().to(torch.uint8).contiguous()
+            cond_bth = self._f32c(cond)
+            spk = self._spk(spk_emb)
+            if self.model == "shallow":   # x_T is produced by the shallow start, never drawn
+                x_T = torch.empty((b, 1, self.mel_bins, T), dtype=torch.float32, device=device)
+            x_T, noises = self._draw(b, T, device, x_T, noises)
+            if self.model == "shallow":
+                t = torch.full((b,), self.num_timesteps - 1, device=device, dtype=torch.long)
+                if start_noise is None:
+                    start_noise = torch.randn((b, 1, self.mel_bins, T), device=device)
+                k = self.num_timesteps - 1
+                self._sched(device)
+                sa, sn = self._sched_cache[2][0][k], self._sched_cache[2][1][k]
+                _lib.check(lib.mgb_shallow_start(
+                    _lib.ptr(self._f32c(coarse_mel)), _lib.ptr(self._f32c(start_noise)),
+                    _lib.ptr(self.spec_min.detach().float().reshape(-1).contiguous()),
+                    _lib.ptr(self.spec_max.detach().float().reshape(-1).contiguous()),
+                    sa, sn,
+                    _lib.ptr(pad), _lib.ptr(x_T), b, T, self.mel_bins, stream), "mgb_shallow_start")
+            x_0_pred, _ = self._sample_core(cond_bth, spk, x_T, noises, pad, want_states=False,
+                                            clip=clip_denoised)
+        return x_0_pred, None, None, None, t

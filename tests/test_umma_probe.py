@@ -1,0 +1,82 @@
+"""Pin the tcgen05 shared-memory descriptor conventions the bf16 path relies on (csrc/tc05.cuh):
+K-major / no-swizzle core-matrix layout, LBO = K-direction stride, SBO = 8-row-group stride,
+a +16 B start address = one-row shift (the k=3 convolution taps), K advance by descriptor."""
+import ctypes as C
+import os
+
+import pytest
+import torch
+
+from mixgan_tts_b200 import _lib
+
+pytestmark = pytest.mark.gpu
+
+
+def _image(mat: torch.Tensor) -> torch.Tensor:
+    """[rows, K] bf16 -> bytes of the [K/8][rows][8] core-matrix image."""
+    rows, K = mat.shape
+    return mat.reshape(rows, K // 8, 8).permute(1, 0, 2).contiguous()
+
+
+def run_probe(A, Bm, *, n, ksteps, shift=0, swap=False, bulk=True, a_rows=None):
+    """A [rows,K] bf16 (rows >= 128+shift), Bm [n,K] bf16.  Returns D [128,n] fp32 and status."""
+    lib = _lib.load()
+    dev = A.device
+    rows = A.shape[0]
+    a_img, b_img = _image(A), _image(Bm)
+    a_lbo, a_sbo = rows * 16, 128
+    b_lbo, b_sbo = n * 16, 128
+    if swap:
+        a_lbo, a_sbo, b_lbo, b_sbo = a_sbo, a_lbo, b_sbo, b_lbo
+    D = torch.full((128, n), float("nan"), device=dev)
+    st = torch.zeros(1, dtype=torch.int32, device=dev)
+    rc = lib.mgb_probe_umma(
+        _lib.ptr(a_img), a_img.numel() * 2, _lib.ptr(b_img), b_img.numel() * 2,
+        shift * 16, a_lbo, a_sbo, 2 * rows * 16,
+        0, b_lbo, b_sbo, 2 * n * 16,
+        n, ksteps, int(bulk), _lib.ptr(D), _lib.ptr(st),
+        C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    _lib.check(rc, "mgb_probe_umma")
+    torch.cuda.synchronize()
+    return D, int(st.item())
+
+
+def _mats(rows, n, K, seed=0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    A = (torch.randn(rows, K, generator=g) * 0.5).bfloat16().cuda()
+    Bm = (torch.randn(n, K, generator=g) * 0.5).bfloat16().cuda()
+    return A, Bm
+
+
+def _expect(A, Bm, shift):
+    return A[shift:shift + 128].float() @ Bm.float().t()
+
+
+def _report(line):
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open("gpurun_out/umma_probe.txt", "a") as f:
+        f.write(line + "\n")
+    print(line)
+
+
+@pytest.mark.parametrize("bulk", [True, False])
+@pytest.mark.parametrize("n,ksteps", [(128, 1), (128, 4), (256, 4), (64, 2)])
+def test_descriptor_convention(n, ksteps, bulk):
+    K = 16 * ksteps
+    A, Bm = _mats(128, n, K)
+    D, st = run_probe(A, Bm, n=n, ksteps=ksteps, bulk=bulk)
+    err = (D - _expect(A, Bm, 0)).abs().max().item()
+    _report(f"convention n={n} ksteps={ksteps} bulk={bulk}: status={st} err={err:.3e}")
+    assert st == 0, "probe timed out"
+    assert err < 1e-3, "canonical LBO/SBO convention wrong"
+
+
+@pytest.mark.parametrize("shift", [1, 2, 7, 8, 9])
+def test_row_shift_by_start_address(shift):
+    n, ksteps = 128, 4
+    A, Bm = _mats(144, n, 16 * ksteps, seed=shift)
+    D, st = run_probe(A, Bm, n=n, ksteps=ksteps, shift=shift)
+    err = (D - _expect(A, Bm, shift)).abs().max().item()
+    err0 = (D - _expect(A, Bm, 0)).abs().max().item()
+    _report(f"row shift {shift}: status={st} err={err:.3e} (err vs unshifted {err0:.3e})")
+    assert st == 0 and err < 1e-3

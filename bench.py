@@ -1,0 +1,310 @@
+#!/usr/bin/env python
+"""Benchmark of the reverse-diffusion hot path (BASELINE.json metric: mel frames/sec).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--precision bf16|fp32] [--impl reference]
+
+A "step" is one full reverse diffusion (all K_diff Denoiser calls + posterior updates + denorm/mask)
+over one synthetic batch.  Workload at any N: BASELINE configs[1] — LJSpeech `naive`, K_diff=4,
+B=64 utterances x T=800 frames per GPU (weak scaling: utterances shard across ranks with no
+collective on the data path).  One JSON line is printed by rank 0.
+
+  value     mel frames/s with inputs resident in HBM (device-timed with CUDA events, max over ranks)
+  e2e       the same metric through the public module API with HOST (pinned) inputs: H2D copy of
+            cond + mask, on-device noise draw, D2H read of the mel, all inside the timed region
+  roofline  the dominant kernel against the measured tensor peak (MEASURED_PEAKS.json)
+  cpu_baseline  the CPU oracle port timed on this box's host cores on a bounded sample (rank 0, N=1)
+
+`--impl reference` times the reference's CPU implementation of the path (the torch-CPU oracle port;
+the reference itself is Python and cannot travel to the GPU box) on all host threads.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOPS_PER_FRAME_STEP = 23_805_952          # SURVEY.md §8d / BASELINE.md §3 (algorithmic, no halo)
+CONV_FLOPS_PER_FRAME_STEP = 786_432        # the k=3 conv alone (dominant kernel of the fp32 path)
+B_PER_GPU, T_FRAMES, K_DIFF = 64, 800, 4   # BASELINE configs[1]
+CPU_SAMPLE_B = 16                          # BASELINE configs[0] shape for the CPU legs
+METRIC, UNIT = "mel_frames_per_sec", "frames/s"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"tensor_tflops": float(d["bf16_tflops_sustained"]), "hbm_gbs": float(d["hbm_gbs"]),
+                "source": "MEASURED_PEAKS.json (bf16_tflops_sustained: kernel timed inside a long step)"}
+    return {"tensor_tflops": 1400.0, "hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) < 7:
+                continue
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        busy = sorted(sm)[len(sm) // 2:]          # upper half = samples under load
+        return {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+def cpu_oracle_throughput(repeats: int, B: int = CPU_SAMPLE_B):
+    """Frames/s of the CPU oracle port on all host threads, best of `repeats` after one warm-up."""
+    import torch
+    from mixgan_tts_b200 import configs, synth
+    from oracle.diffusion import DiffusionOracle
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    _, _, mc, _ = configs.make_configs("LJSpeech", "naive")
+    W = synth.make_denoiser_weights(0)
+    orc = DiffusionOracle(W, model="naive", denoiser_cfg=mc["denoiser"], spec_min=[configs.SPEC_MIN] * 80,
+                          spec_max=[configs.SPEC_MAX] * 80)
+    inp = synth.make_inputs(1234, B, T_FRAMES, K_DIFF)
+    tt = lambda k: torch.from_numpy(inp[k])
+    args = (tt("cond"), None, tt("pad_mask"))
+    kw = dict(x_T=tt("x_T"), noises=tt("noises"))
+    small = synth.make_inputs(1, 1, 64, K_DIFF)
+    orc.forward_inference(torch.from_numpy(small["cond"]), None, torch.from_numpy(small["pad_mask"]),
+                          x_T=torch.from_numpy(small["x_T"]), noises=torch.from_numpy(small["noises"]))  # warm-up
+    times = []
+    for _ in range(max(1, repeats)):
+        t0 = time.perf_counter()
+        orc.forward_inference(*args, **kw)
+        times.append(time.perf_counter() - t0)
+    best = min(times)
+    return {"value": B * T_FRAMES / best, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"LJSpeech naive K=4, B={B} x T={T_FRAMES} (BASELINE configs[0] shape), fp32 torch-CPU oracle, "
+                      f"best of {len(times)} after warm-up, {best:.2f} s per pass, torch {torch.__version__}"}, times
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 5))
+    base, times = cpu_oracle_throughput(steps)
+    ms = 1e3 * statistics.mean(times)
+    val = CPU_SAMPLE_B * T_FRAMES / statistics.mean(times)
+    base = dict(base, value=val)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": len(times), "warmup": 1, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"LJSpeech naive K=4 reverse diffusion, CPU, bounded sample B={CPU_SAMPLE_B} x T={T_FRAMES} "
+                               "per step of the BASELINE configs[1] workload"},
+        "cpu_baseline": base,
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ---------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    from mixgan_tts_b200 import GaussianDiffusion, _lib, configs, synth
+    from mixgan_tts_b200.modules import PRECISIONS
+    lib = _lib.load()
+    dims0 = _lib.ModelDims(80, 256, 256, 20, 0)
+    prec = args.precision
+    if prec == "auto":
+        prec = "bf16" if lib.mgb_packed_bytes(C.byref(dims0), _lib.PREC_BF16) > 0 else "fp32"
+
+    cfg = configs.make_configs("LJSpeech", "naive")
+    gd = GaussianDiffusion(*cfg, precision=prec)
+    W = synth.make_denoiser_weights(0)
+    gd.denoise_fn.load_state_dict({k: torch.from_numpy(v) for k, v in W.items()})
+    gd = gd.to(dev).eval()
+    B, T, K = args.batch, T_FRAMES, gd.num_timesteps
+    den = gd.denoise_fn
+
+    # Rotating input sets so that no step finds its inputs in L2 (3 x ~134 MB > 126 MB L2).
+    NSETS = 3
+    sets = []
+    for i in range(NSETS):
+        inp = synth.make_inputs(1234 + 17 * i + 1000 * rank, B, T, K)
+        sets.append({"cond": torch.from_numpy(inp["cond"]).to(dev), "pad": torch.from_numpy(inp["pad_mask"]).to(dev),
+                     "x_T": torch.from_numpy(inp["x_T"]).to(dev), "noises": torch.from_numpy(inp["noises"]).to(dev)})
+    set_bytes = sum(v.numel() * v.element_size() for v in sets[0].values())
+    pad_u8 = [s["pad"].to(torch.uint8).contiguous() for s in sets]
+
+    def step_resident(i):
+        s = sets[i % NSETS]
+        return gd._sample_core(s["cond"], None, s["x_T"], s["noises"], pad_u8[i % NSETS], want_states=False)[0]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ------------------------------------------------------------------ device-resident timing
+    for i in range(max(args.warmup, 3)):
+        step_resident(i)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    lib.mgb_profile_enable(1)
+    launches0 = lib.mgb_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for i in range(args.steps):
+        step_resident(i)
+    ev1.record()
+    barrier()
+    launches = lib.mgb_launch_count() - launches0
+    ms_total = ev0.elapsed_time(ev1)
+    ktot, kcnt = C.c_float(0), C.c_int(0)
+    _lib.check(lib.mgb_profile_collect(C.byref(ktot), C.byref(kcnt)), "mgb_profile_collect")
+    lib.mgb_profile_enable(0)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ------------------------------------------------------------------ end-to-end timing (host buffers)
+    host = [{"cond": s["cond"].cpu().pin_memory(), "pad": s["pad"].cpu().pin_memory()} for s in sets]
+    out_host = torch.empty((B, T, 80), dtype=torch.float32).pin_memory()
+
+    def step_e2e(i):
+        h = host[i % NSETS]
+        cond = h["cond"].to(dev, non_blocking=True)
+        pad = h["pad"].to(dev, non_blocking=True)
+        mel = gd(None, cond, None, pad)[0]          # the call a user makes; noise drawn on device inside
+        out_host.copy_(mel, non_blocking=True)
+
+    for i in range(3):
+        step_e2e(i)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        step_e2e(i)
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+
+    if world > 1:
+        t = torch.tensor([ms_total, ms_e2e], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total, ms_e2e = float(t[0]), float(t[1])
+
+    if rank == 0:
+        pk = peaks()
+        frames_per_step = world * B * T
+        value = frames_per_step * args.steps / (ms_total * 1e-3)
+        e2e_val = frames_per_step * args.steps / (ms_e2e * 1e-3)
+        k_ms = ktot.value / max(kcnt.value, 1)
+        if prec == "bf16":
+            kern, fl = "fused residual-stack kernel (one launch = one Denoiser call over the batch)", FLOPS_PER_FRAME_STEP
+        else:
+            kern, fl = "conv_gemm_kernel<EPI_GATE> (k=3 conv + gate of one block, fp32 CUDA cores)", CONV_FLOPS_PER_FRAME_STEP
+        achieved = fl * B * T / (k_ms * 1e-3) / 1e12 if k_ms > 0 else 0.0
+        valid = float(sum(int((~s["pad"]).sum()) for s in sets)) / NSETS
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if prec == "bf16" else "f32", "data": "synthetic",
+            "config": {"workload": f"LJSpeech naive K={K} reverse diffusion, B={B} x T={T} per GPU (BASELINE configs[1]), "
+                                   "random-init Denoiser, fixed injected noise",
+                       "precision": prec, "l2": f"inputs rotate over {NSETS} sets of {set_bytes / 1e6:.0f} MB (> 126 MB L2)",
+                       "frames_valid_per_s": value * valid / (B * T), "frame_steps_per_s": value * K,
+                       "rtf_valid_audio": (ms_total / args.steps * 1e-3) / (world * valid * 256 / 22050)},
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": pk["tensor_tflops"], "unit": "TFLOP/s",
+                         "frac": achieved / pk["tensor_tflops"], "traffic": None, "kernel": kern,
+                         "kernel_ms": k_ms, "kernel_launches_timed": kcnt.value,
+                         "kernel_share_of_step": ktot.value / ms_total if ms_total > 0 else None,
+                         "whole_step_tflops": FLOPS_PER_FRAME_STEP * K * B * T * args.steps / (ms_total * 1e-3) / 1e12,
+                         "peak_source": pk["source"]},
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(B * T * 256 * 4 + B * T),
+                    "d2h_bytes_per_step": int(B * T * 80 * 4), "ms_per_step": ms_e2e / args.steps,
+                    "api": "GaussianDiffusion.forward(None, cond, None, mel_mask) from pinned host tensors"},
+            "gpu_launches": int(launches), "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"], _ = cpu_oracle_throughput(2)
+        else:
+            line["cpu_baseline"] = None
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default="auto", choices=["auto", "bf16", "fp32"])
+    ap.add_argument("--batch", type=int, default=B_PER_GPU)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

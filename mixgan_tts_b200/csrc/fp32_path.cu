@@ -9,10 +9,13 @@
 // Activation layout in HBM: frames-major [B*T][C] fp32 (one row per mel frame), so a k=3
 // convolution is three row-shifted GEMMs over the same matrix with zero rows at utterance edges.
 #include "common.cuh"
+#include "small_ops.cuh"
 
 namespace mgb {
 
 namespace {
+
+using namespace smallops;
 
 constexpr int BM = 128, BN = 128, BK = 8, NT = 256, BMP = BM + 4;
 
@@ -201,104 +204,6 @@ __global__ void __launch_bounds__(NT) conv_gemm_kernel(const GemmArgs p) {
   }
 }
 
-// ---- weight packing: dst[k][n'] = src[orig(n')][k] -------------------------------------------
-// src is [n_src][Kin][taps] (state_dict layout); dst is [taps*Kin][ldd], k = tap*Kin + ci.
-// perm: 128-wide column tiles hold 64 first-half then 64 second-half output channels.
-__global__ void pack_wt_kernel(const float* __restrict__ src, float* __restrict__ dst, int n_src,
-                               int Kin, int taps, int ldd, int perm, int half_n) {
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  const int k = blockIdx.y;
-  if (n >= ldd) return;
-  int orig = n;
-  if (perm) {
-    const int tile = n >> 7, pos = n & 127;
-    orig = pos < 64 ? tile * 64 + pos : half_n + tile * 64 + (pos - 64);
-  }
-  const int tap = k / Kin, ci = k - tap * Kin;
-  float v = 0.f;
-  if (orig < n_src) v = src[((size_t)orig * Kin + ci) * taps + tap];
-  dst[(size_t)k * ldd + n] = v;
-}
-
-__global__ void pack_bias_kernel(const float* __restrict__ src, float* __restrict__ dst, int n_src,
-                                 int n_dst, int perm, int half_n) {
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= n_dst) return;
-  int orig = n;
-  if (perm) {
-    const int tile = n >> 7, pos = n & 127;
-    orig = pos < 64 ? tile * 64 + pos : half_n + tile * 64 + (pos - 64);
-  }
-  dst[n] = orig < n_src ? src[orig] : 0.f;
-}
-
-// ---- small per-utterance ops --------------------------------------------------------------------
-// d[b] = W2 * mish(W0 * [sin(t f), cos(t f)])   (blocks.py:906-913, modules.py:433-434)
-__global__ void __launch_bounds__(256) step_mlp_kernel(const int64_t* __restrict__ t,
-                                                       const float* __restrict__ w0t,   // [C][4C]
-                                                       const float* __restrict__ w2t,   // [4C][C]
-                                                       float* __restrict__ d, int C) {
-  extern __shared__ float sm[];
-  float* emb = sm;          // [C]
-  float* h = sm + C;        // [4C]
-  const int b = blockIdx.x, tid = threadIdx.x;
-  const int halfd = C / 2;
-  const float tv = (float)t[b];
-  const float scale = (float)(9.210340371976184 / (double)(halfd - 1));  // ln(10000)/(half-1)
-  for (int i = tid; i < halfd; i += blockDim.x) {
-    const float f = expf((float)i * -scale);
-    const float a = tv * f;
-    emb[i] = sinf(a);
-    emb[halfd + i] = cosf(a);
-  }
-  __syncthreads();
-  for (int j = tid; j < 4 * C; j += blockDim.x) {
-    float s = 0.f;
-    for (int k = 0; k < C; ++k) s = fmaf(w0t[(size_t)k * 4 * C + j], emb[k], s);
-    const float sp = s > 20.f ? s : log1pf(expf(s));  // F.softplus default threshold
-    h[j] = s * tanhf(sp);
-  }
-  __syncthreads();
-  for (int c = tid; c < C; c += blockDim.x) {
-    float s = 0.f;
-    for (int k = 0; k < 4 * C; ++k) s = fmaf(w2t[(size_t)k * C + c], h[k], s);
-    d[(size_t)b * C + c] = s;
-  }
-}
-
-// tab[b][l][c] = sum_k Wt_l[k][c] * v[b][k] (+ bias_l[c]);  v == nullptr -> bias only.
-constexpr int TAB_UB = 8;
-__global__ void __launch_bounds__(256) proj_table_kernel(const float* __restrict__ v, int Kin,
-                                                         const float* __restrict__ wt0, size_t w_stride,
-                                                         const float* __restrict__ bias0, size_t b_stride,
-                                                         float* __restrict__ tab, int B, int L, int C) {
-  extern __shared__ float vs[];  // [TAB_UB][Kin]
-  const int l = blockIdx.x, b0 = blockIdx.y * TAB_UB, c = threadIdx.x;
-  const int nb = min(TAB_UB, B - b0);
-  float acc[TAB_UB];
-#pragma unroll
-  for (int u = 0; u < TAB_UB; ++u) acc[u] = 0.f;
-  if (v) {
-    for (int i = threadIdx.x; i < TAB_UB * Kin; i += blockDim.x) {
-      const int u = i / Kin, k = i - u * Kin;
-      vs[i] = u < nb ? v[(size_t)(b0 + u) * Kin + k] : 0.f;
-    }
-    __syncthreads();
-    const float* wt = wt0 + (size_t)l * w_stride;
-    if (c < C) {
-      for (int k = 0; k < Kin; ++k) {
-        const float w = wt[(size_t)k * C + c];
-#pragma unroll
-        for (int u = 0; u < TAB_UB; ++u) acc[u] = fmaf(w, vs[u * Kin + k], acc[u]);
-      }
-    }
-  }
-  if (c < C) {
-    const float bv = bias0 ? bias0[(size_t)l * b_stride + c] : 0.f;
-    for (int u = 0; u < nb; ++u) tab[((size_t)(b0 + u) * L + l) * C + c] = acc[u] + bv;
-  }
-}
-
 // [B][M][T] -> [B*T][M]
 __global__ void bmt_to_btm_kernel(const float* __restrict__ src, float* __restrict__ dst, int M, int T) {
   __shared__ float tile[32][33];
@@ -363,12 +268,6 @@ WorkF32 work_layout(const mgb_model_dims& d, int B, int T) {
   w.ctab = take((size_t)B * d.layers * C);
   w.total = p;
   return w;
-}
-
-void launch_pack(const float* src, float* dst, int n_src, int Kin, int taps, int ldd, int perm,
-                 int half_n, cudaStream_t s) {
-  dim3 grid((ldd + 127) / 128, taps * Kin);
-  pack_wt_kernel<<<grid, 128, 0, s>>>(src, dst, n_src, Kin, taps, ldd, perm, half_n);
 }
 
 template <int EPI>

@@ -255,8 +255,13 @@ def run_ours(args):
         value = frames_per_step * args.steps / (ms_total * 1e-3)
         e2e_val = frames_per_step * args.steps / (ms_e2e * 1e-3)
         k_ms = ktot.value / max(kcnt.value, 1)
+        calls = args.steps * K                      # Denoiser calls in the timed region
         if prec == "bf16":
-            kern, fl = "fused residual-stack kernel (one launch = one Denoiser call over the batch)", FLOPS_PER_FRAME_STEP
+            # one Denoiser call = `launches_per_call` launches of fused_group_kernel (layer groups);
+            # algorithmic FLOPs per launch = FLOPs per call / launches per call
+            per_call = max(kcnt.value // calls, 1)
+            kern = f"fused_group_kernel (tcgen05; {per_call} launches = one Denoiser call over the batch)"
+            fl = FLOPS_PER_FRAME_STEP / per_call
         else:
             kern, fl = "conv_gemm_kernel<EPI_GATE> (k=3 conv + gate of one block, fp32 CUDA cores)", CONV_FLOPS_PER_FRAME_STEP
         achieved = fl * B * T / (k_ms * 1e-3) / 1e12 if k_ms > 0 else 0.0

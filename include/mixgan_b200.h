@@ -86,6 +86,12 @@ long long mgb_launch_count(void);
 void mgb_profile_enable(int on);
 int mgb_profile_collect(float* total_ms, int* count);
 
+/* Debug: synchronously read the watchdog word of the bf16 path from a workspace that was used with
+ * the same (B, T).  0 = every kernel completed its barrier protocol; non-zero bits name the warp
+ * role whose bounded wait expired (1 producer, 2 MMA issuer, 4 epilogue). */
+int mgb_debug_status(const mgb_model_dims* dims, int precision, int B, int T, const void* workspace,
+                     int* host_status);
+
 /* 0 when `device` can run this library (compute capability 10.x), else MGB_E_ARCH. */
 int mgb_device_check(int device);
 

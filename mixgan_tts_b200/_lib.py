@@ -30,6 +30,7 @@ SIGNATURES = {
     "mgb_launch_count": (C.c_longlong, []),
     "mgb_profile_enable": (None, [_I]),
     "mgb_profile_collect": (_I, [C.POINTER(C.c_float), C.POINTER(C.c_int)]),
+    "mgb_debug_status": (_I, [_D, _I, _I, _I, _P, C.POINTER(C.c_int)]),
     "mgb_device_check": (_I, [_I]),
     "mgb_flat_weight_count": (_Z, [_D]),
     "mgb_packed_bytes": (_Z, [_D, _I]),

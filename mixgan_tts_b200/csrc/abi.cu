@@ -213,6 +213,15 @@ int mgb_profile_collect(float* total_ms, int* count) {
 }
 const char* mgb_last_error(void) { return g_err; }
 
+int mgb_debug_status(const mgb_model_dims* dims, int precision, int B, int T, const void* workspace, int* host_status) {
+  MGB_REQUIRE(dims_supported(dims) && workspace && host_status, MGB_E_ARG, "bad argument");
+  *host_status = 0;
+  if (precision != MGB_PREC_BF16) return MGB_OK;
+  const char* src = static_cast<const char*>(workspace) + bf16_status_offset(*dims, B, T);
+  MGB_CUDA_CHECK(cudaMemcpy(host_status, src, sizeof(int), cudaMemcpyDeviceToHost));
+  return MGB_OK;
+}
+
 int mgb_device_check(int device) {
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n) {

@@ -25,7 +25,7 @@ PRECISIONS = {"fp32": _lib.PREC_FP32, "bf16": _lib.PREC_BF16}
 
 
 def default_precision() -> str:
-    return os.environ.get("MIXGAN_B200_PRECISION", "fp32")
+    return os.environ.get("MIXGAN_B200_PRECISION", "bf16")
 
 
 class _Conv(nn.Module):

@@ -254,7 +254,7 @@ PackedF32 packed_layout(const mgb_model_dims& d) {
 }
 
 struct WorkF32 {
-  size_t X, Y, G, S, xt, d, dtab, ctab, total;
+  size_t X, Y, G, S, xt, d, h, dtab, ctab, total;
 };
 WorkF32 work_layout(const mgb_model_dims& d, int B, int T) {
   const size_t C = d.channels, BT = (size_t)B * T;
@@ -264,6 +264,7 @@ WorkF32 work_layout(const mgb_model_dims& d, int B, int T) {
   w.X = take(BT * C); w.Y = take(BT * C); w.G = take(BT * C); w.S = take(BT * C);
   w.xt = take(BT * d.n_mel);
   w.d = take((size_t)B * C);
+  w.h = take((size_t)B * 4 * C);
   w.dtab = take((size_t)B * d.layers * C);
   w.ctab = take((size_t)B * d.layers * C);
   w.total = p;
@@ -326,7 +327,7 @@ int fp32_denoiser(const mgb_model_dims& d, const void* packed, const float* x, c
   const int rows = B * T;
 
   // per-utterance step embedding, MLP and the per-layer projection tables
-  step_mlp_kernel<<<B, 256, (size_t)5 * C * sizeof(float), s>>>(t, P + o.mlp0_wt, P + o.mlp2_wt, W + w.d, C);
+  launch_step_mlp(t, P + o.mlp0_wt, P + o.mlp2_wt, W + w.h, W + w.d, B, C, s);
   {
     dim3 grid(L, (B + TAB_UB - 1) / TAB_UB);
     proj_table_kernel<<<grid, 256, (size_t)TAB_UB * C * sizeof(float), s>>>(
@@ -338,7 +339,7 @@ int fp32_denoiser(const mgb_model_dims& d, const void* packed, const float* x, c
   {
     dim3 grid((T + 31) / 32, (M + 31) / 32, B), block(32, 8);
     bmt_to_btm_kernel<<<grid, block, 0, s>>>(x, W + w.xt, M, T);
-    note_launch(4);   // step MLP, two projection tables, this transpose
+    note_launch(5);   // step MLP (2), two projection tables, this transpose
   }
   GemmArgs a{};
   a.rows = rows; a.T = T; a.C = C; a.tab_stride = L * C;

@@ -143,32 +143,46 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_group_kernel(const FusedPar
   tc::tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   const uint32_t TM_SKIP = tmem, TM_TEMP0 = tmem + 256, TM_TEMP1 = tmem + 384;
-  int fail = 0;
 
   if (warp < 4) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
-    if (warp == 0 && lane == 0) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    // Both roles below run with WARP-UNIFORM control flow (all 32 lanes wait on the barriers and walk
+    // the schedule); only the instructions that must come from one thread (bulk copies, tcgen05.mma,
+    // tcgen05.commit, expect_tx) are predicated with elect_one().  Waits never feed state back into the
+    // loops (a timeout traps), so ring positions and descriptors stay in uniform registers.
+    const uint32_t bar0 = tc::smem_u32(bars);
+    const uint32_t slots0 = tc::smem_u32(sSlots);
+    if (warp == 0) {
       // =========================== TMA PRODUCER ===========================
-      Ring ring;
+      uint32_t slot = 0, phase = 0;
       const uint8_t* condb = reinterpret_cast<const uint8_t*>(p.condT) +
                              ((size_t)b * 32 * p.Tp + (size_t)(f0 + COND_PAD_LO)) * 16;
+      auto advance = [&]() {
+        const bool wrap = slot == NSLOTS - 1;
+        slot = wrap ? 0u : slot + 1u;
+        phase ^= wrap ? 1u : 0u;
+      };
       auto load_w = [&](int widx, uint32_t bytes) {
-        if (fail) return;
-        if (!tc::mbar_wait(&bars[B_EMPTY + ring.slot], ring.phase ^ 1, WAIT_CYCLES)) { fail = 1; return; }
-        tc::mbar_arrive_expect_tx(&bars[B_FULL + ring.slot], bytes);
-        tc::bulk_g2s(sSlots + ring.slot * SLOT_BYTES, p.wimg + (size_t)widx * SLOT_BYTES, bytes,
-                     &bars[B_FULL + ring.slot]);
-        ring.advance();
+        tc::mbar_wait_trap(bar0 + (B_EMPTY + slot) * 8, phase ^ 1, WAIT_CYCLES, p.status, 1);
+        if (tc::elect_one()) {
+          const uint32_t fb = bar0 + (B_FULL + slot) * 8;
+          tc::mbar_arrive_expect_tx_addr(fb, bytes);
+          tc::bulk_g2s_addr(slots0 + slot * SLOT_BYTES, p.wimg + (size_t)widx * SLOT_BYTES, bytes, fb);
+        }
+        __syncwarp();
+        advance();
       };
       auto load_cond = [&](int kb) {   // cond channels [64kb, 64kb+64) of the tile's 128 frames
-        if (fail) return;
-        if (!tc::mbar_wait(&bars[B_EMPTY + ring.slot], ring.phase ^ 1, WAIT_CYCLES)) { fail = 1; return; }
-        tc::mbar_arrive_expect_tx(&bars[B_FULL + ring.slot], SLOT_BYTES);
+        tc::mbar_wait_trap(bar0 + (B_EMPTY + slot) * 8, phase ^ 1, WAIT_CYCLES, p.status, 1);
+        if (tc::elect_one()) {
+          const uint32_t fb = bar0 + (B_FULL + slot) * 8;
+          tc::mbar_arrive_expect_tx_addr(fb, SLOT_BYTES);
 #pragma unroll
-        for (int k8 = 0; k8 < 8; ++k8)
-          tc::bulk_g2s(sSlots + ring.slot * SLOT_BYTES + k8 * 2048, condb + (size_t)(kb * 8 + k8) * p.Tp * 16, 2048,
-                       &bars[B_FULL + ring.slot]);
-        ring.advance();
+          for (int k8 = 0; k8 < 8; ++k8)
+            tc::bulk_g2s_addr(slots0 + slot * SLOT_BYTES + k8 * 2048, condb + (size_t)(kb * 8 + k8) * p.Tp * 16, 2048, fb);
+        }
+        __syncwarp();
+        advance();
       };
       if (first_group) {
         for (int c = 0; c < 2; ++c) { load_w(W_IN + 2 * c, SLOT_BYTES); load_w(W_IN + 2 * c + 1, 4096); }
@@ -190,97 +204,129 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_group_kernel(const FusedPar
         for (int i = 0; i < 8; ++i) load_w(W_SKIPP + i, SLOT_BYTES);
         for (int i = 0; i < 4; ++i) load_w(W_OUT + i, SLOT_BYTES);
       }
-      if (fail) atomicOr(p.status, 1);
-    } else if (warp == 1 && lane == 0) {
+    } else if (warp == 1) {
       // =========================== MMA ISSUER ===========================
-      Ring ring;
+      uint32_t slot = 0, phase = 0;
       const uint32_t idesc = tc::make_idesc_bf16(128, 128);
-      const uint32_t aA = tc::smem_u32(sA), aG = tc::smem_u32(sG), aS = tc::smem_u32(sSlots);
+      // descriptor templates; a byte offset is added to the 14-bit start-address field (>> 4)
+      const uint64_t dA = tc::make_smem_desc(tc::smem_u32(sA), A_LBO, SBO);
+      const uint64_t dG = tc::make_smem_desc(tc::smem_u32(sG), G_LBO, SBO);
+      const uint64_t dS = tc::make_smem_desc(slots0, W_LBO, SBO);
       uint32_t n_use = 0;            // temp-buffer uses so far; they strictly alternate 0,1,0,1,...
       uint32_t n_aready = 0, n_gready = 0;
 
-      // one weight slot: nk k-steps of K=16; A from a resident tile
-      auto mma_w = [&](uint32_t a_addr, uint32_t a_lbo, int nk, uint32_t d_tmem, uint32_t& acc) {
-        if (fail) return;
-        if (!tc::mbar_wait(&bars[B_FULL + ring.slot], ring.phase, WAIT_CYCLES)) { fail = 1; return; }
+      auto advance = [&]() {
+        const bool wrap = slot == NSLOTS - 1;
+        slot = wrap ? 0u : slot + 1u;
+        phase ^= wrap ? 1u : 0u;
+      };
+      auto wait_full = [&]() {
+        tc::mbar_wait_trap(bar0 + (B_FULL + slot) * 8, phase, WAIT_CYCLES, p.status, 2);
         tc::tc_fence_after();
-        const uint32_t b_addr = aS + ring.slot * SLOT_BYTES;
-        for (int k = 0; k < nk; ++k) {
-          tc::umma_bf16(d_tmem, tc::make_smem_desc(a_addr + k * 2 * a_lbo, a_lbo, SBO),
-                        tc::make_smem_desc(b_addr + k * 2 * W_LBO, W_LBO, SBO), idesc, acc);
-          acc = 1;
+      };
+      // one weight slot = NK k-steps of K=16 with the A operand from a resident tile (descriptor a0)
+      auto mma_w4 = [&](uint64_t a0, uint32_t a_kstep16, uint32_t d_tmem, uint32_t acc_first) {
+        wait_full();
+        if (tc::elect_one()) {
+          const uint64_t b0 = dS + (uint64_t)(slot * (SLOT_BYTES >> 4));
+          tc::umma_bf16(d_tmem, a0, b0, idesc, acc_first);
+          tc::umma_bf16(d_tmem, a0 + a_kstep16, b0 + (2 * W_LBO >> 4), idesc, 1u);
+          tc::umma_bf16(d_tmem, a0 + 2 * a_kstep16, b0 + 2 * (2 * W_LBO >> 4), idesc, 1u);
+          tc::umma_bf16(d_tmem, a0 + 3 * a_kstep16, b0 + 3 * (2 * W_LBO >> 4), idesc, 1u);
+          tc::umma_commit_addr(bar0 + (B_EMPTY + slot) * 8);
         }
-        tc::umma_commit(&bars[B_EMPTY + ring.slot]);
-        ring.advance();
+        __syncwarp();
+        advance();
+      };
+      auto mma_w1 = [&](uint64_t a0, uint32_t d_tmem, uint32_t acc_first) {   // a K=16 slot (input projection tail)
+        wait_full();
+        if (tc::elect_one()) {
+          tc::umma_bf16(d_tmem, a0, dS + (uint64_t)(slot * (SLOT_BYTES >> 4)), idesc, acc_first);
+          tc::umma_commit_addr(bar0 + (B_EMPTY + slot) * 8);
+        }
+        __syncwarp();
+        advance();
       };
       // a cond slot (A operand) followed by its weight slot
-      auto mma_cond = [&](uint32_t d_tmem, uint32_t& acc) {
-        if (fail) return;
-        if (!tc::mbar_wait(&bars[B_FULL + ring.slot], ring.phase, WAIT_CYCLES)) { fail = 1; return; }
-        const int sa = ring.slot;
-        ring.advance();
-        if (!tc::mbar_wait(&bars[B_FULL + ring.slot], ring.phase, WAIT_CYCLES)) { fail = 1; return; }
-        tc::tc_fence_after();
-        const uint32_t a_addr = aS + sa * SLOT_BYTES, b_addr = aS + ring.slot * SLOT_BYTES;
-        for (int k = 0; k < 4; ++k) {
-          tc::umma_bf16(d_tmem, tc::make_smem_desc(a_addr + k * 2 * W_LBO, W_LBO, SBO),
-                        tc::make_smem_desc(b_addr + k * 2 * W_LBO, W_LBO, SBO), idesc, acc);
-          acc = 1;
+      auto mma_cond = [&](uint32_t d_tmem, uint32_t acc_first) {
+        wait_full();
+        const uint32_t sa = slot;
+        advance();
+        wait_full();
+        if (tc::elect_one()) {
+          const uint64_t a0 = dS + (uint64_t)(sa * (SLOT_BYTES >> 4));
+          const uint64_t b0 = dS + (uint64_t)(slot * (SLOT_BYTES >> 4));
+          tc::umma_bf16(d_tmem, a0, b0, idesc, acc_first);
+          tc::umma_bf16(d_tmem, a0 + (2 * W_LBO >> 4), b0 + (2 * W_LBO >> 4), idesc, 1u);
+          tc::umma_bf16(d_tmem, a0 + 2 * (2 * W_LBO >> 4), b0 + 2 * (2 * W_LBO >> 4), idesc, 1u);
+          tc::umma_bf16(d_tmem, a0 + 3 * (2 * W_LBO >> 4), b0 + 3 * (2 * W_LBO >> 4), idesc, 1u);
+          tc::umma_commit_addr(bar0 + (B_EMPTY + sa) * 8);
+          tc::umma_commit_addr(bar0 + (B_EMPTY + slot) * 8);
         }
-        tc::umma_commit(&bars[B_EMPTY + sa]);
-        tc::umma_commit(&bars[B_EMPTY + ring.slot]);
-        ring.advance();
+        __syncwarp();
+        advance();
       };
-      auto temp_acquire = [&](int tb) {   // wait until the epilogue has drained the previous use of buffer tb
-        if (fail) return;
-        if (!tc::mbar_wait(&bars[B_TEMPTY + tb], ((n_use >> 1) + 1) & 1, WAIT_CYCLES)) fail = 1;
+      auto temp_acquire = [&](uint32_t tb) {   // wait until the epilogue has drained the previous use of buffer tb
+        tc::mbar_wait_trap(bar0 + (B_TEMPTY + tb) * 8, ((n_use >> 1) + 1) & 1, WAIT_CYCLES, p.status, 2);
         tc::tc_fence_after();
       };
-      auto temp_publish = [&](int tb) {
-        if (!fail) tc::umma_commit(&bars[B_TFULL + tb]);
+      auto temp_publish = [&](uint32_t tb) {
+        if (tc::elect_one()) tc::umma_commit_addr(bar0 + (B_TFULL + tb) * 8);
+        __syncwarp();
         ++n_use;
       };
-      auto wait_bar = [&](int bar, uint32_t n) {
-        if (fail) return;
-        if (!tc::mbar_wait(&bars[bar], n & 1, WAIT_CYCLES)) fail = 1;
+      auto wait_bar = [&](uint32_t bar, uint32_t n) {
+        tc::mbar_wait_trap(bar0 + bar * 8, n & 1, WAIT_CYCLES, p.status, 2);
         tc::tc_fence_after();
       };
-      auto tm_t = [&](int tb) { return TM_TEMP0 + (uint32_t)tb * 128u; };
+      auto tm_t = [&](uint32_t tb) { return TM_TEMP0 + tb * 128u; };
+      constexpr uint32_t A_K16 = (2 * A_LBO) >> 4, G_K16 = (2 * G_LBO) >> 4;   // descriptor step per K=16
 
       if (first_group) {
         wait_bar(B_AREADY, n_aready++);                 // x_t tile as bf16, channels 0..79, rows 1..128
-        for (int c = 0; c < 2; ++c) {                   // input projection, K = 80
+        for (uint32_t c = 0; c < 2; ++c) {              // input projection, K = 80
           temp_acquire(c);
-          uint32_t acc = 0;
-          mma_w(aA + 16, A_LBO, 4, tm_t(c), acc);
-          mma_w(aA + 16 + 8 * A_LBO, A_LBO, 1, tm_t(c), acc);
+          mma_w4(dA + (16 >> 4), A_K16, tm_t(c), 0u);
+          mma_w1(dA + ((16 + 8 * A_LBO) >> 4), tm_t(c), 1u);
           temp_publish(c);
         }
-        for (int c = 0; c < 2; ++c) {                   // conditioner projection of layer 0
+        for (uint32_t c = 0; c < 2; ++c) {              // conditioner projection of layer 0
           temp_acquire(c);
-          uint32_t acc = 0;
-          for (int j = 0; j < 4; ++j) mma_cond(tm_t(c), acc);
+          for (int j = 0; j < 4; ++j) mma_cond(tm_t(c), j ? 1u : 0u);
           temp_publish(c);
         }
       }
       for (int l = p.lb; l < p.le; ++l) {
         wait_bar(B_AREADY, n_aready++);                 // conv input u_l in sA
-        for (int i = 0; i < 4; ++i) {                   // k=3 conv, chunk i = 64 gate + 64 filter channels
-          const int tb = i & 1;
+#pragma unroll 1
+        for (uint32_t i = 0; i < 4; ++i) {              // k=3 conv, chunk i = 64 gate + 64 filter channels
+          const uint32_t tb = i & 1;
           temp_acquire(tb);
           uint32_t acc = 0;
-          for (int j = 0; j < 12; ++j)
-            mma_w(aA + (j >> 2) * 16 + (j & 3) * 8 * A_LBO, A_LBO, 4, tm_t(tb), acc);
+#pragma unroll 1
+          for (uint32_t tap = 0; tap < 3; ++tap) {      // tap = +16 B row shift of the start address
+            uint64_t a = dA + tap;
+#pragma unroll 1
+            for (uint32_t kb = 0; kb < 4; ++kb) {       // 64-channel blocks
+              mma_w4(a, A_K16, tm_t(tb), acc);
+              acc = 1;
+              a += (8 * A_LBO) >> 4;
+            }
+          }
           temp_publish(tb);
         }
         if (l < p.L - 1) {
-          for (int c = 0; c < 2; ++c) {                 // residual-out + conditioner delta, 128 channels each
+#pragma unroll 1
+          for (uint32_t c = 0; c < 2; ++c) {            // residual-out + conditioner delta, 128 channels each
             temp_acquire(c);
-            uint32_t acc = 0;
-            for (int j = 0; j < 4; ++j) mma_cond(tm_t(c), acc);
-            for (int j = 0; j < 4; ++j) {
+#pragma unroll 1
+            for (uint32_t j = 0; j < 4; ++j) mma_cond(tm_t(c), j ? 1u : 0u);
+            uint64_t a = dG;
+#pragma unroll 1
+            for (uint32_t j = 0; j < 4; ++j) {
               if (c == 0) wait_bar(B_GREADY + j, n_gready);
-              mma_w(aG + j * 8 * G_LBO, G_LBO, 4, tm_t(c), acc);
+              mma_w4(a, G_K16, tm_t(c), 1u);
+              a += (8 * G_LBO) >> 4;
             }
             temp_publish(c);
           }
@@ -288,31 +334,34 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_group_kernel(const FusedPar
           for (int j = 0; j < 4; ++j) wait_bar(B_GREADY + j, n_gready);
         }
         ++n_gready;
-        for (int c = 0; c < 2; ++c) {                   // skip projection accumulates across layers
-          uint32_t acc = (l != p.lb) ? 1u : 0u;
-          for (int j = 0; j < 4; ++j) mma_w(aG + j * 8 * G_LBO, G_LBO, 4, TM_SKIP + c * 128, acc);
+#pragma unroll 1
+        for (uint32_t c = 0; c < 2; ++c) {              // skip projection accumulates across layers
+          uint64_t a = dG;
+#pragma unroll 1
+          for (uint32_t j = 0; j < 4; ++j) {
+            mma_w4(a, G_K16, TM_SKIP + c * 128, (j == 0 && l == p.lb) ? 0u : 1u);
+            a += (8 * G_LBO) >> 4;
+          }
         }
       }
-      if (!fail) tc::umma_commit(&bars[B_SKIPDONE]);
+      if (tc::elect_one()) tc::umma_commit_addr(bar0 + B_SKIPDONE * 8);
+      __syncwarp();
       if (last_group) {
         wait_bar(B_AREADY, n_aready++);                 // skip sum / sqrt(L) as bf16 in sA rows 1..128
-        for (int c = 0; c < 2; ++c) {
+        for (uint32_t c = 0; c < 2; ++c) {
           temp_acquire(c);
-          uint32_t acc = 0;
-          for (int j = 0; j < 4; ++j) mma_w(aA + 16 + j * 8 * A_LBO, A_LBO, 4, tm_t(c), acc);
+          for (int j = 0; j < 4; ++j) mma_w4(dA + ((16 + j * 8 * A_LBO) >> 4), A_K16, tm_t(c), j ? 1u : 0u);
           temp_publish(c);
         }
         wait_bar(B_GREADY + 0, n_gready++);             // relu(skip projection) as bf16 in sG
         temp_acquire(0);
-        uint32_t acc = 0;
-        for (int j = 0; j < 4; ++j) mma_w(aG + j * 8 * G_LBO, G_LBO, 4, tm_t(0), acc);
+        for (int j = 0; j < 4; ++j) mma_w4(dG + ((j * 8 * G_LBO) >> 4), G_K16, tm_t(0), j ? 1u : 0u);
         temp_publish(0);
       }
-      if (fail) atomicOr(p.status, 2);
     }
   } else {
     // =========================== EPILOGUE (warps 4..11) ===========================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
     const int ew = warp - 4;
     const int q = ew & 3;            // TMEM lane quadrant == warp % 4
     const int h = ew >> 2;           // which half of a 128-column chunk
@@ -328,7 +377,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_group_kernel(const FusedPar
     float u[128];                    // fp32 residual stream: channels 128c + 64h + j at index 64c + j
 
     auto temp_wait = [&](int tb) {
-      if (!fail && !tc::mbar_wait(&bars[B_TFULL + tb], (n_use >> 1) & 1, WAIT_CYCLES)) fail = 1;
+      tc::mbar_wait_trap(tc::smem_u32(&bars[B_TFULL + tb]), (n_use >> 1) & 1, WAIT_CYCLES, p.status, 4);
       ++n_use;
       tc::tc_fence_after();
     };
@@ -489,7 +538,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_group_kernel(const FusedPar
     }
 
     // ---- group end ----
-    if (!fail && !tc::mbar_wait(&bars[B_SKIPDONE], 0, WAIT_CYCLES)) fail = 1;
+    tc::mbar_wait_trap(tc::smem_u32(&bars[B_SKIPDONE]), 0, WAIT_CYCLES, p.status, 4);
     tc::tc_fence_after();
     if (!last_group) {
       if (is_out) {
@@ -601,7 +650,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_group_kernel(const FusedPar
       }
       temp_release(0);
     }
-    if (fail) atomicOr(p.status, 4);
   }
 
   // ---- teardown ----
@@ -738,7 +786,7 @@ __global__ void pack_small_kernel(const float* __restrict__ flat, const FlatOffs
 }
 
 struct WorkBf16 {
-  size_t condT, d, dtab, ctab, ktab, k00, U, U2, S, status, total;
+  size_t condT, d, h, dtab, ctab, ktab, k00, U, U2, S, status, total;
   int Tp;
 };
 WorkBf16 work_layout(const mgb_model_dims& d, int B, int T) {
@@ -748,6 +796,7 @@ WorkBf16 work_layout(const mgb_model_dims& d, int B, int T) {
   auto take = [&](size_t bytes) { size_t r = p; p += align_up(bytes, 256); return r; };
   w.condT = take((size_t)B * 32 * w.Tp * 16);
   w.d = take((size_t)B * C * 4);
+  w.h = take((size_t)B * 4 * C * 4);
   w.dtab = take((size_t)B * d.layers * C * 4);
   w.ctab = take((size_t)B * d.layers * C * 4);
   w.ktab = take((size_t)B * d.layers * C * 4);
@@ -826,7 +875,7 @@ int bf16_denoiser(const mgb_model_dims& d, const void* packed, const float* x, c
     MGB_CUDA_CHECK(cudaMemsetAsync(status, 0, sizeof(int), s));
     note_launch();
   }
-  step_mlp_kernel<<<B, 256, (size_t)5 * C * sizeof(float), s>>>(t, P + o.mlp0_wt, P + o.mlp2_wt, dvec, C);
+  launch_step_mlp(t, P + o.mlp0_wt, P + o.mlp2_wt, reinterpret_cast<float*>(W + w.h), dvec, B, C, s);
   {
     dim3 grid(L, (B + TAB_UB - 1) / TAB_UB);
     proj_table_kernel<<<grid, 256, (size_t)TAB_UB * C * sizeof(float), s>>>(dvec, C, P + o.dproj_wt, (size_t)C * C,
@@ -835,7 +884,7 @@ int bf16_denoiser(const mgb_model_dims& d, const void* packed, const float* x, c
         d.multi_speaker ? spk : nullptr, H, P + o.sproj_wt, (size_t)H * C, P + o.cproj_b, (size_t)C, ctab, B, L, C);
     dim3 kgrid(L, B);
     ktab_kernel<<<kgrid, 256, 0, s>>>(dtab, ctab, P + o.bo_x, ktab, k00, L);
-    note_launch(4);
+    note_launch(5);   // step MLP (2), two projection tables, ktab
   }
   FusedParams p{};
   p.wimg = reinterpret_cast<const uint8_t*>(P + o.total);

@@ -73,6 +73,65 @@ static __global__ void __launch_bounds__(256) step_mlp_kernel(const int64_t* __r
   }
 }
 
+// Batched version of the same MLP: one launch per layer, weights read once per 8 utterances.
+//   out[b][n] = f( sum_k in[b][k] * wt[k][n] ),  EMB: in[b] = sinusoidal embedding of t[b],  MISH: f = mish
+constexpr int MLP_UB = 8;
+template <bool EMB, bool MISH>
+static __global__ void __launch_bounds__(128) step_mlp_layer_kernel(const int64_t* __restrict__ t,
+                                                                    const float* __restrict__ in,
+                                                                    const float* __restrict__ wt,
+                                                                    float* __restrict__ out, int B, int K, int N) {
+  extern __shared__ float xs[];   // [MLP_UB][K]
+  const int b0 = blockIdx.y * MLP_UB, n = blockIdx.x * 128 + threadIdx.x;
+  const int halfd = K / 2;
+  const float scale = (float)(9.210340371976184 / (double)(halfd - 1));  // ln(10000)/(half-1)
+  for (int i = threadIdx.x; i < MLP_UB * K; i += 128) {
+    const int u = i / K, k = i - u * K, b = b0 + u;
+    float v = 0.f;
+    if (b < B) {
+      if (EMB) {
+        const int kk = k < halfd ? k : k - halfd;
+        const float a = (float)t[b] * expf((float)kk * -scale);
+        v = k < halfd ? sinf(a) : cosf(a);
+      } else {
+        v = in[(size_t)b * K + k];
+      }
+    }
+    xs[i] = v;
+  }
+  __syncthreads();
+  float acc[MLP_UB];
+#pragma unroll
+  for (int u = 0; u < MLP_UB; ++u) acc[u] = 0.f;
+  if (n < N) {
+    for (int k = 0; k < K; ++k) {
+      const float w = wt[(size_t)k * N + n];
+#pragma unroll
+      for (int u = 0; u < MLP_UB; ++u) acc[u] = fmaf(w, xs[u * K + k], acc[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < MLP_UB; ++u) {
+      if (b0 + u < B) {
+        float s = acc[u];
+        if (MISH) {
+          const float sp = s > 20.f ? s : log1pf(expf(s));  // F.softplus default threshold
+          s = s * tanhf(sp);
+        }
+        out[(size_t)(b0 + u) * N + n] = s;
+      }
+    }
+  }
+}
+
+// d[B][C] = W2 * mish(W0 * emb(t)); `hbuf` is [B][4C] scratch.  Two launches.
+static inline void launch_step_mlp(const int64_t* t, const float* w0t, const float* w2t, float* hbuf, float* d,
+                                   int B, int C, cudaStream_t s) {
+  dim3 g1(4 * C / 128, (B + MLP_UB - 1) / MLP_UB), g2(C / 128, (B + MLP_UB - 1) / MLP_UB);
+  step_mlp_layer_kernel<true, true><<<g1, 128, (size_t)MLP_UB * C * sizeof(float), s>>>(t, nullptr, w0t, hbuf, B, C, 4 * C);
+  step_mlp_layer_kernel<false, false><<<g2, 128, (size_t)MLP_UB * 4 * C * sizeof(float), s>>>(nullptr, hbuf, w2t, d, B,
+                                                                                            4 * C, C);
+}
+
 // tab[b][l][c] = sum_k Wt_l[k][c] * v[b][k] (+ bias_l[c]);  v == nullptr -> bias only.
 constexpr int TAB_UB = 8;
 static __global__ void __launch_bounds__(256) proj_table_kernel(const float* __restrict__ v, int Kin,

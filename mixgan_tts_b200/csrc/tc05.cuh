@@ -66,6 +66,53 @@ __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, long l
   return true;
 }
 
+// Hot-path wait: one try_wait on the fast path and nothing that depends on its outcome afterwards
+// (so callers keep warp-uniform state in uniform registers).  If the phase does not complete within
+// `max_cycles` the watchdog word is set and the kernel traps — a protocol bug fails loudly instead
+// of hanging the GPU.  `bar_addr` is a shared::cta address.
+__device__ __forceinline__ bool mbar_try_wait_addr(uint32_t bar_addr, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}\n"
+      : "=r"(ok)
+      : "r"(bar_addr), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_slow(uint32_t bar_addr, uint32_t parity, long long max_cycles, int* status,
+                                            int code) {
+  const long long t0 = clock64();
+  while (!mbar_try_wait_addr(bar_addr, parity)) {
+    if (clock64() - t0 > max_cycles) {
+      if (status) atomicOr(status, code);
+      __threadfence_system();
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void mbar_wait_trap(uint32_t bar_addr, uint32_t parity, long long max_cycles, int* status,
+                                               int code) {
+  if (!mbar_try_wait_addr(bar_addr, parity)) mbar_wait_slow(bar_addr, parity, max_cycles, status, code);
+}
+
+// address-based variants (shared::cta u32 addresses) for the hot loops
+__device__ __forceinline__ void mbar_arrive_addr(uint32_t bar_addr) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx_addr(uint32_t bar_addr, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_addr), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_addr(uint32_t smem_dst, const void* gmem_src, uint32_t bytes, uint32_t bar_addr) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_dst),
+               "l"(gmem_src), "r"(bytes), "r"(bar_addr)
+               : "memory");
+}
+__device__ __forceinline__ void umma_commit_addr(uint32_t bar_addr) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_addr) : "memory");
+}
+
 // generic-proxy smem writes -> visible to the async proxy (tcgen05.mma / bulk copies)
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

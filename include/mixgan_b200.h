@@ -167,6 +167,12 @@ int mgb_probe_umma(const void* a_img, int a_bytes, const void* b_img, int b_byte
                    int b_start, int b_lbo, int b_sbo, int b_kadv,
                    int n, int ksteps, int use_bulk_copy, float* d_out, int* status_out, void* stream);
 
+/* Same probe for a CTA pair (cta_group::2): M = 256 (a_img holds two 128-row images back to back),
+ * B rows split in halves (b_img holds two n/2-row images back to back); d_out is [256][n]. */
+int mgb_probe_umma_2cta(const void* a_img, int a_bytes, const void* b_img, int b_bytes,
+                        int a_lbo, int a_sbo, int a_kadv, int b_lbo, int b_sbo, int b_kadv,
+                        int n, int ksteps, float* d_out, int* status_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -86,6 +86,7 @@ struct FusedParams {
   float* S;                     // [B*T][C] fp32 partial skip sum between groups
   int B, T, L, lb, le, V, halo, tiles_per_utt;
   int* status;
+  long long* prof;              // debug (MGB_PROFILE): per-tile cycle counters, 16 per tile
 };
 
 __device__ __forceinline__ float tanh_approx(float x) {
@@ -109,7 +110,9 @@ struct Ring {
   }
 };
 
+template <bool PROF>
 __global__ void __launch_bounds__(NTHREADS, 1) fused_group_kernel(const FusedParams p) {
+  const long long t_start = PROF ? clock64() : 0;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sA = smem;
   uint8_t* sG = smem + SMEM_A;
@@ -144,6 +147,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_group_kernel(const FusedPar
   const uint32_t tmem = *tmem_slot;
   const uint32_t TM_SKIP = tmem, TM_TEMP0 = tmem + 256, TM_TEMP1 = tmem + 384;
 
+  long long t_tfull_out = 0;
   if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
     // Both roles below run with WARP-UNIFORM control flow (all 32 lanes wait on the barriers and walk
@@ -162,8 +166,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_group_kernel(const FusedPar
         slot = wrap ? 0u : slot + 1u;
         phase ^= wrap ? 1u : 0u;
       };
-      auto load_w = [&](int widx, uint32_t bytes) {
+      long long t_empty = 0;
+      auto wait_empty = [&]() {
+        const long long t0 = PROF ? clock64() : 0;
         tc::mbar_wait_trap(bar0 + (B_EMPTY + slot) * 8, phase ^ 1, WAIT_CYCLES, p.status, 1);
+        if (PROF) t_empty += clock64() - t0;
+      };
+      auto load_w = [&](int widx, uint32_t bytes) {
+        wait_empty();
         if (tc::elect_one()) {
           const uint32_t fb = bar0 + (B_FULL + slot) * 8;
           tc::mbar_arrive_expect_tx_addr(fb, bytes);
@@ -173,7 +183,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_group_kernel(const FusedPar
         advance();
       };
       auto load_cond = [&](int kb) {   // cond channels [64kb, 64kb+64) of the tile's 128 frames
-        tc::mbar_wait_trap(bar0 + (B_EMPTY + slot) * 8, phase ^ 1, WAIT_CYCLES, p.status, 1);
+        wait_empty();
         if (tc::elect_one()) {
           const uint32_t fb = bar0 + (B_FULL + slot) * 8;
           tc::mbar_arrive_expect_tx_addr(fb, SLOT_BYTES);
@@ -204,6 +214,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_group_kernel(const FusedPar
         for (int i = 0; i < 8; ++i) load_w(W_SKIPP + i, SLOT_BYTES);
         for (int i = 0; i < 4; ++i) load_w(W_OUT + i, SLOT_BYTES);
       }
+      if (PROF && lane == 0) { p.prof[tile * 16 + 12] = t_empty; p.prof[tile * 16 + 13] = clock64() - t_start; }
     } else if (warp == 1) {
       // =========================== MMA ISSUER ===========================
       uint32_t slot = 0, phase = 0;
@@ -220,8 +231,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_group_kernel(const FusedPar
         slot = wrap ? 0u : slot + 1u;
         phase ^= wrap ? 1u : 0u;
       };
+      long long t_full = 0, t_temp = 0, t_ar = 0, t_gr = 0;
       auto wait_full = [&]() {
+        const long long t0 = PROF ? clock64() : 0;
         tc::mbar_wait_trap(bar0 + (B_FULL + slot) * 8, phase, WAIT_CYCLES, p.status, 2);
+        if (PROF) t_full += clock64() - t0;
         tc::tc_fence_after();
       };
       // one weight slot = NK k-steps of K=16 with the A operand from a resident tile (descriptor a0)
@@ -267,7 +281,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_group_kernel(const FusedPar
         advance();
       };
       auto temp_acquire = [&](uint32_t tb) {   // wait until the epilogue has drained the previous use of buffer tb
+        const long long t0 = PROF ? clock64() : 0;
         tc::mbar_wait_trap(bar0 + (B_TEMPTY + tb) * 8, ((n_use >> 1) + 1) & 1, WAIT_CYCLES, p.status, 2);
+        if (PROF) t_temp += clock64() - t0;
         tc::tc_fence_after();
       };
       auto temp_publish = [&](uint32_t tb) {
@@ -276,7 +292,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_group_kernel(const FusedPar
         ++n_use;
       };
       auto wait_bar = [&](uint32_t bar, uint32_t n) {
+        const long long t0 = PROF ? clock64() : 0;
         tc::mbar_wait_trap(bar0 + bar * 8, n & 1, WAIT_CYCLES, p.status, 2);
+        if (PROF) { if (bar == B_AREADY) t_ar += clock64() - t0; else t_gr += clock64() - t0; }
         tc::tc_fence_after();
       };
       auto tm_t = [&](uint32_t tb) { return TM_TEMP0 + tb * 128u; };
@@ -358,6 +376,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_group_kernel(const FusedPar
         for (int j = 0; j < 4; ++j) mma_w4(dG + ((j * 8 * G_LBO) >> 4), G_K16, tm_t(0), j ? 1u : 0u);
         temp_publish(0);
       }
+      if (PROF && lane == 0) {
+        long long* q = p.prof + tile * 16;
+        q[0] = t_full; q[1] = t_temp; q[2] = t_ar; q[3] = t_gr; q[4] = clock64() - t_start;
+      }
     }
   } else {
     // =========================== EPILOGUE (warps 4..11) ===========================
@@ -376,8 +398,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_group_kernel(const FusedPar
     uint32_t n_use = 0;              // temp-buffer uses so far (alternate 0,1,0,1,...)
     float u[128];                    // fp32 residual stream: channels 128c + 64h + j at index 64c + j
 
+    long long t_tfull = 0;
     auto temp_wait = [&](int tb) {
+      const long long t0 = PROF ? clock64() : 0;
       tc::mbar_wait_trap(tc::smem_u32(&bars[B_TFULL + tb]), (n_use >> 1) & 1, WAIT_CYCLES, p.status, 4);
+      if (PROF) t_tfull += clock64() - t0;
       ++n_use;
       tc::tc_fence_after();
     };
@@ -650,8 +675,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_group_kernel(const FusedPar
       }
       temp_release(0);
     }
+    if (PROF) t_tfull_out = t_tfull;
   }
 
+  if (PROF && warp == 4 && lane == 0) { p.prof[tile * 16 + 8] = t_tfull_out; p.prof[tile * 16 + 9] = clock64() - t_start; }
   // ---- teardown ----
   tc::tc_fence_before();
   __syncthreads();
@@ -866,7 +893,7 @@ int bf16_denoiser(const mgb_model_dims& d, const void* packed, const float* x, c
 
   static bool attr_set = false;
   if (!attr_set) {
-    MGB_CUDA_CHECK(cudaFuncSetAttribute(fused_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+    MGB_CUDA_CHECK(cudaFuncSetAttribute(fused_group_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
     attr_set = true;
   }
   if (!cond_ready) {
@@ -907,7 +934,27 @@ int bf16_denoiser(const mgb_model_dims& d, const void* packed, const float* x, c
     p.U_in = Ubuf[g & 1];
     p.U_out = Ubuf[(g + 1) & 1];
     prof_begin(s);
-    fused_group_kernel<<<B * p.tiles_per_utt, NTHREADS, SMEM_TOTAL, s>>>(p);
+    static const bool do_prof = getenv("MGB_PROFILE") != nullptr;
+    if (do_prof) {
+      const int ntile = B * p.tiles_per_utt;
+      long long* dprof = nullptr;
+      cudaMalloc(&dprof, (size_t)ntile * 16 * sizeof(long long));
+      cudaMemset(dprof, 0, (size_t)ntile * 16 * sizeof(long long));
+      p.prof = dprof;
+      cudaFuncSetAttribute(fused_group_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL);
+      fused_group_kernel<true><<<ntile, NTHREADS, SMEM_TOTAL, s>>>(p);
+      cudaStreamSynchronize(s);
+      long long* h = (long long*)malloc((size_t)ntile * 16 * sizeof(long long));
+      cudaMemcpy(h, dprof, (size_t)ntile * 16 * sizeof(long long), cudaMemcpyDeviceToHost);
+      double a[16] = {0};
+      for (int i = 0; i < ntile; ++i) for (int k = 0; k < 16; ++k) a[k] += (double)h[i * 16 + k] / ntile;
+      fprintf(stderr, "[mgb profile] layers [%d,%d) tiles %d | MMA warp: total %.0f wait_full %.0f wait_temp %.0f wait_aready %.0f "
+              "wait_gready %.0f | epilogue w4: total %.0f wait_tfull %.0f | producer: total %.0f wait_empty %.0f (cycles, mean per tile)\n",
+              p.lb, p.le, ntile, a[4], a[0], a[1], a[2], a[3], a[9], a[8], a[13], a[12]);
+      free(h); cudaFree(dprof); p.prof = nullptr;
+    } else {
+      fused_group_kernel<false><<<B * p.tiles_per_utt, NTHREADS, SMEM_TOTAL, s>>>(p);
+    }
     prof_end(s);
     note_launch();
   }

@@ -104,10 +104,15 @@ static __global__ void __launch_bounds__(128) step_mlp_layer_kernel(const int64_
 #pragma unroll
   for (int u = 0; u < MLP_UB; ++u) acc[u] = 0.f;
   if (n < N) {
-    for (int k = 0; k < K; ++k) {
-      const float w = wt[(size_t)k * N + n];
+    for (int k0 = 0; k0 < K; k0 += 16) {     // K % 16 == 0; 16 independent weight loads in flight
+      float w[16];
 #pragma unroll
-      for (int u = 0; u < MLP_UB; ++u) acc[u] = fmaf(w, xs[u * K + k], acc[u]);
+      for (int i = 0; i < 16; ++i) w[i] = __ldg(wt + (size_t)(k0 + i) * N + n);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+#pragma unroll
+        for (int u = 0; u < MLP_UB; ++u) acc[u] = fmaf(w[i], xs[u * K + k0 + i], acc[u]);
+      }
     }
 #pragma unroll
     for (int u = 0; u < MLP_UB; ++u) {
@@ -152,10 +157,15 @@ static __global__ void __launch_bounds__(256) proj_table_kernel(const float* __r
     __syncthreads();
     const float* wt = wt0 + (size_t)l * w_stride;
     if (c < C) {
-      for (int k = 0; k < Kin; ++k) {
-        const float w = wt[(size_t)k * C + c];
+      for (int k0 = 0; k0 < Kin; k0 += 16) {   // Kin % 16 == 0
+        float w[16];
 #pragma unroll
-        for (int u = 0; u < TAB_UB; ++u) acc[u] = fmaf(w, vs[u * Kin + k], acc[u]);
+        for (int i = 0; i < 16; ++i) w[i] = __ldg(wt + (size_t)(k0 + i) * C + c);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+#pragma unroll
+          for (int u = 0; u < TAB_UB; ++u) acc[u] = fmaf(w[i], vs[u * Kin + k0 + i], acc[u]);
+        }
       }
     }
   }

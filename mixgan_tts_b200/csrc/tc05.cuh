@@ -205,3 +205,89 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
 }
 
 }  // namespace tc
+
+// =====================================================================================================
+// 2-CTA (cta_group::2) variants: a CTA pair of one cluster shares every tcgen05.mma (M = 256 = 2 x 128
+// rows, each CTA's accumulator rows in its own TMEM, each CTA's shared memory supplying its own A rows
+// and HALF of the B rows).  Only the leader CTA (cluster rank 0) issues MMAs and commits.
+// =====================================================================================================
+namespace tc {
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {   // every thread of every CTA in the cluster
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cta address -> shared::cluster address of the same offset in CTA `rank`
+__device__ __forceinline__ uint32_t mapa(uint32_t smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_cluster_v4(uint32_t cluster_addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(cluster_addr), "r"(a), "r"(b), "r"(c), "r"(d)
+               : "memory");
+}
+// arrive on a barrier that may live in another CTA of the cluster (release at cluster scope)
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar_addr) : "memory");
+}
+// wait on a local barrier whose arrivals may come from the peer CTA (acquire at cluster scope)
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar_addr, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}\n"
+      : "=r"(ok)
+      : "r"(bar_addr), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster_trap(uint32_t bar_addr, uint32_t parity, long long max_cycles,
+                                                       int* status, int code) {
+  if (mbar_try_wait_cluster(bar_addr, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait_cluster(bar_addr, parity)) {
+    if (clock64() - t0 > max_cycles) {
+      if (status) atomicOr(status, code);
+      __threadfence_system();
+      __trap();
+    }
+  }
+}
+// generic-proxy writes (local or remote shared memory) -> visible to the async proxy
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+template <int kCols>
+__device__ __forceinline__ void tmem_alloc_2cta(uint32_t* slot_in_smem) {   // same warp index in both CTAs
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot_in_smem)),
+               "n"(kCols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <int kCols>
+__device__ __forceinline__ void tmem_dealloc_2cta(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2cta(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive (once all prior MMAs of this thread completed) on the barrier at this offset in BOTH CTAs
+__device__ __forceinline__ void umma_commit_2cta_mc(uint32_t bar_addr) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(bar_addr), "h"((uint16_t)3)
+      : "memory");
+}
+
+}  // namespace tc

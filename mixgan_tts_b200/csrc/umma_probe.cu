@@ -91,6 +91,77 @@ __global__ void __launch_bounds__(128, 1) umma_probe_kernel(const ProbeArgs p) {
   if (warp == 0) tc::tmem_dealloc<256>(tmem);
 }
 
+
+// ---- 2-CTA probe: cluster of two CTAs, M = 256 (128 rows per CTA), N = n, B rows split in halves ----
+struct Probe2Args {
+  const uint8_t* a_img;   // [2][a_bytes]: per-CTA A image (128 rows)
+  const uint8_t* b_img;   // [2][b_bytes]: per-CTA B image (n/2 rows)
+  int a_bytes, b_bytes, b_off;
+  int a_lbo, a_sbo, a_kadv, b_lbo, b_sbo, b_kadv;
+  int n, ksteps;
+  float* d_out;           // [256][n]
+  int* status;
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) umma_probe2_kernel(const Probe2Args p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bar_load, bar_peer, bar_mma;
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = tc::cluster_ctarank();
+
+  if (warp == 0) tc::tmem_alloc_2cta<256>(&tmem_slot);
+  if (tid == 32) {
+    tc::mbar_init(&bar_load, 1);
+    tc::mbar_init(&bar_peer, 1);
+    tc::mbar_init(&bar_mma, 1);
+    tc::fence_barrier_init();
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::cluster_sync_all();
+  tc::tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+
+  if (tid == 0) {
+    tc::mbar_arrive_expect_tx(&bar_load, (uint32_t)(p.a_bytes + p.b_bytes));
+    tc::bulk_g2s(smem, p.a_img + (size_t)rank * p.a_bytes, (uint32_t)p.a_bytes, &bar_load);
+    tc::bulk_g2s(smem + p.b_off, p.b_img + (size_t)rank * p.b_bytes, (uint32_t)p.b_bytes, &bar_load);
+  }
+  // every CTA waits for its own operands; CTA 1 then tells the leader
+  tc::mbar_wait_trap(tc::smem_u32(&bar_load), 0, kProbeTimeout, p.status, 1);
+  __syncthreads();
+  if (rank == 1 && tid == 0) tc::mbar_arrive_cluster(tc::mapa(tc::smem_u32(&bar_peer), 0));
+  if (rank == 0 && warp == 0) {
+    tc::mbar_wait_cluster_trap(tc::smem_u32(&bar_peer), 0, kProbeTimeout, p.status, 2);
+    tc::tc_fence_after();
+    if (tc::elect_one()) {
+      const uint32_t idesc = tc::make_idesc_bf16(256, p.n);
+      const uint32_t a0 = tc::smem_u32(smem), b0 = tc::smem_u32(smem + p.b_off);
+      for (int k = 0; k < p.ksteps; ++k)
+        tc::umma_bf16_2cta(tmem, tc::make_smem_desc(a0 + k * p.a_kadv, p.a_lbo, p.a_sbo),
+                           tc::make_smem_desc(b0 + k * p.b_kadv, p.b_lbo, p.b_sbo), idesc, k > 0 ? 1u : 0u);
+      tc::umma_commit_2cta_mc(tc::smem_u32(&bar_mma));
+    }
+    __syncwarp();
+  }
+  tc::mbar_wait_trap(tc::smem_u32(&bar_mma), 0, kProbeTimeout, p.status, 4);
+  tc::tc_fence_after();
+  const int row = (int)rank * 128 + warp * 32 + lane;
+  for (int c0 = 0; c0 < p.n; c0 += 32) {
+    uint32_t r[32];
+    tc::tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, r);
+    tc::tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (c0 + j < p.n) p.d_out[(size_t)row * p.n + c0 + j] = __uint_as_float(r[j]);
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::cluster_sync_all();
+  if (warp == 0) tc::tmem_dealloc_2cta<256>(tmem);
+}
+
 }  // namespace
 }  // namespace mgb
 
@@ -116,6 +187,29 @@ extern "C" int mgb_probe_umma(const void* a_img, int a_bytes, const void* b_img,
   MGB_REQUIRE(smem <= 200 * 1024, MGB_E_ARG, "operand images too large for shared memory");
   MGB_CUDA_CHECK(cudaFuncSetAttribute(umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   umma_probe_kernel<<<1, 128, smem, static_cast<cudaStream_t>(stream)>>>(p);
+  MGB_LAUNCH_CHECK();
+  return MGB_OK;
+}
+
+extern "C" int mgb_probe_umma_2cta(const void* a_img, int a_bytes, const void* b_img, int b_bytes, int a_lbo, int a_sbo,
+                                   int a_kadv, int b_lbo, int b_sbo, int b_kadv, int n, int ksteps, float* d_out,
+                                   int* status_out, void* stream) {
+  MGB_REQUIRE(a_img && b_img && d_out && status_out, MGB_E_ARG, "NULL pointer argument");
+  MGB_REQUIRE(a_bytes > 0 && b_bytes > 0 && a_bytes % 16 == 0 && b_bytes % 16 == 0, MGB_E_ARG,
+              "operand images must be positive multiples of 16 bytes");
+  MGB_REQUIRE(n >= 32 && n <= 256 && n % 32 == 0 && ksteps >= 1 && ksteps <= 64, MGB_E_ARG, "bad n/ksteps");
+  MGB_REQUIRE(((a_lbo | a_sbo | a_kadv | b_lbo | b_sbo | b_kadv) & 15) == 0, MGB_E_ARG,
+              "descriptor byte fields must be multiples of 16");
+  if (int rc = check_arch()) return rc;
+  Probe2Args p{};
+  p.a_img = static_cast<const uint8_t*>(a_img); p.b_img = static_cast<const uint8_t*>(b_img);
+  p.a_bytes = a_bytes; p.b_bytes = b_bytes; p.b_off = (int)align_up((size_t)a_bytes, 1024);
+  p.a_lbo = a_lbo; p.a_sbo = a_sbo; p.a_kadv = a_kadv; p.b_lbo = b_lbo; p.b_sbo = b_sbo; p.b_kadv = b_kadv;
+  p.n = n; p.ksteps = ksteps; p.d_out = d_out; p.status = status_out;
+  const size_t smem = (size_t)p.b_off + align_up((size_t)b_bytes, 1024);
+  MGB_REQUIRE(smem <= 200 * 1024, MGB_E_ARG, "operand images too large for shared memory");
+  MGB_CUDA_CHECK(cudaFuncSetAttribute(umma_probe2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  umma_probe2_kernel<<<2, 128, smem, static_cast<cudaStream_t>(stream)>>>(p);
   MGB_LAUNCH_CHECK();
   return MGB_OK;
 }

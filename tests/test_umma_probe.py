@@ -80,3 +80,29 @@ def test_row_shift_by_start_address(shift):
     err0 = (D - _expect(A, Bm, 0)).abs().max().item()
     _report(f"row shift {shift}: status={st} err={err:.3e} (err vs unshifted {err0:.3e})")
     assert st == 0 and err < 1e-3
+
+
+@pytest.mark.parametrize("n,ksteps", [(128, 1), (128, 8), (256, 4), (64, 4)])
+def test_two_cta_pair_conventions(n, ksteps):
+    """cta_group::2: M = 256 split by rows across the CTA pair, B split by rows in halves (n/2 each),
+    each CTA reads its accumulator rows from its own TMEM; commit multicast reaches both CTAs."""
+    lib = _lib.load()
+    K = 16 * ksteps
+    g = torch.Generator(device="cpu").manual_seed(n + ksteps)
+    A = (torch.randn(256, K, generator=g) * 0.5).bfloat16().cuda()
+    Bm = (torch.randn(n, K, generator=g) * 0.5).bfloat16().cuda()
+    a_img = torch.stack([_image(A[:128]), _image(A[128:])]).contiguous()
+    b_img = torch.stack([_image(Bm[:n // 2]), _image(Bm[n // 2:])]).contiguous()
+    D = torch.full((256, n), float("nan"), device="cuda")
+    st = torch.zeros(1, dtype=torch.int32, device="cuda")
+    rc = lib.mgb_probe_umma_2cta(_lib.ptr(a_img), 128 * K * 2, _lib.ptr(b_img), (n // 2) * K * 2,
+                                 128 * 16, 128, 2 * 128 * 16, (n // 2) * 16, 128, 2 * (n // 2) * 16,
+                                 n, ksteps, _lib.ptr(D), _lib.ptr(st), C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    _lib.check(rc, "mgb_probe_umma_2cta")
+    torch.cuda.synchronize()
+    ref = A.float() @ Bm.float().t()
+    err = (D - ref).abs().max().item()
+    err_top = (D[:128] - ref[:128]).abs().max().item()
+    err_bot = (D[128:] - ref[128:]).abs().max().item()
+    _report(f"2cta n={n} ksteps={ksteps}: status={int(st.item())} err={err:.3e} (rows 0-127 {err_top:.3e}, rows 128-255 {err_bot:.3e})")
+    assert int(st.item()) == 0 and err < 1e-3

@@ -173,6 +173,14 @@ int mgb_probe_umma_2cta(const void* a_img, int a_bytes, const void* b_img, int b
                         int a_lbo, int a_sbo, int a_kadv, int b_lbo, int b_sbo, int b_kadv,
                         int n, int ksteps, float* d_out, int* status_out, void* stream);
 
+/* tcgen05 issue-rate probe (scripts/umma_rate.py): `grid` CTAs (CTA pairs when cta2 != 0) each issue
+ * reps*ksteps tcgen05.mma (M = 128, or 256 for a pair; N = n; K = 16) on zeroed shared-memory operands with
+ * the given K-major descriptor fields and accumulate into nacc rotating TMEM tiles; cycles_out[i] (device,
+ * int64, one per launched CTA) receives the SM cycles from the first issue to the completion of the commit. */
+int mgb_probe_umma_rate(int cta2, int grid, int n, int ksteps, int reps, int nacc, int a_lbo, int a_sbo,
+                        int a_kadv, int b_lbo, int b_sbo, int b_kadv, int b_off, long long* cycles_out,
+                        int* status_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

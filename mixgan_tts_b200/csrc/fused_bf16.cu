@@ -1,10 +1,13 @@
 // bf16 tensor-core path of the Denoiser (MGB_PREC_BF16): a group of residual blocks is chained in
-// ONE kernel per 128-frame tile.  Weights stream from L2 through a ring of 16 KB shared-memory
-// slots filled by the TMA engine (1-D bulk copies of pre-packed operand images); every convolution
-// is a set of tcgen05.mma (M=128 frames, N=128 channels, K=16) accumulating in TMEM; the gate, the
+// ONE kernel per 256-row tile, and a tile is owned by a CTA PAIR (a 2-CTA cluster on one TPC).
+// Every convolution is a set of tcgen05.mma.cta_group::2 instructions (M = 256 rows = 128 per CTA,
+// N = 128 or 256 channels, K = 16) issued by the leader CTA; each CTA keeps its own 128 rows of every
+// activation tile in its shared memory and streams only HALF of every weight tile from L2 (the
+// tensor cores of the pair exchange the halves), so shared-memory operand traffic per FLOP and
+// L2->SM weight traffic are half of a single-CTA design.  Accumulators live in TMEM; the gate, the
 // residual update, the conditioner add and (in the tail) the skip/out projections and the posterior
-// update are epilogues that read TMEM with tcgen05.ld.  Activations never leave the SM inside a
-// group: the conv input and the gate output live in shared memory as bf16 MMA operands, the fp32
+// update are epilogues that read TMEM with tcgen05.ld.  Activations never leave the SM pair inside
+// a group: the conv input and the gate output live in shared memory as bf16 MMA operands, the fp32
 // residual stream lives in the epilogue threads' registers, the skip sum accumulates in TMEM.
 //
 // Reference behaviour restated: ResidualBlock.forward model/blocks.py:1157-1176, Denoiser.forward
@@ -19,12 +22,17 @@
 //     k_l     = (bo_x,l - bc_l - s_l)/sqrt(2) + d_{l+1} + bc_{l+1} + s_{l+1}      (per utterance)
 // so one K=512 GEMM per block produces the residual update and the conditioner projection at once.
 //
-// Tiling.  A kernel launch runs layers [lb, le) for every tile; a tile is 128 consecutive frames of
-// one utterance of which the middle 128 - 2*(le-lb) are exact after le-lb k=3 convolutions (halo
-// recompute).  Between groups u (fp32) and the partial skip sum are spilled to HBM.
+// Row space.  All utterances of the batch are laid on ONE row axis: utterance b owns rows
+// [b*Tg, b*Tg + T) with Tg = T + 1; the row between two utterances (and every row outside the
+// batch) is a zero row at every layer, which is exactly the reference's zero padding of the k=3
+// convolution (blocks.py:1144).  Tile p covers rows [p*V - halo, p*V - halo + 256) of which the
+// middle V = 256 - 2*halo are exact after `halo` = (layers in the group) k=3 convolutions.  Between
+// groups u (fp32) and the partial skip sum are spilled to HBM.
 //
-// Warp roles (384 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
-// warps 4..11 = epilogue (thread = one frame row x half of a 128-column chunk).
+// Warp roles (384 threads per CTA): warp 0 = TMA producer (both CTAs), warp 1 = MMA issuer in the
+// leader CTA / "relay" in the peer CTA (forwards the peer's ring-slot completions to the leader's
+// barriers), warp 2 = TMEM allocator, warps 4..11 = epilogue (thread = one row x half of a
+// 128-column chunk).
 #include <cstdlib>
 
 #include "common.cuh"
@@ -37,36 +45,42 @@ namespace {
 using namespace smallops;
 
 constexpr int C = 256;
-constexpr int SLOT_BYTES = 16384;      // one operand image: [8 k-chunks][128 rows][8 bf16]
-constexpr int NSLOTS = 6;
-constexpr int A_ROWS = 130;            // 128 tile rows + one zero/halo row each side
+constexpr int SLOT_BYTES = 8192;       // one ring slot: a weight HALF tile or a cond tile of K=32
+constexpr int NSLOTS = 12;
+constexpr int A_ROWS = 130;            // 128 tile rows + one halo row each side
 constexpr uint32_t A_LBO = A_ROWS * 16;
 constexpr uint32_t G_LBO = 128 * 16;
-constexpr uint32_t W_LBO = 128 * 16;
+constexpr uint32_t W128_LBO = 64 * 16;   // weight half tile with 64 rows  (N = 128 MMAs), K = 64 per slot
+constexpr uint32_t W256_LBO = 128 * 16;  // weight half tile with 128 rows (N = 256 MMAs) and cond tiles, K = 32 per slot
 constexpr uint32_t SBO = 128;
 constexpr int SMEM_A = 32 * A_LBO;
 constexpr int SMEM_G = 32 * G_LBO;
 constexpr int SMEM_SLOTS = NSLOTS * SLOT_BYTES;
-constexpr int SMEM_BARS = 256;
+constexpr int SMEM_BARS = 512;
 constexpr int SMEM_TOTAL = SMEM_A + SMEM_G + SMEM_SLOTS + SMEM_BARS;
 constexpr int NTHREADS = 384;
+constexpr int TILE_ROWS = 256;         // rows per CTA pair
 constexpr int MAX_GROUP_LAYERS = 24;
-constexpr int COND_PAD_LO = 32;        // zero rows in front of each utterance in the cond image
+constexpr int COND_PAD_LO = 32;        // zero rows in front of the cond image (>= MAX_GROUP_LAYERS)
+constexpr int COND_PAD_HI = 288;       // zero rows behind it (>= TILE_ROWS + MAX_GROUP_LAYERS)
 constexpr long long WAIT_CYCLES = 400000000LL;   // ~0.2 s: a protocol bug ends the kernel, never hangs it
 
-// weight-image slot indices (see pack_images_kernel)
-constexpr int W_IN = 0, W_P0 = 4, W_SKIPP = 12, W_OUT = 20, W_LAYER0 = 24, W_PER_LAYER = 72;
+// weight-stream slot indices (see pack_images_kernel); each CTA rank has its own image of every slot
+constexpr int W_IN = 0, W_P0 = 3, W_SKIPP = 11, W_OUT = 19, W_LAYER0 = 23, W_PER_LAYER = 72;
+constexpr int WL_CONV = 0, WL_SKIPA = 48, WL_RCOND = 50, WL_RG = 58, WL_SKIPB = 66;
 
 constexpr float RSQRT2 = 0.70710678118654752440f;
 
 // barrier indices
 enum { B_FULL = 0, B_EMPTY = NSLOTS, B_TFULL = 2 * NSLOTS, B_TEMPTY = B_TFULL + 2, B_AREADY = B_TEMPTY + 2,
        B_GREADY = B_AREADY + 1, B_SKIPDONE = B_GREADY + 4, B_COUNT = B_SKIPDONE + 1 };
+static_assert(B_COUNT * 8 + 16 <= SMEM_BARS, "barrier block too small");
 
 struct FusedParams {
-  const uint8_t* wimg;          // weight slot images
-  const __nv_bfloat16* condT;   // [B][32][Tp][8] bf16, rows shifted by COND_PAD_LO, zero outside [0,T)
-  int Tp;
+  const uint8_t* wimg;          // [2 ranks][slots][SLOT_BYTES] weight stream images
+  size_t wimg_rank_stride;
+  const __nv_bfloat16* condT;   // [32][Rp][8] bf16 on the row axis shifted by COND_PAD_LO, zero outside utterances
+  int Rp;
   const float* x_t;             // [B][M][T]
   const float* noise;           // [B][M][T] or null
   float* x_prev;                // [B][M][T] or null
@@ -84,9 +98,9 @@ struct FusedParams {
   const float* U_in;            // [B*T][C] fp32 u spilled by the previous group
   float* U_out;                 // [B*T][C] fp32 u for the next group (ping-pong: neighbours read U_in meanwhile)
   float* S;                     // [B*T][C] fp32 partial skip sum between groups
-  int B, T, L, lb, le, V, halo, tiles_per_utt;
+  int B, T, Tg, R, L, lb, le, V, halo;
   int* status;
-  long long* prof;              // debug (MGB_PROFILE): per-tile cycle counters, 16 per tile
+  long long* prof;              // debug (MGB_PROFILE): per-CTA cycle counters, 16 per CTA
 };
 
 __device__ __forceinline__ float tanh_approx(float x) {
@@ -102,16 +116,8 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
-struct Ring {
-  int slot = 0;
-  uint32_t phase = 0;
-  __device__ __forceinline__ void advance() {
-    if (++slot == NSLOTS) { slot = 0; phase ^= 1; }
-  }
-};
-
 template <bool PROF>
-__global__ void __launch_bounds__(NTHREADS, 1) fused_group_kernel(const FusedParams p) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_pair_kernel(const FusedParams p) {
   const long long t_start = PROF ? clock64() : 0;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sA = smem;
@@ -121,46 +127,57 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_group_kernel(const FusedPar
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + B_COUNT);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int tile = blockIdx.x;
-  const int b = tile / p.tiles_per_utt;
-  const int f0 = (tile - b * p.tiles_per_utt) * p.V - p.halo;   // frame of tile row 0
+  const uint32_t rank = tc::cluster_ctarank();          // 0 = leader (issues the MMAs), 1 = peer
+  const int pair = blockIdx.x >> 1;
+  const int g0 = pair * p.V - p.halo + 128 * (int)rank;   // row (on the batch row axis) of this CTA's tile row 0
   const bool first_group = p.lb == 0, last_group = p.le == p.L;
 
   // ---- setup -------------------------------------------------------------------------------
-  {  // zero the operand tiles (halo rows of A stay zero for the whole kernel)
+  {  // zero the operand tiles (outer halo rows of A stay zero for the whole kernel)
     uint4* z = reinterpret_cast<uint4*>(smem);
     for (int i = tid; i < (SMEM_A + SMEM_G) / 16; i += NTHREADS) z[i] = make_uint4(0u, 0u, 0u, 0u);
   }
-  if (warp == 2) tc::tmem_alloc<512>(tmem_slot);
+  if (warp == 2) tc::tmem_alloc_2cta<512>(tmem_slot);
   if (tid == 0) {
-    for (int i = 0; i < NSLOTS; ++i) { tc::mbar_init(&bars[B_FULL + i], 1); tc::mbar_init(&bars[B_EMPTY + i], 1); }
-    for (int i = 0; i < 2; ++i) { tc::mbar_init(&bars[B_TFULL + i], 1); tc::mbar_init(&bars[B_TEMPTY + i], 8); }
-    tc::mbar_init(&bars[B_AREADY], 8);
-    for (int i = 0; i < 4; ++i) tc::mbar_init(&bars[B_GREADY + i], 8);
+    for (int i = 0; i < NSLOTS; ++i) {
+      tc::mbar_init(&bars[B_FULL + i], rank == 0 ? 2 : 1);   // leader: own TMA + the peer's relay
+      tc::mbar_init(&bars[B_EMPTY + i], 1);
+    }
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&bars[B_TFULL + i], 1); tc::mbar_init(&bars[B_TEMPTY + i], 16); }
+    tc::mbar_init(&bars[B_AREADY], 16);
+    for (int i = 0; i < 4; ++i) tc::mbar_init(&bars[B_GREADY + i], 16);
     tc::mbar_init(&bars[B_SKIPDONE], 1);
     tc::fence_barrier_init();
   }
   tc::fence_proxy_async_smem();
   tc::tc_fence_before();
   __syncthreads();
+  tc::cluster_sync_all();            // both CTAs' barriers are initialised before any remote arrive
   tc::tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t TM_SKIP = tmem, TM_TEMP0 = tmem + 256, TM_TEMP1 = tmem + 384;
+  const uint32_t TM_SKIP = tmem, TM_TEMP0 = tmem + 256;
+
+  const uint32_t bar0 = tc::smem_u32(bars);
+  const uint32_t lead_bar0 = tc::mapa(bar0, 0);          // the leader's barrier block (shared::cluster address)
+  const uint32_t slots0 = tc::smem_u32(sSlots);
+
+  // number of ring-slot loads of this launch (the producer, the relay and the MMA issuer walk the same sequence)
+  int n_loads = (first_group ? 3 + 16 : 0) + (last_group ? 12 : 0);
+  for (int l = p.lb; l < p.le; ++l) n_loads += (l < p.L - 1) ? 80 : 56;
 
   long long t_tfull_out = 0;
   if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
-    // Both roles below run with WARP-UNIFORM control flow (all 32 lanes wait on the barriers and walk
+    // The roles below run with WARP-UNIFORM control flow (all 32 lanes wait on the barriers and walk
     // the schedule); only the instructions that must come from one thread (bulk copies, tcgen05.mma,
-    // tcgen05.commit, expect_tx) are predicated with elect_one().  Waits never feed state back into the
-    // loops (a timeout traps), so ring positions and descriptors stay in uniform registers.
-    const uint32_t bar0 = tc::smem_u32(bars);
-    const uint32_t slots0 = tc::smem_u32(sSlots);
+    // tcgen05.commit, expect_tx, remote arrives) are predicated with elect_one().  Waits never feed state
+    // back into the loops (a timeout traps), so ring positions and descriptors stay in uniform registers.
     if (warp == 0) {
-      // =========================== TMA PRODUCER ===========================
+      // =========================== TMA PRODUCER (both CTAs) ===========================
       uint32_t slot = 0, phase = 0;
-      const uint8_t* condb = reinterpret_cast<const uint8_t*>(p.condT) +
-                             ((size_t)b * 32 * p.Tp + (size_t)(f0 + COND_PAD_LO)) * 16;
+      const uint8_t* wimg = p.wimg + (size_t)rank * p.wimg_rank_stride;
+      const uint8_t* condb = reinterpret_cast<const uint8_t*>(p.condT) + (size_t)(g0 + COND_PAD_LO) * 16;
+      const size_t cond_chunk = (size_t)p.Rp * 16;
       auto advance = [&]() {
         const bool wrap = slot == NSLOTS - 1;
         slot = wrap ? 0u : slot + 1u;
@@ -177,52 +194,62 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_group_kernel(const FusedPar
         if (tc::elect_one()) {
           const uint32_t fb = bar0 + (B_FULL + slot) * 8;
           tc::mbar_arrive_expect_tx_addr(fb, bytes);
-          tc::bulk_g2s_addr(slots0 + slot * SLOT_BYTES, p.wimg + (size_t)widx * SLOT_BYTES, bytes, fb);
+          tc::bulk_g2s_addr(slots0 + slot * SLOT_BYTES, wimg + (size_t)widx * SLOT_BYTES, bytes, fb);
         }
         __syncwarp();
         advance();
       };
-      auto load_cond = [&](int kb) {   // cond channels [64kb, 64kb+64) of the tile's 128 frames
+      auto load_cond = [&](int m) {   // cond channels [32m, 32m+32) of this CTA's 128 rows
         wait_empty();
         if (tc::elect_one()) {
           const uint32_t fb = bar0 + (B_FULL + slot) * 8;
           tc::mbar_arrive_expect_tx_addr(fb, SLOT_BYTES);
 #pragma unroll
-          for (int k8 = 0; k8 < 8; ++k8)
-            tc::bulk_g2s_addr(slots0 + slot * SLOT_BYTES + k8 * 2048, condb + (size_t)(kb * 8 + k8) * p.Tp * 16, 2048, fb);
+          for (int k8 = 0; k8 < 4; ++k8)
+            tc::bulk_g2s_addr(slots0 + slot * SLOT_BYTES + k8 * 2048, condb + (size_t)(m * 4 + k8) * cond_chunk, 2048, fb);
         }
         __syncwarp();
         advance();
       };
       if (first_group) {
-        for (int c = 0; c < 2; ++c) { load_w(W_IN + 2 * c, SLOT_BYTES); load_w(W_IN + 2 * c + 1, 4096); }
-        for (int c = 0; c < 2; ++c)
-          for (int j = 0; j < 4; ++j) { load_cond(j); load_w(W_P0 + 4 * c + j, SLOT_BYTES); }
+        load_w(W_IN, SLOT_BYTES); load_w(W_IN + 1, SLOT_BYTES); load_w(W_IN + 2, 4096);
+        for (int m = 0; m < 8; ++m) { load_cond(m); load_w(W_P0 + m, SLOT_BYTES); }
       }
       for (int l = p.lb; l < p.le; ++l) {
         const int base = W_LAYER0 + l * W_PER_LAYER;
-        for (int i = 0; i < 48; ++i) load_w(base + i, SLOT_BYTES);
+        for (int i = 0; i < 50; ++i) load_w(base + i, SLOT_BYTES);          // conv (48) + skip j=0 (2)
         if (l < p.L - 1) {
-          for (int c = 0; c < 2; ++c) {
-            for (int j = 0; j < 4; ++j) { load_cond(j); load_w(base + 48 + c * 8 + j, SLOT_BYTES); }
-            for (int j = 0; j < 4; ++j) load_w(base + 48 + c * 8 + 4 + j, SLOT_BYTES);
-          }
+          for (int m = 0; m < 8; ++m) { load_cond(m); load_w(base + WL_RCOND + m, SLOT_BYTES); }
+          for (int m = 0; m < 8; ++m) load_w(base + WL_RG + m, SLOT_BYTES);
         }
-        for (int i = 0; i < 8; ++i) load_w(base + 64 + i, SLOT_BYTES);
+        for (int i = 0; i < 6; ++i) load_w(base + WL_SKIPB + i, SLOT_BYTES);
       }
       if (last_group) {
         for (int i = 0; i < 8; ++i) load_w(W_SKIPP + i, SLOT_BYTES);
         for (int i = 0; i < 4; ++i) load_w(W_OUT + i, SLOT_BYTES);
       }
-      if (PROF && lane == 0) { p.prof[tile * 16 + 12] = t_empty; p.prof[tile * 16 + 13] = clock64() - t_start; }
-    } else if (warp == 1) {
-      // =========================== MMA ISSUER ===========================
+      if (PROF && lane == 0) { p.prof[blockIdx.x * 16 + 12] = t_empty; p.prof[blockIdx.x * 16 + 13] = clock64() - t_start; }
+    } else if (warp == 1 && rank != 0) {
+      // =========================== RELAY (peer CTA) ===========================
+      // Forwards "my half of ring slot s has landed" to the leader's FULL[s] barrier.
       uint32_t slot = 0, phase = 0;
-      const uint32_t idesc = tc::make_idesc_bf16(128, 128);
+      for (int i = 0; i < n_loads; ++i) {
+        tc::mbar_wait_trap(bar0 + (B_FULL + slot) * 8, phase, WAIT_CYCLES, p.status, 8);
+        if (tc::elect_one()) tc::mbar_arrive_remote(lead_bar0 + (B_FULL + slot) * 8);
+        __syncwarp();
+        const bool wrap = slot == NSLOTS - 1;
+        slot = wrap ? 0u : slot + 1u;
+        phase ^= wrap ? 1u : 0u;
+      }
+    } else if (warp == 1) {
+      // =========================== MMA ISSUER (leader CTA) ===========================
+      uint32_t slot = 0, phase = 0;
+      const uint32_t idesc128 = tc::make_idesc_bf16(256, 128), idesc256 = tc::make_idesc_bf16(256, 256);
       // descriptor templates; a byte offset is added to the 14-bit start-address field (>> 4)
       const uint64_t dA = tc::make_smem_desc(tc::smem_u32(sA), A_LBO, SBO);
       const uint64_t dG = tc::make_smem_desc(tc::smem_u32(sG), G_LBO, SBO);
-      const uint64_t dS = tc::make_smem_desc(slots0, W_LBO, SBO);
+      const uint64_t dS128 = tc::make_smem_desc(slots0, W128_LBO, SBO);
+      const uint64_t dS256 = tc::make_smem_desc(slots0, W256_LBO, SBO);
       uint32_t n_use = 0;            // temp-buffer uses so far; they strictly alternate 0,1,0,1,...
       uint32_t n_aready = 0, n_gready = 0;
 
@@ -238,58 +265,59 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_group_kernel(const FusedPar
         if (PROF) t_full += clock64() - t0;
         tc::tc_fence_after();
       };
-      // one weight slot = NK k-steps of K=16 with the A operand from a resident tile (descriptor a0)
-      auto mma_w4 = [&](uint64_t a0, uint32_t a_kstep16, uint32_t d_tmem, uint32_t acc_first) {
+      // one N=128 weight slot = 4 k-steps of K=16 with the A operand from a resident tile (descriptor a0)
+      auto mma_w128 = [&](uint64_t a0, uint32_t a_kstep16, uint32_t d_tmem, uint32_t acc_first) {
         wait_full();
         if (tc::elect_one()) {
-          const uint64_t b0 = dS + (uint64_t)(slot * (SLOT_BYTES >> 4));
-          tc::umma_bf16(d_tmem, a0, b0, idesc, acc_first);
-          tc::umma_bf16(d_tmem, a0 + a_kstep16, b0 + (2 * W_LBO >> 4), idesc, 1u);
-          tc::umma_bf16(d_tmem, a0 + 2 * a_kstep16, b0 + 2 * (2 * W_LBO >> 4), idesc, 1u);
-          tc::umma_bf16(d_tmem, a0 + 3 * a_kstep16, b0 + 3 * (2 * W_LBO >> 4), idesc, 1u);
-          tc::umma_commit_addr(bar0 + (B_EMPTY + slot) * 8);
+          const uint64_t b0 = dS128 + (uint64_t)(slot * (SLOT_BYTES >> 4));
+          tc::umma_bf16_2cta(d_tmem, a0, b0, idesc128, acc_first);
+          tc::umma_bf16_2cta(d_tmem, a0 + a_kstep16, b0 + (2 * W128_LBO >> 4), idesc128, 1u);
+          tc::umma_bf16_2cta(d_tmem, a0 + 2 * a_kstep16, b0 + 2 * (2 * W128_LBO >> 4), idesc128, 1u);
+          tc::umma_bf16_2cta(d_tmem, a0 + 3 * a_kstep16, b0 + 3 * (2 * W128_LBO >> 4), idesc128, 1u);
+          tc::umma_commit_2cta_mc(bar0 + (B_EMPTY + slot) * 8);
         }
         __syncwarp();
         advance();
       };
-      auto mma_w1 = [&](uint64_t a0, uint32_t d_tmem, uint32_t acc_first) {   // a K=16 slot (input projection tail)
+      // one N=256 weight slot = 2 k-steps (or 1 for the K=16 tail of the input projection)
+      auto mma_w256 = [&](uint64_t a0, uint32_t a_kstep16, uint32_t d_tmem, uint32_t acc_first, bool two) {
         wait_full();
         if (tc::elect_one()) {
-          tc::umma_bf16(d_tmem, a0, dS + (uint64_t)(slot * (SLOT_BYTES >> 4)), idesc, acc_first);
-          tc::umma_commit_addr(bar0 + (B_EMPTY + slot) * 8);
+          const uint64_t b0 = dS256 + (uint64_t)(slot * (SLOT_BYTES >> 4));
+          tc::umma_bf16_2cta(d_tmem, a0, b0, idesc256, acc_first);
+          if (two) tc::umma_bf16_2cta(d_tmem, a0 + a_kstep16, b0 + (2 * W256_LBO >> 4), idesc256, 1u);
+          tc::umma_commit_2cta_mc(bar0 + (B_EMPTY + slot) * 8);
         }
         __syncwarp();
         advance();
       };
-      // a cond slot (A operand) followed by its weight slot
+      // a cond slot (A operand, K=32) followed by its N=256 weight slot
       auto mma_cond = [&](uint32_t d_tmem, uint32_t acc_first) {
         wait_full();
         const uint32_t sa = slot;
         advance();
         wait_full();
         if (tc::elect_one()) {
-          const uint64_t a0 = dS + (uint64_t)(sa * (SLOT_BYTES >> 4));
-          const uint64_t b0 = dS + (uint64_t)(slot * (SLOT_BYTES >> 4));
-          tc::umma_bf16(d_tmem, a0, b0, idesc, acc_first);
-          tc::umma_bf16(d_tmem, a0 + (2 * W_LBO >> 4), b0 + (2 * W_LBO >> 4), idesc, 1u);
-          tc::umma_bf16(d_tmem, a0 + 2 * (2 * W_LBO >> 4), b0 + 2 * (2 * W_LBO >> 4), idesc, 1u);
-          tc::umma_bf16(d_tmem, a0 + 3 * (2 * W_LBO >> 4), b0 + 3 * (2 * W_LBO >> 4), idesc, 1u);
-          tc::umma_commit_addr(bar0 + (B_EMPTY + sa) * 8);
-          tc::umma_commit_addr(bar0 + (B_EMPTY + slot) * 8);
+          const uint64_t a0 = dS256 + (uint64_t)(sa * (SLOT_BYTES >> 4));
+          const uint64_t b0 = dS256 + (uint64_t)(slot * (SLOT_BYTES >> 4));
+          tc::umma_bf16_2cta(d_tmem, a0, b0, idesc256, acc_first);
+          tc::umma_bf16_2cta(d_tmem, a0 + (2 * W256_LBO >> 4), b0 + (2 * W256_LBO >> 4), idesc256, 1u);
+          tc::umma_commit_2cta_mc(bar0 + (B_EMPTY + sa) * 8);
+          tc::umma_commit_2cta_mc(bar0 + (B_EMPTY + slot) * 8);
         }
         __syncwarp();
         advance();
       };
-      auto temp_acquire = [&](uint32_t tb) {   // wait until the epilogue has drained the previous use of buffer tb
+      auto temp_acquire = [&](uint32_t tb) {   // wait until both CTAs' epilogues drained the previous use of buffer tb
         const long long t0 = PROF ? clock64() : 0;
         tc::mbar_wait_trap(bar0 + (B_TEMPTY + tb) * 8, ((n_use >> 1) + 1) & 1, WAIT_CYCLES, p.status, 2);
         if (PROF) t_temp += clock64() - t0;
         tc::tc_fence_after();
+        ++n_use;
       };
       auto temp_publish = [&](uint32_t tb) {
-        if (tc::elect_one()) tc::umma_commit_addr(bar0 + (B_TFULL + tb) * 8);
+        if (tc::elect_one()) tc::umma_commit_2cta_mc(bar0 + (B_TFULL + tb) * 8);
         __syncwarp();
-        ++n_use;
       };
       auto wait_bar = [&](uint32_t bar, uint32_t n) {
         const long long t0 = PROF ? clock64() : 0;
@@ -302,20 +330,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_group_kernel(const FusedPar
 
       if (first_group) {
         wait_bar(B_AREADY, n_aready++);                 // x_t tile as bf16, channels 0..79, rows 1..128
-        for (uint32_t c = 0; c < 2; ++c) {              // input projection, K = 80
-          temp_acquire(c);
-          mma_w4(dA + (16 >> 4), A_K16, tm_t(c), 0u);
-          mma_w1(dA + ((16 + 8 * A_LBO) >> 4), tm_t(c), 1u);
-          temp_publish(c);
-        }
-        for (uint32_t c = 0; c < 2; ++c) {              // conditioner projection of layer 0
-          temp_acquire(c);
-          for (int j = 0; j < 4; ++j) mma_cond(tm_t(c), j ? 1u : 0u);
-          temp_publish(c);
-        }
+        temp_acquire(0); temp_acquire(1);               // input projection, K = 80, N = 256
+        mma_w256(dA + (16 >> 4), A_K16, tm_t(0), 0u, true);
+        mma_w256(dA + ((16 + 4 * A_LBO) >> 4), A_K16, tm_t(0), 1u, true);
+        mma_w256(dA + ((16 + 8 * A_LBO) >> 4), A_K16, tm_t(0), 1u, false);
+        temp_publish(0); temp_publish(1);
+        temp_acquire(0); temp_acquire(1);               // conditioner projection of layer 0
+        for (int m = 0; m < 8; ++m) mma_cond(tm_t(0), m ? 1u : 0u);
+        temp_publish(0); temp_publish(1);
       }
       for (int l = p.lb; l < p.le; ++l) {
-        wait_bar(B_AREADY, n_aready++);                 // conv input u_l in sA
+        wait_bar(B_AREADY, n_aready++);                 // conv input u_l in sA (both CTAs)
 #pragma unroll 1
         for (uint32_t i = 0; i < 4; ++i) {              // k=3 conv, chunk i = 64 gate + 64 filter channels
           const uint32_t tb = i & 1;
@@ -326,74 +351,78 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_group_kernel(const FusedPar
             uint64_t a = dA + tap;
 #pragma unroll 1
             for (uint32_t kb = 0; kb < 4; ++kb) {       // 64-channel blocks
-              mma_w4(a, A_K16, tm_t(tb), acc);
+              mma_w128(a, A_K16, tm_t(tb), acc);
               acc = 1;
               a += (8 * A_LBO) >> 4;
             }
           }
           temp_publish(tb);
         }
-        if (l < p.L - 1) {
+        const uint32_t skip_first = (l == p.lb) ? 0u : 1u;
+        wait_bar(B_GREADY + 0, n_gready);               // skip projection, gate channels [0, 64)
+        mma_w256(dG, G_K16, TM_SKIP, skip_first, true);
+        mma_w256(dG + ((4 * G_LBO) >> 4), G_K16, TM_SKIP, 1u, true);
+        if (l < p.L - 1) {                              // residual-out + conditioner delta, N = 256
+          temp_acquire(0); temp_acquire(1);
 #pragma unroll 1
-          for (uint32_t c = 0; c < 2; ++c) {            // residual-out + conditioner delta, 128 channels each
-            temp_acquire(c);
-#pragma unroll 1
-            for (uint32_t j = 0; j < 4; ++j) mma_cond(tm_t(c), j ? 1u : 0u);
-            uint64_t a = dG;
-#pragma unroll 1
-            for (uint32_t j = 0; j < 4; ++j) {
-              if (c == 0) wait_bar(B_GREADY + j, n_gready);
-              mma_w4(a, G_K16, tm_t(c), 1u);
-              a += (8 * G_LBO) >> 4;
-            }
-            temp_publish(c);
-          }
-        } else {
-          for (int j = 0; j < 4; ++j) wait_bar(B_GREADY + j, n_gready);
-        }
-        ++n_gready;
-#pragma unroll 1
-        for (uint32_t c = 0; c < 2; ++c) {              // skip projection accumulates across layers
+          for (uint32_t m = 0; m < 8; ++m) mma_cond(tm_t(0), m ? 1u : 0u);
           uint64_t a = dG;
 #pragma unroll 1
-          for (uint32_t j = 0; j < 4; ++j) {
-            mma_w4(a, G_K16, TM_SKIP + c * 128, (j == 0 && l == p.lb) ? 0u : 1u);
-            a += (8 * G_LBO) >> 4;
+          for (uint32_t m = 0; m < 8; ++m) {
+            if ((m & 1) == 0) wait_bar(B_GREADY + (m >> 1), n_gready);
+            mma_w256(a, G_K16, tm_t(0), 1u, true);
+            a += (4 * G_LBO) >> 4;
+          }
+          temp_publish(0); temp_publish(1);
+        } else {
+          for (int j = 1; j < 4; ++j) wait_bar(B_GREADY + j, n_gready);
+        }
+        ++n_gready;
+        {                                               // rest of the skip projection, gate channels [64, 256)
+          uint64_t a = dG + ((8 * G_LBO) >> 4);
+#pragma unroll 1
+          for (uint32_t m = 0; m < 6; ++m) {
+            mma_w256(a, G_K16, TM_SKIP, 1u, true);
+            a += (4 * G_LBO) >> 4;
           }
         }
       }
-      if (tc::elect_one()) tc::umma_commit_addr(bar0 + B_SKIPDONE * 8);
+      if (tc::elect_one()) tc::umma_commit_2cta_mc(bar0 + B_SKIPDONE * 8);
       __syncwarp();
       if (last_group) {
         wait_bar(B_AREADY, n_aready++);                 // skip sum / sqrt(L) as bf16 in sA rows 1..128
-        for (uint32_t c = 0; c < 2; ++c) {
-          temp_acquire(c);
-          for (int j = 0; j < 4; ++j) mma_w4(dA + ((16 + j * 8 * A_LBO) >> 4), A_K16, tm_t(c), j ? 1u : 0u);
-          temp_publish(c);
-        }
+        temp_acquire(0); temp_acquire(1);
+        for (int m = 0; m < 8; ++m) mma_w256(dA + ((16 + m * 4 * A_LBO) >> 4), A_K16, tm_t(0), m ? 1u : 0u, true);
+        temp_publish(0); temp_publish(1);
         wait_bar(B_GREADY + 0, n_gready++);             // relu(skip projection) as bf16 in sG
         temp_acquire(0);
-        for (int j = 0; j < 4; ++j) mma_w4(dG + ((j * 8 * G_LBO) >> 4), G_K16, tm_t(0), j ? 1u : 0u);
+        for (int j = 0; j < 4; ++j) mma_w128(dG + ((j * 8 * G_LBO) >> 4), G_K16, tm_t(0), j ? 1u : 0u);
         temp_publish(0);
       }
       if (PROF && lane == 0) {
-        long long* q = p.prof + tile * 16;
+        long long* q = p.prof + blockIdx.x * 16;
         q[0] = t_full; q[1] = t_temp; q[2] = t_ar; q[3] = t_gr; q[4] = clock64() - t_start;
       }
     }
   } else {
-    // =========================== EPILOGUE (warps 4..11) ===========================
+    // =========================== EPILOGUE (warps 4..11, both CTAs) ===========================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
     const int ew = warp - 4;
     const int q = ew & 3;            // TMEM lane quadrant == warp % 4
     const int h = ew >> 2;           // which half of a 128-column chunk
-    const int r = q * 32 + lane;     // tile row
-    const int f = f0 + r;            // frame
-    const bool in_seq = f >= 0 && f < p.T;
-    const bool is_out = in_seq && r >= p.halo && r < 128 - p.halo;
+    const int r = q * 32 + lane;     // row of this CTA's half tile
+    const int g = g0 + r;            // row on the batch row axis
+    const int b = (g >= 0 && g < p.R) ? g / p.Tg : 0;
+    const int f = g - b * p.Tg;      // frame within the utterance (== T on the gap row)
+    const bool in_seq = g >= 0 && g < p.R && f < p.T;
+    const int tr = 128 * (int)rank + r;
+    const bool is_out = in_seq && tr >= p.halo && tr < TILE_ROWS - p.halo;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     auto tm_t = [&](int tb) { return TM_TEMP0 + lane_off + (uint32_t)tb * 128u; };
     const uint32_t aA = tc::smem_u32(sA), aG = tc::smem_u32(sG);
+    // the pair's two half tiles are neighbours on the row axis: my edge row is the other CTA's halo row
+    const bool halo_src = (rank == 0 && r == 127) || (rank == 1 && r == 0);
+    const uint32_t peer_halo = tc::mapa(aA, rank ^ 1u) + (rank == 0 ? 0u : 129u * 16u);
     const size_t row_g = (size_t)b * p.T + (in_seq ? f : 0);
     uint32_t n_use = 0;              // temp-buffer uses so far (alternate 0,1,0,1,...)
     float u[128];                    // fp32 residual stream: channels 128c + 64h + j at index 64c + j
@@ -401,7 +430,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_group_kernel(const FusedPar
     long long t_tfull = 0;
     auto temp_wait = [&](int tb) {
       const long long t0 = PROF ? clock64() : 0;
-      tc::mbar_wait_trap(tc::smem_u32(&bars[B_TFULL + tb]), (n_use >> 1) & 1, WAIT_CYCLES, p.status, 4);
+      tc::mbar_wait_trap(bar0 + (B_TFULL + tb) * 8, (n_use >> 1) & 1, WAIT_CYCLES, p.status, 4);
       if (PROF) t_tfull += clock64() - t0;
       ++n_use;
       tc::tc_fence_after();
@@ -409,21 +438,27 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_group_kernel(const FusedPar
     auto temp_release = [&](int tb) {
       tc::tc_fence_before();
       __syncwarp();
-      if (lane == 0) tc::mbar_arrive(&bars[B_TEMPTY + tb]);
+      if (lane == 0) tc::mbar_arrive_remote(lead_bar0 + (B_TEMPTY + tb) * 8);
     };
-    auto publish = [&](int bar) {     // smem operand tile written by this warp is ready for the MMA
-      tc::fence_proxy_async_smem();
+    // operand rows written by this warp are ready for the MMA.  `remote` (warp-uniform): the warp also wrote a halo
+    // row into the PEER's shared memory, which needs a cluster-scope fence before the signal.
+    const bool halo_warp = (rank == 0 && q == 3) || (rank == 1 && q == 0);
+    auto publish = [&](int bar, bool remote = false) {
+      if (remote) { tc::fence_acq_rel_cluster(); tc::fence_proxy_async_all(); }
+      else tc::fence_proxy_async_smem();   // .shared::cta: no MEMBAR.GPU (the generic form costs ~8% of the epilogue)
       __syncwarp();
-      if (lane == 0) tc::mbar_arrive(&bars[bar]);
+      if (lane == 0) tc::mbar_arrive_remote(lead_bar0 + bar * 8);
     };
-    // write u[64c .. 64c+64) as bf16 into the conv-input tile (zero outside the utterance)
+    // write u[64c .. 64c+64) as bf16 into the conv-input tile (zero outside the utterances)
     auto write_A = [&](int c, const float* v) {
 #pragma unroll
       for (int jj = 0; jj < 8; ++jj) {
         uint32_t w[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) w[e] = in_seq ? pack_bf16(v[jj * 8 + 2 * e], v[jj * 8 + 2 * e + 1]) : 0u;
-        st_shared_v4(aA + (uint32_t)(16 * c + 8 * h + jj) * A_LBO + (uint32_t)(r + 1) * 16, w[0], w[1], w[2], w[3]);
+        const uint32_t chunk_off = (uint32_t)(16 * c + 8 * h + jj) * A_LBO;
+        st_shared_v4(aA + chunk_off + (uint32_t)(r + 1) * 16, w[0], w[1], w[2], w[3]);
+        if (halo_src) tc::st_cluster_v4(peer_halo + chunk_off, w[0], w[1], w[2], w[3]);
       }
     };
 
@@ -483,7 +518,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_group_kernel(const FusedPar
         temp_release(c);
         write_A(c, &u[64 * c]);
       }
-      publish(B_AREADY);
+      publish(B_AREADY, halo_warp);
     } else {
       // reload u_lb spilled by the previous group
 #pragma unroll
@@ -497,7 +532,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_group_kernel(const FusedPar
         }
         write_A(c, &u[64 * c]);
       }
-      publish(B_AREADY);
+      publish(B_AREADY, halo_warp);
     }
 
     // ---- residual blocks ----
@@ -515,7 +550,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_group_kernel(const FusedPar
         const float4* bf = reinterpret_cast<const float4*>(p.conv_bias + ((size_t)l * 4 + i) * 128 + 64 + 32 * h);
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj) {
-          float g[8];
+          float gv[8];
 #pragma unroll
           for (int e4 = 0; e4 < 2; ++e4) {
             const float4 bgv = __ldg(bg + jj * 2 + e4), bfv = __ldg(bf + jj * 2 + e4);
@@ -526,11 +561,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_group_kernel(const FusedPar
               const float a = __uint_as_float(ga[j]) + bgs[e];
               const float fl = __uint_as_float(fa[j]) + bfs[e];
               const float sg = fmaf(tanh_approx(0.5f * a), 0.5f, 0.5f);   // sigmoid(a)
-              g[e4 * 4 + e] = sg * tanh_approx(fl);
+              gv[e4 * 4 + e] = sg * tanh_approx(fl);
             }
           }
-          st_shared_v4(aG + (uint32_t)(8 * i + 4 * h + jj) * G_LBO + (uint32_t)r * 16, pack_bf16(g[0], g[1]),
-                       pack_bf16(g[2], g[3]), pack_bf16(g[4], g[5]), pack_bf16(g[6], g[7]));
+          st_shared_v4(aG + (uint32_t)(8 * i + 4 * h + jj) * G_LBO + (uint32_t)r * 16, pack_bf16(gv[0], gv[1]),
+                       pack_bf16(gv[2], gv[3]), pack_bf16(gv[4], gv[5]), pack_bf16(gv[6], gv[7]));
         }
         publish(B_GREADY + i);
       }
@@ -558,12 +593,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_group_kernel(const FusedPar
           }
           write_A(c, &u[64 * c]);
         }
-        publish(B_AREADY);
+        publish(B_AREADY, halo_warp);
       }
     }
 
     // ---- group end ----
-    tc::mbar_wait_trap(tc::smem_u32(&bars[B_SKIPDONE]), 0, WAIT_CYCLES, p.status, 4);
+    tc::mbar_wait_trap(bar0 + B_SKIPDONE * 8, 0, WAIT_CYCLES, p.status, 4);
     tc::tc_fence_after();
     if (!last_group) {
       if (is_out) {
@@ -678,27 +713,31 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_group_kernel(const FusedPar
     if (PROF) t_tfull_out = t_tfull;
   }
 
-  if (PROF && warp == 4 && lane == 0) { p.prof[tile * 16 + 8] = t_tfull_out; p.prof[tile * 16 + 9] = clock64() - t_start; }
-  // ---- teardown ----
+  if (PROF && warp == 4 && lane == 0) { p.prof[blockIdx.x * 16 + 8] = t_tfull_out; p.prof[blockIdx.x * 16 + 9] = clock64() - t_start; }
+  // ---- teardown: neither CTA may leave (or free TMEM) while the pair's MMAs can still touch it ----
   tc::tc_fence_before();
   __syncthreads();
-  if (warp == 2) tc::tmem_dealloc<512>(tmem);
+  tc::cluster_sync_all();
+  if (warp == 2) tc::tmem_dealloc_2cta<512>(tmem);
 }
 
-// ---- cond [B][T][H] fp32 -> [B][32][Tp][8] bf16 with COND_PAD_LO leading zero rows ---------------
-__global__ void cond_pack_kernel(const float* __restrict__ cond, __nv_bfloat16* __restrict__ out, int T, int Tp) {
-  const int b = blockIdx.y;
+// ---- cond [B][T][H] fp32 -> [32][Rp][8] bf16 on the batch row axis (zero rows in the gaps and pads) ----
+__global__ void cond_pack_kernel(const float* __restrict__ cond, __nv_bfloat16* __restrict__ out, int T, int Tg, int R,
+                                 int Rp) {
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);   // 8 rows per block, 32 chunks per row
   const int c8 = threadIdx.x & 31;
-  if (row >= Tp) return;
-  const int f = row - COND_PAD_LO;
+  if (row >= Rp) return;
+  const int g = row - COND_PAD_LO;
   uint4 v = make_uint4(0u, 0u, 0u, 0u);
-  if (f >= 0 && f < T) {
-    const float4* src = reinterpret_cast<const float4*>(cond + ((size_t)b * T + f) * C + c8 * 8);
-    const float4 a = __ldg(src), c = __ldg(src + 1);
-    v = make_uint4(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w), pack_bf16(c.x, c.y), pack_bf16(c.z, c.w));
+  if (g >= 0 && g < R) {
+    const int b = g / Tg, f = g - b * Tg;
+    if (f < T) {
+      const float4* src = reinterpret_cast<const float4*>(cond + ((size_t)b * T + f) * C + c8 * 8);
+      const float4 a = __ldg(src), c = __ldg(src + 1);
+      v = make_uint4(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w), pack_bf16(c.x, c.y), pack_bf16(c.z, c.w));
+    }
   }
-  reinterpret_cast<uint4*>(out)[((size_t)b * 32 + c8) * Tp + row] = v;
+  reinterpret_cast<uint4*>(out)[(size_t)c8 * Rp + row] = v;
 }
 
 // ---- per-utterance constants of the u recurrence ----------------------------------------------------
@@ -737,55 +776,59 @@ SmallOff small_layout(const mgb_model_dims& d) {
 }
 inline int num_wslots(const mgb_model_dims& d) { return W_LAYER0 + d.layers * W_PER_LAYER; }
 
+// One block per (slot, rank).  A slot image is [k8][row][8 bf16]: N=256 slots hold 4 k-chunks x 128 rows
+// (K = 32, output rows 128*rank + row), N=128 slots hold 8 k-chunks x 64 rows (K = 64, rows 64*rank + row of
+// the 128-column tile).
 __global__ void pack_images_kernel(const float* __restrict__ flat, const FlatOffsets f, const int L, const int n_mel,
-                                   __nv_bfloat16* __restrict__ img) {
-  const int slot = blockIdx.x;
-  const float* conv_w = nullptr; const float* oproj_w = nullptr; const float* cproj_w = nullptr;
-  const float* cproj_next = nullptr;
-  int kind, c = 0, j = 0, ci = 0;
-  if (slot < W_P0) { kind = 0; c = slot >> 1; j = slot & 1; }
-  else if (slot < W_SKIPP) { kind = 1; c = (slot - W_P0) >> 2; j = (slot - W_P0) & 3; cproj_w = flat + f.layer0 + f.rel.cproj_w; }
-  else if (slot < W_OUT) { kind = 2; c = (slot - W_SKIPP) >> 2; j = (slot - W_SKIPP) & 3; }
-  else if (slot < W_LAYER0) { kind = 3; j = slot - W_OUT; }
+                                   const int nslots, __nv_bfloat16* __restrict__ img) {
+  const int slot = blockIdx.x, rank = blockIdx.y;
+  const float* fl = nullptr;
+  int kind, m = 0, ci = 0, tap = 0, kb = 0;
+  // kind: 0 in-proj, 1 cond-proj layer 0, 2 skip-proj, 3 out-proj, 4 conv, 5 res cond delta, 6 res g (Wo_x), 7 skip (Wo_s)
+  if (slot < W_P0) { kind = 0; m = slot; }
+  else if (slot < W_SKIPP) { kind = 1; m = slot - W_P0; fl = flat + f.layer0; }
+  else if (slot < W_OUT) { kind = 2; m = slot - W_SKIPP; }
+  else if (slot < W_LAYER0) { kind = 3; m = slot - W_OUT; }
   else {
     const int l = (slot - W_LAYER0) / W_PER_LAYER, rr = (slot - W_LAYER0) % W_PER_LAYER;
-    const float* fl = flat + f.layer0 + (size_t)l * f.layer_stride;
-    conv_w = fl + f.rel.conv_w; oproj_w = fl + f.rel.oproj_w; cproj_w = fl + f.rel.cproj_w;
-    cproj_next = (l + 1 < L) ? fl + f.layer_stride + f.rel.cproj_w : nullptr;
-    if (rr < 48) { kind = 4; ci = rr / 12; j = rr % 12; }
-    else if (rr < 64) { const int qq = rr - 48; c = qq >> 3; j = qq & 7; kind = j < 4 ? 5 : 6; j &= 3; }
-    else { kind = 7; c = (rr - 64) >> 2; j = (rr - 64) & 3; }
+    fl = flat + f.layer0 + (size_t)l * f.layer_stride;
+    if (rr < WL_SKIPA) { kind = 4; ci = rr / 12; tap = (rr % 12) >> 2; kb = rr & 3; }
+    else if (rr < WL_RCOND) { kind = 7; m = rr - WL_SKIPA; }
+    else if (rr < WL_RG) { kind = (l + 1 < L) ? 5 : 8; m = rr - WL_RCOND; }
+    else if (rr < WL_SKIPB) { kind = (l + 1 < L) ? 6 : 8; m = rr - WL_RG; }
+    else { kind = 7; m = 2 + rr - WL_SKIPB; }
   }
-  for (int unit = threadIdx.x; unit < 1024; unit += blockDim.x) {
-    const int k8 = unit >> 7, n = unit & 127;
+  const bool n128 = (kind == 3 || kind == 4);
+  const int rows = n128 ? 64 : 128;
+  for (int unit = threadIdx.x; unit < 512; unit += blockDim.x) {
+    const int k8 = unit / rows, row = unit - k8 * rows;
     float v[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      const int k = k8 * 8 + e;
+      const int k = k8 * 8 + e;             // K index inside the slot
       float x = 0.f;
       switch (kind) {
-        case 0: { const int kk = j * 64 + k; if (kk < n_mel) x = flat[f.in_w + (size_t)(128 * c + n) * n_mel + kk]; break; }
-        case 1: x = cproj_w[(size_t)(128 * c + n) * C + 64 * j + k]; break;
-        case 2: x = flat[f.skip_w + (size_t)(128 * c + n) * C + 64 * j + k]; break;
-        case 3: if (n < n_mel) x = flat[f.out_w + (size_t)n * C + 64 * j + k]; break;
+        case 0: { const int n = 128 * rank + row, kk = 32 * m + k; if (kk < n_mel) x = flat[f.in_w + (size_t)n * n_mel + kk]; break; }
+        case 1: x = fl[f.rel.cproj_w + (size_t)(128 * rank + row) * C + 32 * m + k]; break;
+        case 2: x = flat[f.skip_w + (size_t)(128 * rank + row) * C + 32 * m + k]; break;
+        case 3: { const int n = 64 * rank + row; if (n < n_mel) x = flat[f.out_w + (size_t)n * C + 64 * m + k]; break; }
         case 4: {
-          const int oc = n < 64 ? 64 * ci + n : C + 64 * ci + (n - 64);
-          const int tap = j >> 2, cin = (j & 3) * 64 + k;
-          x = conv_w[((size_t)oc * C + cin) * 3 + tap];
+          const int oc = rank == 0 ? 64 * ci + row : C + 64 * ci + row;   // rank 0: gate half, rank 1: filter half
+          x = fl[f.rel.conv_w + ((size_t)oc * C + 64 * kb + k) * 3 + tap];
           break;
         }
-        case 5:
-          if (cproj_next) {
-            const size_t o = (size_t)(128 * c + n) * C + 64 * j + k;
-            x = 1.41421356237309504880f * cproj_next[o] - cproj_w[o];
-          }
+        case 5: {
+          const size_t o = (size_t)(128 * rank + row) * C + 32 * m + k;
+          x = 1.41421356237309504880f * fl[f.layer_stride + f.rel.cproj_w + o] - fl[f.rel.cproj_w + o];
           break;
-        case 6: x = oproj_w[(size_t)(128 * c + n) * C + 64 * j + k]; break;
-        default: x = oproj_w[(size_t)(C + 128 * c + n) * C + 64 * j + k]; break;
+        }
+        case 6: x = fl[f.rel.oproj_w + (size_t)(128 * rank + row) * C + 32 * m + k]; break;
+        case 7: x = fl[f.rel.oproj_w + (size_t)(C + 128 * rank + row) * C + 32 * m + k]; break;
+        default: break;
       }
       v[e] = x;
     }
-    reinterpret_cast<uint4*>(img)[(size_t)slot * 1024 + unit] =
+    reinterpret_cast<uint4*>(img)[((size_t)rank * nslots + slot) * 512 + unit] =
         make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
   }
 }
@@ -814,14 +857,16 @@ __global__ void pack_small_kernel(const float* __restrict__ flat, const FlatOffs
 
 struct WorkBf16 {
   size_t condT, d, h, dtab, ctab, ktab, k00, U, U2, S, status, total;
-  int Tp;
+  int Tg, R, Rp;
 };
 WorkBf16 work_layout(const mgb_model_dims& d, int B, int T) {
   WorkBf16 w{};
-  w.Tp = (int)align_up((size_t)T + COND_PAD_LO + 128 + MAX_GROUP_LAYERS, 8);
+  w.Tg = T + 1;
+  w.R = B * w.Tg;
+  w.Rp = (int)align_up((size_t)COND_PAD_LO + w.R + COND_PAD_HI, 8);
   size_t p = 0;
   auto take = [&](size_t bytes) { size_t r = p; p += align_up(bytes, 256); return r; };
-  w.condT = take((size_t)B * 32 * w.Tp * 16);
+  w.condT = take((size_t)32 * w.Rp * 16);
   w.d = take((size_t)B * C * 4);
   w.h = take((size_t)B * 4 * C * 4);
   w.dtab = take((size_t)B * d.layers * C * 4);
@@ -836,19 +881,38 @@ WorkBf16 work_layout(const mgb_model_dims& d, int B, int T) {
   return w;
 }
 
-int group_layers() {
-  static int g = [] {
+// Layer groups: each group is one launch whose tiles lose 2*(layers in the group) rows to halo recompute.
+// Pick the number of groups that minimises  sum_g waves_g * (layers_g + overhead)  where a wave is one
+// tile per CTA pair on every TPC of the device.
+int plan_groups(int L, int R, int pair_slots) {
+  static const int forced = [] {
     const char* e = getenv("MGB_GROUP_LAYERS");
-    int v = e ? atoi(e) : 10;
-    return v < 1 ? 1 : (v > MAX_GROUP_LAYERS ? MAX_GROUP_LAYERS : v);
+    return e ? atoi(e) : 0;
   }();
-  return g;
+  if (forced > 0) {
+    const int gl = forced > MAX_GROUP_LAYERS ? MAX_GROUP_LAYERS : forced;
+    return (L + gl - 1) / gl;
+  }
+  int best = 0;
+  double best_cost = 1e30;
+  for (int ng = (L + MAX_GROUP_LAYERS - 1) / MAX_GROUP_LAYERS; ng <= L && ng <= 6; ++ng) {
+    double cost = 0;
+    for (int g = 0; g < ng; ++g) {
+      const int n = (g + 1) * L / ng - g * L / ng;
+      const int V = TILE_ROWS - 2 * n;
+      const int tiles = (R + V - 1) / V;
+      const int waves = (tiles + pair_slots - 1) / pair_slots;
+      cost += waves * (n + 0.6);
+    }
+    if (cost < best_cost - 1e-9) { best_cost = cost; best = ng; }
+  }
+  return best;
 }
 
 }  // namespace
 
 size_t bf16_packed_bytes(const mgb_model_dims& d) {
-  return small_layout(d).total * sizeof(float) + (size_t)num_wslots(d) * SLOT_BYTES;
+  return small_layout(d).total * sizeof(float) + (size_t)2 * num_wslots(d) * SLOT_BYTES;
 }
 size_t bf16_workspace_bytes(const mgb_model_dims& d, int B, int T, int) { return work_layout(d, B, T).total; }
 size_t bf16_status_offset(const mgb_model_dims& d, int B, int T) { return work_layout(d, B, T).status; }
@@ -869,7 +933,7 @@ int bf16_pack(const mgb_model_dims& d, const float* flat, void* packed, cudaStre
   pack_small_kernel<<<1, 256, 0, s>>>(flat, f, L, d.n_mel, P + o.conv_bias, P + o.bo_x, P + o.bsum_skip, P + o.b_in,
                                       P + o.b_skip, P + o.b_out);
   __nv_bfloat16* img = reinterpret_cast<__nv_bfloat16*>(P + o.total);
-  pack_images_kernel<<<num_wslots(d), 256, 0, s>>>(flat, f, L, d.n_mel, img);
+  pack_images_kernel<<<dim3(num_wslots(d), 2), 256, 0, s>>>(flat, f, L, d.n_mel, num_wslots(d), img);
   MGB_LAUNCH_CHECK();
   return MGB_OK;
 }
@@ -891,14 +955,17 @@ int bf16_denoiser(const mgb_model_dims& d, const void* packed, const float* x, c
   __nv_bfloat16* condT = reinterpret_cast<__nv_bfloat16*>(W + w.condT);
   int* status = reinterpret_cast<int*>(W + w.status);
 
-  static bool attr_set = false;
-  if (!attr_set) {
-    MGB_CUDA_CHECK(cudaFuncSetAttribute(fused_group_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
-    attr_set = true;
+  static int pair_slots = 0;
+  if (!pair_slots) {
+    int dev = 0, sms = 0;
+    MGB_CUDA_CHECK(cudaGetDevice(&dev));
+    MGB_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    MGB_CUDA_CHECK(cudaFuncSetAttribute(fused_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+    pair_slots = sms / 2 > 0 ? sms / 2 : 1;
   }
   if (!cond_ready) {
-    dim3 grid((w.Tp + 7) / 8, B);
-    cond_pack_kernel<<<grid, 256, 0, s>>>(cond, condT, T, w.Tp);
+    dim3 grid((w.Rp + 7) / 8);
+    cond_pack_kernel<<<grid, 256, 0, s>>>(cond, condT, T, w.Tg, w.R, w.Rp);
     MGB_CUDA_CHECK(cudaMemsetAsync(status, 0, sizeof(int), s));
     note_launch();
   }
@@ -915,45 +982,45 @@ int bf16_denoiser(const mgb_model_dims& d, const void* packed, const float* x, c
   }
   FusedParams p{};
   p.wimg = reinterpret_cast<const uint8_t*>(P + o.total);
-  p.condT = condT; p.Tp = w.Tp;
+  p.wimg_rank_stride = (size_t)num_wslots(d) * SLOT_BYTES;
+  p.condT = condT; p.Rp = w.Rp;
   p.x_t = x; p.noise = noise; p.x_prev = x_prev; p.x0_out = out_x0; p.sched = sched; p.t = t;
   p.K = K; p.clip = clip; p.n_mel = d.n_mel;
   p.ktab = ktab; p.k00 = k00; p.conv_bias = P + o.conv_bias; p.bsum_skip = P + o.bsum_skip;
   p.b_in = P + o.b_in; p.b_skip = P + o.b_skip; p.b_out = P + o.b_out;
   float* Ubuf[2] = {reinterpret_cast<float*>(W + w.U), reinterpret_cast<float*>(W + w.U2)};
   p.S = reinterpret_cast<float*>(W + w.S);
-  p.B = B; p.T = T; p.L = L; p.status = status;
-  const int gl = group_layers();
-  const int ngroups = (L + gl - 1) / gl;
+  p.B = B; p.T = T; p.Tg = w.Tg; p.R = w.R; p.L = L; p.status = status;
+  const int ngroups = plan_groups(L, w.R, pair_slots);
   for (int g = 0; g < ngroups; ++g) {
     p.lb = g * L / ngroups;
     p.le = (g + 1) * L / ngroups;
     p.halo = p.le - p.lb;
-    p.V = 128 - 2 * p.halo;
-    p.tiles_per_utt = (T + p.V - 1) / p.V;
+    p.V = TILE_ROWS - 2 * p.halo;
+    const int npairs = (w.R + p.V - 1) / p.V;
     p.U_in = Ubuf[g & 1];
     p.U_out = Ubuf[(g + 1) & 1];
     prof_begin(s);
     static const bool do_prof = getenv("MGB_PROFILE") != nullptr;
     if (do_prof) {
-      const int ntile = B * p.tiles_per_utt;
+      const int ncta = 2 * npairs;
       long long* dprof = nullptr;
-      cudaMalloc(&dprof, (size_t)ntile * 16 * sizeof(long long));
-      cudaMemset(dprof, 0, (size_t)ntile * 16 * sizeof(long long));
+      cudaMalloc(&dprof, (size_t)ncta * 16 * sizeof(long long));
+      cudaMemset(dprof, 0, (size_t)ncta * 16 * sizeof(long long));
       p.prof = dprof;
-      cudaFuncSetAttribute(fused_group_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL);
-      fused_group_kernel<true><<<ntile, NTHREADS, SMEM_TOTAL, s>>>(p);
+      cudaFuncSetAttribute(fused_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL);
+      fused_pair_kernel<true><<<ncta, NTHREADS, SMEM_TOTAL, s>>>(p);
       cudaStreamSynchronize(s);
-      long long* h = (long long*)malloc((size_t)ntile * 16 * sizeof(long long));
-      cudaMemcpy(h, dprof, (size_t)ntile * 16 * sizeof(long long), cudaMemcpyDeviceToHost);
-      double a[16] = {0};
-      for (int i = 0; i < ntile; ++i) for (int k = 0; k < 16; ++k) a[k] += (double)h[i * 16 + k] / ntile;
-      fprintf(stderr, "[mgb profile] layers [%d,%d) tiles %d | MMA warp: total %.0f wait_full %.0f wait_temp %.0f wait_aready %.0f "
-              "wait_gready %.0f | epilogue w4: total %.0f wait_tfull %.0f | producer: total %.0f wait_empty %.0f (cycles, mean per tile)\n",
-              p.lb, p.le, ntile, a[4], a[0], a[1], a[2], a[3], a[9], a[8], a[13], a[12]);
+      long long* h = (long long*)malloc((size_t)ncta * 16 * sizeof(long long));
+      cudaMemcpy(h, dprof, (size_t)ncta * 16 * sizeof(long long), cudaMemcpyDeviceToHost);
+      double a[16] = {0};   // MMA-warp counters exist on leader CTAs only (even blocks)
+      for (int i = 0; i < ncta; i += 2) for (int k = 0; k < 16; ++k) a[k] += (double)h[i * 16 + k] / npairs;
+      fprintf(stderr, "[mgb profile] layers [%d,%d) pairs %d | MMA warp: total %.0f wait_full %.0f wait_temp %.0f wait_aready %.0f "
+              "wait_gready %.0f | epilogue w4: total %.0f wait_tfull %.0f | producer: total %.0f wait_empty %.0f (cycles, mean per leader CTA)\n",
+              p.lb, p.le, npairs, a[4], a[0], a[1], a[2], a[3], a[9], a[8], a[13], a[12]);
       free(h); cudaFree(dprof); p.prof = nullptr;
     } else {
-      fused_group_kernel<false><<<B * p.tiles_per_utt, NTHREADS, SMEM_TOTAL, s>>>(p);
+      fused_pair_kernel<false><<<2 * npairs, NTHREADS, SMEM_TOTAL, s>>>(p);
     }
     prof_end(s);
     note_launch();

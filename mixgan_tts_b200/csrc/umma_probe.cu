@@ -162,6 +162,60 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) umma_probe2_
   if (warp == 0) tc::tmem_dealloc_2cta<256>(tmem);
 }
 
+
+// ---- issue-rate probe: `reps` back-to-back tcgen05.mma on resident (zero) operands, cycles from the first
+// issue to the completion of the final commit.  cta2 != 0 runs a CTA pair with cta_group::2 (M = 256).
+struct RateArgs {
+  int a_lbo, a_sbo, b_lbo, b_sbo, a_kadv, b_kadv, b_off, n, ksteps, reps, nacc;
+  long long* cycles;   // [gridDim.x]
+  int* status;
+};
+
+template <bool CTA2>
+__global__ void __launch_bounds__(128, 1) umma_rate_kernel(const RateArgs p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bar_mma;
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const uint32_t rank = CTA2 ? tc::cluster_ctarank() : 0u;
+  for (int i = tid; i < (p.b_off * 2) / 16; i += 128) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
+  if (warp == 0) { if (CTA2) tc::tmem_alloc_2cta<512>(&tmem_slot); else tc::tmem_alloc<512>(&tmem_slot); }
+  if (tid == 32) { tc::mbar_init(&bar_mma, 1); tc::fence_barrier_init(); }
+  tc::fence_proxy_async_smem();
+  tc::tc_fence_before();
+  __syncthreads();
+  if (CTA2) tc::cluster_sync_all();
+  tc::tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  long long cyc = 0;
+  if (rank == 0 && warp == 0) {
+    const uint32_t idesc = tc::make_idesc_bf16(CTA2 ? 256 : 128, p.n);
+    const uint32_t a0 = tc::smem_u32(smem), b0 = tc::smem_u32(smem + p.b_off);
+    const uint64_t ad = tc::make_smem_desc(a0, p.a_lbo, p.a_sbo), bd = tc::make_smem_desc(b0, p.b_lbo, p.b_sbo);
+    const long long t0 = clock64();
+    if (tc::elect_one()) {
+      for (int r = 0; r < p.reps; ++r) {
+        const uint32_t d = tmem + (uint32_t)((r % p.nacc) * p.n);
+        for (int k = 0; k < p.ksteps; ++k) {
+          if (CTA2) tc::umma_bf16_2cta(d, ad + (uint64_t)(((k & 3) * p.a_kadv) >> 4), bd + (uint64_t)(((k & 3) * p.b_kadv) >> 4), idesc, k > 0);
+          else tc::umma_bf16(d, ad + (uint64_t)(((k & 3) * p.a_kadv) >> 4), bd + (uint64_t)(((k & 3) * p.b_kadv) >> 4), idesc, k > 0);
+        }
+      }
+      if (CTA2) tc::umma_commit_2cta_mc(tc::smem_u32(&bar_mma)); else tc::umma_commit(&bar_mma);
+    }
+    __syncwarp();
+    tc::mbar_wait_trap(tc::smem_u32(&bar_mma), 0, 2000000000LL, p.status, 2);
+    cyc = clock64() - t0;
+    if ((tid & 31) == 0) p.cycles[blockIdx.x] = cyc;
+  } else if (CTA2 && warp == 0) {
+    tc::mbar_wait_trap(tc::smem_u32(&bar_mma), 0, 2000000000LL, p.status, 4);
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (CTA2) tc::cluster_sync_all();
+  if (warp == 0) { if (CTA2) tc::tmem_dealloc_2cta<512>(tmem); else tc::tmem_dealloc<512>(tmem); }
+}
+
 }  // namespace
 }  // namespace mgb
 
@@ -210,6 +264,41 @@ extern "C" int mgb_probe_umma_2cta(const void* a_img, int a_bytes, const void* b
   MGB_REQUIRE(smem <= 200 * 1024, MGB_E_ARG, "operand images too large for shared memory");
   MGB_CUDA_CHECK(cudaFuncSetAttribute(umma_probe2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   umma_probe2_kernel<<<2, 128, smem, static_cast<cudaStream_t>(stream)>>>(p);
+  MGB_LAUNCH_CHECK();
+  return MGB_OK;
+}
+
+// Issue-rate probe (scripts/umma_rate.py): runs `grid` CTAs (or CTA pairs when cta2) each issuing
+// reps*ksteps tcgen05.mma on zeroed operands; cycles_out[i] = SM cycles of leader CTA i from first issue to
+// commit completion.  Operand regions: A at 0, B at b_off (each b_off bytes, <= 100 KB).
+extern "C" int mgb_probe_umma_rate(int cta2, int grid, int n, int ksteps, int reps, int nacc, int a_lbo, int a_sbo,
+                                   int a_kadv, int b_lbo, int b_sbo, int b_kadv, int b_off, long long* cycles_out,
+                                   int* status_out, void* stream) {
+  MGB_REQUIRE(cycles_out && status_out, MGB_E_ARG, "NULL pointer argument");
+  MGB_REQUIRE(n >= 16 && n <= 256 && n % 16 == 0 && ksteps >= 1 && reps >= 1 && nacc >= 1 && nacc * n <= 512, MGB_E_ARG,
+              "bad n/ksteps/reps/nacc");
+  MGB_REQUIRE(b_off > 0 && b_off % 1024 == 0 && b_off <= 100 * 1024, MGB_E_ARG, "bad b_off");
+  if (int rc = check_arch()) return rc;
+  RateArgs p{};
+  p.a_lbo = a_lbo; p.a_sbo = a_sbo; p.b_lbo = b_lbo; p.b_sbo = b_sbo; p.a_kadv = a_kadv; p.b_kadv = b_kadv;
+  p.b_off = b_off; p.n = n; p.ksteps = ksteps; p.reps = reps; p.nacc = nacc; p.cycles = cycles_out; p.status = status_out;
+  const size_t smem = (size_t)2 * b_off;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(cta2 ? 2 * grid : grid);
+  cfg.blockDim = dim3(128);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = static_cast<cudaStream_t>(stream);
+  cudaLaunchAttribute attr{};
+  attr.id = cudaLaunchAttributeClusterDimension;
+  attr.val.clusterDim.x = cta2 ? 2 : 1; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+  cfg.attrs = &attr; cfg.numAttrs = 1;
+  if (cta2) {
+    MGB_CUDA_CHECK(cudaFuncSetAttribute(umma_rate_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MGB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, umma_rate_kernel<true>, p));
+  } else {
+    MGB_CUDA_CHECK(cudaFuncSetAttribute(umma_rate_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MGB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, umma_rate_kernel<false>, p));
+  }
   MGB_LAUNCH_CHECK();
   return MGB_OK;
 }

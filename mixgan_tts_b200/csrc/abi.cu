@@ -157,8 +157,7 @@ int launch_fill_t(int64_t* t, int B, int64_t value, cudaStream_t s) {
 static int denoiser_dispatch(const mgb_model_dims* dims, int precision, const void* packed,
                              const float* x, const int64_t* t, const float* cond, const float* spk,
                              const float* noise, const float* sched, int K, int clip, float* x_prev,
-                             float* x0_out, int B, int T, void* ws, size_t ws_bytes, bool cond_ready,
-                             cudaStream_t s) {
+                             float* x0_out, int B, int T, void* ws, size_t ws_bytes, cudaStream_t s) {
   MGB_REQUIRE(dims_supported(dims), MGB_E_ARG, "unsupported model dims");
   MGB_REQUIRE(packed && x && t && cond && ws, MGB_E_ARG, "NULL pointer argument");
   MGB_REQUIRE(B > 0 && T > 0, MGB_E_ARG, "B and T must be positive (got %d, %d)", B, T);
@@ -169,9 +168,10 @@ static int denoiser_dispatch(const mgb_model_dims* dims, int precision, const vo
   MGB_REQUIRE(ws_bytes >= need, MGB_E_WORKSPACE, "workspace too small: %zu < %zu", ws_bytes, need);
   if (precision == MGB_PREC_FP32)
     return fp32_denoiser(*dims, packed, x, t, cond, spk, noise, sched, K, clip, x_prev, x0_out, B, T, ws, s);
-  if (precision == MGB_PREC_BF16)
-    return bf16_denoiser(*dims, packed, x, t, cond, spk, noise, sched, K, clip, x_prev, x0_out, B, T, ws,
-                         cond_ready, s);
+  if (precision == MGB_PREC_BF16) {
+    if (int rc = bf16_prepare(*dims, packed, t, 1, cond, spk, B, T, ws, s)) return rc;
+    return bf16_run(*dims, packed, x, t, -1, 0, 1, noise, sched, K, clip, x_prev, x0_out, B, T, ws, s);
+  }
   set_error("unknown precision %d", precision);
   return MGB_E_ARG;
 }
@@ -273,7 +273,7 @@ int mgb_denoiser_forward(const mgb_model_dims* dims, int precision, const void* 
                          void* workspace, size_t workspace_bytes, void* stream) {
   MGB_REQUIRE(out, MGB_E_ARG, "NULL output");
   return denoiser_dispatch(dims, precision, packed, x, t, cond, spk, nullptr, nullptr, 0, 0, nullptr, out,
-                           B, T, workspace, workspace_bytes, false, static_cast<cudaStream_t>(stream));
+                           B, T, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
 }
 
 int mgb_reverse_step(const mgb_model_dims* dims, int precision, const void* packed, const float* x_t,
@@ -282,7 +282,7 @@ int mgb_reverse_step(const mgb_model_dims* dims, int precision, const void* pack
                      void* workspace, size_t workspace_bytes, void* stream) {
   MGB_REQUIRE(noise && sched && x_prev && K > 0, MGB_E_ARG, "reverse_step needs noise, sched, x_prev and K > 0");
   return denoiser_dispatch(dims, precision, packed, x_t, t, cond, spk, noise, sched, K, clip, x_prev, x0_out,
-                           B, T, workspace, workspace_bytes, false, static_cast<cudaStream_t>(stream));
+                           B, T, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
 }
 
 int mgb_sample(const mgb_model_dims* dims, int precision, const void* packed, const float* x_T,
@@ -313,12 +313,25 @@ int mgb_sample(const mgb_model_dims* dims, int precision, const void* packed, co
     note_launch();
   }
   const float* cur = x_T;
+  const bool bf16 = precision == MGB_PREC_BF16;
+  if (bf16) {   // cond image and the per-step tables of all K steps, once
+    MGB_REQUIRE(packed && cond, MGB_E_ARG, "NULL pointer argument");
+    MGB_REQUIRE(!dims->multi_speaker || spk, MGB_E_ARG,
+                "multi_speaker model needs a speaker embedding (reference raises TypeError)");
+    if (int rc = check_arch()) return rc;
+    if (int rc = bf16_prepare(*dims, packed, nullptr, K, cond, spk, B, T, workspace, s)) return rc;
+  }
   for (int i = K - 1, n = 0; i >= 0; --i, ++n) {
-    if (int rc = launch_fill_t(tvec, B, i, s)) return rc;
     float* nxt = (n & 1) ? xb : xa;
-    const int rc = denoiser_dispatch(dims, precision, packed, cur, tvec, cond, spk,
-                                     noises + (size_t)i * B * M * T, sched, K, clip, nxt, nullptr, B, T,
-                                     workspace, workspace_bytes, n > 0, s);
+    const float* nz = noises + (size_t)i * B * M * T;
+    int rc;
+    if (bf16) {
+      rc = bf16_run(*dims, packed, cur, nullptr, i, i, K, nz, sched, K, clip, nxt, nullptr, B, T, workspace, s);
+    } else {
+      if ((rc = launch_fill_t(tvec, B, i, s))) return rc;
+      rc = denoiser_dispatch(dims, precision, packed, cur, tvec, cond, spk, nz, sched, K, clip, nxt, nullptr, B, T,
+                             workspace, workspace_bytes, s);
+    }
     if (rc) return rc;
     cur = nxt;
     if (states_out) {

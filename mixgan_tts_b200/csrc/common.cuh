@@ -113,10 +113,11 @@ size_t bf16_packed_bytes(const mgb_model_dims& d);
 int bf16_pack(const mgb_model_dims& d, const float* flat, void* packed, cudaStream_t s);
 size_t bf16_workspace_bytes(const mgb_model_dims& d, int B, int T, int K);
 size_t bf16_status_offset(const mgb_model_dims& d, int B, int T);
-int bf16_denoiser(const mgb_model_dims& d, const void* packed, const float* x, const int64_t* t,
-                  const float* cond, const float* spk, const float* noise, const float* sched, int K,
-                  int clip, float* x_prev, float* out_x0, int B, int T, void* ws, bool cond_ready,
-                  cudaStream_t s);
+int bf16_prepare(const mgb_model_dims& d, const void* packed, const int64_t* t, int nsteps, const float* cond,
+                 const float* spk, int B, int T, void* ws, cudaStream_t s);
+int bf16_run(const mgb_model_dims& d, const void* packed, const float* x, const int64_t* t, int t_uniform, int step,
+             int nsteps, const float* noise, const float* sched, int K, int clip, float* x_prev, float* out_x0, int B, int T,
+             void* ws, cudaStream_t s);
 
 // ---- elementwise (elementwise.cu) -------------------------------------------------------------
 int launch_fill_t(int64_t* t, int B, int64_t value, cudaStream_t s);

@@ -86,7 +86,8 @@ struct FusedParams {
   float* x_prev;                // [B][M][T] or null
   float* x0_out;                // [B][M][T] or null
   const float* sched;           // [3][K] or null
-  const int64_t* t;             // [B]
+  const int64_t* t;             // [B] (used when t_uniform < 0)
+  int t_uniform;                // >= 0: every utterance is at this timestep (sampling loop)
   int K, clip, n_mel;
   const float* ktab;            // [B][L][C]
   const float* k00;             // [B][C]
@@ -680,7 +681,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_p
       temp_wait(0);
       float c1 = 0.f, c2 = 0.f, sg = 0.f;
       if (p.sched) {
-        const int tb = (int)p.t[b];
+        const int tb = p.t_uniform >= 0 ? p.t_uniform : (int)p.t[b];
         c1 = p.sched[tb]; c2 = p.sched[p.K + tb]; sg = p.sched[2 * p.K + tb];
       }
 #pragma unroll
@@ -741,15 +742,24 @@ __global__ void cond_pack_kernel(const float* __restrict__ cond, __nv_bfloat16* 
 }
 
 // ---- per-utterance constants of the u recurrence ----------------------------------------------------
-// ktab[b][l] = (bo_x,l - ctab[b][l]) / sqrt(2) + dtab[b][l+1] + ctab[b][l+1]  (l < L-1), k00[b] = dtab[b][0] + ctab[b][0]
+// ktab[s][b][l] = (bo_x,l - ctab[b][l]) / sqrt(2) + dtab[r][l+1] + ctab[b][l+1]  (l < L-1),  k00[s][b] = dtab[r][0] + ctab[b][0]
+// with r = s when the timestep is uniform over the batch (dtab has one row per step) and r = b otherwise.
 __global__ void ktab_kernel(const float* __restrict__ dtab, const float* __restrict__ ctab,
-                            const float* __restrict__ bo_x, float* __restrict__ ktab, float* __restrict__ k00, int L) {
-  const int b = blockIdx.y, l = blockIdx.x, c = threadIdx.x;
-  const size_t i = ((size_t)b * L + l) * C + c;
+                            const float* __restrict__ bo_x, float* __restrict__ ktab, float* __restrict__ k00, int L,
+                            int B, int uniform) {
+  const int b = blockIdx.y, l = blockIdx.x, st = blockIdx.z, c = threadIdx.x;
+  const size_t ic = ((size_t)b * L + l) * C + c;
+  const size_t id = ((size_t)(uniform ? st : b) * L + l) * C + c;
+  const size_t io = (((size_t)st * B + b) * L + l) * C + c;
   float v = 0.f;
-  if (l < L - 1) v = (bo_x[(size_t)l * C + c] - ctab[i]) * RSQRT2 + dtab[i + C] + ctab[i + C];
-  ktab[i] = v;
-  if (l == 0) k00[(size_t)b * C + c] = dtab[i] + ctab[i];
+  if (l < L - 1) v = (bo_x[(size_t)l * C + c] - ctab[ic]) * RSQRT2 + dtab[id + C] + ctab[ic + C];
+  ktab[io] = v;
+  if (l == 0) k00[((size_t)st * B + b) * C + c] = dtab[id] + ctab[ic];
+}
+
+__global__ void iota_i64_kernel(int64_t* p, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = i;
 }
 
 // ---- weight images --------------------------------------------------------------------------------
@@ -856,27 +866,29 @@ __global__ void pack_small_kernel(const float* __restrict__ flat, const FlatOffs
 }
 
 struct WorkBf16 {
-  size_t condT, d, h, dtab, ctab, ktab, k00, U, U2, S, status, total;
+  size_t status, condT, tsteps, d, h, dtab, ctab, ktab, k00, U, U2, S, total;
   int Tg, R, Rp;
 };
-WorkBf16 work_layout(const mgb_model_dims& d, int B, int T) {
+WorkBf16 work_layout(const mgb_model_dims& d, int B, int T, int K) {
   WorkBf16 w{};
   w.Tg = T + 1;
   w.R = B * w.Tg;
   w.Rp = (int)align_up((size_t)COND_PAD_LO + w.R + COND_PAD_HI, 8);
+  const size_t U = (size_t)(B > K ? B : K);   // rows of the step-embedding chain: per utterance or per step
   size_t p = 0;
   auto take = [&](size_t bytes) { size_t r = p; p += align_up(bytes, 256); return r; };
+  w.status = take(256);                       // first: its offset must not depend on K (mgb_debug_status)
   w.condT = take((size_t)32 * w.Rp * 16);
-  w.d = take((size_t)B * C * 4);
-  w.h = take((size_t)B * 4 * C * 4);
-  w.dtab = take((size_t)B * d.layers * C * 4);
+  w.tsteps = take((size_t)K * sizeof(int64_t));
+  w.d = take(U * C * 4);
+  w.h = take(U * 4 * C * 4);
+  w.dtab = take(U * d.layers * C * 4);
   w.ctab = take((size_t)B * d.layers * C * 4);
-  w.ktab = take((size_t)B * d.layers * C * 4);
-  w.k00 = take((size_t)B * C * 4);
+  w.ktab = take((size_t)K * B * d.layers * C * 4);
+  w.k00 = take((size_t)K * B * C * 4);
   w.U = take((size_t)B * T * C * 4);
   w.U2 = take((size_t)B * T * C * 4);
   w.S = take((size_t)B * T * C * 4);
-  w.status = take(256);
   w.total = p;
   return w;
 }
@@ -914,8 +926,8 @@ int plan_groups(int L, int R, int pair_slots) {
 size_t bf16_packed_bytes(const mgb_model_dims& d) {
   return small_layout(d).total * sizeof(float) + (size_t)2 * num_wslots(d) * SLOT_BYTES;
 }
-size_t bf16_workspace_bytes(const mgb_model_dims& d, int B, int T, int) { return work_layout(d, B, T).total; }
-size_t bf16_status_offset(const mgb_model_dims& d, int B, int T) { return work_layout(d, B, T).status; }
+size_t bf16_workspace_bytes(const mgb_model_dims& d, int B, int T, int K) { return work_layout(d, B, T, K > 0 ? K : 1).total; }
+size_t bf16_status_offset(const mgb_model_dims& d, int B, int T) { return work_layout(d, B, T, 1).status; }
 
 int bf16_pack(const mgb_model_dims& d, const float* flat, void* packed, cudaStream_t s) {
   const FlatOffsets f = flat_offsets(d);
@@ -938,22 +950,59 @@ int bf16_pack(const mgb_model_dims& d, const float* flat, void* packed, cudaStre
   return MGB_OK;
 }
 
-int bf16_denoiser(const mgb_model_dims& d, const void* packed, const float* x, const int64_t* t, const float* cond,
-                  const float* spk, const float* noise, const float* sched, int K, int clip, float* x_prev,
-                  float* out_x0, int B, int T, void* ws, bool cond_ready, cudaStream_t s) {
+// Once per sampling call (or per Denoiser call): the bf16 cond image and every per-utterance constant.
+//   t != nullptr : one step, per-utterance timesteps t[B] (Denoiser.forward / p_sample)
+//   t == nullptr : `nsteps` steps, step s runs every utterance at timestep s (the sampling loop); the step-embedding
+//                  MLP and the 20 diffusion projections are evaluated once per STEP, not per utterance.
+int bf16_prepare(const mgb_model_dims& d, const void* packed, const int64_t* t, int nsteps, const float* cond,
+                 const float* spk, int B, int T, void* ws, cudaStream_t s) {
   MGB_REQUIRE(d.n_mel == 80, MGB_E_UNSUPPORTED, "the bf16 path is built for n_mel == 80 (got %d)", d.n_mel);
   const SmallOff o = small_layout(d);
-  const WorkBf16 w = work_layout(d, B, T);
+  const WorkBf16 w = work_layout(d, B, T, nsteps);
   const float* P = static_cast<const float*>(packed);
   uint8_t* W = static_cast<uint8_t*>(ws);
   const int L = d.layers, H = d.d_encoder;
   float* dvec = reinterpret_cast<float*>(W + w.d);
   float* dtab = reinterpret_cast<float*>(W + w.dtab);
   float* ctab = reinterpret_cast<float*>(W + w.ctab);
-  float* ktab = reinterpret_cast<float*>(W + w.ktab);
-  float* k00 = reinterpret_cast<float*>(W + w.k00);
-  __nv_bfloat16* condT = reinterpret_cast<__nv_bfloat16*>(W + w.condT);
-  int* status = reinterpret_cast<int*>(W + w.status);
+  const bool uniform = t == nullptr;
+  const int U = uniform ? nsteps : B;
+  {
+    dim3 grid((w.Rp + 7) / 8);
+    cond_pack_kernel<<<grid, 256, 0, s>>>(cond, reinterpret_cast<__nv_bfloat16*>(W + w.condT), T, w.Tg, w.R, w.Rp);
+    MGB_CUDA_CHECK(cudaMemsetAsync(W + w.status, 0, sizeof(int), s));
+    note_launch();
+  }
+  const int64_t* tt = t;
+  if (uniform) {
+    int64_t* ts = reinterpret_cast<int64_t*>(W + w.tsteps);
+    iota_i64_kernel<<<(nsteps + 127) / 128, 128, 0, s>>>(ts, nsteps);
+    note_launch();
+    tt = ts;
+  }
+  launch_step_mlp(tt, P + o.mlp0_wt, P + o.mlp2_wt, reinterpret_cast<float*>(W + w.h), dvec, U, C, s);
+  dim3 gd(L, (U + TAB_UB - 1) / TAB_UB), gc(L, (B + TAB_UB - 1) / TAB_UB);
+  proj_table_kernel<<<gd, 256, (size_t)TAB_UB * C * sizeof(float), s>>>(dvec, C, P + o.dproj_wt, (size_t)C * C, nullptr, 0,
+                                                                        dtab, U, L, C);
+  proj_table_kernel<<<gc, 256, (size_t)TAB_UB * H * sizeof(float), s>>>(
+      d.multi_speaker ? spk : nullptr, H, P + o.sproj_wt, (size_t)H * C, P + o.cproj_b, (size_t)C, ctab, B, L, C);
+  ktab_kernel<<<dim3(L, B, uniform ? nsteps : 1), 256, 0, s>>>(dtab, ctab, P + o.bo_x, reinterpret_cast<float*>(W + w.ktab),
+                                                               reinterpret_cast<float*>(W + w.k00), L, B, uniform ? 1 : 0);
+  note_launch(5);   // step MLP (2), two projection tables, ktab
+  MGB_LAUNCH_CHECK();
+  return MGB_OK;
+}
+
+// One Denoiser call (+ fused posterior update when sched != nullptr) on a workspace prepared by bf16_prepare with
+// the same (B, T, nsteps).  step = which prepared table to use; t_uniform >= 0 replaces t[b] in the posterior.
+int bf16_run(const mgb_model_dims& d, const void* packed, const float* x, const int64_t* t, int t_uniform, int step,
+             int nsteps, const float* noise, const float* sched, int K, int clip, float* x_prev, float* out_x0, int B, int T,
+             void* ws, cudaStream_t s) {
+  const SmallOff o = small_layout(d);
+  const WorkBf16 w = work_layout(d, B, T, nsteps);
+  const float* P = static_cast<const float*>(packed);
+  uint8_t* W = static_cast<uint8_t*>(ws);
+  const int L = d.layers;
 
   static int pair_slots = 0;
   if (!pair_slots) {
@@ -963,34 +1012,19 @@ int bf16_denoiser(const mgb_model_dims& d, const void* packed, const float* x, c
     MGB_CUDA_CHECK(cudaFuncSetAttribute(fused_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
     pair_slots = sms / 2 > 0 ? sms / 2 : 1;
   }
-  if (!cond_ready) {
-    dim3 grid((w.Rp + 7) / 8);
-    cond_pack_kernel<<<grid, 256, 0, s>>>(cond, condT, T, w.Tg, w.R, w.Rp);
-    MGB_CUDA_CHECK(cudaMemsetAsync(status, 0, sizeof(int), s));
-    note_launch();
-  }
-  launch_step_mlp(t, P + o.mlp0_wt, P + o.mlp2_wt, reinterpret_cast<float*>(W + w.h), dvec, B, C, s);
-  {
-    dim3 grid(L, (B + TAB_UB - 1) / TAB_UB);
-    proj_table_kernel<<<grid, 256, (size_t)TAB_UB * C * sizeof(float), s>>>(dvec, C, P + o.dproj_wt, (size_t)C * C,
-                                                                            nullptr, 0, dtab, B, L, C);
-    proj_table_kernel<<<grid, 256, (size_t)TAB_UB * H * sizeof(float), s>>>(
-        d.multi_speaker ? spk : nullptr, H, P + o.sproj_wt, (size_t)H * C, P + o.cproj_b, (size_t)C, ctab, B, L, C);
-    dim3 kgrid(L, B);
-    ktab_kernel<<<kgrid, 256, 0, s>>>(dtab, ctab, P + o.bo_x, ktab, k00, L);
-    note_launch(5);   // step MLP (2), two projection tables, ktab
-  }
   FusedParams p{};
   p.wimg = reinterpret_cast<const uint8_t*>(P + o.total);
   p.wimg_rank_stride = (size_t)num_wslots(d) * SLOT_BYTES;
-  p.condT = condT; p.Rp = w.Rp;
-  p.x_t = x; p.noise = noise; p.x_prev = x_prev; p.x0_out = out_x0; p.sched = sched; p.t = t;
+  p.condT = reinterpret_cast<const __nv_bfloat16*>(W + w.condT); p.Rp = w.Rp;
+  p.x_t = x; p.noise = noise; p.x_prev = x_prev; p.x0_out = out_x0; p.sched = sched; p.t = t; p.t_uniform = t_uniform;
   p.K = K; p.clip = clip; p.n_mel = d.n_mel;
-  p.ktab = ktab; p.k00 = k00; p.conv_bias = P + o.conv_bias; p.bsum_skip = P + o.bsum_skip;
+  p.ktab = reinterpret_cast<const float*>(W + w.ktab) + (size_t)step * B * L * C;
+  p.k00 = reinterpret_cast<const float*>(W + w.k00) + (size_t)step * B * C;
+  p.conv_bias = P + o.conv_bias; p.bsum_skip = P + o.bsum_skip;
   p.b_in = P + o.b_in; p.b_skip = P + o.b_skip; p.b_out = P + o.b_out;
   float* Ubuf[2] = {reinterpret_cast<float*>(W + w.U), reinterpret_cast<float*>(W + w.U2)};
   p.S = reinterpret_cast<float*>(W + w.S);
-  p.B = B; p.T = T; p.Tg = w.Tg; p.R = w.R; p.L = L; p.status = status;
+  p.B = B; p.T = T; p.Tg = w.Tg; p.R = w.R; p.L = L; p.status = reinterpret_cast<int*>(W + w.status);
   const int ngroups = plan_groups(L, w.R, pair_slots);
   for (int g = 0; g < ngroups; ++g) {
     p.lb = g * L / ngroups;

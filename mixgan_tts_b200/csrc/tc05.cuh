@@ -242,6 +242,13 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar_addr) {
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_bar_addr) {
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar_addr) : "memory");
 }
+// Remote (DSMEM) store that reports its bytes to an mbarrier in the DESTINATION CTA (complete_tx): the consumer
+// waits on that barrier instead of the producer paying a cluster-scope fence.  Both addresses are shared::cluster.
+__device__ __forceinline__ void st_async_v4(uint32_t cluster_addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d,
+                                            uint32_t cluster_bar_addr) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
+               ::"r"(cluster_addr), "r"(a), "r"(b), "r"(c), "r"(d), "r"(cluster_bar_addr) : "memory");
+}
 __device__ __forceinline__ void fence_acq_rel_cluster() { asm volatile("fence.acq_rel.cluster;" ::: "memory"); }
 // wait on a local barrier whose arrivals may come from the peer CTA (acquire at cluster scope)
 __device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar_addr, uint32_t parity) {

@@ -106,3 +106,28 @@ def test_two_cta_pair_conventions(n, ksteps):
     err_bot = (D[128:] - ref[128:]).abs().max().item()
     _report(f"2cta n={n} ksteps={ksteps}: status={int(st.item())} err={err:.3e} (rows 0-127 {err_top:.3e}, rows 128-255 {err_bot:.3e})")
     assert int(st.item()) == 0 and err < 1e-3
+
+
+@pytest.mark.parametrize("n", [128, 256])
+def test_aliased_operand_lbo0_sbo0(n):
+    """LBO = SBO = 0 makes every 8-row group and both k-chunks of the A operand read the SAME 128-byte core
+    matrix: A[r][k] = block[r % 8][k % 8].  The fused kernel uses this as a 128-byte "ones" operand that adds the
+    convolution bias inside the MMA."""
+    lib = _lib.load()
+    g = torch.Generator(device="cpu").manual_seed(n)
+    block = (torch.randn(8, 8, generator=g) * 0.5).bfloat16().cuda()
+    Bm = (torch.randn(n, 16, generator=g) * 0.5).bfloat16().cuda()
+    a_img = torch.zeros(128 * 16, dtype=torch.bfloat16, device="cuda")     # 4 KB image, only the first 128 B matter
+    a_img[:64] = block.reshape(-1)
+    b_img = _image(Bm)
+    D = torch.full((128, n), float("nan"), device="cuda")
+    st = torch.zeros(1, dtype=torch.int32, device="cuda")
+    rc = lib.mgb_probe_umma(_lib.ptr(a_img), a_img.numel() * 2, _lib.ptr(b_img), b_img.numel() * 2,
+                            0, 0, 0, 0, 0, n * 16, 128, 2 * n * 16, n, 1, 1, _lib.ptr(D), _lib.ptr(st),
+                            C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    _lib.check(rc, "mgb_probe_umma")
+    torch.cuda.synchronize()
+    A = block.float().repeat(16, 2)                       # [128, 16]
+    err = (D - A @ Bm.float().t()).abs().max().item()
+    _report(f"aliased A operand (LBO=SBO=0) n={n}: status={int(st.item())} err={err:.3e}")
+    assert int(st.item()) == 0 and err < 1e-3

@@ -45,13 +45,13 @@ namespace {
 using namespace smallops;
 
 constexpr int C = 256;
-constexpr int SLOT_BYTES = 8192;       // one ring slot: a weight HALF tile or a cond tile of K=32
-constexpr int NSLOTS = 12;
+constexpr int SLOT_BYTES = 16384;      // one ring slot: a weight HALF tile (K=128 x 64 rows or K=64 x 128 rows) or a cond tile of K=64
+constexpr int NSLOTS = 6;
 constexpr int A_ROWS = 130;            // 128 tile rows + one halo row each side
 constexpr uint32_t A_LBO = A_ROWS * 16;
 constexpr uint32_t G_LBO = 128 * 16;
-constexpr uint32_t W128_LBO = 64 * 16;   // weight half tile with 64 rows  (N = 128 MMAs), K = 64 per slot
-constexpr uint32_t W256_LBO = 128 * 16;  // weight half tile with 128 rows (N = 256 MMAs) and cond tiles, K = 32 per slot
+constexpr uint32_t W128_LBO = 64 * 16;   // weight half tile with 64 rows  (N = 128 MMAs), K = 128 per slot
+constexpr uint32_t W256_LBO = 128 * 16;  // weight half tile with 128 rows (N = 256 MMAs) and cond tiles, K = 64 per slot
 constexpr uint32_t SBO = 128;
 constexpr int SMEM_A = 32 * A_LBO;
 constexpr int SMEM_G = 32 * G_LBO;
@@ -66,9 +66,10 @@ constexpr int COND_PAD_HI = 288;       // zero rows behind it (>= TILE_ROWS + MA
 constexpr long long WAIT_CYCLES = 400000000LL;   // ~0.2 s: a protocol bug ends the kernel, never hangs it
 
 // weight-stream slot indices (see pack_images_kernel); each CTA rank has its own image of every slot
-constexpr int W_IN = 0, W_P0 = 3, W_SKIPP = 11, W_OUT = 19, W_LAYER0 = 23, W_PER_LAYER = 76;
-// per layer: 4 conv chunks x (12 weight slots in (kb, tap) order + 1 bias slot), skip j=0, res cond, res g, skip j=1..3
-constexpr int WL_SKIPA = 52, WL_RCOND = 54, WL_RG = 62, WL_SKIPB = 70;
+constexpr int W_IN = 0, W_P0 = 2, W_SKIPP = 6, W_OUT = 10, W_LAYER0 = 12, W_PER_LAYER = 40;
+// per layer: 4 conv chunks x (6 weight slots of two (kb, tap) blocks each + 1 bias slot), skip j=0, res cond (4),
+// res g (4), skip j=1..3 (3)
+constexpr int WL_SKIPA = 28, WL_RCOND = 29, WL_RG = 33, WL_SKIPB = 37;
 constexpr int BIAS_SLOT_BYTES = 2048;  // [2 k-chunks][64 rows][8 bf16]: k=0 bias hi, k=1 bias lo
 constexpr int ONES_OFF = 384;          // 128-byte all-rows-equal [1,1,0,...] operand inside the barrier block
 
@@ -171,8 +172,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_p
   const uint32_t slots0 = tc::smem_u32(sSlots);
 
   // number of ring-slot loads of this launch (the producer, the relay and the MMA issuer walk the same sequence)
-  int n_loads = (first_group ? 3 + 16 : 0) + (last_group ? 12 : 0);
-  for (int l = p.lb; l < p.le; ++l) n_loads += (l < p.L - 1) ? 84 : 60;
+  int n_loads = (first_group ? 2 + 8 : 0) + (last_group ? 6 : 0);
+  for (int l = p.lb; l < p.le; ++l) n_loads += (l < p.L - 1) ? 44 : 32;
 
   // conv-input tiles of this launch whose edge rows are exchanged between the two CTAs (u_lb and one per block)
   int n_halo_gens = 1;
@@ -212,38 +213,38 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_p
         __syncwarp();
         advance();
       };
-      auto load_cond = [&](int m) {   // cond channels [32m, 32m+32) of this CTA's 128 rows
+      auto load_cond = [&](int m) {   // cond channels [64m, 64m+64) of this CTA's 128 rows
         wait_empty();
         if (tc::elect_one()) {
           const uint32_t fb = bar0 + (B_FULL + slot) * 8;
           tc::mbar_arrive_expect_tx_addr(fb, SLOT_BYTES);
 #pragma unroll
-          for (int k8 = 0; k8 < 4; ++k8)
-            tc::bulk_g2s_addr(slots0 + slot * SLOT_BYTES + k8 * 2048, condb + (size_t)(m * 4 + k8) * cond_chunk, 2048, fb);
+          for (int k8 = 0; k8 < 8; ++k8)
+            tc::bulk_g2s_addr(slots0 + slot * SLOT_BYTES + k8 * 2048, condb + (size_t)(m * 8 + k8) * cond_chunk, 2048, fb);
         }
         __syncwarp();
         advance();
       };
       if (first_group) {
-        load_w(W_IN, SLOT_BYTES); load_w(W_IN + 1, SLOT_BYTES); load_w(W_IN + 2, 4096);
-        for (int m = 0; m < 8; ++m) { load_cond(m); load_w(W_P0 + m, SLOT_BYTES); }
+        load_w(W_IN, SLOT_BYTES); load_w(W_IN + 1, 4096);
+        for (int m = 0; m < 4; ++m) { load_cond(m); load_w(W_P0 + m, SLOT_BYTES); }
       }
       for (int l = p.lb; l < p.le; ++l) {
         const int base = W_LAYER0 + l * W_PER_LAYER;
-        for (int i = 0; i < 4; ++i) {                                       // conv chunk: 12 weight slots + bias slot
-          for (int j = 0; j < 12; ++j) load_w(base + 13 * i + j, SLOT_BYTES);
-          load_w(base + 13 * i + 12, BIAS_SLOT_BYTES);
+        for (int i = 0; i < 4; ++i) {                                       // conv chunk: 6 weight slots + bias slot
+          for (int j = 0; j < 6; ++j) load_w(base + 7 * i + j, SLOT_BYTES);
+          load_w(base + 7 * i + 6, BIAS_SLOT_BYTES);
         }
-        load_w(base + WL_SKIPA, SLOT_BYTES); load_w(base + WL_SKIPA + 1, SLOT_BYTES);   // skip j=0
+        load_w(base + WL_SKIPA, SLOT_BYTES);                                  // skip j=0
         if (l < p.L - 1) {
-          for (int m = 0; m < 8; ++m) { load_cond(m); load_w(base + WL_RCOND + m, SLOT_BYTES); }
-          for (int m = 0; m < 8; ++m) load_w(base + WL_RG + m, SLOT_BYTES);
+          for (int m = 0; m < 4; ++m) { load_cond(m); load_w(base + WL_RCOND + m, SLOT_BYTES); }
+          for (int m = 0; m < 4; ++m) load_w(base + WL_RG + m, SLOT_BYTES);
         }
-        for (int i = 0; i < 6; ++i) load_w(base + WL_SKIPB + i, SLOT_BYTES);
+        for (int i = 0; i < 3; ++i) load_w(base + WL_SKIPB + i, SLOT_BYTES);
       }
       if (last_group) {
-        for (int i = 0; i < 8; ++i) load_w(W_SKIPP + i, SLOT_BYTES);
-        for (int i = 0; i < 4; ++i) load_w(W_OUT + i, SLOT_BYTES);
+        for (int i = 0; i < 4; ++i) load_w(W_SKIPP + i, SLOT_BYTES);
+        for (int i = 0; i < 2; ++i) load_w(W_OUT + i, SLOT_BYTES);
       }
       if (PROF && lane == 0) { p.prof[blockIdx.x * 16 + 12] = t_empty; p.prof[blockIdx.x * 16 + 13] = clock64() - t_start; }
     } else if (warp == 1 && rank != 0) {
@@ -291,9 +292,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_p
         phase ^= wrap ? 1u : 0u;
       };
       long long t_full = 0, t_temp = 0, t_ar = 0, t_gr = 0, t_full_first = -1, t_full_max = 0, n_full_slow = 0;
+      // FULL barrier of the CURRENT slot, tested one slot ahead: the ~90-cycle try_wait of the next slot runs
+      // while this slot's MMAs are being issued.
+      uint32_t pre = 0;
+      auto pretest = [&]() { pre = tc::mbar_try_wait_addr(bar0 + (B_FULL + slot) * 8, phase) ? 1u : 0u; };
       auto wait_full = [&]() {
         const long long t0 = PROF ? clock64() : 0;
-        tc::mbar_wait_trap(bar0 + (B_FULL + slot) * 8, phase, WAIT_CYCLES, p.status, 2);
+        if (!pre) tc::mbar_wait_trap(bar0 + (B_FULL + slot) * 8, phase, WAIT_CYCLES, p.status, 2);
         if (PROF) {
           const long long dt = clock64() - t0;
           t_full += dt;
@@ -302,58 +307,80 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_p
         }
         tc::tc_fence_after();
       };
-      // one N=128 weight slot = 4 k-steps of K=16 with the A operand from a resident tile (descriptor a0)
-      auto mma_w128 = [&](uint64_t a0, uint32_t a_kstep16, uint32_t d_tmem, uint32_t acc_first) {
+      // one N=128 weight slot = 8 k-steps of K=16: the first four against a0, the last four against a1
+      auto mma_w128 = [&](uint64_t a0, uint64_t a1, uint32_t a_kstep16, uint32_t d_tmem, uint32_t acc_first) {
         wait_full();
+        const uint32_t s0 = slot;
+        advance();
+        pretest();
         if (tc::elect_one()) {
-          const uint64_t b0 = dS128 + (uint64_t)(slot * (SLOT_BYTES >> 4));
+          const uint64_t b0 = dS128 + (uint64_t)(s0 * (SLOT_BYTES >> 4));
+          constexpr uint32_t BK = (2 * W128_LBO) >> 4;
           tc::umma_bf16_2cta(d_tmem, a0, b0, idesc128, acc_first);
-          tc::umma_bf16_2cta(d_tmem, a0 + a_kstep16, b0 + (2 * W128_LBO >> 4), idesc128, 1u);
-          tc::umma_bf16_2cta(d_tmem, a0 + 2 * a_kstep16, b0 + 2 * (2 * W128_LBO >> 4), idesc128, 1u);
-          tc::umma_bf16_2cta(d_tmem, a0 + 3 * a_kstep16, b0 + 3 * (2 * W128_LBO >> 4), idesc128, 1u);
-          tc::umma_commit_2cta_mc(bar0 + (B_EMPTY + slot) * 8);
+          tc::umma_bf16_2cta(d_tmem, a0 + a_kstep16, b0 + BK, idesc128, 1u);
+          tc::umma_bf16_2cta(d_tmem, a0 + 2 * a_kstep16, b0 + 2 * BK, idesc128, 1u);
+          tc::umma_bf16_2cta(d_tmem, a0 + 3 * a_kstep16, b0 + 3 * BK, idesc128, 1u);
+          tc::umma_bf16_2cta(d_tmem, a1, b0 + 4 * BK, idesc128, 1u);
+          tc::umma_bf16_2cta(d_tmem, a1 + a_kstep16, b0 + 5 * BK, idesc128, 1u);
+          tc::umma_bf16_2cta(d_tmem, a1 + 2 * a_kstep16, b0 + 6 * BK, idesc128, 1u);
+          tc::umma_bf16_2cta(d_tmem, a1 + 3 * a_kstep16, b0 + 7 * BK, idesc128, 1u);
+          tc::umma_commit_2cta_mc(bar0 + (B_EMPTY + s0) * 8);
         }
         __syncwarp();
-        advance();
       };
       // the bias slot of a conv chunk: one K=16 step against the "ones" operand adds (bias_hi + bias_lo) to every row
       auto mma_bias = [&](uint32_t d_tmem) {
         wait_full();
+        const uint32_t s0 = slot;
+        advance();
+        pretest();
         if (tc::elect_one()) {
-          tc::umma_bf16_2cta(d_tmem, dOnes, dS128 + (uint64_t)(slot * (SLOT_BYTES >> 4)), idesc128, 1u);
-          tc::umma_commit_2cta_mc(bar0 + (B_EMPTY + slot) * 8);
+          tc::umma_bf16_2cta(d_tmem, dOnes, dS128 + (uint64_t)(s0 * (SLOT_BYTES >> 4)), idesc128, 1u);
+          tc::umma_commit_2cta_mc(bar0 + (B_EMPTY + s0) * 8);
         }
         __syncwarp();
-        advance();
       };
-      // one N=256 weight slot = 2 k-steps (or 1 for the K=16 tail of the input projection)
-      auto mma_w256 = [&](uint64_t a0, uint32_t a_kstep16, uint32_t d_tmem, uint32_t acc_first, bool two) {
+      // one N=256 weight slot = 4 k-steps (or 1 for the K=16 tail of the input projection)
+      auto mma_w256 = [&](uint64_t a0, uint32_t a_kstep16, uint32_t d_tmem, uint32_t acc_first, bool four) {
         wait_full();
+        const uint32_t s0 = slot;
+        advance();
+        pretest();
         if (tc::elect_one()) {
-          const uint64_t b0 = dS256 + (uint64_t)(slot * (SLOT_BYTES >> 4));
+          const uint64_t b0 = dS256 + (uint64_t)(s0 * (SLOT_BYTES >> 4));
+          constexpr uint32_t BK = (2 * W256_LBO) >> 4;
           tc::umma_bf16_2cta(d_tmem, a0, b0, idesc256, acc_first);
-          if (two) tc::umma_bf16_2cta(d_tmem, a0 + a_kstep16, b0 + (2 * W256_LBO >> 4), idesc256, 1u);
-          tc::umma_commit_2cta_mc(bar0 + (B_EMPTY + slot) * 8);
+          if (four) {
+            tc::umma_bf16_2cta(d_tmem, a0 + a_kstep16, b0 + BK, idesc256, 1u);
+            tc::umma_bf16_2cta(d_tmem, a0 + 2 * a_kstep16, b0 + 2 * BK, idesc256, 1u);
+            tc::umma_bf16_2cta(d_tmem, a0 + 3 * a_kstep16, b0 + 3 * BK, idesc256, 1u);
+          }
+          tc::umma_commit_2cta_mc(bar0 + (B_EMPTY + s0) * 8);
         }
         __syncwarp();
-        advance();
       };
-      // a cond slot (A operand, K=32) followed by its N=256 weight slot
+      // a cond slot (A operand, K=64) followed by its N=256 weight slot
       auto mma_cond = [&](uint32_t d_tmem, uint32_t acc_first) {
         wait_full();
         const uint32_t sa = slot;
         advance();
+        pretest();
         wait_full();
+        const uint32_t sb = slot;
+        advance();
+        pretest();
         if (tc::elect_one()) {
           const uint64_t a0 = dS256 + (uint64_t)(sa * (SLOT_BYTES >> 4));
-          const uint64_t b0 = dS256 + (uint64_t)(slot * (SLOT_BYTES >> 4));
+          const uint64_t b0 = dS256 + (uint64_t)(sb * (SLOT_BYTES >> 4));
+          constexpr uint32_t BK = (2 * W256_LBO) >> 4;
           tc::umma_bf16_2cta(d_tmem, a0, b0, idesc256, acc_first);
-          tc::umma_bf16_2cta(d_tmem, a0 + (2 * W256_LBO >> 4), b0 + (2 * W256_LBO >> 4), idesc256, 1u);
+          tc::umma_bf16_2cta(d_tmem, a0 + BK, b0 + BK, idesc256, 1u);
+          tc::umma_bf16_2cta(d_tmem, a0 + 2 * BK, b0 + 2 * BK, idesc256, 1u);
+          tc::umma_bf16_2cta(d_tmem, a0 + 3 * BK, b0 + 3 * BK, idesc256, 1u);
           tc::umma_commit_2cta_mc(bar0 + (B_EMPTY + sa) * 8);
-          tc::umma_commit_2cta_mc(bar0 + (B_EMPTY + slot) * 8);
+          tc::umma_commit_2cta_mc(bar0 + (B_EMPTY + sb) * 8);
         }
         __syncwarp();
-        advance();
       };
       auto temp_acquire = [&](uint32_t tb) {   // wait until both CTAs' epilogues drained the previous use of buffer tb
         const long long t0 = PROF ? clock64() : 0;
@@ -375,15 +402,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_p
       auto tm_t = [&](uint32_t tb) { return TM_TEMP0 + tb * 128u; };
       constexpr uint32_t A_K16 = (2 * A_LBO) >> 4, G_K16 = (2 * G_LBO) >> 4;   // descriptor step per K=16
 
+      pretest();
       if (first_group) {
         wait_bar(B_AREADY, n_aready); wait_bar(B_AREADY + 1, n_aready); ++n_aready;   // x_t tile as bf16, channels 0..79
         temp_acquire(0); temp_acquire(1);               // input projection, K = 80, N = 256
         mma_w256(dA + (16 >> 4), A_K16, tm_t(0), 0u, true);
-        mma_w256(dA + ((16 + 4 * A_LBO) >> 4), A_K16, tm_t(0), 1u, true);
         mma_w256(dA + ((16 + 8 * A_LBO) >> 4), A_K16, tm_t(0), 1u, false);
         temp_publish(0); temp_publish(1);
         temp_acquire(0); temp_acquire(1);               // conditioner projection of layer 0
-        for (int m = 0; m < 8; ++m) mma_cond(tm_t(0), m ? 1u : 0u);
+        for (int m = 0; m < 4; ++m) mma_cond(tm_t(0), m ? 1u : 0u);
         temp_publish(0); temp_publish(1);
       }
       for (int l = p.lb; l < p.le; ++l) {
@@ -393,17 +420,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_p
         for (uint32_t i = 0; i < 4; ++i) {              // k=3 conv, chunk i = 64 gate + 64 filter channels
           const uint32_t tb = i & 1;
           temp_acquire(tb);
-          uint32_t acc = 0;
-          uint64_t a = dA;
 #pragma unroll 1
-          for (uint32_t kb = 0; kb < 4; ++kb) {         // 64-channel blocks
-            if (i == 0 && kb == 2) { wait_bar(B_AREADY + 1, n_aready); wait_bar(B_HALOP + 1, n_halo); }   // channels [128, 256)
-#pragma unroll 1
-            for (uint32_t tap = 0; tap < 3; ++tap) {    // tap = +16 B row shift of the start address
-              mma_w128(a + tap, A_K16, tm_t(tb), acc);
-              acc = 1;
-            }
-            a += (8 * A_LBO) >> 4;
+          for (uint32_t j = 0; j < 6; ++j) {            // slot j = blocks q = 2j, 2j+1 of the (kb, tap) sequence q = 3 kb + tap
+            if (i == 0 && j == 3) { wait_bar(B_AREADY + 1, n_aready); wait_bar(B_HALOP + 1, n_halo); }   // channels [128, 256)
+            const uint32_t q0 = 2 * j, q1 = 2 * j + 1;
+            const uint32_t kb0 = q0 / 3, kb1 = q1 / 3;
+            const uint64_t a0 = dA + (q0 - 3 * kb0) + kb0 * ((8 * A_LBO) >> 4);   // tap = +16 B row shift of the start address
+            const uint64_t a1 = dA + (q1 - 3 * kb1) + kb1 * ((8 * A_LBO) >> 4);
+            mma_w128(a0, a1, A_K16, tm_t(tb), j ? 1u : 0u);
           }
           mma_bias(tm_t(tb));
           temp_publish(tb);
@@ -412,17 +436,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_p
         const uint32_t skip_first = (l == p.lb) ? 0u : 1u;
         wait_bar(B_GREADY + 0, n_gready);               // skip projection, gate channels [0, 64)
         mma_w256(dG, G_K16, TM_SKIP, skip_first, true);
-        mma_w256(dG + ((4 * G_LBO) >> 4), G_K16, TM_SKIP, 1u, true);
         if (l < p.L - 1) {                              // residual-out + conditioner delta, N = 256
           temp_acquire(0); temp_acquire(1);
 #pragma unroll 1
-          for (uint32_t m = 0; m < 8; ++m) mma_cond(tm_t(0), m ? 1u : 0u);
+          for (uint32_t m = 0; m < 4; ++m) mma_cond(tm_t(0), m ? 1u : 0u);
           uint64_t a = dG;
 #pragma unroll 1
-          for (uint32_t m = 0; m < 8; ++m) {
-            if ((m & 1) == 0) wait_bar(B_GREADY + (m >> 1), n_gready);
+          for (uint32_t m = 0; m < 4; ++m) {
+            wait_bar(B_GREADY + m, n_gready);
             mma_w256(a, G_K16, tm_t(0), 1u, true);
-            a += (4 * G_LBO) >> 4;
+            a += (8 * G_LBO) >> 4;
           }
           temp_publish(0); temp_publish(1);
         } else {
@@ -432,9 +455,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_p
         {                                               // rest of the skip projection, gate channels [64, 256)
           uint64_t a = dG + ((8 * G_LBO) >> 4);
 #pragma unroll 1
-          for (uint32_t m = 0; m < 6; ++m) {
+          for (uint32_t m = 0; m < 3; ++m) {
             mma_w256(a, G_K16, TM_SKIP, 1u, true);
-            a += (4 * G_LBO) >> 4;
+            a += (8 * G_LBO) >> 4;
           }
         }
       }
@@ -443,11 +466,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_p
       if (last_group) {
         wait_bar(B_AREADY, n_aready); wait_bar(B_AREADY + 1, n_aready); ++n_aready;   // skip sum / sqrt(L) as bf16 in sA
         temp_acquire(0); temp_acquire(1);
-        for (int m = 0; m < 8; ++m) mma_w256(dA + ((16 + m * 4 * A_LBO) >> 4), A_K16, tm_t(0), m ? 1u : 0u, true);
+        for (int m = 0; m < 4; ++m) mma_w256(dA + ((16 + m * 8 * A_LBO) >> 4), A_K16, tm_t(0), m ? 1u : 0u, true);
         temp_publish(0); temp_publish(1);
         wait_bar(B_GREADY + 0, n_gready++);             // relu(skip projection) as bf16 in sG
         temp_acquire(0);
-        for (int j = 0; j < 4; ++j) mma_w128(dG + ((j * 8 * G_LBO) >> 4), G_K16, tm_t(0), j ? 1u : 0u);
+        for (int j = 0; j < 2; ++j)
+          mma_w128(dG + ((j * 16 * G_LBO) >> 4), dG + (((j * 16 + 8) * G_LBO) >> 4), G_K16, tm_t(0), j ? 1u : 0u);
         temp_publish(0);
       }
       if (PROF && lane == 0) {
@@ -858,7 +882,7 @@ __global__ void pack_images_kernel(const float* __restrict__ flat, const FlatOff
                                    const int nslots, __nv_bfloat16* __restrict__ img) {
   const int slot = blockIdx.x, rank = blockIdx.y;
   const float* fl = nullptr;
-  int kind, m = 0, ci = 0, tap = 0, kb = 0;
+  int kind, m = 0, ci = 0, j = 0;
   // kind: 0 in-proj, 1 cond-proj layer 0, 2 skip-proj, 3 out-proj, 4 conv, 5 res cond delta, 6 res g (Wo_x),
   //       7 skip (Wo_s), 8 unused (zeros), 9 conv bias
   if (slot < W_P0) { kind = 0; m = slot; }
@@ -869,42 +893,44 @@ __global__ void pack_images_kernel(const float* __restrict__ flat, const FlatOff
     const int l = (slot - W_LAYER0) / W_PER_LAYER, rr = (slot - W_LAYER0) % W_PER_LAYER;
     fl = flat + f.layer0 + (size_t)l * f.layer_stride;
     if (rr < WL_SKIPA) {
-      ci = rr / 13;
-      const int idx = rr % 13;
-      if (idx < 12) { kind = 4; kb = idx / 3; tap = idx % 3; } else { kind = 9; }
+      ci = rr / 7;
+      j = rr % 7;
+      kind = j < 6 ? 4 : 9;
     }
-    else if (rr < WL_RCOND) { kind = 7; m = rr - WL_SKIPA; }
+    else if (rr < WL_RCOND) { kind = 7; m = 0; }
     else if (rr < WL_RG) { kind = (l + 1 < L) ? 5 : 8; m = rr - WL_RCOND; }
     else if (rr < WL_SKIPB) { kind = (l + 1 < L) ? 6 : 8; m = rr - WL_RG; }
-    else { kind = 7; m = 2 + rr - WL_SKIPB; }
+    else { kind = 7; m = 1 + rr - WL_SKIPB; }
   }
   const bool n128 = (kind == 3 || kind == 4 || kind == 9);
   const int rows = n128 ? 64 : 128;
   const float gate_scale = rank == 0 ? 0.5f : 1.0f;      // rank 0 holds the gate half of every conv chunk
-  for (int unit = threadIdx.x; unit < 512; unit += blockDim.x) {
+  for (int unit = threadIdx.x; unit < 1024; unit += blockDim.x) {
     const int k8 = unit / rows, row = unit - k8 * rows;
     float v[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      const int k = k8 * 8 + e;             // K index inside the slot
+      const int k = k8 * 8 + e;             // K index inside the slot: [0, 64) for N=256 slots, [0, 128) for N=128 slots
       float x = 0.f;
       switch (kind) {
-        case 0: { const int n = 128 * rank + row, kk = 32 * m + k; if (kk < n_mel) x = flat[f.in_w + (size_t)n * n_mel + kk]; break; }
-        case 1: x = fl[f.rel.cproj_w + (size_t)(128 * rank + row) * C + 32 * m + k]; break;
-        case 2: x = flat[f.skip_w + (size_t)(128 * rank + row) * C + 32 * m + k]; break;
-        case 3: { const int n = 64 * rank + row; if (n < n_mel) x = flat[f.out_w + (size_t)n * C + 64 * m + k]; break; }
+        case 0: { const int n = 128 * rank + row, kk = 64 * m + k; if (kk < n_mel) x = flat[f.in_w + (size_t)n * n_mel + kk]; break; }
+        case 1: x = fl[f.rel.cproj_w + (size_t)(128 * rank + row) * C + 64 * m + k]; break;
+        case 2: x = flat[f.skip_w + (size_t)(128 * rank + row) * C + 64 * m + k]; break;
+        case 3: { const int n = 64 * rank + row; if (n < n_mel) x = flat[f.out_w + (size_t)n * C + 128 * m + k]; break; }
         case 4: {
           const int oc = rank == 0 ? 64 * ci + row : C + 64 * ci + row;   // rank 0: gate half, rank 1: filter half
-          x = gate_scale * fl[f.rel.conv_w + ((size_t)oc * C + 64 * kb + k) * 3 + tap];
+          const int q = 2 * j + (k >> 6);                                 // block of the (kb, tap) sequence, q = 3 kb + tap
+          const int kb = q / 3, tap = q - 3 * kb;
+          x = gate_scale * fl[f.rel.conv_w + ((size_t)oc * C + 64 * kb + (k & 63)) * 3 + tap];
           break;
         }
         case 5: {
-          const size_t o = (size_t)(128 * rank + row) * C + 32 * m + k;
+          const size_t o = (size_t)(128 * rank + row) * C + 64 * m + k;
           x = 1.41421356237309504880f * fl[f.layer_stride + f.rel.cproj_w + o] - fl[f.rel.cproj_w + o];
           break;
         }
-        case 6: x = 0.5f * fl[f.rel.oproj_w + (size_t)(128 * rank + row) * C + 32 * m + k]; break;
-        case 7: x = 0.5f * fl[f.rel.oproj_w + (size_t)(C + 128 * rank + row) * C + 32 * m + k]; break;
+        case 6: x = 0.5f * fl[f.rel.oproj_w + (size_t)(128 * rank + row) * C + 64 * m + k]; break;
+        case 7: x = 0.5f * fl[f.rel.oproj_w + (size_t)(C + 128 * rank + row) * C + 64 * m + k]; break;
         case 9: {   // K = 16 against the "ones" operand [1,1,0,...]: k=0 carries bf16(b), k=1 the bf16 remainder
           if (k < 2) {
             const int oc = rank == 0 ? 64 * ci + row : C + 64 * ci + row;
@@ -918,7 +944,7 @@ __global__ void pack_images_kernel(const float* __restrict__ flat, const FlatOff
       }
       v[e] = x;
     }
-    reinterpret_cast<uint4*>(img)[((size_t)rank * nslots + slot) * 512 + unit] =
+    reinterpret_cast<uint4*>(img)[((size_t)rank * nslots + slot) * 1024 + unit] =
         make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
   }
 }

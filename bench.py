@@ -61,7 +61,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:
@@ -79,13 +79,13 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
             if len(r) < 7:
                 continue
             try:
-                sm.append(float(r[0])); mx.append(float(r[1]))
+                sm.append(float(r[0])); mx.append(float(r[1])); pw.append(float(r[2]))
             except ValueError:
                 continue
             for n, v in zip(names, r[3:7]):
@@ -93,9 +93,10 @@ class ClockSampler:
                     reasons.add(n)
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        busy = sorted(sm)[len(sm) // 2:]          # upper half = samples under load
-        return {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
-                "samples": len(sm)}
+        pmax = max(pw)
+        busy = [c for c, w in zip(sm, pw) if w >= 0.6 * pmax] or sm      # samples taken under load
+        return {"sm_mhz": statistics.median(busy), "sm_min_mhz": min(busy), "sm_max_mhz": max(mx), "power_w_max": pmax,
+                "reasons": sorted(reasons), "samples": len(sm), "samples_under_load": len(busy)}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -206,7 +207,6 @@ def run_ours(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    lib.mgb_profile_enable(1)
     launches0 = lib.mgb_launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -217,37 +217,49 @@ def run_ours(args):
     barrier()
     launches = lib.mgb_launch_count() - launches0
     ms_total = ev0.elapsed_time(ev1)
+
+    # dominant-kernel duration: a short separate pass in which the library brackets every launch of the fused
+    # kernel with CUDA events on the launching stream (kept out of the pass above: the events cost a few us each)
+    prof_steps = min(args.steps, 4)
+    lib.mgb_profile_enable(1)
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0.record()
+    for i in range(prof_steps):
+        step_resident(i)
+    p1.record()
+    torch.cuda.synchronize()
+    ms_prof_pass = p0.elapsed_time(p1)
     ktot, kcnt = C.c_float(0), C.c_int(0)
     _lib.check(lib.mgb_profile_collect(C.byref(ktot), C.byref(kcnt)), "mgb_profile_collect")
     lib.mgb_profile_enable(0)
-    clocks = sampler.stop() if rank == 0 else None
 
     # ------------------------------------------------------------------ end-to-end timing (host buffers)
-    host = [{"cond": s["cond"].cpu().pin_memory(), "pad": s["pad"].cpu().pin_memory()} for s in sets]
-    out_host = torch.empty((B, T, 80), dtype=torch.float32).pin_memory()
+    # The public batch-synthesis harness: pinned host cond/mask in, pinned host mel out; the H2D copy of batch i+1
+    # and the D2H copy of batch i-1 overlap the reverse diffusion of batch i.  Every step's copies are inside the
+    # timed region; the noise is drawn on the device inside GaussianDiffusion.forward, as the reference does.
+    from mixgan_tts_b200.pipeline import BatchSynthesizer
+    host = [(s["cond"].cpu().pin_memory(), s["pad"].cpu().pin_memory()) for s in sets]
+    synth_pipe = BatchSynthesizer(gd, dev)
 
-    def step_e2e(i):
-        h = host[i % NSETS]
-        cond = h["cond"].to(dev, non_blocking=True)
-        pad = h["pad"].to(dev, non_blocking=True)
-        mel = gd(None, cond, None, pad)[0]          # the call a user makes; noise drawn on device inside
-        out_host.copy_(mel, non_blocking=True)
+    def run_e2e(n):
+        acc = 0.0
+        for mel in synth_pipe.run(host[i % NSETS] for i in range(n)):
+            acc += float(mel[0, 0, 0])          # touch the host result of every step
+        return acc
 
-    for i in range(3):
-        step_e2e(i)
+    run_e2e(3)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for i in range(args.steps):
-        step_e2e(i)
+    run_e2e(args.steps)
     e1.record()
     barrier()
     ms_e2e = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
 
-    if world > 1:
-        t = torch.tensor([ms_total, ms_e2e], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total, ms_e2e = float(t[0]), float(t[1])
+    from mixgan_tts_b200 import shard
+    ms_total = shard.max_over_ranks(ms_total, dev)
+    ms_e2e = shard.max_over_ranks(ms_e2e, dev)
 
     if rank == 0:
         pk = peaks()
@@ -255,7 +267,7 @@ def run_ours(args):
         value = frames_per_step * args.steps / (ms_total * 1e-3)
         e2e_val = frames_per_step * args.steps / (ms_e2e * 1e-3)
         k_ms = ktot.value / max(kcnt.value, 1)
-        calls = args.steps * K                      # Denoiser calls in the timed region
+        calls = prof_steps * K                      # Denoiser calls in the profiled pass
         if prec == "bf16":
             # one Denoiser call = `launches_per_call` launches of fused_group_kernel (layer groups);
             # algorithmic FLOPs per launch = FLOPs per call / launches per call
@@ -278,12 +290,13 @@ def run_ours(args):
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": pk["tensor_tflops"], "unit": "TFLOP/s",
                          "frac": achieved / pk["tensor_tflops"], "traffic": None, "kernel": kern,
                          "kernel_ms": k_ms, "kernel_launches_timed": kcnt.value,
-                         "kernel_share_of_step": ktot.value / ms_total if ms_total > 0 else None,
+                         "kernel_share_of_step": ktot.value / ms_prof_pass if ms_prof_pass > 0 else None,
                          "whole_step_tflops": FLOPS_PER_FRAME_STEP * K * B * T * args.steps / (ms_total * 1e-3) / 1e12,
                          "peak_source": pk["source"]},
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(B * T * 256 * 4 + B * T),
                     "d2h_bytes_per_step": int(B * T * 80 * 4), "ms_per_step": ms_e2e / args.steps,
-                    "api": "GaussianDiffusion.forward(None, cond, None, mel_mask) from pinned host tensors"},
+                    "api": "BatchSynthesizer.run (GaussianDiffusion.forward per batch; pinned host cond/mask in, pinned host mel "
+                           "out; copies of neighbouring batches overlap compute on separate streams)"},
             "gpu_launches": int(launches), "clocks": clocks,
         }
         if world == 1 and not args.no_cpu_baseline:
@@ -298,7 +311,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="auto", choices=["auto", "bf16", "fp32"])

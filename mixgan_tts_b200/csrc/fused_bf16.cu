@@ -246,7 +246,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_p
         for (int i = 0; i < 4; ++i) load_w(W_SKIPP + i, SLOT_BYTES);
         for (int i = 0; i < 2; ++i) load_w(W_OUT + i, SLOT_BYTES);
       }
-      if (PROF && lane == 0) { p.prof[blockIdx.x * 16 + 12] = t_empty; p.prof[blockIdx.x * 16 + 13] = clock64() - t_start; }
+      if (PROF && lane == 0) { p.prof[blockIdx.x * 64 + 12] = t_empty; p.prof[blockIdx.x * 64 + 13] = clock64() - t_start; }
     } else if (warp == 1 && rank != 0) {
       // =========================== RELAY (peer CTA) ===========================
       // Forwards "my half of ring slot s has landed" to the leader's FULL[s] barrier.
@@ -295,6 +295,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_p
       // FULL barrier of the CURRENT slot, tested one slot ahead: the ~90-cycle try_wait of the next slot runs
       // while this slot's MMAs are being issued.
       uint32_t pre = 0;
+      long long t_fsite[6] = {0, 0, 0, 0, 0, 0};   // PROF: wait_full by phase: 0 conv, 1 skip j0, 2 res cond, 3 res g, 4 skip j1-3, 5 other
+      int fsite = 5;
       auto pretest = [&]() { pre = tc::mbar_try_wait_addr(bar0 + (B_FULL + slot) * 8, phase) ? 1u : 0u; };
       auto wait_full = [&]() {
         const long long t0 = PROF ? clock64() : 0;
@@ -302,6 +304,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_p
         if (PROF) {
           const long long dt = clock64() - t0;
           t_full += dt;
+          t_fsite[fsite] += dt;
           if (t_full_first < 0) t_full_first = dt; else if (dt > t_full_max) t_full_max = dt;
           if (dt > 300) ++n_full_slow;
         }
@@ -382,10 +385,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_p
         }
         __syncwarp();
       };
+      long long t_site[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // PROF: 0 conv acquire, 1 res acquire T0, 2 res acquire T1, 3 other acquire,
+                                                        //       4 AREADY0, 5 HALOP0, 6 AREADY1, 7 HALOP1
+      int site = 3;
       auto temp_acquire = [&](uint32_t tb) {   // wait until both CTAs' epilogues drained the previous use of buffer tb
         const long long t0 = PROF ? clock64() : 0;
         tc::mbar_wait_trap(bar0 + (B_TEMPTY + tb) * 8, ((n_use >> 1) + 1) & 1, WAIT_CYCLES, p.status, 2);
-        if (PROF) t_temp += clock64() - t0;
+        if (PROF) { t_temp += clock64() - t0; t_site[site == 1 ? 1 + tb : site] += clock64() - t0; }
         tc::tc_fence_after();
         ++n_use;
       };
@@ -396,7 +402,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_p
       auto wait_bar = [&](uint32_t bar, uint32_t n) {
         const long long t0 = PROF ? clock64() : 0;
         tc::mbar_wait_trap(bar0 + bar * 8, n & 1, WAIT_CYCLES, p.status, 2);
-        if (PROF) { if (bar <= B_AREADY + 1) t_ar += clock64() - t0; else t_gr += clock64() - t0; }
+        if (PROF) {
+          const long long dt = clock64() - t0;
+          if (bar <= B_AREADY + 1) { t_ar += dt; t_site[4 + 2 * (bar - B_AREADY)] += dt; }
+          else if (bar >= B_HALOP) { t_ar += dt; t_site[5 + 2 * (bar - B_HALOP)] += dt; }
+          else t_gr += dt;
+        }
         tc::tc_fence_after();
       };
       auto tm_t = [&](uint32_t tb) { return TM_TEMP0 + tb * 128u; };
@@ -419,7 +430,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_p
 #pragma unroll 1
         for (uint32_t i = 0; i < 4; ++i) {              // k=3 conv, chunk i = 64 gate + 64 filter channels
           const uint32_t tb = i & 1;
+          site = 0;
           temp_acquire(tb);
+          site = 3;
+          fsite = 0;
 #pragma unroll 1
           for (uint32_t j = 0; j < 6; ++j) {            // slot j = blocks q = 2j, 2j+1 of the (kb, tap) sequence q = 3 kb + tap
             if (i == 0 && j == 3) { wait_bar(B_AREADY + 1, n_aready); wait_bar(B_HALOP + 1, n_halo); }   // channels [128, 256)
@@ -435,11 +449,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_p
         ++n_aready; ++n_halo;
         const uint32_t skip_first = (l == p.lb) ? 0u : 1u;
         wait_bar(B_GREADY + 0, n_gready);               // skip projection, gate channels [0, 64)
+        fsite = 1;
         mma_w256(dG, G_K16, TM_SKIP, skip_first, true);
         if (l < p.L - 1) {                              // residual-out + conditioner delta, N = 256
+          site = 1;
           temp_acquire(0); temp_acquire(1);
+          site = 3;
+          fsite = 2;
 #pragma unroll 1
           for (uint32_t m = 0; m < 4; ++m) mma_cond(tm_t(0), m ? 1u : 0u);
+          fsite = 3;
           uint64_t a = dG;
 #pragma unroll 1
           for (uint32_t m = 0; m < 4; ++m) {
@@ -452,6 +471,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_p
           for (int j = 1; j < 4; ++j) wait_bar(B_GREADY + j, n_gready);
         }
         ++n_gready;
+        fsite = 4;
         {                                               // rest of the skip projection, gate channels [64, 256)
           uint64_t a = dG + ((8 * G_LBO) >> 4);
 #pragma unroll 1
@@ -475,9 +495,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_p
         temp_publish(0);
       }
       if (PROF && lane == 0) {
-        long long* q = p.prof + blockIdx.x * 16;
+        long long* q = p.prof + blockIdx.x * 64;
         q[0] = t_full; q[1] = t_temp; q[2] = t_ar; q[3] = t_gr; q[4] = clock64() - t_start;
         q[5] = t_full_first; q[6] = t_full_max; q[7] = n_full_slow;
+        for (int i = 0; i < 8; ++i) q[16 + i] = t_site[i];
+        for (int i = 0; i < 6; ++i) q[24 + i] = t_fsite[i];
       }
     }
   } else {
@@ -505,10 +527,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_p
     float u[128];                    // fp32 residual stream: channels 128c + 64h + j at index 64c + j
 
     long long t_tfull = 0;
+    int ts_n = -1;                   // PROF: timeline of accumulator-ready events of layers lb+2 .. lb+4 (warp 4 of every CTA)
     auto temp_wait = [&](int tb) {
       const long long t0 = PROF ? clock64() : 0;
       tc::mbar_wait_trap(bar0 + (B_TFULL + tb) * 8, (n_use >> 1) & 1, WAIT_CYCLES, p.status, 4);
       if (PROF) t_tfull += clock64() - t0;
+      if (PROF && warp == 4 && lane == 0 && ts_n >= 0 && ts_n < 24) p.prof[blockIdx.x * 64 + 32 + ts_n++] = clock64() - t_start;
       ++n_use;
       tc::tc_fence_after();
     };
@@ -620,6 +644,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_p
 
     // ---- residual blocks ----
     for (int l = p.lb; l < p.le; ++l) {
+      if (PROF && l == p.lb + 2) ts_n = 0;
 #pragma unroll 1
       for (int i = 0; i < 4; ++i) {     // conv chunk i: gate columns [32h,32h+32), filter columns 64+[32h,32h+32)
         const int tb = i & 1;
@@ -802,7 +827,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_p
     if (PROF) t_tfull_out = t_tfull;
   }
 
-  if (PROF && warp == 4 && lane == 0) { p.prof[blockIdx.x * 16 + 8] = t_tfull_out; p.prof[blockIdx.x * 16 + 9] = clock64() - t_start; }
+  if (PROF && warp == 4 && lane == 0) { p.prof[blockIdx.x * 64 + 8] = t_tfull_out; p.prof[blockIdx.x * 64 + 9] = clock64() - t_start; }
   // ---- teardown: neither CTA may leave (or free TMEM) while the pair's MMAs can still touch it ----
   tc::tc_fence_before();
   __syncthreads();
@@ -1140,20 +1165,27 @@ int bf16_run(const mgb_model_dims& d, const void* packed, const float* x, const 
     if (do_prof) {
       const int ncta = 2 * npairs;
       long long* dprof = nullptr;
-      cudaMalloc(&dprof, (size_t)ncta * 16 * sizeof(long long));
-      cudaMemset(dprof, 0, (size_t)ncta * 16 * sizeof(long long));
+      cudaMalloc(&dprof, (size_t)ncta * 64 * sizeof(long long));
+      cudaMemset(dprof, 0, (size_t)ncta * 64 * sizeof(long long));
       p.prof = dprof;
       cudaFuncSetAttribute(fused_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL);
       fused_pair_kernel<true><<<ncta, NTHREADS, SMEM_TOTAL, s>>>(p);
       cudaStreamSynchronize(s);
-      long long* h = (long long*)malloc((size_t)ncta * 16 * sizeof(long long));
-      cudaMemcpy(h, dprof, (size_t)ncta * 16 * sizeof(long long), cudaMemcpyDeviceToHost);
-      double a[16] = {0};   // MMA-warp counters exist on leader CTAs only (even blocks)
-      for (int i = 0; i < ncta; i += 2) for (int k = 0; k < 16; ++k) a[k] += (double)h[i * 16 + k] / npairs;
+      long long* h = (long long*)malloc((size_t)ncta * 64 * sizeof(long long));
+      cudaMemcpy(h, dprof, (size_t)ncta * 64 * sizeof(long long), cudaMemcpyDeviceToHost);
+      double a[64] = {0};   // MMA-warp counters exist on leader CTAs only (even blocks)
+      for (int i = 0; i < ncta; i += 2) for (int k = 0; k < 64; ++k) a[k] += (double)h[i * 64 + k] / npairs;
       fprintf(stderr, "[mgb profile] layers [%d,%d) pairs %d | MMA warp: total %.0f wait_full %.0f wait_temp %.0f wait_aready %.0f "
               "wait_gready %.0f (first wait_full %.0f, max later %.0f, waits > 300 cyc: %.0f) | epilogue w4: total %.0f wait_tfull %.0f | "
-              "producer: total %.0f wait_empty %.0f (cycles, mean per leader CTA)\n",
-              p.lb, p.le, npairs, a[4], a[0], a[1], a[2], a[3], a[5], a[6], a[7], a[9], a[8], a[13], a[12]);
+              "producer: total %.0f wait_empty %.0f | temp by site: conv %.0f resT0 %.0f resT1 %.0f other %.0f | A-ready by site: A0 %.0f H0 %.0f "
+              "A1 %.0f H1 %.0f (cycles, mean per leader CTA)\n",
+              p.lb, p.le, npairs, a[4], a[0], a[1], a[2], a[3], a[5], a[6], a[7], a[9], a[8], a[13], a[12], a[16], a[17], a[18],
+              a[19], a[20], a[21], a[22], a[23]);
+      fprintf(stderr, "[mgb profile] wait_full by phase: conv %.0f skip0 %.0f rescond %.0f resg %.0f skip123 %.0f other %.0f\n", a[24], a[25],
+              a[26], a[27], a[28], a[29]);
+      fprintf(stderr, "[mgb timeline] accumulator-ready deltas from layer %d (conv c0..c3, res T0, res T1, ...):", p.lb + 2);
+      for (int k = 1; k < 18; ++k) fprintf(stderr, " %.0f", a[32 + k] - a[32 + k - 1]);
+      fprintf(stderr, "\n");
       free(h); cudaFree(dprof); p.prof = nullptr;
     } else {
       fused_pair_kernel<false><<<2 * npairs, NTHREADS, SMEM_TOTAL, s>>>(p);

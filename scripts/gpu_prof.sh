@@ -1,6 +1,6 @@
 #!/bin/bash
 set -u
-MGB_PROFILE=1 timeout 300 python - <<'PY' 2>&1 | grep -E "mgb profile|Error|error" | head -12
+MGB_PROFILE=1 timeout 300 python - <<'PY' 2>&1 | grep -E "mgb profile|mgb timeline|Error|error" | head -12
 import sys, torch
 sys.path.insert(0, '.'); sys.path.insert(0, 'tests')
 from helpers import Case

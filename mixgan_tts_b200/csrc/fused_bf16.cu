@@ -70,6 +70,7 @@ constexpr int W_IN = 0, W_P0 = 2, W_SKIPP = 6, W_OUT = 10, W_LAYER0 = 12, W_PER_
 // per layer: 4 conv chunks x (6 weight slots of two (kb, tap) blocks each + 1 bias slot), skip j=0, res cond (4),
 // res g (4), skip j=1..3 (3)
 constexpr int WL_SKIPA = 28, WL_RCOND = 29, WL_RG = 33, WL_SKIPB = 37;
+constexpr int KIMG_BYTES = 4096;        // [2 k-chunks][128 rows][8 bf16]
 constexpr int BIAS_SLOT_BYTES = 2048;  // [2 k-chunks][64 rows][8 bf16]: k=0 bias hi, k=1 bias lo
 constexpr int ONES_OFF = 384;          // 128-byte all-rows-equal [1,1,0,...] operand inside the barrier block
 
@@ -96,6 +97,7 @@ struct FusedParams {
   int t_uniform;                // >= 0: every utterance is at this timestep (sampling loop)
   int K, clip, n_mel;
   const float* ktab;            // [B][L][C]
+  const uint8_t* kimg;          // KUNI: [L][2 ranks][4096] bf16 (hi, lo) images of sqrt(2) * k_l as N=256 K=16 weight halves
   const float* k00;             // [B][C]
   const float* bsum_skip;       // [C]
   const float* b_in;            // [C]
@@ -122,7 +124,9 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
-template <bool PROF>
+// KUNI: every utterance shares the per-layer constant k_l (uniform timestep, single speaker): it is added inside
+// the residual GEMM by one more K=16 step against the "ones" operand (kimg) instead of being loaded by the epilogue.
+template <bool PROF, bool KUNI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_pair_kernel(const FusedParams p) {
   const long long t_start = PROF ? clock64() : 0;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -173,7 +177,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_p
 
   // number of ring-slot loads of this launch (the producer, the relay and the MMA issuer walk the same sequence)
   int n_loads = (first_group ? 2 + 8 : 0) + (last_group ? 6 : 0);
-  for (int l = p.lb; l < p.le; ++l) n_loads += (l < p.L - 1) ? 44 : 32;
+  for (int l = p.lb; l < p.le; ++l) n_loads += (l < p.L - 1) ? (KUNI ? 45 : 44) : 32;
 
   // conv-input tiles of this launch whose edge rows are exchanged between the two CTAs (u_lb and one per block)
   int n_halo_gens = 1;
@@ -213,6 +217,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_p
         __syncwarp();
         advance();
       };
+      auto load_raw = [&](const uint8_t* src, uint32_t bytes) {
+        wait_empty();
+        if (tc::elect_one()) {
+          const uint32_t fb = bar0 + (B_FULL + slot) * 8;
+          tc::mbar_arrive_expect_tx_addr(fb, bytes);
+          tc::bulk_g2s_addr(slots0 + slot * SLOT_BYTES, src, bytes, fb);
+        }
+        __syncwarp();
+        advance();
+      };
       auto load_cond = [&](int m) {   // cond channels [64m, 64m+64) of this CTA's 128 rows
         wait_empty();
         if (tc::elect_one()) {
@@ -239,6 +253,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_p
         if (l < p.L - 1) {
           for (int m = 0; m < 4; ++m) { load_cond(m); load_w(base + WL_RCOND + m, SLOT_BYTES); }
           for (int m = 0; m < 4; ++m) load_w(base + WL_RG + m, SLOT_BYTES);
+          if (KUNI) load_raw(p.kimg + ((size_t)l * 2 + rank) * KIMG_BYTES, KIMG_BYTES);
         }
         for (int i = 0; i < 3; ++i) load_w(base + WL_SKIPB + i, SLOT_BYTES);
       }
@@ -339,6 +354,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_p
         pretest();
         if (tc::elect_one()) {
           tc::umma_bf16_2cta(d_tmem, dOnes, dS128 + (uint64_t)(s0 * (SLOT_BYTES >> 4)), idesc128, 1u);
+          tc::umma_commit_2cta_mc(bar0 + (B_EMPTY + s0) * 8);
+        }
+        __syncwarp();
+      };
+      auto mma_kbias = [&](uint32_t d_tmem) {       // KUNI: + sqrt(2) k_l on every row of the residual accumulator
+        wait_full();
+        const uint32_t s0 = slot;
+        advance();
+        pretest();
+        if (tc::elect_one()) {
+          tc::umma_bf16_2cta(d_tmem, dOnes, dS256 + (uint64_t)(s0 * (SLOT_BYTES >> 4)), idesc256, 1u);
           tc::umma_commit_2cta_mc(bar0 + (B_EMPTY + s0) * 8);
         }
         __syncwarp();
@@ -466,6 +492,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_p
             mma_w256(a, G_K16, tm_t(0), 1u, true);
             a += (8 * G_LBO) >> 4;
           }
+          if (KUNI) mma_kbias(tm_t(0));
           temp_publish(0); temp_publish(1);
         } else {
           for (int j = 1; j < 4; ++j) wait_bar(B_GREADY + j, n_gready);
@@ -671,42 +698,62 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_p
         publish(B_GREADY + i);
       }
       if (l < p.L - 1) {
-        // u <- (u + acc)/sqrt(2) + k_l ; write the next conv input.  k_l comes from L2 (no L1 to speak of next to
-        // 227 KB of shared memory): each 32-column phase prefetches the next phase's k before it waits on TMEM.
-        const float4* kbase = reinterpret_cast<const float4*>(p.ktab + ((size_t)b * p.L + l) * C + 64 * h);
-        float4 kv[8];
+        if (KUNI) {
+          // u <- (u + acc)/sqrt(2): acc already holds sqrt(2) k_l (kimg step of the residual GEMM)
 #pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4) kv[j4] = __ldg(kbase + j4);
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          temp_wait(c);
-#pragma unroll
-          for (int hh = 0; hh < 2; ++hh) {
-            uint32_t a[32];
-            tc::tmem_ld32(tm_t(c) + 64 * h + 32 * hh, a);
-            float4 kn[8];
-            if (c * 2 + hh < 3) {
-              const float4* kp = kbase + (hh == 0 ? 32 * c + 8 : 32);   // (c, hh+1) or (1, 0); float4 units
-#pragma unroll
-              for (int j4 = 0; j4 < 8; ++j4) kn[j4] = __ldg(kp + j4);
-            }
+          for (int c = 0; c < 2; ++c) {
+            temp_wait(c);
+            uint32_t a0[32], a1[32];
+            tc::tmem_ld32(tm_t(c) + 64 * h, a0);
+            tc::tmem_ld32(tm_t(c) + 64 * h + 32, a1);
             tc::tmem_ld_wait();
-            if (hh == 1) temp_release(c);
+            temp_release(c);
 #pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) {
-              float* uu = &u[64 * c + 32 * hh + 4 * j4];
-              uu[0] = fmaf(uu[0] + __uint_as_float(a[4 * j4 + 0]), RSQRT2, kv[j4].x);
-              uu[1] = fmaf(uu[1] + __uint_as_float(a[4 * j4 + 1]), RSQRT2, kv[j4].y);
-              uu[2] = fmaf(uu[2] + __uint_as_float(a[4 * j4 + 2]), RSQRT2, kv[j4].z);
-              uu[3] = fmaf(uu[3] + __uint_as_float(a[4 * j4 + 3]), RSQRT2, kv[j4].w);
+            for (int j = 0; j < 32; ++j) {
+              u[64 * c + j] = (u[64 * c + j] + __uint_as_float(a0[j])) * RSQRT2;
+              u[64 * c + 32 + j] = (u[64 * c + 32 + j] + __uint_as_float(a1[j])) * RSQRT2;
             }
-            if (c * 2 + hh < 3) {
-#pragma unroll
-              for (int j4 = 0; j4 < 8; ++j4) kv[j4] = kn[j4];
-            }
+            write_A(c, &u[64 * c]);
+            publish_a(c);
           }
-          write_A(c, &u[64 * c]);
-          publish_a(c);
+        } else {
+          // u <- (u + acc)/sqrt(2) + k_l ; write the next conv input.  k_l comes from L2 (no L1 to speak of next to
+          // 227 KB of shared memory): each 16-column phase prefetches the next phase's k before it waits on TMEM.
+          const float4* kbase = reinterpret_cast<const float4*>(p.ktab + ((size_t)b * p.L + l) * C + 64 * h);
+          float4 kv[4];
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) kv[j4] = __ldg(kbase + j4);
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            temp_wait(c);
+#pragma unroll
+            for (int ph = 0; ph < 4; ++ph) {         // 16 columns per phase
+              uint32_t a[16];
+              tc::tmem_ld16(tm_t(c) + 64 * h + 16 * ph, a);
+              float4 kn[4];
+              if (c * 4 + ph < 7) {
+                const float4* kp = kbase + (ph < 3 ? 32 * c + 4 * (ph + 1) : 32);   // next phase; float4 units
+#pragma unroll
+                for (int j4 = 0; j4 < 4; ++j4) kn[j4] = __ldg(kp + j4);
+              }
+              tc::tmem_ld_wait();
+              if (ph == 3) temp_release(c);
+#pragma unroll
+              for (int j4 = 0; j4 < 4; ++j4) {
+                float* uu = &u[64 * c + 16 * ph + 4 * j4];
+                uu[0] = fmaf(uu[0] + __uint_as_float(a[4 * j4 + 0]), RSQRT2, kv[j4].x);
+                uu[1] = fmaf(uu[1] + __uint_as_float(a[4 * j4 + 1]), RSQRT2, kv[j4].y);
+                uu[2] = fmaf(uu[2] + __uint_as_float(a[4 * j4 + 2]), RSQRT2, kv[j4].z);
+                uu[3] = fmaf(uu[3] + __uint_as_float(a[4 * j4 + 3]), RSQRT2, kv[j4].w);
+              }
+              if (c * 4 + ph < 7) {
+#pragma unroll
+                for (int j4 = 0; j4 < 4; ++j4) kv[j4] = kn[j4];
+              }
+            }
+            write_A(c, &u[64 * c]);
+            publish_a(c);
+          }
         }
       }
     }
@@ -870,6 +917,17 @@ __global__ void ktab_kernel(const float* __restrict__ dtab, const float* __restr
   if (l == 0) k00[((size_t)st * B + b) * C + c] = dtab[id] + ctab[ic];
 }
 
+// KUNI: kimg[s][l][rank] = N=256 weight half ([2 k-chunks][128 rows][8 bf16]) whose K=0/1 columns hold the bf16 hi/lo
+// split of sqrt(2) * ktab[s][0][l][128 rank + row]; all other columns are zero.
+__global__ void kimg_kernel(const float* __restrict__ ktab, uint8_t* __restrict__ kimg, int L, int B) {
+  const int l = blockIdx.x, st = blockIdx.y, rank = blockIdx.z, row = threadIdx.x;   // 128 threads
+  const float v = 1.41421356237309504880f * ktab[(((size_t)st * B) * L + l) * C + 128 * rank + row];
+  const float hi = __bfloat162float(__float2bfloat16_rn(v));
+  uint4* dst = reinterpret_cast<uint4*>(kimg + (((size_t)st * L + l) * 2 + rank) * KIMG_BYTES);
+  dst[row] = make_uint4(pack_bf16(hi, v - hi), 0u, 0u, 0u);
+  dst[128 + row] = make_uint4(0u, 0u, 0u, 0u);
+}
+
 __global__ void iota_i64_kernel(int64_t* p, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = i;
@@ -992,7 +1050,7 @@ __global__ void pack_small_kernel(const float* __restrict__ flat, const FlatOffs
 }
 
 struct WorkBf16 {
-  size_t status, condT, tsteps, d, h, dtab, ctab, ktab, k00, U, U2, S, total;
+  size_t status, condT, tsteps, d, h, dtab, ctab, ktab, k00, kimg, U, U2, S, total;
   int Tg, R, Rp;
 };
 WorkBf16 work_layout(const mgb_model_dims& d, int B, int T, int K) {
@@ -1012,6 +1070,7 @@ WorkBf16 work_layout(const mgb_model_dims& d, int B, int T, int K) {
   w.ctab = take((size_t)B * d.layers * C * 4);
   w.ktab = take((size_t)K * B * d.layers * C * 4);
   w.k00 = take((size_t)K * B * C * 4);
+  w.kimg = take((size_t)K * d.layers * 2 * KIMG_BYTES);
   w.U = take((size_t)B * T * C * 4);
   w.U2 = take((size_t)B * T * C * 4);
   w.S = take((size_t)B * T * C * 4);
@@ -1115,6 +1174,10 @@ int bf16_prepare(const mgb_model_dims& d, const void* packed, const int64_t* t, 
   ktab_kernel<<<dim3(L, B, uniform ? nsteps : 1), 256, 0, s>>>(dtab, ctab, P + o.bo_x, reinterpret_cast<float*>(W + w.ktab),
                                                                reinterpret_cast<float*>(W + w.k00), L, B, uniform ? 1 : 0);
   note_launch(5);   // step MLP (2), two projection tables, ktab
+  if (uniform && !d.multi_speaker) {   // k_l is the same for every utterance: hand it to the residual GEMM (KUNI kernels)
+    kimg_kernel<<<dim3(L, nsteps, 2), 128, 0, s>>>(reinterpret_cast<const float*>(W + w.ktab), W + w.kimg, L, B);
+    note_launch();
+  }
   MGB_LAUNCH_CHECK();
   return MGB_OK;
 }
@@ -1135,7 +1198,8 @@ int bf16_run(const mgb_model_dims& d, const void* packed, const float* x, const 
     int dev = 0, sms = 0;
     MGB_CUDA_CHECK(cudaGetDevice(&dev));
     MGB_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    MGB_CUDA_CHECK(cudaFuncSetAttribute(fused_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+    MGB_CUDA_CHECK(cudaFuncSetAttribute(fused_pair_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+    MGB_CUDA_CHECK(cudaFuncSetAttribute(fused_pair_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
     pair_slots = sms / 2 > 0 ? sms / 2 : 1;
   }
   FusedParams p{};
@@ -1146,6 +1210,8 @@ int bf16_run(const mgb_model_dims& d, const void* packed, const float* x, const 
   p.K = K; p.clip = clip; p.n_mel = d.n_mel;
   p.ktab = reinterpret_cast<const float*>(W + w.ktab) + (size_t)step * B * L * C;
   p.k00 = reinterpret_cast<const float*>(W + w.k00) + (size_t)step * B * C;
+  const bool kuni = t_uniform >= 0 && !d.multi_speaker;   // bf16_prepare built kimg for exactly this case
+  p.kimg = W + w.kimg + (size_t)step * L * 2 * KIMG_BYTES;
   p.bsum_skip = P + o.bsum_skip;
   p.b_in = P + o.b_in; p.b_skip = P + o.b_skip; p.b_out = P + o.b_out;
   float* Ubuf[2] = {reinterpret_cast<float*>(W + w.U), reinterpret_cast<float*>(W + w.U2)};
@@ -1168,8 +1234,10 @@ int bf16_run(const mgb_model_dims& d, const void* packed, const float* x, const 
       cudaMalloc(&dprof, (size_t)ncta * 64 * sizeof(long long));
       cudaMemset(dprof, 0, (size_t)ncta * 64 * sizeof(long long));
       p.prof = dprof;
-      cudaFuncSetAttribute(fused_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL);
-      fused_pair_kernel<true><<<ncta, NTHREADS, SMEM_TOTAL, s>>>(p);
+      cudaFuncSetAttribute(fused_pair_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL);
+      cudaFuncSetAttribute(fused_pair_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL);
+      if (kuni) fused_pair_kernel<true, true><<<ncta, NTHREADS, SMEM_TOTAL, s>>>(p);
+      else fused_pair_kernel<true, false><<<ncta, NTHREADS, SMEM_TOTAL, s>>>(p);
       cudaStreamSynchronize(s);
       long long* h = (long long*)malloc((size_t)ncta * 64 * sizeof(long long));
       cudaMemcpy(h, dprof, (size_t)ncta * 64 * sizeof(long long), cudaMemcpyDeviceToHost);
@@ -1188,7 +1256,8 @@ int bf16_run(const mgb_model_dims& d, const void* packed, const float* x, const 
       fprintf(stderr, "\n");
       free(h); cudaFree(dprof); p.prof = nullptr;
     } else {
-      fused_pair_kernel<false><<<2 * npairs, NTHREADS, SMEM_TOTAL, s>>>(p);
+      if (kuni) fused_pair_kernel<false, true><<<2 * npairs, NTHREADS, SMEM_TOTAL, s>>>(p);
+      else fused_pair_kernel<false, false><<<2 * npairs, NTHREADS, SMEM_TOTAL, s>>>(p);
     }
     prof_end(s);
     note_launch();

@@ -73,19 +73,23 @@ static __global__ void __launch_bounds__(256) step_mlp_kernel(const int64_t* __r
   }
 }
 
-// Batched version of the same MLP: one launch per layer, weights read once per 8 utterances.
+// Batched version of the same MLP: one launch per layer, weights read once per 8 rows.
 //   out[b][n] = f( sum_k in[b][k] * wt[k][n] ),  EMB: in[b] = sinusoidal embedding of t[b],  MISH: f = mish
-constexpr int MLP_UB = 8;
+// Block = 32 output columns x 8 K-slices (256 threads): the K loop is split eight ways so that the few rows of a
+// sampling call (one per diffusion step) do not serialise a 1024-long chain of L2-latency weight loads.
+constexpr int MLP_UB = 8, MLP_KS = 8;
 template <bool EMB, bool MISH>
-static __global__ void __launch_bounds__(128) step_mlp_layer_kernel(const int64_t* __restrict__ t,
+static __global__ void __launch_bounds__(256) step_mlp_layer_kernel(const int64_t* __restrict__ t,
                                                                     const float* __restrict__ in,
                                                                     const float* __restrict__ wt,
                                                                     float* __restrict__ out, int B, int K, int N) {
-  extern __shared__ float xs[];   // [MLP_UB][K]
-  const int b0 = blockIdx.y * MLP_UB, n = blockIdx.x * 128 + threadIdx.x;
+  extern __shared__ float xs[];   // [MLP_UB][K] inputs, then [MLP_KS][MLP_UB][32] partial sums
+  float* part = xs + MLP_UB * K;
+  const int col = threadIdx.x & 31, ks = threadIdx.x >> 5;
+  const int b0 = blockIdx.y * MLP_UB, n = blockIdx.x * 32 + col;
   const int halfd = K / 2;
   const float scale = (float)(9.210340371976184 / (double)(halfd - 1));  // ln(10000)/(half-1)
-  for (int i = threadIdx.x; i < MLP_UB * K; i += 128) {
+  for (int i = threadIdx.x; i < MLP_UB * K; i += 256) {
     const int u = i / K, k = i - u * K, b = b0 + u;
     float v = 0.f;
     if (b < B) {
@@ -103,8 +107,10 @@ static __global__ void __launch_bounds__(128) step_mlp_layer_kernel(const int64_
   float acc[MLP_UB];
 #pragma unroll
   for (int u = 0; u < MLP_UB; ++u) acc[u] = 0.f;
+  const int kper = K / MLP_KS;             // K % (8 * 16) == 0 for K = 256, 1024
+  const int kbeg = ks * kper;
   if (n < N) {
-    for (int k0 = 0; k0 < K; k0 += 16) {     // K % 16 == 0; 16 independent weight loads in flight
+    for (int k0 = kbeg; k0 < kbeg + kper; k0 += 16) {     // 16 independent weight loads in flight
       float w[16];
 #pragma unroll
       for (int i = 0; i < 16; ++i) w[i] = __ldg(wt + (size_t)(k0 + i) * N + n);
@@ -114,16 +120,21 @@ static __global__ void __launch_bounds__(128) step_mlp_layer_kernel(const int64_
         for (int u = 0; u < MLP_UB; ++u) acc[u] = fmaf(w[i], xs[u * K + k0 + i], acc[u]);
       }
     }
+  }
 #pragma unroll
-    for (int u = 0; u < MLP_UB; ++u) {
-      if (b0 + u < B) {
-        float s = acc[u];
-        if (MISH) {
-          const float sp = s > 20.f ? s : log1pf(expf(s));  // F.softplus default threshold
-          s = s * tanhf(sp);
-        }
-        out[(size_t)(b0 + u) * N + n] = s;
+  for (int u = 0; u < MLP_UB; ++u) part[(ks * MLP_UB + u) * 32 + col] = acc[u];
+  __syncthreads();
+  {                                        // thread (u = ks, col) sums the 8 K-slices in a fixed order
+    const int u = ks;
+    float s = 0.f;
+#pragma unroll
+    for (int q = 0; q < MLP_KS; ++q) s += part[(q * MLP_UB + u) * 32 + col];
+    if (n < N && b0 + u < B) {
+      if (MISH) {
+        const float sp = s > 20.f ? s : log1pf(expf(s));  // F.softplus default threshold
+        s = s * tanhf(sp);
       }
+      out[(size_t)(b0 + u) * N + n] = s;
     }
   }
 }
@@ -131,10 +142,11 @@ static __global__ void __launch_bounds__(128) step_mlp_layer_kernel(const int64_
 // d[B][C] = W2 * mish(W0 * emb(t)); `hbuf` is [B][4C] scratch.  Two launches.
 static inline void launch_step_mlp(const int64_t* t, const float* w0t, const float* w2t, float* hbuf, float* d,
                                    int B, int C, cudaStream_t s) {
-  dim3 g1(4 * C / 128, (B + MLP_UB - 1) / MLP_UB), g2(C / 128, (B + MLP_UB - 1) / MLP_UB);
-  step_mlp_layer_kernel<true, true><<<g1, 128, (size_t)MLP_UB * C * sizeof(float), s>>>(t, nullptr, w0t, hbuf, B, C, 4 * C);
-  step_mlp_layer_kernel<false, false><<<g2, 128, (size_t)MLP_UB * 4 * C * sizeof(float), s>>>(nullptr, hbuf, w2t, d, B,
-                                                                                            4 * C, C);
+  dim3 g1(4 * C / 32, (B + MLP_UB - 1) / MLP_UB), g2(C / 32, (B + MLP_UB - 1) / MLP_UB);
+  const size_t sm1 = (size_t)(MLP_UB * C + MLP_KS * MLP_UB * 32) * sizeof(float);
+  const size_t sm2 = (size_t)(MLP_UB * 4 * C + MLP_KS * MLP_UB * 32) * sizeof(float);
+  step_mlp_layer_kernel<true, true><<<g1, 256, sm1, s>>>(t, nullptr, w0t, hbuf, B, C, 4 * C);
+  step_mlp_layer_kernel<false, false><<<g2, 256, sm2, s>>>(nullptr, hbuf, w2t, d, B, 4 * C, C);
 }
 
 // tab[b][l][c] = sum_k Wt_l[k][c] * v[b][k] (+ bias_l[c]);  v == nullptr -> bias only.

@@ -1,0 +1,88 @@
+"""Turn the scratch artefacts in gpurun_out/ (ncu report, launch list, role profile, bench lines) into the small
+tracked summaries under profiles/<round>/.  Run here (no GPU needed): python scripts/summarize_profiles.py r01"""
+import collections, csv, json, os, shutil, subprocess, sys
+
+rnd = sys.argv[1] if len(sys.argv) > 1 else "r01"
+out = os.path.join("profiles", rnd)
+os.makedirs(out, exist_ok=True)
+G = "gpurun_out"
+
+# ---- ncu --set full of the fused kernel (both layer-group launches of one Denoiser call)
+rep = os.path.join(G, "prof_pair.ncu-rep")
+raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rows = list(csv.reader(raw.splitlines()))
+hdr = rows[0]
+want = ["Kernel Name", "gpu__time_duration.sum", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "sm__cycles_elapsed.avg", "sm__cycles_active.avg",
+        "sm__cycles_elapsed.avg.per_second", "dram__bytes_read.sum", "dram__bytes_write.sum", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+        "lts__t_sector_hit_rate.pct", "l1tex__m_xbar2l1tex_read_bytes.sum", "l1tex__m_xbar2l1tex_read_bytes.sum.per_second",
+        "l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed", "l1tex__data_bank_reads.avg.pct_of_peak_sustained_elapsed",
+        "l1tex__data_bank_writes.avg.pct_of_peak_sustained_elapsed", "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
+        "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum", "launch__grid_size", "launch__block_size",
+        "launch__cluster_size", "launch__registers_per_thread", "launch__shared_mem_per_block_dynamic", "launch__waves_per_multiprocessor"]
+with open(os.path.join(out, "ncu_fused_pair_kernel_summary.txt"), "w") as f:
+    f.write("ncu --set full --clock-control none --import-source on -k regex:fused_pair_kernel -s 8 -c 2  python bench.py --steps 2 --warmup 3\n"
+            "(columns: launch 1 = layers [0,10) of a Denoiser call, launch 2 = layers [10,20) + tail; ncu flushes caches between\n"
+            " replays, so launch 2 re-reads the spilled residual stream / skip sum from DRAM here but mostly from L2 in a real step)\n\n")
+    for i, h in enumerate(hdr):
+        if h in want:
+            f.write(f"{h} [{rows[1][i]}] = {' | '.join(r[i] for r in rows[2:])}\n")
+    src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+    srows = list(csv.reader(src.splitlines()))
+    sh = srows[1]
+    body = []
+    for r in srows[2:]:
+        if r and r[0] == "Kernel Name":
+            break
+        if len(r) > 5 and r[0].startswith("0x"):
+            body.append(r)
+    isamp, isrc = sh.index("# Samples"), sh.index("Source")
+    tot = sum(int(r[isamp] or 0) for r in body)
+    ops = collections.Counter()
+    for r in body:
+        op = r[isrc].strip().split()
+        op = [o for o in op if not o.startswith("@")][0].split(".")[0] if op else "?"
+        ops[op] += 0
+    sass = collections.Counter()
+    for r in body:
+        t = r[isrc]
+        for key in ("UTCHMMA", "UTCBAR", "LDTM", "UBLKCP", "STAS", "SYNCS", "MUFU.TANH", "UTCATOM", " HMMA"):
+            if key in t:
+                sass[key] += 1
+    f.write(f"\nSASS mnemonics present (static count, launch 1): {dict(sass)}\n")
+    f.write(f"\nwarp-stall samples, launch 1 (total {tot}); top instructions:\n")
+    for s, i in sorted(((int(r[isamp] or 0), i) for i, r in enumerate(body)), reverse=True)[:16]:
+        f.write(f"  {s:6d} {100 * s / tot:5.1f}%  #{i:5d}  {body[i][isrc].strip()[:100]}\n")
+
+# ---- launch list
+ll = os.path.join(G, "launches_bf16.csv")
+rows = list(csv.reader(open(ll)))
+for i, r in enumerate(rows):
+    if r and r[0] == "ID":
+        hdr, start = r, i + 1
+        break
+ik, iv = hdr.index("Kernel Name"), hdr.index("Metric Value")
+tot = collections.OrderedDict()
+for r in rows[start:]:
+    if len(r) <= iv:
+        continue
+    n = r[ik].split("(")[0].split("::")[-1]
+    tot.setdefault(n, [0.0, 0])
+    tot[n][0] += float(r[iv].replace(",", ""))
+    tot[n][1] += 1
+T = sum(v[0] for v in tot.values())
+shutil.copy(ll, os.path.join(out, "launches_bf16_pair.csv"))
+with open(os.path.join(out, "launches_bf16_pair_summary.txt"), "w") as f:
+    f.write("ncu --metrics gpu__time_duration.sum --clock-control none -s 58 -c 40  python bench.py --steps 2 --warmup 3\n"
+            "(cold-cache, serialised launches: compare SHARES, not absolutes)\n\n")
+    for n, v in tot.items():
+        f.write(f"{v[0] / 1e3:10.1f} us {v[1]:3d}x {100 * v[0] / T:5.1f}%  {n}\n")
+    f.write(f"{T / 1e3:10.1f} us total\n")
+
+# ---- role profile + bench lines
+for src, dst in (("role_profile.txt", "role_profile_pair_kernel.txt"), ("bench_ours.json", "bench_bf16_pair.json"),
+                 ("bench_ref.json", "bench_reference_arm.json"), ("umma_rate.txt", "umma_issue_rate_probe.txt")):
+    p = os.path.join(G, src)
+    if os.path.exists(p):
+        shutil.copy(p, os.path.join(out, dst))
+print("wrote", sorted(os.listdir(out)))

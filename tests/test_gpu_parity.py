@@ -145,6 +145,47 @@ def test_shard_equivalence_and_determinism_full_size(precision):
     assert rel_l2(m1, c1.oracle_forward()[0]) < TOL[precision]["mel"]
 
 
+@pytest.mark.parametrize("precision", PRECS)
+def test_long_multispeaker_utterances_config4(precision):
+    """BASELINE configs[3] shape class: AISHELL3 shallow, multi-speaker, T = 1500 (not a multiple of any tile size).
+    One utterance against the oracle at full length, then size-independent properties on a batch: determinism and
+    bit-exact utterance sharding (a tile may span two utterances on the batch row axis)."""
+    c1 = Case("AISHELL3", "shallow", True, 1, 1500, wseed=7, iseed=41)
+    gd = build(c1, precision)
+    kw = lambda c: dict(coarse_mel=cu(c.t("coarse_mel")), x_T=cu(c.t("x_T")), noises=cu(c.t("noises")),
+                        start_noise=cu(c.t("start_noise")))
+    m1 = gd(None, cu(c1.t("cond")), cu(c1.t("spk")), cu(c1.t("pad_mask")), **kw(c1))[0]
+    assert rel_l2(m1, c1.oracle_forward()[0]) < TOL[precision]["mel"]
+    c = Case("AISHELL3", "shallow", True, 6, 1500, wseed=7, iseed=42)
+    cond, spk, pad = cu(c.t("cond")), cu(c.t("spk")), cu(c.t("pad_mask"))
+    a = gd(None, cond, spk, pad, **kw(c))[0]
+    assert torch.equal(a, gd(None, cond, spk, pad, **kw(c))[0])
+    parts = []
+    for sl in (slice(0, 1), slice(1, 4), slice(4, 6)):
+        k = kw(c)
+        parts.append(gd(None, cond[sl], spk[sl], pad[sl], coarse_mel=k["coarse_mel"][sl].contiguous(),
+                        x_T=k["x_T"][sl].contiguous(), noises=k["noises"][:, sl].contiguous(),
+                        start_noise=k["start_noise"][sl].contiguous())[0])
+    assert torch.equal(torch.cat(parts), a)
+    assert torch.isfinite(a).all() and float(a[pad].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("precision", PRECS)
+def test_sampling_loop_matches_step_by_step_p_sample(precision):
+    """`forward`/`sampling` (all K steps prepared once, uniform timestep, constant k_l added inside the GEMM) must agree
+    with K explicit `p_sample` calls (per-utterance timesteps, k_l added by the epilogue): two different kernels."""
+    c = Case("LJSpeech", "naive", False, 3, 300, wseed=0, iseed=8)
+    gd = build(c, precision)
+    cond, pad = cu(c.t("cond")), cu(c.t("pad_mask"))
+    x, noises = cu(c.t("x_T")), cu(c.t("noises"))
+    mel = gd(None, cond, None, pad, x_T=x, noises=noises)[0]
+    for i in reversed(range(gd.num_timesteps)):
+        t = torch.full((c.B,), i, dtype=torch.long, device="cuda")
+        x = gd.p_sample(x, t, cond.transpose(1, 2), None, noise=noises[i])
+    ref = gd.denorm_spec(x[:, 0].transpose(1, 2)) * (~pad).unsqueeze(-1)
+    assert rel_l2(mel, ref) < (1e-5 if precision == "fp32" else 2e-3)
+
+
 def test_shallow_start_and_denorm_elementwise_exact():
     c = golden_case("shallow_lj_B2_T130")
     lib = _lib.load()

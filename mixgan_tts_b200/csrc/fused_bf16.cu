@@ -183,6 +183,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_p
   int n_halo_gens = 1;
   for (int l = p.lb; l < p.le; ++l) n_halo_gens += (l < p.L - 1) ? 1 : 0;
 
+  // PROF: ring-load latency window = the 96 loads starting with layer lb+2
+  int prof_w0 = first_group ? 10 : 0;
+  for (int l = p.lb; l < p.lb + 2 && l < p.le; ++l) prof_w0 += (l < p.L - 1) ? (KUNI ? 45 : 44) : 32;
+
   long long t_tfull_out = 0;
   if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
@@ -196,7 +200,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_p
       const uint8_t* wimg = p.wimg + (size_t)rank * p.wimg_rank_stride;
       const uint8_t* condb = reinterpret_cast<const uint8_t*>(p.condT) + (size_t)(g0 + COND_PAD_LO) * 16;
       const size_t cond_chunk = (size_t)p.Rp * 16;
+      int n_issued = 0;
       auto advance = [&]() {
+        if (PROF) {
+          const int w = n_issued - prof_w0;
+          if (w >= 0 && w < 96 && lane == 0) p.prof[blockIdx.x * 256 + 64 + w] = clock64() - t_start;
+          ++n_issued;
+        }
         const bool wrap = slot == NSLOTS - 1;
         slot = wrap ? 0u : slot + 1u;
         phase ^= wrap ? 1u : 0u;
@@ -246,7 +256,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_p
       for (int l = p.lb; l < p.le; ++l) {
         const int base = W_LAYER0 + l * W_PER_LAYER;
         for (int i = 0; i < 4; ++i) {                                       // conv chunk: 6 weight slots + bias slot
-          for (int j = 0; j < 6; ++j) load_w(base + 7 * i + j, SLOT_BYTES);
+          for (int j = 0; j < 6; ++j) {
+            load_w(base + 7 * i + j, SLOT_BYTES);
+            if (PROF && l == p.lb + 3 && i == 0 && j == 0 && lane == 0) p.prof[blockIdx.x * 256 + 60] = clock64() - t_start;
+          }
           load_w(base + 7 * i + 6, BIAS_SLOT_BYTES);
         }
         load_w(base + WL_SKIPA, SLOT_BYTES);                                  // skip j=0
@@ -261,7 +274,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_p
         for (int i = 0; i < 4; ++i) load_w(W_SKIPP + i, SLOT_BYTES);
         for (int i = 0; i < 2; ++i) load_w(W_OUT + i, SLOT_BYTES);
       }
-      if (PROF && lane == 0) { p.prof[blockIdx.x * 64 + 12] = t_empty; p.prof[blockIdx.x * 64 + 13] = clock64() - t_start; }
+      if (PROF && lane == 0) { p.prof[blockIdx.x * 256 + 12] = t_empty; p.prof[blockIdx.x * 256 + 13] = clock64() - t_start; }
     } else if (warp == 1 && rank != 0) {
       // =========================== RELAY (peer CTA) ===========================
       // Forwards "my half of ring slot s has landed" to the leader's FULL[s] barrier.
@@ -273,6 +286,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_p
         const bool wrap = slot == NSLOTS - 1;
         slot = wrap ? 0u : slot + 1u;
         phase ^= wrap ? 1u : 0u;
+      }
+    } else if (warp == 2) {
+      // PROF only: observe when every ring load of the window completes (leader: own half AND the relay's arrive)
+      if (PROF) {
+        uint32_t slot = 0, phase = 0;
+        for (int i = 0; i < n_loads; ++i) {
+          tc::mbar_wait_trap(bar0 + (B_FULL + slot) * 8, phase, WAIT_CYCLES, p.status, 32);
+          const int w = i - prof_w0;
+          if (w >= 0 && w < 96 && lane == 0) p.prof[blockIdx.x * 256 + 160 + w] = clock64() - t_start;
+          const bool wrap = slot == NSLOTS - 1;
+          slot = wrap ? 0u : slot + 1u;
+          phase ^= wrap ? 1u : 0u;
+        }
       }
     } else if (warp == 3) {
       // =========================== HALO RELAY (both CTAs) ===========================
@@ -326,8 +352,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_p
         tc::tc_fence_after();
       };
       // one N=128 weight slot = 8 k-steps of K=16: the first four against a0, the last four against a1
+      bool stamp_next_full = false;
       auto mma_w128 = [&](uint64_t a0, uint64_t a1, uint32_t a_kstep16, uint32_t d_tmem, uint32_t acc_first) {
         wait_full();
+        if (PROF && stamp_next_full && lane == 0) { p.prof[blockIdx.x * 256 + 62] = clock64() - t_start; }
+        stamp_next_full = false;
         const uint32_t s0 = slot;
         advance();
         pretest();
@@ -450,9 +479,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_p
         for (int m = 0; m < 4; ++m) mma_cond(tm_t(0), m ? 1u : 0u);
         temp_publish(0); temp_publish(1);
       }
+      auto stamp = [&](int l, int lref, int id) {
+        if (PROF && l == lref && lane == 0) p.prof[blockIdx.x * 256 + 48 + id] = clock64() - t_start;
+      };
       for (int l = p.lb; l < p.le; ++l) {
         wait_bar(B_AREADY, n_aready);                   // conv input u_l, channels [0, 128), in sA (both CTAs)
+        stamp(l, p.lb + 3, 3);
         wait_bar(B_HALOP, n_halo);                      // ... including the edge rows the CTAs exchange
+        stamp(l, p.lb + 3, 4);
 #pragma unroll 1
         for (uint32_t i = 0; i < 4; ++i) {              // k=3 conv, chunk i = 64 gate + 64 filter channels
           const uint32_t tb = i & 1;
@@ -460,6 +494,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_p
           temp_acquire(tb);
           site = 3;
           fsite = 0;
+          if (PROF && l == p.lb + 3 && i == 0) { stamp(l, p.lb + 3, 13); stamp_next_full = true; }
 #pragma unroll 1
           for (uint32_t j = 0; j < 6; ++j) {            // slot j = blocks q = 2j, 2j+1 of the (kb, tap) sequence q = 3 kb + tap
             if (i == 0 && j == 3) { wait_bar(B_AREADY + 1, n_aready); wait_bar(B_HALOP + 1, n_halo); }   // channels [128, 256)
@@ -468,6 +503,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_p
             const uint64_t a0 = dA + (q0 - 3 * kb0) + kb0 * ((8 * A_LBO) >> 4);   // tap = +16 B row shift of the start address
             const uint64_t a1 = dA + (q1 - 3 * kb1) + kb1 * ((8 * A_LBO) >> 4);
             mma_w128(a0, a1, A_K16, tm_t(tb), j ? 1u : 0u);
+            if (i == 0 && j == 0) stamp(l, p.lb + 3, 5);
+            if (i == 0 && j == 5) stamp(l, p.lb + 3, 6);
           }
           mma_bias(tm_t(tb));
           temp_publish(tb);
@@ -481,6 +518,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_p
           site = 1;
           temp_acquire(0); temp_acquire(1);
           site = 3;
+          stamp(l, p.lb + 2, 0);
           fsite = 2;
 #pragma unroll 1
           for (uint32_t m = 0; m < 4; ++m) mma_cond(tm_t(0), m ? 1u : 0u);
@@ -494,6 +532,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_p
           }
           if (KUNI) mma_kbias(tm_t(0));
           temp_publish(0); temp_publish(1);
+          stamp(l, p.lb + 2, 1);
         } else {
           for (int j = 1; j < 4; ++j) wait_bar(B_GREADY + j, n_gready);
         }
@@ -507,6 +546,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_p
             a += (8 * G_LBO) >> 4;
           }
         }
+        stamp(l, p.lb + 2, 2);
       }
       if (tc::elect_one()) tc::umma_commit_2cta_mc(bar0 + B_SKIPDONE * 8);
       __syncwarp();
@@ -522,7 +562,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_p
         temp_publish(0);
       }
       if (PROF && lane == 0) {
-        long long* q = p.prof + blockIdx.x * 64;
+        long long* q = p.prof + blockIdx.x * 256;
         q[0] = t_full; q[1] = t_temp; q[2] = t_ar; q[3] = t_gr; q[4] = clock64() - t_start;
         q[5] = t_full_first; q[6] = t_full_max; q[7] = n_full_slow;
         for (int i = 0; i < 8; ++i) q[16 + i] = t_site[i];
@@ -559,7 +599,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_p
       const long long t0 = PROF ? clock64() : 0;
       tc::mbar_wait_trap(bar0 + (B_TFULL + tb) * 8, (n_use >> 1) & 1, WAIT_CYCLES, p.status, 4);
       if (PROF) t_tfull += clock64() - t0;
-      if (PROF && warp == 4 && lane == 0 && ts_n >= 0 && ts_n < 24) p.prof[blockIdx.x * 64 + 32 + ts_n++] = clock64() - t_start;
+      if (PROF && warp == 4 && lane == 0 && ts_n >= 0 && ts_n < 16) p.prof[blockIdx.x * 256 + 32 + ts_n++] = clock64() - t_start;
       ++n_use;
       tc::tc_fence_after();
     };
@@ -703,6 +743,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_p
 #pragma unroll
           for (int c = 0; c < 2; ++c) {
             temp_wait(c);
+            if (PROF && l == p.lb + 2 && warp == 4 && lane == 0) p.prof[blockIdx.x * 256 + 56 + 2 * c] = clock64() - t_start;
             uint32_t a0[32], a1[32];
             tc::tmem_ld32(tm_t(c) + 64 * h, a0);
             tc::tmem_ld32(tm_t(c) + 64 * h + 32, a1);
@@ -715,6 +756,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_p
             }
             write_A(c, &u[64 * c]);
             publish_a(c);
+            if (PROF && l == p.lb + 2 && warp == 4 && lane == 0) p.prof[blockIdx.x * 256 + 57 + 2 * c] = clock64() - t_start;
           }
         } else {
           // u <- (u + acc)/sqrt(2) + k_l ; write the next conv input.  k_l comes from L2 (no L1 to speak of next to
@@ -874,7 +916,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_p
     if (PROF) t_tfull_out = t_tfull;
   }
 
-  if (PROF && warp == 4 && lane == 0) { p.prof[blockIdx.x * 64 + 8] = t_tfull_out; p.prof[blockIdx.x * 64 + 9] = clock64() - t_start; }
+  if (PROF && warp == 4 && lane == 0) { p.prof[blockIdx.x * 256 + 8] = t_tfull_out; p.prof[blockIdx.x * 256 + 9] = clock64() - t_start; }
   // ---- teardown: neither CTA may leave (or free TMEM) while the pair's MMAs can still touch it ----
   tc::tc_fence_before();
   __syncthreads();
@@ -1231,18 +1273,18 @@ int bf16_run(const mgb_model_dims& d, const void* packed, const float* x, const 
     if (do_prof) {
       const int ncta = 2 * npairs;
       long long* dprof = nullptr;
-      cudaMalloc(&dprof, (size_t)ncta * 64 * sizeof(long long));
-      cudaMemset(dprof, 0, (size_t)ncta * 64 * sizeof(long long));
+      cudaMalloc(&dprof, (size_t)ncta * 256 * sizeof(long long));
+      cudaMemset(dprof, 0, (size_t)ncta * 256 * sizeof(long long));
       p.prof = dprof;
       cudaFuncSetAttribute(fused_pair_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL);
       cudaFuncSetAttribute(fused_pair_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL);
       if (kuni) fused_pair_kernel<true, true><<<ncta, NTHREADS, SMEM_TOTAL, s>>>(p);
       else fused_pair_kernel<true, false><<<ncta, NTHREADS, SMEM_TOTAL, s>>>(p);
       cudaStreamSynchronize(s);
-      long long* h = (long long*)malloc((size_t)ncta * 64 * sizeof(long long));
-      cudaMemcpy(h, dprof, (size_t)ncta * 64 * sizeof(long long), cudaMemcpyDeviceToHost);
+      long long* h = (long long*)malloc((size_t)ncta * 256 * sizeof(long long));
+      cudaMemcpy(h, dprof, (size_t)ncta * 256 * sizeof(long long), cudaMemcpyDeviceToHost);
       double a[64] = {0};   // MMA-warp counters exist on leader CTAs only (even blocks)
-      for (int i = 0; i < ncta; i += 2) for (int k = 0; k < 64; ++k) a[k] += (double)h[i * 64 + k] / npairs;
+      for (int i = 0; i < ncta; i += 2) for (int k = 0; k < 64; ++k) a[k] += (double)h[i * 256 + k] / npairs;
       fprintf(stderr, "[mgb profile] layers [%d,%d) pairs %d | MMA warp: total %.0f wait_full %.0f wait_temp %.0f wait_aready %.0f "
               "wait_gready %.0f (first wait_full %.0f, max later %.0f, waits > 300 cyc: %.0f) | epilogue w4: total %.0f wait_tfull %.0f | "
               "producer: total %.0f wait_empty %.0f | temp by site: conv %.0f resT0 %.0f resT1 %.0f other %.0f | A-ready by site: A0 %.0f H0 %.0f "
@@ -1251,8 +1293,26 @@ int bf16_run(const mgb_model_dims& d, const void* packed, const float* x, const 
               a[19], a[20], a[21], a[22], a[23]);
       fprintf(stderr, "[mgb profile] wait_full by phase: conv %.0f skip0 %.0f rescond %.0f resg %.0f skip123 %.0f other %.0f\n", a[24], a[25],
               a[26], a[27], a[28], a[29]);
+      fprintf(stderr, "[mgb boundary] layer %d->%d, cycles after the residual accumulator was seen ready by epilogue warp 4: "
+              "MMA warp: res acquired %.0f, res issued %.0f, skip issued %.0f, A0 passed %.0f, halo0 passed %.0f, conv slot0 issued %.0f, "
+              "conv chunk0 issued %.0f | epilogue: A0 published %.0f, T1 seen %.0f, A1 published %.0f\n", p.lb + 2, p.lb + 3,
+              a[48] - a[56], a[49] - a[56], a[50] - a[56], a[51] - a[56], a[52] - a[56], a[53] - a[56], a[54] - a[56], a[57] - a[56],
+              a[58] - a[56], a[59] - a[56]);
+      fprintf(stderr, "[mgb boundary] conv slot0 of layer %d: producer issued its load at %.0f, MMA warp acquired T0 at %.0f, saw the slot full at %.0f\n",
+              p.lb + 3, a[60] - a[56], a[61] - a[56], a[62] - a[56]);
+      {
+        double lat[2][96] = {{0}}, iss[96] = {0};
+        for (int i = 0; i < ncta; ++i)
+          for (int k = 0; k < 96; ++k) {
+            lat[i & 1][k] += (double)(h[i * 256 + 160 + k] - h[i * 256 + 64 + k]) / npairs;
+            if (!(i & 1)) iss[k] += (double)h[i * 256 + 64 + k] / npairs;
+          }
+        fprintf(stderr, "[mgb ring] load latency (issue -> FULL seen) from layer %d, leader incl. relay / peer own half; issue time delta:", p.lb + 2);
+        for (int k = 0; k < 96; ++k) fprintf(stderr, " %d:%.0f/%.0f(+%.0f)", k, lat[0][k], lat[1][k], k ? iss[k] - iss[k - 1] : 0.0);
+        fprintf(stderr, "\n");
+      }
       fprintf(stderr, "[mgb timeline] accumulator-ready deltas from layer %d (conv c0..c3, res T0, res T1, ...):", p.lb + 2);
-      for (int k = 1; k < 18; ++k) fprintf(stderr, " %.0f", a[32 + k] - a[32 + k - 1]);
+      for (int k = 1; k < 16; ++k) fprintf(stderr, " %.0f", a[32 + k] - a[32 + k - 1]);
       fprintf(stderr, "\n");
       free(h); cudaFree(dprof); p.prof = nullptr;
     } else {

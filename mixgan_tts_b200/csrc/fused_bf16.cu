@@ -338,6 +338,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_p
       uint32_t pre = 0;
       long long t_fsite[6] = {0, 0, 0, 0, 0, 0};   // PROF: wait_full by phase: 0 conv, 1 skip j0, 2 res cond, 3 res g, 4 skip j1-3, 5 other
       int fsite = 5;
+      // called right after advance(): test the FULL barrier of the new current slot (one slot ahead of its use; testing
+      // two slots ahead is too early for a 6-slot ring - the test always fails and every wait takes the slow path)
       auto pretest = [&]() { pre = tc::mbar_try_wait_addr(bar0 + (B_FULL + slot) * 8, phase) ? 1u : 0u; };
       auto wait_full = [&]() {
         const long long t0 = PROF ? clock64() : 0;
@@ -497,6 +499,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_p
           if (PROF && l == p.lb + 3 && i == 0) { stamp(l, p.lb + 3, 13); stamp_next_full = true; }
 #pragma unroll 1
           for (uint32_t j = 0; j < 6; ++j) {            // slot j = blocks q = 2j, 2j+1 of the (kb, tap) sequence q = 3 kb + tap
+            // (keep the three taps of one 64-channel block adjacent: they re-read the same shared-memory lines, and a
+            //  "centre taps first" order that breaks this locality measured 82 instead of 64 cycles per MMA)
             if (i == 0 && j == 3) { wait_bar(B_AREADY + 1, n_aready); wait_bar(B_HALOP + 1, n_halo); }   // channels [128, 256)
             const uint32_t q0 = 2 * j, q1 = 2 * j + 1;
             const uint32_t kb0 = q0 / 3, kb1 = q1 / 3;
@@ -638,17 +642,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_p
 
     // ---- group start: produce u_lb ----
     if (first_group) {
-      // x_t tile -> bf16 A operand (channels 0..79): this thread converts bins [40h, 40h+40)
+      // x_t tile -> bf16 A operand (channels 0..79): this thread converts bins [40h, 40h+40); all 40 loads are issued
+      // before the first store so that one DRAM latency is exposed, not five
+      {
+        float xv[40];
+        const size_t o0 = ((size_t)b * p.n_mel + 40 * h) * p.T + f;
 #pragma unroll
-      for (int jj = 0; jj < 5; ++jj) {
-        float v[8];
+        for (int j = 0; j < 40; ++j)
+          xv[j] = (in_seq && 40 * h + j < p.n_mel) ? __ldg(p.x_t + o0 + (size_t)j * p.T) : 0.f;
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const int n = 40 * h + jj * 8 + e;
-          v[e] = (in_seq && n < p.n_mel) ? p.x_t[((size_t)b * p.n_mel + n) * p.T + f] : 0.f;
-        }
-        st_shared_v4(aA + (uint32_t)(5 * h + jj) * A_LBO + (uint32_t)(r + 1) * 16, pack_bf16(v[0], v[1]),
-                     pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+        for (int jj = 0; jj < 5; ++jj)
+          st_shared_v4(aA + (uint32_t)(5 * h + jj) * A_LBO + (uint32_t)(r + 1) * 16, pack_bf16(xv[8 * jj], xv[8 * jj + 1]),
+                       pack_bf16(xv[8 * jj + 2], xv[8 * jj + 3]), pack_bf16(xv[8 * jj + 4], xv[8 * jj + 5]),
+                       pack_bf16(xv[8 * jj + 6], xv[8 * jj + 7]));
       }
       publish_a(-1);
 #pragma unroll
@@ -694,7 +700,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_p
       }
       publish_a(-1);
     } else {
-      // reload u_lb spilled by the previous group
+      // reload u_lb spilled by the previous group (all 32 loads in flight before the first use)
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         const float4* up = reinterpret_cast<const float4*>(p.U_in + row_g * C + 128 * c + 64 * h);
@@ -704,8 +710,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_p
           u[64 * c + 4 * j4 + 0] = v.x; u[64 * c + 4 * j4 + 1] = v.y;
           u[64 * c + 4 * j4 + 2] = v.z; u[64 * c + 4 * j4 + 3] = v.w;
         }
-        write_A(c, &u[64 * c]);
       }
+      write_A(0, &u[0]);
+      write_A(1, &u[64]);
       publish_a(-1);
     }
 
@@ -839,13 +846,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_p
         tc::tmem_ld_wait();
         const float4* sp = reinterpret_cast<const float4*>(p.S + row_g * C + 128 * h + 32 * cc);
         const float4* bp = reinterpret_cast<const float4*>(p.bsum_skip + 128 * h + 32 * cc);
+        float4 s8[8];                    // all eight loads in flight before the first use (S was written by the previous launch)
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) s8[j4] = (!first_group && in_seq) ? __ldg(sp + j4) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj) {
           float v[8];
 #pragma unroll
           for (int e4 = 0; e4 < 2; ++e4) {
             const float4 bv = __ldg(bp + jj * 2 + e4);
-            const float4 sv = (!first_group && in_seq) ? sp[jj * 2 + e4] : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 sv = s8[jj * 2 + e4];
             v[e4 * 4 + 0] = (__uint_as_float(a[jj * 8 + e4 * 4 + 0]) + sv.x + bv.x) * inv_sqrt_l;
             v[e4 * 4 + 1] = (__uint_as_float(a[jj * 8 + e4 * 4 + 1]) + sv.y + bv.y) * inv_sqrt_l;
             v[e4 * 4 + 2] = (__uint_as_float(a[jj * 8 + e4 * 4 + 2]) + sv.z + bv.z) * inv_sqrt_l;
@@ -856,6 +866,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_p
         }
       }
       publish_a(-1);
+      // This thread's share of the posterior update: mel bins [40h, 40h+40) of its frame.  x_t and the noise are
+      // fetched NOW so that their DRAM latency hides behind the two tail GEMMs instead of following them.
+      constexpr int NB = 40;
+      float xt[NB], nz[NB];
+      const bool upd = is_out && p.sched != nullptr;
+      {
+        const size_t o0 = ((size_t)b * p.n_mel + NB * h) * p.T + f;
+#pragma unroll
+        for (int j = 0; j < NB; ++j) {
+          const bool ok = upd && NB * h + j < p.n_mel;
+          xt[j] = ok ? __ldg(p.x_t + o0 + (size_t)j * p.T) : 0.f;
+          nz[j] = ok ? __ldg(p.noise + o0 + (size_t)j * p.T) : 0.f;
+        }
+      }
 #pragma unroll
       for (int c = 0; c < 2; ++c) {     // relu(skip_projection): channels 128c + 64h + [0,64) -> sG
         temp_wait(c);
@@ -879,33 +903,31 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_p
         }
       }
       publish(B_GREADY + 0);
-      // output projection: mel bins 64h + [0, 64) (only bins < n_mel exist), then the posterior update
-      temp_wait(0);
+      // output projection -> clamp -> posterior mean + sigma * noise (diffusion.py:104-129), bins [40h, 40h+40)
       float c1 = 0.f, c2 = 0.f, sg = 0.f;
       if (p.sched) {
         const int tb = p.t_uniform >= 0 ? p.t_uniform : (int)p.t[b];
         c1 = p.sched[tb]; c2 = p.sched[p.K + tb]; sg = p.sched[2 * p.K + tb];
       }
+      temp_wait(0);
+      {
+        uint32_t a[32], a2[16];
+        tc::tmem_ld32(tm_t(0) + NB * h, a);
+        tc::tmem_ld16(tm_t(0) + NB * h + 32, a2);
+        tc::tmem_ld_wait();
+        if (is_out) {
+          const size_t o0 = ((size_t)b * p.n_mel + NB * h) * p.T + f;
 #pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {
-        const int n0 = 64 * h + 32 * hh;
-        if (n0 < p.n_mel) {              // warp-uniform
-          uint32_t a[32];
-          tc::tmem_ld32(tm_t(0) + n0, a);
-          tc::tmem_ld_wait();
-          if (is_out) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int n = n0 + j;
-              if (n < p.n_mel) {
-                float x0 = __uint_as_float(a[j]) + __ldg(p.b_out + n);
-                if (p.clip) x0 = fminf(fmaxf(x0, -1.f), 1.f);
-                const size_t o = ((size_t)b * p.n_mel + n) * p.T + f;
-                if (p.x0_out) p.x0_out[o] = x0;
-                if (p.sched) {
-                  const float mean = __fadd_rn(__fmul_rn(c1, x0), __fmul_rn(c2, p.x_t[o]));
-                  p.x_prev[o] = __fadd_rn(mean, __fmul_rn(sg, p.noise[o]));
-                }
+          for (int j = 0; j < NB; ++j) {
+            const int n = NB * h + j;
+            if (n < p.n_mel) {
+              float x0 = __uint_as_float(j < 32 ? a[j] : a2[j - 32]) + __ldg(p.b_out + n);
+              if (p.clip) x0 = fminf(fmaxf(x0, -1.f), 1.f);
+              const size_t o = o0 + (size_t)j * p.T;
+              if (p.x0_out) p.x0_out[o] = x0;
+              if (p.sched) {
+                const float mean = __fadd_rn(__fmul_rn(c1, x0), __fmul_rn(c2, xt[j]));
+                p.x_prev[o] = __fadd_rn(mean, __fmul_rn(sg, nz[j]));
               }
             }
           }

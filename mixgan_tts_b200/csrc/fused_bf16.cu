@@ -31,8 +31,13 @@
 //
 // Warp roles (384 threads per CTA): warp 0 = TMA producer (both CTAs), warp 1 = MMA issuer in the
 // leader CTA / "relay" in the peer CTA (forwards the peer's ring-slot completions to the leader's
-// barriers), warp 2 = TMEM allocator, warps 4..11 = epilogue (thread = one row x half of a
-// 128-column chunk).
+// barriers), warp 2 = TMEM allocator (+ ring observer when profiling), warp 3 = halo relay (the
+// pair's two half tiles are neighbours on the row axis: each CTA's edge row is the other's halo row and
+// travels as st.async DSMEM stores tracked by an mbarrier in the destination CTA), warps 4..11 =
+// epilogue (thread = one row x half of a 128-column chunk).
+//
+// MGB_PROFILE=1 runs the PROF instantiation: per-role wait counters, a per-layer timeline of
+// accumulator-ready events, layer-boundary stamps and per-load ring latencies (see bf16_run).
 #include <cstdlib>
 
 #include "common.cuh"

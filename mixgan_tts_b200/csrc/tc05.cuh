@@ -228,10 +228,6 @@ __device__ __forceinline__ uint32_t mapa(uint32_t smem_addr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
   return r;
 }
-__device__ __forceinline__ void st_cluster_v4(uint32_t cluster_addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-  asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(cluster_addr), "r"(a), "r"(b), "r"(c), "r"(d)
-               : "memory");
-}
 // arrive on a barrier that may live in another CTA of the cluster (release at cluster scope)
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar_addr) : "memory");
@@ -249,7 +245,6 @@ __device__ __forceinline__ void st_async_v4(uint32_t cluster_addr, uint32_t a, u
   asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
                ::"r"(cluster_addr), "r"(a), "r"(b), "r"(c), "r"(d), "r"(cluster_bar_addr) : "memory");
 }
-__device__ __forceinline__ void fence_acq_rel_cluster() { asm volatile("fence.acq_rel.cluster;" ::: "memory"); }
 // wait on a local barrier whose arrivals may come from the peer CTA (acquire at cluster scope)
 __device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar_addr, uint32_t parity) {
   uint32_t ok;
@@ -274,8 +269,6 @@ __device__ __forceinline__ void mbar_wait_cluster_trap(uint32_t bar_addr, uint32
     }
   }
 }
-// generic-proxy writes (local or remote shared memory) -> visible to the async proxy
-__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
 template <int kCols>
 __device__ __forceinline__ void tmem_alloc_2cta(uint32_t* slot_in_smem) {   // same warp index in both CTAs

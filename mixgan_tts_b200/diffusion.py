@@ -9,7 +9,9 @@ with ``torch.randn`` on the device, as the reference does.
 
 Hot methods (``p_sample``, ``sampling``, inference ``forward``) call the C ABI; the light
 training-time helpers (``q_sample``, ``q_posterior``, ``norm_spec`` ...) are plain torch on the
-registered buffers.  The training branch of ``forward`` is not built yet and raises.
+registered buffers.  The training branch of ``forward`` (``mel`` given) computes the reference's
+forward VALUES (as ``evaluate.py`` uses them under ``torch.no_grad()``); there is no backward yet, so
+it raises when autograd would need one.
 """
 from __future__ import annotations
 
@@ -224,17 +226,19 @@ class GaussianDiffusion(nn.Module):
         return self.denorm_spec(x[:, 0].transpose(1, 2))
 
     def forward(self, mel, cond, spk_emb, mel_mask, coarse_mel=None, clip_denoised=True, *,
-                x_T=None, noises=None, start_noise=None):
+                x_T=None, noises=None, start_noise=None, t=None, noise_t=None, noise_prev=None, post_noise=None):
         """diffusion.py:187-226.  ``cond [B,T,H]``; ``mel_mask [B,T]`` True = padding.
-        Inference (``mel is None``) returns ``(x_0_pred [B,T,M], None, None, None, t)``."""
+        Inference (``mel is None``) returns ``(x_0_pred [B,T,M], None, None, None, t)``; with ``mel`` given the
+        reference's training-branch 5-tuple ``(x_0_pred, x_t, x_t_prev, x_t_prev_pred, t)`` (forward values only)."""
         b, device = cond.shape[0], cond.device
-        t = None
         self.cond = cond.transpose(1, 2).detach()
         self.spk_emb = spk_emb.detach() if spk_emb is not None else None
-        if mel is not None:
-            raise NotImplementedError("training branch (mel given) is not built in the B200 path yet")
         if device.type != "cuda":
             raise RuntimeError("mixgan_tts_b200.GaussianDiffusion needs CUDA tensors (no CPU fallback)")
+        if mel is not None:
+            return self._forward_training(mel, cond, spk_emb, mel_mask, coarse_mel, clip_denoised, t, noise_t,
+                                          noise_prev, post_noise)
+        t = None
         T = cond.shape[1]
         with torch.no_grad(), torch.cuda.device(device):
             lib, den, prec, stream = self._call_ctx(cond)
@@ -260,3 +264,29 @@ class GaussianDiffusion(nn.Module):
             x_0_pred, _ = self._sample_core(cond_bth, spk, x_T, noises, pad, want_states=False,
                                             clip=clip_denoised)
         return x_0_pred, None, None, None, t
+
+    def _forward_training(self, mel, cond, spk_emb, mel_mask, coarse_mel, clip_denoised, t, noise_t, noise_prev,
+                          post_noise):
+        """diffusion.py:201-225, forward values only: the Denoiser call runs in the library (per-utterance
+        timesteps), the light elementwise steps are torch on the registered buffers."""
+        if torch.is_grad_enabled() and (cond.requires_grad or any(p.requires_grad for p in self.denoise_fn.parameters())):
+            raise NotImplementedError("the B200 GaussianDiffusion has no backward in this build: evaluate the training "
+                                      "branch under torch.no_grad() (as evaluate.py does) or train with the reference module")
+        b, device = cond.shape[0], cond.device
+        with torch.no_grad(), torch.cuda.device(device):
+            valid = (~mel_mask)[:, None, None, :]                                   # :190, :202
+            if t is None:
+                t = torch.randint(0, self.num_timesteps, (b,), device=device)       # :203
+            t = t.long()
+            x_t = self.diffuse_fn(mel, t.clone(), noise=noise_t) * valid             # :206
+            x_t_prev = self.diffuse_fn(mel, t - 1, noise=noise_prev) * valid         # :207
+            x_0_pred = self.denoise_fn(x_t, t, cond.transpose(1, 2), spk_emb) * valid   # :210
+            if clip_denoised:
+                x_0_pred.clamp_(-1., 1.)                                            # :211-212
+            if self.model != "shallow":
+                x_start = x_0_pred
+            else:
+                x_start = self.norm_spec(coarse_mel).transpose(1, 2)[:, None, :, :]  # :218-219
+            x_t_prev_pred = self.q_posterior_sample(x_start=x_start, x_t=x_t, t=t, noise=post_noise) * valid   # :220
+            tr = lambda x: x[:, 0].transpose(1, 2)
+        return tr(x_0_pred), tr(x_t), tr(x_t_prev), tr(x_t_prev_pred), t

@@ -150,7 +150,7 @@ class Denoiser(nn.Module):
         -> ``[B,1,M,T]``.  ``mask`` is accepted and ignored, as in the reference."""
         if mel.device.type != "cuda":
             raise RuntimeError("mixgan_tts_b200.Denoiser needs CUDA tensors (no CPU fallback)")
-        if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+        if torch.is_grad_enabled() and self.training and any(p.requires_grad for p in self.parameters()):
             raise NotImplementedError("the B200 Denoiser has no backward in this build: call .eval() or "
                                       "run under torch.no_grad() (outputs never carry a graph)")
         if self.dims.multi_speaker and speaker_emb is None:

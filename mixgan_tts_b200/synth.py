@@ -103,3 +103,19 @@ def make_inputs(seed: int, B: int, T: int, K: int, *, n_mel: int = 80, d_encoder
     out["x_T"] = g.standard_normal((B, 1, n_mel, T), dtype=np.float32)
     out["noises"] = g.standard_normal((K, B, 1, n_mel, T), dtype=np.float32)
     return out
+
+
+def make_train_extras(seed: int, B: int, T: int, K: int, *, n_mel: int = 80, spec_min: float = -11.5129,
+                      spec_max: float = 2.0) -> dict:
+    """Extra draws of the training branch of ``GaussianDiffusion.forward`` (model/diffusion.py:201-225): the target
+    ``mel [B,T,M]``, the timesteps ``t [B]`` (mixed, always containing 0 when B > 1 so that the ``t - 1 = -1`` case is hit),
+    and the three noise tensors ``noise_t``, ``noise_prev``, ``post_noise`` ``[B,1,M,T]``."""
+    g = _rng(seed)
+    mel = g.standard_normal((B, T, n_mel), dtype=np.float32) * np.float32(2.0) - np.float32(5.0)
+    t = np.array([(K - 1 - b) % K for b in range(B)], dtype=np.int64)   # mixed timesteps, deterministic
+    if B > 1:
+        t[-1] = 0
+    return {"mel": np.clip(mel, spec_min, spec_max).astype(np.float32), "t": t,
+            "noise_t": g.standard_normal((B, 1, n_mel, T), dtype=np.float32),
+            "noise_prev": g.standard_normal((B, 1, n_mel, T), dtype=np.float32),
+            "post_noise": g.standard_normal((B, 1, n_mel, T), dtype=np.float32)}

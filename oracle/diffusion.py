@@ -106,3 +106,25 @@ class DiffusionOracle:
             start = self.diffuse_fn(coarse_mel, t, start_noise) * valid.unsqueeze(-1).transpose(1, -1)  # :198
         states, x0s = self.sampling(cond_bht, spk, start, noises)
         return states[-1] * valid, states, x0s, start
+
+    @torch.no_grad()
+    def forward_training(self, mel, cond, spk, pad_mask, *, t, noise_t, noise_prev, post_noise,
+                         coarse_mel=None, clip_denoised=True):
+        """The ``mel is not None`` branch of ``GaussianDiffusion.forward`` (model/diffusion.py:201-225),
+        forward values only.  ``t`` is what the reference draws with ``torch.randint`` (:203),
+        ``noise_t`` / ``noise_prev`` the two ``randn_like`` draws of ``diffuse_fn`` (:206-207, :182) and
+        ``post_noise`` the draw inside ``q_posterior_sample`` (:116).  Returns the reference's 5-tuple."""
+        valid = (~pad_mask)[:, None, None, :]                                   # :190, :202  [B,1,1,T]
+        cond_bht = cond.transpose(1, 2)                                         # :191
+        x_t = self.diffuse_fn(mel, t.clone(), noise_t) * valid                   # :206
+        x_t_prev = self.diffuse_fn(mel, t - 1, noise_prev) * valid               # :207 (t-1 = -1 -> the clean mel)
+        x0 = denoiser_forward(self.W, x_t, t, cond_bht, spk) * valid             # :210
+        if clip_denoised:
+            x0 = x0.clamp(-1.0, 1.0)                                            # :211-212
+        if self.model != "shallow":
+            x_start = x0                                                        # :215-216
+        else:
+            x_start = self.norm_spec(coarse_mel).transpose(1, 2)[:, None, :, :]  # :218-219
+        x_prev_pred = self.q_posterior_sample(x_start, x_t, t, post_noise) * valid   # :220
+        tr = lambda x: x[:, 0].transpose(1, 2)                                  # :222-225
+        return tr(x0), tr(x_t), tr(x_t_prev), tr(x_prev_pred), t

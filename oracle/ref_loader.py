@@ -87,21 +87,25 @@ class injected_noise:
     """Context manager: make the reference's ``noise_like`` / ``randn_like`` return
     the given tensors, in call order."""
 
-    def __init__(self, noise_like_seq=(), randn_like_seq=()):
+    def __init__(self, noise_like_seq=(), randn_like_seq=(), randint_seq=()):
         self.nl = list(noise_like_seq)
         self.rl = list(randn_like_seq)
+        self.ri = list(randint_seq)
 
     def __enter__(self):
         import torch
         self.mod = load()
-        self._nl, self._rl = self.mod.noise_like, torch.randn_like
-        nl, rl = iter(self.nl), iter(self.rl)
+        self._nl, self._rl, self._ri = self.mod.noise_like, torch.randn_like, torch.randint
+        nl, rl, ri = iter(self.nl), iter(self.rl), iter(self.ri)
         self.mod.noise_like = lambda shape, device, repeat=False: next(nl)
         self.mod.torch.randn_like = lambda x, **k: next(rl)
+        if self.ri:
+            self.mod.torch.randint = lambda *a, **k: next(ri)
         return self
 
     def __exit__(self, *exc):
         import torch
         self.mod.noise_like = self._nl
         torch.randn_like = self._rl
+        torch.randint = self._ri
         return False

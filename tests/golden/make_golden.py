@@ -89,6 +89,40 @@ def run_case(name, dataset, model, multi, B, T, wseed, iseed):
     print(name, "K", K, "final", tuple(res[0].shape), "rms", float(res[0].pow(2).mean().sqrt()))
 
 
+TRAIN_CASES = {
+    # name: dataset, model, multi_speaker, B, T, weight seed, input seed   (training branch, forward values only)
+    "train_naive_lj_B3_T48": ("LJSpeech", "naive", False, 3, 48, 0, 21),
+    "train_shallow_aishell_spk_B2_T40": ("AISHELL3", "shallow", True, 2, 40, 7, 22),
+}
+
+
+def run_train_case(name, dataset, model, multi, B, T, wseed, iseed):
+    """model/diffusion.py:201-225 with every random draw injected in call order: randint (:203), two randn_like
+    (diffuse_fn :182 via :206-207) and one noise_like (q_posterior_sample :116)."""
+    torch.set_num_threads(1)
+    args, pc, mc, tc = configs.make_configs(dataset, model, multi)
+    W = synth.make_denoiser_weights(wseed, layers=mc["denoiser"]["residual_layers"], multi_speaker=multi)
+    gd = ref_loader.build_reference_diffusion(args, pc, mc, tc, W)
+    K = gd.num_timesteps
+    inp = synth.make_inputs(iseed, B, T, K, multi_speaker=multi, shallow=(model == "shallow"))
+    ex = synth.make_train_extras(iseed + 1000, B, T, K)
+    tt = lambda a: None if a is None else torch.from_numpy(a)
+    with ref_loader.injected_noise(noise_like_seq=[tt(ex["post_noise"])],
+                                   randn_like_seq=[tt(ex["noise_t"]), tt(ex["noise_prev"])],
+                                   randint_seq=[tt(ex["t"]).clone()]):
+        with torch.no_grad():
+            res = gd(tt(ex["mel"]), tt(inp["cond"]), tt(inp["spk"]), tt(inp["pad_mask"]), coarse_mel=tt(inp["coarse_mel"]))
+    out = {"weights_sha256": synth.weights_digest(W), "torch_version": torch.__version__, "K": K,
+           "x_0_pred": res[0].numpy(), "x_t": res[1].numpy(), "x_t_prev": res[2].numpy(),
+           "x_t_prev_pred": res[3].numpy(), "t": res[4].numpy()}
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(name, "K", K, "t", res[4].tolist(), "x0 rms", float(res[0].pow(2).mean().sqrt()))
+
+
 if __name__ == "__main__":
-    for name, spec in CASES.items():
-        run_case(name, *spec)
+    only_train = "--train-only" in sys.argv
+    if not only_train:
+        for name, spec in CASES.items():
+            run_case(name, *spec)
+    for name, spec in TRAIN_CASES.items():
+        run_train_case(name, *spec)

@@ -20,6 +20,22 @@ GOLDEN_CASES = {
 }
 
 
+# training-branch goldens (forward values): same tuple layout
+TRAIN_CASES = {
+    "train_naive_lj_B3_T48": ("LJSpeech", "naive", False, 3, 48, 0, 21),
+    "train_shallow_aishell_spk_B2_T40": ("AISHELL3", "shallow", True, 2, 40, 7, 22),
+}
+TRAIN_KEYS = ("x_0_pred", "x_t", "x_t_prev", "x_t_prev_pred")
+
+
+def train_case(name):
+    """(Case, extras dict of torch tensors) of one training-branch golden."""
+    spec = TRAIN_CASES[name]
+    c = Case(*spec)
+    ex = synth.make_train_extras(spec[6] + 1000, c.B, c.T, c.K)
+    return c, {k: torch.from_numpy(v) for k, v in ex.items()}
+
+
 def rel_l2(a, b) -> float:
     a = torch.as_tensor(a, dtype=torch.float64).cpu()
     b = torch.as_tensor(b, dtype=torch.float64).cpu()

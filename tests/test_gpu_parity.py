@@ -15,7 +15,7 @@ import torch
 from mixgan_tts_b200 import GaussianDiffusion, _lib
 from mixgan_tts_b200.length_regulator import LengthRegulator
 
-from helpers import GOLDEN_CASES, Case, golden_case, load_golden, rel_l2
+from helpers import GOLDEN_CASES, TRAIN_CASES, TRAIN_KEYS, Case, golden_case, load_golden, rel_l2, train_case
 
 pytestmark = pytest.mark.gpu
 
@@ -184,6 +184,25 @@ def test_sampling_loop_matches_step_by_step_p_sample(precision):
         x = gd.p_sample(x, t, cond.transpose(1, 2), None, noise=noises[i])
     ref = gd.denorm_spec(x[:, 0].transpose(1, 2)) * (~pad).unsqueeze(-1)
     assert rel_l2(mel, ref) < (1e-5 if precision == "fp32" else 2e-3)
+
+
+@pytest.mark.parametrize("precision", PRECS)
+@pytest.mark.parametrize("name", list(TRAIN_CASES))
+def test_training_branch_forward_values_vs_golden(name, precision):
+    """`forward(mel given)` under no_grad (evaluate.py's use): the reference's 5-tuple, every draw injected."""
+    g = load_golden(name)
+    c, ex = train_case(name)
+    gd = build(c, precision)
+    with torch.no_grad():
+        out = gd(cu(ex["mel"]), cu(c.t("cond")), cu(c.t("spk")), cu(c.t("pad_mask")), coarse_mel=cu(c.t("coarse_mel")),
+                 t=cu(ex["t"]), noise_t=cu(ex["noise_t"]), noise_prev=cu(ex["noise_prev"]), post_noise=cu(ex["post_noise"]))
+    assert torch.equal(out[4].cpu(), torch.from_numpy(g["t"]))
+    for k, v in zip(TRAIN_KEYS, out):
+        tol = 1e-5 if k in ("x_t", "x_t_prev") else TOL[precision]["norm"]     # the two diffused states involve no network
+        assert rel_l2(v, g[k]) < tol, k
+    gd.train()
+    with pytest.raises(NotImplementedError):                                    # autograd would need a backward
+        gd(cu(ex["mel"]), cu(c.t("cond")), cu(c.t("spk")), cu(c.t("pad_mask")), coarse_mel=cu(c.t("coarse_mel")))
 
 
 def test_shallow_start_and_denorm_elementwise_exact():

@@ -8,7 +8,7 @@ from mixgan_tts_b200 import synth
 from oracle import schedule
 from oracle.denoiser import denoiser_forward
 
-from helpers import GOLDEN_CASES, golden_case, load_golden, rel_l2
+from helpers import GOLDEN_CASES, TRAIN_CASES, TRAIN_KEYS, golden_case, load_golden, rel_l2, train_case
 
 # fp32 on a different host CPU may pick different oneDNN kernels: allow rounding-level drift.
 TOL = 2e-5
@@ -89,3 +89,21 @@ def test_full_inference_matches_reference_golden(name):
     # padded frames are zeroed by the final mask (model/diffusion.py:200)
     pad = c.t("pad_mask")
     assert float(final[pad].abs().max()) == 0.0 if pad.any() else True
+
+
+@pytest.mark.parametrize("name", list(TRAIN_CASES))
+def test_training_branch_matches_reference_golden(name):
+    """model/diffusion.py:201-225 (forward values) with every random draw injected."""
+    g = load_golden(name)
+    c, ex = train_case(name)
+    assert synth.weights_digest(c.W) == str(g["weights_sha256"])
+    out = c.oracle.forward_training(ex["mel"], c.t("cond"), c.t("spk"), c.t("pad_mask"), t=ex["t"], noise_t=ex["noise_t"],
+                                    noise_prev=ex["noise_prev"], post_noise=ex["post_noise"], coarse_mel=c.t("coarse_mel"))
+    assert np.array_equal(out[4].numpy(), g["t"])
+    for k, v in zip(TRAIN_KEYS, out):
+        assert v.shape == g[k].shape, k
+        assert rel_l2(v, g[k]) < TOL, k
+    # t = 0 rows: x_{t-1} is the clean (normalised) mel and the posterior sample equals x_start exactly (coef1 = 1, sigma = 0)
+    b0 = int(np.nonzero(g["t"] == 0)[0][0])
+    valid = ~c.t("pad_mask")[b0]
+    assert torch.equal(out[2][b0][valid], c.oracle.norm_spec(ex["mel"])[b0][valid])

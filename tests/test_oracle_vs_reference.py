@@ -42,3 +42,21 @@ def test_multi_speaker_without_embedding_raises_like_reference():
     with pytest.raises(TypeError):
         denoiser_forward(c.oracle.W, c.t("x_T"), torch.zeros(1, dtype=torch.long),
                          c.t("cond").transpose(1, 2), None)
+
+
+@pytest.mark.parametrize("model,multi", [("naive", False), ("shallow", True)])
+def test_training_branch_oracle_matches_live_reference(model, multi):
+    """model/diffusion.py:201-225 with randint / randn_like / noise_like injected in call order."""
+    from mixgan_tts_b200 import synth
+    c = Case("LJSpeech", model, multi, 3, 40, wseed=3, iseed=12, layers=3)
+    ex = {k: torch.from_numpy(v) for k, v in synth.make_train_extras(77, c.B, c.T, c.K).items()}
+    gd = ref_loader.build_reference_diffusion(c.args, c.pc, c.mc, c.tc, c.W)
+    with ref_loader.injected_noise(noise_like_seq=[ex["post_noise"]], randn_like_seq=[ex["noise_t"], ex["noise_prev"]],
+                                   randint_seq=[ex["t"].clone()]):
+        with torch.no_grad():
+            ref = gd(ex["mel"], c.t("cond"), c.t("spk"), c.t("pad_mask"), coarse_mel=c.t("coarse_mel"))
+    out = c.oracle.forward_training(ex["mel"], c.t("cond"), c.t("spk"), c.t("pad_mask"), t=ex["t"], noise_t=ex["noise_t"],
+                                    noise_prev=ex["noise_prev"], post_noise=ex["post_noise"], coarse_mel=c.t("coarse_mel"))
+    for a, b in zip(out[:4], ref[:4]):
+        assert rel_l2(a, b) < 1e-6
+    assert torch.equal(out[4], ref[4])

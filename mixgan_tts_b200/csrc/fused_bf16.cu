@@ -40,6 +40,8 @@
 // accumulator-ready events, layer-boundary stamps and per-load ring latencies (see bf16_run).
 #include <cstdlib>
 
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 #include "small_ops.cuh"
 #include "tc05.cuh"
@@ -108,11 +110,15 @@ struct FusedParams {
   const float* b_in;            // [C]
   const float* b_skip;          // [C]
   const float* b_out;           // [128]
-  const float* U_in;            // [B*T][C] fp32 u spilled by the previous group
-  float* U_out;                 // [B*T][C] fp32 u for the next group (ping-pong: neighbours read U_in meanwhile)
-  float* S;                     // [B*T][C] fp32 partial skip sum between groups
+  // Between layer groups the residual stream and the partial skip sum are spilled as fp16 (saturating): half the
+  // HBM traffic of fp32, small enough to stay mostly L2-resident until the next launch re-reads it, and a 2^-11
+  // rounding once per group boundary is far below the bf16 operand rounding of every layer.
+  const __half* U_in;           // [B*T][C] u spilled by the previous group
+  __half* U_out;                // [B*T][C] u for the next group (ping-pong: neighbours read U_in meanwhile)
+  __half* S;                    // [B*T][C] partial skip sum between groups
   int B, T, Tg, R, L, lb, le, V, halo;
   int* status;
+  int debug_mode;               // MGB_DEBUG_MODE: 1 = setup + teardown only (timing experiment)
   long long* prof;              // debug (MGB_PROFILE): per-CTA cycle counters, 16 per CTA
 };
 
@@ -125,6 +131,13 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
 }
+__device__ __forceinline__ uint32_t pack_f16_sat(float lo, float hi) {   // two floats -> fp16x2, clamped to the finite range
+  lo = fminf(fmaxf(lo, -65504.f), 65504.f);
+  hi = fminf(fmaxf(hi, -65504.f), 65504.f);
+  __half2 v = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float2 unpack_f16(uint32_t w) { return __half22float2(*reinterpret_cast<__half2*>(&w)); }
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
@@ -192,8 +205,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_p
   int prof_w0 = first_group ? 10 : 0;
   for (int l = p.lb; l < p.lb + 2 && l < p.le; ++l) prof_w0 += (l < p.L - 1) ? (KUNI ? 45 : 44) : 32;
 
+#define MGB_STAMP(cond_, id_) do { if (PROF && (cond_)) p.prof[blockIdx.x * 320 + 256 + (id_)] = clock64() - t_start; } while (0)
+  MGB_STAMP(tid == 0, 0);   // setup done
+
   long long t_tfull_out = 0;
-  if (warp < 4) {
+  if (p.debug_mode & 1) {
+    // nothing: measure setup + teardown
+  } else if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
     // The roles below run with WARP-UNIFORM control flow (all 32 lanes wait on the barriers and walk
     // the schedule); only the instructions that must come from one thread (bulk copies, tcgen05.mma,
@@ -209,7 +227,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_p
       auto advance = [&]() {
         if (PROF) {
           const int w = n_issued - prof_w0;
-          if (w >= 0 && w < 96 && lane == 0) p.prof[blockIdx.x * 256 + 64 + w] = clock64() - t_start;
+          if (w >= 0 && w < 96 && lane == 0) p.prof[blockIdx.x * 320 + 64 + w] = clock64() - t_start;
           ++n_issued;
         }
         const bool wrap = slot == NSLOTS - 1;
@@ -263,7 +281,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_p
         for (int i = 0; i < 4; ++i) {                                       // conv chunk: 6 weight slots + bias slot
           for (int j = 0; j < 6; ++j) {
             load_w(base + 7 * i + j, SLOT_BYTES);
-            if (PROF && l == p.lb + 3 && i == 0 && j == 0 && lane == 0) p.prof[blockIdx.x * 256 + 60] = clock64() - t_start;
+            if (PROF && l == p.lb + 3 && i == 0 && j == 0 && lane == 0) p.prof[blockIdx.x * 320 + 60] = clock64() - t_start;
           }
           load_w(base + 7 * i + 6, BIAS_SLOT_BYTES);
         }
@@ -279,7 +297,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_p
         for (int i = 0; i < 4; ++i) load_w(W_SKIPP + i, SLOT_BYTES);
         for (int i = 0; i < 2; ++i) load_w(W_OUT + i, SLOT_BYTES);
       }
-      if (PROF && lane == 0) { p.prof[blockIdx.x * 256 + 12] = t_empty; p.prof[blockIdx.x * 256 + 13] = clock64() - t_start; }
+      if (PROF && lane == 0) { p.prof[blockIdx.x * 320 + 12] = t_empty; p.prof[blockIdx.x * 320 + 13] = clock64() - t_start; }
     } else if (warp == 1 && rank != 0) {
       // =========================== RELAY (peer CTA) ===========================
       // Forwards "my half of ring slot s has landed" to the leader's FULL[s] barrier.
@@ -299,7 +317,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_p
         for (int i = 0; i < n_loads; ++i) {
           tc::mbar_wait_trap(bar0 + (B_FULL + slot) * 8, phase, WAIT_CYCLES, p.status, 32);
           const int w = i - prof_w0;
-          if (w >= 0 && w < 96 && lane == 0) p.prof[blockIdx.x * 256 + 160 + w] = clock64() - t_start;
+          if (w >= 0 && w < 96 && lane == 0) p.prof[blockIdx.x * 320 + 160 + w] = clock64() - t_start;
           const bool wrap = slot == NSLOTS - 1;
           slot = wrap ? 0u : slot + 1u;
           phase ^= wrap ? 1u : 0u;
@@ -362,7 +380,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_p
       bool stamp_next_full = false;
       auto mma_w128 = [&](uint64_t a0, uint64_t a1, uint32_t a_kstep16, uint32_t d_tmem, uint32_t acc_first) {
         wait_full();
-        if (PROF && stamp_next_full && lane == 0) { p.prof[blockIdx.x * 256 + 62] = clock64() - t_start; }
+        if (PROF && stamp_next_full && lane == 0) { p.prof[blockIdx.x * 320 + 62] = clock64() - t_start; }
         stamp_next_full = false;
         const uint32_t s0 = slot;
         advance();
@@ -478,6 +496,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_p
       pretest();
       if (first_group) {
         wait_bar(B_AREADY, n_aready); wait_bar(B_AREADY + 1, n_aready); ++n_aready;   // x_t tile as bf16, channels 0..79
+        MGB_STAMP(lane == 0, 1);                        // x_t tile seen
         temp_acquire(0); temp_acquire(1);               // input projection, K = 80, N = 256
         mma_w256(dA + (16 >> 4), A_K16, tm_t(0), 0u, true);
         mma_w256(dA + ((16 + 8 * A_LBO) >> 4), A_K16, tm_t(0), 1u, false);
@@ -487,7 +506,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_p
         temp_publish(0); temp_publish(1);
       }
       auto stamp = [&](int l, int lref, int id) {
-        if (PROF && l == lref && lane == 0) p.prof[blockIdx.x * 256 + 48 + id] = clock64() - t_start;
+        if (PROF && l == lref && lane == 0) p.prof[blockIdx.x * 320 + 48 + id] = clock64() - t_start;
       };
       for (int l = p.lb; l < p.le; ++l) {
         wait_bar(B_AREADY, n_aready);                   // conv input u_l, channels [0, 128), in sA (both CTAs)
@@ -512,6 +531,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_p
             const uint64_t a0 = dA + (q0 - 3 * kb0) + kb0 * ((8 * A_LBO) >> 4);   // tap = +16 B row shift of the start address
             const uint64_t a1 = dA + (q1 - 3 * kb1) + kb1 * ((8 * A_LBO) >> 4);
             mma_w128(a0, a1, A_K16, tm_t(tb), j ? 1u : 0u);
+            MGB_STAMP(lane == 0 && l == p.lb && i == 0 && j == 0, 4);   // first conv slot of the launch issued
             if (i == 0 && j == 0) stamp(l, p.lb + 3, 5);
             if (i == 0 && j == 5) stamp(l, p.lb + 3, 6);
           }
@@ -559,6 +579,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_p
       }
       if (tc::elect_one()) tc::umma_commit_2cta_mc(bar0 + B_SKIPDONE * 8);
       __syncwarp();
+      MGB_STAMP(lane == 0, 5);                          // last layer issued
       if (last_group) {
         wait_bar(B_AREADY, n_aready); wait_bar(B_AREADY + 1, n_aready); ++n_aready;   // skip sum / sqrt(L) as bf16 in sA
         temp_acquire(0); temp_acquire(1);
@@ -571,7 +592,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_p
         temp_publish(0);
       }
       if (PROF && lane == 0) {
-        long long* q = p.prof + blockIdx.x * 256;
+        long long* q = p.prof + blockIdx.x * 320;
         q[0] = t_full; q[1] = t_temp; q[2] = t_ar; q[3] = t_gr; q[4] = clock64() - t_start;
         q[5] = t_full_first; q[6] = t_full_max; q[7] = n_full_slow;
         for (int i = 0; i < 8; ++i) q[16 + i] = t_site[i];
@@ -608,7 +629,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_p
       const long long t0 = PROF ? clock64() : 0;
       tc::mbar_wait_trap(bar0 + (B_TFULL + tb) * 8, (n_use >> 1) & 1, WAIT_CYCLES, p.status, 4);
       if (PROF) t_tfull += clock64() - t0;
-      if (PROF && warp == 4 && lane == 0 && ts_n >= 0 && ts_n < 16) p.prof[blockIdx.x * 256 + 32 + ts_n++] = clock64() - t_start;
+      if (PROF && warp == 4 && lane == 0 && ts_n >= 0 && ts_n < 16) p.prof[blockIdx.x * 320 + 32 + ts_n++] = clock64() - t_start;
       ++n_use;
       tc::tc_fence_after();
     };
@@ -662,6 +683,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_p
                        pack_bf16(xv[8 * jj + 6], xv[8 * jj + 7]));
       }
       publish_a(-1);
+      MGB_STAMP(warp == 4 && lane == 0, 8);             // x_t published
 #pragma unroll
       for (int c = 0; c < 2; ++c) {     // u = relu(W_in x + b_in)
         temp_wait(c);
@@ -682,9 +704,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_p
         }
         temp_release(c);
       }
+      MGB_STAMP(warp == 4 && lane == 0, 9);             // relu done
 #pragma unroll
       for (int c = 0; c < 2; ++c) {     // u += Wc_0 cond + (d_0 + bc_0 + s_0)
         temp_wait(c);
+        MGB_STAMP(warp == 4 && lane == 0 && c == 0, 10);   // cond0 accumulator seen
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
           uint32_t a[32];
@@ -705,15 +729,23 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_p
       }
       publish_a(-1);
     } else {
-      // reload u_lb spilled by the previous group (all 32 loads in flight before the first use)
+      // reload u_lb spilled by the previous group (fp16; all 16 loads in flight before the first use)
+      {
+        uint4 raw[16];
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        const float4* up = reinterpret_cast<const float4*>(p.U_in + row_g * C + 128 * c + 64 * h);
+        for (int c = 0; c < 2; ++c) {
+          const uint4* up = reinterpret_cast<const uint4*>(p.U_in + row_g * C + 128 * c + 64 * h);
 #pragma unroll
-        for (int j4 = 0; j4 < 16; ++j4) {
-          const float4 v = in_seq ? __ldg(up + j4) : make_float4(0.f, 0.f, 0.f, 0.f);
-          u[64 * c + 4 * j4 + 0] = v.x; u[64 * c + 4 * j4 + 1] = v.y;
-          u[64 * c + 4 * j4 + 2] = v.z; u[64 * c + 4 * j4 + 3] = v.w;
+          for (int j8 = 0; j8 < 8; ++j8) raw[8 * c + j8] = in_seq ? __ldg(up + j8) : make_uint4(0u, 0u, 0u, 0u);
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const uint32_t w4[4] = {raw[i].x, raw[i].y, raw[i].z, raw[i].w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 f2 = unpack_f16(w4[e]);
+            u[8 * i + 2 * e] = f2.x; u[8 * i + 2 * e + 1] = f2.y;
+          }
         }
       }
       write_A(0, &u[0]);
@@ -721,6 +753,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_p
       publish_a(-1);
     }
 
+    MGB_STAMP(warp == 4 && lane == 0, 11);              // u_lb published
     // ---- residual blocks ----
     for (int l = p.lb; l < p.le; ++l) {
       if (PROF && l == p.lb + 2) ts_n = 0;
@@ -755,7 +788,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_p
 #pragma unroll
           for (int c = 0; c < 2; ++c) {
             temp_wait(c);
-            if (PROF && l == p.lb + 2 && warp == 4 && lane == 0) p.prof[blockIdx.x * 256 + 56 + 2 * c] = clock64() - t_start;
+            if (PROF && l == p.lb + 2 && warp == 4 && lane == 0) p.prof[blockIdx.x * 320 + 56 + 2 * c] = clock64() - t_start;
             uint32_t a0[32], a1[32];
             tc::tmem_ld32(tm_t(c) + 64 * h, a0);
             tc::tmem_ld32(tm_t(c) + 64 * h + 32, a1);
@@ -768,7 +801,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_p
             }
             write_A(c, &u[64 * c]);
             publish_a(c);
-            if (PROF && l == p.lb + 2 && warp == 4 && lane == 0) p.prof[blockIdx.x * 256 + 57 + 2 * c] = clock64() - t_start;
+            if (PROF && l == p.lb + 2 && warp == 4 && lane == 0) p.prof[blockIdx.x * 320 + 57 + 2 * c] = clock64() - t_start;
           }
         } else {
           // u <- (u + acc)/sqrt(2) + k_l ; write the next conv input.  k_l comes from L2 (no L1 to speak of next to
@@ -813,31 +846,48 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_p
     }
 
     // ---- group end ----
-    tc::mbar_wait_trap(bar0 + B_SKIPDONE * 8, 0, WAIT_CYCLES, p.status, 4);
-    tc::tc_fence_after();
+    MGB_STAMP(warp == 4 && lane == 0, 12);              // last layer's epilogue done
+    uint4 sraw[16];                                     // last group: this thread's 128 channels of the spilled skip sum
     if (!last_group) {
-      if (is_out) {
+      if (is_out) {                                     // spill u while the last skip GEMM is still running
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
-          float4* up = reinterpret_cast<float4*>(p.U_out + row_g * C + 128 * c + 64 * h);
+          uint4* up = reinterpret_cast<uint4*>(p.U_out + row_g * C + 128 * c + 64 * h);
 #pragma unroll
-          for (int j4 = 0; j4 < 16; ++j4)
-            up[j4] = make_float4(u[64 * c + 4 * j4], u[64 * c + 4 * j4 + 1], u[64 * c + 4 * j4 + 2], u[64 * c + 4 * j4 + 3]);
+          for (int j8 = 0; j8 < 8; ++j8) {
+            const float* v = &u[64 * c + 8 * j8];
+            up[j8] = make_uint4(pack_f16_sat(v[0], v[1]), pack_f16_sat(v[2], v[3]), pack_f16_sat(v[4], v[5]), pack_f16_sat(v[6], v[7]));
+          }
         }
       }
+    } else if (!first_group) {                          // fetch the earlier groups' skip sum before waiting for this group's
+      const uint4* sp = reinterpret_cast<const uint4*>(p.S + row_g * C + 128 * h);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) sraw[i] = in_seq ? __ldg(sp + i) : make_uint4(0u, 0u, 0u, 0u);
+    }
+    tc::mbar_wait_trap(bar0 + B_SKIPDONE * 8, 0, WAIT_CYCLES, p.status, 4);
+    tc::tc_fence_after();
+    MGB_STAMP(warp == 4 && lane == 0, 13);              // skip accumulator complete
+    if (!last_group) {
 #pragma unroll
       for (int cc = 0; cc < 4; ++cc) {  // partial skip sum, channels [128h + 32cc, +32)
         uint32_t a[32];
         tc::tmem_ld32(TM_SKIP + lane_off + 128 * h + 32 * cc, a);
         tc::tmem_ld_wait();
         if (is_out) {
-          float4* sp = reinterpret_cast<float4*>(p.S + row_g * C + 128 * h + 32 * cc);
+          uint4* sp = reinterpret_cast<uint4*>(p.S + row_g * C + 128 * h + 32 * cc);
 #pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) {
-            float4 v = first_group ? make_float4(0.f, 0.f, 0.f, 0.f) : sp[j4];
-            v.x += __uint_as_float(a[4 * j4 + 0]); v.y += __uint_as_float(a[4 * j4 + 1]);
-            v.z += __uint_as_float(a[4 * j4 + 2]); v.w += __uint_as_float(a[4 * j4 + 3]);
-            sp[j4] = v;
+          for (int j8 = 0; j8 < 4; ++j8) {
+            float v[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(a[8 * j8 + e]);
+            if (!first_group) {                         // three or more groups: accumulate into the spilled sum
+              const uint4 o = sp[j8];
+              const uint32_t w4[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) { const float2 f2 = unpack_f16(w4[e]); v[2 * e] += f2.x; v[2 * e + 1] += f2.y; }
+            }
+            sp[j8] = make_uint4(pack_f16_sat(v[0], v[1]), pack_f16_sat(v[2], v[3]), pack_f16_sat(v[4], v[5]), pack_f16_sat(v[6], v[7]));
           }
         }
       }
@@ -849,22 +899,27 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_p
         uint32_t a[32];
         tc::tmem_ld32(TM_SKIP + lane_off + 128 * h + 32 * cc, a);
         tc::tmem_ld_wait();
-        const float4* sp = reinterpret_cast<const float4*>(p.S + row_g * C + 128 * h + 32 * cc);
         const float4* bp = reinterpret_cast<const float4*>(p.bsum_skip + 128 * h + 32 * cc);
-        float4 s8[8];                    // all eight loads in flight before the first use (S was written by the previous launch)
-#pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4) s8[j4] = (!first_group && in_seq) ? __ldg(sp + j4) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj) {
           float v[8];
+          float sv[8];
+          if (!first_group) {
+            const uint4 o = sraw[4 * cc + jj];
+            const uint32_t w4[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { const float2 f2 = unpack_f16(w4[e]); sv[2 * e] = f2.x; sv[2 * e + 1] = f2.y; }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) sv[e] = 0.f;
+          }
 #pragma unroll
           for (int e4 = 0; e4 < 2; ++e4) {
             const float4 bv = __ldg(bp + jj * 2 + e4);
-            const float4 sv = s8[jj * 2 + e4];
-            v[e4 * 4 + 0] = (__uint_as_float(a[jj * 8 + e4 * 4 + 0]) + sv.x + bv.x) * inv_sqrt_l;
-            v[e4 * 4 + 1] = (__uint_as_float(a[jj * 8 + e4 * 4 + 1]) + sv.y + bv.y) * inv_sqrt_l;
-            v[e4 * 4 + 2] = (__uint_as_float(a[jj * 8 + e4 * 4 + 2]) + sv.z + bv.z) * inv_sqrt_l;
-            v[e4 * 4 + 3] = (__uint_as_float(a[jj * 8 + e4 * 4 + 3]) + sv.w + bv.w) * inv_sqrt_l;
+            v[e4 * 4 + 0] = (__uint_as_float(a[jj * 8 + e4 * 4 + 0]) + sv[e4 * 4 + 0] + bv.x) * inv_sqrt_l;
+            v[e4 * 4 + 1] = (__uint_as_float(a[jj * 8 + e4 * 4 + 1]) + sv[e4 * 4 + 1] + bv.y) * inv_sqrt_l;
+            v[e4 * 4 + 2] = (__uint_as_float(a[jj * 8 + e4 * 4 + 2]) + sv[e4 * 4 + 2] + bv.z) * inv_sqrt_l;
+            v[e4 * 4 + 3] = (__uint_as_float(a[jj * 8 + e4 * 4 + 3]) + sv[e4 * 4 + 3] + bv.w) * inv_sqrt_l;
           }
           st_shared_v4(aA + (uint32_t)(16 * h + 4 * cc + jj) * A_LBO + (uint32_t)(r + 1) * 16, pack_bf16(v[0], v[1]),
                        pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
@@ -943,7 +998,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_p
     if (PROF) t_tfull_out = t_tfull;
   }
 
-  if (PROF && warp == 4 && lane == 0) { p.prof[blockIdx.x * 256 + 8] = t_tfull_out; p.prof[blockIdx.x * 256 + 9] = clock64() - t_start; }
+  MGB_STAMP(warp == 4 && lane == 0, 14);                // group end / tail done
+  if (PROF && warp == 4 && lane == 0) { p.prof[blockIdx.x * 320 + 8] = t_tfull_out; p.prof[blockIdx.x * 320 + 9] = clock64() - t_start; }
   // ---- teardown: neither CTA may leave (or free TMEM) while the pair's MMAs can still touch it ----
   tc::tc_fence_before();
   __syncthreads();
@@ -1140,9 +1196,9 @@ WorkBf16 work_layout(const mgb_model_dims& d, int B, int T, int K) {
   w.ktab = take((size_t)K * B * d.layers * C * 4);
   w.k00 = take((size_t)K * B * C * 4);
   w.kimg = take((size_t)K * d.layers * 2 * KIMG_BYTES);
-  w.U = take((size_t)B * T * C * 4);
-  w.U2 = take((size_t)B * T * C * 4);
-  w.S = take((size_t)B * T * C * 4);
+  w.U = take((size_t)B * T * C * 2);
+  w.U2 = take((size_t)B * T * C * 2);
+  w.S = take((size_t)B * T * C * 2);
   w.total = p;
   return w;
 }
@@ -1283,9 +1339,11 @@ int bf16_run(const mgb_model_dims& d, const void* packed, const float* x, const 
   p.kimg = W + w.kimg + (size_t)step * L * 2 * KIMG_BYTES;
   p.bsum_skip = P + o.bsum_skip;
   p.b_in = P + o.b_in; p.b_skip = P + o.b_skip; p.b_out = P + o.b_out;
-  float* Ubuf[2] = {reinterpret_cast<float*>(W + w.U), reinterpret_cast<float*>(W + w.U2)};
-  p.S = reinterpret_cast<float*>(W + w.S);
+  __half* Ubuf[2] = {reinterpret_cast<__half*>(W + w.U), reinterpret_cast<__half*>(W + w.U2)};
+  p.S = reinterpret_cast<__half*>(W + w.S);
   p.B = B; p.T = T; p.Tg = w.Tg; p.R = w.R; p.L = L; p.status = reinterpret_cast<int*>(W + w.status);
+  static const int debug_mode = getenv("MGB_DEBUG_MODE") ? atoi(getenv("MGB_DEBUG_MODE")) : 0;
+  p.debug_mode = debug_mode;
   const int ngroups = plan_groups(L, w.R, pair_slots);
   for (int g = 0; g < ngroups; ++g) {
     p.lb = g * L / ngroups;
@@ -1295,23 +1353,27 @@ int bf16_run(const mgb_model_dims& d, const void* packed, const float* x, const 
     const int npairs = (w.R + p.V - 1) / p.V;
     p.U_in = Ubuf[g & 1];
     p.U_out = Ubuf[(g + 1) & 1];
+    // timing experiments (MGB_DEBUG_MODE bit mask): 1 = setup + teardown only, 2 = prologue + ending without layers,
+    // 4 = skip the first group's launch, 8 = skip the later groups' launches.  Results are garbage in every mode.
+    if (debug_mode & 2) { if (g == 0) p.le = p.lb; else p.lb = p.le; }
+    if (((debug_mode & 4) && g == 0) || ((debug_mode & 8) && g > 0)) continue;
     prof_begin(s);
     static const bool do_prof = getenv("MGB_PROFILE") != nullptr;
     if (do_prof) {
       const int ncta = 2 * npairs;
       long long* dprof = nullptr;
-      cudaMalloc(&dprof, (size_t)ncta * 256 * sizeof(long long));
-      cudaMemset(dprof, 0, (size_t)ncta * 256 * sizeof(long long));
+      cudaMalloc(&dprof, (size_t)ncta * 320 * sizeof(long long));
+      cudaMemset(dprof, 0, (size_t)ncta * 320 * sizeof(long long));
       p.prof = dprof;
       cudaFuncSetAttribute(fused_pair_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL);
       cudaFuncSetAttribute(fused_pair_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL);
       if (kuni) fused_pair_kernel<true, true><<<ncta, NTHREADS, SMEM_TOTAL, s>>>(p);
       else fused_pair_kernel<true, false><<<ncta, NTHREADS, SMEM_TOTAL, s>>>(p);
       cudaStreamSynchronize(s);
-      long long* h = (long long*)malloc((size_t)ncta * 256 * sizeof(long long));
-      cudaMemcpy(h, dprof, (size_t)ncta * 256 * sizeof(long long), cudaMemcpyDeviceToHost);
+      long long* h = (long long*)malloc((size_t)ncta * 320 * sizeof(long long));
+      cudaMemcpy(h, dprof, (size_t)ncta * 320 * sizeof(long long), cudaMemcpyDeviceToHost);
       double a[64] = {0};   // MMA-warp counters exist on leader CTAs only (even blocks)
-      for (int i = 0; i < ncta; i += 2) for (int k = 0; k < 64; ++k) a[k] += (double)h[i * 256 + k] / npairs;
+      for (int i = 0; i < ncta; i += 2) for (int k = 0; k < 64; ++k) a[k] += (double)h[i * 320 + k] / npairs;
       fprintf(stderr, "[mgb profile] layers [%d,%d) pairs %d | MMA warp: total %.0f wait_full %.0f wait_temp %.0f wait_aready %.0f "
               "wait_gready %.0f (first wait_full %.0f, max later %.0f, waits > 300 cyc: %.0f) | epilogue w4: total %.0f wait_tfull %.0f | "
               "producer: total %.0f wait_empty %.0f | temp by site: conv %.0f resT0 %.0f resT1 %.0f other %.0f | A-ready by site: A0 %.0f H0 %.0f "
@@ -1331,11 +1393,25 @@ int bf16_run(const mgb_model_dims& d, const void* packed, const float* x, const 
         double lat[2][96] = {{0}}, iss[96] = {0};
         for (int i = 0; i < ncta; ++i)
           for (int k = 0; k < 96; ++k) {
-            lat[i & 1][k] += (double)(h[i * 256 + 160 + k] - h[i * 256 + 64 + k]) / npairs;
-            if (!(i & 1)) iss[k] += (double)h[i * 256 + 64 + k] / npairs;
+            lat[i & 1][k] += (double)(h[i * 320 + 160 + k] - h[i * 320 + 64 + k]) / npairs;
+            if (!(i & 1)) iss[k] += (double)h[i * 320 + 64 + k] / npairs;
           }
         fprintf(stderr, "[mgb ring] load latency (issue -> FULL seen) from layer %d, leader incl. relay / peer own half; issue time delta:", p.lb + 2);
         for (int k = 0; k < 96; ++k) fprintf(stderr, " %d:%.0f/%.0f(+%.0f)", k, lat[0][k], lat[1][k], k ? iss[k] - iss[k - 1] : 0.0);
+        fprintf(stderr, "\n");
+      }
+      {
+        double st[16] = {0};
+        for (int i = 0; i < ncta; i += 2) for (int k = 0; k < 16; ++k) st[k] += (double)h[i * 320 + 256 + k] / npairs;
+        fprintf(stderr, "[mgb tile] cycles since kernel start (leader CTA means): setup done %.0f | MMA: x_t seen %.0f, relu drained %.0f, cond0 issued %.0f, "
+                "first conv slot issued %.0f, last layer issued %.0f | epilogue w4: x_t published %.0f, relu done %.0f, cond0 seen %.0f, u published %.0f, "
+                "last layer done %.0f, skip complete %.0f, end %.0f\n", st[0], st[1], st[2], st[3], st[4], st[5], st[8], st[9], st[10], st[11],
+                st[12], st[13], st[14]);
+      }
+      {
+        // distribution of "setup done" and "end" over leader CTAs in launch order
+        fprintf(stderr, "[mgb tile] setup-done / first-conv / end per leader CTA (every 12th):");
+        for (int i = 0; i < ncta; i += 24) fprintf(stderr, " %d:%lld/%lld/%lld", i / 2, h[i * 320 + 256], h[i * 320 + 260], h[i * 320 + 270]);
         fprintf(stderr, "\n");
       }
       fprintf(stderr, "[mgb timeline] accumulator-ready deltas from layer %d (conv c0..c3, res T0, res T1, ...):", p.lb + 2);

@@ -73,7 +73,8 @@ constexpr int COND_PAD_HI = 288;       // zero rows behind it (>= TILE_ROWS + MA
 constexpr long long WAIT_CYCLES = 400000000LL;   // ~0.2 s: a protocol bug ends the kernel, never hangs it
 
 // weight-stream slot indices (see pack_images_kernel); each CTA rank has its own image of every slot
-constexpr int W_IN = 0, W_P0 = 2, W_SKIPP = 6, W_OUT = 10, W_LAYER0 = 12, W_PER_LAYER = 40;
+constexpr int W_IN = 0, W_INB = 2, W_P0 = 3, W_SKIPP = 7, W_SKIPPB = 11, W_OUT = 12, W_OUTB = 14, W_LAYER0 = 15, W_PER_LAYER = 40;
+// W_INB / W_SKIPPB / W_OUTB: bias slots (bf16 hi + lo against the "ones" operand) of the input, skip and output projections
 // per layer: 4 conv chunks x (6 weight slots of two (kb, tap) blocks each + 1 bias slot), skip j=0, res cond (4),
 // res g (4), skip j=1..3 (3)
 constexpr int WL_SKIPA = 28, WL_RCOND = 29, WL_RG = 33, WL_SKIPB = 37;
@@ -104,12 +105,9 @@ struct FusedParams {
   int t_uniform;                // >= 0: every utterance is at this timestep (sampling loop)
   int K, clip, n_mel;
   const float* ktab;            // [B][L][C]
+  const uint8_t* k00img;        // KUNI: [2 ranks][4096] image of k00 (added inside the layer-0 conditioner GEMM)
   const uint8_t* kimg;          // KUNI: [L][2 ranks][4096] bf16 (hi, lo) images of sqrt(2) * k_l as N=256 K=16 weight halves
   const float* k00;             // [B][C]
-  const float* bsum_skip;       // [C]
-  const float* b_in;            // [C]
-  const float* b_skip;          // [C]
-  const float* b_out;           // [128]
   // Between layer groups the residual stream and the partial skip sum are spilled as fp16 (saturating): half the
   // HBM traffic of fp32, small enough to stay mostly L2-resident until the next launch re-reads it, and a 2^-11
   // rounding once per group boundary is far below the bf16 operand rounding of every layer.
@@ -194,7 +192,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_p
   const uint32_t slots0 = tc::smem_u32(sSlots);
 
   // number of ring-slot loads of this launch (the producer, the relay and the MMA issuer walk the same sequence)
-  int n_loads = (first_group ? 2 + 8 : 0) + (last_group ? 6 : 0);
+  int n_loads = (first_group ? 3 + 8 + (KUNI ? 1 : 0) : 0) + (last_group ? 8 : 0);
   for (int l = p.lb; l < p.le; ++l) n_loads += (l < p.L - 1) ? (KUNI ? 45 : 44) : 32;
 
   // conv-input tiles of this launch whose edge rows are exchanged between the two CTAs (u_lb and one per block)
@@ -202,7 +200,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_p
   for (int l = p.lb; l < p.le; ++l) n_halo_gens += (l < p.L - 1) ? 1 : 0;
 
   // PROF: ring-load latency window = the 96 loads starting with layer lb+2
-  int prof_w0 = first_group ? 10 : 0;
+  int prof_w0 = first_group ? 11 + (KUNI ? 1 : 0) : 0;
   for (int l = p.lb; l < p.lb + 2 && l < p.le; ++l) prof_w0 += (l < p.L - 1) ? (KUNI ? 45 : 44) : 32;
 
 #define MGB_STAMP(cond_, id_) do { if (PROF && (cond_)) p.prof[blockIdx.x * 320 + 256 + (id_)] = clock64() - t_start; } while (0)
@@ -273,8 +271,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_p
         advance();
       };
       if (first_group) {
-        load_w(W_IN, SLOT_BYTES); load_w(W_IN + 1, 4096);
+        load_w(W_IN, SLOT_BYTES); load_w(W_IN + 1, 4096); load_w(W_INB, KIMG_BYTES);
         for (int m = 0; m < 4; ++m) { load_cond(m); load_w(W_P0 + m, SLOT_BYTES); }
+        if (KUNI) load_raw(p.k00img + (size_t)rank * KIMG_BYTES, KIMG_BYTES);
       }
       for (int l = p.lb; l < p.le; ++l) {
         const int base = W_LAYER0 + l * W_PER_LAYER;
@@ -295,7 +294,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_p
       }
       if (last_group) {
         for (int i = 0; i < 4; ++i) load_w(W_SKIPP + i, SLOT_BYTES);
+        load_w(W_SKIPPB, KIMG_BYTES);
         for (int i = 0; i < 2; ++i) load_w(W_OUT + i, SLOT_BYTES);
+        load_w(W_OUTB, BIAS_SLOT_BYTES);
       }
       if (PROF && lane == 0) { p.prof[blockIdx.x * 320 + 12] = t_empty; p.prof[blockIdx.x * 320 + 13] = clock64() - t_start; }
     } else if (warp == 1 && rank != 0) {
@@ -500,9 +501,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_p
         temp_acquire(0); temp_acquire(1);               // input projection, K = 80, N = 256
         mma_w256(dA + (16 >> 4), A_K16, tm_t(0), 0u, true);
         mma_w256(dA + ((16 + 8 * A_LBO) >> 4), A_K16, tm_t(0), 1u, false);
+        mma_kbias(tm_t(0));                             // + b_in
         temp_publish(0); temp_publish(1);
         temp_acquire(0); temp_acquire(1);               // conditioner projection of layer 0
         for (int m = 0; m < 4; ++m) mma_cond(tm_t(0), m ? 1u : 0u);
+        if (KUNI) mma_kbias(tm_t(0));                   // + k00 (uniform over the batch)
         temp_publish(0); temp_publish(1);
       }
       auto stamp = [&](int l, int lref, int id) {
@@ -584,12 +587,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_p
         wait_bar(B_AREADY, n_aready); wait_bar(B_AREADY + 1, n_aready); ++n_aready;   // skip sum / sqrt(L) as bf16 in sA
         temp_acquire(0); temp_acquire(1);
         for (int m = 0; m < 4; ++m) mma_w256(dA + ((16 + m * 8 * A_LBO) >> 4), A_K16, tm_t(0), m ? 1u : 0u, true);
+        mma_kbias(tm_t(0));                             // + b_skip + W_skip (sum of the blocks' skip biases) / sqrt(L)
         temp_publish(0); temp_publish(1);
+        MGB_STAMP(lane == 0, 6);                        // tail: skip projection issued
         wait_bar(B_GREADY + 0, n_gready++);             // relu(skip projection) as bf16 in sG
         temp_acquire(0);
         for (int j = 0; j < 2; ++j)
           mma_w128(dG + ((j * 16 * G_LBO) >> 4), dG + (((j * 16 + 8) * G_LBO) >> 4), G_K16, tm_t(0), j ? 1u : 0u);
+        mma_bias(tm_t(0));                              // + b_out
         temp_publish(0);
+        MGB_STAMP(lane == 0, 7);                        // tail: output projection issued
       }
       if (PROF && lane == 0) {
         long long* q = p.prof + blockIdx.x * 320;
@@ -692,15 +699,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_p
           uint32_t a[32];
           tc::tmem_ld32(tm_t(c) + 64 * h + 32 * hh, a);
           tc::tmem_ld_wait();
-          const float4* bp = reinterpret_cast<const float4*>(p.b_in + 128 * c + 64 * h + 32 * hh);
 #pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) {
-            const float4 bv = __ldg(bp + j4);
-            u[64 * c + 32 * hh + 4 * j4 + 0] = fmaxf(__uint_as_float(a[4 * j4 + 0]) + bv.x, 0.f);
-            u[64 * c + 32 * hh + 4 * j4 + 1] = fmaxf(__uint_as_float(a[4 * j4 + 1]) + bv.y, 0.f);
-            u[64 * c + 32 * hh + 4 * j4 + 2] = fmaxf(__uint_as_float(a[4 * j4 + 2]) + bv.z, 0.f);
-            u[64 * c + 32 * hh + 4 * j4 + 3] = fmaxf(__uint_as_float(a[4 * j4 + 3]) + bv.w, 0.f);
-          }
+          for (int j = 0; j < 32; ++j) u[64 * c + 32 * hh + j] = fmaxf(__uint_as_float(a[j]), 0.f);   // b_in came with the GEMM
         }
         temp_release(c);
       }
@@ -714,14 +714,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_p
           uint32_t a[32];
           tc::tmem_ld32(tm_t(c) + 64 * h + 32 * hh, a);
           tc::tmem_ld_wait();
-          const float4* kp = reinterpret_cast<const float4*>(p.k00 + (size_t)b * C + 128 * c + 64 * h + 32 * hh);
+          if (KUNI) {                   // k00 came with the GEMM
 #pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) {
-            const float4 kv = __ldg(kp + j4);
-            u[64 * c + 32 * hh + 4 * j4 + 0] += __uint_as_float(a[4 * j4 + 0]) + kv.x;
-            u[64 * c + 32 * hh + 4 * j4 + 1] += __uint_as_float(a[4 * j4 + 1]) + kv.y;
-            u[64 * c + 32 * hh + 4 * j4 + 2] += __uint_as_float(a[4 * j4 + 2]) + kv.z;
-            u[64 * c + 32 * hh + 4 * j4 + 3] += __uint_as_float(a[4 * j4 + 3]) + kv.w;
+            for (int j = 0; j < 32; ++j) u[64 * c + 32 * hh + j] += __uint_as_float(a[j]);
+          } else {
+            const float4* kp = reinterpret_cast<const float4*>(p.k00 + (size_t)b * C + 128 * c + 64 * h + 32 * hh);
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const float4 kv = __ldg(kp + j4);
+              u[64 * c + 32 * hh + 4 * j4 + 0] += __uint_as_float(a[4 * j4 + 0]) + kv.x;
+              u[64 * c + 32 * hh + 4 * j4 + 1] += __uint_as_float(a[4 * j4 + 1]) + kv.y;
+              u[64 * c + 32 * hh + 4 * j4 + 2] += __uint_as_float(a[4 * j4 + 2]) + kv.z;
+              u[64 * c + 32 * hh + 4 * j4 + 3] += __uint_as_float(a[4 * j4 + 3]) + kv.w;
+            }
           }
         }
         temp_release(c);
@@ -899,33 +904,28 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_p
         uint32_t a[32];
         tc::tmem_ld32(TM_SKIP + lane_off + 128 * h + 32 * cc, a);
         tc::tmem_ld_wait();
-        const float4* bp = reinterpret_cast<const float4*>(p.bsum_skip + 128 * h + 32 * cc);
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj) {
           float v[8];
-          float sv[8];
-          if (!first_group) {
+          if (!first_group) {           // + the earlier groups' skip sum (the blocks' skip biases live in the skip-projection bias)
             const uint4 o = sraw[4 * cc + jj];
             const uint32_t w4[4] = {o.x, o.y, o.z, o.w};
 #pragma unroll
-            for (int e = 0; e < 4; ++e) { const float2 f2 = unpack_f16(w4[e]); sv[2 * e] = f2.x; sv[2 * e + 1] = f2.y; }
+            for (int e = 0; e < 4; ++e) {
+              const float2 f2 = unpack_f16(w4[e]);
+              v[2 * e] = (__uint_as_float(a[jj * 8 + 2 * e]) + f2.x) * inv_sqrt_l;
+              v[2 * e + 1] = (__uint_as_float(a[jj * 8 + 2 * e + 1]) + f2.y) * inv_sqrt_l;
+            }
           } else {
 #pragma unroll
-            for (int e = 0; e < 8; ++e) sv[e] = 0.f;
-          }
-#pragma unroll
-          for (int e4 = 0; e4 < 2; ++e4) {
-            const float4 bv = __ldg(bp + jj * 2 + e4);
-            v[e4 * 4 + 0] = (__uint_as_float(a[jj * 8 + e4 * 4 + 0]) + sv[e4 * 4 + 0] + bv.x) * inv_sqrt_l;
-            v[e4 * 4 + 1] = (__uint_as_float(a[jj * 8 + e4 * 4 + 1]) + sv[e4 * 4 + 1] + bv.y) * inv_sqrt_l;
-            v[e4 * 4 + 2] = (__uint_as_float(a[jj * 8 + e4 * 4 + 2]) + sv[e4 * 4 + 2] + bv.z) * inv_sqrt_l;
-            v[e4 * 4 + 3] = (__uint_as_float(a[jj * 8 + e4 * 4 + 3]) + sv[e4 * 4 + 3] + bv.w) * inv_sqrt_l;
+            for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(a[jj * 8 + e]) * inv_sqrt_l;
           }
           st_shared_v4(aA + (uint32_t)(16 * h + 4 * cc + jj) * A_LBO + (uint32_t)(r + 1) * 16, pack_bf16(v[0], v[1]),
                        pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
         }
       }
       publish_a(-1);
+      MGB_STAMP(warp == 4 && lane == 0, 16);            // tail: skip sum published
       // This thread's share of the posterior update: mel bins [40h, 40h+40) of its frame.  x_t and the noise are
       // fetched NOW so that their DRAM latency hides behind the two tail GEMMs instead of following them.
       constexpr int NB = 40;
@@ -949,20 +949,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_p
           tc::tmem_ld32(tm_t(c) + 64 * h + 32 * hh, a);
           tc::tmem_ld_wait();
           if (hh == 1) temp_release(c);
-          const float4* bp = reinterpret_cast<const float4*>(p.b_skip + 128 * c + 64 * h + 32 * hh);
 #pragma unroll
-          for (int jj = 0; jj < 4; ++jj) {
-            const float4 b0 = __ldg(bp + jj * 2), b1 = __ldg(bp + jj * 2 + 1);
-            const float v0 = fmaxf(__uint_as_float(a[jj * 8 + 0]) + b0.x, 0.f), v1 = fmaxf(__uint_as_float(a[jj * 8 + 1]) + b0.y, 0.f);
-            const float v2 = fmaxf(__uint_as_float(a[jj * 8 + 2]) + b0.z, 0.f), v3 = fmaxf(__uint_as_float(a[jj * 8 + 3]) + b0.w, 0.f);
-            const float v4 = fmaxf(__uint_as_float(a[jj * 8 + 4]) + b1.x, 0.f), v5 = fmaxf(__uint_as_float(a[jj * 8 + 5]) + b1.y, 0.f);
-            const float v6 = fmaxf(__uint_as_float(a[jj * 8 + 6]) + b1.z, 0.f), v7 = fmaxf(__uint_as_float(a[jj * 8 + 7]) + b1.w, 0.f);
-            st_shared_v4(aG + (uint32_t)(16 * c + 8 * h + 4 * hh + jj) * G_LBO + (uint32_t)r * 16, pack_bf16(v0, v1),
-                         pack_bf16(v2, v3), pack_bf16(v4, v5), pack_bf16(v6, v7));
+          for (int jj = 0; jj < 4; ++jj) {          // b_skip came with the GEMM
+            float v[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = fmaxf(__uint_as_float(a[jj * 8 + e]), 0.f);
+            st_shared_v4(aG + (uint32_t)(16 * c + 8 * h + 4 * hh + jj) * G_LBO + (uint32_t)r * 16, pack_bf16(v[0], v[1]),
+                         pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
           }
         }
       }
       publish(B_GREADY + 0);
+      MGB_STAMP(warp == 4 && lane == 0, 17);            // tail: relu(skip projection) published
       // output projection -> clamp -> posterior mean + sigma * noise (diffusion.py:104-129), bins [40h, 40h+40)
       float c1 = 0.f, c2 = 0.f, sg = 0.f;
       if (p.sched) {
@@ -970,6 +968,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_p
         c1 = p.sched[tb]; c2 = p.sched[p.K + tb]; sg = p.sched[2 * p.K + tb];
       }
       temp_wait(0);
+      MGB_STAMP(warp == 4 && lane == 0, 18);            // tail: output projection seen
       {
         uint32_t a[32], a2[16];
         tc::tmem_ld32(tm_t(0) + NB * h, a);
@@ -981,7 +980,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_p
           for (int j = 0; j < NB; ++j) {
             const int n = NB * h + j;
             if (n < p.n_mel) {
-              float x0 = __uint_as_float(j < 32 ? a[j] : a2[j - 32]) + __ldg(p.b_out + n);
+              float x0 = __uint_as_float(j < 32 ? a[j] : a2[j - 32]);   // b_out came with the GEMM
               if (p.clip) x0 = fminf(fmaxf(x0, -1.f), 1.f);
               const size_t o = o0 + (size_t)j * p.T;
               if (p.x0_out) p.x0_out[o] = x0;
@@ -1043,12 +1042,21 @@ __global__ void ktab_kernel(const float* __restrict__ dtab, const float* __restr
 }
 
 // KUNI: kimg[s][l][rank] = N=256 weight half ([2 k-chunks][128 rows][8 bf16]) whose K=0/1 columns hold the bf16 hi/lo
-// split of sqrt(2) * ktab[s][0][l][128 rank + row]; all other columns are zero.
-__global__ void kimg_kernel(const float* __restrict__ ktab, uint8_t* __restrict__ kimg, int L, int B) {
+// split of sqrt(2) * ktab[s][0][l][128 rank + row]; all other columns are zero.  Block x == L builds the image of
+// k00[s][0] (no sqrt(2): it is added to u_0 directly).
+__global__ void kimg_kernel(const float* __restrict__ ktab, const float* __restrict__ k00, uint8_t* __restrict__ kimg,
+                            uint8_t* __restrict__ k00img, int L, int B) {
   const int l = blockIdx.x, st = blockIdx.y, rank = blockIdx.z, row = threadIdx.x;   // 128 threads
-  const float v = 1.41421356237309504880f * ktab[(((size_t)st * B) * L + l) * C + 128 * rank + row];
+  float v;
+  uint4* dst;
+  if (l < L) {
+    v = 1.41421356237309504880f * ktab[(((size_t)st * B) * L + l) * C + 128 * rank + row];
+    dst = reinterpret_cast<uint4*>(kimg + (((size_t)st * L + l) * 2 + rank) * KIMG_BYTES);
+  } else {
+    v = k00[((size_t)st * B) * C + 128 * rank + row];
+    dst = reinterpret_cast<uint4*>(k00img + ((size_t)st * 2 + rank) * KIMG_BYTES);
+  }
   const float hi = __bfloat162float(__float2bfloat16_rn(v));
-  uint4* dst = reinterpret_cast<uint4*>(kimg + (((size_t)st * L + l) * 2 + rank) * KIMG_BYTES);
   dst[row] = make_uint4(pack_bf16(hi, v - hi), 0u, 0u, 0u);
   dst[128 + row] = make_uint4(0u, 0u, 0u, 0u);
 }
@@ -1087,16 +1095,20 @@ inline int num_wslots(const mgb_model_dims& d) { return W_LAYER0 + d.layers * W_
 // (weights and bias) carries 0.5 so the epilogue computes tanh(a/2) without a multiply, and Wo_x / Wo_s carry the
 // 0.5 of sigmoid(a)*tanh(f) = 0.5*(tanh(a/2)*tanh(f) + tanh(f)).
 __global__ void pack_images_kernel(const float* __restrict__ flat, const FlatOffsets f, const int L, const int n_mel,
-                                   const int nslots, __nv_bfloat16* __restrict__ img) {
+                                   const int nslots, const float* __restrict__ b_in, const float* __restrict__ b_skipp,
+                                   const float* __restrict__ b_out, __nv_bfloat16* __restrict__ img) {
   const int slot = blockIdx.x, rank = blockIdx.y;
   const float* fl = nullptr;
   int kind, m = 0, ci = 0, j = 0;
   // kind: 0 in-proj, 1 cond-proj layer 0, 2 skip-proj, 3 out-proj, 4 conv, 5 res cond delta, 6 res g (Wo_x),
-  //       7 skip (Wo_s), 8 unused (zeros), 9 conv bias
-  if (slot < W_P0) { kind = 0; m = slot; }
+  //       7 skip (Wo_s), 8 unused (zeros), 9 conv bias, 10 / 11 / 12 input / skip / output projection bias
+  if (slot < W_INB) { kind = 0; m = slot; }
+  else if (slot == W_INB) { kind = 10; }
   else if (slot < W_SKIPP) { kind = 1; m = slot - W_P0; fl = flat + f.layer0; }
-  else if (slot < W_OUT) { kind = 2; m = slot - W_SKIPP; }
-  else if (slot < W_LAYER0) { kind = 3; m = slot - W_OUT; }
+  else if (slot < W_SKIPPB) { kind = 2; m = slot - W_SKIPP; }
+  else if (slot == W_SKIPPB) { kind = 11; }
+  else if (slot < W_OUTB) { kind = 3; m = slot - W_OUT; }
+  else if (slot == W_OUTB) { kind = 12; }
   else {
     const int l = (slot - W_LAYER0) / W_PER_LAYER, rr = (slot - W_LAYER0) % W_PER_LAYER;
     fl = flat + f.layer0 + (size_t)l * f.layer_stride;
@@ -1110,7 +1122,7 @@ __global__ void pack_images_kernel(const float* __restrict__ flat, const FlatOff
     else if (rr < WL_SKIPB) { kind = (l + 1 < L) ? 6 : 8; m = rr - WL_RG; }
     else { kind = 7; m = 1 + rr - WL_SKIPB; }
   }
-  const bool n128 = (kind == 3 || kind == 4 || kind == 9);
+  const bool n128 = (kind == 3 || kind == 4 || kind == 9 || kind == 12);
   const int rows = n128 ? 64 : 128;
   const float gate_scale = rank == 0 ? 0.5f : 1.0f;      // rank 0 holds the gate half of every conv chunk
   for (int unit = threadIdx.x; unit < 1024; unit += blockDim.x) {
@@ -1148,6 +1160,14 @@ __global__ void pack_images_kernel(const float* __restrict__ flat, const FlatOff
           }
           break;
         }
+        case 10: case 11: case 12: {   // K = 16 against the "ones" operand: k=0 bf16(b), k=1 the bf16 remainder
+          if (k < 2) {
+            const float bv = kind == 10 ? b_in[128 * rank + row] : kind == 11 ? b_skipp[128 * rank + row] : b_out[64 * rank + row];
+            const float hi = __bfloat162float(__float2bfloat16_rn(bv));
+            x = k == 0 ? hi : bv - hi;
+          }
+          break;
+        }
         default: break;
       }
       v[e] = x;
@@ -1161,6 +1181,7 @@ __global__ void pack_images_kernel(const float* __restrict__ flat, const FlatOff
 __global__ void pack_small_kernel(const float* __restrict__ flat, const FlatOffsets f, const int L, const int n_mel,
                                   float* __restrict__ bo_x, float* __restrict__ bsum,
                                   float* __restrict__ b_in, float* __restrict__ b_skip, float* __restrict__ b_out) {
+  __shared__ float sb[C];
   const int c = threadIdx.x;   // 256 threads
   float s = 0.f;
   for (int l = 0; l < L; ++l) {
@@ -1169,13 +1190,19 @@ __global__ void pack_small_kernel(const float* __restrict__ flat, const FlatOffs
     s += fl[f.rel.oproj_b + C + c];
   }
   bsum[c] = s;
+  sb[c] = s;
+  __syncthreads();
   b_in[c] = flat[f.in_b + c];
-  b_skip[c] = flat[f.skip_b + c];
+  // The blocks' skip biases pass through the skip projection as a constant: fold W_skip (sum_l bo_s,l) / sqrt(L) into
+  // its bias, in fp32 (modules.py:441-442).
+  float acc = 0.f;
+  for (int k = 0; k < C; ++k) acc = fmaf(flat[f.skip_w + (size_t)c * C + k], sb[k], acc);
+  b_skip[c] = flat[f.skip_b + c] + acc / sqrtf((float)L);
   if (c < 128) b_out[c] = c < n_mel ? flat[f.out_b + c] : 0.f;
 }
 
 struct WorkBf16 {
-  size_t status, condT, tsteps, d, h, dtab, ctab, ktab, k00, kimg, U, U2, S, total;
+  size_t status, condT, tsteps, d, h, dtab, ctab, ktab, k00, kimg, k00img, U, U2, S, total;
   int Tg, R, Rp;
 };
 WorkBf16 work_layout(const mgb_model_dims& d, int B, int T, int K) {
@@ -1196,6 +1223,7 @@ WorkBf16 work_layout(const mgb_model_dims& d, int B, int T, int K) {
   w.ktab = take((size_t)K * B * d.layers * C * 4);
   w.k00 = take((size_t)K * B * C * 4);
   w.kimg = take((size_t)K * d.layers * 2 * KIMG_BYTES);
+  w.k00img = take((size_t)K * 2 * KIMG_BYTES);
   w.U = take((size_t)B * T * C * 2);
   w.U2 = take((size_t)B * T * C * 2);
   w.S = take((size_t)B * T * C * 2);
@@ -1255,7 +1283,8 @@ int bf16_pack(const mgb_model_dims& d, const float* flat, void* packed, cudaStre
   pack_small_kernel<<<1, 256, 0, s>>>(flat, f, L, d.n_mel, P + o.bo_x, P + o.bsum_skip, P + o.b_in,
                                       P + o.b_skip, P + o.b_out);
   __nv_bfloat16* img = reinterpret_cast<__nv_bfloat16*>(P + o.total);
-  pack_images_kernel<<<dim3(num_wslots(d), 2), 256, 0, s>>>(flat, f, L, d.n_mel, num_wslots(d), img);
+  pack_images_kernel<<<dim3(num_wslots(d), 2), 256, 0, s>>>(flat, f, L, d.n_mel, num_wslots(d), P + o.b_in, P + o.b_skip,
+                                                            P + o.b_out, img);
   MGB_LAUNCH_CHECK();
   return MGB_OK;
 }
@@ -1300,7 +1329,8 @@ int bf16_prepare(const mgb_model_dims& d, const void* packed, const int64_t* t, 
                                                                reinterpret_cast<float*>(W + w.k00), L, B, uniform ? 1 : 0);
   note_launch(5);   // step MLP (2), two projection tables, ktab
   if (uniform && !d.multi_speaker) {   // k_l is the same for every utterance: hand it to the residual GEMM (KUNI kernels)
-    kimg_kernel<<<dim3(L, nsteps, 2), 128, 0, s>>>(reinterpret_cast<const float*>(W + w.ktab), W + w.kimg, L, B);
+    kimg_kernel<<<dim3(L + 1, nsteps, 2), 128, 0, s>>>(reinterpret_cast<const float*>(W + w.ktab),
+                                                       reinterpret_cast<const float*>(W + w.k00), W + w.kimg, W + w.k00img, L, B);
     note_launch();
   }
   MGB_LAUNCH_CHECK();
@@ -1337,8 +1367,7 @@ int bf16_run(const mgb_model_dims& d, const void* packed, const float* x, const 
   p.k00 = reinterpret_cast<const float*>(W + w.k00) + (size_t)step * B * C;
   const bool kuni = t_uniform >= 0 && !d.multi_speaker;   // bf16_prepare built kimg for exactly this case
   p.kimg = W + w.kimg + (size_t)step * L * 2 * KIMG_BYTES;
-  p.bsum_skip = P + o.bsum_skip;
-  p.b_in = P + o.b_in; p.b_skip = P + o.b_skip; p.b_out = P + o.b_out;
+  p.k00img = W + w.k00img + (size_t)step * 2 * KIMG_BYTES;
   __half* Ubuf[2] = {reinterpret_cast<__half*>(W + w.U), reinterpret_cast<__half*>(W + w.U2)};
   p.S = reinterpret_cast<__half*>(W + w.S);
   p.B = B; p.T = T; p.Tg = w.Tg; p.R = w.R; p.L = L; p.status = reinterpret_cast<int*>(W + w.status);
@@ -1401,12 +1430,13 @@ int bf16_run(const mgb_model_dims& d, const void* packed, const float* x, const 
         fprintf(stderr, "\n");
       }
       {
-        double st[16] = {0};
-        for (int i = 0; i < ncta; i += 2) for (int k = 0; k < 16; ++k) st[k] += (double)h[i * 320 + 256 + k] / npairs;
+        double st[24] = {0};
+        for (int i = 0; i < ncta; i += 2) for (int k = 0; k < 24; ++k) st[k] += (double)h[i * 320 + 256 + k] / npairs;
         fprintf(stderr, "[mgb tile] cycles since kernel start (leader CTA means): setup done %.0f | MMA: x_t seen %.0f, relu drained %.0f, cond0 issued %.0f, "
                 "first conv slot issued %.0f, last layer issued %.0f | epilogue w4: x_t published %.0f, relu done %.0f, cond0 seen %.0f, u published %.0f, "
-                "last layer done %.0f, skip complete %.0f, end %.0f\n", st[0], st[1], st[2], st[3], st[4], st[5], st[8], st[9], st[10], st[11],
-                st[12], st[13], st[14]);
+                "last layer done %.0f, skip complete %.0f, end %.0f | tail: skip sum published %.0f, MMA skip-proj issued %.0f, relu published %.0f, "
+                "MMA out-proj issued %.0f, out-proj seen %.0f\n", st[0], st[1], st[2], st[3], st[4], st[5], st[8], st[9], st[10], st[11],
+                st[12], st[13], st[14], st[16], st[6], st[17], st[7], st[18]);
       }
       {
         // distribution of "setup done" and "end" over leader CTAs in launch order

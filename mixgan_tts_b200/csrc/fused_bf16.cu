@@ -158,6 +158,34 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_p
   const int g0 = pair * p.V - p.halo + 128 * (int)rank;   // row (on the batch row axis) of this CTA's tile row 0
   const bool first_group = p.lb == 0, last_group = p.le == p.L;
 
+  // ---- first global reads of the epilogue threads, issued BEFORE the setup so that their DRAM latency overlaps it:
+  // the x_t tile (first group: 40 mel bins of this thread's frame) or the spilled residual stream (later groups)
+  uint32_t pf[64];
+  if (warp >= 4) {
+    const int e_h = (warp - 4) >> 2, e_r = ((warp - 4) & 3) * 32 + lane;
+    const int e_g = g0 + e_r;
+    const int e_b = (e_g >= 0 && e_g < p.R) ? e_g / p.Tg : 0;
+    const int e_f = e_g - e_b * p.Tg;
+    const bool e_in = e_g >= 0 && e_g < p.R && e_f < p.T;
+    if (first_group) {
+      const float* src = p.x_t + ((size_t)e_b * p.n_mel + 40 * e_h) * p.T + e_f;
+#pragma unroll
+      for (int j = 0; j < 40; ++j)
+        pf[j] = (e_in && 40 * e_h + j < p.n_mel) ? __float_as_uint(__ldg(src + (size_t)j * p.T)) : 0u;
+    } else {
+      const size_t e_row = (size_t)e_b * p.T + (e_in ? e_f : 0);
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const uint4* up = reinterpret_cast<const uint4*>(p.U_in + e_row * C + 128 * c + 64 * e_h);
+#pragma unroll
+        for (int j8 = 0; j8 < 8; ++j8) {
+          const uint4 v = e_in ? __ldg(up + j8) : make_uint4(0u, 0u, 0u, 0u);
+          pf[32 * c + 4 * j8 + 0] = v.x; pf[32 * c + 4 * j8 + 1] = v.y; pf[32 * c + 4 * j8 + 2] = v.z; pf[32 * c + 4 * j8 + 3] = v.w;
+        }
+      }
+    }
+  }
+
   // ---- setup -------------------------------------------------------------------------------
   {  // zero the operand tiles (outer halo rows of A stay zero for the whole kernel)
     uint4* z = reinterpret_cast<uint4*>(smem);
@@ -675,19 +703,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_p
 
     // ---- group start: produce u_lb ----
     if (first_group) {
-      // x_t tile -> bf16 A operand (channels 0..79): this thread converts bins [40h, 40h+40); all 40 loads are issued
-      // before the first store so that one DRAM latency is exposed, not five
-      {
-        float xv[40];
-        const size_t o0 = ((size_t)b * p.n_mel + 40 * h) * p.T + f;
+      // x_t tile -> bf16 A operand (channels 0..79): this thread converts bins [40h, 40h+40) (fetched before the setup)
 #pragma unroll
-        for (int j = 0; j < 40; ++j)
-          xv[j] = (in_seq && 40 * h + j < p.n_mel) ? __ldg(p.x_t + o0 + (size_t)j * p.T) : 0.f;
-#pragma unroll
-        for (int jj = 0; jj < 5; ++jj)
-          st_shared_v4(aA + (uint32_t)(5 * h + jj) * A_LBO + (uint32_t)(r + 1) * 16, pack_bf16(xv[8 * jj], xv[8 * jj + 1]),
-                       pack_bf16(xv[8 * jj + 2], xv[8 * jj + 3]), pack_bf16(xv[8 * jj + 4], xv[8 * jj + 5]),
-                       pack_bf16(xv[8 * jj + 6], xv[8 * jj + 7]));
+      for (int jj = 0; jj < 5; ++jj) {
+        const uint32_t* xv = &pf[8 * jj];
+        st_shared_v4(aA + (uint32_t)(5 * h + jj) * A_LBO + (uint32_t)(r + 1) * 16,
+                     pack_bf16(__uint_as_float(xv[0]), __uint_as_float(xv[1])), pack_bf16(__uint_as_float(xv[2]), __uint_as_float(xv[3])),
+                     pack_bf16(__uint_as_float(xv[4]), __uint_as_float(xv[5])), pack_bf16(__uint_as_float(xv[6]), __uint_as_float(xv[7])));
       }
       publish_a(-1);
       MGB_STAMP(warp == 4 && lane == 0, 8);             // x_t published
@@ -734,24 +756,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_p
       }
       publish_a(-1);
     } else {
-      // reload u_lb spilled by the previous group (fp16; all 16 loads in flight before the first use)
-      {
-        uint4 raw[16];
+      // u_lb spilled by the previous group (fp16, fetched before the setup)
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          const uint4* up = reinterpret_cast<const uint4*>(p.U_in + row_g * C + 128 * c + 64 * h);
-#pragma unroll
-          for (int j8 = 0; j8 < 8; ++j8) raw[8 * c + j8] = in_seq ? __ldg(up + j8) : make_uint4(0u, 0u, 0u, 0u);
-        }
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const uint32_t w4[4] = {raw[i].x, raw[i].y, raw[i].z, raw[i].w};
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float2 f2 = unpack_f16(w4[e]);
-            u[8 * i + 2 * e] = f2.x; u[8 * i + 2 * e + 1] = f2.y;
-          }
-        }
+      for (int i = 0; i < 64; ++i) {
+        const float2 f2 = unpack_f16(pf[i]);
+        u[2 * i] = f2.x; u[2 * i + 1] = f2.y;
       }
       write_A(0, &u[0]);
       write_A(1, &u[64]);

@@ -39,6 +39,19 @@ CPU_SAMPLE_B = 16                          # BASELINE configs[0] shape for the C
 METRIC, UNIT = "mel_frames_per_sec", "frames/s"
 
 
+def ncu_traffic(B, T):
+    """dram bytes per launch of the dominant kernel from the committed ncu --set full capture (same workload), or None."""
+    import glob
+    if (B, T) != (B_PER_GPU, T_FRAMES):
+        return None
+    for p in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*", "ncu_traffic.json")), reverse=True):
+        try:
+            return float(json.load(open(p))["mean_bytes_per_launch"])
+        except Exception:
+            continue
+    return None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -272,7 +285,7 @@ def run_ours(args):
             # one Denoiser call = `launches_per_call` launches of fused_group_kernel (layer groups);
             # algorithmic FLOPs per launch = FLOPs per call / launches per call
             per_call = max(kcnt.value // calls, 1)
-            kern = f"fused_group_kernel (tcgen05; {per_call} launches = one Denoiser call over the batch)"
+            kern = f"fused_pair_kernel (tcgen05 cta_group::2; {per_call} launches = one Denoiser call over the batch)"
             fl = FLOPS_PER_FRAME_STEP / per_call
         else:
             kern, fl = "conv_gemm_kernel<EPI_GATE> (k=3 conv + gate of one block, fp32 CUDA cores)", CONV_FLOPS_PER_FRAME_STEP
@@ -288,7 +301,8 @@ def run_ours(args):
                        "frames_valid_per_s": value * valid / (B * T), "frame_steps_per_s": value * K,
                        "rtf_valid_audio": (ms_total / args.steps * 1e-3) / (world * valid * 256 / 22050)},
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": pk["tensor_tflops"], "unit": "TFLOP/s",
-                         "frac": achieved / pk["tensor_tflops"], "traffic": None, "kernel": kern,
+                         "frac": achieved / pk["tensor_tflops"],
+                         "traffic": ncu_traffic(B, T) if prec == "bf16" else None, "kernel": kern,
                          "kernel_ms": k_ms, "kernel_launches_timed": kcnt.value,
                          "kernel_share_of_step": ktot.value / ms_prof_pass if ms_prof_pass > 0 else None,
                          "whole_step_tflops": FLOPS_PER_FRAME_STEP * K * B * T * args.steps / (ms_total * 1e-3) / 1e12,

@@ -27,6 +27,12 @@ with open(os.path.join(out, "ncu_fused_pair_kernel_summary.txt"), "w") as f:
     for i, h in enumerate(hdr):
         if h in want:
             f.write(f"{h} [{rows[1][i]}] = {' | '.join(r[i] for r in rows[2:])}\n")
+    ir, iw = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+    unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    per = [float(r[ir]) * unit[rows[1][ir]] + float(r[iw]) * unit[rows[1][iw]] for r in rows[2:]]
+    json.dump({"kernel": "fused_pair_kernel", "dram_bytes_per_launch": per, "mean_bytes_per_launch": sum(per) / len(per),
+               "source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, cold caches (workload B=64 x T=800)"},
+              open(os.path.join(out, "ncu_traffic.json"), "w"), indent=1)
     src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
     srows = list(csv.reader(src.splitlines()))
     sh = srows[1]
@@ -73,7 +79,7 @@ for r in rows[start:]:
 T = sum(v[0] for v in tot.values())
 shutil.copy(ll, os.path.join(out, "launches_bf16_pair.csv"))
 with open(os.path.join(out, "launches_bf16_pair_summary.txt"), "w") as f:
-    f.write("ncu --metrics gpu__time_duration.sum --clock-control none -s 58 -c 40  python bench.py --steps 2 --warmup 3\n"
+    f.write("ncu --metrics gpu__time_duration.sum --clock-control none -c 400  python bench.py --steps 2 --warmup 3\n"
             "(cold-cache, serialised launches: compare SHARES, not absolutes)\n\n")
     for n, v in tot.items():
         f.write(f"{v[0] / 1e3:10.1f} us {v[1]:3d}x {100 * v[0] / T:5.1f}%  {n}\n")

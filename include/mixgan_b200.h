@@ -15,6 +15,8 @@
  *                                                                model/diffusion.py:155-165,200
  *   mgb_shallow_start      GaussianDiffusion.diffuse_fn * mask   model/diffusion.py:177-185,198-199
  *   mgb_denorm_mask        GaussianDiffusion.denorm_spec * mask  model/diffusion.py:231-232,164,200
+ *   mgb_denoiser_train_forward / mgb_denoiser_backward
+ *                          autograd through Denoiser.forward     model/modules.py:420-446 (train.py:126-184)
  *   mgb_length_regulate    LengthRegulator.LR / expand / pad     model/linguistic_encoder.py:383-416,
  *                          get_mask_from_lengths                 utils/tools.py:144-153,374-392
  *
@@ -155,6 +157,37 @@ int mgb_denorm_mask(const float* x, const float* spec_min, const float* spec_max
 int mgb_length_regulate(const float* x, const int64_t* dur, float* out, int64_t* mel_len,
                         int B, int S, int D, int max_len, void* workspace, size_t workspace_bytes,
                         void* stream);
+
+/*
+ * Training (BASELINE configs[4]): Denoiser forward that keeps the activations its backward needs, and the
+ * backward itself.  Replaces torch autograd through Denoiser.forward (model/modules.py:420-446,
+ * model/blocks.py:1157-1176) as train.py:126-184 drives it.  MGB_PREC_FP32 only in this build.
+ *   packed      : mgb_pack_weights(MGB_PREC_FP32) image of the CURRENT parameters
+ *   flat        : the same parameters in the canonical flat order (mgb_pack_weights' input)
+ *   saved       : caller-owned activation stash, mgb_train_saved_bytes(dims, B, T) bytes, written by the forward
+ *   workspace   : mgb_train_workspace_bytes(dims, B, T) bytes, shared by forward and backward
+ *   grad_out    : d loss / d out, [B][n_mel][T]
+ *   grad_flat   : d loss / d parameters in the canonical flat order (WRITTEN, not accumulated)
+ *   grad_cond   : [B][T][d_encoder] or NULL;  grad_spk: [B][d_encoder] or NULL;  grad_x: [B][n_mel][T] or NULL
+ * The backward is a sequence of mgb_train_segments(dims) = layers + 2 segments: 0 = output/skip projections,
+ * 1..layers = residual blocks from the last to the first, layers + 1 = input projection + step MLP.  A call runs
+ * segments [seg_begin, seg_end) and must be issued in order on one stream; after segment s the slice
+ * [flat_begin, flat_end) that mgb_train_segment_range reports is final, so the host can start the NCCL
+ * all-reduce of that gradient bucket while later segments run (grad_cond/grad_spk/grad_x are final after the last).
+ */
+size_t mgb_train_saved_bytes(const mgb_model_dims* dims, int B, int T);
+size_t mgb_train_workspace_bytes(const mgb_model_dims* dims, int B, int T);
+int mgb_train_segments(const mgb_model_dims* dims);
+int mgb_train_segment_range(const mgb_model_dims* dims, int seg, size_t* flat_begin, size_t* flat_end);
+int mgb_denoiser_train_forward(const mgb_model_dims* dims, int precision, const void* packed, const float* x,
+                               const int64_t* t, const float* cond, const float* spk, float* out,
+                               void* saved, size_t saved_bytes, int B, int T,
+                               void* workspace, size_t workspace_bytes, void* stream);
+int mgb_denoiser_backward(const mgb_model_dims* dims, int precision, const float* flat, const void* saved,
+                          size_t saved_bytes, const int64_t* t, const float* cond, const float* spk,
+                          const float* grad_out, float* grad_flat, float* grad_cond, float* grad_spk,
+                          float* grad_x, int B, int T, int seg_begin, int seg_end,
+                          void* workspace, size_t workspace_bytes, void* stream);
 
 /*
  * tcgen05 descriptor probe (used by tests/test_umma_probe.py to pin the shared-memory

@@ -349,6 +349,64 @@ int mgb_sample(const mgb_model_dims* dims, int precision, const void* packed, co
   return MGB_OK;
 }
 
+size_t mgb_train_saved_bytes(const mgb_model_dims* dims, int B, int T) {
+  if (!dims_supported(dims) || B <= 0 || T <= 0) return 0;
+  return train_saved_layout(*dims, B, T).total * sizeof(float);
+}
+
+size_t mgb_train_workspace_bytes(const mgb_model_dims* dims, int B, int T) {
+  if (!dims_supported(dims) || B <= 0 || T <= 0) return 0;
+  return train_workspace_bytes(*dims, B, T);
+}
+
+int mgb_train_segments(const mgb_model_dims* dims) { return dims_supported(dims) ? dims->layers + 2 : 0; }
+
+int mgb_train_segment_range(const mgb_model_dims* dims, int seg, size_t* flat_begin, size_t* flat_end) {
+  MGB_REQUIRE(dims_supported(dims) && flat_begin && flat_end, MGB_E_ARG, "bad argument");
+  const FlatOffsets f = flat_offsets(*dims);
+  const int L = dims->layers;
+  MGB_REQUIRE(seg >= 0 && seg <= L + 1, MGB_E_ARG, "segment %d out of range [0, %d]", seg, L + 1);
+  if (seg == 0) { *flat_begin = f.skip_w; *flat_end = f.total; }
+  else if (seg <= L) { *flat_begin = f.layer0 + (size_t)(L - seg) * f.layer_stride; *flat_end = *flat_begin + f.layer_stride; }
+  else { *flat_begin = 0; *flat_end = f.layer0; }
+  return MGB_OK;
+}
+
+int mgb_denoiser_train_forward(const mgb_model_dims* dims, int precision, const void* packed, const float* x,
+                               const int64_t* t, const float* cond, const float* spk, float* out, void* saved,
+                               size_t saved_bytes, int B, int T, void* workspace, size_t workspace_bytes, void* stream) {
+  MGB_REQUIRE(dims_supported(dims), MGB_E_ARG, "unsupported model dims");
+  MGB_REQUIRE(packed && x && t && cond && out && saved && workspace, MGB_E_ARG, "NULL pointer argument");
+  MGB_REQUIRE(B > 0 && T > 0, MGB_E_ARG, "B and T must be positive (got %d, %d)", B, T);
+  MGB_REQUIRE(!dims->multi_speaker || spk, MGB_E_ARG, "multi_speaker model needs a speaker embedding");
+  MGB_REQUIRE(precision == MGB_PREC_FP32, MGB_E_UNSUPPORTED, "the training path computes in fp32 only in this build");
+  if (int rc = check_arch()) return rc;
+  MGB_REQUIRE(saved_bytes >= mgb_train_saved_bytes(dims, B, T), MGB_E_WORKSPACE, "activation stash too small: %zu < %zu",
+              saved_bytes, mgb_train_saved_bytes(dims, B, T));
+  MGB_REQUIRE(workspace_bytes >= mgb_train_workspace_bytes(dims, B, T), MGB_E_WORKSPACE, "workspace too small: %zu < %zu",
+              workspace_bytes, mgb_train_workspace_bytes(dims, B, T));
+  return fp32_train_forward(*dims, packed, x, t, cond, spk, out, static_cast<float*>(saved), B, T, workspace,
+                            static_cast<cudaStream_t>(stream));
+}
+
+int mgb_denoiser_backward(const mgb_model_dims* dims, int precision, const float* flat, const void* saved,
+                          size_t saved_bytes, const int64_t* t, const float* cond, const float* spk,
+                          const float* grad_out, float* grad_flat, float* grad_cond, float* grad_spk, float* grad_x,
+                          int B, int T, int seg_begin, int seg_end, void* workspace, size_t workspace_bytes, void* stream) {
+  MGB_REQUIRE(dims_supported(dims), MGB_E_ARG, "unsupported model dims");
+  MGB_REQUIRE(flat && saved && t && cond && grad_out && grad_flat && workspace, MGB_E_ARG, "NULL pointer argument");
+  MGB_REQUIRE(B > 0 && T > 0, MGB_E_ARG, "B and T must be positive (got %d, %d)", B, T);
+  MGB_REQUIRE(!dims->multi_speaker || spk, MGB_E_ARG, "multi_speaker model needs a speaker embedding");
+  MGB_REQUIRE(precision == MGB_PREC_FP32, MGB_E_UNSUPPORTED, "the training path computes in fp32 only in this build");
+  MGB_REQUIRE(seg_begin >= 0 && seg_begin <= seg_end && seg_end <= dims->layers + 2, MGB_E_ARG,
+              "bad segment range [%d, %d)", seg_begin, seg_end);
+  if (int rc = check_arch()) return rc;
+  MGB_REQUIRE(saved_bytes >= mgb_train_saved_bytes(dims, B, T), MGB_E_WORKSPACE, "activation stash too small");
+  MGB_REQUIRE(workspace_bytes >= mgb_train_workspace_bytes(dims, B, T), MGB_E_WORKSPACE, "workspace too small");
+  return fp32_train_backward(*dims, flat, static_cast<const float*>(saved), t, cond, spk, grad_out, grad_flat, grad_cond,
+                             grad_spk, grad_x, B, T, seg_begin, seg_end, workspace, static_cast<cudaStream_t>(stream));
+}
+
 int mgb_shallow_start(const float* coarse, const float* noise, const float* spec_min, const float* spec_max,
                       float sqrt_acp, float sqrt_1m_acp, const uint8_t* pad_mask, float* x_T, int B, int T,
                       int n_mel, void* stream) {

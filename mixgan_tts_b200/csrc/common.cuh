@@ -106,7 +106,54 @@ size_t fp32_workspace_bytes(const mgb_model_dims& d, int B, int T);
 // receives the (optionally clamped) x0 when non-null.
 int fp32_denoiser(const mgb_model_dims& d, const void* packed, const float* x, const int64_t* t,
                   const float* cond, const float* spk, const float* noise, const float* sched, int K,
-                  int clip, float* x_prev, float* out_x0, int B, int T, void* ws, cudaStream_t s);
+                  int clip, float* x_prev, float* out_x0, int B, int T, void* ws, cudaStream_t s,
+                  float* saved = nullptr);
+
+// ---- fp32 training path (fp32_path.cu forward with stash, train_fp32.cu backward) -----------------
+// Activations the forward keeps for the backward, all fp32 frames-major (F = B*T rows); offsets in floats.
+struct TrainSaved {
+  size_t xt;            // [F][n_mel]  input, frames-major
+  size_t X0;            // [F][C]      relu(input projection)
+  size_t layer0, layer_stride;
+  size_t rY, rZ, rG;    // per layer: conv input [F][C], conv pre-activation [F][2C] (gate | filter), gate output [F][C]
+  size_t Sn;            // [F][C]      skip sum / sqrt(L)
+  size_t P;             // [F][C]      relu(skip projection)
+  size_t dvec;          // [B][C]      step MLP output
+  size_t h;             // [B][4C]     mish(W0 emb)
+  size_t total;
+};
+inline TrainSaved train_saved_layout(const mgb_model_dims& d, int B, int T) {
+  const size_t C = d.channels, F = (size_t)B * T;
+  TrainSaved o{};
+  size_t p = 0;
+  auto take = [&](size_t n) { size_t r = p; p += align_up(n, 64); return r; };
+  o.xt = take(F * d.n_mel);
+  o.X0 = take(F * C);
+  o.layer0 = p;
+  {
+    size_t q = 0;
+    auto tk = [&](size_t n) { size_t r = q; q += align_up(n, 64); return r; };
+    o.rY = tk(F * C); o.rZ = tk(F * 2 * C); o.rG = tk(F * C);
+    o.layer_stride = q;
+  }
+  p += o.layer_stride * d.layers;
+  o.Sn = take(F * C);
+  o.P = take(F * C);
+  o.dvec = take((size_t)B * C);
+  o.h = take((size_t)B * 4 * C);
+  o.total = p;
+  return o;
+}
+size_t train_workspace_bytes(const mgb_model_dims& d, int B, int T);
+// Denoiser.forward keeping the activations the backward needs (`saved`, TrainSaved layout); out = [B][n_mel][T].
+int fp32_train_forward(const mgb_model_dims& d, const void* packed, const float* x, const int64_t* t, const float* cond,
+                       const float* spk, float* out, float* saved, int B, int T, void* ws, cudaStream_t s);
+// Backward segments in execution order: 0 = tail (output/skip projections), 1..L = residual layers L-1..0,
+// L+1 = head (input projection, step MLP).  Runs segments [seg_begin, seg_end).  Gradients are WRITTEN (not accumulated)
+// into grad_flat (canonical flat order) / grad_cond [B][T][H] / grad_spk [B][H] / grad_x [B][n_mel][T] (each optional).
+int fp32_train_backward(const mgb_model_dims& d, const float* flat, const float* saved, const int64_t* t,
+                        const float* cond, const float* spk, const float* grad_out, float* grad_flat, float* grad_cond,
+                        float* grad_spk, float* grad_x, int B, int T, int seg_begin, int seg_end, void* ws, cudaStream_t s);
 
 // ---- bf16 tcgen05 path (fused_bf16.cu) -------------------------------------------------------
 size_t bf16_packed_bytes(const mgb_model_dims& d);

@@ -9,6 +9,7 @@
 // Activation layout in HBM: frames-major [B*T][C] fp32 (one row per mel frame), so a k=3
 // convolution is three row-shifted GEMMs over the same matrix with zero rows at utterance edges.
 #include "common.cuh"
+#include "gemm_fp32.cuh"
 #include "small_ops.cuh"
 
 namespace mgb {
@@ -17,7 +18,7 @@ namespace {
 
 using namespace smallops;
 
-constexpr int BM = 128, BN = 128, BK = 8, NT = 256, BMP = BM + 4;
+using gemm32::BK; using gemm32::BM; using gemm32::BMP; using gemm32::BN; using gemm32::NT;
 
 enum Epi { EPI_RELU = 0, EPI_COND = 1, EPI_GATE = 2, EPI_OUT = 3, EPI_FINAL = 4 };
 
@@ -29,7 +30,8 @@ struct GemmArgs {
   // epilogue operands
   float* out;          // RELU/COND/GATE: [rows][C]; OUT: X in/out; FINAL: x_prev or x0 [B][M][T]
   float* out2;         // OUT: skip accumulator; FINAL: optional x0 copy
-  const float* x;      // COND: X [rows][C]
+  const float* x;      // COND: X [rows][C]; OUT: residual-stream input when it is not `out` (training: X0 is kept)
+  float* zsave;        // GATE: optional [rows][2C] copy of the pre-activation (gate | filter halves), for the backward
   const float* dtab;   // COND/OUT: per-utterance step bias for this layer, row stride tab_stride
   const float* ctab;   // COND: per-utterance conditioner-side bias (bc + speaker), same stride
   int tab_stride;
@@ -50,68 +52,10 @@ __global__ void __launch_bounds__(NT) conv_gemm_kernel(const GemmArgs p) {
 
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
-
-  // global->smem assignments
-  const int a_row = tid >> 1, a_kq = (tid & 1) * 4;
-  const int a_m = m0 + a_row;
-  const int a_t = a_m % p.T;
-  const bool a_in = a_m < p.rows;
-  const int b_k = tid >> 5, b_n = (tid & 31) * 4;
-
   float acc[8][8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
-
-  const int Ktot = p.taps * p.Kin;
-  const int nk = Ktot / BK;
-  const int half = p.taps >> 1;
-
-  float4 ra, rb;
-  auto gload = [&](int kt) {
-    const int kk = kt * BK;
-    const int tap = kk / p.Kin;
-    const int k0 = kk - tap * p.Kin;
-    const int sh = tap - half;
-    const int ts = a_t + sh;
-    if (a_in && ts >= 0 && ts < p.T)
-      ra = *reinterpret_cast<const float4*>(p.A + (size_t)(a_m + sh) * p.lda + k0 + a_kq);
-    else
-      ra = make_float4(0.f, 0.f, 0.f, 0.f);
-    rb = *reinterpret_cast<const float4*>(p.Wt + (size_t)(kk + b_k) * p.ldw + n0 + b_n);
-  };
-  auto sstore = [&](int buf) {
-    As[buf][a_kq + 0][a_row] = ra.x;
-    As[buf][a_kq + 1][a_row] = ra.y;
-    As[buf][a_kq + 2][a_row] = ra.z;
-    As[buf][a_kq + 3][a_row] = ra.w;
-    *reinterpret_cast<float4*>(&Bs[buf][b_k][b_n]) = rb;
-  };
-
-  gload(0);
-  sstore(0);
-  __syncthreads();
-  for (int kt = 0; kt < nk; ++kt) {
-    const int cur = kt & 1;
-    if (kt + 1 < nk) gload(kt + 1);
-#pragma unroll
-    for (int k = 0; k < BK; ++k) {
-      const float4 a0 = *reinterpret_cast<const float4*>(&As[cur][k][ty * 4]);
-      const float4 a1 = *reinterpret_cast<const float4*>(&As[cur][k][64 + ty * 4]);
-      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[cur][k][tx * 4]);
-      const float4 b1 = *reinterpret_cast<const float4*>(&Bs[cur][k][64 + tx * 4]);
-      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-      const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
-    }
-    if (kt + 1 < nk) {
-      sstore(cur ^ 1);
-      __syncthreads();
-    }
+  {
+    gemm32::FrameGemm g{p.A, nullptr, p.Wt, p.lda, 0, 0, p.ldw, p.rows, p.T, p.Kin, p.taps};
+    gemm32::frame_gemm_mainloop(g, m0, n0, acc, As, Bs);
   }
 
   // ---------------------------------------------------------------- epilogues
@@ -158,10 +102,14 @@ __global__ void __launch_bounds__(NT) conv_gemm_kernel(const GemmArgs p) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) g[j] = sigmoidf_(lo[j]) * tanhf(hi[j]);
         *reinterpret_cast<float4*>(p.out + (size_t)m * C + ch) = make_float4(g[0], g[1], g[2], g[3]);
+        if (p.zsave) {
+          *reinterpret_cast<float4*>(p.zsave + (size_t)m * 2 * C + ch) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+          *reinterpret_cast<float4*>(p.zsave + (size_t)m * 2 * C + C + ch) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+        }
       } else {
         float4* xp = reinterpret_cast<float4*>(p.out + (size_t)m * C + ch);
         float4* sp = reinterpret_cast<float4*>(p.out2 + (size_t)m * C + ch);
-        const float4 xv = *xp;
+        const float4 xv = p.x ? *reinterpret_cast<const float4*>(p.x + (size_t)m * C + ch) : *xp;
         const float4 dv = *reinterpret_cast<const float4*>(p.dtab + (size_t)b * p.tab_stride + ch);
         const float SQRT2 = 1.41421356237309504880f;
         float4 xn;
@@ -318,63 +266,81 @@ int fp32_pack(const mgb_model_dims& d, const float* flat, void* packed, cudaStre
 
 int fp32_denoiser(const mgb_model_dims& d, const void* packed, const float* x, const int64_t* t,
                   const float* cond, const float* spk, const float* noise, const float* sched, int K,
-                  int clip, float* x_prev, float* out_x0, int B, int T, void* ws, cudaStream_t s) {
+                  int clip, float* x_prev, float* out_x0, int B, int T, void* ws, cudaStream_t s, float* saved) {
   const PackedF32 o = packed_layout(d);
   const WorkF32 w = work_layout(d, B, T);
   const float* P = static_cast<const float*>(packed);
   float* W = static_cast<float*>(ws);
   const int C = d.channels, H = d.d_encoder, M = d.n_mel, L = d.layers;
   const int rows = B * T;
+  // training: activations go straight into the caller's stash instead of the reused scratch buffers
+  const TrainSaved sv = train_saved_layout(d, B, T);
+  float* const xt_buf = saved ? saved + sv.xt : W + w.xt;
+  float* const x0_buf = saved ? saved + sv.X0 : W + w.X;
+  float* const s_buf = saved ? saved + sv.Sn : W + w.S;
+  float* const p_buf = saved ? saved + sv.P : W + w.Y;
+  float* const d_buf = saved ? saved + sv.dvec : W + w.d;
+  float* const h_buf = saved ? saved + sv.h : W + w.h;
 
   // per-utterance step embedding, MLP and the per-layer projection tables
-  launch_step_mlp(t, P + o.mlp0_wt, P + o.mlp2_wt, W + w.h, W + w.d, B, C, s);
+  launch_step_mlp(t, P + o.mlp0_wt, P + o.mlp2_wt, h_buf, d_buf, B, C, s);
   {
     dim3 grid(L, (B + TAB_UB - 1) / TAB_UB);
     proj_table_kernel<<<grid, 256, (size_t)TAB_UB * C * sizeof(float), s>>>(
-        W + w.d, C, P + o.layer0 + o.r_dproj_wt, o.layer_stride, nullptr, 0, W + w.dtab, B, L, C);
+        d_buf, C, P + o.layer0 + o.r_dproj_wt, o.layer_stride, nullptr, 0, W + w.dtab, B, L, C);
     proj_table_kernel<<<grid, 256, (size_t)TAB_UB * H * sizeof(float), s>>>(
         d.multi_speaker ? spk : nullptr, H, P + o.layer0 + o.r_sproj_wt, o.layer_stride,
         P + o.layer0 + o.r_cproj_b, o.layer_stride, W + w.ctab, B, L, C);
   }
   {
     dim3 grid((T + 31) / 32, (M + 31) / 32, B), block(32, 8);
-    bmt_to_btm_kernel<<<grid, block, 0, s>>>(x, W + w.xt, M, T);
+    bmt_to_btm_kernel<<<grid, block, 0, s>>>(x, xt_buf, M, T);
     note_launch(5);   // step MLP (2), two projection tables, this transpose
   }
   GemmArgs a{};
   a.rows = rows; a.T = T; a.C = C; a.tab_stride = L * C;
   // input projection + ReLU (the second F.relu at modules.py:431 is idempotent)
-  a.A = W + w.xt; a.lda = M; a.Wt = P + o.in_wt; a.ldw = C; a.bias = P + o.in_b; a.Kin = M; a.taps = 1;
-  a.out = W + w.X;
+  a.A = xt_buf; a.lda = M; a.Wt = P + o.in_wt; a.ldw = C; a.bias = P + o.in_b; a.Kin = M; a.taps = 1;
+  a.out = x0_buf;
   launch_gemm<EPI_RELU>(a, C, s);
   for (int l = 0; l < L; ++l) {
     const float* pl = P + o.layer0 + (size_t)l * o.layer_stride;
+    float* const sl = saved ? saved + sv.layer0 + (size_t)l * sv.layer_stride : nullptr;
+    const float* x_in = l == 0 ? x0_buf : W + w.X;
+    float* const y_buf = sl ? sl + sv.rY : W + w.Y;
+    float* const g_buf = sl ? sl + sv.rG : W + w.G;
     GemmArgs c = a;
     c.A = cond; c.lda = H; c.Wt = pl + o.r_cproj_wt; c.ldw = C; c.Kin = H; c.taps = 1; c.bias = nullptr;
-    c.x = W + w.X; c.dtab = W + w.dtab + (size_t)l * C; c.ctab = W + w.ctab + (size_t)l * C;
-    c.out = W + w.Y;
+    c.x = x_in; c.dtab = W + w.dtab + (size_t)l * C; c.ctab = W + w.ctab + (size_t)l * C;
+    c.out = y_buf;
     launch_gemm<EPI_COND>(c, C, s);
     GemmArgs g = a;
-    g.A = W + w.Y; g.lda = C; g.Wt = pl + o.r_conv_wt; g.ldw = 2 * C; g.Kin = C; g.taps = 3;
-    g.bias = pl + o.r_conv_b; g.out = W + w.G;
+    g.A = y_buf; g.lda = C; g.Wt = pl + o.r_conv_wt; g.ldw = 2 * C; g.Kin = C; g.taps = 3;
+    g.bias = pl + o.r_conv_b; g.out = g_buf; g.zsave = sl ? sl + sv.rZ : nullptr;
     launch_gemm<EPI_GATE>(g, 2 * C, s);
     GemmArgs q = a;
-    q.A = W + w.G; q.lda = C; q.Wt = pl + o.r_oproj_wt; q.ldw = 2 * C; q.Kin = C; q.taps = 1;
-    q.bias = pl + o.r_oproj_b; q.out = W + w.X; q.out2 = W + w.S; q.dtab = W + w.dtab + (size_t)l * C;
+    q.A = g_buf; q.lda = C; q.Wt = pl + o.r_oproj_wt; q.ldw = 2 * C; q.Kin = C; q.taps = 1;
+    q.bias = pl + o.r_oproj_b; q.out = W + w.X; q.out2 = s_buf; q.dtab = W + w.dtab + (size_t)l * C;
+    q.x = (x_in == W + w.X) ? nullptr : x_in;   // layer 0 of a training forward reads X0 and leaves it intact
     q.first = (l == 0); q.last = (l == L - 1); q.inv_div = sqrtf((float)L);
     launch_gemm<EPI_OUT>(q, 2 * C, s);
   }
   GemmArgs k = a;
-  k.A = W + w.S; k.lda = C; k.Wt = P + o.skip_wt; k.ldw = C; k.Kin = C; k.taps = 1; k.bias = P + o.skip_b;
-  k.out = W + w.Y;
+  k.A = s_buf; k.lda = C; k.Wt = P + o.skip_wt; k.ldw = C; k.Kin = C; k.taps = 1; k.bias = P + o.skip_b;
+  k.out = p_buf;
   launch_gemm<EPI_RELU>(k, C, s);
   GemmArgs f = a;
-  f.A = W + w.Y; f.lda = C; f.Wt = P + o.out_wt; f.ldw = 128; f.Kin = C; f.taps = 1; f.bias = P + o.out_b;
+  f.A = p_buf; f.lda = C; f.Wt = P + o.out_wt; f.ldw = 128; f.Kin = C; f.taps = 1; f.bias = P + o.out_b;
   f.n_mel = M; f.clip = clip; f.K = K; f.t = t; f.sched = sched; f.x_t = x; f.noise = noise;
   f.out = sched ? x_prev : out_x0; f.out2 = sched ? out_x0 : nullptr;
   launch_gemm<EPI_FINAL>(f, 128, s);
   MGB_LAUNCH_CHECK();
   return MGB_OK;
+}
+
+int fp32_train_forward(const mgb_model_dims& d, const void* packed, const float* x, const int64_t* t, const float* cond,
+                       const float* spk, float* out, float* saved, int B, int T, void* ws, cudaStream_t s) {
+  return fp32_denoiser(d, packed, x, t, cond, spk, nullptr, nullptr, 0, 0, nullptr, out, B, T, ws, s, saved);
 }
 
 }  // namespace mgb

@@ -9,9 +9,8 @@ with ``torch.randn`` on the device, as the reference does.
 
 Hot methods (``p_sample``, ``sampling``, inference ``forward``) call the C ABI; the light
 training-time helpers (``q_sample``, ``q_posterior``, ``norm_spec`` ...) are plain torch on the
-registered buffers.  The training branch of ``forward`` (``mel`` given) computes the reference's
-forward VALUES (as ``evaluate.py`` uses them under ``torch.no_grad()``); there is no backward yet, so
-it raises when autograd would need one.
+registered buffers.  The training branch of ``forward`` (``mel`` given) returns the reference's 5-tuple;
+with autograd enabled the Denoiser's backward runs in the library as well (``mgb_denoiser_backward``).
 """
 from __future__ import annotations
 
@@ -229,7 +228,7 @@ class GaussianDiffusion(nn.Module):
                 x_T=None, noises=None, start_noise=None, t=None, noise_t=None, noise_prev=None, post_noise=None):
         """diffusion.py:187-226.  ``cond [B,T,H]``; ``mel_mask [B,T]`` True = padding.
         Inference (``mel is None``) returns ``(x_0_pred [B,T,M], None, None, None, t)``; with ``mel`` given the
-        reference's training-branch 5-tuple ``(x_0_pred, x_t, x_t_prev, x_t_prev_pred, t)`` (forward values only)."""
+        reference's training-branch 5-tuple ``(x_0_pred, x_t, x_t_prev, x_t_prev_pred, t)``."""
         b, device = cond.shape[0], cond.device
         self.cond = cond.transpose(1, 2).detach()
         self.spk_emb = spk_emb.detach() if spk_emb is not None else None
@@ -267,13 +266,11 @@ class GaussianDiffusion(nn.Module):
 
     def _forward_training(self, mel, cond, spk_emb, mel_mask, coarse_mel, clip_denoised, t, noise_t, noise_prev,
                           post_noise):
-        """diffusion.py:201-225, forward values only: the Denoiser call runs in the library (per-utterance
-        timesteps), the light elementwise steps are torch on the registered buffers."""
-        if torch.is_grad_enabled() and (cond.requires_grad or any(p.requires_grad for p in self.denoise_fn.parameters())):
-            raise NotImplementedError("the B200 GaussianDiffusion has no backward in this build: evaluate the training "
-                                      "branch under torch.no_grad() (as evaluate.py does) or train with the reference module")
+        """diffusion.py:201-225.  The Denoiser call runs in the library (per-utterance timesteps; with autograd
+        enabled its backward runs there too, see ``modules._DenoiserGradFn``), the light elementwise steps around it
+        are torch on the registered buffers, so torch autograd chains through them as in the reference."""
         b, device = cond.shape[0], cond.device
-        with torch.no_grad(), torch.cuda.device(device):
+        with torch.cuda.device(device):
             valid = (~mel_mask)[:, None, None, :]                                   # :190, :202
             if t is None:
                 t = torch.randint(0, self.num_timesteps, (b,), device=device)       # :203
@@ -282,7 +279,7 @@ class GaussianDiffusion(nn.Module):
             x_t_prev = self.diffuse_fn(mel, t - 1, noise=noise_prev) * valid         # :207
             x_0_pred = self.denoise_fn(x_t, t, cond.transpose(1, 2), spk_emb) * valid   # :210
             if clip_denoised:
-                x_0_pred.clamp_(-1., 1.)                                            # :211-212
+                x_0_pred = x_0_pred.clamp(-1., 1.)                                  # :211-212
             if self.model != "shallow":
                 x_start = x_0_pred
             else:

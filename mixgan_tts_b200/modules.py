@@ -89,7 +89,10 @@ class Denoiser(nn.Module):
         nn.init.zeros_(self.output_projection.conv.weight)   # as the reference (modules.py:418)
 
         self._packed = {}          # precision -> (fingerprint, packed tensor)
+        self._flat = None          # (fingerprint, flat fp32 parameter vector) of the last pack
         self._ws = _Workspace()
+        self._train_ws = _Workspace()
+        self.grad_sync = None      # optional mixgan_tts_b200.grad_sync.GradSync (data-parallel training)
 
     # ---------------------------------------------------------------- weights
     def _ordered_params(self):
@@ -121,7 +124,11 @@ class Denoiser(nn.Module):
                                "move the module with .cuda() first")
         lib = _lib.load()
         with torch.cuda.device(dev):
-            flat = torch.cat([p.detach().reshape(-1).float() for p in params]).contiguous()
+            if self._flat is not None and self._flat[0] == fp:
+                flat = self._flat[1]
+            else:
+                flat = torch.cat([p.detach().reshape(-1).float() for p in params]).contiguous()
+                self._flat = (fp, flat)
             assert flat.numel() == lib.mgb_flat_weight_count(C.byref(self.dims))
             nbytes = lib.mgb_packed_bytes(C.byref(self.dims), prec)
             if nbytes == 0:
@@ -150,14 +157,16 @@ class Denoiser(nn.Module):
         -> ``[B,1,M,T]``.  ``mask`` is accepted and ignored, as in the reference."""
         if mel.device.type != "cuda":
             raise RuntimeError("mixgan_tts_b200.Denoiser needs CUDA tensors (no CPU fallback)")
-        if torch.is_grad_enabled() and self.training and any(p.requires_grad for p in self.parameters()):
-            raise NotImplementedError("the B200 Denoiser has no backward in this build: call .eval() or "
-                                      "run under torch.no_grad() (outputs never carry a graph)")
         if self.dims.multi_speaker and speaker_emb is None:
             raise TypeError("multi_speaker Denoiser needs speaker_emb")   # reference: F.linear(None) TypeError
         B, _, M, T = mel.shape
         if M != self.dims.n_mel or conditioner.shape != (B, self.dims.d_encoder, T):
             raise ValueError(f"shape mismatch: mel {tuple(mel.shape)}, conditioner {tuple(conditioner.shape)}")
+        if torch.is_grad_enabled() and (
+                mel.requires_grad or conditioner.requires_grad
+                or (speaker_emb is not None and speaker_emb.requires_grad)
+                or any(p.requires_grad for p in self.parameters())):
+            return self._forward_with_grad(mel, diffusion_step, conditioner, speaker_emb)
         lib = _lib.load()
         dev = mel.device
         with torch.cuda.device(dev):
@@ -174,3 +183,94 @@ class Denoiser(nn.Module):
                 _lib.ptr(cond), _lib.ptr(spk), _lib.ptr(out), B, T, _lib.ptr(ws), ws.numel(),
                 C.c_void_p(stream)), "mgb_denoiser_forward")
         return out
+
+    # ---------------------------------------------------------------- training (autograd)
+    def flat_weights(self) -> torch.Tensor:
+        """The parameters as one fp32 vector in the canonical order (cached together with the fp32 pack)."""
+        self.packed_weights("fp32")
+        return self._flat[1]
+
+    def train_workspace(self, B: int, T: int, device) -> torch.Tensor:
+        lib = _lib.load()
+        n = lib.mgb_train_workspace_bytes(C.byref(self.dims), B, T)
+        if n == 0:
+            raise ValueError(f"unsupported shape B={B} T={T}")
+        return self._train_ws.get(n, device)
+
+    def _forward_with_grad(self, mel, diffusion_step, conditioner, speaker_emb):
+        """Forward that records a graph node whose backward runs in the library (fp32 arithmetic, whatever
+        ``self.precision`` the inference path uses).  The transposes/casts around it are ordinary torch ops."""
+        cond_bth = conditioner.transpose(1, 2).float().contiguous()
+        spk = speaker_emb.float().contiguous() if self.dims.multi_speaker else None
+        params = self._ordered_params()
+        return _DenoiserGradFn.apply(self, mel.float().contiguous(), diffusion_step, cond_bth, spk, *params)
+
+
+class _DenoiserGradFn(torch.autograd.Function):
+    """autograd node for ``Denoiser.forward``: ``mgb_denoiser_train_forward`` / ``mgb_denoiser_backward``.
+
+    The backward runs as gradient buckets (groups of backward segments); when the module has a ``grad_sync``
+    the all-reduce of a finished bucket is started while the next bucket is computed."""
+
+    @staticmethod
+    def forward(ctx, den, x, t, cond_bth, spk, *params):
+        lib = _lib.load()
+        dev = x.device
+        B, _, M, T = x.shape
+        with torch.cuda.device(dev):
+            packed = den.packed_weights("fp32")
+            tt = t.detach().to(torch.int64).contiguous()
+            out = torch.empty_like(x)
+            saved = torch.empty(lib.mgb_train_saved_bytes(C.byref(den.dims), B, T), dtype=torch.uint8, device=dev)
+            ws = den.train_workspace(B, T, dev)
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            _lib.check(lib.mgb_denoiser_train_forward(
+                C.byref(den.dims), _lib.PREC_FP32, _lib.ptr(packed), _lib.ptr(x), _lib.ptr(tt), _lib.ptr(cond_bth),
+                _lib.ptr(spk), _lib.ptr(out), _lib.ptr(saved), saved.numel(), B, T, _lib.ptr(ws), ws.numel(),
+                C.c_void_p(stream)), "mgb_denoiser_train_forward")
+        ctx.den, ctx.saved, ctx.tt, ctx.cond, ctx.spk = den, saved, tt, cond_bth, spk
+        ctx.flat = den.flat_weights()
+        ctx.shape = (B, M, T)
+        ctx.param_shapes = [p.shape for p in params]
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        from .grad_sync import plan_buckets
+        den, lib = ctx.den, _lib.load()
+        B, M, T = ctx.shape
+        dev = gout.device
+        need = ctx.needs_input_grad          # (den, x, t, cond, spk, *params)
+        with torch.cuda.device(dev):
+            gout = gout.float().contiguous()
+            gflat = torch.empty_like(ctx.flat)
+            gx = torch.empty((B, 1, M, T), dtype=torch.float32, device=dev) if need[1] else None
+            gcond = torch.empty_like(ctx.cond) if need[3] else None
+            gspk = torch.empty_like(ctx.spk) if (ctx.spk is not None and need[4]) else None
+            ws = den.train_workspace(B, T, dev)
+            stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            sync = den.grad_sync
+            nseg = lib.mgb_train_segments(C.byref(den.dims))
+            ranges = []
+            for s in range(nseg):
+                b, e = C.c_size_t(0), C.c_size_t(0)
+                _lib.check(lib.mgb_train_segment_range(C.byref(den.dims), s, C.byref(b), C.byref(e)), "segment range")
+                ranges.append((b.value, e.value))
+            buckets = plan_buckets(ranges, sync.bucket_bytes if sync is not None else None)
+            for sb, se, fb, fe in buckets:
+                _lib.check(lib.mgb_denoiser_backward(
+                    C.byref(den.dims), _lib.PREC_FP32, _lib.ptr(ctx.flat), _lib.ptr(ctx.saved), ctx.saved.numel(),
+                    _lib.ptr(ctx.tt), _lib.ptr(ctx.cond), _lib.ptr(ctx.spk), _lib.ptr(gout), _lib.ptr(gflat),
+                    _lib.ptr(gcond), _lib.ptr(gspk), _lib.ptr(gx), B, T, sb, se, _lib.ptr(ws), ws.numel(), stream),
+                    "mgb_denoiser_backward")
+                if sync is not None:
+                    sync.reduce_async(gflat[fb:fe])
+            if sync is not None:
+                sync.finish()
+        grads, off = [], 0
+        for shp, nd in zip(ctx.param_shapes, need[5:]):
+            n = int(torch.Size(shp).numel())
+            grads.append(gflat[off:off + n].view(shp) if nd else None)
+            off += n
+        ctx.saved = None
+        return (None, gx, None, gcond, gspk, *grads)

@@ -119,3 +119,16 @@ def make_train_extras(seed: int, B: int, T: int, K: int, *, n_mel: int = 80, spe
             "noise_t": g.standard_normal((B, 1, n_mel, T), dtype=np.float32),
             "noise_prev": g.standard_normal((B, 1, n_mel, T), dtype=np.float32),
             "post_noise": g.standard_normal((B, 1, n_mel, T), dtype=np.float32)}
+
+
+def grad_probe(seed: int, B: int, T: int, *, n_mel: int = 80) -> dict:
+    """Fixed random weights ``r0, r1 [B,T,M]`` of the linear probe loss used by the gradient parity tests:
+    ``loss = <x_0_pred, r0> + <x_t_prev_pred, r1>`` over the training branch's outputs."""
+    g = _rng(seed)
+    return {"r0": g.standard_normal((B, T, n_mel), dtype=np.float32),
+            "r1": g.standard_normal((B, T, n_mel), dtype=np.float32)}
+
+
+def grad_sample_index(n: int, k: int = 257) -> np.ndarray:
+    """Indices of the strided sample of a flattened gradient that the gradient goldens store."""
+    return np.unique(np.linspace(0, n - 1, min(n, k)).astype(np.int64))

@@ -67,11 +67,11 @@ def residual_block(W: dict, l: int, x, cond, d, spk):
     return (xo + res) / math.sqrt(2.0), skip                                             # :1176
 
 
-@torch.no_grad()
-def denoiser_forward(W: dict, mel, t, cond, spk=None):
+def denoiser_forward_graph(W: dict, mel, t, cond, spk=None):
     """``mel [B,1,M,T]``, ``t`` int64 ``[B]``, ``cond [B,H,T]``, ``spk [B,H]|None`` -> ``[B,1,M,T]``.
 
-    model/modules.py:420-446.
+    model/modules.py:420-446.  Plain torch ops, so torch autograd differentiates it exactly as it differentiates
+    the reference module: this is the gradient oracle of the training path.
     """
     L = num_layers(W)
     x = mel[:, 0]
@@ -85,3 +85,9 @@ def denoiser_forward(W: dict, mel, t, cond, spk=None):
     x = F.relu(F.conv1d(x, W["skip_projection.conv.weight"], W["skip_projection.conv.bias"]))
     x = F.conv1d(x, W["output_projection.conv.weight"], W["output_projection.conv.bias"])
     return x[:, None, :, :]
+
+
+@torch.no_grad()
+def denoiser_forward(W: dict, mel, t, cond, spk=None):
+    """Forward values only (inference)."""
+    return denoiser_forward_graph(W, mel, t, cond, spk)

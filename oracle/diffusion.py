@@ -14,7 +14,7 @@ import numpy as np
 import torch
 
 from . import schedule
-from .denoiser import as_torch, denoiser_forward
+from .denoiser import as_torch, denoiser_forward, denoiser_forward_graph
 
 
 class DiffusionOracle:
@@ -108,17 +108,22 @@ class DiffusionOracle:
         return states[-1] * valid, states, x0s, start
 
     @torch.no_grad()
-    def forward_training(self, mel, cond, spk, pad_mask, *, t, noise_t, noise_prev, post_noise,
-                         coarse_mel=None, clip_denoised=True):
+    def forward_training(self, mel, cond, spk, pad_mask, **kw):
+        """Forward values of ``forward_training_graph`` (what ``evaluate.py`` uses under ``no_grad``)."""
+        return self.forward_training_graph(mel, cond, spk, pad_mask, **kw)
+
+    def forward_training_graph(self, mel, cond, spk, pad_mask, *, t, noise_t, noise_prev, post_noise,
+                               coarse_mel=None, clip_denoised=True, W=None):
         """The ``mel is not None`` branch of ``GaussianDiffusion.forward`` (model/diffusion.py:201-225),
-        forward values only.  ``t`` is what the reference draws with ``torch.randint`` (:203),
+        differentiable by torch autograd (pass ``W`` with ``requires_grad`` tensors to get parameter gradients).
+        ``t`` is what the reference draws with ``torch.randint`` (:203),
         ``noise_t`` / ``noise_prev`` the two ``randn_like`` draws of ``diffuse_fn`` (:206-207, :182) and
         ``post_noise`` the draw inside ``q_posterior_sample`` (:116).  Returns the reference's 5-tuple."""
         valid = (~pad_mask)[:, None, None, :]                                   # :190, :202  [B,1,1,T]
         cond_bht = cond.transpose(1, 2)                                         # :191
         x_t = self.diffuse_fn(mel, t.clone(), noise_t) * valid                   # :206
         x_t_prev = self.diffuse_fn(mel, t - 1, noise_prev) * valid               # :207 (t-1 = -1 -> the clean mel)
-        x0 = denoiser_forward(self.W, x_t, t, cond_bht, spk) * valid             # :210
+        x0 = denoiser_forward_graph(W if W is not None else self.W, x_t, t, cond_bht, spk) * valid   # :210
         if clip_denoised:
             x0 = x0.clamp(-1.0, 1.0)                                            # :211-212
         if self.model != "shallow":

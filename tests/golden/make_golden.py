@@ -119,10 +119,52 @@ def run_train_case(name, dataset, model, multi, B, T, wseed, iseed):
     print(name, "K", K, "t", res[4].tolist(), "x0 rms", float(res[0].pow(2).mean().sqrt()))
 
 
+def run_grad_case(name, dataset, model, multi, B, T, wseed, iseed):
+    """Gradients of the REAL reference (torch autograd through model/diffusion.py:201-225 and the Denoiser) for the
+    linear probe loss of ``synth.grad_probe``: full d loss / d cond and d loss / d spk, and per parameter the gradient's
+    L2 norm plus a strided sample (the full 55 MB of parameter gradients are not committed)."""
+    torch.set_num_threads(1)
+    args, pc, mc, tc = configs.make_configs(dataset, model, multi)
+    W = synth.make_denoiser_weights(wseed, layers=mc["denoiser"]["residual_layers"], multi_speaker=multi)
+    gd = ref_loader.build_reference_diffusion(args, pc, mc, tc, W)
+    K = gd.num_timesteps
+    inp = synth.make_inputs(iseed, B, T, K, multi_speaker=multi, shallow=(model == "shallow"))
+    ex = synth.make_train_extras(iseed + 1000, B, T, K)
+    pr = synth.grad_probe(iseed + 2000, B, T)
+    tt = lambda a: None if a is None else torch.from_numpy(a)
+    cond = tt(inp["cond"]).requires_grad_(True)
+    spk = tt(inp["spk"])
+    if spk is not None:
+        spk.requires_grad_(True)
+    for p in gd.denoise_fn.parameters():
+        p.requires_grad_(True)
+    with ref_loader.injected_noise(noise_like_seq=[tt(ex["post_noise"])],
+                                   randn_like_seq=[tt(ex["noise_t"]), tt(ex["noise_prev"])],
+                                   randint_seq=[tt(ex["t"]).clone()]):
+        res = gd(tt(ex["mel"]), cond, spk, tt(inp["pad_mask"]), coarse_mel=tt(inp["coarse_mel"]))
+    loss = (res[0] * tt(pr["r0"])).sum() + (res[3] * tt(pr["r1"])).sum()
+    loss.backward()
+    out = {"weights_sha256": synth.weights_digest(W), "torch_version": torch.__version__, "K": K,
+           "loss": np.float64(loss.item()), "grad_cond": cond.grad.numpy()}
+    if spk is not None:
+        out["grad_spk"] = spk.grad.numpy()
+    for k, p in gd.denoise_fn.named_parameters():
+        g = p.grad.detach().numpy().reshape(-1)
+        out["gnorm/" + k] = np.float64(np.sqrt((g.astype(np.float64) ** 2).sum()))
+        out["gsample/" + k] = g[synth.grad_sample_index(g.size)]
+    np.savez_compressed(os.path.join(HERE, name.replace("train_", "grad_") + ".npz"), **out)
+    print(name, "loss", loss.item(), "|d cond|", float(cond.grad.norm()))
+
+
 if __name__ == "__main__":
+    if "--grad-only" in sys.argv:
+        for name, spec in TRAIN_CASES.items():
+            run_grad_case(name, *spec)
+        sys.exit(0)
     only_train = "--train-only" in sys.argv
     if not only_train:
         for name, spec in CASES.items():
             run_case(name, *spec)
     for name, spec in TRAIN_CASES.items():
         run_train_case(name, *spec)
+        run_grad_case(name, *spec)

@@ -1,0 +1,158 @@
+"""GPU parity of the training path (BASELINE configs[4]): Denoiser forward + backward in the library against torch
+autograd through the CPU oracle and against the gradients the REAL reference produced (tests/golden/grad_*.npz).
+
+Tolerance (relative L2, fp32 arithmetic on both sides): 1e-4 per gradient tensor; measured ~1e-6."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from mixgan_tts_b200 import GaussianDiffusion, _lib, synth
+from helpers import (TRAIN_CASES, Case, check_grads_against_golden, grad_golden_name, load_golden,
+                     oracle_training_grads, rel_l2, train_case)
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+# Random edge shapes: a ReLU / clamp mask can legitimately flip for a pre-activation within rounding distance of the
+# threshold (different fp32 summation order on the two sides); ONE flipped element moves a gradient by ~3e-4 relative
+# at these small sizes, so the sweep uses north_star's fp32 bar instead of the 1e-4 the pinned golden cases meet.
+TOL_EDGE = 1e-3
+
+
+def build(case: Case) -> GaussianDiffusion:
+    gd = GaussianDiffusion(case.args, case.pc, case.mc, case.tc, precision="fp32")
+    gd.denoise_fn.load_state_dict({k: torch.from_numpy(v) for k, v in case.W.items()})
+    return gd.cuda().train()
+
+
+def cu(t, grad=False):
+    if t is None:
+        return None
+    t = t.cuda()
+    return t.requires_grad_(True) if grad else t
+
+
+def run_library(c, ex, probe, gd=None):
+    gd = gd or build(c)
+    gd.zero_grad(set_to_none=True)
+    cond, spk = cu(c.t("cond"), True), cu(c.t("spk"), c.t("spk") is not None)
+    out = gd(cu(ex["mel"]), cond, spk, cu(c.t("pad_mask")), coarse_mel=cu(c.t("coarse_mel")), t=cu(ex["t"]),
+             noise_t=cu(ex["noise_t"]), noise_prev=cu(ex["noise_prev"]), post_noise=cu(ex["post_noise"]))
+    loss = (out[0] * cu(probe["r0"])).sum() + (out[3] * cu(probe["r1"])).sum()
+    loss.backward()
+    torch.cuda.synchronize()
+    grads = {k: p.grad.detach().cpu() for k, p in gd.denoise_fn.named_parameters()}
+    return loss.detach().cpu(), out, grads, cond.grad.cpu(), (spk.grad.cpu() if spk is not None else None), gd
+
+
+def probe_for(name, c):
+    return {k: torch.from_numpy(v) for k, v in synth.grad_probe(TRAIN_CASES[name][6] + 2000, c.B, c.T).items()}
+
+
+@pytest.mark.parametrize("name", list(TRAIN_CASES))
+def test_gradients_vs_reference_golden_and_oracle(name):
+    g = load_golden(grad_golden_name(name))
+    c, ex = train_case(name)
+    probe = probe_for(name, c)
+    loss, out, grads, gcond, gspk, _ = run_library(c, ex, probe)
+    assert abs(float(loss) - float(g["loss"])) < 1e-4 * max(1.0, abs(float(g["loss"])))
+    check_grads_against_golden(g, grads, gcond, gspk, tol=TOL)
+    # every element of every gradient against torch autograd through the oracle
+    _, oout, ograds, ogcond, ogspk = oracle_training_grads(c, ex, probe)
+    for a, b in zip(out[:4], oout[:4]):
+        assert rel_l2(a.detach(), b.detach()) < TOL
+    assert rel_l2(gcond, ogcond) < TOL
+    if ogspk is not None:
+        assert rel_l2(gspk, ogspk) < TOL
+    total = float(torch.sqrt(sum(v.double().pow(2).sum() for v in ograds.values())))
+    for k, ref in ograds.items():
+        err = float((grads[k].double() - ref.double()).norm()) / max(float(ref.double().norm()), 1e-6 * total)
+        assert err < TOL, (k, err)
+
+
+@pytest.mark.parametrize("multi,B,T,L", [(False, 1, 1, 2), (False, 2, 3, 1), (True, 2, 129, 3), (False, 3, 257, 2)])
+def test_gradients_edge_shapes_vs_oracle(multi, B, T, L):
+    """Short / ragged / non-multiple-of-tile utterances and shallow stacks, incl. d loss / d mel of a bare Denoiser call."""
+    c = Case("AISHELL3" if multi else "LJSpeech", "naive", multi, B, T, wseed=3, iseed=40 + T, layers=L)
+    from oracle.denoiser import denoiser_forward_graph
+    gd = build(c)
+    x = cu(c.t("x_T"), True)
+    cond = cu(c.t("cond").transpose(1, 2).contiguous(), True)
+    spk = cu(c.t("spk"), multi)
+    t = torch.arange(B, dtype=torch.long).cuda() % c.K
+    r = torch.randn(B, 1, 80, T, generator=torch.Generator().manual_seed(5))
+    out = gd.denoise_fn(x, t, cond, spk)
+    (out * r.cuda()).sum().backward()
+    W = {k: torch.from_numpy(v).requires_grad_(True) for k, v in c.W.items()}
+    ox = c.t("x_T").requires_grad_(True)
+    ocond = c.t("cond").transpose(1, 2).contiguous().requires_grad_(True)
+    ospk = c.t("spk").requires_grad_(True) if multi else None
+    oout = denoiser_forward_graph(W, ox, t.cpu(), ocond, ospk)
+    (oout * r).sum().backward()
+    assert rel_l2(out.detach(), oout.detach()) < TOL_EDGE
+    assert rel_l2(x.grad, ox.grad) < TOL_EDGE
+    assert rel_l2(cond.grad, ocond.grad) < TOL_EDGE
+    if multi:
+        assert rel_l2(spk.grad, ospk.grad) < TOL_EDGE
+    total = float(torch.sqrt(sum(v.grad.double().pow(2).sum() for v in W.values() if v.grad is not None)))
+    for k, p in gd.denoise_fn.named_parameters():
+        ref = W[k].grad if W[k].grad is not None else torch.zeros_like(W[k])
+        err = float((p.grad.cpu().double() - ref.double()).norm()) / max(float(ref.double().norm()), 1e-6 * total)
+        assert err < TOL_EDGE, (k, err)
+
+
+def test_segmented_backward_is_bitwise_the_one_shot_backward_and_deterministic():
+    """Gradient buckets (what the all-reduce overlaps with) change the launch grouping only, not one bit of the result."""
+    from mixgan_tts_b200.grad_sync import plan_buckets
+    name = "train_naive_lj_B3_T48"
+    c, ex = train_case(name)
+    probe = probe_for(name, c)
+    _, _, g1, gc1, _, gd = run_library(c, ex, probe)
+    _, _, g2, gc2, _, _ = run_library(c, ex, probe, gd)
+    assert all(torch.equal(g1[k], g2[k]) for k in g1) and torch.equal(gc1, gc2)
+
+    class OneRankSync:            # buckets without communication
+        bucket_bytes = 4 << 20
+        n = 0
+        def reduce_async(self, b): self.n += 1
+        def finish(self): pass
+    gd.denoise_fn.grad_sync = OneRankSync()
+    _, _, g3, gc3, _, _ = run_library(c, ex, probe, gd)
+    assert gd.denoise_fn.grad_sync.n > 3
+    assert all(torch.equal(g1[k], g3[k]) for k in g1) and torch.equal(gc1, gc3)
+
+
+def test_optimizer_step_repacks_weights_and_inference_sees_them():
+    """After an optimizer step the cached kernel-layout weights are rebuilt (parameter versions change)."""
+    c, ex = train_case("train_naive_lj_B3_T48")
+    probe = probe_for("train_naive_lj_B3_T48", c)
+    gd = build(c)
+    opt = torch.optim.SGD(gd.parameters(), lr=1e-3)
+    l0 = run_library(c, ex, probe, gd)[0]
+    opt.step()
+    l1 = run_library(c, ex, probe, gd)[0]
+    assert float(l1) < float(l0)          # a descent step on a linear probe loss lowers it
+    with torch.no_grad():
+        gd.eval()
+        y = gd.denoise_fn(cu(c.t("x_T")), torch.zeros(c.B, dtype=torch.long).cuda(), cu(c.t("cond")).transpose(1, 2), None)
+    W2 = {k: v.detach().cpu().numpy() for k, v in gd.denoise_fn.state_dict().items()}
+    from oracle.denoiser import denoiser_forward
+    ref = denoiser_forward({k: torch.from_numpy(v) for k, v in W2.items()}, c.t("x_T"), torch.zeros(c.B, dtype=torch.long),
+                           c.t("cond").transpose(1, 2), None)
+    assert rel_l2(y, ref) < TOL
+
+
+def test_train_abi_errors():
+    lib = _lib.load()
+    d = _lib.ModelDims(80, 256, 256, 20, 0)
+    assert lib.mgb_train_segments(C.byref(d)) == 22
+    assert lib.mgb_denoiser_backward(C.byref(d), _lib.PREC_BF16, None, None, 0, None, None, None, None, None, None, None,
+                                     None, 1, 8, 0, 22, None, 0, None) == _lib.E_ARG
+    x = torch.zeros(16, device="cuda")
+    rc = lib.mgb_denoiser_train_forward(C.byref(d), _lib.PREC_BF16, _lib.ptr(x), _lib.ptr(x), _lib.ptr(x), _lib.ptr(x), None,
+                                        _lib.ptr(x), _lib.ptr(x), 64, 1, 8, _lib.ptr(x), 64, None)
+    assert rc == _lib.E_UNSUPPORTED
+    rc = lib.mgb_denoiser_train_forward(C.byref(d), _lib.PREC_FP32, _lib.ptr(x), _lib.ptr(x), _lib.ptr(x), _lib.ptr(x), None,
+                                        _lib.ptr(x), _lib.ptr(x), 64, 1, 8, _lib.ptr(x), 64, None)
+    assert rc == _lib.E_WORKSPACE

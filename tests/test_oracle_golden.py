@@ -107,3 +107,16 @@ def test_training_branch_matches_reference_golden(name):
     b0 = int(np.nonzero(g["t"] == 0)[0][0])
     valid = ~c.t("pad_mask")[b0]
     assert torch.equal(out[2][b0][valid], c.oracle.norm_spec(ex["mel"])[b0][valid])
+
+
+@pytest.mark.parametrize("name", list(TRAIN_CASES))
+def test_oracle_gradients_vs_reference_golden(name):
+    """torch autograd through the oracle reproduces the REAL reference's gradients (tests/golden/grad_*.npz)."""
+    from helpers import check_grads_against_golden, grad_golden_name, oracle_training_grads
+    g = load_golden(grad_golden_name(name))
+    c, ex = train_case(name)
+    assert synth.weights_digest(c.W) == str(g["weights_sha256"])
+    probe = {k: torch.from_numpy(v) for k, v in synth.grad_probe(TRAIN_CASES[name][6] + 2000, c.B, c.T).items()}
+    loss, _, grads, gcond, gspk = oracle_training_grads(c, ex, probe)
+    assert abs(float(loss) - float(g["loss"])) < 1e-4 * max(1.0, abs(float(g["loss"])))
+    check_grads_against_golden(g, grads, gcond, gspk, tol=5e-5)

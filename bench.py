@@ -322,6 +322,128 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+# ---------------------------------------------------------------------------------------------
+def run_train(args):
+    """--workload train: BASELINE configs[4] restricted to this repo's path — the diffusion decoder's training branch
+    (GaussianDiffusion.forward with mel given: q_sample x2, Denoiser forward, clamp, posterior sample), backward through
+    the library's Denoiser backward, data-parallel gradient all-reduce (NCCL, bucketed, overlapped with the backward) and
+    a fused Adam step on the Denoiser's parameters.  Per GPU: B=8 utterances x T=800 frames (config/LJSpeech/train.yaml:6).
+    The JCU discriminator / FastSpeech2 encoder of the full training step stay the reference's torch code (out of scope)."""
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    from mixgan_tts_b200 import GaussianDiffusion, _lib, configs, synth, shard
+    from mixgan_tts_b200.grad_sync import GradSync
+    lib = _lib.load()
+    B, T = args.train_batch, T_FRAMES
+    cfg = configs.make_configs("LJSpeech", "naive")
+    gd = GaussianDiffusion(*cfg, precision="fp32")
+    gd.denoise_fn.load_state_dict({k: torch.from_numpy(v) for k, v in synth.make_denoiser_weights(0).items()})
+    gd = gd.to(dev).train()
+    K = gd.num_timesteps
+    opt = torch.optim.Adam(gd.denoise_fn.parameters(), lr=1e-5, fused=True)
+    sync = GradSync() if world > 1 else None
+    NSETS = 3
+    sets = []
+    for i in range(NSETS):
+        inp = synth.make_inputs(77 + 13 * i + 1000 * rank, B, T, K)
+        ex = synth.make_train_extras(78 + 13 * i + 1000 * rank, B, T, K)
+        pr = synth.grad_probe(79 + 13 * i + 1000 * rank, B, T)
+        to = lambda a: torch.from_numpy(a).to(dev)
+        sets.append({"cond": to(inp["cond"]), "pad": to(inp["pad_mask"]), "mel": to(ex["mel"]), "r0": to(pr["r0"]), "r1": to(pr["r1"])})
+
+    def step(i, with_sync=True):
+        s = sets[i % NSETS]
+        gd.denoise_fn.grad_sync = sync if with_sync else None
+        opt.zero_grad(set_to_none=True)
+        cond = s["cond"].detach().requires_grad_(True)     # the encoder would receive d loss / d cond
+        out = gd(s["mel"], cond, None, s["pad"])
+        loss = (out[0] * s["r0"]).sum() + (out[3] * s["r1"]).sum()
+        loss.backward()
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(n, **kw):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(n):
+            step(i, **kw)
+        e1.record()
+        barrier()
+        return shard.max_over_ranks(e0.elapsed_time(e1), dev)
+
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    n0 = lib.mgb_launch_count()
+    ms = timed(args.steps)
+    launches = lib.mgb_launch_count() - n0
+    ms_nosync = timed(args.steps, with_sync=False) if world > 1 else ms
+    clocks = sampler.stop() if rank == 0 else None
+    if rank == 0:
+        frames = world * B * T
+        flops = 3 * FLOPS_PER_FRAME_STEP * frames            # forward + data-grad + weight-grad GEMMs
+        line = {"metric": "train_frames_per_sec", "value": frames * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
+                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": f"LJSpeech naive diffusion-decoder training branch: Denoiser fwd+bwd + fused Adam, B={B} x T={T} "
+                                       "per GPU (BASELINE configs[4] restricted to the Denoiser path), gradient all-reduce over NCCL",
+                           "tflops": flops * args.steps / (ms * 1e-3) / 1e12,
+                           "allreduce_exposed_ms_per_step": (ms - ms_nosync) / args.steps,
+                           "grad_bytes": int(lib.mgb_flat_weight_count(C.byref(gd.denoise_fn.dims))) * 4},
+                "gpu_launches": int(launches), "clocks": clocks}
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_oracle_train_throughput(B)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_oracle_train_throughput(B: int):
+    """The oracle's training branch + torch autograd on all host threads, one step at the same shape."""
+    import torch
+    from mixgan_tts_b200 import configs, synth
+    from oracle.diffusion import DiffusionOracle
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    _, _, mc, _ = configs.make_configs("LJSpeech", "naive")
+    W = synth.make_denoiser_weights(0)
+    orc = DiffusionOracle(W, model="naive", denoiser_cfg=mc["denoiser"], spec_min=[configs.SPEC_MIN] * 80, spec_max=[configs.SPEC_MAX] * 80)
+    inp, ex, pr = synth.make_inputs(77, B, T_FRAMES, K_DIFF), synth.make_train_extras(78, B, T_FRAMES, K_DIFF), synth.grad_probe(79, B, T_FRAMES)
+    tt = lambda a: torch.from_numpy(a)
+    Wt = {k: tt(v).requires_grad_(True) for k, v in W.items()}
+    best = None
+    for _ in range(2):
+        t0 = time.perf_counter()
+        cond = tt(inp["cond"]).requires_grad_(True)
+        out = orc.forward_training_graph(tt(ex["mel"]), cond, None, tt(inp["pad_mask"]), t=tt(ex["t"]).clone(), noise_t=tt(ex["noise_t"]),
+                                         noise_prev=tt(ex["noise_prev"]), post_noise=tt(ex["post_noise"]), W=Wt)
+        ((out[0] * tt(pr["r0"])).sum() + (out[3] * tt(pr["r1"])).sum()).backward()
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return {"value": B * T_FRAMES / best, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"one training-branch step (forward + autograd backward, no optimizer) at B={B} x T={T_FRAMES}, fp32 torch-CPU oracle, "
+                      f"best of 2, {best:.2f} s, torch {torch.__version__}"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -331,8 +453,13 @@ def main():
     ap.add_argument("--precision", default="auto", choices=["auto", "bf16", "fp32"])
     ap.add_argument("--batch", type=int, default=B_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="sample", choices=["sample", "train"],
+                    help="sample = the headline reverse-diffusion benchmark; train = Denoiser training step (configs[4] path)")
+    ap.add_argument("--train-batch", type=int, default=8)
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.workload == "train" and args.impl == "ours":
+        run_train(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)

@@ -194,6 +194,8 @@ int mgb_denoiser_backward(const mgb_model_dims* dims, int precision, const float
  * descriptor conventions the bf16 path relies on).  Copies `a_bytes`/`b_bytes` raw bytes into
  * shared memory, issues `ksteps` tcgen05.mma (M=128, N=n, K=16, bf16 -> fp32) with the given
  * descriptor fields (all byte quantities, multiples of 16), and writes D[128][n] fp32.
+ * use_bulk_copy: bit 0 = stage the images with cp.async.bulk, bit 1 = the A operand is MN-major (instruction
+ * descriptor bit 15), bit 2 = the B operand is MN-major (bit 16).
  */
 int mgb_probe_umma(const void* a_img, int a_bytes, const void* b_img, int b_bytes,
                    int a_start, int a_lbo, int a_sbo, int a_kadv,

@@ -38,7 +38,7 @@ __global__ void __launch_bounds__(128, 1) umma_probe_kernel(const ProbeArgs p) {
   tc::tc_fence_after();
   const uint32_t tmem = tmem_slot;
 
-  if (p.use_bulk) {
+  if (p.use_bulk & 1) {
     if (tid == 0) {
       tc::mbar_arrive_expect_tx(&bar_load, (uint32_t)(p.a_bytes + p.b_bytes));
       tc::bulk_g2s(smem, p.a_img, (uint32_t)p.a_bytes, &bar_load);
@@ -59,7 +59,9 @@ __global__ void __launch_bounds__(128, 1) umma_probe_kernel(const ProbeArgs p) {
   if (warp == 0 && status == 0) {
     tc::tc_fence_after();
     if (tc::elect_one()) {
-      const uint32_t idesc = tc::make_idesc_bf16(128, p.n);
+      // use_bulk bit 1: A operand is MN-major (M contiguous), bit 2: B operand is MN-major (N contiguous)
+      const uint32_t idesc = tc::make_idesc_bf16(128, p.n) | (((uint32_t)p.use_bulk >> 1 & 1u) << 15) |
+                             (((uint32_t)p.use_bulk >> 2 & 1u) << 16);
       const uint32_t a0 = tc::smem_u32(smem) + p.a_start;
       const uint32_t b0 = tc::smem_u32(smem + p.b_off) + p.b_start;
       for (int k = 0; k < p.ksteps; ++k) {

@@ -131,3 +131,42 @@ def test_aliased_operand_lbo0_sbo0(n):
     err = (D - A @ Bm.float().t()).abs().max().item()
     _report(f"aliased A operand (LBO=SBO=0) n={n}: status={int(st.item())} err={err:.3e}")
     assert int(st.item()) == 0 and err < 1e-3
+
+
+def _image_mn(mat: torch.Tensor) -> torch.Tensor:
+    """[rows(M or N), K] bf16 -> the [rows/8][K][8] image: 8 consecutive ROWS contiguous (16 B), k running at 16 B —
+    i.e. the frames-major activation image [C/8][frames][8] seen as an operand whose K axis is the frame axis."""
+    rows, K = mat.shape
+    return mat.t().reshape(K, rows // 8, 8).permute(1, 0, 2).contiguous()
+
+
+@pytest.mark.parametrize("which", ["a", "b", "ab"])
+@pytest.mark.parametrize("n,ksteps,shift", [(128, 4, 0), (256, 8, 0), (128, 4, 1), (128, 4, 2)])
+def test_mn_major_operands(which, n, ksteps, shift):
+    """MN-major (no swizzle) operands as the weight-gradient GEMMs of the training path read them: the activation image
+    [C/8][frames][8] with the FRAME axis as K.  Convention pinned here: LBO = 128 B (next 8-frame group), SBO = byte
+    stride between 8-channel chunks, K advance of one MMA (16 frames) = 256 B, a +16 B start = one frame later."""
+    lib = _lib.load()
+    K = 16 * ksteps
+    Kp = K + 8                                  # room for the shifted read
+    g = torch.Generator(device="cpu").manual_seed(n + ksteps + shift)
+    A = (torch.randn(128, Kp, generator=g) * 0.5).bfloat16().cuda()
+    Bm = (torch.randn(n, Kp, generator=g) * 0.5).bfloat16().cuda()
+    a_mn, b_mn = "a" in which, "b" in which
+    a_img = _image_mn(A) if a_mn else _image(A[:, :K].contiguous())
+    b_img = _image_mn(Bm) if b_mn else _image(Bm[:, :K].contiguous())
+    a_desc = (shift * 16, 128, Kp * 16, 256) if a_mn else (0, 128 * 16, 128, 2 * 128 * 16)
+    b_desc = (shift * 16, 128, Kp * 16, 256) if b_mn else (0, n * 16, 128, 2 * n * 16)
+    D = torch.full((128, n), float("nan"), device="cuda")
+    st = torch.zeros(1, dtype=torch.int32, device="cuda")
+    flags = 1 | (2 if a_mn else 0) | (4 if b_mn else 0)
+    rc = lib.mgb_probe_umma(_lib.ptr(a_img), a_img.numel() * 2, _lib.ptr(b_img), b_img.numel() * 2,
+                            *a_desc, *b_desc, n, ksteps, flags, _lib.ptr(D), _lib.ptr(st),
+                            C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    _lib.check(rc, "mgb_probe_umma")
+    torch.cuda.synchronize()
+    Ae = A[:, shift:shift + K] if a_mn else A[:, :K]
+    Be = Bm[:, shift:shift + K] if b_mn else Bm[:, :K]
+    err = (D - Ae.float() @ Be.float().t()).abs().max().item()
+    _report(f"MN-major {which} n={n} ksteps={ksteps} shift={shift}: status={int(st.item())} err={err:.3e}")
+    assert int(st.item()) == 0 and err < 1e-3

@@ -347,7 +347,8 @@ def run_train(args):
     lib = _lib.load()
     B, T = args.train_batch, T_FRAMES
     cfg = configs.make_configs("LJSpeech", "naive")
-    gd = GaussianDiffusion(*cfg, precision="fp32")
+    prec = "bf16" if args.precision == "auto" else args.precision
+    gd = GaussianDiffusion(*cfg, precision=prec)
     gd.denoise_fn.load_state_dict({k: torch.from_numpy(v) for k, v in synth.make_denoiser_weights(0).items()})
     gd = gd.to(dev).train()
     K = gd.num_timesteps
@@ -403,8 +404,8 @@ def run_train(args):
         flops = 3 * FLOPS_PER_FRAME_STEP * frames            # forward + data-grad + weight-grad GEMMs
         line = {"metric": "train_frames_per_sec", "value": frames * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
                 "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": f"LJSpeech naive diffusion-decoder training branch: Denoiser fwd+bwd + fused Adam, B={B} x T={T} "
+                "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if prec == "bf16" else "f32", "data": "synthetic",
+                "config": {"precision": prec, "workload": f"LJSpeech naive diffusion-decoder training branch: Denoiser fwd+bwd + fused Adam, B={B} x T={T} "
                                        "per GPU (BASELINE configs[4] restricted to the Denoiser path), gradient all-reduce over NCCL",
                            "tflops": flops * args.steps / (ms * 1e-3) / 1e12,
                            "allreduce_exposed_ms_per_step": (ms - ms_nosync) / args.steps,

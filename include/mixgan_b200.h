@@ -161,11 +161,13 @@ int mgb_length_regulate(const float* x, const int64_t* dur, float* out, int64_t*
 /*
  * Training (BASELINE configs[4]): Denoiser forward that keeps the activations its backward needs, and the
  * backward itself.  Replaces torch autograd through Denoiser.forward (model/modules.py:420-446,
- * model/blocks.py:1157-1176) as train.py:126-184 drives it.  MGB_PREC_FP32 only in this build.
- *   packed      : mgb_pack_weights(MGB_PREC_FP32) image of the CURRENT parameters
+ * model/blocks.py:1157-1176) as train.py:126-184 drives it.  MGB_PREC_FP32: fp32 GEMMs on the CUDA cores (parity mode);
+ * MGB_PREC_BF16: every GEMM on tcgen05 (bf16 operands, fp32 accumulation, fp32 residual/skip/gradient streams).
+ *   packed      : mgb_pack_weights(MGB_PREC_FP32) image of the CURRENT parameters (both precisions: the per-utterance
+ *                 step MLP and projection tables are fp32)
  *   flat        : the same parameters in the canonical flat order (mgb_pack_weights' input)
- *   saved       : caller-owned activation stash, mgb_train_saved_bytes(dims, B, T) bytes, written by the forward
- *   workspace   : mgb_train_workspace_bytes(dims, B, T) bytes, shared by forward and backward
+ *   saved       : caller-owned activation stash, mgb_train_saved_bytes(dims, precision, B, T) bytes, written by the forward
+ *   workspace   : mgb_train_workspace_bytes(dims, precision, B, T) bytes, shared by forward and backward
  *   grad_out    : d loss / d out, [B][n_mel][T]
  *   grad_flat   : d loss / d parameters in the canonical flat order (WRITTEN, not accumulated)
  *   grad_cond   : [B][T][d_encoder] or NULL;  grad_spk: [B][d_encoder] or NULL;  grad_x: [B][n_mel][T] or NULL
@@ -175,12 +177,12 @@ int mgb_length_regulate(const float* x, const int64_t* dur, float* out, int64_t*
  * [flat_begin, flat_end) that mgb_train_segment_range reports is final, so the host can start the NCCL
  * all-reduce of that gradient bucket while later segments run (grad_cond/grad_spk/grad_x are final after the last).
  */
-size_t mgb_train_saved_bytes(const mgb_model_dims* dims, int B, int T);
-size_t mgb_train_workspace_bytes(const mgb_model_dims* dims, int B, int T);
+size_t mgb_train_saved_bytes(const mgb_model_dims* dims, int precision, int B, int T);
+size_t mgb_train_workspace_bytes(const mgb_model_dims* dims, int precision, int B, int T);
 int mgb_train_segments(const mgb_model_dims* dims);
 int mgb_train_segment_range(const mgb_model_dims* dims, int seg, size_t* flat_begin, size_t* flat_end);
-int mgb_denoiser_train_forward(const mgb_model_dims* dims, int precision, const void* packed, const float* x,
-                               const int64_t* t, const float* cond, const float* spk, float* out,
+int mgb_denoiser_train_forward(const mgb_model_dims* dims, int precision, const void* packed, const float* flat,
+                               const float* x, const int64_t* t, const float* cond, const float* spk, float* out,
                                void* saved, size_t saved_bytes, int B, int T,
                                void* workspace, size_t workspace_bytes, void* stream);
 int mgb_denoiser_backward(const mgb_model_dims* dims, int precision, const float* flat, const void* saved,
@@ -188,6 +190,8 @@ int mgb_denoiser_backward(const mgb_model_dims* dims, int precision, const float
                           const float* grad_out, float* grad_flat, float* grad_cond, float* grad_spk,
                           float* grad_x, int B, int T, int seg_begin, int seg_end,
                           void* workspace, size_t workspace_bytes, void* stream);
+/* Debug: synchronously read the watchdog word of the bf16 training kernels from a workspace used with (B, T). */
+int mgb_train_debug_status(const mgb_model_dims* dims, int B, int T, const void* workspace, int* host_status);
 
 /*
  * tcgen05 descriptor probe (used by tests/test_umma_probe.py to pin the shared-memory

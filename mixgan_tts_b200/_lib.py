@@ -39,11 +39,12 @@ SIGNATURES = {
     "mgb_denoiser_forward": (_I, [_D, _I, _P, _P, _P, _P, _P, _P, _I, _I, _P, _Z, _P]),
     "mgb_reverse_step": (_I, [_D, _I, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _I, _I, _P, _Z, _P]),
     "mgb_sample": (_I, [_D, _I, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P, _I, _I, _P, _Z, _P]),
-    "mgb_train_saved_bytes": (_Z, [_D, _I, _I]),
-    "mgb_train_workspace_bytes": (_Z, [_D, _I, _I]),
+    "mgb_train_saved_bytes": (_Z, [_D, _I, _I, _I]),
+    "mgb_train_workspace_bytes": (_Z, [_D, _I, _I, _I]),
+    "mgb_train_debug_status": (_I, [_D, _I, _I, _P, C.POINTER(C.c_int)]),
     "mgb_train_segments": (_I, [_D]),
     "mgb_train_segment_range": (_I, [_D, _I, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
-    "mgb_denoiser_train_forward": (_I, [_D, _I, _P, _P, _P, _P, _P, _P, _P, _Z, _I, _I, _P, _Z, _P]),
+    "mgb_denoiser_train_forward": (_I, [_D, _I, _P, _P, _P, _P, _P, _P, _P, _P, _Z, _I, _I, _P, _Z, _P]),
     "mgb_denoiser_backward": (_I, [_D, _I, _P, _P, _Z, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _Z, _P]),
     "mgb_shallow_start": (_I, [_P, _P, _P, _P, _F, _F, _P, _P, _I, _I, _I, _P]),
     "mgb_denorm_mask": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P]),

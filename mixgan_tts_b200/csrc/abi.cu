@@ -349,14 +349,17 @@ int mgb_sample(const mgb_model_dims* dims, int precision, const void* packed, co
   return MGB_OK;
 }
 
-size_t mgb_train_saved_bytes(const mgb_model_dims* dims, int B, int T) {
-  if (!dims_supported(dims) || B <= 0 || T <= 0) return 0;
-  return train_saved_layout(*dims, B, T).total * sizeof(float);
+static bool train_prec_ok(int precision) { return precision == MGB_PREC_FP32 || precision == MGB_PREC_BF16; }
+
+size_t mgb_train_saved_bytes(const mgb_model_dims* dims, int precision, int B, int T) {
+  if (!dims_supported(dims) || B <= 0 || T <= 0 || !train_prec_ok(precision)) return 0;
+  return precision == MGB_PREC_FP32 ? train_saved_layout(*dims, B, T).total * sizeof(float)
+                                    : bf16_train_saved_bytes(*dims, B, T);
 }
 
-size_t mgb_train_workspace_bytes(const mgb_model_dims* dims, int B, int T) {
-  if (!dims_supported(dims) || B <= 0 || T <= 0) return 0;
-  return train_workspace_bytes(*dims, B, T);
+size_t mgb_train_workspace_bytes(const mgb_model_dims* dims, int precision, int B, int T) {
+  if (!dims_supported(dims) || B <= 0 || T <= 0 || !train_prec_ok(precision)) return 0;
+  return precision == MGB_PREC_FP32 ? train_workspace_bytes(*dims, B, T) : bf16_train_workspace_bytes(*dims, B, T);
 }
 
 int mgb_train_segments(const mgb_model_dims* dims) { return dims_supported(dims) ? dims->layers + 2 : 0; }
@@ -372,21 +375,24 @@ int mgb_train_segment_range(const mgb_model_dims* dims, int seg, size_t* flat_be
   return MGB_OK;
 }
 
-int mgb_denoiser_train_forward(const mgb_model_dims* dims, int precision, const void* packed, const float* x,
-                               const int64_t* t, const float* cond, const float* spk, float* out, void* saved,
-                               size_t saved_bytes, int B, int T, void* workspace, size_t workspace_bytes, void* stream) {
+int mgb_denoiser_train_forward(const mgb_model_dims* dims, int precision, const void* packed, const float* flat,
+                               const float* x, const int64_t* t, const float* cond, const float* spk, float* out,
+                               void* saved, size_t saved_bytes, int B, int T, void* workspace, size_t workspace_bytes,
+                               void* stream) {
   MGB_REQUIRE(dims_supported(dims), MGB_E_ARG, "unsupported model dims");
-  MGB_REQUIRE(packed && x && t && cond && out && saved && workspace, MGB_E_ARG, "NULL pointer argument");
+  MGB_REQUIRE(packed && flat && x && t && cond && out && saved && workspace, MGB_E_ARG, "NULL pointer argument");
   MGB_REQUIRE(B > 0 && T > 0, MGB_E_ARG, "B and T must be positive (got %d, %d)", B, T);
   MGB_REQUIRE(!dims->multi_speaker || spk, MGB_E_ARG, "multi_speaker model needs a speaker embedding");
-  MGB_REQUIRE(precision == MGB_PREC_FP32, MGB_E_UNSUPPORTED, "the training path computes in fp32 only in this build");
+  MGB_REQUIRE(train_prec_ok(precision), MGB_E_ARG, "unknown precision %d", precision);
   if (int rc = check_arch()) return rc;
-  MGB_REQUIRE(saved_bytes >= mgb_train_saved_bytes(dims, B, T), MGB_E_WORKSPACE, "activation stash too small: %zu < %zu",
-              saved_bytes, mgb_train_saved_bytes(dims, B, T));
-  MGB_REQUIRE(workspace_bytes >= mgb_train_workspace_bytes(dims, B, T), MGB_E_WORKSPACE, "workspace too small: %zu < %zu",
-              workspace_bytes, mgb_train_workspace_bytes(dims, B, T));
-  return fp32_train_forward(*dims, packed, x, t, cond, spk, out, static_cast<float*>(saved), B, T, workspace,
-                            static_cast<cudaStream_t>(stream));
+  MGB_REQUIRE(saved_bytes >= mgb_train_saved_bytes(dims, precision, B, T), MGB_E_WORKSPACE,
+              "activation stash too small: %zu < %zu", saved_bytes, mgb_train_saved_bytes(dims, precision, B, T));
+  MGB_REQUIRE(workspace_bytes >= mgb_train_workspace_bytes(dims, precision, B, T), MGB_E_WORKSPACE,
+              "workspace too small: %zu < %zu", workspace_bytes, mgb_train_workspace_bytes(dims, precision, B, T));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (precision == MGB_PREC_FP32)
+    return fp32_train_forward(*dims, packed, x, t, cond, spk, out, static_cast<float*>(saved), B, T, workspace, s);
+  return bf16_train_forward(*dims, packed, flat, x, t, cond, spk, out, saved, B, T, workspace, s);
 }
 
 int mgb_denoiser_backward(const mgb_model_dims* dims, int precision, const float* flat, const void* saved,
@@ -397,14 +403,27 @@ int mgb_denoiser_backward(const mgb_model_dims* dims, int precision, const float
   MGB_REQUIRE(flat && saved && t && cond && grad_out && grad_flat && workspace, MGB_E_ARG, "NULL pointer argument");
   MGB_REQUIRE(B > 0 && T > 0, MGB_E_ARG, "B and T must be positive (got %d, %d)", B, T);
   MGB_REQUIRE(!dims->multi_speaker || spk, MGB_E_ARG, "multi_speaker model needs a speaker embedding");
-  MGB_REQUIRE(precision == MGB_PREC_FP32, MGB_E_UNSUPPORTED, "the training path computes in fp32 only in this build");
+  MGB_REQUIRE(train_prec_ok(precision), MGB_E_ARG, "unknown precision %d", precision);
   MGB_REQUIRE(seg_begin >= 0 && seg_begin <= seg_end && seg_end <= dims->layers + 2, MGB_E_ARG,
               "bad segment range [%d, %d)", seg_begin, seg_end);
   if (int rc = check_arch()) return rc;
-  MGB_REQUIRE(saved_bytes >= mgb_train_saved_bytes(dims, B, T), MGB_E_WORKSPACE, "activation stash too small");
-  MGB_REQUIRE(workspace_bytes >= mgb_train_workspace_bytes(dims, B, T), MGB_E_WORKSPACE, "workspace too small");
-  return fp32_train_backward(*dims, flat, static_cast<const float*>(saved), t, cond, spk, grad_out, grad_flat, grad_cond,
-                             grad_spk, grad_x, B, T, seg_begin, seg_end, workspace, static_cast<cudaStream_t>(stream));
+  MGB_REQUIRE(saved_bytes >= mgb_train_saved_bytes(dims, precision, B, T), MGB_E_WORKSPACE, "activation stash too small");
+  MGB_REQUIRE(workspace_bytes >= mgb_train_workspace_bytes(dims, precision, B, T), MGB_E_WORKSPACE, "workspace too small");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (precision == MGB_PREC_FP32)
+    return fp32_train_backward(*dims, flat, static_cast<const float*>(saved), t, cond, spk, grad_out, grad_flat, grad_cond,
+                               grad_spk, grad_x, B, T, seg_begin, seg_end, workspace, s);
+  return bf16_train_backward(*dims, flat, saved, t, cond, spk, grad_out, grad_flat, grad_cond, grad_spk, grad_x, B, T,
+                             seg_begin, seg_end, workspace, s);
+}
+
+/* Debug: watchdog word of the bf16 training kernels (0 = every kernel completed its barrier protocol). */
+int mgb_train_debug_status(const mgb_model_dims* dims, int B, int T, const void* workspace, int* host_status) {
+  MGB_REQUIRE(dims_supported(dims) && workspace && host_status && B > 0 && T > 0, MGB_E_ARG, "bad argument");
+  MGB_CUDA_CHECK(cudaDeviceSynchronize());
+  MGB_CUDA_CHECK(cudaMemcpy(host_status, static_cast<const uint8_t*>(workspace) + bf16_train_status_offset(*dims, B, T),
+                            sizeof(int), cudaMemcpyDeviceToHost));
+  return MGB_OK;
 }
 
 int mgb_shallow_start(const float* coarse, const float* noise, const float* spec_min, const float* spec_max,

@@ -144,6 +144,8 @@ inline TrainSaved train_saved_layout(const mgb_model_dims& d, int B, int T) {
   o.total = p;
   return o;
 }
+int fp32_step_tables(const mgb_model_dims& d, const void* packed, const int64_t* t, const float* spk, int B, float* d_buf,
+                     float* h_buf, float* dtab, float* ctab, cudaStream_t s);
 size_t train_workspace_bytes(const mgb_model_dims& d, int B, int T);
 // Denoiser.forward keeping the activations the backward needs (`saved`, TrainSaved layout); out = [B][n_mel][T].
 int fp32_train_forward(const mgb_model_dims& d, const void* packed, const float* x, const int64_t* t, const float* cond,
@@ -154,6 +156,16 @@ int fp32_train_forward(const mgb_model_dims& d, const void* packed, const float*
 int fp32_train_backward(const mgb_model_dims& d, const float* flat, const float* saved, const int64_t* t,
                         const float* cond, const float* spk, const float* grad_out, float* grad_flat, float* grad_cond,
                         float* grad_spk, float* grad_x, int B, int T, int seg_begin, int seg_end, void* ws, cudaStream_t s);
+
+// ---- bf16 tcgen05 training path (train_bf16.cu): same segments and gradient layout as the fp32 one ----
+size_t bf16_train_saved_bytes(const mgb_model_dims& d, int B, int T);
+size_t bf16_train_workspace_bytes(const mgb_model_dims& d, int B, int T);
+size_t bf16_train_status_offset(const mgb_model_dims& d, int B, int T);
+int bf16_train_forward(const mgb_model_dims& d, const void* packed_fp32, const float* flat, const float* x, const int64_t* t,
+                       const float* cond, const float* spk, float* out, void* saved, int B, int T, void* ws, cudaStream_t s);
+int bf16_train_backward(const mgb_model_dims& d, const float* flat, const void* saved, const int64_t* t, const float* cond,
+                        const float* spk, const float* grad_out, float* grad_flat, float* grad_cond, float* grad_spk,
+                        float* grad_x, int B, int T, int seg_begin, int seg_end, void* ws, cudaStream_t s);
 
 // ---- bf16 tcgen05 path (fused_bf16.cu) -------------------------------------------------------
 size_t bf16_packed_bytes(const mgb_model_dims& d);

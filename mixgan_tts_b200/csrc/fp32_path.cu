@@ -264,6 +264,24 @@ int fp32_pack(const mgb_model_dims& d, const float* flat, void* packed, cudaStre
   return MGB_OK;
 }
 
+// d[B][C] = step MLP(t); dtab[b][l] = Wd_l d[b]; ctab[b][l] = bc_l (+ Ws_l spk[b])   (blocks.py:1159-1164)
+int fp32_step_tables(const mgb_model_dims& d, const void* packed, const int64_t* t, const float* spk, int B, float* d_buf,
+                     float* h_buf, float* dtab, float* ctab, cudaStream_t s) {
+  const PackedF32 o = packed_layout(d);
+  const float* P = static_cast<const float*>(packed);
+  const int C = d.channels, H = d.d_encoder, L = d.layers;
+  launch_step_mlp(t, P + o.mlp0_wt, P + o.mlp2_wt, h_buf, d_buf, B, C, s);
+  dim3 grid(L, (B + TAB_UB - 1) / TAB_UB);
+  proj_table_kernel<<<grid, 256, (size_t)TAB_UB * C * sizeof(float), s>>>(
+      d_buf, C, P + o.layer0 + o.r_dproj_wt, o.layer_stride, nullptr, 0, dtab, B, L, C);
+  proj_table_kernel<<<grid, 256, (size_t)TAB_UB * H * sizeof(float), s>>>(
+      d.multi_speaker ? spk : nullptr, H, P + o.layer0 + o.r_sproj_wt, o.layer_stride,
+      P + o.layer0 + o.r_cproj_b, o.layer_stride, ctab, B, L, C);
+  note_launch(4);   // step MLP (2), two projection tables
+  MGB_LAUNCH_CHECK();
+  return MGB_OK;
+}
+
 int fp32_denoiser(const mgb_model_dims& d, const void* packed, const float* x, const int64_t* t,
                   const float* cond, const float* spk, const float* noise, const float* sched, int K,
                   int clip, float* x_prev, float* out_x0, int B, int T, void* ws, cudaStream_t s, float* saved) {
@@ -283,19 +301,11 @@ int fp32_denoiser(const mgb_model_dims& d, const void* packed, const float* x, c
   float* const h_buf = saved ? saved + sv.h : W + w.h;
 
   // per-utterance step embedding, MLP and the per-layer projection tables
-  launch_step_mlp(t, P + o.mlp0_wt, P + o.mlp2_wt, h_buf, d_buf, B, C, s);
-  {
-    dim3 grid(L, (B + TAB_UB - 1) / TAB_UB);
-    proj_table_kernel<<<grid, 256, (size_t)TAB_UB * C * sizeof(float), s>>>(
-        d_buf, C, P + o.layer0 + o.r_dproj_wt, o.layer_stride, nullptr, 0, W + w.dtab, B, L, C);
-    proj_table_kernel<<<grid, 256, (size_t)TAB_UB * H * sizeof(float), s>>>(
-        d.multi_speaker ? spk : nullptr, H, P + o.layer0 + o.r_sproj_wt, o.layer_stride,
-        P + o.layer0 + o.r_cproj_b, o.layer_stride, W + w.ctab, B, L, C);
-  }
+  fp32_step_tables(d, packed, t, spk, B, d_buf, h_buf, W + w.dtab, W + w.ctab, s);
   {
     dim3 grid((T + 31) / 32, (M + 31) / 32, B), block(32, 8);
     bmt_to_btm_kernel<<<grid, block, 0, s>>>(x, xt_buf, M, T);
-    note_launch(5);   // step MLP (2), two projection tables, this transpose
+    note_launch();
   }
   GemmArgs a{};
   a.rows = rows; a.T = T; a.C = C; a.tab_stride = L * C;

@@ -1,0 +1,1037 @@
+// bf16 tensor-core training path of the Denoiser (BASELINE configs[4]): forward with an activation stash and the
+// backward, every GEMM on tcgen05 (bf16 operands staged by the TMA engine's bulk copies, fp32 accumulation in TMEM),
+// fp32 residual / skip / gradient streams and fp32 weight gradients.  Same algebra and segment structure as the fp32
+// path (train_fp32.cu header); reference: autograd through model/modules.py:420-446, model/blocks.py:1157-1176.
+//
+// One activation layout serves both GEMM families.  Activations live as bf16 "images" [C/8][Rp][8] on a row axis that
+// holds all utterances (utterance b owns rows RLEAD + b*(T+1) + [0,T); the row between two utterances and the margins
+// are zero, which is the convolution's zero padding):
+//   * frames GEMMs (forward, data gradients): a 128-row x 8-channel block is one contiguous 2 KB bulk copy that lands
+//     in the K-major no-swizzle core-matrix order (LBO = 2048, SBO = 128); a convolution tap is the same copy one
+//     row earlier/later;
+//   * weight-gradient GEMMs (reduction over frames): the very same block is an MN-major operand whose K axis is the
+//     frame axis (LBO = 128, SBO = 2048; pinned by tests/test_umma_probe.py::test_mn_major_operands), so dW = P^T Q
+//     needs no transposed copy of any activation.  The frame axis is split over CTAs; fp32 partials are summed in a
+//     fixed order (train_small.cuh) straight into the flat gradient.
+// Weights are re-packed to bf16 K-major tiles once per step (they change every step).
+#include "common.cuh"
+#include "tc05.cuh"
+#include "train_small.cuh"
+
+#include <cstdlib>
+
+namespace mgb {
+
+namespace {
+
+using namespace trainsmall;
+using bf16 = __nv_bfloat16;
+
+constexpr int C = 256;            // channels == d_encoder (dims_supported)
+constexpr int RLEAD = 8;          // zero rows in front of the first utterance
+constexpr int TILE = 128;         // rows (frames) per CTA tile
+constexpr long long kTimeout = 200000000LL;    // ~0.1 s of SM cycles: a protocol bug traps instead of hanging
+constexpr float RSQRT2 = 0.70710678118654752440f;
+
+// MGB_TRAIN_TRACE=1: name every launch on stderr and synchronise after it (debug aid; never set in production)
+bool trace_on() {
+  static const bool on = [] { const char* e = getenv("MGB_TRAIN_TRACE"); return e && *e == '1'; }();
+  return on;
+}
+void trace(const char* what, cudaStream_t s) {
+  if (!trace_on()) return;
+  fprintf(stderr, "[mgb train] %s ...", what);
+  fflush(stderr);
+  const cudaError_t e = cudaStreamSynchronize(s);
+  fprintf(stderr, " %s\n", cudaGetErrorString(e));
+  fflush(stderr);
+}
+
+struct RowSpace { int T, Tg, R, ntiles, Rp; };
+RowSpace row_space(int B, int T) {
+  RowSpace r{};
+  r.T = T; r.Tg = T + 1; r.R = B * r.Tg;
+  r.ntiles = (r.R + TILE - 1) / TILE;
+  r.Rp = RLEAD + r.ntiles * TILE + 8;
+  return r;
+}
+
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float2 unpack2(uint32_t u) {
+  return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u));
+}
+// 32 consecutive channels [ch0, ch0+32) of image row `rho` <-> registers
+__device__ __forceinline__ void store_img32(bf16* img, int Rp, int rho, int ch0, const float (&v)[32]) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    uint4 u = make_uint4(pack2(v[q * 8], v[q * 8 + 1]), pack2(v[q * 8 + 2], v[q * 8 + 3]),
+                         pack2(v[q * 8 + 4], v[q * 8 + 5]), pack2(v[q * 8 + 6], v[q * 8 + 7]));
+    *reinterpret_cast<uint4*>(img + ((size_t)(ch0 / 8 + q) * Rp + rho) * 8) = u;
+  }
+}
+__device__ __forceinline__ void load_img32(const bf16* img, int Rp, int rho, int ch0, float (&v)[32]) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const uint4 u = *reinterpret_cast<const uint4*>(img + ((size_t)(ch0 / 8 + q) * Rp + rho) * 8);
+    float2 a = unpack2(u.x), b = unpack2(u.y), c = unpack2(u.z), d = unpack2(u.w);
+    v[q * 8] = a.x; v[q * 8 + 1] = a.y; v[q * 8 + 2] = b.x; v[q * 8 + 3] = b.y;
+    v[q * 8 + 4] = c.x; v[q * 8 + 5] = c.y; v[q * 8 + 6] = d.x; v[q * 8 + 7] = d.y;
+  }
+}
+__device__ __forceinline__ void load_f32x32(const float* p, float (&v)[32]) {
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const float4 a = *reinterpret_cast<const float4*>(p + q * 4);
+    v[q * 4] = a.x; v[q * 4 + 1] = a.y; v[q * 4 + 2] = a.z; v[q * 4 + 3] = a.w;
+  }
+}
+__device__ __forceinline__ void store_f32x32(float* p, const float (&v)[32]) {
+#pragma unroll
+  for (int q = 0; q < 8; ++q)
+    *reinterpret_cast<float4*>(p + q * 4) = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+}
+__device__ __forceinline__ void tmem_ld_f32x32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  tc::tmem_ld32(taddr, r);
+  tc::tmem_ld_wait();
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+}
+
+// =====================================================================================================
+// frames GEMM: D[128 rows][NT cols] = sum over k-steps of A[128][64] * B[NT][64]^T
+// =====================================================================================================
+enum FMode {
+  F_IN = 0, F_COND, F_GATE, F_OUT, F_SKIP, F_FINAL,              // forward
+  B_PMASK, B_DS, B_GATE, B_DX, B_COND, B_DXT                      // backward (data gradients)
+};
+
+struct FArgs {
+  const bf16* A0; const bf16* A1;   // activation images; K = taps x (steps0 from A0, then steps1 from A1) x 64 channels
+  int steps0, steps1, taps;
+  const bf16* Bpk;                  // packed weights [n-tile][ksteps_b][8][NT][8]
+  int ksteps_b, kstep_b0;
+  int Rp, B, T, L;
+  int* status;
+  // epilogue operands (meaning depends on the mode; see fgemm_epilogue)
+  const float* bias;                // flat-order bias vector
+  const float* dtab; const float* ctab;   // [B][L][C] tables, already offset to the layer
+  const float* fin;                 // fp32 [Rp][C] input stream (x / e / X0)
+  float* fout;                      // fp32 [Rp][C] output stream (x / e) or [B][n_mel][T] / [B][T][C] user tensors
+  float* fout2;                     // fp32 [Rp][C] skip sum
+  bf16* img; bf16* img2;            // output images
+  const bf16* aux_img;              // input image (P for the ReLU mask)
+  uint32_t* sgth; const uint32_t* sgth_in;   // [Rp][C] (sigmoid, tanh) bf16 pairs of the gate
+  int first, last, relu0, n_mel;
+  float scale;
+};
+
+template <int NT>
+struct FSmem {
+  static constexpr int A_BYTES = 8 * TILE * 16;       // 64 channels x 128 rows
+  static constexpr int B_BYTES = NT * 128;            // NT rows x 64 k
+  static constexpr int STAGE = A_BYTES + B_BYTES;
+  static constexpr int STAGES = NT == 256 ? 4 : 5;
+  static constexpr int TOTAL = STAGES * STAGE + 1024;
+};
+
+template <int MODE>
+__device__ __forceinline__ void fgemm_epilogue(const FArgs& p, uint32_t tmem_row, int rho, int b, int t, bool valid,
+                                               int ntile) {
+  const int L = p.L;
+  if constexpr (MODE == F_IN || MODE == F_SKIP) {
+    // relu(acc + bias): F_IN -> fp32 X0 stream; F_SKIP -> P image
+#pragma unroll 1
+    for (int cg = 0; cg < 8; ++cg) {
+      float v[32];
+      tmem_ld_f32x32(tmem_row + cg * 32, v);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = valid ? fmaxf(v[j] + p.bias[cg * 32 + j], 0.f) : 0.f;
+      if constexpr (MODE == F_IN) store_f32x32(p.fout + (size_t)rho * C + cg * 32, v);
+      else store_img32(p.img, p.Rp, rho, cg * 32, v);
+    }
+  } else if constexpr (MODE == F_COND) {
+    // y = (x + d_l) + (Wc cond + bc_l [+ s_l])   (blocks.py:1166-1168) -> conv input image (zero outside utterances)
+#pragma unroll 1
+    for (int cg = 0; cg < 8; ++cg) {
+      float v[32], x[32];
+      tmem_ld_f32x32(tmem_row + cg * 32, v);
+      if (valid) {
+        load_f32x32(p.fin + (size_t)rho * C + cg * 32, x);
+        const float* dt = p.dtab + (size_t)b * L * C + cg * 32;
+        const float* ct = p.ctab + (size_t)b * L * C + cg * 32;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = (x[j] + dt[j]) + (v[j] + ct[j]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0.f;
+      }
+      store_img32(p.img, p.Rp, rho, cg * 32, v);
+    }
+  } else if constexpr (MODE == F_GATE) {
+    // tile = 128 gate + 128 filter columns of channels [ntile*128, +128): g = sigmoid(a) tanh(f)  (blocks.py:1170-1171)
+#pragma unroll 1
+    for (int cg = 0; cg < 4; ++cg) {
+      const int ch0 = ntile * 128 + cg * 32;
+      float a[32], f[32];
+      tmem_ld_f32x32(tmem_row + cg * 32, a);
+      tmem_ld_f32x32(tmem_row + 128 + cg * 32, f);
+      uint32_t st[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float sg = 1.0f / (1.0f + __expf(-(a[j] + p.bias[ch0 + j])));
+        const float th = tanhf(f[j] + p.bias[C + ch0 + j]);
+        st[j] = pack2(sg, th);
+        a[j] = valid ? sg * th : 0.f;
+      }
+      store_img32(p.img, p.Rp, rho, ch0, a);
+      uint4* sp = reinterpret_cast<uint4*>(p.sgth + (size_t)rho * C + ch0);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) sp[q] = make_uint4(st[q * 4], st[q * 4 + 1], st[q * 4 + 2], st[q * 4 + 3]);
+    }
+  } else if constexpr (MODE == F_OUT) {
+    // tile = 128 x-columns + 128 skip columns: x' = (o_x + (x + d_l)) / sqrt(2), skip sum += o_s   (blocks.py:1173-1176)
+#pragma unroll 1
+    for (int cg = 0; cg < 4; ++cg) {
+      const int ch0 = ntile * 128 + cg * 32;
+      float ox[32], os[32], x[32];
+      tmem_ld_f32x32(tmem_row + cg * 32, ox);
+      tmem_ld_f32x32(tmem_row + 128 + cg * 32, os);
+      if (valid) {
+        load_f32x32(p.fin + (size_t)rho * C + ch0, x);
+        const float* dt = p.dtab + (size_t)b * L * C + ch0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) x[j] = ((ox[j] + p.bias[ch0 + j]) + (x[j] + dt[j])) * RSQRT2;
+        store_f32x32(p.fout + (size_t)rho * C + ch0, x);
+        if (!p.first) load_f32x32(p.fout2 + (size_t)rho * C + ch0, x);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          os[j] = (p.first ? 0.f : x[j]) + (os[j] + p.bias[C + ch0 + j]);
+          if (p.last) os[j] *= p.scale;
+        }
+        store_f32x32(p.fout2 + (size_t)rho * C + ch0, os);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) os[j] = 0.f;
+      }
+      if (p.last) store_img32(p.img, p.Rp, rho, ch0, os);
+    }
+  } else if constexpr (MODE == F_FINAL || MODE == B_DXT) {
+    // [B][n_mel][T] user tensor, coalesced over frames: out = acc (+ bias)
+#pragma unroll 1
+    for (int cg = 0; cg < 4; ++cg) {
+      if (cg * 32 >= p.n_mel) break;
+      float v[32];
+      tmem_ld_f32x32(tmem_row + cg * 32, v);
+      if (valid) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int m = cg * 32 + j;
+          if (m < p.n_mel) p.fout[((size_t)b * p.n_mel + m) * p.T + t] = v[j] + (MODE == F_FINAL ? p.bias[m] : 0.f);
+        }
+      }
+    }
+  } else if constexpr (MODE == B_PMASK || MODE == B_DS) {
+#pragma unroll 1
+    for (int cg = 0; cg < 8; ++cg) {
+      float v[32];
+      tmem_ld_f32x32(tmem_row + cg * 32, v);
+      if constexpr (MODE == B_PMASK) {
+        float a[32];
+        load_img32(p.aux_img, p.Rp, rho, cg * 32, a);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = (valid && a[j] > 0.f) ? v[j] : 0.f;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = valid ? v[j] * p.scale : 0.f;
+      }
+      store_img32(p.img, p.Rp, rho, cg * 32, v);
+    }
+  } else if constexpr (MODE == B_GATE) {
+    // dza = dg th sg (1 - sg), dzb = dg sg (1 - th^2) -> dZ image [gate C | filter C], zero outside utterances
+#pragma unroll 1
+    for (int cg = 0; cg < 8; ++cg) {
+      float dg[32], df[32];
+      tmem_ld_f32x32(tmem_row + cg * 32, dg);
+      const uint4* sp = reinterpret_cast<const uint4*>(p.sgth_in + (size_t)rho * C + cg * 32);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const uint4 u = sp[q];
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int j = q * 4 + e;
+          const float2 s = unpack2(w[e]);
+          const float g = valid ? dg[j] : 0.f;
+          dg[j] = g * s.y * s.x * (1.0f - s.x);
+          df[j] = g * s.x * (1.0f - s.y * s.y);
+        }
+      }
+      store_img32(p.img, p.Rp, rho, cg * 32, dg);
+      store_img32(p.img, p.Rp, rho, C + cg * 32, df);
+    }
+  } else if constexpr (MODE == B_DX) {
+    // dY = acc; dx_l = e_l + dY; e_{l-1} = dx_l / sqrt(2)   (layer 0: ReLU mask of the input projection instead)
+#pragma unroll 1
+    for (int cg = 0; cg < 8; ++cg) {
+      float dy[32], e[32];
+      tmem_ld_f32x32(tmem_row + cg * 32, dy);
+      if (valid) {
+        if (!p.first) load_f32x32(p.fout + (size_t)rho * C + cg * 32, e);
+        float x0[32];
+        if (p.relu0) load_f32x32(p.fin + (size_t)rho * C + cg * 32, x0);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float dx = (p.first ? 0.f : e[j]) + dy[j];
+          e[j] = p.relu0 ? (x0[j] > 0.f ? dx : 0.f) : dx * RSQRT2;
+        }
+        store_f32x32(p.fout + (size_t)rho * C + cg * 32, e);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) { dy[j] = 0.f; e[j] = 0.f; }
+      }
+      store_img32(p.img, p.Rp, rho, cg * 32, dy);
+      store_img32(p.img2, p.Rp, rho, cg * 32, e);
+    }
+  } else if constexpr (MODE == B_COND) {
+    // grad_cond[b][t][:] (+)= dY Wc.  The TMEM load is warp-collective (.sync.aligned): every lane issues it, only the
+    // global accesses are predicated on the row being a real frame.
+    float* o = p.fout + ((size_t)(valid ? b : 0) * p.T + (valid ? t : 0)) * C;
+#pragma unroll 1
+    for (int cg = 0; cg < 8; ++cg) {
+      float v[32], a[32];
+      tmem_ld_f32x32(tmem_row + cg * 32, v);
+      if (valid) {
+        if (!p.first) {
+          load_f32x32(o + cg * 32, a);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += a[j];
+        }
+        store_f32x32(o + cg * 32, v);
+      }
+    }
+  }
+}
+
+template <int NT, int MODE>
+__global__ void __launch_bounds__(192, 1) fgemm_kernel(const FArgs p) {
+  using S = FSmem<NT>;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ __align__(8) uint64_t bar_full[S::STAGES], bar_empty[S::STAGES], bar_acc;
+  __shared__ uint32_t tmem_slot;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tile = blockIdx.x, ntile = blockIdx.y;
+
+  if (warp == 1) tc::tmem_alloc<NT>(&tmem_slot);
+  if (tid == 0) {
+    for (int i = 0; i < S::STAGES; ++i) { tc::mbar_init(&bar_full[i], 1); tc::mbar_init(&bar_empty[i], 1); }
+    tc::mbar_init(&bar_acc, 1);
+    tc::fence_barrier_init();
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+
+  const int per_tap = p.steps0 + p.steps1;
+  const int nsteps = p.taps * per_tap;
+  const uint32_t smem_base = tc::smem_u32(smem);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const bf16* bsrc = p.Bpk + ((size_t)ntile * p.ksteps_b + p.kstep_b0) * (size_t)(NT * 64);
+      for (int s = 0; s < nsteps; ++s) {
+        const int stage = s % S::STAGES, ph = (s / S::STAGES) & 1;
+        tc::mbar_wait_trap(tc::smem_u32(&bar_empty[stage]), ph ^ 1, kTimeout, p.status, 1);
+        const int tap = s / per_tap, j = s - tap * per_tap;
+        const bf16* img = j < p.steps0 ? p.A0 : p.A1;
+        const int ch0 = (j < p.steps0 ? j : j - p.steps0) * 8;
+        const int row = RLEAD + tile * TILE + tap - (p.taps >> 1);
+        const uint32_t sa = smem_base + stage * S::STAGE, sb = sa + S::A_BYTES;
+        const uint32_t fb = tc::smem_u32(&bar_full[stage]);
+        tc::mbar_arrive_expect_tx_addr(fb, S::STAGE);
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          tc::bulk_g2s_addr(sa + c * (TILE * 16), img + ((size_t)(ch0 + c) * p.Rp + row) * 8, TILE * 16, fb);
+        tc::bulk_g2s_addr(sb, bsrc + (size_t)s * (NT * 64), S::B_BYTES, fb);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = tc::make_idesc_bf16(128, NT);
+      for (int s = 0; s < nsteps; ++s) {
+        const int stage = s % S::STAGES, ph = (s / S::STAGES) & 1;
+        tc::mbar_wait_trap(tc::smem_u32(&bar_full[stage]), ph, kTimeout, p.status, 2);
+        tc::tc_fence_after();
+        const uint32_t sa = smem_base + stage * S::STAGE, sb = sa + S::A_BYTES;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint64_t ad = tc::make_smem_desc(sa + k * 2 * (TILE * 16), TILE * 16, 128);
+          const uint64_t bd = tc::make_smem_desc(sb + k * 2 * (NT * 16), NT * 16, 128);
+          tc::umma_bf16(tmem, ad, bd, idesc, (s | k) ? 1u : 0u);
+        }
+        tc::umma_commit(&bar_empty[stage]);
+      }
+      tc::umma_commit(&bar_acc);
+    }
+  } else {
+    tc::mbar_wait_trap(tc::smem_u32(&bar_acc), 0, kTimeout, p.status, 4);
+    tc::tc_fence_after();
+    const int i = (warp & 3) * 32 + lane;                  // TMEM lane = tile row (a warp reaches lanes 32*(warp%4)..)
+    const int rho = RLEAD + tile * TILE + i;
+    const int r = rho - RLEAD, Tg = p.T + 1;
+    const int b = r / Tg, t = r - b * Tg;
+    const bool valid = b < p.B && t < p.T;
+    fgemm_epilogue<MODE>(p, tmem + ((uint32_t)((warp & 3) * 32) << 16), rho, b, t, valid, ntile);
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tc::tmem_dealloc<NT>(tmem);
+}
+
+template <int NT, int MODE>
+int launch_fgemm(const FArgs& a, int ntiles, int n_tiles_n, cudaStream_t s) {
+  static bool configured = false;
+  if (!configured) {
+    MGB_CUDA_CHECK(cudaFuncSetAttribute(fgemm_kernel<NT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        FSmem<NT>::TOTAL));
+    configured = true;
+  }
+  fgemm_kernel<NT, MODE><<<dim3(ntiles, n_tiles_n), 192, FSmem<NT>::TOTAL, s>>>(a);
+  note_launch();
+  if (trace_on()) { char b[64]; snprintf(b, sizeof b, "fgemm<%d, mode %d>", NT, MODE); trace(b, s); }
+  return MGB_OK;
+}
+
+// =====================================================================================================
+// weight-gradient GEMM: part[z][m][n] = sum over the split's frames of P[f][m] * Q[f + sh][ci]
+// =====================================================================================================
+struct WgArgs {
+  const bf16* P0; const bf16* P1; int mtiles0;   // M tile (128 out-channels) x < mtiles0 from P0, else from P1
+  const bf16* Q;
+  int taps, ntiles_per_tap, Kin, Mo, N;
+  float* part;
+  int Rp, nblocks, blocks_per_split;
+  int* status;
+};
+template <int NT>
+struct WSmem {
+  static constexpr int A_BYTES = 16 * TILE * 16;        // 128 channels x 128 frames
+  static constexpr int B_BYTES = (NT / 8) * TILE * 16;  // NT channels x 128 frames
+  static constexpr int STAGE = A_BYTES + B_BYTES;
+  static constexpr int STAGES = 2;
+  static constexpr int TOTAL = STAGES * STAGE + 1024;
+};
+
+template <int NT>
+__global__ void __launch_bounds__(192, 1) wgemm_kernel(const WgArgs p) {
+  using S = WSmem<NT>;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ __align__(8) uint64_t bar_full[S::STAGES], bar_empty[S::STAGES], bar_acc;
+  __shared__ uint32_t tmem_slot;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int mtile = blockIdx.x, ny = blockIdx.y, z = blockIdx.z;
+  const int tap = ny / p.ntiles_per_tap, nt = ny - tap * p.ntiles_per_tap;
+  const int kb0 = z * p.blocks_per_split;
+  const int kb1 = min(p.nblocks, kb0 + p.blocks_per_split);
+  const int nsteps = kb1 - kb0;
+
+  if (warp == 1) tc::tmem_alloc<NT>(&tmem_slot);
+  if (tid == 0) {
+    for (int i = 0; i < S::STAGES; ++i) { tc::mbar_init(&bar_full[i], 1); tc::mbar_init(&bar_empty[i], 1); }
+    tc::mbar_init(&bar_acc, 1);
+    tc::fence_barrier_init();
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  const uint32_t smem_base = tc::smem_u32(smem);
+
+  if (warp == 0) {
+    const bf16* P = mtile < p.mtiles0 ? p.P0 : p.P1;
+    const int mchunk0 = (mtile < p.mtiles0 ? mtile : mtile - p.mtiles0) * 16;
+    const int nchunk0 = nt * (NT / 8);
+    const int sh = tap - (p.taps >> 1);
+    for (int s = 0; s < nsteps; ++s) {
+      const int stage = s % S::STAGES, ph = (s / S::STAGES) & 1;
+      tc::mbar_wait_trap(tc::smem_u32(&bar_empty[stage]), ph ^ 1, kTimeout, p.status, 1);
+      const uint32_t sa = smem_base + stage * S::STAGE, sb = sa + S::A_BYTES;
+      const uint32_t fb = tc::smem_u32(&bar_full[stage]);
+      if (lane == 0) tc::mbar_arrive_expect_tx_addr(fb, S::STAGE);
+      __syncwarp();
+      const int row = RLEAD + (kb0 + s) * TILE;
+      if (lane < 16)
+        tc::bulk_g2s_addr(sa + lane * (TILE * 16), P + ((size_t)(mchunk0 + lane) * p.Rp + row) * 8, TILE * 16, fb);
+      for (int c = lane; c < NT / 8; c += 32)
+        tc::bulk_g2s_addr(sb + c * (TILE * 16), p.Q + ((size_t)(nchunk0 + c) * p.Rp + row + sh) * 8, TILE * 16, fb);
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // both operands MN-major (the frame axis is K): instruction-descriptor bits 15 and 16
+      const uint32_t idesc = tc::make_idesc_bf16(128, NT) | (1u << 15) | (1u << 16);
+      for (int s = 0; s < nsteps; ++s) {
+        const int stage = s % S::STAGES, ph = (s / S::STAGES) & 1;
+        tc::mbar_wait_trap(tc::smem_u32(&bar_full[stage]), ph, kTimeout, p.status, 2);
+        tc::tc_fence_after();
+        const uint32_t sa = smem_base + stage * S::STAGE, sb = sa + S::A_BYTES;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {      // 16 frames per MMA = 256 B along the frame axis
+          const uint64_t ad = tc::make_smem_desc(sa + k * 256, 128, TILE * 16);
+          const uint64_t bd = tc::make_smem_desc(sb + k * 256, 128, TILE * 16);
+          tc::umma_bf16(tmem, ad, bd, idesc, (s | k) ? 1u : 0u);
+        }
+        tc::umma_commit(&bar_empty[stage]);
+      }
+      tc::umma_commit(&bar_acc);
+    }
+  } else {
+    tc::mbar_wait_trap(tc::smem_u32(&bar_acc), 0, kTimeout, p.status, 4);
+    tc::tc_fence_after();
+    const int i = (warp & 3) * 32 + lane;
+    const int m = mtile * 128 + i;
+    const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    float* dst = p.part + ((size_t)z * p.Mo + m) * p.N + (size_t)tap * p.Kin;
+#pragma unroll 1
+    for (int cg = 0; cg < NT / 32; ++cg) {
+      const int ci0 = nt * NT + cg * 32;
+      if (ci0 >= p.Kin) break;                       // uniform over the warp
+      float v[32];
+      if (nsteps > 0) {
+        tmem_ld_f32x32(trow + cg * 32, v);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0.f;
+      }
+      if (m < p.Mo) {
+        if (ci0 + 32 <= p.Kin) {
+          store_f32x32(dst + ci0, v);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (ci0 + j < p.Kin) dst[ci0 + j] = v[j];
+        }
+      }
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tc::tmem_dealloc<NT>(tmem);
+}
+
+struct WPlan { int S, blocks_per_split; };
+WPlan plan_wg(int nblocks, int mtiles, int ntiles) {
+  int S = (148 + mtiles * ntiles - 1) / (mtiles * ntiles);     // about one CTA per SM
+  if (S > nblocks) S = nblocks;
+  if (S < 1) S = 1;
+  const int per = (nblocks + S - 1) / S;
+  return {(nblocks + per - 1) / per, per};
+}
+size_t wg_part_floats(int nblocks, int Mo, int Kin, int taps, int NT) {
+  const int mt = (Mo + 127) / 128, ntl = taps * ((Kin + NT - 1) / NT);
+  return (size_t)plan_wg(nblocks, mt, ntl).S * Mo * Kin * taps;
+}
+
+// dst (flat gradient, state_dict layout) = sum over frames of P^T Q
+template <int NT>
+int launch_wg(const bf16* P0, const bf16* P1, int mtiles0, int Mo, const bf16* Q, int Kin, int taps, const RowSpace& rs,
+              float* part, float* dst, int* status, cudaStream_t s) {
+  static bool configured = false;
+  if (!configured) {
+    MGB_CUDA_CHECK(cudaFuncSetAttribute(wgemm_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, WSmem<NT>::TOTAL));
+    configured = true;
+  }
+  WgArgs a{};
+  a.P0 = P0; a.P1 = P1; a.mtiles0 = mtiles0; a.Q = Q; a.taps = taps; a.ntiles_per_tap = (Kin + NT - 1) / NT;
+  a.Kin = Kin; a.Mo = Mo; a.N = Kin * taps; a.part = part; a.Rp = rs.Rp; a.nblocks = rs.ntiles; a.status = status;
+  const int mt = (Mo + 127) / 128, ntl = taps * a.ntiles_per_tap;
+  const WPlan pl = plan_wg(rs.ntiles, mt, ntl);
+  a.blocks_per_split = pl.blocks_per_split;
+  wgemm_kernel<NT><<<dim3(mt, ntl, pl.S), 192, WSmem<NT>::TOTAL, s>>>(a);
+  if (trace_on()) { char b[96]; snprintf(b, sizeof b, "wgemm<%d> grid %d x %d x %d, Mo %d Kin %d taps %d", NT, mt, ntl, pl.S, Mo, Kin, taps); trace(b, s); }
+  const size_t tot = (size_t)Mo * a.N;
+  wgrad_reduce_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(part, pl.S, Mo, a.N, Kin, taps, dst);
+  note_launch(2);
+  return MGB_OK;
+}
+
+// =====================================================================================================
+// weight packing: fp32 flat parameters -> bf16 K-major tiles [n-tile][k-step][8][NT][8]
+// W_eff[n][tap*Kin + ci] = flat[base + n*sn + ci*sc + tap'*st],  tap' = rev ? taps-1-tap : tap
+// =====================================================================================================
+struct PackDesc {
+  long long dst, base;
+  int N, NT, Kin, Kin_pad, taps, sn, sc, st, rev, perm;
+};
+constexpr int PACK_MAX = 8;
+struct PackArgs { PackDesc d[PACK_MAX]; int n; const float* flat; bf16* out; };
+
+__global__ void __launch_bounds__(256) pack_tiles_kernel(const PackArgs a) {
+  const PackDesc& d = a.d[blockIdx.y];
+  const int ksteps = d.taps * (d.Kin_pad / 64);
+  const int n_tiles = (d.N + d.NT - 1) / d.NT;
+  const long long total = (long long)n_tiles * ksteps * 8 * d.NT;      // 16-byte units
+  for (long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x; u < total; u += (long long)gridDim.x * blockDim.x) {
+    const int nn = (int)(u % d.NT);
+    long long r = u / d.NT;
+    const int kc = (int)(r % 8); r /= 8;
+    const int s = (int)(r % ksteps);
+    const int ntile = (int)(r / ksteps);
+    int n = ntile * d.NT + nn;
+    if (d.perm) {
+      const int half = d.NT / 2;
+      n = nn < half ? ntile * half + nn : d.N / 2 + ntile * half + (nn - half);
+    }
+    const int per_tap = d.Kin_pad / 64;
+    const int tap = s / per_tap, j = s - tap * per_tap;
+    const int tp = d.rev ? d.taps - 1 - tap : tap;
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int ci = j * 64 + kc * 8 + e;
+      v[e] = (n < d.N && ci < d.Kin) ? a.flat[d.base + (long long)n * d.sn + (long long)ci * d.sc + (long long)tp * d.st] : 0.f;
+    }
+    *reinterpret_cast<uint4*>(a.out + d.dst + u * 8) =
+        make_uint4(pack2(v[0], v[1]), pack2(v[2], v[3]), pack2(v[4], v[5]), pack2(v[6], v[7]));
+  }
+}
+
+// =====================================================================================================
+// input packers, margins, column sums
+// =====================================================================================================
+// src [B][M][T] fp32 -> image [nchunks][Rp][8] (channels >= M, separator rows and margins zero)
+__global__ void __launch_bounds__(256) bmt_to_image_kernel(const float* __restrict__ src, bf16* __restrict__ img, int M,
+                                                           int nchunks, int B, int T, int Rp) {
+  const int rho = blockIdx.x * 256 + threadIdx.x, chunk = blockIdx.y;
+  if (rho >= Rp) return;
+  const int r = rho - RLEAD, Tg = T + 1;
+  float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (r >= 0) {
+    const int b = r / Tg, t = r - b * Tg;
+    if (b < B && t < T) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int m = chunk * 8 + e;
+        if (m < M) v[e] = src[((size_t)b * M + m) * T + t];
+      }
+    }
+  }
+  *reinterpret_cast<uint4*>(img + ((size_t)chunk * Rp + rho) * 8) =
+      make_uint4(pack2(v[0], v[1]), pack2(v[2], v[3]), pack2(v[4], v[5]), pack2(v[6], v[7]));
+}
+// cond [B][T][H] fp32 -> image [H/8][Rp][8]
+__global__ void __launch_bounds__(256) bth_to_image_kernel(const float* __restrict__ src, bf16* __restrict__ img, int H,
+                                                           int B, int T, int Rp) {
+  const int rho = blockIdx.x * 8 + (threadIdx.x >> 5), chunk = threadIdx.x & 31;   // H == 256: 32 chunks per row
+  if (rho >= Rp) return;
+  const int r = rho - RLEAD, Tg = T + 1;
+  uint4 u = make_uint4(0u, 0u, 0u, 0u);
+  if (r >= 0) {
+    const int b = r / Tg, t = r - b * Tg;
+    if (b < B && t < T) {
+      const float4* s4 = reinterpret_cast<const float4*>(src + ((size_t)b * T + t) * H + chunk * 8);
+      const float4 a = __ldg(s4), c = __ldg(s4 + 1);
+      u = make_uint4(pack2(a.x, a.y), pack2(a.z, a.w), pack2(c.x, c.y), pack2(c.z, c.w));
+    }
+  }
+  *reinterpret_cast<uint4*>(img + ((size_t)chunk * Rp + rho) * 8) = u;
+}
+// zero the RLEAD leading and 8 trailing rows of `nimg` images of `nchunks` chunks each (stride img_stride elements)
+__global__ void zero_margins_kernel(bf16* img, size_t img_stride, int nchunks, int Rp) {
+  const int chunk = blockIdx.x, which = blockIdx.y, i = threadIdx.x;   // 16 threads: 8 lead + 8 trail rows
+  const int rho = i < 8 ? i : Rp - 16 + i;
+  *reinterpret_cast<uint4*>(img + (size_t)which * img_stride + ((size_t)chunk * Rp + rho) * 8) = make_uint4(0u, 0u, 0u, 0u);
+}
+// out[b][chunk*8 + e] = sum_t img[chunk][row(b,t)][e]
+__global__ void __launch_bounds__(256) img_colsum_kernel(const bf16* __restrict__ img, int Rp, int T, float* __restrict__ out,
+                                                         int ldo) {
+  __shared__ float red[256][9];
+  const int chunk = blockIdx.x, b = blockIdx.y;
+  const bf16* base = img + ((size_t)chunk * Rp + RLEAD + (size_t)b * (T + 1)) * 8;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int t = threadIdx.x; t < T; t += 256) {
+    const uint4 u = *reinterpret_cast<const uint4*>(base + (size_t)t * 8);
+    const float2 a = unpack2(u.x), c = unpack2(u.y), d = unpack2(u.z), e = unpack2(u.w);
+    acc[0] += a.x; acc[1] += a.y; acc[2] += c.x; acc[3] += c.y; acc[4] += d.x; acc[5] += d.y; acc[6] += e.x; acc[7] += e.y;
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) red[threadIdx.x][e] = acc[e];
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    float s = 0.f;
+    for (int k = 0; k < 256; ++k) s += red[k][threadIdx.x];
+    out[(size_t)b * ldo + chunk * 8 + threadIdx.x] = s;
+  }
+}
+void launch_colsum_img(const bf16* img, int nchunks, const RowSpace& rs, int B, float* out, int ldo, cudaStream_t s) {
+  img_colsum_kernel<<<dim3(nchunks, B), 256, 0, s>>>(img, rs.Rp, rs.T, out, ldo);
+  note_launch();
+  trace("img_colsum", s);
+}
+
+// =====================================================================================================
+// buffers
+// =====================================================================================================
+struct PackedB16 {   // offsets in bf16 elements into the packed-weight buffer (re-packed every step)
+  size_t in_f, skip_f, out_f;                       // forward
+  size_t out_b, skip_b, in_b;                       // backward (transposed)
+  size_t layer0, layer_stride;
+  size_t r_cond_f, r_conv_f, r_oproj_f, r_oproj_b, r_conv_b, r_cond_b;
+  size_t total;
+};
+PackedB16 packed16_layout(const mgb_model_dims& d) {
+  PackedB16 o{};
+  size_t p = 0;
+  auto take = [&](size_t n) { size_t r = p; p += n; return r; };
+  o.in_f = take((size_t)256 * 128);        // N=256, K=80 -> 128
+  o.skip_f = take((size_t)256 * 256);
+  o.out_f = take((size_t)128 * 256);       // N=80 -> 128
+  o.out_b = take((size_t)256 * 128);       // N=256 (channels), K=80 -> 128
+  o.skip_b = take((size_t)256 * 256);
+  o.in_b = take((size_t)128 * 256);        // N=80 -> 128, K=256
+  o.layer0 = p;
+  size_t q = 0;
+  auto tk = [&](size_t n) { size_t r = q; q += n; return r; };
+  o.r_cond_f = tk((size_t)256 * 256);
+  o.r_conv_f = tk((size_t)512 * 768);
+  o.r_oproj_f = tk((size_t)512 * 256);
+  o.r_oproj_b = tk((size_t)256 * 512);
+  o.r_conv_b = tk((size_t)256 * 1536);
+  o.r_cond_b = tk((size_t)256 * 256);
+  o.layer_stride = q;
+  p += q * d.layers;
+  o.total = p;
+  return o;
+}
+
+struct Saved16 {     // byte offsets into the activation stash
+  size_t xt, cond, X0, layer0, layer_stride, rY, rG, rSGTH, Sn, P, dvec, h, wpk, total;
+};
+Saved16 saved16_layout(const mgb_model_dims& d, int B, int T) {
+  const RowSpace rs = row_space(B, T);
+  const size_t Rp = rs.Rp;
+  Saved16 o{};
+  size_t p = 0;
+  auto take = [&](size_t n) { size_t r = p; p += align_up(n, 256); return r; };
+  o.xt = take(16 * Rp * 16);
+  o.cond = take(32 * Rp * 16);
+  o.X0 = take(Rp * C * 4);
+  o.layer0 = p;
+  {
+    size_t q = 0;
+    auto tk = [&](size_t n) { size_t r = q; q += align_up(n, 256); return r; };
+    o.rY = tk(32 * Rp * 16); o.rG = tk(32 * Rp * 16); o.rSGTH = tk(Rp * C * 4);
+    o.layer_stride = q;
+  }
+  p += o.layer_stride * d.layers;
+  o.Sn = take(32 * Rp * 16);
+  o.P = take(32 * Rp * 16);
+  o.dvec = take((size_t)B * C * 4);
+  o.h = take((size_t)B * 4 * C * 4);
+  o.wpk = take(packed16_layout(d).total * 2);     // the step's bf16 weight tiles (the backward reuses them)
+  o.total = p;
+  return o;
+}
+
+struct Work16 {      // byte offsets into the workspace
+  size_t status, X, S, dtab, ctab, dout, dPre, dS, E, Eimg, dZ, dY, part, usumE, usumZ, usumY, usumS, usumT, ddvec,
+      dspk, dpre, total;
+};
+Work16 work16_layout(const mgb_model_dims& d, int B, int T) {
+  const RowSpace rs = row_space(B, T);
+  const size_t Rp = rs.Rp;
+  Work16 w{};
+  size_t p = 0;
+  auto take = [&](size_t n) { size_t r = p; p += align_up(n, 256); return r; };
+  w.status = take(256);
+  w.X = take(Rp * C * 4);
+  w.S = take(Rp * C * 4);
+  w.dtab = take((size_t)B * d.layers * C * 4);
+  w.ctab = take((size_t)B * d.layers * C * 4);
+  w.dout = take(16 * Rp * 16);
+  w.dPre = take(32 * Rp * 16);
+  w.dS = take(32 * Rp * 16);
+  w.E = take(Rp * C * 4);
+  w.Eimg = take(32 * Rp * 16);
+  w.dZ = take(64 * Rp * 16);
+  w.dY = take(32 * Rp * 16);
+  size_t part = wg_part_floats(rs.ntiles, 512, 256, 3, 256);
+  auto mx = [&](size_t v) { if (v > part) part = v; };
+  mx(wg_part_floats(rs.ntiles, 512, 256, 1, 256));
+  mx(wg_part_floats(rs.ntiles, 256, 256, 1, 256));
+  mx(wg_part_floats(rs.ntiles, 80, 256, 1, 256));
+  mx(wg_part_floats(rs.ntiles, 256, 80, 1, 128));
+  w.part = take(part * 4);
+  w.usumE = take((size_t)B * C * 4);
+  w.usumZ = take((size_t)B * 2 * C * 4);
+  w.usumY = take((size_t)B * C * 4);
+  w.usumS = take((size_t)B * C * 4);
+  w.usumT = take((size_t)B * C * 4);
+  w.ddvec = take((size_t)B * C * 4);
+  w.dspk = take((size_t)B * C * 4);
+  w.dpre = take((size_t)B * 4 * C * 4);
+  w.total = p;
+  return w;
+}
+
+int pack_step_weights(const mgb_model_dims& d, const float* flat, bf16* out, cudaStream_t s) {
+  const FlatOffsets f = flat_offsets(d);
+  const PackedB16 o = packed16_layout(d);
+  const int M = d.n_mel;
+  auto desc = [](size_t dst, size_t base, int N, int NT, int Kin, int taps, int sn, int sc, int st, int rev, int perm) {
+    PackDesc p{};
+    p.dst = (long long)dst; p.base = (long long)base; p.N = N; p.NT = NT; p.Kin = Kin; p.Kin_pad = (Kin + 63) / 64 * 64;
+    p.taps = taps; p.sn = sn; p.sc = sc; p.st = st; p.rev = rev; p.perm = perm;
+    return p;
+  };
+  auto run = [&](PackArgs& a) {
+    a.flat = flat; a.out = out;
+    pack_tiles_kernel<<<dim3(96, a.n), 256, 0, s>>>(a);
+    note_launch();
+  };
+  {
+    PackArgs a{};
+    a.n = 6;
+    a.d[0] = desc(o.in_f, f.in_w, C, 256, M, 1, M, 1, 0, 0, 0);          // W[c][m]
+    a.d[1] = desc(o.skip_f, f.skip_w, C, 256, C, 1, C, 1, 0, 0, 0);
+    a.d[2] = desc(o.out_f, f.out_w, M, 128, C, 1, C, 1, 0, 0, 0);        // W[m][c]
+    a.d[3] = desc(o.out_b, f.out_w, C, 256, M, 1, 1, C, 0, 0, 0);        // W_eff[n=c][k=m] = Wout[m][c]
+    a.d[4] = desc(o.skip_b, f.skip_w, C, 256, C, 1, 1, C, 0, 0, 0);      // Wsk^T
+    a.d[5] = desc(o.in_b, f.in_w, M, 128, C, 1, 1, M, 0, 0, 0);          // W_eff[n=m][k=c] = Win[c][m]
+    run(a);
+  }
+  for (int l = 0; l < d.layers; ++l) {
+    const size_t fl = f.layer0 + (size_t)l * f.layer_stride, ol = o.layer0 + (size_t)l * o.layer_stride;
+    PackArgs a{};
+    a.n = 6;
+    a.d[0] = desc(ol + o.r_cond_f, fl + f.rel.cproj_w, C, 256, C, 1, C, 1, 0, 0, 0);
+    a.d[1] = desc(ol + o.r_conv_f, fl + f.rel.conv_w, 2 * C, 256, C, 3, 3 * C, 3, 1, 0, 1);      // W3[co][ci][tap], gate|filter tiles
+    a.d[2] = desc(ol + o.r_oproj_f, fl + f.rel.oproj_w, 2 * C, 256, C, 1, C, 1, 0, 0, 1);        // Wo[co][ci], x|skip tiles
+    a.d[3] = desc(ol + o.r_oproj_b, fl + f.rel.oproj_w, C, 256, 2 * C, 1, 1, C, 0, 0, 0);        // W_eff[n=ci][k=co]
+    a.d[4] = desc(ol + o.r_conv_b, fl + f.rel.conv_w, C, 256, 2 * C, 3, 3, 3 * C, 1, 1, 0);      // W_eff[n=ci][tap', co] = W3[co][ci][2-tap']
+    a.d[5] = desc(ol + o.r_cond_b, fl + f.rel.cproj_w, C, 256, C, 1, 1, C, 0, 0, 0);             // Wc^T
+    run(a);
+  }
+  MGB_LAUNCH_CHECK();
+  return MGB_OK;
+}
+
+}  // namespace
+
+size_t bf16_train_saved_bytes(const mgb_model_dims& d, int B, int T) { return saved16_layout(d, B, T).total; }
+size_t bf16_train_workspace_bytes(const mgb_model_dims& d, int B, int T) { return work16_layout(d, B, T).total; }
+
+int bf16_train_forward(const mgb_model_dims& d, const void* packed_fp32, const float* flat, const float* x, const int64_t* t,
+                       const float* cond, const float* spk, float* out, void* saved, int B, int T, void* ws, cudaStream_t s) {
+  const RowSpace rs = row_space(B, T);
+  const Saved16 sv = saved16_layout(d, B, T);
+  const Work16 w = work16_layout(d, B, T);
+  const PackedB16 o = packed16_layout(d);
+  const FlatOffsets f = flat_offsets(d);
+  uint8_t* SV = static_cast<uint8_t*>(saved);
+  uint8_t* W = static_cast<uint8_t*>(ws);
+  const int L = d.layers, M = d.n_mel;
+  auto img = [](uint8_t* p) { return reinterpret_cast<bf16*>(p); };
+  auto f32 = [](uint8_t* p) { return reinterpret_cast<float*>(p); };
+  int* status = reinterpret_cast<int*>(W + w.status);
+  bf16* wpk = img(SV + sv.wpk);
+
+  MGB_CUDA_CHECK(cudaMemsetAsync(status, 0, sizeof(int), s));
+  if (int rc = pack_step_weights(d, flat, wpk, s)) return rc;
+  if (int rc = fp32_step_tables(d, packed_fp32, t, spk, B, f32(SV + sv.dvec), f32(SV + sv.h), f32(W + w.dtab),
+                                f32(W + w.ctab), s)) return rc;
+  bmt_to_image_kernel<<<dim3((rs.Rp + 255) / 256, 16), 256, 0, s>>>(x, img(SV + sv.xt), M, 16, B, T, rs.Rp);
+  bth_to_image_kernel<<<(rs.Rp + 7) / 8, 256, 0, s>>>(cond, img(SV + sv.cond), C, B, T, rs.Rp);
+  zero_margins_kernel<<<dim3(32, L), 16, 0, s>>>(img(SV + sv.layer0 + sv.rY), sv.layer_stride / 2, 32, rs.Rp);
+  note_launch(3);
+
+  FArgs base{};
+  base.Rp = rs.Rp; base.B = B; base.T = T; base.L = L; base.status = status; base.taps = 1; base.n_mel = M;
+  {
+    FArgs a = base;                                     // input projection + ReLU (modules.py:429-431)
+    a.A0 = img(SV + sv.xt); a.steps0 = 2; a.Bpk = wpk + o.in_f; a.ksteps_b = 2;
+    a.bias = flat + f.in_b; a.fout = f32(SV + sv.X0);
+    if (int rc = launch_fgemm<256, F_IN>(a, rs.ntiles, 1, s)) return rc;
+  }
+  for (int l = 0; l < L; ++l) {
+    uint8_t* sl = SV + sv.layer0 + (size_t)l * sv.layer_stride;
+    const bf16* wl = wpk + o.layer0 + (size_t)l * o.layer_stride;
+    const float* fl = flat + f.layer0 + (size_t)l * f.layer_stride;
+    const float* xin = l == 0 ? f32(SV + sv.X0) : f32(W + w.X);
+    {
+      FArgs a = base;                                   // conditioner projection, y = (x + d) + (c + bc [+ s])
+      a.A0 = img(SV + sv.cond); a.steps0 = 4; a.Bpk = wl + o.r_cond_f; a.ksteps_b = 4;
+      a.fin = xin; a.dtab = f32(W + w.dtab) + (size_t)l * C; a.ctab = f32(W + w.ctab) + (size_t)l * C; a.img = img(sl + sv.rY);
+      if (int rc = launch_fgemm<256, F_COND>(a, rs.ntiles, 1, s)) return rc;
+    }
+    {
+      FArgs a = base;                                   // k=3 conv + gate
+      a.A0 = img(sl + sv.rY); a.steps0 = 4; a.taps = 3; a.Bpk = wl + o.r_conv_f; a.ksteps_b = 12;
+      a.bias = fl + f.rel.conv_b; a.img = img(sl + sv.rG); a.sgth = reinterpret_cast<uint32_t*>(sl + sv.rSGTH);
+      if (int rc = launch_fgemm<256, F_GATE>(a, rs.ntiles, 2, s)) return rc;
+    }
+    {
+      FArgs a = base;                                   // output projection, residual + skip
+      a.A0 = img(sl + sv.rG); a.steps0 = 4; a.Bpk = wl + o.r_oproj_f; a.ksteps_b = 4;
+      a.bias = fl + f.rel.oproj_b; a.fin = xin; a.fout = f32(W + w.X); a.fout2 = f32(W + w.S);
+      a.dtab = f32(W + w.dtab) + (size_t)l * C; a.first = l == 0; a.last = l == L - 1;
+      a.scale = 1.0f / sqrtf((float)L); a.img = img(SV + sv.Sn);
+      if (int rc = launch_fgemm<256, F_OUT>(a, rs.ntiles, 2, s)) return rc;
+    }
+  }
+  {
+    FArgs a = base;                                     // skip projection + ReLU
+    a.A0 = img(SV + sv.Sn); a.steps0 = 4; a.Bpk = wpk + o.skip_f; a.ksteps_b = 4;
+    a.bias = flat + f.skip_b; a.img = img(SV + sv.P);
+    if (int rc = launch_fgemm<256, F_SKIP>(a, rs.ntiles, 1, s)) return rc;
+  }
+  {
+    FArgs a = base;                                     // output projection -> [B][n_mel][T]
+    a.A0 = img(SV + sv.P); a.steps0 = 4; a.Bpk = wpk + o.out_f; a.ksteps_b = 4;
+    a.bias = flat + f.out_b; a.fout = out;
+    if (int rc = launch_fgemm<128, F_FINAL>(a, rs.ntiles, 1, s)) return rc;
+  }
+  MGB_LAUNCH_CHECK();
+  return MGB_OK;
+}
+
+int bf16_train_backward(const mgb_model_dims& d, const float* flat, const void* saved, const int64_t* t, const float* cond,
+                        const float* spk, const float* grad_out, float* grad_flat, float* grad_cond, float* grad_spk,
+                        float* grad_x, int B, int T, int seg_begin, int seg_end, void* ws, cudaStream_t s) {
+  (void)cond;
+  const RowSpace rs = row_space(B, T);
+  const Saved16 sv = saved16_layout(d, B, T);
+  const Work16 w = work16_layout(d, B, T);
+  const PackedB16 o = packed16_layout(d);
+  const FlatOffsets f = flat_offsets(d);
+  const uint8_t* SV = static_cast<const uint8_t*>(saved);
+  uint8_t* W = static_cast<uint8_t*>(ws);
+  const int L = d.layers, M = d.n_mel, H = d.d_encoder;
+  auto img = [](uint8_t* p) { return reinterpret_cast<bf16*>(p); };
+  auto cimg = [](const uint8_t* p) { return reinterpret_cast<const bf16*>(p); };
+  auto f32 = [](uint8_t* p) { return reinterpret_cast<float*>(p); };
+  auto cf32 = [](const uint8_t* p) { return reinterpret_cast<const float*>(p); };
+  int* status = reinterpret_cast<int*>(W + w.status);
+  const bf16* wpk = cimg(SV + sv.wpk);
+  float* part = f32(W + w.part);
+
+  FArgs base{};
+  base.Rp = rs.Rp; base.B = B; base.T = T; base.L = L; base.status = status; base.taps = 1; base.n_mel = M;
+
+  for (int seg = seg_begin; seg < seg_end; ++seg) {
+    if (seg == 0) {
+      bmt_to_image_kernel<<<dim3((rs.Rp + 255) / 256, 16), 256, 0, s>>>(grad_out, img(W + w.dout), M, 16, B, T, rs.Rp);
+      zero_margins_kernel<<<dim3(64, 1), 16, 0, s>>>(img(W + w.dZ), 0, 64, rs.Rp);
+      note_launch(2);
+      // dWout = dout^T P, dbout
+      if (int rc = launch_wg<256>(cimg(W + w.dout), nullptr, 1, M, cimg(SV + sv.P), C, 1, rs, part, grad_flat + f.out_w,
+                                  status, s)) return rc;
+      launch_colsum_img(cimg(W + w.dout), 10, rs, B, f32(W + w.usumT), C, s);
+      bias_from_usum_kernel<<<1, 128, 0, s>>>(f32(W + w.usumT), B, M, C, grad_flat + f.out_b);
+      note_launch();
+      {
+        FArgs a = base;                                 // dPre = (dout Wout) masked by P > 0
+        a.A0 = cimg(W + w.dout); a.steps0 = 2; a.Bpk = wpk + o.out_b; a.ksteps_b = 2;
+        a.aux_img = cimg(SV + sv.P); a.img = img(W + w.dPre);
+        if (int rc = launch_fgemm<256, B_PMASK>(a, rs.ntiles, 1, s)) return rc;
+      }
+      if (int rc = launch_wg<256>(cimg(W + w.dPre), nullptr, 2, C, cimg(SV + sv.Sn), C, 1, rs, part, grad_flat + f.skip_w,
+                                  status, s)) return rc;
+      launch_colsum_img(cimg(W + w.dPre), 32, rs, B, f32(W + w.usumT), C, s);
+      bias_from_usum_kernel<<<2, 128, 0, s>>>(f32(W + w.usumT), B, C, C, grad_flat + f.skip_b);
+      note_launch();
+      {
+        FArgs a = base;                                 // dS = (dPre Wsk) / sqrt(L)
+        a.A0 = cimg(W + w.dPre); a.steps0 = 4; a.Bpk = wpk + o.skip_b; a.ksteps_b = 4;
+        a.scale = 1.0f / sqrtf((float)L); a.img = img(W + w.dS);
+        if (int rc = launch_fgemm<256, B_DS>(a, rs.ntiles, 1, s)) return rc;
+      }
+      launch_colsum_img(cimg(W + w.dS), 32, rs, B, f32(W + w.usumS), C, s);
+    } else if (seg <= L) {
+      const int l = L - seg;
+      const bool top = (l == L - 1);
+      const uint8_t* sl = SV + sv.layer0 + (size_t)l * sv.layer_stride;
+      const bf16* wl = wpk + o.layer0 + (size_t)l * o.layer_stride;
+      const float* fl = flat + f.layer0 + (size_t)l * f.layer_stride;
+      float* gl = grad_flat + f.layer0 + (size_t)l * f.layer_stride;
+      {
+        FArgs a = base;                                 // dG = [e | dS] Wo; gate backward -> dZ
+        if (top) { a.A0 = cimg(W + w.dS); a.steps0 = 4; a.kstep_b0 = 4; }
+        else { a.A0 = cimg(W + w.Eimg); a.steps0 = 4; a.A1 = cimg(W + w.dS); a.steps1 = 4; }
+        a.Bpk = wl + o.r_oproj_b; a.ksteps_b = 8;
+        a.sgth_in = reinterpret_cast<const uint32_t*>(sl + sv.rSGTH); a.img = img(W + w.dZ);
+        if (int rc = launch_fgemm<256, B_GATE>(a, rs.ntiles, 1, s)) return rc;
+      }
+      if (top) {                                        // dWo = [e | dS]^T g  (top block: e = 0)
+        MGB_CUDA_CHECK(cudaMemsetAsync(gl + f.rel.oproj_w, 0, sizeof(float) * (size_t)C * C, s));
+        if (int rc = launch_wg<256>(cimg(W + w.dS), nullptr, 2, C, cimg(sl + sv.rG), C, 1, rs, part,
+                                    gl + f.rel.oproj_w + (size_t)C * C, status, s)) return rc;
+      } else {
+        if (int rc = launch_wg<256>(cimg(W + w.Eimg), cimg(W + w.dS), 2, 2 * C, cimg(sl + sv.rG), C, 1, rs, part,
+                                    gl + f.rel.oproj_w, status, s)) return rc;
+        launch_colsum_img(cimg(W + w.Eimg), 32, rs, B, f32(W + w.usumE), C, s);
+      }
+      launch_colsum_img(cimg(W + w.dZ), 64, rs, B, f32(W + w.usumZ), 2 * C, s);
+      {
+        FArgs a = base;                                 // dY = conv3^T(dZ); dx = e + dY; e' = dx / sqrt(2)
+        a.A0 = cimg(W + w.dZ); a.steps0 = 8; a.taps = 3; a.Bpk = wl + o.r_conv_b; a.ksteps_b = 24;
+        a.fout = f32(W + w.E); a.fin = cf32(SV + sv.X0); a.img = img(W + w.dY); a.img2 = img(W + w.Eimg);
+        a.first = top ? 1 : 0; a.relu0 = (l == 0) ? 1 : 0;
+        if (int rc = launch_fgemm<256, B_DX>(a, rs.ntiles, 1, s)) return rc;
+      }
+      if (int rc = launch_wg<256>(cimg(W + w.dZ), nullptr, 4, 2 * C, cimg(sl + sv.rY), C, 3, rs, part, gl + f.rel.conv_w,
+                                  status, s)) return rc;
+      if (int rc = launch_wg<256>(cimg(W + w.dY), nullptr, 2, C, cimg(SV + sv.cond), H, 1, rs, part, gl + f.rel.cproj_w,
+                                  status, s)) return rc;
+      if (grad_cond) {
+        FArgs a = base;                                 // dCond (+)= dY Wc
+        a.A0 = cimg(W + w.dY); a.steps0 = 4; a.Bpk = wl + o.r_cond_b; a.ksteps_b = 4;
+        a.fout = grad_cond; a.first = top ? 1 : 0;
+        if (int rc = launch_fgemm<256, B_COND>(a, rs.ntiles, 1, s)) return rc;
+      }
+      launch_colsum_img(cimg(W + w.dY), 32, rs, B, f32(W + w.usumY), C, s);
+      LayerSmallArgs q{};
+      q.usumE = top ? nullptr : f32(W + w.usumE); q.usumZ = f32(W + w.usumZ); q.usumY = f32(W + w.usumY);
+      q.usumS = f32(W + w.usumS); q.dvec = cf32(SV + sv.dvec); q.spk = d.multi_speaker ? spk : nullptr;
+      q.Wd = fl + f.rel.dproj_w; q.Ws = d.multi_speaker ? fl + f.rel.sproj_w : nullptr;
+      q.g_conv_b = gl + f.rel.conv_b; q.g_oproj_b = gl + f.rel.oproj_b; q.g_cproj_b = gl + f.rel.cproj_b;
+      q.g_dproj_w = gl + f.rel.dproj_w; q.g_sproj_w = d.multi_speaker ? gl + f.rel.sproj_w : nullptr;
+      q.ddvec = f32(W + w.ddvec); q.dspk = d.multi_speaker ? f32(W + w.dspk) : nullptr;
+      q.B = B; q.C = C; q.H = H; q.first = top ? 1 : 0;
+      layer_small_kernel<<<C + B + 1, 256, 0, s>>>(q);
+      note_launch();
+    } else if (seg == L + 1) {
+      // head: E / Eimg hold the ReLU-masked gradient of the input projection's pre-activation
+      if (int rc = launch_wg<128>(cimg(W + w.Eimg), nullptr, 2, C, cimg(SV + sv.xt), M, 1, rs, part, grad_flat + f.in_w,
+                                  status, s)) return rc;
+      launch_colsum_img(cimg(W + w.Eimg), 32, rs, B, f32(W + w.usumT), C, s);
+      bias_from_usum_kernel<<<2, 128, 0, s>>>(f32(W + w.usumT), B, C, C, grad_flat + f.in_b);
+      note_launch();
+      if (grad_x) {
+        FArgs a = base;                                 // d loss / d mel = dPre0 Win
+        a.A0 = cimg(W + w.Eimg); a.steps0 = 4; a.Bpk = wpk + o.in_b; a.ksteps_b = 4; a.fout = grad_x;
+        if (int rc = launch_fgemm<128, B_DXT>(a, rs.ntiles, 1, s)) return rc;
+      }
+      mlp_bwd_w2_kernel<<<C, 256, 0, s>>>(f32(W + w.ddvec), cf32(SV + sv.h), grad_flat + f.mlp2_w, B, C);
+      mlp_bwd_pre_kernel<<<dim3(4 * C / 256, B), 256, 0, s>>>(t, f32(W + w.ddvec), flat + f.mlp0_w, flat + f.mlp2_w,
+                                                             f32(W + w.dpre), C);
+      mlp_bwd_w0_kernel<<<4 * C, C, 0, s>>>(t, f32(W + w.dpre), grad_flat + f.mlp0_w, B, C);
+      note_launch(3);
+      if (grad_spk && d.multi_speaker)
+        MGB_CUDA_CHECK(cudaMemcpyAsync(grad_spk, W + w.dspk, sizeof(float) * (size_t)B * H, cudaMemcpyDeviceToDevice, s));
+    }
+  }
+  MGB_LAUNCH_CHECK();
+  return MGB_OK;
+}
+
+size_t bf16_train_status_offset(const mgb_model_dims& d, int B, int T) { return work16_layout(d, B, T).status; }
+
+}  // namespace mgb

@@ -1,0 +1,148 @@
+// Small kernels shared by the fp32 and bf16 training paths (train_fp32.cu, train_bf16.cu): the fixed-order reduction of
+// split weight-gradient partials, the per-layer bias / projection terms, and the step-MLP backward.  All fp32.
+#pragma once
+
+#include "common.cuh"
+
+namespace mgb {
+namespace trainsmall {
+
+// dst[(m*Kin + ci)*taps + tap] = sum_s part[s][m][tap*Kin + ci]   (state_dict layout [out][in][k])
+static __global__ void wgrad_reduce_kernel(const float* __restrict__ part, int S, int Mo, int N, int Kin, int taps,
+                                    float* __restrict__ dst) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t tot = (size_t)Mo * N;
+  if (i >= tot) return;
+  float s = 0.f;
+  for (int k = 0; k < S; ++k) s += part[(size_t)k * tot + i];
+  const int m = (int)(i / N), n = (int)(i - (size_t)m * N);
+  const int tap = n / Kin, ci = n - tap * Kin;
+  dst[((size_t)m * Kin + ci) * taps + tap] = s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-layer small terms (B rows each): bias gradients, diffusion/speaker projection gradients, and the
+// accumulation of d loss / d dvec and d loss / d spk over layers.
+struct LayerSmallArgs {
+  const float* usumE;   // [B][C]   per-utterance column sums of e_l (nullptr for the top block: zero)
+  const float* usumZ;   // [B][2C]  of dZ
+  const float* usumY;   // [B][C]   of dY
+  const float* usumS;   // [B][C]   of dS
+  const float* dvec;    // [B][C]
+  const float* spk;     // [B][H] or nullptr
+  const float* Wd;      // [C][C]   diffusion_projection.linear.weight  (raw [out][in])
+  const float* Ws;      // [C][H]   speaker_projection.linear.weight or nullptr
+  float *g_conv_b, *g_oproj_b, *g_cproj_b, *g_dproj_w, *g_sproj_w;
+  float* ddvec;         // [B][C]  accumulated over layers
+  float* dspk;          // [B][H]  accumulated over layers (or nullptr)
+  int B, C, H, first;   // first: this is the first layer processed (overwrite the accumulators)
+};
+// grid: C blocks (row co of dWd / dWs) + B blocks (ddvec / dspk rows) + 1 block (biases); 256 threads, C == H == 256
+static __global__ void __launch_bounds__(256) layer_small_kernel(const LayerSmallArgs p) {
+  __shared__ float dd[256];
+  const int C = p.C, tid = threadIdx.x;
+  const int blk = blockIdx.x;
+  if (blk < C) {
+    // dWd[co][ci] = sum_b dd[b][co] * dvec[b][ci],  dd = usumE + usumY ; dWs[co][h] = sum_b usumY[b][co] * spk[b][h]
+    const int co = blk;
+    float gd = 0.f, gs = 0.f;
+    for (int b = 0; b < p.B; ++b) {
+      const float y = p.usumY[(size_t)b * C + co];
+      const float e = p.usumE ? p.usumE[(size_t)b * C + co] : 0.f;
+      gd = fmaf(e + y, p.dvec[(size_t)b * C + tid], gd);
+      if (p.Ws) gs = fmaf(y, p.spk[(size_t)b * p.H + tid], gs);
+    }
+    p.g_dproj_w[(size_t)co * C + tid] = gd;
+    if (p.Ws) p.g_sproj_w[(size_t)co * p.H + tid] = gs;
+  } else if (blk < C + p.B) {
+    // ddvec[b][ci] += sum_co dd[b][co] * Wd[co][ci] ; dspk[b][h] += sum_co usumY[b][co] * Ws[co][h]
+    const int b = blk - C;
+    dd[tid] = (p.usumE ? p.usumE[(size_t)b * C + tid] : 0.f) + p.usumY[(size_t)b * C + tid];
+    __syncthreads();
+    float s = 0.f;
+    for (int co = 0; co < C; ++co) s = fmaf(dd[co], p.Wd[(size_t)co * C + tid], s);
+    p.ddvec[(size_t)b * C + tid] = (p.first ? 0.f : p.ddvec[(size_t)b * C + tid]) + s;
+    if (p.Ws) {
+      float q = 0.f;
+      for (int co = 0; co < C; ++co) q = fmaf(p.usumY[(size_t)b * C + co], p.Ws[(size_t)co * p.H + tid], q);
+      p.dspk[(size_t)b * p.H + tid] = (p.first ? 0.f : p.dspk[(size_t)b * p.H + tid]) + q;
+    }
+  } else {
+    // conv bias [2C], output-projection bias [x-half from e_l | skip half from dS], conditioner bias [C]
+    for (int c = tid; c < 2 * C; c += blockDim.x) {
+      float z = 0.f;
+      for (int b = 0; b < p.B; ++b) z += p.usumZ[(size_t)b * 2 * C + c];
+      p.g_conv_b[c] = z;
+    }
+    for (int c = tid; c < C; c += blockDim.x) {
+      float e = 0.f, sk = 0.f, y = 0.f;
+      for (int b = 0; b < p.B; ++b) {
+        if (p.usumE) e += p.usumE[(size_t)b * C + c];
+        sk += p.usumS[(size_t)b * C + c];
+        y += p.usumY[(size_t)b * C + c];
+      }
+      p.g_oproj_b[c] = e;
+      p.g_oproj_b[C + c] = sk;
+      p.g_cproj_b[c] = y;
+    }
+  }
+}
+
+// out[c] = sum_b usum[b][c]
+static __global__ void bias_from_usum_kernel(const float* __restrict__ usum, int B, int n, int ld, float* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n) return;
+  float s = 0.f;
+  for (int b = 0; b < B; ++b) s += usum[(size_t)b * ld + c];
+  out[c] = s;
+}
+
+// ---- step MLP backward (modules.py:433-434, blocks.py:894-913); all operands are B rows ----------
+// phase 0: dW2[c][j] = sum_b ddvec[b][c] * h[b][j]                    grid C blocks x 256 threads (j strided)
+// phase 1: dpre[b][j] = (sum_c ddvec[b][c] * W2[c][j]) * mish'(pre[b][j]),  pre = W0 emb(t_b)      grid (4C/256, B)
+// phase 2: dW0[j][k] = sum_b dpre[b][j] * emb[b][k]                   grid 4C blocks x C threads
+static __device__ __forceinline__ float emb_value(float tv, int k, int C) {
+  const int halfd = C / 2;
+  const float scale = (float)(9.210340371976184 / (double)(halfd - 1));
+  const int kk = k < halfd ? k : k - halfd;
+  const float a = tv * expf((float)kk * -scale);
+  return k < halfd ? sinf(a) : cosf(a);
+}
+static __global__ void __launch_bounds__(256) mlp_bwd_w2_kernel(const float* __restrict__ ddvec, const float* __restrict__ h,
+                                                         float* __restrict__ gW2, int B, int C) {
+  const int c = blockIdx.x;
+  for (int j = threadIdx.x; j < 4 * C; j += blockDim.x) {
+    float s = 0.f;
+    for (int b = 0; b < B; ++b) s = fmaf(ddvec[(size_t)b * C + c], h[(size_t)b * 4 * C + j], s);
+    gW2[(size_t)c * 4 * C + j] = s;
+  }
+}
+static __global__ void __launch_bounds__(256) mlp_bwd_pre_kernel(const int64_t* __restrict__ t, const float* __restrict__ ddvec,
+                                                          const float* __restrict__ W0, const float* __restrict__ W2,
+                                                          float* __restrict__ dpre, int C) {
+  __shared__ float emb[256];
+  const int b = blockIdx.y, j = blockIdx.x * blockDim.x + threadIdx.x;
+  const float tv = (float)t[b];
+  for (int k = threadIdx.x; k < C; k += blockDim.x) emb[k] = emb_value(tv, k, C);
+  __syncthreads();
+  float pre = 0.f;
+  for (int k = 0; k < C; ++k) pre = fmaf(W0[(size_t)j * C + k], emb[k], pre);
+  float dh = 0.f;
+  for (int c = 0; c < C; ++c) dh = fmaf(ddvec[(size_t)b * C + c], W2[(size_t)c * 4 * C + j], dh);
+  // mish(x) = x tanh(softplus(x));  mish'(x) = tanh(sp) + x (1 - tanh(sp)^2) sigmoid(x)
+  const float sp = pre > 20.f ? pre : log1pf(expf(pre));
+  const float th = tanhf(sp);
+  const float sg = 1.0f / (1.0f + expf(-pre));
+  dpre[(size_t)b * 4 * C + j] = dh * (th + pre * (1.0f - th * th) * sg);
+}
+static __global__ void __launch_bounds__(256) mlp_bwd_w0_kernel(const int64_t* __restrict__ t, const float* __restrict__ dpre,
+                                                         float* __restrict__ gW0, int B, int C) {
+  const int j = blockIdx.x, k = threadIdx.x;
+  float s = 0.f;
+  for (int b = 0; b < B; ++b) s = fmaf(dpre[(size_t)b * 4 * C + j], emb_value((float)t[b], k, C), s);
+  gW0[(size_t)j * C + k] = s;
+}
+
+
+}  // namespace trainsmall
+}  // namespace mgb

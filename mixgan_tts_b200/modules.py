@@ -192,14 +192,15 @@ class Denoiser(nn.Module):
 
     def train_workspace(self, B: int, T: int, device) -> torch.Tensor:
         lib = _lib.load()
-        n = lib.mgb_train_workspace_bytes(C.byref(self.dims), B, T)
+        n = lib.mgb_train_workspace_bytes(C.byref(self.dims), PRECISIONS[self.precision], B, T)
         if n == 0:
             raise ValueError(f"unsupported shape B={B} T={T}")
         return self._train_ws.get(n, device)
 
     def _forward_with_grad(self, mel, diffusion_step, conditioner, speaker_emb):
-        """Forward that records a graph node whose backward runs in the library (fp32 arithmetic, whatever
-        ``self.precision`` the inference path uses).  The transposes/casts around it are ordinary torch ops."""
+        """Forward that records a graph node whose backward runs in the library, in ``self.precision`` arithmetic
+        (``fp32``: CUDA-core GEMMs, the parity mode; ``bf16``: every GEMM on tcgen05 with fp32 accumulation and fp32
+        residual/skip/gradient streams).  The transposes/casts around it are ordinary torch ops."""
         cond_bth = conditioner.transpose(1, 2).float().contiguous()
         spk = speaker_emb.float().contiguous() if self.dims.multi_speaker else None
         params = self._ordered_params()
@@ -218,18 +219,20 @@ class _DenoiserGradFn(torch.autograd.Function):
         dev = x.device
         B, _, M, T = x.shape
         with torch.cuda.device(dev):
-            packed = den.packed_weights("fp32")
+            packed = den.packed_weights("fp32")      # both precisions: the per-utterance step MLP / tables are fp32
+            flat = den.flat_weights()
+            prec = PRECISIONS[den.precision]
             tt = t.detach().to(torch.int64).contiguous()
             out = torch.empty_like(x)
-            saved = torch.empty(lib.mgb_train_saved_bytes(C.byref(den.dims), B, T), dtype=torch.uint8, device=dev)
+            saved = torch.empty(lib.mgb_train_saved_bytes(C.byref(den.dims), prec, B, T), dtype=torch.uint8, device=dev)
             ws = den.train_workspace(B, T, dev)
             stream = torch.cuda.current_stream(dev).cuda_stream
             _lib.check(lib.mgb_denoiser_train_forward(
-                C.byref(den.dims), _lib.PREC_FP32, _lib.ptr(packed), _lib.ptr(x), _lib.ptr(tt), _lib.ptr(cond_bth),
+                C.byref(den.dims), prec, _lib.ptr(packed), _lib.ptr(flat), _lib.ptr(x), _lib.ptr(tt), _lib.ptr(cond_bth),
                 _lib.ptr(spk), _lib.ptr(out), _lib.ptr(saved), saved.numel(), B, T, _lib.ptr(ws), ws.numel(),
                 C.c_void_p(stream)), "mgb_denoiser_train_forward")
         ctx.den, ctx.saved, ctx.tt, ctx.cond, ctx.spk = den, saved, tt, cond_bth, spk
-        ctx.flat = den.flat_weights()
+        ctx.flat, ctx.prec = flat, prec
         ctx.shape = (B, M, T)
         ctx.param_shapes = [p.shape for p in params]
         return out
@@ -259,7 +262,7 @@ class _DenoiserGradFn(torch.autograd.Function):
             buckets = plan_buckets(ranges, sync.bucket_bytes if sync is not None else None)
             for sb, se, fb, fe in buckets:
                 _lib.check(lib.mgb_denoiser_backward(
-                    C.byref(den.dims), _lib.PREC_FP32, _lib.ptr(ctx.flat), _lib.ptr(ctx.saved), ctx.saved.numel(),
+                    C.byref(den.dims), ctx.prec, _lib.ptr(ctx.flat), _lib.ptr(ctx.saved), ctx.saved.numel(),
                     _lib.ptr(ctx.tt), _lib.ptr(ctx.cond), _lib.ptr(ctx.spk), _lib.ptr(gout), _lib.ptr(gflat),
                     _lib.ptr(gcond), _lib.ptr(gspk), _lib.ptr(gx), B, T, sb, se, _lib.ptr(ws), ws.numel(), stream),
                     "mgb_denoiser_backward")

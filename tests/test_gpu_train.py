@@ -20,8 +20,8 @@ TOL = 1e-4
 TOL_EDGE = 1e-3
 
 
-def build(case: Case) -> GaussianDiffusion:
-    gd = GaussianDiffusion(case.args, case.pc, case.mc, case.tc, precision="fp32")
+def build(case: Case, precision: str = "fp32") -> GaussianDiffusion:
+    gd = GaussianDiffusion(case.args, case.pc, case.mc, case.tc, precision=precision)
     gd.denoise_fn.load_state_dict({k: torch.from_numpy(v) for k, v in case.W.items()})
     return gd.cuda().train()
 
@@ -147,12 +147,110 @@ def test_train_abi_errors():
     lib = _lib.load()
     d = _lib.ModelDims(80, 256, 256, 20, 0)
     assert lib.mgb_train_segments(C.byref(d)) == 22
-    assert lib.mgb_denoiser_backward(C.byref(d), _lib.PREC_BF16, None, None, 0, None, None, None, None, None, None, None,
+    assert lib.mgb_denoiser_backward(C.byref(d), _lib.PREC_FP32, None, None, 0, None, None, None, None, None, None, None,
                                      None, 1, 8, 0, 22, None, 0, None) == _lib.E_ARG
     x = torch.zeros(16, device="cuda")
-    rc = lib.mgb_denoiser_train_forward(C.byref(d), _lib.PREC_BF16, _lib.ptr(x), _lib.ptr(x), _lib.ptr(x), _lib.ptr(x), None,
+    rc = lib.mgb_denoiser_train_forward(C.byref(d), 7, _lib.ptr(x), _lib.ptr(x), _lib.ptr(x), _lib.ptr(x), _lib.ptr(x), None,
                                         _lib.ptr(x), _lib.ptr(x), 64, 1, 8, _lib.ptr(x), 64, None)
-    assert rc == _lib.E_UNSUPPORTED
-    rc = lib.mgb_denoiser_train_forward(C.byref(d), _lib.PREC_FP32, _lib.ptr(x), _lib.ptr(x), _lib.ptr(x), _lib.ptr(x), None,
-                                        _lib.ptr(x), _lib.ptr(x), 64, 1, 8, _lib.ptr(x), 64, None)
-    assert rc == _lib.E_WORKSPACE
+    assert rc == _lib.E_ARG
+    for prec in (_lib.PREC_FP32, _lib.PREC_BF16):
+        rc = lib.mgb_denoiser_train_forward(C.byref(d), prec, _lib.ptr(x), _lib.ptr(x), _lib.ptr(x), _lib.ptr(x), _lib.ptr(x), None,
+                                            _lib.ptr(x), _lib.ptr(x), 64, 1, 8, _lib.ptr(x), 64, None)
+        assert rc == _lib.E_WORKSPACE
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# bf16 tensor-core training path.  Stated tolerances (relative L2 against fp32 torch autograd through the oracle; the
+# measured values are written to gpurun_out/train_bf16_parity.txt):
+#   outputs 2e-2 (the inference path's bf16 bar);
+#   gradients 2e-2 per tensor when the two ReLU masks are stable (biases shifted so that no pre-activation sits near 0):
+#     this isolates the arithmetic of the GEMMs/epilogues — bf16 operand rounding (2^-9 per element) through 20 blocks;
+#   gradients 1e-1 per tensor with the random-init weights: there ~0.25 % of the skip-projection / input-projection
+#     pre-activations lie within the bf16 forward error of zero, their ReLU masks flip against the fp32 run, and a
+#     fraction p of flipped units moves a gradient by ~sqrt(p) = 5 % in L2 (measured 5-6 %, uniform over layers).  Any
+#     bf16 training of this network has this property; it is not an error of the kernels.
+TOL_BF16_OUT, TOL_BF16_GRAD, TOL_BF16_GRAD_RELU = 2e-2, 2e-2, 1e-1
+
+
+def _status(gd, B, T):
+    lib = _lib.load()
+    st = C.c_int(-1)
+    den = gd.denoise_fn
+    _lib.check(lib.mgb_train_debug_status(C.byref(den.dims), B, T, _lib.ptr(den._train_ws.buf), C.byref(st)), "status")
+    return st.value
+
+
+def _report(line):
+    import os
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open("gpurun_out/train_bf16_parity.txt", "a") as f:
+        f.write(line + "\n")
+    print(line)
+
+
+@pytest.mark.parametrize("name", list(TRAIN_CASES))
+def test_bf16_training_path_vs_oracle(name):
+    c, ex = train_case(name)
+    probe = probe_for(name, c)
+    gd = build(c, "bf16")
+    loss, out, grads, gcond, gspk, _ = run_library(c, ex, probe, gd)
+    assert _status(gd, c.B, c.T) == 0, "a bf16 training kernel hit its watchdog"
+    oloss, oout, ograds, ogcond, ogspk = oracle_training_grads(c, ex, probe)
+    e_out = max(rel_l2(a.detach(), b.detach()) for a, b in zip(out[:4], oout[:4]))
+    e_cond = rel_l2(gcond, ogcond)
+    _report(f"{name}: loss {float(loss):.5f} (oracle {float(oloss):.5f})  out {e_out:.3e}  grad_cond {e_cond:.3e}"
+            + (f"  grad_spk {rel_l2(gspk, ogspk):.3e}" if ogspk is not None else ""))
+    total = float(torch.sqrt(sum(v.double().pow(2).sum() for v in ograds.values())))
+    worst = ("", 0.0)
+    for k, ref in ograds.items():
+        err = float((grads[k].double() - ref.double()).norm()) / max(float(ref.double().norm()), 1e-3 * total)
+        if err > worst[1]:
+            worst = (k, err)
+        if not k.startswith("residual_layers.") or k.startswith("residual_layers.0.") or k.startswith("residual_layers.19."):
+            _report(f"    {k:55s} {err:.3e}  |ref| {float(ref.norm()):.3e}")
+    _report(f"    worst: {worst[0]} {worst[1]:.3e}")
+    assert e_out < TOL_BF16_OUT and e_cond < TOL_BF16_GRAD_RELU
+    if ogspk is not None:
+        assert rel_l2(gspk, ogspk) < TOL_BF16_GRAD_RELU
+    assert worst[1] < TOL_BF16_GRAD_RELU, worst
+
+
+@pytest.mark.parametrize("multi,B,T,L", [(False, 1, 1, 2), (False, 2, 3, 1), (True, 2, 129, 3), (False, 3, 257, 2),
+                                         (True, 4, 200, 20)])
+def test_bf16_training_edge_shapes_vs_fp32_path(multi, B, T, L):
+    """bf16 path against the library's own fp32 path (which the tests above pin to the oracle) on ragged shapes, with the
+    two ReLU masks made stable (+8 on the input- and skip-projection biases) so that the comparison measures arithmetic."""
+    c = Case("AISHELL3" if multi else "LJSpeech", "naive", multi, B, T, wseed=3, iseed=40 + T, layers=L)
+    c.W = dict(c.W)
+    for k in ("input_projection.0.conv.bias", "skip_projection.conv.bias"):
+        c.W[k] = c.W[k] + np.float32(8.0)
+    res = {}
+    for prec in ("fp32", "bf16"):
+        gd = build(c, prec)
+        x = cu(c.t("x_T"), True)
+        cond = cu(c.t("cond").transpose(1, 2).contiguous(), True)
+        spk = cu(c.t("spk"), multi)
+        t = torch.arange(B, dtype=torch.long).cuda() % c.K
+        r = torch.randn(B, 1, 80, T, generator=torch.Generator().manual_seed(5)).cuda()
+        out = gd.denoise_fn(x, t, cond, spk)
+        (out * r).sum().backward()
+        torch.cuda.synchronize()
+        if prec == "bf16":
+            assert _status(gd, B, T) == 0
+        res[prec] = (out.detach(), x.grad, cond.grad, spk.grad if multi else None,
+                     {k: p.grad.detach() for k, p in gd.denoise_fn.named_parameters()})
+    a, b = res["bf16"], res["fp32"]
+    errs = {"out": rel_l2(a[0], b[0]), "dx": rel_l2(a[1], b[1]), "dcond": rel_l2(a[2], b[2])}
+    if multi:
+        errs["dspk"] = rel_l2(a[3], b[3])
+    total = float(torch.sqrt(sum(v.double().pow(2).sum() for v in b[4].values())))
+    worst = ("", 0.0)
+    for k, ref in b[4].items():
+        err = float((a[4][k].double() - ref.double()).norm()) / max(float(ref.double().norm()), 1e-3 * total)
+        if err > worst[1]:
+            worst = (k, err)
+    _report(f"stable-mask multi={multi} B={B} T={T} L={L}: " + " ".join(f"{k} {v:.3e}" for k, v in errs.items())
+            + f"  worst param grad {worst[0]} {worst[1]:.3e}")
+    assert errs["out"] < TOL_BF16_OUT
+    assert all(v < TOL_BF16_GRAD for k, v in errs.items() if k != "out"), errs
+    assert worst[1] < TOL_BF16_GRAD, worst

@@ -81,6 +81,7 @@ __device__ __forceinline__ void load_img32(const bf16* img, int Rp, int rho, int
     v[q * 8 + 4] = c.x; v[q * 8 + 5] = c.y; v[q * 8 + 6] = d.x; v[q * 8 + 7] = d.y;
   }
 }
+// 32 consecutive floats of a row-major row (user tensors, bias vectors, per-utterance tables)
 __device__ __forceinline__ void load_f32x32(const float* p, float (&v)[32]) {
 #pragma unroll
   for (int q = 0; q < 8; ++q) {
@@ -92,6 +93,22 @@ __device__ __forceinline__ void store_f32x32(float* p, const float (&v)[32]) {
 #pragma unroll
   for (int q = 0; q < 8; ++q)
     *reinterpret_cast<float4*>(p + q * 4) = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+}
+// fp32 streams (x, skip sum, e, X0) and the (sigmoid, tanh) pairs live in a chunked layout [C/4][Rp][4]: one thread owns
+// one row, so a warp's 16-byte access to chunk q is 512 contiguous bytes (a row-major [Rp][C] array would cost 32
+// separate sectors per warp instruction)
+__device__ __forceinline__ void load_s32(const float* base, int Rp, int rho, int ch0, float (&v)[32]) {
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const float4 a = *reinterpret_cast<const float4*>(base + ((size_t)(ch0 / 4 + q) * Rp + rho) * 4);
+    v[q * 4] = a.x; v[q * 4 + 1] = a.y; v[q * 4 + 2] = a.z; v[q * 4 + 3] = a.w;
+  }
+}
+__device__ __forceinline__ void store_s32(float* base, int Rp, int rho, int ch0, const float (&v)[32]) {
+#pragma unroll
+  for (int q = 0; q < 8; ++q)
+    *reinterpret_cast<float4*>(base + ((size_t)(ch0 / 4 + q) * Rp + rho) * 4) =
+        make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
 }
 __device__ __forceinline__ void tmem_ld_f32x32(uint32_t taddr, float (&v)[32]) {
   uint32_t r[32];
@@ -144,25 +161,28 @@ __device__ __forceinline__ void fgemm_epilogue(const FArgs& p, uint32_t tmem_row
   const int L = p.L;
   if constexpr (MODE == F_IN || MODE == F_SKIP) {
     // relu(acc + bias): F_IN -> fp32 X0 stream; F_SKIP -> P image
-#pragma unroll 1
+#pragma unroll 2
     for (int cg = 0; cg < 8; ++cg) {
       float v[32];
       tmem_ld_f32x32(tmem_row + cg * 32, v);
+      float bv[32];
+      load_f32x32(p.bias + cg * 32, bv);
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = valid ? fmaxf(v[j] + p.bias[cg * 32 + j], 0.f) : 0.f;
-      if constexpr (MODE == F_IN) store_f32x32(p.fout + (size_t)rho * C + cg * 32, v);
+      for (int j = 0; j < 32; ++j) v[j] = valid ? fmaxf(v[j] + bv[j], 0.f) : 0.f;
+      if constexpr (MODE == F_IN) store_s32(p.fout, p.Rp, rho, cg * 32, v);
       else store_img32(p.img, p.Rp, rho, cg * 32, v);
     }
   } else if constexpr (MODE == F_COND) {
     // y = (x + d_l) + (Wc cond + bc_l [+ s_l])   (blocks.py:1166-1168) -> conv input image (zero outside utterances)
-#pragma unroll 1
+#pragma unroll 2
     for (int cg = 0; cg < 8; ++cg) {
       float v[32], x[32];
       tmem_ld_f32x32(tmem_row + cg * 32, v);
       if (valid) {
-        load_f32x32(p.fin + (size_t)rho * C + cg * 32, x);
-        const float* dt = p.dtab + (size_t)b * L * C + cg * 32;
-        const float* ct = p.ctab + (size_t)b * L * C + cg * 32;
+        float dt[32], ct[32];
+        load_s32(p.fin, p.Rp, rho, cg * 32, x);
+        load_f32x32(p.dtab + (size_t)b * L * C + cg * 32, dt);
+        load_f32x32(p.ctab + (size_t)b * L * C + cg * 32, ct);
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = (x[j] + dt[j]) + (v[j] + ct[j]);
       } else {
@@ -173,46 +193,53 @@ __device__ __forceinline__ void fgemm_epilogue(const FArgs& p, uint32_t tmem_row
     }
   } else if constexpr (MODE == F_GATE) {
     // tile = 128 gate + 128 filter columns of channels [ntile*128, +128): g = sigmoid(a) tanh(f)  (blocks.py:1170-1171)
-#pragma unroll 1
+#pragma unroll 2
     for (int cg = 0; cg < 4; ++cg) {
       const int ch0 = ntile * 128 + cg * 32;
       float a[32], f[32];
       tmem_ld_f32x32(tmem_row + cg * 32, a);
       tmem_ld_f32x32(tmem_row + 128 + cg * 32, f);
       uint32_t st[32];
+      float ba[32], bf[32];
+      load_f32x32(p.bias + ch0, ba);
+      load_f32x32(p.bias + C + ch0, bf);
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
-        const float sg = 1.0f / (1.0f + __expf(-(a[j] + p.bias[ch0 + j])));
-        const float th = tanhf(f[j] + p.bias[C + ch0 + j]);
+        const float sg = 1.0f / (1.0f + __expf(-(a[j] + ba[j])));
+        const float th = tanhf(f[j] + bf[j]);
         st[j] = pack2(sg, th);
         a[j] = valid ? sg * th : 0.f;
       }
       store_img32(p.img, p.Rp, rho, ch0, a);
-      uint4* sp = reinterpret_cast<uint4*>(p.sgth + (size_t)rho * C + ch0);
 #pragma unroll
-      for (int q = 0; q < 8; ++q) sp[q] = make_uint4(st[q * 4], st[q * 4 + 1], st[q * 4 + 2], st[q * 4 + 3]);
+      for (int q = 0; q < 8; ++q)
+        *reinterpret_cast<uint4*>(p.sgth + ((size_t)(ch0 / 4 + q) * p.Rp + rho) * 4) =
+            make_uint4(st[q * 4], st[q * 4 + 1], st[q * 4 + 2], st[q * 4 + 3]);
     }
   } else if constexpr (MODE == F_OUT) {
     // tile = 128 x-columns + 128 skip columns: x' = (o_x + (x + d_l)) / sqrt(2), skip sum += o_s   (blocks.py:1173-1176)
-#pragma unroll 1
+#pragma unroll 2
     for (int cg = 0; cg < 4; ++cg) {
       const int ch0 = ntile * 128 + cg * 32;
       float ox[32], os[32], x[32];
       tmem_ld_f32x32(tmem_row + cg * 32, ox);
       tmem_ld_f32x32(tmem_row + 128 + cg * 32, os);
       if (valid) {
-        load_f32x32(p.fin + (size_t)rho * C + ch0, x);
-        const float* dt = p.dtab + (size_t)b * L * C + ch0;
+        float dt[32], bx[32], bs[32], sk[32];
+        load_s32(p.fin, p.Rp, rho, ch0, x);
+        if (!p.first) load_s32(p.fout2, p.Rp, rho, ch0, sk);
+        load_f32x32(p.dtab + (size_t)b * L * C + ch0, dt);
+        load_f32x32(p.bias + ch0, bx);
+        load_f32x32(p.bias + C + ch0, bs);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) x[j] = ((ox[j] + p.bias[ch0 + j]) + (x[j] + dt[j])) * RSQRT2;
-        store_f32x32(p.fout + (size_t)rho * C + ch0, x);
-        if (!p.first) load_f32x32(p.fout2 + (size_t)rho * C + ch0, x);
+        for (int j = 0; j < 32; ++j) x[j] = ((ox[j] + bx[j]) + (x[j] + dt[j])) * RSQRT2;
+        store_s32(p.fout, p.Rp, rho, ch0, x);
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          os[j] = (p.first ? 0.f : x[j]) + (os[j] + p.bias[C + ch0 + j]);
+          os[j] = (p.first ? 0.f : sk[j]) + (os[j] + bs[j]);
           if (p.last) os[j] *= p.scale;
         }
-        store_f32x32(p.fout2 + (size_t)rho * C + ch0, os);
+        store_s32(p.fout2, p.Rp, rho, ch0, os);
       } else {
 #pragma unroll
         for (int j = 0; j < 32; ++j) os[j] = 0.f;
@@ -235,7 +262,7 @@ __device__ __forceinline__ void fgemm_epilogue(const FArgs& p, uint32_t tmem_row
       }
     }
   } else if constexpr (MODE == B_PMASK || MODE == B_DS) {
-#pragma unroll 1
+#pragma unroll 2
     for (int cg = 0; cg < 8; ++cg) {
       float v[32];
       tmem_ld_f32x32(tmem_row + cg * 32, v);
@@ -252,14 +279,13 @@ __device__ __forceinline__ void fgemm_epilogue(const FArgs& p, uint32_t tmem_row
     }
   } else if constexpr (MODE == B_GATE) {
     // dza = dg th sg (1 - sg), dzb = dg sg (1 - th^2) -> dZ image [gate C | filter C], zero outside utterances
-#pragma unroll 1
+#pragma unroll 2
     for (int cg = 0; cg < 8; ++cg) {
       float dg[32], df[32];
       tmem_ld_f32x32(tmem_row + cg * 32, dg);
-      const uint4* sp = reinterpret_cast<const uint4*>(p.sgth_in + (size_t)rho * C + cg * 32);
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
-        const uint4 u = sp[q];
+        const uint4 u = *reinterpret_cast<const uint4*>(p.sgth_in + ((size_t)(cg * 8 + q) * p.Rp + rho) * 4);
         const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
@@ -275,20 +301,20 @@ __device__ __forceinline__ void fgemm_epilogue(const FArgs& p, uint32_t tmem_row
     }
   } else if constexpr (MODE == B_DX) {
     // dY = acc; dx_l = e_l + dY; e_{l-1} = dx_l / sqrt(2)   (layer 0: ReLU mask of the input projection instead)
-#pragma unroll 1
+#pragma unroll 2
     for (int cg = 0; cg < 8; ++cg) {
       float dy[32], e[32];
       tmem_ld_f32x32(tmem_row + cg * 32, dy);
       if (valid) {
-        if (!p.first) load_f32x32(p.fout + (size_t)rho * C + cg * 32, e);
+        if (!p.first) load_s32(p.fout, p.Rp, rho, cg * 32, e);
         float x0[32];
-        if (p.relu0) load_f32x32(p.fin + (size_t)rho * C + cg * 32, x0);
+        if (p.relu0) load_s32(p.fin, p.Rp, rho, cg * 32, x0);
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           const float dx = (p.first ? 0.f : e[j]) + dy[j];
           e[j] = p.relu0 ? (x0[j] > 0.f ? dx : 0.f) : dx * RSQRT2;
         }
-        store_f32x32(p.fout + (size_t)rho * C + cg * 32, e);
+        store_s32(p.fout, p.Rp, rho, cg * 32, e);
       } else {
 #pragma unroll
         for (int j = 0; j < 32; ++j) { dy[j] = 0.f; e[j] = 0.f; }
@@ -300,7 +326,7 @@ __device__ __forceinline__ void fgemm_epilogue(const FArgs& p, uint32_t tmem_row
     // grad_cond[b][t][:] (+)= dY Wc.  The TMEM load is warp-collective (.sync.aligned): every lane issues it, only the
     // global accesses are predicated on the row being a real frame.
     float* o = p.fout + ((size_t)(valid ? b : 0) * p.T + (valid ? t : 0)) * C;
-#pragma unroll 1
+#pragma unroll 2
     for (int cg = 0; cg < 8; ++cg) {
       float v[32], a[32];
       tmem_ld_f32x32(tmem_row + cg * 32, v);
@@ -683,7 +709,8 @@ struct PackedB16 {   // offsets in bf16 elements into the packed-weight buffer (
   size_t in_f, skip_f, out_f;                       // forward
   size_t out_b, skip_b, in_b;                       // backward (transposed)
   size_t layer0, layer_stride;
-  size_t r_cond_f, r_conv_f, r_oproj_f, r_oproj_b, r_conv_b, r_cond_b;
+  size_t r_cond_f, r_conv_f, r_oproj_f, r_oproj_b, r_conv_b;
+  size_t cond_b_all;                                // Wc^T of all layers, 4 k-steps each, contiguous (one K = 256 L GEMM)
   size_t total;
 };
 PackedB16 packed16_layout(const mgb_model_dims& d) {
@@ -704,9 +731,9 @@ PackedB16 packed16_layout(const mgb_model_dims& d) {
   o.r_oproj_f = tk((size_t)512 * 256);
   o.r_oproj_b = tk((size_t)256 * 512);
   o.r_conv_b = tk((size_t)256 * 1536);
-  o.r_cond_b = tk((size_t)256 * 256);
   o.layer_stride = q;
   p += q * d.layers;
+  o.cond_b_all = take((size_t)256 * 256 * d.layers);
   o.total = p;
   return o;
 }
@@ -742,7 +769,7 @@ Saved16 saved16_layout(const mgb_model_dims& d, int B, int T) {
 
 struct Work16 {      // byte offsets into the workspace
   size_t status, X, S, dtab, ctab, dout, dPre, dS, E, Eimg, dZ, dY, part, usumE, usumZ, usumY, usumS, usumT, ddvec,
-      dspk, dpre, total;
+      dspk, dpre, dd_all, ds_all, lpart, total;
 };
 Work16 work16_layout(const mgb_model_dims& d, int B, int T) {
   const RowSpace rs = row_space(B, T);
@@ -761,7 +788,7 @@ Work16 work16_layout(const mgb_model_dims& d, int B, int T) {
   w.E = take(Rp * C * 4);
   w.Eimg = take(32 * Rp * 16);
   w.dZ = take(64 * Rp * 16);
-  w.dY = take(32 * Rp * 16);
+  w.dY = take((size_t)d.layers * 32 * Rp * 16);   // every layer's dY image: d loss / d cond is ONE GEMM over K = 256 L at the head
   size_t part = wg_part_floats(rs.ntiles, 512, 256, 3, 256);
   auto mx = [&](size_t v) { if (v > part) part = v; };
   mx(wg_part_floats(rs.ntiles, 512, 256, 1, 256));
@@ -777,6 +804,9 @@ Work16 work16_layout(const mgb_model_dims& d, int B, int T) {
   w.ddvec = take((size_t)B * C * 4);
   w.dspk = take((size_t)B * C * 4);
   w.dpre = take((size_t)B * 4 * C * 4);
+  w.dd_all = take((size_t)d.layers * B * C * 4);
+  w.ds_all = take((size_t)d.layers * B * C * 4);
+  w.lpart = take((size_t)d.layers * B * C * 4);
   w.total = p;
   return w;
 }
@@ -816,7 +846,7 @@ int pack_step_weights(const mgb_model_dims& d, const float* flat, bf16* out, cud
     a.d[2] = desc(ol + o.r_oproj_f, fl + f.rel.oproj_w, 2 * C, 256, C, 1, C, 1, 0, 0, 1);        // Wo[co][ci], x|skip tiles
     a.d[3] = desc(ol + o.r_oproj_b, fl + f.rel.oproj_w, C, 256, 2 * C, 1, 1, C, 0, 0, 0);        // W_eff[n=ci][k=co]
     a.d[4] = desc(ol + o.r_conv_b, fl + f.rel.conv_w, C, 256, 2 * C, 3, 3, 3 * C, 1, 1, 0);      // W_eff[n=ci][tap', co] = W3[co][ci][2-tap']
-    a.d[5] = desc(ol + o.r_cond_b, fl + f.rel.cproj_w, C, 256, C, 1, 1, C, 0, 0, 0);             // Wc^T
+    a.d[5] = desc(o.cond_b_all + (size_t)l * 256 * 256, fl + f.rel.cproj_w, C, 256, C, 1, 1, C, 0, 0, 0);   // Wc^T
     run(a);
   }
   MGB_LAUNCH_CHECK();
@@ -961,6 +991,7 @@ int bf16_train_backward(const mgb_model_dims& d, const float* flat, const void* 
       const bf16* wl = wpk + o.layer0 + (size_t)l * o.layer_stride;
       const float* fl = flat + f.layer0 + (size_t)l * f.layer_stride;
       float* gl = grad_flat + f.layer0 + (size_t)l * f.layer_stride;
+      bf16* dYl = img(W + w.dY) + (size_t)l * 32 * rs.Rp * 8;
       {
         FArgs a = base;                                 // dG = [e | dS] Wo; gate backward -> dZ
         if (top) { a.A0 = cimg(W + w.dS); a.steps0 = 4; a.kstep_b0 = 4; }
@@ -982,29 +1013,23 @@ int bf16_train_backward(const mgb_model_dims& d, const float* flat, const void* 
       {
         FArgs a = base;                                 // dY = conv3^T(dZ); dx = e + dY; e' = dx / sqrt(2)
         a.A0 = cimg(W + w.dZ); a.steps0 = 8; a.taps = 3; a.Bpk = wl + o.r_conv_b; a.ksteps_b = 24;
-        a.fout = f32(W + w.E); a.fin = cf32(SV + sv.X0); a.img = img(W + w.dY); a.img2 = img(W + w.Eimg);
+        a.fout = f32(W + w.E); a.fin = cf32(SV + sv.X0); a.img = dYl; a.img2 = img(W + w.Eimg);
         a.first = top ? 1 : 0; a.relu0 = (l == 0) ? 1 : 0;
         if (int rc = launch_fgemm<256, B_DX>(a, rs.ntiles, 1, s)) return rc;
       }
       if (int rc = launch_wg<256>(cimg(W + w.dZ), nullptr, 4, 2 * C, cimg(sl + sv.rY), C, 3, rs, part, gl + f.rel.conv_w,
                                   status, s)) return rc;
-      if (int rc = launch_wg<256>(cimg(W + w.dY), nullptr, 2, C, cimg(SV + sv.cond), H, 1, rs, part, gl + f.rel.cproj_w,
+      if (int rc = launch_wg<256>(dYl, nullptr, 2, C, cimg(SV + sv.cond), H, 1, rs, part, gl + f.rel.cproj_w,
                                   status, s)) return rc;
-      if (grad_cond) {
-        FArgs a = base;                                 // dCond (+)= dY Wc
-        a.A0 = cimg(W + w.dY); a.steps0 = 4; a.Bpk = wl + o.r_cond_b; a.ksteps_b = 4;
-        a.fout = grad_cond; a.first = top ? 1 : 0;
-        if (int rc = launch_fgemm<256, B_COND>(a, rs.ntiles, 1, s)) return rc;
-      }
-      launch_colsum_img(cimg(W + w.dY), 32, rs, B, f32(W + w.usumY), C, s);
+      launch_colsum_img(dYl, 32, rs, B, f32(W + w.usumY), C, s);
       LayerSmallArgs q{};
       q.usumE = top ? nullptr : f32(W + w.usumE); q.usumZ = f32(W + w.usumZ); q.usumY = f32(W + w.usumY);
       q.usumS = f32(W + w.usumS); q.dvec = cf32(SV + sv.dvec); q.spk = d.multi_speaker ? spk : nullptr;
       q.Wd = fl + f.rel.dproj_w; q.Ws = d.multi_speaker ? fl + f.rel.sproj_w : nullptr;
       q.g_conv_b = gl + f.rel.conv_b; q.g_oproj_b = gl + f.rel.oproj_b; q.g_cproj_b = gl + f.rel.cproj_b;
       q.g_dproj_w = gl + f.rel.dproj_w; q.g_sproj_w = d.multi_speaker ? gl + f.rel.sproj_w : nullptr;
-      q.ddvec = f32(W + w.ddvec); q.dspk = d.multi_speaker ? f32(W + w.dspk) : nullptr;
-      q.B = B; q.C = C; q.H = H; q.first = top ? 1 : 0;
+      q.dd_l = f32(W + w.dd_all) + (size_t)l * B * C; q.ds_l = d.multi_speaker ? f32(W + w.ds_all) + (size_t)l * B * C : nullptr;
+      q.B = B; q.C = C; q.H = H;
       layer_small_kernel<<<C + B + 1, 256, 0, s>>>(q);
       note_launch();
     } else if (seg == L + 1) {
@@ -1014,11 +1039,22 @@ int bf16_train_backward(const mgb_model_dims& d, const float* flat, const void* 
       launch_colsum_img(cimg(W + w.Eimg), 32, rs, B, f32(W + w.usumT), C, s);
       bias_from_usum_kernel<<<2, 128, 0, s>>>(f32(W + w.usumT), B, C, C, grad_flat + f.in_b);
       note_launch();
+      if (grad_cond) {
+        // d loss / d cond = sum_l dY_l Wc_l: the L dY images are one image of 32 L chunks, so this is a single GEMM over
+        // K = 256 L whose epilogue writes the user tensor once (no read-modify-write per layer)
+        FArgs a = base;
+        a.A0 = cimg(W + w.dY); a.steps0 = 4 * L; a.Bpk = wpk + o.cond_b_all; a.ksteps_b = 4 * L;
+        a.fout = grad_cond; a.first = 1;
+        if (int rc = launch_fgemm<256, B_COND>(a, rs.ntiles, 1, s)) return rc;
+      }
       if (grad_x) {
         FArgs a = base;                                 // d loss / d mel = dPre0 Win
         a.A0 = cimg(W + w.Eimg); a.steps0 = 4; a.Bpk = wpk + o.in_b; a.ksteps_b = 4; a.fout = grad_x;
         if (int rc = launch_fgemm<128, B_DXT>(a, rs.ntiles, 1, s)) return rc;
       }
+      launch_dvec_contraction(f32(W + w.dd_all), f32(W + w.ds_all), flat + f.layer0 + f.rel.dproj_w,
+                              d.multi_speaker ? flat + f.layer0 + f.rel.sproj_w : nullptr, f.layer_stride, f32(W + w.lpart),
+                              f32(W + w.ddvec), f32(W + w.dspk), B, L, s);
       mlp_bwd_w2_kernel<<<C, 256, 0, s>>>(f32(W + w.ddvec), cf32(SV + sv.h), grad_flat + f.mlp2_w, B, C);
       mlp_bwd_pre_kernel<<<dim3(4 * C / 256, B), 256, 0, s>>>(t, f32(W + w.ddvec), flat + f.mlp0_w, flat + f.mlp2_w,
                                                              f32(W + w.dpre), C);

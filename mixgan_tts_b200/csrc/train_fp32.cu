@@ -322,7 +322,7 @@ __global__ void pad_cols_kernel(const float* __restrict__ src, float* __restrict
 
 struct TrainWork {
   size_t fwd;                                   // the forward's scratch (WorkF32) lives at the front
-  size_t doutf, dPre, dS, E, dZ, dY, w3t, winpad, part, usumE, usumZ, usumY, usumS, usumT, ddvec, dspk, dpre, total;
+  size_t doutf, dPre, dS, E, dZ, dY, w3t, winpad, part, usumE, usumZ, usumY, usumS, usumT, ddvec, dspk, dpre, dd_all, ds_all, lpart, total;
 };
 TrainWork train_work_layout(const mgb_model_dims& d, int B, int T) {
   const size_t C = d.channels, H = d.d_encoder, M = d.n_mel, F = (size_t)B * T;
@@ -355,6 +355,9 @@ TrainWork train_work_layout(const mgb_model_dims& d, int B, int T) {
   w.ddvec = take((size_t)B * C);
   w.dspk = take((size_t)B * H);
   w.dpre = take((size_t)B * 4 * C);
+  w.dd_all = take((size_t)d.layers * B * C);
+  w.ds_all = take((size_t)d.layers * B * C);
+  w.lpart = take((size_t)d.layers * B * C);
   w.total = p;
   return w;
 }
@@ -502,8 +505,8 @@ int fp32_train_backward(const mgb_model_dims& d, const float* flat, const float*
         q.Wd = fl + f.rel.dproj_w; q.Ws = d.multi_speaker ? fl + f.rel.sproj_w : nullptr;
         q.g_conv_b = gl + f.rel.conv_b; q.g_oproj_b = gl + f.rel.oproj_b; q.g_cproj_b = gl + f.rel.cproj_b;
         q.g_dproj_w = gl + f.rel.dproj_w; q.g_sproj_w = d.multi_speaker ? gl + f.rel.sproj_w : nullptr;
-        q.ddvec = W + w.ddvec; q.dspk = d.multi_speaker ? W + w.dspk : nullptr;
-        q.B = B; q.C = C; q.H = H; q.first = top ? 1 : 0;
+        q.dd_l = W + w.dd_all + (size_t)l * B * C; q.ds_l = d.multi_speaker ? W + w.ds_all + (size_t)l * B * C : nullptr;
+        q.B = B; q.C = C; q.H = H;
         layer_small_kernel<<<C + B + 1, 256, 0, s>>>(q);
         note_launch();
       }
@@ -525,6 +528,9 @@ int fp32_train_backward(const mgb_model_dims& d, const float* flat, const float*
         launch_bgemm<B_DXT>(a, 128, s);
         note_launch();
       }
+      launch_dvec_contraction(W + w.dd_all, W + w.ds_all, flat + f.layer0 + f.rel.dproj_w,
+                              d.multi_speaker ? flat + f.layer0 + f.rel.sproj_w : nullptr, f.layer_stride, W + w.lpart,
+                              W + w.ddvec, W + w.dspk, B, L, s);
       mlp_bwd_w2_kernel<<<C, 256, 0, s>>>(W + w.ddvec, saved + sv.h, grad_flat + f.mlp2_w, B, C);
       mlp_bwd_pre_kernel<<<dim3(4 * C / 256, B), 256, 0, s>>>(t, W + w.ddvec, flat + f.mlp0_w, flat + f.mlp2_w,
                                                              W + w.dpre, C);

@@ -33,13 +33,12 @@ struct LayerSmallArgs {
   const float* Wd;      // [C][C]   diffusion_projection.linear.weight  (raw [out][in])
   const float* Ws;      // [C][H]   speaker_projection.linear.weight or nullptr
   float *g_conv_b, *g_oproj_b, *g_cproj_b, *g_dproj_w, *g_sproj_w;
-  float* ddvec;         // [B][C]  accumulated over layers
-  float* dspk;          // [B][H]  accumulated over layers (or nullptr)
-  int B, C, H, first;   // first: this is the first layer processed (overwrite the accumulators)
+  float* dd_l;          // [B][C]  this layer's slot of dd_all [L][B][C]
+  float* ds_l;          // [B][C]  this layer's slot of ds_all [L][B][C] (or nullptr)
+  int B, C, H;
 };
 // grid: C blocks (row co of dWd / dWs) + B blocks (ddvec / dspk rows) + 1 block (biases); 256 threads, C == H == 256
 static __global__ void __launch_bounds__(256) layer_small_kernel(const LayerSmallArgs p) {
-  __shared__ float dd[256];
   const int C = p.C, tid = threadIdx.x;
   const int blk = blockIdx.x;
   if (blk < C) {
@@ -55,18 +54,12 @@ static __global__ void __launch_bounds__(256) layer_small_kernel(const LayerSmal
     p.g_dproj_w[(size_t)co * C + tid] = gd;
     if (p.Ws) p.g_sproj_w[(size_t)co * p.H + tid] = gs;
   } else if (blk < C + p.B) {
-    // ddvec[b][ci] += sum_co dd[b][co] * Wd[co][ci] ; dspk[b][h] += sum_co usumY[b][co] * Ws[co][h]
+    // keep dd_l = usumE + usumY and ds_l = usumY per layer: d loss / d dvec and d loss / d spk are contracted with all
+    // layers' projection weights in one launch at the head (layers_rowgemm_kernel) instead of a serial chain per layer
     const int b = blk - C;
-    dd[tid] = (p.usumE ? p.usumE[(size_t)b * C + tid] : 0.f) + p.usumY[(size_t)b * C + tid];
-    __syncthreads();
-    float s = 0.f;
-    for (int co = 0; co < C; ++co) s = fmaf(dd[co], p.Wd[(size_t)co * C + tid], s);
-    p.ddvec[(size_t)b * C + tid] = (p.first ? 0.f : p.ddvec[(size_t)b * C + tid]) + s;
-    if (p.Ws) {
-      float q = 0.f;
-      for (int co = 0; co < C; ++co) q = fmaf(p.usumY[(size_t)b * C + co], p.Ws[(size_t)co * p.H + tid], q);
-      p.dspk[(size_t)b * p.H + tid] = (p.first ? 0.f : p.dspk[(size_t)b * p.H + tid]) + q;
-    }
+    const float y = p.usumY[(size_t)b * C + tid];
+    p.dd_l[(size_t)b * C + tid] = (p.usumE ? p.usumE[(size_t)b * C + tid] : 0.f) + y;
+    if (p.Ws) p.ds_l[(size_t)b * C + tid] = y;
   } else {
     // conv bias [2C], output-projection bias [x-half from e_l | skip half from dS], conditioner bias [C]
     for (int c = tid; c < 2 * C; c += blockDim.x) {
@@ -85,6 +78,67 @@ static __global__ void __launch_bounds__(256) layer_small_kernel(const LayerSmal
       p.g_oproj_b[C + c] = sk;
       p.g_cproj_b[c] = y;
     }
+  }
+}
+
+// part[l][b][n] = sum_k in[l][b][k] * W_l[k][n]  (K = N = 256; W_l = raw [out=k][in=n] projection weight of layer l).
+// grid (N/32, ceil(B/8), L), 256 threads = 32 columns x 8 K-slices; 16 weight loads in flight per thread.
+static __global__ void __launch_bounds__(256) layers_rowgemm_kernel(const float* __restrict__ in, const float* __restrict__ w0,
+                                                                    size_t w_lstride, float* __restrict__ part, int B) {
+  constexpr int K = 256, N = 256, UB = 8, KS = 8;
+  __shared__ float xs[UB * K];
+  __shared__ float ps[KS * UB * 32];
+  const int l = blockIdx.z, b0 = blockIdx.y * UB, col = threadIdx.x & 31, ks = threadIdx.x >> 5;
+  const int n = blockIdx.x * 32 + col;
+  const float* inl = in + (size_t)l * B * K;
+  for (int i = threadIdx.x; i < UB * K; i += 256) {
+    const int u = i / K, k = i - u * K;
+    xs[i] = b0 + u < B ? inl[(size_t)(b0 + u) * K + k] : 0.f;
+  }
+  __syncthreads();
+  const float* w = w0 + (size_t)l * w_lstride;
+  float acc[UB];
+#pragma unroll
+  for (int u = 0; u < UB; ++u) acc[u] = 0.f;
+  const int kbeg = ks * (K / KS);
+  for (int k0 = kbeg; k0 < kbeg + K / KS; k0 += 16) {
+    float wv[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) wv[i] = __ldg(w + (size_t)(k0 + i) * N + n);
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+#pragma unroll
+      for (int u = 0; u < UB; ++u) acc[u] = fmaf(wv[i], xs[u * K + k0 + i], acc[u]);
+  }
+#pragma unroll
+  for (int u = 0; u < UB; ++u) ps[(ks * UB + u) * 32 + col] = acc[u];
+  __syncthreads();
+  const int u = ks;
+  float sum = 0.f;
+#pragma unroll
+  for (int q = 0; q < KS; ++q) sum += ps[(q * UB + u) * 32 + col];
+  if (b0 + u < B) part[((size_t)l * B + b0 + u) * N + n] = sum;
+}
+// out[i] = sum_l part[l][i]   (fixed order)
+static __global__ void sum_layers_kernel(const float* __restrict__ part, int L, int n, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float s = 0.f;
+  for (int l = 0; l < L; ++l) s += part[(size_t)l * n + i];
+  out[i] = s;
+}
+// ddvec[B][C] = sum_l dd_all[l] Wd_l ; dspk[B][H] = sum_l ds_all[l] Ws_l (when spk_w0 != nullptr)
+static inline void launch_dvec_contraction(const float* dd_all, const float* ds_all, const float* dproj_w0, const float* sproj_w0,
+                                           size_t w_lstride, float* part, float* ddvec, float* dspk, int B, int L,
+                                           cudaStream_t s) {
+  const dim3 grid(256 / 32, (B + 7) / 8, L);
+  layers_rowgemm_kernel<<<grid, 256, 0, s>>>(dd_all, dproj_w0, w_lstride, part, B);
+  sum_layers_kernel<<<(B * 256 + 255) / 256, 256, 0, s>>>(part, L, B * 256, ddvec);
+  note_launch(2);
+  if (sproj_w0) {
+    layers_rowgemm_kernel<<<grid, 256, 0, s>>>(ds_all, sproj_w0, w_lstride, part, B);
+    sum_layers_kernel<<<(B * 256 + 255) / 256, 256, 0, s>>>(part, L, B * 256, dspk);
+    note_launch(2);
   }
 }
 

@@ -125,6 +125,22 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
       ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
       : "memory");
 }
+// Multicast form: the bytes land at the same CTA-relative offset in every CTA of `cta_mask` and each destination
+// CTA's mbarrier (same CTA-relative offset) receives the complete_tx.
+__device__ __forceinline__ void bulk_g2s_multicast_addr(uint32_t smem_dst, const void* gmem_src, uint32_t bytes,
+                                                        uint32_t bar_addr, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+      ::"r"(smem_dst), "l"(gmem_src), "r"(bytes), "r"(bar_addr), "h"(cta_mask)
+      : "memory");
+}
+// cta_group::1 commit whose arrive is multicast to the barrier at this offset in every CTA of `cta_mask`
+__device__ __forceinline__ void umma_commit_mc_addr(uint32_t bar_addr, uint16_t cta_mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(bar_addr), "h"(cta_mask)
+      : "memory");
+}
 __device__ __forceinline__ void bulk_prefetch_l2(const void* gmem_src, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem_src), "r"(bytes) : "memory");
 }

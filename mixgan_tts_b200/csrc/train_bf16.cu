@@ -30,6 +30,7 @@ using bf16 = __nv_bfloat16;
 constexpr int C = 256;            // channels == d_encoder (dims_supported)
 constexpr int RLEAD = 8;          // zero rows in front of the first utterance
 constexpr int TILE = 128;         // rows (frames) per CTA tile
+constexpr int FCL = 4;            // frames-GEMM cluster: 4 row tiles share every weight tile (one multicast quarter each)
 constexpr long long kTimeout = 200000000LL;    // ~0.1 s of SM cycles: a protocol bug traps instead of hanging
 constexpr float RSQRT2 = 0.70710678118654752440f;
 
@@ -51,7 +52,7 @@ struct RowSpace { int T, Tg, R, ntiles, Rp; };
 RowSpace row_space(int B, int T) {
   RowSpace r{};
   r.T = T; r.Tg = T + 1; r.R = B * r.Tg;
-  r.ntiles = (r.R + TILE - 1) / TILE;
+  r.ntiles = ((r.R + TILE - 1) / TILE + FCL - 1) / FCL * FCL;
   r.Rp = RLEAD + r.ntiles * TILE + 8;
   return r;
 }
@@ -342,6 +343,11 @@ __device__ __forceinline__ void fgemm_epilogue(const FArgs& p, uint32_t tmem_row
   }
 }
 
+// A cluster of FCL CTAs (FCL consecutive row tiles, same column tile) shares every weight tile: CTA r fetches quarter r
+// and multicasts it into all FCL shared memories, so the L2 serves each weight byte once per cluster instead of once
+// per CTA (measured: 102 CTAs pulling the same 32 KB tile at once are bound by the few L2 slices that hold it).
+// EMPTY barriers count FCL arrivals (every CTA's MMA warp multicasts its commit), so a producer overwrites a stage in its
+// peers only after all of them have consumed it.
 template <int NT, int MODE>
 __global__ void __launch_bounds__(192, 1) fgemm_kernel(const FArgs p) {
   using S = FSmem<NT>;
@@ -352,15 +358,18 @@ __global__ void __launch_bounds__(192, 1) fgemm_kernel(const FArgs p) {
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int tile = blockIdx.x, ntile = blockIdx.y;
+  const uint32_t rank = tc::cluster_ctarank();
+  constexpr uint16_t kMask = (1u << FCL) - 1;
 
   if (warp == 1) tc::tmem_alloc<NT>(&tmem_slot);
   if (tid == 0) {
-    for (int i = 0; i < S::STAGES; ++i) { tc::mbar_init(&bar_full[i], 1); tc::mbar_init(&bar_empty[i], 1); }
+    for (int i = 0; i < S::STAGES; ++i) { tc::mbar_init(&bar_full[i], 1); tc::mbar_init(&bar_empty[i], FCL); }
     tc::mbar_init(&bar_acc, 1);
     tc::fence_barrier_init();
   }
   tc::tc_fence_before();
   __syncthreads();
+  tc::cluster_sync_all();            // every CTA's barriers exist before any multicast / remote arrive
   tc::tc_fence_after();
   const uint32_t tmem = tmem_slot;
 
@@ -370,10 +379,10 @@ __global__ void __launch_bounds__(192, 1) fgemm_kernel(const FArgs p) {
 
   if (warp == 0) {
     if (lane == 0) {
-      const bf16* bsrc = p.Bpk + ((size_t)ntile * p.ksteps_b + p.kstep_b0) * (size_t)(NT * 64);
+      const bf16* bsrc = p.Bpk + ((size_t)ntile * p.ksteps_b + p.kstep_b0) * (size_t)(NT * 64) + (size_t)rank * (NT * 64 / FCL);
       for (int s = 0; s < nsteps; ++s) {
         const int stage = s % S::STAGES, ph = (s / S::STAGES) & 1;
-        tc::mbar_wait_trap(tc::smem_u32(&bar_empty[stage]), ph ^ 1, kTimeout, p.status, 1);
+        tc::mbar_wait_cluster_trap(tc::smem_u32(&bar_empty[stage]), ph ^ 1, kTimeout, p.status, 1);
         const int tap = s / per_tap, j = s - tap * per_tap;
         const bf16* img = j < p.steps0 ? p.A0 : p.A1;
         const int ch0 = (j < p.steps0 ? j : j - p.steps0) * 8;
@@ -384,7 +393,7 @@ __global__ void __launch_bounds__(192, 1) fgemm_kernel(const FArgs p) {
 #pragma unroll
         for (int c = 0; c < 8; ++c)
           tc::bulk_g2s_addr(sa + c * (TILE * 16), img + ((size_t)(ch0 + c) * p.Rp + row) * 8, TILE * 16, fb);
-        tc::bulk_g2s_addr(sb, bsrc + (size_t)s * (NT * 64), S::B_BYTES, fb);
+        tc::bulk_g2s_multicast_addr(sb + rank * (S::B_BYTES / FCL), bsrc + (size_t)s * (NT * 64), S::B_BYTES / FCL, fb, kMask);
       }
     }
   } else if (warp == 1) {
@@ -392,7 +401,7 @@ __global__ void __launch_bounds__(192, 1) fgemm_kernel(const FArgs p) {
       const uint32_t idesc = tc::make_idesc_bf16(128, NT);
       for (int s = 0; s < nsteps; ++s) {
         const int stage = s % S::STAGES, ph = (s / S::STAGES) & 1;
-        tc::mbar_wait_trap(tc::smem_u32(&bar_full[stage]), ph, kTimeout, p.status, 2);
+        tc::mbar_wait_cluster_trap(tc::smem_u32(&bar_full[stage]), ph, kTimeout, p.status, 2);
         tc::tc_fence_after();
         const uint32_t sa = smem_base + stage * S::STAGE, sb = sa + S::A_BYTES;
 #pragma unroll
@@ -401,7 +410,7 @@ __global__ void __launch_bounds__(192, 1) fgemm_kernel(const FArgs p) {
           const uint64_t bd = tc::make_smem_desc(sb + k * 2 * (NT * 16), NT * 16, 128);
           tc::umma_bf16(tmem, ad, bd, idesc, (s | k) ? 1u : 0u);
         }
-        tc::umma_commit(&bar_empty[stage]);
+        tc::umma_commit_mc_addr(tc::smem_u32(&bar_empty[stage]), kMask);
       }
       tc::umma_commit(&bar_acc);
     }
@@ -418,6 +427,18 @@ __global__ void __launch_bounds__(192, 1) fgemm_kernel(const FArgs p) {
   tc::tc_fence_before();
   __syncthreads();
   if (warp == 1) tc::tmem_dealloc<NT>(tmem);
+  tc::cluster_sync_all();            // no CTA leaves while a peer may still multicast into it or arrive on its barriers
+}
+
+template <typename K, typename A>
+cudaError_t launch_cluster(K kernel, dim3 grid, int cluster_x, size_t smem, cudaStream_t s, const A& args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = dim3(192); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = cluster_x; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, args);
 }
 
 template <int NT, int MODE>
@@ -428,7 +449,7 @@ int launch_fgemm(const FArgs& a, int ntiles, int n_tiles_n, cudaStream_t s) {
                                         FSmem<NT>::TOTAL));
     configured = true;
   }
-  fgemm_kernel<NT, MODE><<<dim3(ntiles, n_tiles_n), 192, FSmem<NT>::TOTAL, s>>>(a);
+  MGB_CUDA_CHECK(launch_cluster(fgemm_kernel<NT, MODE>, dim3(ntiles, n_tiles_n), FCL, FSmem<NT>::TOTAL, s, a));
   note_launch();
   if (trace_on()) { char b[64]; snprintf(b, sizeof b, "fgemm<%d, mode %d>", NT, MODE); trace(b, s); }
   return MGB_OK;

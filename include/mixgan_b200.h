@@ -220,6 +220,12 @@ int mgb_probe_umma_rate(int cta2, int grid, int n, int ksteps, int reps, int nac
                         int a_kadv, int b_lbo, int b_sbo, int b_kadv, int b_off, long long* cycles_out,
                         int* status_out, void* stream);
 
+/* Bulk-copy ingest-rate probe (scripts/bulk_rate.py): `grid` CTAs each stream iters * copies_per_slot copies of copy_bytes
+ * from `src` (device, src_bytes long, L2-resident when small) into a `slots`-deep shared-memory ring; cycles_out[i] = SM
+ * cycles CTA i needed.  Measures how the per-SM shared-memory fill rate depends on the size of one cp.async.bulk. */
+int mgb_probe_bulk_rate(const void* src, long long src_bytes, int grid, int copy_bytes, int copies_per_slot,
+                        int slots, int iters, long long* cycles_out, int* status_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

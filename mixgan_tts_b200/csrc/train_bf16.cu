@@ -575,7 +575,9 @@ __global__ void __launch_bounds__(192, 1) wgemm_kernel(const WgArgs p) {
 
 struct WPlan { int S, blocks_per_split; };
 WPlan plan_wg(int nblocks, int mtiles, int ntiles) {
-  int S = (148 + mtiles * ntiles - 1) / (mtiles * ntiles);     // about one CTA per SM
+  int S = (148 + mtiles * ntiles - 1) / (mtiles * ntiles);     // about one CTA per SM ...
+  const int cap = (nblocks + 3) / 4;                           // ... but at least 4 frame blocks per CTA: every split costs a
+  if (S > cap) S = cap;                                        // 128 x NT fp32 partial that the reduction has to read back
   if (S > nblocks) S = nblocks;
   if (S < 1) S = 1;
   const int per = (nblocks + S - 1) / S;
@@ -617,7 +619,7 @@ struct PackDesc {
   long long dst, base;
   int N, NT, Kin, Kin_pad, taps, sn, sc, st, rev, perm;
 };
-constexpr int PACK_MAX = 8;
+constexpr int PACK_MAX = 42;
 struct PackArgs { PackDesc d[PACK_MAX]; int n; const float* flat; bf16* out; };
 
 __global__ void __launch_bounds__(256) pack_tiles_kernel(const PackArgs a) {
@@ -717,6 +719,29 @@ __global__ void __launch_bounds__(256) img_colsum_kernel(const bf16* __restrict_
     out[(size_t)b * ldo + chunk * 8 + threadIdx.x] = s;
   }
 }
+// up to three images in one launch (blockIdx.x runs over the concatenated chunk lists)
+struct Colsum3 { const bf16* img[3]; float* out[3]; int nchunks[3], ldo[3]; };
+__global__ void __launch_bounds__(256) img_colsum3_kernel(const Colsum3 a, int Rp, int T) {
+  __shared__ float red[256][9];
+  int chunk = blockIdx.x, w = 0;
+  while (w < 2 && chunk >= a.nchunks[w]) { chunk -= a.nchunks[w]; ++w; }
+  const int b = blockIdx.y;
+  const bf16* base = a.img[w] + ((size_t)chunk * Rp + RLEAD + (size_t)b * (T + 1)) * 8;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int t = threadIdx.x; t < T; t += 256) {
+    const uint4 u = *reinterpret_cast<const uint4*>(base + (size_t)t * 8);
+    const float2 p0 = unpack2(u.x), p1 = unpack2(u.y), p2 = unpack2(u.z), p3 = unpack2(u.w);
+    acc[0] += p0.x; acc[1] += p0.y; acc[2] += p1.x; acc[3] += p1.y; acc[4] += p2.x; acc[5] += p2.y; acc[6] += p3.x; acc[7] += p3.y;
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) red[threadIdx.x][e] = acc[e];
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    float s = 0.f;
+    for (int k = 0; k < 256; ++k) s += red[k][threadIdx.x];
+    a.out[w][(size_t)b * a.ldo[w] + chunk * 8 + threadIdx.x] = s;
+  }
+}
 void launch_colsum_img(const bf16* img, int nchunks, const RowSpace& rs, int B, float* out, int ldo, cudaStream_t s) {
   img_colsum_kernel<<<dim3(nchunks, B), 256, 0, s>>>(img, rs.Rp, rs.T, out, ldo);
   note_launch();
@@ -789,7 +814,7 @@ Saved16 saved16_layout(const mgb_model_dims& d, int B, int T) {
 }
 
 struct Work16 {      // byte offsets into the workspace
-  size_t status, X, S, dtab, ctab, dout, dPre, dS, E, Eimg, dZ, dY, part, usumE, usumZ, usumY, usumS, usumT, ddvec,
+  size_t status, X, S, dtab, ctab, dout, dPre, dS, E, Eimg, dZ, dY, part, usumE, usumE2, usumZ, usumY, usumS, usumT, ddvec,
       dspk, dpre, dd_all, ds_all, lpart, total;
 };
 Work16 work16_layout(const mgb_model_dims& d, int B, int T) {
@@ -818,6 +843,7 @@ Work16 work16_layout(const mgb_model_dims& d, int B, int T) {
   mx(wg_part_floats(rs.ntiles, 256, 80, 1, 128));
   w.part = take(part * 4);
   w.usumE = take((size_t)B * C * 4);
+  w.usumE2 = take((size_t)B * C * 4);
   w.usumZ = take((size_t)B * 2 * C * 4);
   w.usumY = take((size_t)B * C * 4);
   w.usumS = take((size_t)B * C * 4);
@@ -844,32 +870,30 @@ int pack_step_weights(const mgb_model_dims& d, const float* flat, bf16* out, cud
   };
   auto run = [&](PackArgs& a) {
     a.flat = flat; a.out = out;
-    pack_tiles_kernel<<<dim3(96, a.n), 256, 0, s>>>(a);
+    pack_tiles_kernel<<<dim3(48, a.n), 256, 0, s>>>(a);
     note_launch();
   };
-  {
-    PackArgs a{};
-    a.n = 6;
-    a.d[0] = desc(o.in_f, f.in_w, C, 256, M, 1, M, 1, 0, 0, 0);          // W[c][m]
-    a.d[1] = desc(o.skip_f, f.skip_w, C, 256, C, 1, C, 1, 0, 0, 0);
-    a.d[2] = desc(o.out_f, f.out_w, M, 128, C, 1, C, 1, 0, 0, 0);        // W[m][c]
-    a.d[3] = desc(o.out_b, f.out_w, C, 256, M, 1, 1, C, 0, 0, 0);        // W_eff[n=c][k=m] = Wout[m][c]
-    a.d[4] = desc(o.skip_b, f.skip_w, C, 256, C, 1, 1, C, 0, 0, 0);      // Wsk^T
-    a.d[5] = desc(o.in_b, f.in_w, M, 128, C, 1, 1, M, 0, 0, 0);          // W_eff[n=m][k=c] = Win[c][m]
-    run(a);
-  }
+  PackArgs a{};
+  auto push = [&](const PackDesc& pd) {
+    a.d[a.n++] = pd;
+    if (a.n == PACK_MAX) { run(a); a.n = 0; }
+  };
+  push(desc(o.in_f, f.in_w, C, 256, M, 1, M, 1, 0, 0, 0));          // W[c][m]
+  push(desc(o.skip_f, f.skip_w, C, 256, C, 1, C, 1, 0, 0, 0));
+  push(desc(o.out_f, f.out_w, M, 128, C, 1, C, 1, 0, 0, 0));        // W[m][c]
+  push(desc(o.out_b, f.out_w, C, 256, M, 1, 1, C, 0, 0, 0));        // W_eff[n=c][k=m] = Wout[m][c]
+  push(desc(o.skip_b, f.skip_w, C, 256, C, 1, 1, C, 0, 0, 0));      // Wsk^T
+  push(desc(o.in_b, f.in_w, M, 128, C, 1, 1, M, 0, 0, 0));          // W_eff[n=m][k=c] = Win[c][m]
   for (int l = 0; l < d.layers; ++l) {
     const size_t fl = f.layer0 + (size_t)l * f.layer_stride, ol = o.layer0 + (size_t)l * o.layer_stride;
-    PackArgs a{};
-    a.n = 6;
-    a.d[0] = desc(ol + o.r_cond_f, fl + f.rel.cproj_w, C, 256, C, 1, C, 1, 0, 0, 0);
-    a.d[1] = desc(ol + o.r_conv_f, fl + f.rel.conv_w, 2 * C, 256, C, 3, 3 * C, 3, 1, 0, 1);      // W3[co][ci][tap], gate|filter tiles
-    a.d[2] = desc(ol + o.r_oproj_f, fl + f.rel.oproj_w, 2 * C, 256, C, 1, C, 1, 0, 0, 1);        // Wo[co][ci], x|skip tiles
-    a.d[3] = desc(ol + o.r_oproj_b, fl + f.rel.oproj_w, C, 256, 2 * C, 1, 1, C, 0, 0, 0);        // W_eff[n=ci][k=co]
-    a.d[4] = desc(ol + o.r_conv_b, fl + f.rel.conv_w, C, 256, 2 * C, 3, 3, 3 * C, 1, 1, 0);      // W_eff[n=ci][tap', co] = W3[co][ci][2-tap']
-    a.d[5] = desc(o.cond_b_all + (size_t)l * 256 * 256, fl + f.rel.cproj_w, C, 256, C, 1, 1, C, 0, 0, 0);   // Wc^T
-    run(a);
+    push(desc(ol + o.r_cond_f, fl + f.rel.cproj_w, C, 256, C, 1, C, 1, 0, 0, 0));
+    push(desc(ol + o.r_conv_f, fl + f.rel.conv_w, 2 * C, 256, C, 3, 3 * C, 3, 1, 0, 1));      // W3[co][ci][tap], gate|filter tiles
+    push(desc(ol + o.r_oproj_f, fl + f.rel.oproj_w, 2 * C, 256, C, 1, C, 1, 0, 0, 1));        // Wo[co][ci], x|skip tiles
+    push(desc(ol + o.r_oproj_b, fl + f.rel.oproj_w, C, 256, 2 * C, 1, 1, C, 0, 0, 0));        // W_eff[n=ci][k=co]
+    push(desc(ol + o.r_conv_b, fl + f.rel.conv_w, C, 256, 2 * C, 3, 3, 3 * C, 1, 1, 0));      // W_eff[n=ci][tap', co] = W3[co][ci][2-tap']
+    push(desc(o.cond_b_all + (size_t)l * 256 * 256, fl + f.rel.cproj_w, C, 256, C, 1, 1, C, 0, 0, 0));   // Wc^T
   }
+  if (a.n) run(a);
   MGB_LAUNCH_CHECK();
   return MGB_OK;
 }
@@ -1028,9 +1052,7 @@ int bf16_train_backward(const mgb_model_dims& d, const float* flat, const void* 
       } else {
         if (int rc = launch_wg<256>(cimg(W + w.Eimg), cimg(W + w.dS), 2, 2 * C, cimg(sl + sv.rG), C, 1, rs, part,
                                     gl + f.rel.oproj_w, status, s)) return rc;
-        launch_colsum_img(cimg(W + w.Eimg), 32, rs, B, f32(W + w.usumE), C, s);
       }
-      launch_colsum_img(cimg(W + w.dZ), 64, rs, B, f32(W + w.usumZ), 2 * C, s);
       {
         FArgs a = base;                                 // dY = conv3^T(dZ); dx = e + dY; e' = dx / sqrt(2)
         a.A0 = cimg(W + w.dZ); a.steps0 = 8; a.taps = 3; a.Bpk = wl + o.r_conv_b; a.ksteps_b = 24;
@@ -1042,9 +1064,21 @@ int bf16_train_backward(const mgb_model_dims& d, const float* flat, const void* 
                                   status, s)) return rc;
       if (int rc = launch_wg<256>(dYl, nullptr, 2, C, cimg(SV + sv.cond), H, 1, rs, part, gl + f.rel.cproj_w,
                                   status, s)) return rc;
-      launch_colsum_img(dYl, 32, rs, B, f32(W + w.usumY), C, s);
+      // per-utterance column sums of dZ_l, dY_l and of the NEW e image (= e_{l-1}, used by the next block's small terms):
+      // one launch; the two e-sum buffers alternate between blocks
+      float* usumE_cur = f32(W + ((seg & 1) ? w.usumE : w.usumE2));
+      float* usumE_next = f32(W + ((seg & 1) ? w.usumE2 : w.usumE));
+      {
+        Colsum3 c3{};
+        c3.img[0] = cimg(W + w.dZ); c3.nchunks[0] = 64; c3.out[0] = f32(W + w.usumZ); c3.ldo[0] = 2 * C;
+        c3.img[1] = dYl; c3.nchunks[1] = 32; c3.out[1] = f32(W + w.usumY); c3.ldo[1] = C;
+        c3.img[2] = cimg(W + w.Eimg); c3.nchunks[2] = 32; c3.out[2] = usumE_next; c3.ldo[2] = C;
+        img_colsum3_kernel<<<dim3(128, B), 256, 0, s>>>(c3, rs.Rp, rs.T);
+        note_launch();
+        trace("img_colsum3", s);
+      }
       LayerSmallArgs q{};
-      q.usumE = top ? nullptr : f32(W + w.usumE); q.usumZ = f32(W + w.usumZ); q.usumY = f32(W + w.usumY);
+      q.usumE = top ? nullptr : usumE_cur; q.usumZ = f32(W + w.usumZ); q.usumY = f32(W + w.usumY);
       q.usumS = f32(W + w.usumS); q.dvec = cf32(SV + sv.dvec); q.spk = d.multi_speaker ? spk : nullptr;
       q.Wd = fl + f.rel.dproj_w; q.Ws = d.multi_speaker ? fl + f.rel.sproj_w : nullptr;
       q.g_conv_b = gl + f.rel.conv_b; q.g_oproj_b = gl + f.rel.oproj_b; q.g_cproj_b = gl + f.rel.cproj_b;

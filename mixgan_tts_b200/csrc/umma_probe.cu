@@ -304,3 +304,56 @@ extern "C" int mgb_probe_umma_rate(int cta2, int grid, int n, int ksteps, int re
   MGB_LAUNCH_CHECK();
   return MGB_OK;
 }
+
+
+// ---- bulk-copy (TMA engine, 1-D) ingest-rate probe: every CTA streams `total_bytes` from an L2-resident buffer into a
+// 2-slot shared-memory ring with copies of `copy_bytes` each (`copies_per_slot` per barrier phase) and reports cycles.
+namespace mgb {
+namespace {
+struct BulkRateArgs { const uint8_t* src; long long src_bytes; int copy_bytes, copies_per_slot, slots, iters; long long* cycles; int* status; };
+__global__ void __launch_bounds__(64, 1) bulk_rate_kernel(const BulkRateArgs p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bar[8];
+  const int tid = threadIdx.x;
+  if (tid == 0) { for (int i = 0; i < p.slots; ++i) tc::mbar_init(&bar[i], 1); tc::fence_barrier_init(); }
+  __syncthreads();
+  if (tid == 0) {
+    const int slot_bytes = p.copy_bytes * p.copies_per_slot;
+    const long long span = p.src_bytes - slot_bytes;
+    long long off = ((long long)blockIdx.x * 7919 * slot_bytes) % span;
+    off &= ~15LL;
+    const long long t0 = clock64();
+    for (int it = 0; it < p.iters + p.slots; ++it) {
+      const int slot = it % p.slots;
+      if (it >= p.slots) {                              // wait for the copies issued `slots` iterations ago
+        if (!tc::mbar_wait(&bar[slot], ((it / p.slots) - 1) & 1, 400000000LL)) { atomicOr(p.status, 1); break; }
+      }
+      if (it < p.iters) {
+        tc::mbar_arrive_expect_tx(&bar[slot], (uint32_t)slot_bytes);
+        for (int c = 0; c < p.copies_per_slot; ++c)
+          tc::bulk_g2s(smem + (size_t)slot * slot_bytes + (size_t)c * p.copy_bytes, p.src + off + (size_t)c * p.copy_bytes,
+                       (uint32_t)p.copy_bytes, &bar[slot]);
+        off += slot_bytes;
+        if (off > span) off = 0;
+      }
+    }
+    p.cycles[blockIdx.x] = clock64() - t0;
+  }
+}
+}  // namespace
+}  // namespace mgb
+
+extern "C" int mgb_probe_bulk_rate(const void* src, long long src_bytes, int grid, int copy_bytes, int copies_per_slot,
+                                   int slots, int iters, long long* cycles_out, int* status_out, void* stream) {
+  using namespace mgb;
+  MGB_REQUIRE(src && cycles_out && status_out && grid > 0 && copy_bytes % 16 == 0 && copy_bytes > 0 && copies_per_slot > 0 &&
+              slots >= 1 && slots <= 8 && iters > 0, MGB_E_ARG, "bad argument");
+  const size_t smem = (size_t)copy_bytes * copies_per_slot * slots;
+  MGB_REQUIRE(smem <= 200 * 1024 && (long long)copy_bytes * copies_per_slot * 2 < src_bytes, MGB_E_ARG, "ring too large");
+  if (int rc = check_arch()) return rc;
+  BulkRateArgs a{static_cast<const uint8_t*>(src), src_bytes, copy_bytes, copies_per_slot, slots, iters, cycles_out, status_out};
+  MGB_CUDA_CHECK(cudaFuncSetAttribute(bulk_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  bulk_rate_kernel<<<grid, 64, smem, static_cast<cudaStream_t>(stream)>>>(a);
+  MGB_LAUNCH_CHECK();
+  return MGB_OK;
+}

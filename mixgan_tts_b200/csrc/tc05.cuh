@@ -141,6 +141,22 @@ __device__ __forceinline__ void umma_commit_mc_addr(uint32_t bar_addr, uint16_t 
       ::"r"(bar_addr), "h"(cta_mask)
       : "memory");
 }
+// Tensor-map TMA, 2-D tile: one instruction moves a whole box (measured on B200: a 2 KB cp.async.bulk costs ~60-110 cycles
+// of TMA-engine time whatever its size, so many small 1-D copies fill shared memory at ~20-30 B/clk/SM while one 16-64 KB box
+// reaches 75-125 B/clk/SM; profiles/r01/bulk_copy_rate_probe.txt).  `tmap` = generic address of a __grid_constant__ CUtensorMap.
+__device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const void* tmap, int c0, int c1, uint32_t bar_addr) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(smem_dst), "l"(tmap), "r"(c0), "r"(c1), "r"(bar_addr)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_multicast(uint32_t smem_dst, const void* tmap, int c0, int c1, uint32_t bar_addr,
+                                                      uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%2, %3}], [%4], %5;"
+      ::"r"(smem_dst), "l"(tmap), "r"(c0), "r"(c1), "r"(bar_addr), "h"(cta_mask)
+      : "memory");
+}
 __device__ __forceinline__ void bulk_prefetch_l2(const void* gmem_src, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem_src), "r"(bytes) : "memory");
 }

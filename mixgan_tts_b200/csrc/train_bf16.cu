@@ -18,6 +18,7 @@
 #include "tc05.cuh"
 #include "train_small.cuh"
 
+#include <cuda.h>
 #include <cstdlib>
 
 namespace mgb {
@@ -46,6 +47,36 @@ void trace(const char* what, cudaStream_t s) {
   const cudaError_t e = cudaStreamSynchronize(s);
   fprintf(stderr, " %s\n", cudaGetErrorString(e));
   fflush(stderr);
+}
+
+// Tensor map of an activation image [nchunks][Rp][8] bf16, seen as a 2-D array of 8-byte words: dim0 = 2 words per row
+// (contiguous, Rp rows), dim1 = chunks.  A box of 256 words x k chunks is 128 rows x 8k channels and lands in shared memory
+// as [chunk][128 rows][16 B] — the no-swizzle core-matrix order both GEMM families read.  Coordinates: (2 * row, chunk).
+typedef CUresult (*TmapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+TmapEncodeFn tmap_encode_fn() {
+  static TmapEncodeFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess) p = nullptr;
+    return reinterpret_cast<TmapEncodeFn>(p);
+  }();
+  return fn;
+}
+int make_image_map(CUtensorMap* m, const void* img, int nchunks, int Rp, int box_chunks) {
+  TmapEncodeFn fn = tmap_encode_fn();
+  MGB_REQUIRE(fn != nullptr, MGB_E_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+  const cuuint64_t dims[2] = {(cuuint64_t)Rp * 2, (cuuint64_t)nchunks};
+  const cuuint64_t strides[1] = {(cuuint64_t)Rp * 16};
+  const cuuint32_t box[2] = {256, (cuuint32_t)box_chunks};
+  const cuuint32_t es[2] = {1, 1};
+  const CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, const_cast<void*>(img), dims, strides, box, es,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  MGB_REQUIRE(r == CUDA_SUCCESS, MGB_E_CUDA, "cuTensorMapEncodeTiled failed (%d) for an image of %d chunks x %d rows", (int)r,
+              nchunks, Rp);
+  return MGB_OK;
 }
 
 struct RowSpace { int T, Tg, R, ntiles, Rp; };
@@ -343,13 +374,16 @@ __device__ __forceinline__ void fgemm_epilogue(const FArgs& p, uint32_t tmem_row
   }
 }
 
-// A cluster of FCL CTAs (FCL consecutive row tiles, same column tile) shares every weight tile: CTA r fetches quarter r
-// and multicasts it into all FCL shared memories, so the L2 serves each weight byte once per cluster instead of once
+// A cluster of CL CTAs (CL consecutive row tiles, same column tile) shares every weight tile: CTA r fetches part r
+// and multicasts it into all CL shared memories, so the L2 serves each weight byte once per cluster instead of once
 // per CTA (measured: 102 CTAs pulling the same 32 KB tile at once are bound by the few L2 slices that hold it).
-// EMPTY barriers count FCL arrivals (every CTA's MMA warp multicasts its commit), so a producer overwrites a stage in its
-// peers only after all of them have consumed it.
-template <int NT, int MODE>
-__global__ void __launch_bounds__(192, 1) fgemm_kernel(const FArgs p) {
+// EMPTY barriers count CL arrivals (every CTA's MMA warp multicasts its commit), so a producer overwrites a stage in its
+// peers only after all of them have consumed it.  CL = 4 for GEMMs with one column tile; CL = 2 for the N = 512 GEMMs
+// (two column tiles): with one 193 KB CTA per SM only ~32 clusters of 4 fit on the 148 SMs at once (sum over GPCs of
+// floor(SMs / 4)), and 2 x 26 clusters of 4 would run as two waves.
+template <int NT, int MODE, int CL>
+__global__ void __launch_bounds__(192, 1) fgemm_kernel(const FArgs p, const __grid_constant__ CUtensorMap tmA0,
+                                                       const __grid_constant__ CUtensorMap tmA1) {
   using S = FSmem<NT>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -359,11 +393,11 @@ __global__ void __launch_bounds__(192, 1) fgemm_kernel(const FArgs p) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int tile = blockIdx.x, ntile = blockIdx.y;
   const uint32_t rank = tc::cluster_ctarank();
-  constexpr uint16_t kMask = (1u << FCL) - 1;
+  constexpr uint16_t kMask = (1u << CL) - 1;
 
   if (warp == 1) tc::tmem_alloc<NT>(&tmem_slot);
   if (tid == 0) {
-    for (int i = 0; i < S::STAGES; ++i) { tc::mbar_init(&bar_full[i], 1); tc::mbar_init(&bar_empty[i], FCL); }
+    for (int i = 0; i < S::STAGES; ++i) { tc::mbar_init(&bar_full[i], 1); tc::mbar_init(&bar_empty[i], CL); }
     tc::mbar_init(&bar_acc, 1);
     tc::fence_barrier_init();
   }
@@ -379,21 +413,19 @@ __global__ void __launch_bounds__(192, 1) fgemm_kernel(const FArgs p) {
 
   if (warp == 0) {
     if (lane == 0) {
-      const bf16* bsrc = p.Bpk + ((size_t)ntile * p.ksteps_b + p.kstep_b0) * (size_t)(NT * 64) + (size_t)rank * (NT * 64 / FCL);
+      const bf16* bsrc = p.Bpk + ((size_t)ntile * p.ksteps_b + p.kstep_b0) * (size_t)(NT * 64) + (size_t)rank * (NT * 64 / CL);
       for (int s = 0; s < nsteps; ++s) {
         const int stage = s % S::STAGES, ph = (s / S::STAGES) & 1;
         tc::mbar_wait_cluster_trap(tc::smem_u32(&bar_empty[stage]), ph ^ 1, kTimeout, p.status, 1);
         const int tap = s / per_tap, j = s - tap * per_tap;
-        const bf16* img = j < p.steps0 ? p.A0 : p.A1;
+        const void* tm = j < p.steps0 ? &tmA0 : &tmA1;
         const int ch0 = (j < p.steps0 ? j : j - p.steps0) * 8;
         const int row = RLEAD + tile * TILE + tap - (p.taps >> 1);
         const uint32_t sa = smem_base + stage * S::STAGE, sb = sa + S::A_BYTES;
         const uint32_t fb = tc::smem_u32(&bar_full[stage]);
         tc::mbar_arrive_expect_tx_addr(fb, S::STAGE);
-#pragma unroll
-        for (int c = 0; c < 8; ++c)
-          tc::bulk_g2s_addr(sa + c * (TILE * 16), img + ((size_t)(ch0 + c) * p.Rp + row) * 8, TILE * 16, fb);
-        tc::bulk_g2s_multicast_addr(sb + rank * (S::B_BYTES / FCL), bsrc + (size_t)s * (NT * 64), S::B_BYTES / FCL, fb, kMask);
+        tc::tma_load_2d(sa, tm, 2 * row, ch0, fb);          // 128 rows x 64 channels in ONE 16 KB box
+        tc::bulk_g2s_multicast_addr(sb + rank * (S::B_BYTES / CL), bsrc + (size_t)s * (NT * 64), S::B_BYTES / CL, fb, kMask);
       }
     }
   } else if (warp == 1) {
@@ -430,26 +462,31 @@ __global__ void __launch_bounds__(192, 1) fgemm_kernel(const FArgs p) {
   tc::cluster_sync_all();            // no CTA leaves while a peer may still multicast into it or arrive on its barriers
 }
 
-template <typename K, typename A>
-cudaError_t launch_cluster(K kernel, dim3 grid, int cluster_x, size_t smem, cudaStream_t s, const A& args) {
+template <typename K, typename... A>
+cudaError_t launch_cluster(K kernel, dim3 grid, int cluster_x, size_t smem, cudaStream_t s, const A&... args) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid; cfg.blockDim = dim3(192); cfg.dynamicSmemBytes = smem; cfg.stream = s;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = cluster_x; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, kernel, args);
+  return cudaLaunchKernelEx(&cfg, kernel, args...);
 }
 
 template <int NT, int MODE>
 int launch_fgemm(const FArgs& a, int ntiles, int n_tiles_n, cudaStream_t s) {
+  constexpr int CL = (MODE == F_GATE || MODE == F_OUT) ? 2 : FCL;
   static bool configured = false;
   if (!configured) {
-    MGB_CUDA_CHECK(cudaFuncSetAttribute(fgemm_kernel<NT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    MGB_CUDA_CHECK(cudaFuncSetAttribute(fgemm_kernel<NT, MODE, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         FSmem<NT>::TOTAL));
     configured = true;
   }
-  MGB_CUDA_CHECK(launch_cluster(fgemm_kernel<NT, MODE>, dim3(ntiles, n_tiles_n), FCL, FSmem<NT>::TOTAL, s, a));
+  CUtensorMap m0, m1;
+  if (int rc = make_image_map(&m0, a.A0, a.steps0 * 8, a.Rp, 8)) return rc;
+  if (a.steps1 > 0) { if (int rc = make_image_map(&m1, a.A1, a.steps1 * 8, a.Rp, 8)) return rc; }
+  else m1 = m0;
+  MGB_CUDA_CHECK(launch_cluster(fgemm_kernel<NT, MODE, CL>, dim3(ntiles, n_tiles_n), CL, FSmem<NT>::TOTAL, s, a, m0, m1));
   note_launch();
   if (trace_on()) { char b[64]; snprintf(b, sizeof b, "fgemm<%d, mode %d>", NT, MODE); trace(b, s); }
   return MGB_OK;
@@ -476,7 +513,9 @@ struct WSmem {
 };
 
 template <int NT>
-__global__ void __launch_bounds__(192, 1) wgemm_kernel(const WgArgs p) {
+__global__ void __launch_bounds__(192, 1) wgemm_kernel(const WgArgs p, const __grid_constant__ CUtensorMap tmP0,
+                                                       const __grid_constant__ CUtensorMap tmP1,
+                                                       const __grid_constant__ CUtensorMap tmQ) {
   using S = WSmem<NT>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -503,22 +542,21 @@ __global__ void __launch_bounds__(192, 1) wgemm_kernel(const WgArgs p) {
   const uint32_t smem_base = tc::smem_u32(smem);
 
   if (warp == 0) {
-    const bf16* P = mtile < p.mtiles0 ? p.P0 : p.P1;
-    const int mchunk0 = (mtile < p.mtiles0 ? mtile : mtile - p.mtiles0) * 16;
-    const int nchunk0 = nt * (NT / 8);
-    const int sh = tap - (p.taps >> 1);
-    for (int s = 0; s < nsteps; ++s) {
-      const int stage = s % S::STAGES, ph = (s / S::STAGES) & 1;
-      tc::mbar_wait_trap(tc::smem_u32(&bar_empty[stage]), ph ^ 1, kTimeout, p.status, 1);
-      const uint32_t sa = smem_base + stage * S::STAGE, sb = sa + S::A_BYTES;
-      const uint32_t fb = tc::smem_u32(&bar_full[stage]);
-      if (lane == 0) tc::mbar_arrive_expect_tx_addr(fb, S::STAGE);
-      __syncwarp();
-      const int row = RLEAD + (kb0 + s) * TILE;
-      if (lane < 16)
-        tc::bulk_g2s_addr(sa + lane * (TILE * 16), P + ((size_t)(mchunk0 + lane) * p.Rp + row) * 8, TILE * 16, fb);
-      for (int c = lane; c < NT / 8; c += 32)
-        tc::bulk_g2s_addr(sb + c * (TILE * 16), p.Q + ((size_t)(nchunk0 + c) * p.Rp + row + sh) * 8, TILE * 16, fb);
+    if (lane == 0) {
+      const void* tmP = mtile < p.mtiles0 ? &tmP0 : &tmP1;
+      const int mchunk0 = (mtile < p.mtiles0 ? mtile : mtile - p.mtiles0) * 16;
+      const int nchunk0 = nt * (NT / 8);
+      const int sh = tap - (p.taps >> 1);
+      for (int s = 0; s < nsteps; ++s) {
+        const int stage = s % S::STAGES, ph = (s / S::STAGES) & 1;
+        tc::mbar_wait_trap(tc::smem_u32(&bar_empty[stage]), ph ^ 1, kTimeout, p.status, 1);
+        const uint32_t sa = smem_base + stage * S::STAGE, sb = sa + S::A_BYTES;
+        const uint32_t fb = tc::smem_u32(&bar_full[stage]);
+        tc::mbar_arrive_expect_tx_addr(fb, S::STAGE);
+        const int row = RLEAD + (kb0 + s) * TILE;
+        tc::tma_load_2d(sa, tmP, 2 * row, mchunk0, fb);              // 128 channels x 128 frames: one 32 KB box
+        tc::tma_load_2d(sb, &tmQ, 2 * (row + sh), nchunk0, fb);      // NT channels x 128 frames: one 32/64 KB box
+      }
     }
   } else if (warp == 1) {
     if (lane == 0) {
@@ -575,8 +613,8 @@ __global__ void __launch_bounds__(192, 1) wgemm_kernel(const WgArgs p) {
 
 struct WPlan { int S, blocks_per_split; };
 WPlan plan_wg(int nblocks, int mtiles, int ntiles) {
-  int S = (148 + mtiles * ntiles - 1) / (mtiles * ntiles);     // about one CTA per SM ...
-  const int cap = (nblocks + 3) / 4;                           // ... but at least 4 frame blocks per CTA: every split costs a
+  int S = 148 / (mtiles * ntiles);                             // one wave: at most one CTA per SM ...
+  const int cap = (nblocks + 1) / 2;                           // ... but at least 2 frame blocks per CTA: every split costs a
   if (S > cap) S = cap;                                        // 128 x NT fp32 partial that the reduction has to read back
   if (S > nblocks) S = nblocks;
   if (S < 1) S = 1;
@@ -603,7 +641,12 @@ int launch_wg(const bf16* P0, const bf16* P1, int mtiles0, int Mo, const bf16* Q
   const int mt = (Mo + 127) / 128, ntl = taps * a.ntiles_per_tap;
   const WPlan pl = plan_wg(rs.ntiles, mt, ntl);
   a.blocks_per_split = pl.blocks_per_split;
-  wgemm_kernel<NT><<<dim3(mt, ntl, pl.S), 192, WSmem<NT>::TOTAL, s>>>(a);
+  CUtensorMap mP0, mP1, mQ;
+  if (int rc = make_image_map(&mP0, P0, mtiles0 * 16, rs.Rp, 16)) return rc;
+  if (mt > mtiles0) { if (int rc = make_image_map(&mP1, P1, (mt - mtiles0) * 16, rs.Rp, 16)) return rc; }
+  else mP1 = mP0;
+  if (int rc = make_image_map(&mQ, Q, a.ntiles_per_tap * (NT / 8), rs.Rp, NT / 8)) return rc;
+  wgemm_kernel<NT><<<dim3(mt, ntl, pl.S), 192, WSmem<NT>::TOTAL, s>>>(a, mP0, mP1, mQ);
   if (trace_on()) { char b[96]; snprintf(b, sizeof b, "wgemm<%d> grid %d x %d x %d, Mo %d Kin %d taps %d", NT, mt, ntl, pl.S, Mo, Kin, taps); trace(b, s); }
   const size_t tot = (size_t)Mo * a.N;
   wgrad_reduce_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(part, pl.S, Mo, a.N, Kin, taps, dst);

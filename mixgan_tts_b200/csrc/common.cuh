@@ -6,6 +6,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 
 #include "../../include/mixgan_b200.h"
 
@@ -42,6 +43,35 @@ void set_error(const char* fmt, ...);
   } while (0)
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// Programmatic dependent launch (PDL).  A kernel launched with launch_pdl() may start while its predecessor in the stream
+// is still running: its CTAs do their private setup (barrier init, TMEM allocation, cluster sync), then pdl_wait() blocks
+// until the predecessor grid has completed and its memory is visible.  pdl_trigger() (issued right away by every CTA)
+// lets the successor be scheduled as soon as all of this grid's CTAs are resident.  Both are no-ops in a kernel that was
+// launched the ordinary way, so kernels shared with the fp32 path behave as before.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename K, typename... A>
+inline cudaError_t launch_pdl(K kernel, dim3 grid, dim3 block, size_t smem, cudaStream_t s, int cluster_x, const A&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute at[2];
+  int n = 0;
+  static const int pdl_on = [] { const char* e = getenv("MGB_NO_PDL"); return (e && *e == '1') ? 0 : 1; }();   // A/B switch
+  at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[n].val.programmaticStreamSerializationAllowed = pdl_on;
+  ++n;
+  if (cluster_x > 1) {
+    at[n].id = cudaLaunchAttributeClusterDimension;
+    at[n].val.clusterDim.x = cluster_x; at[n].val.clusterDim.y = 1; at[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  cfg.attrs = at; cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+#endif
 
 // ---- canonical flat fp32 weight order (include/mixgan_b200.h) -----------------------------
 struct FlatLayer {

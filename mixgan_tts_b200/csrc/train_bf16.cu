@@ -406,6 +406,8 @@ __global__ void __launch_bounds__(192, 1) fgemm_kernel(const FArgs p, const __gr
   tc::cluster_sync_all();            // every CTA's barriers exist before any multicast / remote arrive
   tc::tc_fence_after();
   const uint32_t tmem = tmem_slot;
+  pdl_trigger();                     // setup done: the next kernel may start its own setup on free SMs ...
+  pdl_wait();                        // ... and this one touches global memory only after its predecessor has completed
 
   const int per_tap = p.steps0 + p.steps1;
   const int nsteps = p.taps * per_tap;
@@ -486,7 +488,7 @@ int launch_fgemm(const FArgs& a, int ntiles, int n_tiles_n, cudaStream_t s) {
   if (int rc = make_image_map(&m0, a.A0, a.steps0 * 8, a.Rp, 8)) return rc;
   if (a.steps1 > 0) { if (int rc = make_image_map(&m1, a.A1, a.steps1 * 8, a.Rp, 8)) return rc; }
   else m1 = m0;
-  MGB_CUDA_CHECK(launch_cluster(fgemm_kernel<NT, MODE, CL>, dim3(ntiles, n_tiles_n), CL, FSmem<NT>::TOTAL, s, a, m0, m1));
+  MGB_CUDA_CHECK(launch_pdl(fgemm_kernel<NT, MODE, CL>, dim3(ntiles, n_tiles_n), dim3(192), FSmem<NT>::TOTAL, s, CL, a, m0, m1));
   note_launch();
   if (trace_on()) { char b[64]; snprintf(b, sizeof b, "fgemm<%d, mode %d>", NT, MODE); trace(b, s); }
   return MGB_OK;
@@ -540,6 +542,8 @@ __global__ void __launch_bounds__(192, 1) wgemm_kernel(const WgArgs p, const __g
   tc::tc_fence_after();
   const uint32_t tmem = tmem_slot;
   const uint32_t smem_base = tc::smem_u32(smem);
+  pdl_trigger();
+  pdl_wait();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -646,10 +650,11 @@ int launch_wg(const bf16* P0, const bf16* P1, int mtiles0, int Mo, const bf16* Q
   if (mt > mtiles0) { if (int rc = make_image_map(&mP1, P1, (mt - mtiles0) * 16, rs.Rp, 16)) return rc; }
   else mP1 = mP0;
   if (int rc = make_image_map(&mQ, Q, a.ntiles_per_tap * (NT / 8), rs.Rp, NT / 8)) return rc;
-  wgemm_kernel<NT><<<dim3(mt, ntl, pl.S), 192, WSmem<NT>::TOTAL, s>>>(a, mP0, mP1, mQ);
+  MGB_CUDA_CHECK(launch_pdl(wgemm_kernel<NT>, dim3(mt, ntl, pl.S), dim3(192), WSmem<NT>::TOTAL, s, 1, a, mP0, mP1, mQ));
   if (trace_on()) { char b[96]; snprintf(b, sizeof b, "wgemm<%d> grid %d x %d x %d, Mo %d Kin %d taps %d", NT, mt, ntl, pl.S, Mo, Kin, taps); trace(b, s); }
   const size_t tot = (size_t)Mo * a.N;
-  wgrad_reduce_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(part, pl.S, Mo, a.N, Kin, taps, dst);
+  MGB_CUDA_CHECK(launch_pdl(wgrad_reduce_kernel, dim3((unsigned)((tot + 255) / 256)), dim3(256), 0, s, 1,
+                            (const float*)part, pl.S, Mo, a.N, Kin, taps, dst));
   note_launch(2);
   return MGB_OK;
 }
@@ -745,6 +750,8 @@ __global__ void zero_margins_kernel(bf16* img, size_t img_stride, int nchunks, i
 __global__ void __launch_bounds__(256) img_colsum_kernel(const bf16* __restrict__ img, int Rp, int T, float* __restrict__ out,
                                                          int ldo) {
   __shared__ float red[256][9];
+  pdl_trigger();
+  pdl_wait();
   const int chunk = blockIdx.x, b = blockIdx.y;
   const bf16* base = img + ((size_t)chunk * Rp + RLEAD + (size_t)b * (T + 1)) * 8;
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -766,6 +773,8 @@ __global__ void __launch_bounds__(256) img_colsum_kernel(const bf16* __restrict_
 struct Colsum3 { const bf16* img[3]; float* out[3]; int nchunks[3], ldo[3]; };
 __global__ void __launch_bounds__(256) img_colsum3_kernel(const Colsum3 a, int Rp, int T) {
   __shared__ float red[256][9];
+  pdl_trigger();
+  pdl_wait();
   int chunk = blockIdx.x, w = 0;
   while (w < 2 && chunk >= a.nchunks[w]) { chunk -= a.nchunks[w]; ++w; }
   const int b = blockIdx.y;
@@ -786,7 +795,7 @@ __global__ void __launch_bounds__(256) img_colsum3_kernel(const Colsum3 a, int R
   }
 }
 void launch_colsum_img(const bf16* img, int nchunks, const RowSpace& rs, int B, float* out, int ldo, cudaStream_t s) {
-  img_colsum_kernel<<<dim3(nchunks, B), 256, 0, s>>>(img, rs.Rp, rs.T, out, ldo);
+  launch_pdl(img_colsum_kernel, dim3(nchunks, B), dim3(256), 0, s, 1, img, rs.Rp, rs.T, out, ldo);
   note_launch();
   trace("img_colsum", s);
 }
@@ -1116,7 +1125,7 @@ int bf16_train_backward(const mgb_model_dims& d, const float* flat, const void* 
         c3.img[0] = cimg(W + w.dZ); c3.nchunks[0] = 64; c3.out[0] = f32(W + w.usumZ); c3.ldo[0] = 2 * C;
         c3.img[1] = dYl; c3.nchunks[1] = 32; c3.out[1] = f32(W + w.usumY); c3.ldo[1] = C;
         c3.img[2] = cimg(W + w.Eimg); c3.nchunks[2] = 32; c3.out[2] = usumE_next; c3.ldo[2] = C;
-        img_colsum3_kernel<<<dim3(128, B), 256, 0, s>>>(c3, rs.Rp, rs.T);
+        launch_pdl(img_colsum3_kernel, dim3(128, B), dim3(256), 0, s, 1, c3, rs.Rp, rs.T);
         note_launch();
         trace("img_colsum3", s);
       }
@@ -1128,7 +1137,7 @@ int bf16_train_backward(const mgb_model_dims& d, const float* flat, const void* 
       q.g_dproj_w = gl + f.rel.dproj_w; q.g_sproj_w = d.multi_speaker ? gl + f.rel.sproj_w : nullptr;
       q.dd_l = f32(W + w.dd_all) + (size_t)l * B * C; q.ds_l = d.multi_speaker ? f32(W + w.ds_all) + (size_t)l * B * C : nullptr;
       q.B = B; q.C = C; q.H = H;
-      layer_small_kernel<<<C + B + 1, 256, 0, s>>>(q);
+      launch_pdl(layer_small_kernel, dim3(C + B + 1), dim3(256), 0, s, 1, q);
       note_launch();
     } else if (seg == L + 1) {
       // head: E / Eimg hold the ReLU-masked gradient of the input projection's pre-activation

@@ -10,6 +10,8 @@ namespace trainsmall {
 // dst[(m*Kin + ci)*taps + tap] = sum_s part[s][m][tap*Kin + ci]   (state_dict layout [out][in][k])
 static __global__ void wgrad_reduce_kernel(const float* __restrict__ part, int S, int Mo, int N, int Kin, int taps,
                                     float* __restrict__ dst) {
+  pdl_trigger();
+  pdl_wait();
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t tot = (size_t)Mo * N;
   if (i >= tot) return;
@@ -39,6 +41,8 @@ struct LayerSmallArgs {
 };
 // grid: C blocks (row co of dWd / dWs) + B blocks (ddvec / dspk rows) + 1 block (biases); 256 threads, C == H == 256
 static __global__ void __launch_bounds__(256) layer_small_kernel(const LayerSmallArgs p) {
+  pdl_trigger();
+  pdl_wait();
   const int C = p.C, tid = threadIdx.x;
   const int blk = blockIdx.x;
   if (blk < C) {
@@ -144,6 +148,8 @@ static inline void launch_dvec_contraction(const float* dd_all, const float* ds_
 
 // out[c] = sum_b usum[b][c]
 static __global__ void bias_from_usum_kernel(const float* __restrict__ usum, int B, int n, int ld, float* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= n) return;
   float s = 0.f;

@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmixgan_b200.so")
 SOURCES = ["abi.cu", "fp32_path.cu", "train_fp32.cu", "train_bf16.cu", "fused_bf16.cu", "umma_probe.cu"]
-HEADERS = ["common.cuh", "tc05.cuh", "small_ops.cuh", "gemm_fp32.cuh", "train_small.cuh", os.path.join("..", "..", "include", "mixgan_b200.h")]
+HEADERS = ["common.cuh", "tc05.cuh", "small_ops.cuh", "gemm_fp32.cuh", "train_small.cuh", "tmap.cuh", os.path.join("..", "..", "include", "mixgan_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 

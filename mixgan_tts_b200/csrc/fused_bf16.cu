@@ -45,6 +45,7 @@
 #include "common.cuh"
 #include "small_ops.cuh"
 #include "tc05.cuh"
+#include "tmap.cuh"
 
 namespace mgb {
 namespace {
@@ -143,7 +144,7 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t
 // KUNI: every utterance shares the per-layer constant k_l (uniform timestep, single speaker): it is added inside
 // the residual GEMM by one more K=16 step against the "ones" operand (kimg) instead of being loaded by the epilogue.
 template <bool PROF, bool KUNI>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_pair_kernel(const FusedParams p) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_pair_kernel(const FusedParams p, const __grid_constant__ CUtensorMap tmCond) {
   const long long t_start = PROF ? clock64() : 0;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sA = smem;
@@ -247,8 +248,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_p
       // =========================== TMA PRODUCER (both CTAs) ===========================
       uint32_t slot = 0, phase = 0;
       const uint8_t* wimg = p.wimg + (size_t)rank * p.wimg_rank_stride;
-      const uint8_t* condb = reinterpret_cast<const uint8_t*>(p.condT) + (size_t)(g0 + COND_PAD_LO) * 16;
-      const size_t cond_chunk = (size_t)p.Rp * 16;
+      const int cond_row = g0 + COND_PAD_LO;     // this CTA's first row in the cond image
       int n_issued = 0;
       auto advance = [&]() {
         if (PROF) {
@@ -291,9 +291,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_p
         if (tc::elect_one()) {
           const uint32_t fb = bar0 + (B_FULL + slot) * 8;
           tc::mbar_arrive_expect_tx_addr(fb, SLOT_BYTES);
-#pragma unroll
-          for (int k8 = 0; k8 < 8; ++k8)
-            tc::bulk_g2s_addr(slots0 + slot * SLOT_BYTES + k8 * 2048, condb + (size_t)(m * 8 + k8) * cond_chunk, 2048, fb);
+          // ONE tensor-map TMA box (128 rows x 64 channels = 16 KB) instead of eight 2 KB bulk copies: a bulk copy costs
+          // ~60-110 cycles of TMA-engine time whatever its size (profiles/r01/bulk_copy_rate_probe.txt), and the eight
+          // small copies made the ring refill-bound at the conditioner slots
+          tc::tma_load_2d(slots0 + slot * SLOT_BYTES, &tmCond, 2 * cond_row, m * 8, fb);
         }
         __syncwarp();
         advance();
@@ -1366,6 +1367,8 @@ int bf16_run(const mgb_model_dims& d, const void* packed, const float* x, const 
     MGB_CUDA_CHECK(cudaFuncSetAttribute(fused_pair_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
     pair_slots = sms / 2 > 0 ? sms / 2 : 1;
   }
+  CUtensorMap tm_cond;   // cond image [32 chunks][Rp rows][8]: boxes of 128 rows x 8 chunks
+  if (int rc = make_image_map(&tm_cond, W + w.condT, 32, w.Rp, 8)) return rc;
   FusedParams p{};
   p.wimg = reinterpret_cast<const uint8_t*>(P + o.total);
   p.wimg_rank_stride = (size_t)num_wslots(d) * SLOT_BYTES;
@@ -1405,8 +1408,8 @@ int bf16_run(const mgb_model_dims& d, const void* packed, const float* x, const 
       p.prof = dprof;
       cudaFuncSetAttribute(fused_pair_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL);
       cudaFuncSetAttribute(fused_pair_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL);
-      if (kuni) fused_pair_kernel<true, true><<<ncta, NTHREADS, SMEM_TOTAL, s>>>(p);
-      else fused_pair_kernel<true, false><<<ncta, NTHREADS, SMEM_TOTAL, s>>>(p);
+      if (kuni) fused_pair_kernel<true, true><<<ncta, NTHREADS, SMEM_TOTAL, s>>>(p, tm_cond);
+      else fused_pair_kernel<true, false><<<ncta, NTHREADS, SMEM_TOTAL, s>>>(p, tm_cond);
       cudaStreamSynchronize(s);
       long long* h = (long long*)malloc((size_t)ncta * 320 * sizeof(long long));
       cudaMemcpy(h, dprof, (size_t)ncta * 320 * sizeof(long long), cudaMemcpyDeviceToHost);
@@ -1458,8 +1461,8 @@ int bf16_run(const mgb_model_dims& d, const void* packed, const float* x, const 
       fprintf(stderr, "\n");
       free(h); cudaFree(dprof); p.prof = nullptr;
     } else {
-      if (kuni) fused_pair_kernel<false, true><<<2 * npairs, NTHREADS, SMEM_TOTAL, s>>>(p);
-      else fused_pair_kernel<false, false><<<2 * npairs, NTHREADS, SMEM_TOTAL, s>>>(p);
+      if (kuni) fused_pair_kernel<false, true><<<2 * npairs, NTHREADS, SMEM_TOTAL, s>>>(p, tm_cond);
+      else fused_pair_kernel<false, false><<<2 * npairs, NTHREADS, SMEM_TOTAL, s>>>(p, tm_cond);
     }
     prof_end(s);
     note_launch();

@@ -1,0 +1,41 @@
+// Host-side helper: CUtensorMap of an activation image for tensor-map TMA (cp.async.bulk.tensor).  The encoder is looked
+// up through the runtime (cudaGetDriverEntryPoint), so the library does not link against libcuda.
+#pragma once
+
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace mgb {
+
+// Tensor map of an activation image [nchunks][Rp][8] bf16, seen as a 2-D array of 8-byte words: dim0 = 2 words per row
+// (contiguous, Rp rows), dim1 = chunks.  A box of 256 words x k chunks is 128 rows x 8k channels and lands in shared memory
+// as [chunk][128 rows][16 B] — the no-swizzle core-matrix order both GEMM families read.  Coordinates: (2 * row, chunk).
+typedef CUresult (*TmapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+inline TmapEncodeFn tmap_encode_fn() {
+  static TmapEncodeFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess) p = nullptr;
+    return reinterpret_cast<TmapEncodeFn>(p);
+  }();
+  return fn;
+}
+inline int make_image_map(CUtensorMap* m, const void* img, int nchunks, int Rp, int box_chunks) {
+  TmapEncodeFn fn = tmap_encode_fn();
+  MGB_REQUIRE(fn != nullptr, MGB_E_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+  const cuuint64_t dims[2] = {(cuuint64_t)Rp * 2, (cuuint64_t)nchunks};
+  const cuuint64_t strides[1] = {(cuuint64_t)Rp * 16};
+  const cuuint32_t box[2] = {256, (cuuint32_t)box_chunks};
+  const cuuint32_t es[2] = {1, 1};
+  const CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, const_cast<void*>(img), dims, strides, box, es,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  MGB_REQUIRE(r == CUDA_SUCCESS, MGB_E_CUDA, "cuTensorMapEncodeTiled failed (%d) for an image of %d chunks x %d rows", (int)r,
+              nchunks, Rp);
+  return MGB_OK;
+}
+
+}  // namespace mgb

@@ -58,6 +58,11 @@ RowSpace row_space(int B, int T) {
   return r;
 }
 
+__device__ __forceinline__ float tanh_mufu(float x) {   // MUFU.TANH, as the inference kernel's gate
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);
@@ -207,8 +212,8 @@ __device__ __forceinline__ void fgemm_epilogue(const FArgs& p, uint32_t tmem_row
       load_f32x32(p.bias + C + ch0, bf);
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
-        const float sg = 1.0f / (1.0f + __expf(-(a[j] + ba[j])));
-        const float th = tanhf(f[j] + bf[j]);
+        const float sg = fmaf(0.5f, tanh_mufu(0.5f * (a[j] + ba[j])), 0.5f);   // sigmoid(a) = (1 + tanh(a / 2)) / 2
+        const float th = tanh_mufu(f[j] + bf[j]);
         st[j] = pack2(sg, th);
         a[j] = valid ? sg * th : 0.f;
       }
@@ -557,7 +562,10 @@ __global__ void __launch_bounds__(192, 1) wgemm_kernel(const WgArgs p, const __g
     const int i = (warp & 3) * 32 + lane;
     const int m = mtile * 128 + i;
     const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-    float* dst = p.part + ((size_t)z * p.Mo + m) * p.N + (size_t)tap * p.Kin;
+    // partials in the chunked layout part[z][n/4][m][4]: thread = output row m, so every 16-byte store of a warp is
+    // 512 contiguous bytes (a row-major [m][n] partial costs 32 sectors per store instruction)
+    float* dst = p.part + (size_t)z * p.Mo * p.N;
+    const int nbase = tap * p.Kin;
 #pragma unroll 1
     for (int cg = 0; cg < NT / 32; ++cg) {
       const int ci0 = nt * NT + cg * 32;
@@ -570,13 +578,11 @@ __global__ void __launch_bounds__(192, 1) wgemm_kernel(const WgArgs p, const __g
         for (int j = 0; j < 32; ++j) v[j] = 0.f;
       }
       if (m < p.Mo) {
-        if (ci0 + 32 <= p.Kin) {
-          store_f32x32(dst + ci0, v);
-        } else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (ci0 + j < p.Kin) dst[ci0 + j] = v[j];
-        }
+        for (int q = 0; q < 8; ++q)
+          if (ci0 + q * 4 < p.Kin)                   // Kin % 4 == 0
+            *reinterpret_cast<float4*>(dst + ((size_t)((nbase + ci0) / 4 + q) * p.Mo + m) * 4) =
+                make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
       }
     }
   }
@@ -623,7 +629,7 @@ int launch_wg(const bf16* P0, const bf16* P1, int mtiles0, int Mo, const bf16* Q
   MGB_CUDA_CHECK(launch_pdl(wgemm_kernel<NT>, dim3(mt, ntl, pl.S), dim3(192), WSmem<NT>::TOTAL, s, 1, a, mP0, mP1, mQ));
   if (trace_on()) { char b[96]; snprintf(b, sizeof b, "wgemm<%d> grid %d x %d x %d, Mo %d Kin %d taps %d", NT, mt, ntl, pl.S, Mo, Kin, taps); trace(b, s); }
   const size_t tot = (size_t)Mo * a.N;
-  MGB_CUDA_CHECK(launch_pdl(wgrad_reduce_kernel, dim3((unsigned)((tot + 255) / 256)), dim3(256), 0, s, 1,
+  MGB_CUDA_CHECK(launch_pdl(wgrad_reduce_chunked_kernel, dim3((unsigned)((tot + 255) / 256)), dim3(256), 0, s, 1,
                             (const float*)part, pl.S, Mo, a.N, Kin, taps, dst));
   note_launch(2);
   return MGB_OK;

@@ -22,6 +22,24 @@ static __global__ void wgrad_reduce_kernel(const float* __restrict__ part, int S
   dst[((size_t)m * Kin + ci) * taps + tap] = s;
 }
 
+// Same reduction for partials stored in the chunked layout part[s][n/4][m][4] (the tcgen05 weight-gradient kernel owns
+// one output row m per thread, so a warp's 16-byte store to chunk n/4 is 512 contiguous bytes).
+static __global__ void wgrad_reduce_chunked_kernel(const float* __restrict__ part, int S, int Mo, int N, int Kin, int taps,
+                                                   float* __restrict__ dst) {
+  pdl_trigger();
+  pdl_wait();
+  const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t tot = (size_t)Mo * N;
+  if (j >= tot) return;
+  float s = 0.f;
+  for (int k = 0; k < S; ++k) s += part[(size_t)k * tot + j];
+  const int nq = (int)(j / ((size_t)Mo * 4));
+  const int rem = (int)(j - (size_t)nq * Mo * 4);
+  const int m = rem >> 2, n = nq * 4 + (rem & 3);
+  const int tap = n / Kin, ci = n - tap * Kin;
+  dst[((size_t)m * Kin + ci) * taps + tap] = s;
+}
+
 // ------------------------------------------------------------------------------------------------
 // per-layer small terms (B rows each): bias gradients, diffusion/speaker projection gradients, and the
 // accumulation of d loss / d dvec and d loss / d spk over layers.

@@ -92,3 +92,33 @@ for src, dst in (("role_profile.txt", "role_profile_pair_kernel.txt"), ("bench_o
     if os.path.exists(p):
         shutil.copy(p, os.path.join(out, dst))
 print("wrote", sorted(os.listdir(out)))
+
+# ---- training path: ncu --set full of a few backward GEMM launches + the launch list of one training step
+rep = os.path.join(G, "prof_train.ncu-rep")
+if os.path.exists(rep):
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr = rows[0]
+    want = ["Kernel Name", "gpu__time_duration.sum", "launch__grid_size", "launch__cluster_size", "launch__registers_per_thread",
+            "launch__shared_mem_per_block_dynamic", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
+            "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "sm__cycles_elapsed.avg", "dram__bytes_read.sum",
+            "dram__bytes_write.sum", "lts__t_sector_hit_rate.pct", "l1tex__m_xbar2l1tex_read_bytes.sum",
+            "l1tex__t_sectors_pipe_lsu_mem_global_op_st.sum", "l1tex__t_requests_pipe_lsu_mem_global_op_st.sum",
+            "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum", "l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum"]
+    with open(os.path.join(out, "ncu_train_gemm_summary.txt"), "w") as f:
+        f.write("ncu --set full --clock-control none --import-source on -k regex:'fgemm_kernel|wgemm_kernel' -s 590 -c 8  "
+                "python bench.py --workload train --precision bf16 --steps 2 --warmup 3\n"
+                "(consecutive GEMM launches inside the backward of one training step, B=8 x T=800: mode 8 = gate-backward GEMM,\n"
+                " mode 9 = transposed-conv GEMM, wgemm = weight-gradient GEMMs; cold caches, serialised)\n\n")
+        for i, h in enumerate(hdr):
+            if h in want:
+                f.write(f"{h} [{rows[1][i]}] = {' | '.join(r[i][:40] for r in rows[2:])}\n")
+    src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+    with open(os.path.join(out, "ncu_train_gemm_summary.txt"), "a") as f:
+        for key in ("UTCHMMA", "UTMALDG", "UBLKCP", "LDTM", "UTCBAR", "SYNCS"):
+            f.write(f"SASS {key}: {sum(1 for l in src.splitlines() if key in l)} occurrences in the captured kernels\n")
+for src_name, dst in (("launches_train_bf16.csv", "launches_train_bf16.csv"), ("launches_train_bf16_summary.txt", "launches_train_bf16_summary.txt"),
+                      ("train_bf16_parity.txt", "train_bf16_parity.txt"), ("bulk_rate.txt", "bulk_copy_rate_probe.txt")):
+    p = os.path.join(G, src_name)
+    if os.path.exists(p):
+        shutil.copy(p, os.path.join(out, dst))

@@ -4,6 +4,8 @@
 
 #include <cuda.h>
 
+#include <unordered_map>
+
 #include "common.cuh"
 
 namespace mgb {
@@ -23,7 +25,26 @@ inline TmapEncodeFn tmap_encode_fn() {
   }();
   return fn;
 }
+// Encoding costs ~1 us of host time and a training step needs several hundred maps over a few dozen distinct images whose
+// addresses repeat from step to step (workspace, and the caching allocator's activation stash), so maps are memoised.
+struct TmapKey {
+  const void* img; int nchunks, Rp, box;
+  bool operator==(const TmapKey& o) const { return img == o.img && nchunks == o.nchunks && Rp == o.Rp && box == o.box; }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    size_t h = reinterpret_cast<size_t>(k.img) >> 4;
+    h = h * 1000003u ^ (size_t)k.nchunks;
+    h = h * 1000003u ^ (size_t)k.Rp;
+    return h * 1000003u ^ (size_t)k.box;
+  }
+};
 inline int make_image_map(CUtensorMap* m, const void* img, int nchunks, int Rp, int box_chunks) {
+  static thread_local std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;
+  const TmapKey key{img, nchunks, Rp, box_chunks};
+  auto it = cache.find(key);
+  if (it != cache.end()) { *m = it->second; return MGB_OK; }
+  if (cache.size() > 8192) cache.clear();
   TmapEncodeFn fn = tmap_encode_fn();
   MGB_REQUIRE(fn != nullptr, MGB_E_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
   const cuuint64_t dims[2] = {(cuuint64_t)Rp * 2, (cuuint64_t)nchunks};
@@ -35,6 +56,7 @@ inline int make_image_map(CUtensorMap* m, const void* img, int nchunks, int Rp, 
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   MGB_REQUIRE(r == CUDA_SUCCESS, MGB_E_CUDA, "cuTensorMapEncodeTiled failed (%d) for an image of %d chunks x %d rows", (int)r,
               nchunks, Rp);
+  cache.emplace(key, *m);
   return MGB_OK;
 }
 

@@ -472,14 +472,23 @@ int launch_fgemm(const FArgs& a, int ntiles, int n_tiles_n, cudaStream_t s) {
 // =====================================================================================================
 // weight-gradient GEMM: part[z][m][n] = sum over the split's frames of P[f][m] * Q[f + sh][ci]
 // =====================================================================================================
-struct WgArgs {
-  const bf16* P0; const bf16* P1; int mtiles0;   // M tile (128 out-channels) x < mtiles0 from P0, else from P1
-  const bf16* Q;
+// Up to three independent problems per launch (a block's dWo, dW3 and dWc share one launch and one reduction):
+// blockIdx.x runs over the concatenated (m-tile, n-tile) lists, blockIdx.y over the frame splits.
+struct WProb {
+  int mtiles, mtiles0;           // M tiles (128 out-channels); tiles < mtiles0 come from P0, the rest from P1
   int taps, ntiles_per_tap, Kin, Mo, N;
+  int tile0;                     // first blockIdx.x of this problem
+  long long part_off;            // floats: this problem's partials start here; layout [split][n/4][m][4]
+};
+constexpr int WPROB_MAX = 3;
+struct WgArgs {
+  WProb pr[WPROB_MAX];
+  int nprob;
   float* part;
   int Rp, nblocks, blocks_per_split;
   int* status;
 };
+struct WgMaps { CUtensorMap P0[WPROB_MAX], P1[WPROB_MAX], Q[WPROB_MAX]; };
 template <int NT>
 struct WSmem {
   static constexpr int A_BYTES = 16 * TILE * 16;        // 128 channels x 128 frames
@@ -490,9 +499,7 @@ struct WSmem {
 };
 
 template <int NT>
-__global__ void __launch_bounds__(192, 1) wgemm_kernel(const WgArgs p, const __grid_constant__ CUtensorMap tmP0,
-                                                       const __grid_constant__ CUtensorMap tmP1,
-                                                       const __grid_constant__ CUtensorMap tmQ) {
+__global__ void __launch_bounds__(192, 1) wgemm_kernel(const WgArgs p, const __grid_constant__ WgMaps maps) {
   using S = WSmem<NT>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -500,8 +507,12 @@ __global__ void __launch_bounds__(192, 1) wgemm_kernel(const WgArgs p, const __g
   __shared__ uint32_t tmem_slot;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int mtile = blockIdx.x, ny = blockIdx.y, z = blockIdx.z;
-  const int tap = ny / p.ntiles_per_tap, nt = ny - tap * p.ntiles_per_tap;
+  int k = 0;
+  while (k + 1 < p.nprob && (int)blockIdx.x >= p.pr[k + 1].tile0) ++k;
+  const WProb& q = p.pr[k];
+  const int local = blockIdx.x - q.tile0;
+  const int mtile = local % q.mtiles, ny = local / q.mtiles, z = blockIdx.y;
+  const int tap = ny / q.ntiles_per_tap, nt = ny - tap * q.ntiles_per_tap;
   const int kb0 = z * p.blocks_per_split;
   const int kb1 = min(p.nblocks, kb0 + p.blocks_per_split);
   const int nsteps = kb1 - kb0;
@@ -522,10 +533,11 @@ __global__ void __launch_bounds__(192, 1) wgemm_kernel(const WgArgs p, const __g
 
   if (warp == 0) {
     if (lane == 0) {
-      const void* tmP = mtile < p.mtiles0 ? &tmP0 : &tmP1;
-      const int mchunk0 = (mtile < p.mtiles0 ? mtile : mtile - p.mtiles0) * 16;
+      const void* tmP = mtile < q.mtiles0 ? &maps.P0[k] : &maps.P1[k];
+      const void* tmQ = &maps.Q[k];
+      const int mchunk0 = (mtile < q.mtiles0 ? mtile : mtile - q.mtiles0) * 16;
       const int nchunk0 = nt * (NT / 8);
-      const int sh = tap - (p.taps >> 1);
+      const int sh = tap - (q.taps >> 1);
       for (int s = 0; s < nsteps; ++s) {
         const int stage = s % S::STAGES, ph = (s / S::STAGES) & 1;
         tc::mbar_wait_trap(tc::smem_u32(&bar_empty[stage]), ph ^ 1, kTimeout, p.status, 1);
@@ -534,7 +546,7 @@ __global__ void __launch_bounds__(192, 1) wgemm_kernel(const WgArgs p, const __g
         tc::mbar_arrive_expect_tx_addr(fb, S::STAGE);
         const int row = RLEAD + (kb0 + s) * TILE;
         tc::tma_load_2d(sa, tmP, 2 * row, mchunk0, fb);              // 128 channels x 128 frames: one 32 KB box
-        tc::tma_load_2d(sb, &tmQ, 2 * (row + sh), nchunk0, fb);      // NT channels x 128 frames: one 32/64 KB box
+        tc::tma_load_2d(sb, tmQ, 2 * (row + sh), nchunk0, fb);       // NT channels x 128 frames: one 32/64 KB box
       }
     }
   } else if (warp == 1) {
@@ -547,10 +559,10 @@ __global__ void __launch_bounds__(192, 1) wgemm_kernel(const WgArgs p, const __g
         tc::tc_fence_after();
         const uint32_t sa = smem_base + stage * S::STAGE, sb = sa + S::A_BYTES;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {      // 16 frames per MMA = 256 B along the frame axis
-          const uint64_t ad = tc::make_smem_desc(sa + k * 256, 128, TILE * 16);
-          const uint64_t bd = tc::make_smem_desc(sb + k * 256, 128, TILE * 16);
-          tc::umma_bf16(tmem, ad, bd, idesc, (s | k) ? 1u : 0u);
+        for (int kk = 0; kk < 8; ++kk) {      // 16 frames per MMA = 256 B along the frame axis
+          const uint64_t ad = tc::make_smem_desc(sa + kk * 256, 128, TILE * 16);
+          const uint64_t bd = tc::make_smem_desc(sb + kk * 256, 128, TILE * 16);
+          tc::umma_bf16(tmem, ad, bd, idesc, (s | kk) ? 1u : 0u);
         }
         tc::umma_commit(&bar_empty[stage]);
       }
@@ -564,12 +576,12 @@ __global__ void __launch_bounds__(192, 1) wgemm_kernel(const WgArgs p, const __g
     const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     // partials in the chunked layout part[z][n/4][m][4]: thread = output row m, so every 16-byte store of a warp is
     // 512 contiguous bytes (a row-major [m][n] partial costs 32 sectors per store instruction)
-    float* dst = p.part + (size_t)z * p.Mo * p.N;
-    const int nbase = tap * p.Kin;
+    float* dst = p.part + q.part_off + (size_t)z * q.Mo * q.N;
+    const int nbase = tap * q.Kin;
 #pragma unroll 1
     for (int cg = 0; cg < NT / 32; ++cg) {
       const int ci0 = nt * NT + cg * 32;
-      if (ci0 >= p.Kin) break;                       // uniform over the warp
+      if (ci0 >= q.Kin) break;                       // uniform over the warp
       float v[32];
       if (nsteps > 0) {
         tmem_ld_f32x32(trow + cg * 32, v);
@@ -577,12 +589,12 @@ __global__ void __launch_bounds__(192, 1) wgemm_kernel(const WgArgs p, const __g
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = 0.f;
       }
-      if (m < p.Mo) {
+      if (m < q.Mo) {
 #pragma unroll
-        for (int q = 0; q < 8; ++q)
-          if (ci0 + q * 4 < p.Kin)                   // Kin % 4 == 0
-            *reinterpret_cast<float4*>(dst + ((size_t)((nbase + ci0) / 4 + q) * p.Mo + m) * 4) =
-                make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+        for (int c4 = 0; c4 < 8; ++c4)
+          if (ci0 + c4 * 4 < q.Kin)                  // Kin % 4 == 0
+            *reinterpret_cast<float4*>(dst + ((size_t)((nbase + ci0) / 4 + c4) * q.Mo + m) * 4) =
+                make_float4(v[c4 * 4], v[c4 * 4 + 1], v[c4 * 4 + 2], v[c4 * 4 + 3]);
       }
     }
   }
@@ -591,9 +603,31 @@ __global__ void __launch_bounds__(192, 1) wgemm_kernel(const WgArgs p, const __g
   if (warp == 1) tc::tmem_dealloc<NT>(tmem);
 }
 
+// dst[k][(m*Kin + ci)*taps + tap] = sum over splits of problem k's partials (fixed order), for up to three problems
+struct WRedSeg { long long part_off, begin; float* dst; int Mo, N, Kin, taps; };
+struct WRedArgs { WRedSeg seg[WPROB_MAX]; int nseg, S; long long total; const float* part; };
+__global__ void __launch_bounds__(256) wgrad_reduce_multi_kernel(const WRedArgs a) {
+  pdl_trigger();
+  pdl_wait();
+  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= a.total) return;
+  int k = 0;
+  while (k + 1 < a.nseg && j >= a.seg[k + 1].begin) ++k;
+  const WRedSeg& g = a.seg[k];
+  const long long i = j - g.begin, tot = (long long)g.Mo * g.N;
+  const float* src = a.part + g.part_off + i;
+  float s = 0.f;
+  for (int z = 0; z < a.S; ++z) s += src[(size_t)z * tot];
+  const int nq = (int)(i / ((long long)g.Mo * 4));
+  const int rem = (int)(i - (long long)nq * g.Mo * 4);
+  const int m = rem >> 2, n = nq * 4 + (rem & 3);
+  const int tap = n / g.Kin, ci = n - tap * g.Kin;
+  g.dst[((size_t)m * g.Kin + ci) * g.taps + tap] = s;
+}
+
 struct WPlan { int S, blocks_per_split; };
-WPlan plan_wg(int nblocks, int mtiles, int ntiles) {
-  int S = 148 / (mtiles * ntiles);                             // one wave: at most one CTA per SM ...
+WPlan plan_wg(int nblocks, int tiles) {
+  int S = 148 / tiles;                                         // one wave: at most one CTA per SM ...
   const int cap = (nblocks + 1) / 2;                           // ... but at least 2 frame blocks per CTA: every split costs a
   if (S > cap) S = cap;                                        // 128 x NT fp32 partial that the reduction has to read back
   if (S > nblocks) S = nblocks;
@@ -601,38 +635,61 @@ WPlan plan_wg(int nblocks, int mtiles, int ntiles) {
   const int per = (nblocks + S - 1) / S;
   return {(nblocks + per - 1) / per, per};
 }
-size_t wg_part_floats(int nblocks, int Mo, int Kin, int taps, int NT) {
-  const int mt = (Mo + 127) / 128, ntl = taps * ((Kin + NT - 1) / NT);
-  return (size_t)plan_wg(nblocks, mt, ntl).S * Mo * Kin * taps;
+// upper bound of the partial buffer: the three per-block problems together
+size_t wg_part_floats_max(int nblocks) {
+  const size_t out_elems = (size_t)512 * 768 + (size_t)512 * 256 + (size_t)256 * 256;
+  return (size_t)plan_wg(nblocks, 18).S * out_elems + (size_t)nblocks * 256 * 256;   // + room for the single-problem launches
 }
 
-// dst (flat gradient, state_dict layout) = sum over frames of P^T Q
+struct WgSpec {                   // one weight-gradient problem: dst (flat gradient, state_dict layout) = P^T Q over frames
+  const bf16* P0; const bf16* P1; int mtiles0; int Mo; const bf16* Q; int Kin; int taps; float* dst;
+};
 template <int NT>
-int launch_wg(const bf16* P0, const bf16* P1, int mtiles0, int Mo, const bf16* Q, int Kin, int taps, const RowSpace& rs,
-              float* part, float* dst, int* status, cudaStream_t s) {
+int launch_wg_multi(const WgSpec* sp, int n, const RowSpace& rs, float* part, int* status, cudaStream_t s) {
   static bool configured = false;
   if (!configured) {
     MGB_CUDA_CHECK(cudaFuncSetAttribute(wgemm_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, WSmem<NT>::TOTAL));
     configured = true;
   }
   WgArgs a{};
-  a.P0 = P0; a.P1 = P1; a.mtiles0 = mtiles0; a.Q = Q; a.taps = taps; a.ntiles_per_tap = (Kin + NT - 1) / NT;
-  a.Kin = Kin; a.Mo = Mo; a.N = Kin * taps; a.part = part; a.Rp = rs.Rp; a.nblocks = rs.ntiles; a.status = status;
-  const int mt = (Mo + 127) / 128, ntl = taps * a.ntiles_per_tap;
-  const WPlan pl = plan_wg(rs.ntiles, mt, ntl);
+  WgMaps maps{};
+  WRedArgs r{};
+  a.nprob = n; a.part = part; a.Rp = rs.Rp; a.nblocks = rs.ntiles; a.status = status;
+  int tiles = 0;
+  for (int k = 0; k < n; ++k) {
+    WProb& q = a.pr[k];
+    q.mtiles = (sp[k].Mo + 127) / 128; q.mtiles0 = sp[k].mtiles0; q.taps = sp[k].taps;
+    q.ntiles_per_tap = (sp[k].Kin + NT - 1) / NT; q.Kin = sp[k].Kin; q.Mo = sp[k].Mo; q.N = sp[k].Kin * sp[k].taps;
+    q.tile0 = tiles;
+    tiles += q.mtiles * q.taps * q.ntiles_per_tap;
+    if (int rc = make_image_map(&maps.P0[k], sp[k].P0, q.mtiles0 * 16, rs.Rp, 16)) return rc;
+    if (q.mtiles > q.mtiles0) { if (int rc = make_image_map(&maps.P1[k], sp[k].P1, (q.mtiles - q.mtiles0) * 16, rs.Rp, 16)) return rc; }
+    else maps.P1[k] = maps.P0[k];
+    if (int rc = make_image_map(&maps.Q[k], sp[k].Q, q.ntiles_per_tap * (NT / 8), rs.Rp, NT / 8)) return rc;
+  }
+  for (int k = n; k < WPROB_MAX; ++k) { maps.P0[k] = maps.P0[0]; maps.P1[k] = maps.P0[0]; maps.Q[k] = maps.Q[0]; }
+  const WPlan pl = plan_wg(rs.ntiles, tiles);
   a.blocks_per_split = pl.blocks_per_split;
-  CUtensorMap mP0, mP1, mQ;
-  if (int rc = make_image_map(&mP0, P0, mtiles0 * 16, rs.Rp, 16)) return rc;
-  if (mt > mtiles0) { if (int rc = make_image_map(&mP1, P1, (mt - mtiles0) * 16, rs.Rp, 16)) return rc; }
-  else mP1 = mP0;
-  if (int rc = make_image_map(&mQ, Q, a.ntiles_per_tap * (NT / 8), rs.Rp, NT / 8)) return rc;
-  MGB_CUDA_CHECK(launch_pdl(wgemm_kernel<NT>, dim3(mt, ntl, pl.S), dim3(192), WSmem<NT>::TOTAL, s, 1, a, mP0, mP1, mQ));
-  if (trace_on()) { char b[96]; snprintf(b, sizeof b, "wgemm<%d> grid %d x %d x %d, Mo %d Kin %d taps %d", NT, mt, ntl, pl.S, Mo, Kin, taps); trace(b, s); }
-  const size_t tot = (size_t)Mo * a.N;
-  MGB_CUDA_CHECK(launch_pdl(wgrad_reduce_chunked_kernel, dim3((unsigned)((tot + 255) / 256)), dim3(256), 0, s, 1,
-                            (const float*)part, pl.S, Mo, a.N, Kin, taps, dst));
+  long long off = 0, begin = 0;
+  for (int k = 0; k < n; ++k) {
+    a.pr[k].part_off = off;
+    r.seg[k].part_off = off; r.seg[k].begin = begin; r.seg[k].dst = sp[k].dst; r.seg[k].Mo = a.pr[k].Mo; r.seg[k].N = a.pr[k].N;
+    r.seg[k].Kin = a.pr[k].Kin; r.seg[k].taps = a.pr[k].taps;
+    off += (long long)pl.S * a.pr[k].Mo * a.pr[k].N;
+    begin += (long long)a.pr[k].Mo * a.pr[k].N;
+  }
+  r.nseg = n; r.S = pl.S; r.total = begin; r.part = part;
+  MGB_CUDA_CHECK(launch_pdl(wgemm_kernel<NT>, dim3(tiles, pl.S), dim3(192), WSmem<NT>::TOTAL, s, 1, a, maps));
+  if (trace_on()) { char b[96]; snprintf(b, sizeof b, "wgemm<%d> %d problems, grid %d x %d", NT, n, tiles, pl.S); trace(b, s); }
+  MGB_CUDA_CHECK(launch_pdl(wgrad_reduce_multi_kernel, dim3((unsigned)((begin + 255) / 256)), dim3(256), 0, s, 1, r));
   note_launch(2);
   return MGB_OK;
+}
+template <int NT>
+int launch_wg(const bf16* P0, const bf16* P1, int mtiles0, int Mo, const bf16* Q, int Kin, int taps, const RowSpace& rs,
+              float* part, float* dst, int* status, cudaStream_t s) {
+  const WgSpec sp{P0, P1, mtiles0, Mo, Q, Kin, taps, dst};
+  return launch_wg_multi<NT>(&sp, 1, rs, part, status, s);
 }
 
 // =====================================================================================================
@@ -860,16 +917,10 @@ Work16 work16_layout(const mgb_model_dims& d, int B, int T) {
   w.dPre = take(32 * Rp * 16);
   w.dS = take(32 * Rp * 16);
   w.E = take(Rp * C * 4);
-  w.Eimg = take(32 * Rp * 16);
+  w.Eimg = take(2 * 32 * Rp * 16);   // e_l / e_{l-1} ping-pong: the block's dWo still needs e_l after dx has produced e_{l-1}
   w.dZ = take(64 * Rp * 16);
   w.dY = take((size_t)d.layers * 32 * Rp * 16);   // every layer's dY image: d loss / d cond is ONE GEMM over K = 256 L at the head
-  size_t part = wg_part_floats(rs.ntiles, 512, 256, 3, 256);
-  auto mx = [&](size_t v) { if (v > part) part = v; };
-  mx(wg_part_floats(rs.ntiles, 512, 256, 1, 256));
-  mx(wg_part_floats(rs.ntiles, 256, 256, 1, 256));
-  mx(wg_part_floats(rs.ntiles, 80, 256, 1, 256));
-  mx(wg_part_floats(rs.ntiles, 256, 80, 1, 128));
-  w.part = take(part * 4);
+  w.part = take(wg_part_floats_max(rs.ntiles) * 4);
   w.usumE = take((size_t)B * C * 4);
   w.usumE2 = take((size_t)B * C * 4);
   w.usumZ = take((size_t)B * 2 * C * 4);
@@ -1065,33 +1116,39 @@ int bf16_train_backward(const mgb_model_dims& d, const float* flat, const void* 
       const float* fl = flat + f.layer0 + (size_t)l * f.layer_stride;
       float* gl = grad_flat + f.layer0 + (size_t)l * f.layer_stride;
       bf16* dYl = img(W + w.dY) + (size_t)l * 32 * rs.Rp * 8;
+      // e images ping-pong between blocks: e_cur = e_l (input of this block), e_new = e_{l-1} (written by this block)
+      const size_t eimg_bytes = (size_t)32 * rs.Rp * 16;
+      bf16* e_cur = img(W + w.Eimg + ((seg & 1) ? 0 : eimg_bytes));
+      bf16* e_new = img(W + w.Eimg + ((seg & 1) ? eimg_bytes : 0));
       {
         FArgs a = base;                                 // dG = [e | dS] Wo; gate backward -> dZ
         if (top) { a.A0 = cimg(W + w.dS); a.steps0 = 4; a.kstep_b0 = 4; }
-        else { a.A0 = cimg(W + w.Eimg); a.steps0 = 4; a.A1 = cimg(W + w.dS); a.steps1 = 4; }
+        else { a.A0 = e_cur; a.steps0 = 4; a.A1 = cimg(W + w.dS); a.steps1 = 4; }
         a.Bpk = wl + o.r_oproj_b; a.ksteps_b = 8;
         a.sgth_in = reinterpret_cast<const uint32_t*>(sl + sv.rSGTH); a.img = img(W + w.dZ);
         if (int rc = launch_fgemm<256, B_GATE>(a, rs.ntiles, 1, s)) return rc;
       }
-      if (top) {                                        // dWo = [e | dS]^T g  (top block: e = 0)
-        MGB_CUDA_CHECK(cudaMemsetAsync(gl + f.rel.oproj_w, 0, sizeof(float) * (size_t)C * C, s));
-        if (int rc = launch_wg<256>(cimg(W + w.dS), nullptr, 2, C, cimg(sl + sv.rG), C, 1, rs, part,
-                                    gl + f.rel.oproj_w + (size_t)C * C, status, s)) return rc;
-      } else {
-        if (int rc = launch_wg<256>(cimg(W + w.Eimg), cimg(W + w.dS), 2, 2 * C, cimg(sl + sv.rG), C, 1, rs, part,
-                                    gl + f.rel.oproj_w, status, s)) return rc;
-      }
       {
         FArgs a = base;                                 // dY = conv3^T(dZ); dx = e + dY; e' = dx / sqrt(2)
         a.A0 = cimg(W + w.dZ); a.steps0 = 8; a.taps = 3; a.Bpk = wl + o.r_conv_b; a.ksteps_b = 24;
-        a.fout = f32(W + w.E); a.fin = cf32(SV + sv.X0); a.img = dYl; a.img2 = img(W + w.Eimg);
+        a.fout = f32(W + w.E); a.fin = cf32(SV + sv.X0); a.img = dYl; a.img2 = e_new;
         a.first = top ? 1 : 0; a.relu0 = (l == 0) ? 1 : 0;
         if (int rc = launch_fgemm<256, B_DX>(a, rs.ntiles, 1, s)) return rc;
       }
-      if (int rc = launch_wg<256>(cimg(W + w.dZ), nullptr, 4, 2 * C, cimg(sl + sv.rY), C, 3, rs, part, gl + f.rel.conv_w,
-                                  status, s)) return rc;
-      if (int rc = launch_wg<256>(dYl, nullptr, 2, C, cimg(SV + sv.cond), H, 1, rs, part, gl + f.rel.cproj_w,
-                                  status, s)) return rc;
+      {
+        // the block's three weight gradients in ONE launch (18 output tiles x 8 frame splits = one wave) + one reduction:
+        //   dWo = [e_l | dS]^T g_l (top block: e = 0, only the skip half), dW3 = dZ^T shift(y_l), dWc = dY^T cond
+        WgSpec sp[3];
+        if (top) {
+          MGB_CUDA_CHECK(cudaMemsetAsync(gl + f.rel.oproj_w, 0, sizeof(float) * (size_t)C * C, s));
+          sp[0] = WgSpec{cimg(W + w.dS), nullptr, 2, C, cimg(sl + sv.rG), C, 1, gl + f.rel.oproj_w + (size_t)C * C};
+        } else {
+          sp[0] = WgSpec{e_cur, cimg(W + w.dS), 2, 2 * C, cimg(sl + sv.rG), C, 1, gl + f.rel.oproj_w};
+        }
+        sp[1] = WgSpec{cimg(W + w.dZ), nullptr, 4, 2 * C, cimg(sl + sv.rY), C, 3, gl + f.rel.conv_w};
+        sp[2] = WgSpec{dYl, nullptr, 2, C, cimg(SV + sv.cond), H, 1, gl + f.rel.cproj_w};
+        if (int rc = launch_wg_multi<256>(sp, 3, rs, part, status, s)) return rc;
+      }
       // per-utterance column sums of dZ_l, dY_l and of the NEW e image (= e_{l-1}, used by the next block's small terms):
       // one launch; the two e-sum buffers alternate between blocks
       float* usumE_cur = f32(W + ((seg & 1) ? w.usumE : w.usumE2));
@@ -1100,7 +1157,7 @@ int bf16_train_backward(const mgb_model_dims& d, const float* flat, const void* 
         Colsum3 c3{};
         c3.img[0] = cimg(W + w.dZ); c3.nchunks[0] = 64; c3.out[0] = f32(W + w.usumZ); c3.ldo[0] = 2 * C;
         c3.img[1] = dYl; c3.nchunks[1] = 32; c3.out[1] = f32(W + w.usumY); c3.ldo[1] = C;
-        c3.img[2] = cimg(W + w.Eimg); c3.nchunks[2] = 32; c3.out[2] = usumE_next; c3.ldo[2] = C;
+        c3.img[2] = e_new; c3.nchunks[2] = 32; c3.out[2] = usumE_next; c3.ldo[2] = C;
         launch_pdl(img_colsum3_kernel, dim3(128, B), dim3(256), 0, s, 1, c3, rs.Rp, rs.T);
         note_launch();
         trace("img_colsum3", s);
@@ -1116,10 +1173,11 @@ int bf16_train_backward(const mgb_model_dims& d, const float* flat, const void* 
       launch_pdl(layer_small_kernel, dim3(C + B + 1), dim3(256), 0, s, 1, q);
       note_launch();
     } else if (seg == L + 1) {
-      // head: E / Eimg hold the ReLU-masked gradient of the input projection's pre-activation
-      if (int rc = launch_wg<128>(cimg(W + w.Eimg), nullptr, 2, C, cimg(SV + sv.xt), M, 1, rs, part, grad_flat + f.in_w,
+      // head: E and the e image written by block 0 hold the ReLU-masked gradient of the input projection's pre-activation
+      const bf16* e_last = cimg(W + w.Eimg + ((L & 1) ? (size_t)32 * rs.Rp * 16 : 0));
+      if (int rc = launch_wg<128>(e_last, nullptr, 2, C, cimg(SV + sv.xt), M, 1, rs, part, grad_flat + f.in_w,
                                   status, s)) return rc;
-      launch_colsum_img(cimg(W + w.Eimg), 32, rs, B, f32(W + w.usumT), C, s);
+      launch_colsum_img(e_last, 32, rs, B, f32(W + w.usumT), C, s);
       bias_from_usum_kernel<<<2, 128, 0, s>>>(f32(W + w.usumT), B, C, C, grad_flat + f.in_b);
       note_launch();
       if (grad_cond) {
@@ -1132,7 +1190,7 @@ int bf16_train_backward(const mgb_model_dims& d, const float* flat, const void* 
       }
       if (grad_x) {
         FArgs a = base;                                 // d loss / d mel = dPre0 Win
-        a.A0 = cimg(W + w.Eimg); a.steps0 = 4; a.Bpk = wpk + o.in_b; a.ksteps_b = 4; a.fout = grad_x;
+        a.A0 = e_last; a.steps0 = 4; a.Bpk = wpk + o.in_b; a.ksteps_b = 4; a.fout = grad_x;
         if (int rc = launch_fgemm<128, B_DXT>(a, rs.ntiles, 1, s)) return rc;
       }
       launch_dvec_contraction(f32(W + w.dd_all), f32(W + w.ds_all), flat + f.layer0 + f.rel.dproj_w,

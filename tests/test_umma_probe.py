@@ -170,3 +170,24 @@ def test_mn_major_operands(which, n, ksteps, shift):
     err = (D - Ae.float() @ Be.float().t()).abs().max().item()
     _report(f"MN-major {which} n={n} ksteps={ksteps} shift={shift}: status={int(st.item())} err={err:.3e}")
     assert int(st.item()) == 0 and err < 1e-3
+
+
+def test_bulk_copy_size_sets_the_shared_memory_fill_rate():
+    """The finding behind the tensor-map TMA boxes: one cp.async.bulk costs ~60-110 cycles of TMA-engine time
+    whatever its size, so a ring refilled with 2 KB copies fills at a fraction of the rate of one refilled with 32 KB copies."""
+    lib = _lib.load()
+    src = torch.zeros(32 << 20, dtype=torch.uint8, device="cuda")
+    st = torch.zeros(1, dtype=torch.int32, device="cuda")
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    rate = {}
+    for copy, per, slots in ((2048, 8, 4), (32768, 3, 2)):
+        cyc = torch.zeros(1, dtype=torch.int64, device="cuda")
+        iters = (8 << 20) // (copy * per)
+        for _ in range(2):
+            _lib.check(lib.mgb_probe_bulk_rate(_lib.ptr(src), src.numel(), 1, copy, per, slots, iters, _lib.ptr(cyc), _lib.ptr(st),
+                                               stream), "mgb_probe_bulk_rate")
+            torch.cuda.synchronize()
+        assert int(st.item()) == 0
+        rate[copy] = copy * per * iters / float(cyc.item())
+    _report(f"bulk copy fill rate, one SM: 2 KB copies {rate[2048]:.1f} B/clk, 32 KB copies {rate[32768]:.1f} B/clk")
+    assert rate[32768] > 2.5 * rate[2048]

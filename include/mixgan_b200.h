@@ -85,6 +85,8 @@ const char* mgb_last_error(void);
  * dominant kernel with CUDA events on the launching stream; mgb_profile_collect synchronises
  * those events, returns their summed duration and count, and clears them. */
 long long mgb_launch_count(void);
+/* A host that replays a captured CUDA graph of this library's launches reports the replayed launches here. */
+void mgb_note_launches(long long n);
 void mgb_profile_enable(int on);
 int mgb_profile_collect(float* total_ms, int* count);
 

@@ -28,6 +28,7 @@ SIGNATURES = {
     "mgb_abi_version": (_I, []),
     "mgb_last_error": (C.c_char_p, []),
     "mgb_launch_count": (C.c_longlong, []),
+    "mgb_note_launches": (None, [C.c_longlong]),
     "mgb_profile_enable": (None, [_I]),
     "mgb_profile_collect": (_I, [C.POINTER(C.c_float), C.POINTER(C.c_int)]),
     "mgb_debug_status": (_I, [_D, _I, _I, _I, _P, C.POINTER(C.c_int)]),

@@ -185,6 +185,7 @@ extern "C" {
 int mgb_abi_version(void) { return MGB_ABI_VERSION; }
 
 long long mgb_launch_count(void) { return g_launches.load(); }
+void mgb_note_launches(long long n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 void mgb_profile_enable(int on) {
   std::lock_guard<std::mutex> lk(g_prof_mu);

@@ -15,6 +15,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import weakref
 
 import torch
 from torch import nn
@@ -93,6 +94,13 @@ class Denoiser(nn.Module):
         self._ws = _Workspace()
         self._train_ws = _Workspace()
         self.grad_sync = None      # optional mixgan_tts_b200.grad_sync.GradSync (data-parallel training)
+        # Opt-in (MIXGAN_B200_TRAIN_GRAPHS=1 or `den.use_cuda_graphs = True`): from the third call with one signature on,
+        # the library's ~220 launches per training step are replayed as CUDA graphs over static buffers.  Measured on
+        # B200 at B=8 x T=800: host enqueue time 3.98 -> 3.36 ms per step, device time 3.82 ms — the step is then bound by
+        # the device and by torch's own per-parameter host work (autograd, fused Adam over 162 tensors), so the gain is
+        # ~3 %; bit-identical to the eager path (tests/test_gpu_train.py).
+        self.use_cuda_graphs = os.environ.get("MIXGAN_B200_TRAIN_GRAPHS", "0") == "1"
+        self._train_graphs = {}
 
     # ---------------------------------------------------------------- weights
     def _ordered_params(self):
@@ -207,6 +215,63 @@ class Denoiser(nn.Module):
         return _DenoiserGradFn.apply(self, mel.float().contiguous(), diffusion_step, cond_bth, spk, *params)
 
 
+class _TrainGraph:
+    """Static buffers + captured CUDA graphs of the library's training forward / backward for one call signature.
+
+    A graph replays fixed addresses, so inputs are copied into the static buffers and results are cloned out of them;
+    the flat parameter vector is refreshed with one multi-tensor copy and the fp32 weight pack is part of the forward
+    graph.  One forward may be in flight per signature (the activation stash is static); a second forward before the
+    first one's backward simply takes the eager path."""
+
+    WARMUP_CALLS = 2      # eager calls before capturing (first-use initialisation inside the library must not be captured)
+
+    def __init__(self, den, B, T, prec, device):
+        lib, dims = _lib.load(), den.dims
+        M, H = dims.n_mel, dims.d_encoder
+        f32 = dict(dtype=torch.float32, device=device)
+        u8 = dict(dtype=torch.uint8, device=device)
+        self.calls = 0
+        self.x = torch.empty((B, 1, M, T), **f32)
+        self.t = torch.empty((B,), dtype=torch.int64, device=device)
+        self.cond = torch.empty((B, T, H), **f32)
+        self.spk = torch.empty((B, H), **f32) if dims.multi_speaker else None
+        self.out = torch.empty((B, 1, M, T), **f32)
+        self.saved = torch.empty(lib.mgb_train_saved_bytes(C.byref(dims), prec, B, T), **u8)
+        nflat = lib.mgb_flat_weight_count(C.byref(dims))
+        self.flat = torch.empty(nflat, **f32)
+        self.flat_views, off = [], 0
+        for p in den._ordered_params():
+            self.flat_views.append(self.flat[off:off + p.numel()].view(p.shape))
+            off += p.numel()
+        self.flat_fp = None
+        self.packed = torch.empty(lib.mgb_packed_bytes(C.byref(dims), _lib.PREC_FP32), **u8)
+        self.gout = torch.empty((B, 1, M, T), **f32)
+        self.gflat = torch.empty(nflat, **f32)
+        self.gx = torch.empty((B, 1, M, T), **f32)
+        self.gcond = torch.empty((B, T, H), **f32)
+        self.gspk = torch.empty((B, H), **f32) if dims.multi_speaker else None
+        self.fwd = None                 # (graph, launches)
+        self.bwd = {}                   # (bucket plan, need flags) -> [(graph, launches, flat_begin, flat_end)]
+        self.token_ref = None
+
+    def busy(self) -> bool:
+        return self.token_ref is not None and self.token_ref() is not None
+
+
+class _Token:
+    """Held by the autograd context of the forward that owns a _TrainGraph's activation stash."""
+    __slots__ = ("__weakref__",)
+
+
+def _capture(lib, fn):
+    """Capture the launches `fn(stream)` enqueues into a CUDA graph; returns (graph, number of library launches)."""
+    g = torch.cuda.CUDAGraph()
+    n0 = lib.mgb_launch_count()
+    with torch.cuda.graph(g):
+        fn(C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    return g, lib.mgb_launch_count() - n0
+
+
 class _DenoiserGradFn(torch.autograd.Function):
     """autograd node for ``Denoiser.forward``: ``mgb_denoiser_train_forward`` / ``mgb_denoiser_backward``.
 
@@ -218,10 +283,51 @@ class _DenoiserGradFn(torch.autograd.Function):
         lib = _lib.load()
         dev = x.device
         B, _, M, T = x.shape
+        prec = PRECISIONS[den.precision]
+        tg = None
+        if den.use_cuda_graphs:
+            key = (B, T, prec, dev)
+            tg = den._train_graphs.get(key)
+            if tg is None:
+                tg = den._train_graphs[key] = _TrainGraph(den, B, T, prec, dev)
+            tg.calls += 1
+            if tg.calls <= _TrainGraph.WARMUP_CALLS or tg.busy():
+                tg = None
+        if tg is not None:
+            with torch.cuda.device(dev):
+                fp = tuple((p.data_ptr(), p._version) for p in params)
+                if tg.flat_fp != fp:
+                    torch._foreach_copy_(tg.flat_views, [p.detach() for p in params])
+                    tg.flat_fp = fp
+                tg.x.copy_(x)
+                tg.t.copy_(t.detach())
+                tg.cond.copy_(cond_bth)
+                if tg.spk is not None:
+                    tg.spk.copy_(spk)
+                if tg.fwd is None:
+                    ws = den.train_workspace(B, T, dev)
+
+                    def enqueue(stream):
+                        _lib.check(lib.mgb_pack_weights(C.byref(den.dims), _lib.PREC_FP32, _lib.ptr(tg.flat), _lib.ptr(tg.packed),
+                                                        tg.packed.numel(), stream), "mgb_pack_weights")
+                        _lib.check(lib.mgb_denoiser_train_forward(
+                            C.byref(den.dims), prec, _lib.ptr(tg.packed), _lib.ptr(tg.flat), _lib.ptr(tg.x), _lib.ptr(tg.t),
+                            _lib.ptr(tg.cond), _lib.ptr(tg.spk), _lib.ptr(tg.out), _lib.ptr(tg.saved), tg.saved.numel(), B, T,
+                            _lib.ptr(ws), ws.numel(), stream), "mgb_denoiser_train_forward")
+                    tg.fwd = _capture(lib, enqueue)
+                tg.fwd[0].replay()
+                lib.mgb_note_launches(tg.fwd[1])
+                out = tg.out.clone()
+            token = _Token()
+            tg.token_ref = weakref.ref(token)
+            ctx.den, ctx.tg, ctx.token, ctx.prec = den, tg, token, prec
+            ctx.shape = (B, M, T)
+            ctx.param_shapes = [p.shape for p in params]
+            return out
+        ctx.tg = None
         with torch.cuda.device(dev):
             packed = den.packed_weights("fp32")      # both precisions: the per-utterance step MLP / tables are fp32
             flat = den.flat_weights()
-            prec = PRECISIONS[den.precision]
             tt = t.detach().to(torch.int64).contiguous()
             out = torch.empty_like(x)
             saved = torch.empty(lib.mgb_train_saved_bytes(C.byref(den.dims), prec, B, T), dtype=torch.uint8, device=dev)
@@ -238,8 +344,66 @@ class _DenoiserGradFn(torch.autograd.Function):
         return out
 
     @staticmethod
+    def _segment_ranges(den):
+        lib = _lib.load()
+        ranges = []
+        for s in range(lib.mgb_train_segments(C.byref(den.dims))):
+            b, e = C.c_size_t(0), C.c_size_t(0)
+            _lib.check(lib.mgb_train_segment_range(C.byref(den.dims), s, C.byref(b), C.byref(e)), "segment range")
+            ranges.append((b.value, e.value))
+        return ranges
+
+    @staticmethod
+    def _backward_graphed(ctx, gout):
+        from .grad_sync import plan_buckets
+        den, lib, tg = ctx.den, _lib.load(), ctx.tg
+        B, M, T = ctx.shape
+        dev = gout.device
+        need = ctx.needs_input_grad
+        with torch.cuda.device(dev):
+            sync = den.grad_sync
+            buckets = tuple(plan_buckets(_DenoiserGradFn._segment_ranges(den), sync.bucket_bytes if sync is not None else None))
+            want = (bool(need[1]), bool(need[3]), bool(tg.spk is not None and need[4]))
+            tg.gout.copy_(gout)
+            graphs = tg.bwd.get((buckets, want))
+            if graphs is None:
+                ws = den.train_workspace(B, T, dev)
+                graphs = []
+                for sb, se, fb, fe in buckets:
+                    def enqueue(stream, sb=sb, se=se):
+                        _lib.check(lib.mgb_denoiser_backward(
+                            C.byref(den.dims), ctx.prec, _lib.ptr(tg.flat), _lib.ptr(tg.saved), tg.saved.numel(), _lib.ptr(tg.t),
+                            _lib.ptr(tg.cond), _lib.ptr(tg.spk), _lib.ptr(tg.gout), _lib.ptr(tg.gflat),
+                            _lib.ptr(tg.gcond if want[1] else None), _lib.ptr(tg.gspk if want[2] else None),
+                            _lib.ptr(tg.gx if want[0] else None), B, T, sb, se, _lib.ptr(ws), ws.numel(), stream),
+                            "mgb_denoiser_backward")
+                    g, n = _capture(lib, enqueue)
+                    graphs.append((g, n, fb, fe))
+                tg.bwd[(buckets, want)] = graphs
+            for g, n, fb, fe in graphs:
+                g.replay()
+                lib.mgb_note_launches(n)
+                if sync is not None:
+                    sync.reduce_async(tg.gflat[fb:fe])
+            if sync is not None:
+                sync.finish()
+            gflat = tg.gflat.clone()          # the static buffers are rewritten by the next step
+            gx = tg.gx.clone() if want[0] else None
+            gcond = tg.gcond.clone() if want[1] else None
+            gspk = tg.gspk.clone() if want[2] else None
+        grads, off = [], 0
+        for shp, nd in zip(ctx.param_shapes, need[5:]):
+            n = int(torch.Size(shp).numel())
+            grads.append(gflat[off:off + n].view(shp) if nd else None)
+            off += n
+        ctx.token = None                      # releases the signature's activation stash
+        return (None, gx, None, gcond, gspk, *grads)
+
+    @staticmethod
     def backward(ctx, gout):
         from .grad_sync import plan_buckets
+        if ctx.tg is not None:
+            return _DenoiserGradFn._backward_graphed(ctx, gout.float().contiguous())
         den, lib = ctx.den, _lib.load()
         B, M, T = ctx.shape
         dev = gout.device

@@ -254,3 +254,54 @@ def test_bf16_training_edge_shapes_vs_fp32_path(multi, B, T, L):
     assert errs["out"] < TOL_BF16_OUT
     assert all(v < TOL_BF16_GRAD for k, v in errs.items() if k != "out"), errs
     assert worst[1] < TOL_BF16_GRAD, worst
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_cuda_graph_replay_matches_eager_bit_for_bit(precision):
+    """From the third call on, the library's launch sequences are replayed as CUDA graphs (static buffers); the
+    gradients and the parameter trajectory under an optimizer must be bit-identical to the eager path."""
+    name = "train_shallow_aishell_spk_B2_T40"
+    c, ex = train_case(name)
+    probe = probe_for(name, c)
+    hist = {}
+    for graphs in (False, True):
+        gd = build(c, precision)
+        gd.denoise_fn.use_cuda_graphs = graphs
+        opt = torch.optim.SGD(gd.parameters(), lr=1e-3)
+        losses = []
+        for step in range(6):
+            loss, _, grads, gcond, gspk, _ = run_library(c, ex, probe, gd)
+            opt.step()
+            losses.append((float(loss), gcond.clone(), gspk.clone(), {k: v.clone() for k, v in grads.items()}))
+        hist[graphs] = losses
+        if graphs:
+            tgs = list(gd.denoise_fn._train_graphs.values())
+            assert len(tgs) == 1 and tgs[0].fwd is not None and len(tgs[0].bwd) == 1, "the graph path was not taken"
+            if precision == "bf16":
+                assert _status(gd, c.B, c.T) == 0
+    for (la, ca, sa, ga), (lb, cb, sb, gb) in zip(hist[False], hist[True]):
+        assert la == lb
+        assert torch.equal(ca, cb) and torch.equal(sa, sb)
+        assert all(torch.equal(ga[k], gb[k]) for k in ga)
+    assert hist[True][-1][0] < hist[True][0][0]      # and the optimizer actually moved the parameters
+
+
+def test_second_forward_before_backward_falls_back_to_eager():
+    """The graph path owns ONE activation stash per signature: a second forward in flight takes the eager path."""
+    c = Case("LJSpeech", "naive", False, 2, 33, wseed=3, iseed=9, layers=2)
+    gd = build(c, "fp32")
+    den = gd.denoise_fn
+    x, cond = cu(c.t("x_T")), cu(c.t("cond").transpose(1, 2).contiguous())
+    t = torch.zeros(2, dtype=torch.long).cuda()
+    outs = []
+    for _ in range(3):                                   # warm-up eager calls, then one graphed forward
+        cr = cond.clone().requires_grad_(True)
+        o = den(x, t, cr, None)
+        o.sum().backward()
+        outs.append(cr.grad.clone())
+    c1, c2 = cond.clone().requires_grad_(True), cond.clone().requires_grad_(True)
+    o1 = den(x, t, c1, None)                             # graphed, holds the stash
+    o2 = den(x, t, c2, None)                             # must not clobber it
+    o2.sum().backward()
+    o1.sum().backward()
+    assert torch.equal(c1.grad, outs[0]) and torch.equal(c2.grad, outs[0])

@@ -146,6 +146,16 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    if args.workload == "train":
+        base = cpu_oracle_train_throughput(args.train_batch)
+        print(json.dumps({
+            "impl": "reference", "metric": "train_frames_per_sec", "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": 2, "warmup": 0, "ms_per_step": 1e3 * args.train_batch * T_FRAMES / base["value"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"LJSpeech naive diffusion-decoder training branch (forward + autograd backward), CPU, "
+                                   f"B={args.train_batch} x T={T_FRAMES}"},
+            "cpu_baseline": base, "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
     steps = max(1, min(args.steps, 5))
     base, times = cpu_oracle_throughput(steps)
     ms = 1e3 * statistics.mean(times)

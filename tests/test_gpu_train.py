@@ -216,7 +216,7 @@ def test_bf16_training_path_vs_oracle(name):
 
 
 @pytest.mark.parametrize("multi,B,T,L", [(False, 1, 1, 2), (False, 2, 3, 1), (True, 2, 129, 3), (False, 3, 257, 2),
-                                         (True, 4, 200, 20)])
+                                         (True, 4, 200, 20), (False, 8, 800, 20), (True, 12, 1500, 20)])
 def test_bf16_training_edge_shapes_vs_fp32_path(multi, B, T, L):
     """bf16 path against the library's own fp32 path (which the tests above pin to the oracle) on ragged shapes, with the
     two ReLU masks made stable (+8 on the input- and skip-projection biases) so that the comparison measures arithmetic."""

@@ -428,6 +428,86 @@ def run_train(args):
         dist.destroy_process_group()
 
 
+def run_c3(args):
+    """--workload c3: BASELINE configs[2] / SURVEY 8(d) C3 — LJSpeech `shallow` (aux-decoder mel -> K=1 shallow diffusion),
+    512 utterances of T=800 sharded contiguously by utterance over the N ranks (STRONG scaling, no collective on the data
+    path), every rank running mixgan_tts_b200.pipeline.BatchSynthesizer on its shard in batches of 64 with pinned HOST
+    buffers in and out.  value = 512 * 800 frames / (max over ranks of the device-timed pass)."""
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    from mixgan_tts_b200 import GaussianDiffusion, _lib, configs, synth, shard
+    from mixgan_tts_b200.pipeline import BatchSynthesizer
+    lib = _lib.load()
+    N_UTT, T, BATCH = 512, T_FRAMES, 64
+    cfg = configs.make_configs("LJSpeech", "shallow")
+    gd = GaussianDiffusion(*cfg, precision="bf16" if args.precision == "auto" else args.precision)
+    gd.denoise_fn.load_state_dict({k: torch.from_numpy(v) for k, v in synth.make_denoiser_weights(0).items()})
+    gd = gd.to(dev).eval()
+    lo, hi = shard.contiguous_shard(N_UTT, world, rank)
+    # the shard's utterances as pinned host batches (3 distinct synthetic batches, cycled: > L2 per pass)
+    protos = []
+    for i in range(3):
+        inp = synth.make_inputs(500 + 7 * i + 100 * rank, BATCH, T, 1, shallow=True)
+        protos.append(tuple(torch.from_numpy(inp[k]).pin_memory() for k in ("cond", "pad_mask")) + (None,)
+                      + (torch.from_numpy(inp["coarse_mel"]).pin_memory(),))
+    batches = []
+    for b0 in range(lo, hi, BATCH):
+        n = min(BATCH, hi - b0)
+        pr = protos[(b0 // BATCH) % 3]
+        batches.append(tuple(None if t is None else t[:n] for t in pr))
+    pipe = BatchSynthesizer(gd, dev)
+
+    def one_pass():
+        acc = 0.0
+        for mel in pipe.run(iter(batches)):
+            acc += float(mel[0, 0, 0])
+        return acc
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        one_pass()
+    barrier()
+    n0 = lib.mgb_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        one_pass()
+    e1.record()
+    barrier()
+    ms = shard.max_over_ranks(e0.elapsed_time(e1), dev)
+    launches = lib.mgb_launch_count() - n0
+    if rank == 0:
+        val = N_UTT * T * args.steps / (ms * 1e-3)
+        print(json.dumps({
+            "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic",
+            "config": {"workload": f"LJSpeech shallow K=1 batch synthesis, {N_UTT} utterances x T={T} sharded by utterance over "
+                                   f"{world} GPU(s) in batches of {BATCH} (BASELINE configs[2]); end to end: pinned host cond / mask / "
+                                   "coarse mel in, pinned host mel out, copies overlapped with compute",
+                       "utterances_per_rank": hi - lo},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": int(N_UTT * T * (256 * 4 + 80 * 4 + 1)),
+                    "d2h_bytes_per_step": int(N_UTT * T * 80 * 4), "ms_per_step": ms / args.steps},
+            "gpu_launches": int(launches)}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def cpu_oracle_train_throughput(B: int):
     """The oracle's training branch + torch autograd on all host threads, one step at the same shape."""
     import torch
@@ -464,12 +544,15 @@ def main():
     ap.add_argument("--precision", default="auto", choices=["auto", "bf16", "fp32"])
     ap.add_argument("--batch", type=int, default=B_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="sample", choices=["sample", "train"],
-                    help="sample = the headline reverse-diffusion benchmark; train = Denoiser training step (configs[4] path)")
+    ap.add_argument("--workload", default="sample", choices=["sample", "train", "c3"],
+                    help="sample = the headline reverse-diffusion benchmark; train = Denoiser training step (configs[4] path); "
+                         "c3 = 512-utterance shallow-diffusion batch synthesis, strong scaling (configs[2])")
     ap.add_argument("--train-batch", type=int, default=8)
     args = ap.parse_args()
     if args.workload == "train" and args.impl == "ours":
         run_train(args)
+    elif args.workload == "c3" and args.impl == "ours":
+        run_c3(args)
     elif args.impl == "reference":
         run_reference(args)
     else:

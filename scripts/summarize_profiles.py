@@ -106,10 +106,11 @@ if os.path.exists(rep):
             "l1tex__t_sectors_pipe_lsu_mem_global_op_st.sum", "l1tex__t_requests_pipe_lsu_mem_global_op_st.sum",
             "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum", "l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum"]
     with open(os.path.join(out, "ncu_train_gemm_summary.txt"), "w") as f:
-        f.write("ncu --set full --clock-control none --import-source on -k regex:'fgemm_kernel|wgemm_kernel' -s 590 -c 8  "
+        f.write("ncu --set full --clock-control none --import-source on -k regex:'fgemm_kernel|wgemm_kernel' -s 560 -c 8  "
                 "python bench.py --workload train --precision bf16 --steps 2 --warmup 3\n"
-                "(consecutive GEMM launches inside the backward of one training step, B=8 x T=800: mode 8 = gate-backward GEMM,\n"
-                " mode 9 = transposed-conv GEMM, wgemm = weight-gradient GEMMs; cold caches, serialised)\n\n")
+                "(eight consecutive GEMM launches of one training step, B=8 x T=800; fgemm_kernel<NT, MODE, CLUSTER>: mode 1 = conditioner\n"
+                " GEMM, 2 = k=3 conv + gate, 3 = output projection, 8 = gate-backward GEMM, 9 = transposed-conv GEMM; wgemm = weight-\n"
+                " gradient GEMMs; cold caches, serialised)\n\n")
         for i, h in enumerate(hdr):
             if h in want:
                 f.write(f"{h} [{rows[1][i]}] = {' | '.join(r[i][:40] for r in rows[2:])}\n")

@@ -324,7 +324,7 @@ def run_ours(args):
             "gpu_launches": int(launches), "clocks": clocks,
         }
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"], _ = cpu_oracle_throughput(2)
+            line["cpu_baseline"], _ = cpu_oracle_throughput(8)      # ~10 s of CPU work on the box's host cores
         else:
             line["cpu_baseline"] = None
         print(json.dumps(line))

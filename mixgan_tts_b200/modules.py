@@ -237,6 +237,9 @@ class _TrainGraph:
         self.spk = torch.empty((B, H), **f32) if dims.multi_speaker else None
         self.out = torch.empty((B, 1, M, T), **f32)
         self.saved = torch.empty(lib.mgb_train_saved_bytes(C.byref(dims), prec, B, T), **u8)
+        # its own workspace: the module's shared one is reallocated when a larger shape comes along, and a captured graph
+        # must keep replaying the addresses it was captured with
+        self.ws = torch.empty(lib.mgb_train_workspace_bytes(C.byref(dims), prec, B, T), **u8)
         nflat = lib.mgb_flat_weight_count(C.byref(dims))
         self.flat = torch.empty(nflat, **f32)
         self.flat_views, off = [], 0
@@ -305,7 +308,7 @@ class _DenoiserGradFn(torch.autograd.Function):
                 if tg.spk is not None:
                     tg.spk.copy_(spk)
                 if tg.fwd is None:
-                    ws = den.train_workspace(B, T, dev)
+                    ws = tg.ws
 
                     def enqueue(stream):
                         _lib.check(lib.mgb_pack_weights(C.byref(den.dims), _lib.PREC_FP32, _lib.ptr(tg.flat), _lib.ptr(tg.packed),
@@ -357,6 +360,9 @@ class _DenoiserGradFn(torch.autograd.Function):
     def _backward_graphed(ctx, gout):
         from .grad_sync import plan_buckets
         den, lib, tg = ctx.den, _lib.load(), ctx.tg
+        if ctx.token is None:
+            raise RuntimeError("mixgan_tts_b200.Denoiser: the activation stash is released by the first backward "
+                               "(a second backward through the same forward / retain_graph=True is not supported)")
         B, M, T = ctx.shape
         dev = gout.device
         need = ctx.needs_input_grad
@@ -367,7 +373,7 @@ class _DenoiserGradFn(torch.autograd.Function):
             tg.gout.copy_(gout)
             graphs = tg.bwd.get((buckets, want))
             if graphs is None:
-                ws = den.train_workspace(B, T, dev)
+                ws = tg.ws
                 graphs = []
                 for sb, se, fb, fe in buckets:
                     def enqueue(stream, sb=sb, se=se):
@@ -405,6 +411,9 @@ class _DenoiserGradFn(torch.autograd.Function):
         if ctx.tg is not None:
             return _DenoiserGradFn._backward_graphed(ctx, gout.float().contiguous())
         den, lib = ctx.den, _lib.load()
+        if ctx.saved is None:
+            raise RuntimeError("mixgan_tts_b200.Denoiser: the activation stash is released by the first backward "
+                               "(a second backward through the same forward / retain_graph=True is not supported)")
         B, M, T = ctx.shape
         dev = gout.device
         need = ctx.needs_input_grad          # (den, x, t, cond, spk, *params)

@@ -172,11 +172,12 @@ def test_train_abi_errors():
 TOL_BF16_OUT, TOL_BF16_GRAD, TOL_BF16_GRAD_RELU = 2e-2, 2e-2, 1e-1
 
 
-def _status(gd, B, T):
+def _status(gd, B, T, ws=None):
     lib = _lib.load()
     st = C.c_int(-1)
     den = gd.denoise_fn
-    _lib.check(lib.mgb_train_debug_status(C.byref(den.dims), B, T, _lib.ptr(den._train_ws.buf), C.byref(st)), "status")
+    _lib.check(lib.mgb_train_debug_status(C.byref(den.dims), B, T, _lib.ptr(ws if ws is not None else den._train_ws.buf),
+                                          C.byref(st)), "status")
     return st.value
 
 
@@ -278,7 +279,7 @@ def test_cuda_graph_replay_matches_eager_bit_for_bit(precision):
             tgs = list(gd.denoise_fn._train_graphs.values())
             assert len(tgs) == 1 and tgs[0].fwd is not None and len(tgs[0].bwd) == 1, "the graph path was not taken"
             if precision == "bf16":
-                assert _status(gd, c.B, c.T) == 0
+                assert _status(gd, c.B, c.T) == 0 and _status(gd, c.B, c.T, tgs[0].ws) == 0
     for (la, ca, sa, ga), (lb, cb, sb, gb) in zip(hist[False], hist[True]):
         assert la == lb
         assert torch.equal(ca, cb) and torch.equal(sa, sb)

@@ -97,8 +97,8 @@ class Denoiser(nn.Module):
         # Opt-in (MIXGAN_B200_TRAIN_GRAPHS=1 or `den.use_cuda_graphs = True`): from the third call with one signature on,
         # the library's ~220 launches per training step are replayed as CUDA graphs over static buffers.  Measured on
         # B200 at B=8 x T=800: host enqueue time 3.98 -> 3.36 ms per step, device time 3.82 ms — the step is then bound by
-        # the device and by torch's own per-parameter host work (autograd, fused Adam over 162 tensors), so the gain is
-        # ~3 %; bit-identical to the eager path (tests/test_gpu_train.py).
+        # the device and by torch's own per-parameter host work (autograd, fused Adam over 162 tensors), so the step time
+        # does not change measurably; bit-identical to the eager path (tests/test_gpu_train.py).
         self.use_cuda_graphs = os.environ.get("MIXGAN_B200_TRAIN_GRAPHS", "0") == "1"
         self._train_graphs = {}
 

@@ -68,6 +68,10 @@ enum {
   MGB_PREC_BF16 = 1  /* bf16 operands on tcgen05 tensor cores, fp32 accumulation in TMEM,
                         fp32 residual stream, fp32 posterior update                             */
 };
+/* mgb_pack_weights / mgb_packed_bytes only: the MGB_PREC_FP32 buffer (same size and offsets) with ONLY the per-utterance
+ * table weights filled (step MLP, diffusion / speaker projections, conditioner bias) in one launch — what the bf16
+ * training forward needs as `packed`, re-packed every step. */
+#define MGB_PACK_FP32_TABLES 2
 
 typedef struct mgb_model_dims {
   int32_t n_mel;         /* 80  */

@@ -12,6 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libmixgan_b200.so")
 
 PREC_FP32, PREC_BF16 = 0, 1
+PACK_FP32_TABLES = 2       # mgb_pack_weights only: the fp32 buffer with just the per-utterance table weights
 E_ARG, E_ARCH, E_WORKSPACE, E_CUDA, E_UNSUPPORTED = -1, -2, -3, -4, -5
 
 

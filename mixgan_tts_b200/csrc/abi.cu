@@ -244,7 +244,7 @@ size_t mgb_flat_weight_count(const mgb_model_dims* dims) {
 
 size_t mgb_packed_bytes(const mgb_model_dims* dims, int precision) {
   if (!dims_supported(dims)) return 0;
-  return precision == MGB_PREC_FP32 ? fp32_packed_bytes(*dims)
+  return (precision == MGB_PREC_FP32 || precision == MGB_PACK_FP32_TABLES) ? fp32_packed_bytes(*dims)
        : precision == MGB_PREC_BF16 ? bf16_packed_bytes(*dims) : 0;
 }
 
@@ -257,6 +257,7 @@ int mgb_pack_weights(const mgb_model_dims* dims, int precision, const float* fla
   MGB_REQUIRE(need > 0, MGB_E_ARG, "unknown precision %d", precision);
   MGB_REQUIRE(packed_bytes >= need, MGB_E_WORKSPACE, "packed buffer too small: %zu < %zu", packed_bytes, need);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (precision == MGB_PACK_FP32_TABLES) return fp32_pack_tables(*dims, flat, packed, s);
   return precision == MGB_PREC_FP32 ? fp32_pack(*dims, flat, packed, s) : bf16_pack(*dims, flat, packed, s);
 }
 

@@ -131,6 +131,7 @@ void prof_end(cudaStream_t s);
 // ---- fp32 path (fp32_path.cu) ---------------------------------------------------------------
 size_t fp32_packed_bytes(const mgb_model_dims& d);
 int fp32_pack(const mgb_model_dims& d, const float* flat, void* packed, cudaStream_t s);
+int fp32_pack_tables(const mgb_model_dims& d, const float* flat, void* packed, cudaStream_t s);
 size_t fp32_workspace_bytes(const mgb_model_dims& d, int B, int T);
 // One Denoiser call.  If sched != nullptr the posterior update is fused (writes x_prev); out_x0
 // receives the (optionally clamped) x0 when non-null.

@@ -264,6 +264,50 @@ int fp32_pack(const mgb_model_dims& d, const float* flat, void* packed, cudaStre
   return MGB_OK;
 }
 
+// Only what fp32_step_tables reads (step MLP, diffusion / speaker projections, conditioner bias), same offsets as the full
+// pack, ONE launch: the bf16 training forward re-packs these every step (the parameters change every step).
+struct TablesPack {
+  size_t src[4], dst[4];   // [0] mlp0 [4C][C] -> [C][4C], [1] mlp2 [C][4C] -> [4C][C], [2] dproj [C][C] (per layer), [3] sproj
+  size_t src_cb, dst_cb, src_lstride, dst_lstride;
+  int C, H, L, multi;
+};
+__global__ void __launch_bounds__(256) pack_tables_kernel(const float* __restrict__ flat, float* __restrict__ P, const TablesPack a) {
+  // blockIdx.y: 0 = mlp0, 1 = mlp2, 2 + l = layer l (dproj, sproj, cproj_b)
+  const int which = blockIdx.y, C = a.C, H = a.H;
+  auto transpose = [&](const float* src, float* dst, int n_out, int n_in) {   // dst[k][n] = src[n][k]
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_out * n_in; i += gridDim.x * blockDim.x) {
+      const int k = i / n_out, n = i - k * n_out;
+      dst[i] = src[(size_t)n * n_in + k];
+    }
+  };
+  if (which == 0) transpose(flat + a.src[0], P + a.dst[0], 4 * C, C);
+  else if (which == 1) transpose(flat + a.src[1], P + a.dst[1], C, 4 * C);
+  else {
+    const int l = which - 2;
+    const float* fl = flat + (size_t)l * a.src_lstride;
+    float* pl = P + (size_t)l * a.dst_lstride;
+    transpose(fl + a.src[2], pl + a.dst[2], C, C);
+    if (a.multi) transpose(fl + a.src[3], pl + a.dst[3], C, H);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < C; i += gridDim.x * blockDim.x) pl[a.dst_cb + i] = fl[a.src_cb + i];
+  }
+}
+int fp32_pack_tables(const mgb_model_dims& d, const float* flat, void* packed, cudaStream_t s) {
+  const FlatOffsets f = flat_offsets(d);
+  const PackedF32 o = packed_layout(d);
+  TablesPack a{};
+  a.C = d.channels; a.H = d.d_encoder; a.L = d.layers; a.multi = d.multi_speaker;
+  a.src[0] = f.mlp0_w; a.dst[0] = o.mlp0_wt;
+  a.src[1] = f.mlp2_w; a.dst[1] = o.mlp2_wt;
+  a.src[2] = f.layer0 + f.rel.dproj_w; a.dst[2] = o.layer0 + o.r_dproj_wt;
+  a.src[3] = f.layer0 + f.rel.sproj_w; a.dst[3] = o.layer0 + o.r_sproj_wt;
+  a.src_cb = f.layer0 + f.rel.cproj_b; a.dst_cb = o.layer0 + o.r_cproj_b;
+  a.src_lstride = f.layer_stride; a.dst_lstride = o.layer_stride;
+  pack_tables_kernel<<<dim3(32, 2 + d.layers), 256, 0, s>>>(flat, static_cast<float*>(packed), a);
+  note_launch();
+  MGB_LAUNCH_CHECK();
+  return MGB_OK;
+}
+
 // d[B][C] = step MLP(t); dtab[b][l] = Wd_l d[b]; ctab[b][l] = bc_l (+ Ws_l spk[b])   (blocks.py:1159-1164)
 int fp32_step_tables(const mgb_model_dims& d, const void* packed, const int64_t* t, const float* spk, int B, float* d_buf,
                      float* h_buf, float* dtab, float* ctab, cudaStream_t s) {

@@ -23,6 +23,29 @@ from torch import nn
 from . import _lib
 
 PRECISIONS = {"fp32": _lib.PREC_FP32, "bf16": _lib.PREC_BF16}
+_PACK_KINDS = dict(PRECISIONS, fp32_tables=_lib.PACK_FP32_TABLES)
+
+# Fused optimizers (torch.optim.Adam(fused=True) ...) update parameters in place WITHOUT bumping Tensor._version, so the
+# (data_ptr, _version) fingerprint alone would keep serving stale kernel-layout weights after an optimizer step.  Every
+# optimizer step therefore advances this epoch, which is part of the fingerprint.
+_PARAM_EPOCH = [0]
+
+
+def _on_optimizer_step(*_args, **_kwargs):
+    _PARAM_EPOCH[0] += 1
+
+
+try:
+    from torch.optim.optimizer import register_optimizer_step_post_hook as _register_post_hook
+    _register_post_hook(_on_optimizer_step)
+except Exception:                                   # pragma: no cover - very old torch: fall back to never caching
+    _PARAM_EPOCH = None
+
+
+def _param_fingerprint(params):
+    if _PARAM_EPOCH is None:
+        return object()                             # never equal: rebuild every time
+    return (_PARAM_EPOCH[0],) + tuple((p.data_ptr(), p._version) for p in params)
 
 
 def default_precision() -> str:
@@ -120,9 +143,9 @@ class Denoiser(nn.Module):
     def packed_weights(self, precision: str | None = None) -> torch.Tensor:
         """Kernel-layout copy of the parameters; rebuilt when any parameter changes."""
         precision = precision or self.precision
-        prec = PRECISIONS[precision]
+        prec = _PACK_KINDS[precision]
         params = self._ordered_params()
-        fp = tuple((p.data_ptr(), p._version) for p in params)
+        fp = _param_fingerprint(params)
         hit = self._packed.get(precision)
         if hit is not None and hit[0] == fp:
             return hit[1]
@@ -194,8 +217,8 @@ class Denoiser(nn.Module):
 
     # ---------------------------------------------------------------- training (autograd)
     def flat_weights(self) -> torch.Tensor:
-        """The parameters as one fp32 vector in the canonical order (cached together with the fp32 pack)."""
-        self.packed_weights("fp32")
+        """The parameters as one fp32 vector in the canonical order (built together with a weight pack)."""
+        self.packed_weights("fp32" if self.precision == "fp32" else "fp32_tables")
         return self._flat[1]
 
     def train_workspace(self, B: int, T: int, device) -> torch.Tensor:
@@ -298,7 +321,7 @@ class _DenoiserGradFn(torch.autograd.Function):
                 tg = None
         if tg is not None:
             with torch.cuda.device(dev):
-                fp = tuple((p.data_ptr(), p._version) for p in params)
+                fp = _param_fingerprint(params)
                 if tg.flat_fp != fp:
                     torch._foreach_copy_(tg.flat_views, [p.detach() for p in params])
                     tg.flat_fp = fp
@@ -311,7 +334,8 @@ class _DenoiserGradFn(torch.autograd.Function):
                     ws = tg.ws
 
                     def enqueue(stream):
-                        _lib.check(lib.mgb_pack_weights(C.byref(den.dims), _lib.PREC_FP32, _lib.ptr(tg.flat), _lib.ptr(tg.packed),
+                        kind = _lib.PREC_FP32 if prec == _lib.PREC_FP32 else _lib.PACK_FP32_TABLES
+                        _lib.check(lib.mgb_pack_weights(C.byref(den.dims), kind, _lib.ptr(tg.flat), _lib.ptr(tg.packed),
                                                         tg.packed.numel(), stream), "mgb_pack_weights")
                         _lib.check(lib.mgb_denoiser_train_forward(
                             C.byref(den.dims), prec, _lib.ptr(tg.packed), _lib.ptr(tg.flat), _lib.ptr(tg.x), _lib.ptr(tg.t),
@@ -329,7 +353,8 @@ class _DenoiserGradFn(torch.autograd.Function):
             return out
         ctx.tg = None
         with torch.cuda.device(dev):
-            packed = den.packed_weights("fp32")      # both precisions: the per-utterance step MLP / tables are fp32
+            # both precisions read fp32 per-utterance tables; the bf16 mode needs nothing else from the fp32 pack
+            packed = den.packed_weights("fp32" if den.precision == "fp32" else "fp32_tables")
             flat = den.flat_weights()
             tt = t.detach().to(torch.int64).contiguous()
             out = torch.empty_like(x)

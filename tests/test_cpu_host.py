@@ -134,3 +134,20 @@ def test_light_helpers_match_oracle_on_cpu():
     assert torch.equal(gd.denorm_spec(m), c.oracle.denorm_spec(m))
     tt = torch.tensor([2, -1])
     assert torch.equal(gd.diffuse_fn(m, tt.clone(), noise=nz), c.oracle.diffuse_fn(m, tt.clone(), nz))
+
+
+def test_weight_cache_fingerprint_sees_fused_optimizer_steps():
+    """torch's fused optimizers update parameters in place WITHOUT bumping Tensor._version; the kernel-layout weight
+    caches must still be invalidated (a global optimizer post-step hook advances an epoch that is part of the key)."""
+    from mixgan_tts_b200.modules import _param_fingerprint
+    ps = [torch.nn.Parameter(torch.randn(8)) for _ in range(3)]
+    for p in ps:
+        p.grad = torch.randn(8)
+    fp0 = _param_fingerprint(ps)
+    assert _param_fingerprint(ps) == fp0
+    try:
+        opt = torch.optim.Adam(ps, lr=1e-2, fused=True)
+    except (RuntimeError, ValueError):
+        opt = torch.optim.Adam(ps, lr=1e-2)
+    opt.step()
+    assert _param_fingerprint(ps) != fp0

@@ -143,6 +143,28 @@ def test_optimizer_step_repacks_weights_and_inference_sees_them():
     assert rel_l2(y, ref) < TOL
 
 
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_fused_adam_updates_reach_the_kernels(precision):
+    """Regression: torch.optim.Adam(fused=True) does not bump Tensor._version; the library must still see the new weights
+    in the next training forward AND in inference afterwards."""
+    c, ex = train_case("train_naive_lj_B3_T48")
+    probe = probe_for("train_naive_lj_B3_T48", c)
+    gd = build(c, precision)
+    opt = torch.optim.Adam(gd.parameters(), lr=1e-5, fused=True)
+    losses = []
+    for _ in range(4):
+        losses.append(float(run_library(c, ex, probe, gd)[0]))
+        opt.step()
+    assert losses[3] < losses[2] < losses[1] < losses[0], losses     # every forward saw the previous step's update
+    with torch.no_grad():
+        gd.eval()
+        y = gd.denoise_fn(cu(c.t("x_T")), torch.zeros(c.B, dtype=torch.long).cuda(), cu(c.t("cond")).transpose(1, 2), None)
+    from oracle.denoiser import denoiser_forward
+    W2 = {k: v.detach().cpu() for k, v in gd.denoise_fn.state_dict().items()}
+    ref = denoiser_forward(W2, c.t("x_T"), torch.zeros(c.B, dtype=torch.long), c.t("cond").transpose(1, 2), None)
+    assert rel_l2(y, ref) < (TOL if precision == "fp32" else TOL_BF16_OUT)
+
+
 def test_train_abi_errors():
     lib = _lib.load()
     d = _lib.ModelDims(80, 256, 256, 20, 0)

@@ -114,6 +114,7 @@ class Denoiser(nn.Module):
 
         self._packed = {}          # precision -> (fingerprint, packed tensor)
         self._flat = None          # (fingerprint, flat fp32 parameter vector) of the last pack
+        self._flat_store = None    # (device, persistent flat buffer, per-parameter views into it)
         self._ws = _Workspace()
         self._train_ws = _Workspace()
         self.grad_sync = None      # optional mixgan_tts_b200.grad_sync.GradSync (data-parallel training)
@@ -158,7 +159,19 @@ class Denoiser(nn.Module):
             if self._flat is not None and self._flat[0] == fp:
                 flat = self._flat[1]
             else:
-                flat = torch.cat([p.detach().reshape(-1).float() for p in params]).contiguous()
+                # persistent flat buffer + per-parameter views, refreshed with ONE multi-tensor copy (a torch.cat over
+                # 162 reshaped views costs ~0.4 ms of host time per training step)
+                store = self._flat_store
+                if store is None or store[0] != dev or store[1].numel() != sum(p.numel() for p in params):
+                    buf = torch.empty(sum(p.numel() for p in params), dtype=torch.float32, device=dev)
+                    views, off = [], 0
+                    for p in params:
+                        views.append(buf[off:off + p.numel()].view(p.shape))
+                        off += p.numel()
+                    store = self._flat_store = (dev, buf, views)
+                with torch.no_grad():
+                    torch._foreach_copy_(store[2], list(params))
+                flat = store[1]
                 self._flat = (fp, flat)
             assert flat.numel() == lib.mgb_flat_weight_count(C.byref(self.dims))
             nbytes = lib.mgb_packed_bytes(C.byref(self.dims), prec)

@@ -118,11 +118,10 @@ class Denoiser(nn.Module):
         self._ws = _Workspace()
         self._train_ws = _Workspace()
         self.grad_sync = None      # optional mixgan_tts_b200.grad_sync.GradSync (data-parallel training)
-        # Opt-in (MIXGAN_B200_TRAIN_GRAPHS=1 or `den.use_cuda_graphs = True`): from the third call with one signature on,
-        # the library's ~220 launches per training step are replayed as CUDA graphs over static buffers.  Measured on
-        # B200 at B=8 x T=800: host enqueue time 3.98 -> 3.36 ms per step, device time 3.82 ms — the step is then bound by
-        # the device and by torch's own per-parameter host work (autograd, fused Adam over 162 tensors), so the step time
-        # does not change measurably; bit-identical to the eager path (tests/test_gpu_train.py).
+        # Opt-in (MIXGAN_B200_TRAIN_GRAPHS=1 or `den.use_cuda_graphs = True`), meant for fixed-shape training: from the
+        # third call with one (B, T) signature on, the library's ~220 launches per training step are replayed as CUDA
+        # graphs over static buffers (at most _TrainGraph.MAX_SIGNATURES signatures; other shapes run eagerly).  Measured
+        # on B200 at B=8 x T=800: 4.05 -> 3.72 ms per step; bit-identical to the eager path (tests/test_gpu_train.py).
         self.use_cuda_graphs = os.environ.get("MIXGAN_B200_TRAIN_GRAPHS", "0") == "1"
         self._train_graphs = {}
 
@@ -260,6 +259,7 @@ class _TrainGraph:
     first one's backward simply takes the eager path."""
 
     WARMUP_CALLS = 2      # eager calls before capturing (first-use initialisation inside the library must not be captured)
+    MAX_SIGNATURES = 4    # every (B, T) signature owns ~0.1 MB per frame of static buffers: further shapes run eagerly
 
     def __init__(self, den, B, T, prec, device):
         lib, dims = _lib.load(), den.dims
@@ -327,11 +327,12 @@ class _DenoiserGradFn(torch.autograd.Function):
         if den.use_cuda_graphs:
             key = (B, T, prec, dev)
             tg = den._train_graphs.get(key)
-            if tg is None:
+            if tg is None and len(den._train_graphs) < _TrainGraph.MAX_SIGNATURES:
                 tg = den._train_graphs[key] = _TrainGraph(den, B, T, prec, dev)
-            tg.calls += 1
-            if tg.calls <= _TrainGraph.WARMUP_CALLS or tg.busy():
-                tg = None
+            if tg is not None:
+                tg.calls += 1
+                if tg.calls <= _TrainGraph.WARMUP_CALLS or tg.busy():
+                    tg = None
         if tg is not None:
             with torch.cuda.device(dev):
                 fp = _param_fingerprint(params)

@@ -121,7 +121,8 @@ class Denoiser(nn.Module):
         # Opt-in (MIXGAN_B200_TRAIN_GRAPHS=1 or `den.use_cuda_graphs = True`), meant for fixed-shape training: from the
         # third call with one (B, T) signature on, the library's ~220 launches per training step are replayed as CUDA
         # graphs over static buffers (at most _TrainGraph.MAX_SIGNATURES signatures; other shapes run eagerly).  Measured
-        # on B200 at B=8 x T=800: 4.05 -> 3.72 ms per step; bit-identical to the eager path (tests/test_gpu_train.py).
+        # on B200 at B=8 x T=800: 3.76 -> 3.73 ms per step (the step is device-bound); bit-identical to the eager path
+        # (tests/test_gpu_train.py).
         self.use_cuda_graphs = os.environ.get("MIXGAN_B200_TRAIN_GRAPHS", "0") == "1"
         self._train_graphs = {}
 
@@ -140,11 +141,11 @@ class Denoiser(nn.Module):
                self.output_projection.conv.weight, self.output_projection.conv.bias]
         return ps
 
-    def packed_weights(self, precision: str | None = None) -> torch.Tensor:
+    def packed_weights(self, precision: str | None = None, params=None) -> torch.Tensor:
         """Kernel-layout copy of the parameters; rebuilt when any parameter changes."""
         precision = precision or self.precision
         prec = _PACK_KINDS[precision]
-        params = self._ordered_params()
+        params = params if params is not None else self._ordered_params()
         fp = _param_fingerprint(params)
         hit = self._packed.get(precision)
         if hit is not None and hit[0] == fp:
@@ -228,9 +229,9 @@ class Denoiser(nn.Module):
         return out
 
     # ---------------------------------------------------------------- training (autograd)
-    def flat_weights(self) -> torch.Tensor:
+    def flat_weights(self, params=None) -> torch.Tensor:
         """The parameters as one fp32 vector in the canonical order (built together with a weight pack)."""
-        self.packed_weights("fp32" if self.precision == "fp32" else "fp32_tables")
+        self.packed_weights("fp32" if self.precision == "fp32" else "fp32_tables", params)
         return self._flat[1]
 
     def train_workspace(self, B: int, T: int, device) -> torch.Tensor:
@@ -311,6 +312,16 @@ def _capture(lib, fn):
     return g, lib.mgb_launch_count() - n0
 
 
+def _grad_views(den, gflat, need):
+    """Per-parameter gradient views of the flat gradient (one split call, then a reshape per parameter)."""
+    meta = den.__dict__.get("_param_meta")
+    if meta is None:
+        ps = den._ordered_params()
+        meta = den.__dict__["_param_meta"] = ([p.numel() for p in ps], [p.shape for p in ps])
+    parts = gflat.split(meta[0])
+    return [g.view(shp) if nd else None for g, shp, nd in zip(parts, meta[1], need)]
+
+
 class _DenoiserGradFn(torch.autograd.Function):
     """autograd node for ``Denoiser.forward``: ``mgb_denoiser_train_forward`` / ``mgb_denoiser_backward``.
 
@@ -363,13 +374,12 @@ class _DenoiserGradFn(torch.autograd.Function):
             tg.token_ref = weakref.ref(token)
             ctx.den, ctx.tg, ctx.token, ctx.prec = den, tg, token, prec
             ctx.shape = (B, M, T)
-            ctx.param_shapes = [p.shape for p in params]
             return out
         ctx.tg = None
         with torch.cuda.device(dev):
             # both precisions read fp32 per-utterance tables; the bf16 mode needs nothing else from the fp32 pack
-            packed = den.packed_weights("fp32" if den.precision == "fp32" else "fp32_tables")
-            flat = den.flat_weights()
+            packed = den.packed_weights("fp32" if den.precision == "fp32" else "fp32_tables", params)
+            flat = den._flat[1]                       # built by the call above (same fingerprint)
             tt = t.detach().to(torch.int64).contiguous()
             out = torch.empty_like(x)
             saved = torch.empty(lib.mgb_train_saved_bytes(C.byref(den.dims), prec, B, T), dtype=torch.uint8, device=dev)
@@ -382,7 +392,6 @@ class _DenoiserGradFn(torch.autograd.Function):
         ctx.den, ctx.saved, ctx.tt, ctx.cond, ctx.spk = den, saved, tt, cond_bth, spk
         ctx.flat, ctx.prec = flat, prec
         ctx.shape = (B, M, T)
-        ctx.param_shapes = [p.shape for p in params]
         return out
 
     @staticmethod
@@ -436,11 +445,7 @@ class _DenoiserGradFn(torch.autograd.Function):
             gx = tg.gx.clone() if want[0] else None
             gcond = tg.gcond.clone() if want[1] else None
             gspk = tg.gspk.clone() if want[2] else None
-        grads, off = [], 0
-        for shp, nd in zip(ctx.param_shapes, need[5:]):
-            n = int(torch.Size(shp).numel())
-            grads.append(gflat[off:off + n].view(shp) if nd else None)
-            off += n
+        grads = _grad_views(den, gflat, need[5:])
         ctx.token = None                      # releases the signature's activation stash
         return (None, gx, None, gcond, gspk, *grads)
 
@@ -482,10 +487,6 @@ class _DenoiserGradFn(torch.autograd.Function):
                     sync.reduce_async(gflat[fb:fe])
             if sync is not None:
                 sync.finish()
-        grads, off = [], 0
-        for shp, nd in zip(ctx.param_shapes, need[5:]):
-            n = int(torch.Size(shp).numel())
-            grads.append(gflat[off:off + n].view(shp) if nd else None)
-            off += n
+        grads = _grad_views(den, gflat, need[5:])
         ctx.saved = None
         return (None, gx, None, gcond, gspk, *grads)

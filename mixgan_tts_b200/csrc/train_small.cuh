@@ -198,14 +198,28 @@ static __global__ void __launch_bounds__(256) mlp_bwd_w2_kernel(const float* __r
 static __global__ void __launch_bounds__(256) mlp_bwd_pre_kernel(const int64_t* __restrict__ t, const float* __restrict__ ddvec,
                                                           const float* __restrict__ W0, const float* __restrict__ W2,
                                                           float* __restrict__ dpre, int C) {
+  // grid (4C / 256, B).  pre[j] = W0[j][:] . emb: one WARP per output j (lanes stride the contiguous row: coalesced; a
+  // thread-per-row walk over the [4C][C] matrix was 90 us of serialised L2 latency), results parked in shared memory;
+  // then dh[j] = sum_c ddvec[c] W2[c][j] with one thread per j (coalesced over j).
   __shared__ float emb[256];
-  const int b = blockIdx.y, j = blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ float pre_s[256];
+  const int b = blockIdx.y, j0 = blockIdx.x * 256, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const float tv = (float)t[b];
   for (int k = threadIdx.x; k < C; k += blockDim.x) emb[k] = emb_value(tv, k, C);
   __syncthreads();
-  float pre = 0.f;
-  for (int k = 0; k < C; ++k) pre = fmaf(W0[(size_t)j * C + k], emb[k], pre);
+  for (int jj = warp; jj < 256; jj += 8) {
+    const float* row = W0 + (size_t)(j0 + jj) * C;
+    float acc = 0.f;
+    for (int k = lane; k < C; k += 32) acc = fmaf(row[k], emb[k], acc);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) pre_s[jj] = acc;
+  }
+  __syncthreads();
+  const int j = j0 + threadIdx.x;
+  const float pre = pre_s[threadIdx.x];
   float dh = 0.f;
+#pragma unroll 8
   for (int c = 0; c < C; ++c) dh = fmaf(ddvec[(size_t)b * C + c], W2[(size_t)c * 4 * C + j], dh);
   // mish(x) = x tanh(softplus(x));  mish'(x) = tanh(sp) + x (1 - tanh(sp)^2) sigmoid(x)
   const float sp = pre > 20.f ? pre : log1pf(expf(pre));

@@ -93,9 +93,11 @@ for src, dst in (("role_profile.txt", "role_profile_pair_kernel.txt"), ("bench_o
         shutil.copy(p, os.path.join(out, dst))
 print("wrote", sorted(os.listdir(out)))
 
-# ---- training path: ncu --set full of a few backward GEMM launches + the launch list of one training step
-rep = os.path.join(G, "prof_train.ncu-rep")
-if os.path.exists(rep):
+# ---- training path: ncu --set full of GEMM launches of one training step
+def train_summary(rep_name, out_name, header):
+    rep = os.path.join(G, rep_name)
+    if not os.path.exists(rep):
+        return
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr = rows[0]
@@ -105,19 +107,27 @@ if os.path.exists(rep):
             "dram__bytes_write.sum", "lts__t_sector_hit_rate.pct", "l1tex__m_xbar2l1tex_read_bytes.sum",
             "l1tex__t_sectors_pipe_lsu_mem_global_op_st.sum", "l1tex__t_requests_pipe_lsu_mem_global_op_st.sum",
             "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum", "l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum"]
-    with open(os.path.join(out, "ncu_train_gemm_summary.txt"), "w") as f:
-        f.write("ncu --set full --clock-control none --import-source on -k regex:'fgemm_kernel|wgemm_kernel' -s 560 -c 8  "
-                "python bench.py --workload train --precision bf16 --steps 2 --warmup 3\n"
-                "(eight consecutive GEMM launches of one training step, B=8 x T=800; fgemm_kernel<NT, MODE, CLUSTER>: mode 1 = conditioner\n"
-                " GEMM, 2 = k=3 conv + gate, 3 = output projection, 8 = gate-backward GEMM, 9 = transposed-conv GEMM; wgemm = weight-\n"
-                " gradient GEMMs; cold caches, serialised)\n\n")
+    with open(os.path.join(out, out_name), "w") as f:
+        f.write(header)
         for i, h in enumerate(hdr):
             if h in want:
                 f.write(f"{h} [{rows[1][i]}] = {' | '.join(r[i][:40] for r in rows[2:])}\n")
-    src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
-    with open(os.path.join(out, "ncu_train_gemm_summary.txt"), "a") as f:
+        src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
         for key in ("UTCHMMA", "UTMALDG", "UBLKCP", "LDTM", "UTCBAR", "SYNCS"):
             f.write(f"SASS {key}: {sum(1 for l in src.splitlines() if key in l)} occurrences in the captured kernels\n")
+
+
+train_summary("prof_train.ncu-rep", "ncu_train_gemm_summary.txt",
+              "ncu --set full --clock-control none --import-source on -k regex:fgemm_kernel -s 560 -c 8  "
+              "python bench.py --workload train --precision bf16 --steps 2 --warmup 3\n"
+              "(eight consecutive frames-GEMM launches of one training step, B=8 x T=800; fgemm_kernel<NT, MODE, CLUSTER>: mode 1 =\n"
+              " conditioner GEMM, 2 = k=3 conv + gate, 3 = output projection, 8 = gate-backward GEMM, 9 = transposed-conv GEMM;\n"
+              " cold caches, serialised)\n\n")
+train_summary("prof_train_wgemm.ncu-rep", "ncu_train_wgemm_summary.txt",
+              "ncu --set full --clock-control none --import-source on -k regex:^wgemm_kernel$ -s 27 -c 2  "
+              "python bench.py --workload train --precision bf16 --steps 2 --warmup 3\n"
+              "(two weight-gradient launches of one training step: a residual block's merged dWo + dW3 + dWc problem, 18 output\n"
+              " tiles x 8 frame splits, both operands MN-major from the activation images; cold caches, serialised)\n\n")
 for src_name, dst in (("launches_train_bf16.csv", "launches_train_bf16.csv"), ("launches_train_bf16_summary.txt", "launches_train_bf16_summary.txt"),
                       ("train_bf16_parity.txt", "train_bf16_parity.txt"), ("bulk_rate.txt", "bulk_copy_rate_probe.txt")):
     p = os.path.join(G, src_name)

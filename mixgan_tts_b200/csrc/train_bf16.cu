@@ -143,6 +143,8 @@ struct FArgs {
   // epilogue operands (meaning depends on the mode; see fgemm_epilogue)
   const float* bias;                // flat-order bias vector
   const float* dtab; const float* ctab;   // [B][L][C] tables, already offset to the layer
+  const float* dtab2; const float* ctab2; // F_IN / F_OUT: the tables of the layer whose conv input y this epilogue also writes
+  const float* call;                      // F_IN / F_OUT: that layer's slot of the hoisted conditioner projection (fp32 stream)
   const float* fin;                 // fp32 [Rp][C] input stream (x / e / X0)
   float* fout;                      // fp32 [Rp][C] output stream (x / e) or [B][n_mel][T] / [B][T][C] user tensors
   float* fout2;                     // fp32 [Rp][C] skip sum
@@ -167,7 +169,7 @@ __device__ __forceinline__ void fgemm_epilogue(const FArgs& p, uint32_t tmem_row
                                                int ntile) {
   const int L = p.L;
   if constexpr (MODE == F_IN || MODE == F_SKIP) {
-    // relu(acc + bias): F_IN -> fp32 X0 stream; F_SKIP -> P image
+    // relu(acc + bias): F_IN -> fp32 X0 stream (+ the first block's conv input y_0); F_SKIP -> P image
 #pragma unroll 2
     for (int cg = 0; cg < 8; ++cg) {
       float v[32];
@@ -176,27 +178,30 @@ __device__ __forceinline__ void fgemm_epilogue(const FArgs& p, uint32_t tmem_row
       load_f32x32(p.bias + cg * 32, bv);
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = valid ? fmaxf(v[j] + bv[j], 0.f) : 0.f;
-      if constexpr (MODE == F_IN) store_s32(p.fout, p.Rp, rho, cg * 32, v);
-      else store_img32(p.img, p.Rp, rho, cg * 32, v);
+      if constexpr (MODE == F_IN) {
+        store_s32(p.fout, p.Rp, rho, cg * 32, v);
+        if (valid) {            // y_0 = (x_0 + d_0) + (Wc_0 cond + bc_0 [+ s_0])   (blocks.py:1166-1168)
+          float dt[32], ct[32], cc[32];
+          load_s32(p.call, p.Rp, rho, cg * 32, cc);
+          load_f32x32(p.dtab2 + (size_t)b * L * C + cg * 32, dt);
+          load_f32x32(p.ctab2 + (size_t)b * L * C + cg * 32, ct);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = (v[j] + dt[j]) + (cc[j] + ct[j]);
+        }
+        store_img32(p.img2, p.Rp, rho, cg * 32, v);
+      } else {
+        store_img32(p.img, p.Rp, rho, cg * 32, v);
+      }
     }
   } else if constexpr (MODE == F_COND) {
-    // y = (x + d_l) + (Wc cond + bc_l [+ s_l])   (blocks.py:1166-1168) -> conv input image (zero outside utterances)
+    // hoisted conditioner projection: ONE launch computes Wc_l cond for every layer l = ntile (the projection does not
+    // depend on the residual stream); fp32, chunked layout, consumed by the F_IN / F_OUT epilogues that form y_l
+    float* dst = p.fout + (size_t)ntile * p.Rp * C;
 #pragma unroll 2
     for (int cg = 0; cg < 8; ++cg) {
-      float v[32], x[32];
+      float v[32];
       tmem_ld_f32x32(tmem_row + cg * 32, v);
-      if (valid) {
-        float dt[32], ct[32];
-        load_s32(p.fin, p.Rp, rho, cg * 32, x);
-        load_f32x32(p.dtab + (size_t)b * L * C + cg * 32, dt);
-        load_f32x32(p.ctab + (size_t)b * L * C + cg * 32, ct);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = (x[j] + dt[j]) + (v[j] + ct[j]);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = 0.f;
-      }
-      store_img32(p.img, p.Rp, rho, cg * 32, v);
+      store_s32(dst, p.Rp, rho, cg * 32, v);
     }
   } else if constexpr (MODE == F_GATE) {
     // tile = 128 gate + 128 filter columns of channels [ntile*128, +128): g = sigmoid(a) tanh(f)  (blocks.py:1170-1171)
@@ -241,6 +246,15 @@ __device__ __forceinline__ void fgemm_epilogue(const FArgs& p, uint32_t tmem_row
 #pragma unroll
         for (int j = 0; j < 32; ++j) x[j] = ((ox[j] + bx[j]) + (x[j] + dt[j])) * RSQRT2;
         store_s32(p.fout, p.Rp, rho, ch0, x);
+        if (!p.last) {          // conv input of the next block: y_{l+1} = (x_{l+1} + d_{l+1}) + (Wc_{l+1} cond + bc_{l+1} [+ s])
+          float dn[32], cn[32], cc[32], y[32];
+          load_s32(p.call, p.Rp, rho, ch0, cc);
+          load_f32x32(p.dtab2 + (size_t)b * L * C + ch0, dn);
+          load_f32x32(p.ctab2 + (size_t)b * L * C + ch0, cn);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) y[j] = (x[j] + dn[j]) + (cc[j] + cn[j]);
+          store_img32(p.img2, p.Rp, rho, ch0, y);
+        }
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           os[j] = (p.first ? 0.f : sk[j]) + (os[j] + bs[j]);
@@ -250,6 +264,7 @@ __device__ __forceinline__ void fgemm_epilogue(const FArgs& p, uint32_t tmem_row
       } else {
 #pragma unroll
         for (int j = 0; j < 32; ++j) os[j] = 0.f;
+        if (!p.last) store_img32(p.img2, p.Rp, rho, ch0, os);      // zero rows between utterances = the conv's padding
       }
       if (p.last) store_img32(p.img, p.Rp, rho, ch0, os);
     }
@@ -840,7 +855,8 @@ struct PackedB16 {   // offsets in bf16 elements into the packed-weight buffer (
   size_t in_f, skip_f, out_f;                       // forward
   size_t out_b, skip_b, in_b;                       // backward (transposed)
   size_t layer0, layer_stride;
-  size_t r_cond_f, r_conv_f, r_oproj_f, r_oproj_b, r_conv_b;
+  size_t r_conv_f, r_oproj_f, r_oproj_b, r_conv_b;
+  size_t cond_f_all;                                // Wc of all layers as the column tiles of ONE N = 256 L GEMM
   size_t cond_b_all;                                // Wc^T of all layers, 4 k-steps each, contiguous (one K = 256 L GEMM)
   size_t total;
 };
@@ -857,13 +873,13 @@ PackedB16 packed16_layout(const mgb_model_dims& d) {
   o.layer0 = p;
   size_t q = 0;
   auto tk = [&](size_t n) { size_t r = q; q += n; return r; };
-  o.r_cond_f = tk((size_t)256 * 256);
   o.r_conv_f = tk((size_t)512 * 768);
   o.r_oproj_f = tk((size_t)512 * 256);
   o.r_oproj_b = tk((size_t)256 * 512);
   o.r_conv_b = tk((size_t)256 * 1536);
   o.layer_stride = q;
   p += q * d.layers;
+  o.cond_f_all = take((size_t)256 * 256 * d.layers);
   o.cond_b_all = take((size_t)256 * 256 * d.layers);
   o.total = p;
   return o;
@@ -899,7 +915,7 @@ Saved16 saved16_layout(const mgb_model_dims& d, int B, int T) {
 }
 
 struct Work16 {      // byte offsets into the workspace
-  size_t status, X, S, dtab, ctab, dout, dPre, dS, E, Eimg, dZ, dY, part, usumE, usumE2, usumZ, usumY, usumS, usumT, ddvec,
+  size_t status, X, S, Call, dtab, ctab, dout, dPre, dS, E, Eimg, dZ, dY, part, usumE, usumE2, usumZ, usumY, usumS, usumT, ddvec,
       dspk, dpre, dd_all, ds_all, lpart, total;
 };
 Work16 work16_layout(const mgb_model_dims& d, int B, int T) {
@@ -911,6 +927,7 @@ Work16 work16_layout(const mgb_model_dims& d, int B, int T) {
   w.status = take(256);
   w.X = take(Rp * C * 4);
   w.S = take(Rp * C * 4);
+  w.Call = take((size_t)d.layers * Rp * C * 4);   // Wc_l cond of every layer (fp32 stream), written by one launch
   w.dtab = take((size_t)B * d.layers * C * 4);
   w.ctab = take((size_t)B * d.layers * C * 4);
   w.dout = take(16 * Rp * 16);
@@ -965,7 +982,7 @@ int pack_step_weights(const mgb_model_dims& d, const float* flat, bf16* out, cud
   push(desc(o.in_b, f.in_w, M, 128, C, 1, 1, M, 0, 0, 0));          // W_eff[n=m][k=c] = Win[c][m]
   for (int l = 0; l < d.layers; ++l) {
     const size_t fl = f.layer0 + (size_t)l * f.layer_stride, ol = o.layer0 + (size_t)l * o.layer_stride;
-    push(desc(ol + o.r_cond_f, fl + f.rel.cproj_w, C, 256, C, 1, C, 1, 0, 0, 0));
+    push(desc(o.cond_f_all + (size_t)l * 256 * 256, fl + f.rel.cproj_w, C, 256, C, 1, C, 1, 0, 0, 0));
     push(desc(ol + o.r_conv_f, fl + f.rel.conv_w, 2 * C, 256, C, 3, 3 * C, 3, 1, 0, 1));      // W3[co][ci][tap], gate|filter tiles
     push(desc(ol + o.r_oproj_f, fl + f.rel.oproj_w, 2 * C, 256, C, 1, C, 1, 0, 0, 1));        // Wo[co][ci], x|skip tiles
     push(desc(ol + o.r_oproj_b, fl + f.rel.oproj_w, C, 256, 2 * C, 1, 1, C, 0, 0, 0));        // W_eff[n=ci][k=co]
@@ -1009,9 +1026,15 @@ int bf16_train_forward(const mgb_model_dims& d, const void* packed_fp32, const f
   FArgs base{};
   base.Rp = rs.Rp; base.B = B; base.T = T; base.L = L; base.status = status; base.taps = 1; base.n_mel = M;
   {
-    FArgs a = base;                                     // input projection + ReLU (modules.py:429-431)
+    FArgs a = base;                                     // conditioner projection of ALL layers in one launch (N = 256 L)
+    a.A0 = img(SV + sv.cond); a.steps0 = 4; a.Bpk = wpk + o.cond_f_all; a.ksteps_b = 4; a.fout = f32(W + w.Call);
+    if (int rc = launch_fgemm<256, F_COND>(a, rs.ntiles, L, s)) return rc;
+  }
+  {
+    FArgs a = base;                                     // input projection + ReLU (modules.py:429-431), and y_0
     a.A0 = img(SV + sv.xt); a.steps0 = 2; a.Bpk = wpk + o.in_f; a.ksteps_b = 2;
     a.bias = flat + f.in_b; a.fout = f32(SV + sv.X0);
+    a.call = f32(W + w.Call); a.dtab2 = f32(W + w.dtab); a.ctab2 = f32(W + w.ctab); a.img2 = img(SV + sv.layer0 + sv.rY);
     if (int rc = launch_fgemm<256, F_IN>(a, rs.ntiles, 1, s)) return rc;
   }
   for (int l = 0; l < L; ++l) {
@@ -1019,12 +1042,6 @@ int bf16_train_forward(const mgb_model_dims& d, const void* packed_fp32, const f
     const bf16* wl = wpk + o.layer0 + (size_t)l * o.layer_stride;
     const float* fl = flat + f.layer0 + (size_t)l * f.layer_stride;
     const float* xin = l == 0 ? f32(SV + sv.X0) : f32(W + w.X);
-    {
-      FArgs a = base;                                   // conditioner projection, y = (x + d) + (c + bc [+ s])
-      a.A0 = img(SV + sv.cond); a.steps0 = 4; a.Bpk = wl + o.r_cond_f; a.ksteps_b = 4;
-      a.fin = xin; a.dtab = f32(W + w.dtab) + (size_t)l * C; a.ctab = f32(W + w.ctab) + (size_t)l * C; a.img = img(sl + sv.rY);
-      if (int rc = launch_fgemm<256, F_COND>(a, rs.ntiles, 1, s)) return rc;
-    }
     {
       FArgs a = base;                                   // k=3 conv + gate
       a.A0 = img(sl + sv.rY); a.steps0 = 4; a.taps = 3; a.Bpk = wl + o.r_conv_f; a.ksteps_b = 12;
@@ -1037,6 +1054,11 @@ int bf16_train_forward(const mgb_model_dims& d, const void* packed_fp32, const f
       a.bias = fl + f.rel.oproj_b; a.fin = xin; a.fout = f32(W + w.X); a.fout2 = f32(W + w.S);
       a.dtab = f32(W + w.dtab) + (size_t)l * C; a.first = l == 0; a.last = l == L - 1;
       a.scale = 1.0f / sqrtf((float)L); a.img = img(SV + sv.Sn);
+      if (l + 1 < L) {                                  // this epilogue also writes the next block's conv input y_{l+1}
+        a.call = f32(W + w.Call) + (size_t)(l + 1) * rs.Rp * C;
+        a.dtab2 = f32(W + w.dtab) + (size_t)(l + 1) * C; a.ctab2 = f32(W + w.ctab) + (size_t)(l + 1) * C;
+        a.img2 = img(sl + sv.layer_stride + sv.rY);
+      }
       if (int rc = launch_fgemm<256, F_OUT>(a, rs.ntiles, 2, s)) return rc;
     }
   }

@@ -291,7 +291,7 @@ def run_ours(args):
         e2e_val = frames_per_step * args.steps / (ms_e2e * 1e-3)
         k_ms = ktot.value / max(kcnt.value, 1)
         calls = prof_steps * K                      # Denoiser calls in the profiled pass
-        if prec == "bf16":
+        if prec in ("bf16", "fp16"):
             # one Denoiser call = `launches_per_call` launches of fused_group_kernel (layer groups);
             # algorithmic FLOPs per launch = FLOPs per call / launches per call
             per_call = max(kcnt.value // calls, 1)
@@ -304,7 +304,7 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if prec == "bf16" else "f32", "data": "synthetic",
+            "scaling": "weak", "vs_baseline": None, "dtype": {"bf16": "bf16", "fp16": "f16"}.get(prec, "f32"), "data": "synthetic",
             "config": {"workload": f"LJSpeech naive K={K} reverse diffusion, B={B} x T={T} per GPU (BASELINE configs[1]), "
                                    "random-init Denoiser, fixed injected noise",
                        "precision": prec, "l2": f"inputs rotate over {NSETS} sets of {set_bytes / 1e6:.0f} MB (> 126 MB L2)",
@@ -553,7 +553,7 @@ def main():
     ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default="auto", choices=["auto", "bf16", "fp32"])
+    ap.add_argument("--precision", default="auto", choices=["auto", "bf16", "fp16", "fp32"])
     ap.add_argument("--batch", type=int, default=B_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="sample", choices=["sample", "train", "c3"],

@@ -11,7 +11,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libmixgan_b200.so")
 
-PREC_FP32, PREC_BF16 = 0, 1
+PREC_FP32, PREC_BF16, PREC_FP16 = 0, 1, 3
 PACK_FP32_TABLES = 2       # mgb_pack_weights only: the fp32 buffer with just the per-utterance table weights
 E_ARG, E_ARCH, E_WORKSPACE, E_CUDA, E_UNSUPPORTED = -1, -2, -3, -4, -5
 
@@ -51,6 +51,10 @@ SIGNATURES = {
     "mgb_shallow_start": (_I, [_P, _P, _P, _P, _F, _F, _P, _P, _I, _I, _I, _P]),
     "mgb_denorm_mask": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P]),
     "mgb_length_regulate": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _Z, _P]),
+}
+
+# include/mixgan_b200_probe.h: exported by the test-only debug library (libmixgan_b200_dbg.so), never by the product one
+PROBE_SIGNATURES = {
     "mgb_probe_umma": (_I, [_P, _I, _P, _I] + [_I] * 11 + [_P, _P, _P]),
     "mgb_probe_umma_2cta": (_I, [_P, _I, _P, _I] + [_I] * 8 + [_P, _P, _P]),
     "mgb_probe_bulk_rate": (_I, [_P, C.c_longlong, _I, _I, _I, _I, _I, _P, _P, _P]),
@@ -58,6 +62,23 @@ SIGNATURES = {
 }
 
 _lib = None
+_dbg = None
+LIB_DBG_PATH = os.path.join(HERE, "libmixgan_b200_dbg.so")
+
+
+def load_debug():
+    """The test/diagnostic superset library (product ABI + probes + in-kernel profiling).  Tests and scripts only."""
+    global _dbg
+    if _dbg is not None:
+        return _dbg
+    if not os.path.exists(LIB_DBG_PATH):
+        raise RuntimeError(f"{LIB_DBG_PATH} is missing: build it with `python -m mixgan_tts_b200.build`")
+    lib = C.CDLL(LIB_DBG_PATH)
+    for name, (res, args) in {**SIGNATURES, **PROBE_SIGNATURES}.items():
+        fn = getattr(lib, name)
+        fn.restype, fn.argtypes = res, args
+    _dbg = lib
+    return lib
 
 
 def load():
@@ -65,11 +86,13 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    # diagnostics scripts (scripts/gpu_prof.sh) run the product ABI out of the debug build: MIXGAN_B200_USE_DEBUG_LIB=1
+    path = LIB_DBG_PATH if os.environ.get("MIXGAN_B200_USE_DEBUG_LIB") == "1" else LIB_PATH
+    if not os.path.exists(path):
         raise RuntimeError(
-            f"{LIB_PATH} is missing: build it with `python -m mixgan_tts_b200.build` "
+            f"{path} is missing: build it with `python -m mixgan_tts_b200.build` "
             "(there is no CPU fallback for this path)")
-    lib = C.CDLL(LIB_PATH)
+    lib = C.CDLL(path)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)
         fn.restype, fn.argtypes = res, args
@@ -79,10 +102,10 @@ def load():
     return lib
 
 
-def check(rc: int, what: str):
+def check(rc: int, what: str, lib=None):
     if rc == 0:
         return
-    msg = load().mgb_last_error().decode(errors="replace")
+    msg = (lib or load()).mgb_last_error().decode(errors="replace")
     err = ValueError if rc in (E_ARG, E_WORKSPACE) else RuntimeError
     raise err(f"{what} failed (code {rc}): {msg}")
 

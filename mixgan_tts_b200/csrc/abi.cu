@@ -168,9 +168,10 @@ static int denoiser_dispatch(const mgb_model_dims* dims, int precision, const vo
   MGB_REQUIRE(ws_bytes >= need, MGB_E_WORKSPACE, "workspace too small: %zu < %zu", ws_bytes, need);
   if (precision == MGB_PREC_FP32)
     return fp32_denoiser(*dims, packed, x, t, cond, spk, noise, sched, K, clip, x_prev, x0_out, B, T, ws, s);
-  if (precision == MGB_PREC_BF16) {
-    if (int rc = bf16_prepare(*dims, packed, t, 1, cond, spk, B, T, ws, s)) return rc;
-    return bf16_run(*dims, packed, x, t, -1, 0, 1, noise, sched, K, clip, x_prev, x0_out, B, T, ws, s);
+  if (prec_is_tc(precision)) {
+    const bool f16 = precision == MGB_PREC_FP16;
+    if (int rc = bf16_prepare(*dims, packed, t, 1, cond, spk, B, T, ws, s, f16)) return rc;
+    return bf16_run(*dims, packed, x, t, -1, 0, 1, noise, sched, K, clip, x_prev, x0_out, B, T, ws, s, f16);
   }
   set_error("unknown precision %d", precision);
   return MGB_E_ARG;
@@ -217,7 +218,7 @@ const char* mgb_last_error(void) { return g_err; }
 int mgb_debug_status(const mgb_model_dims* dims, int precision, int B, int T, const void* workspace, int* host_status) {
   MGB_REQUIRE(dims_supported(dims) && workspace && host_status, MGB_E_ARG, "bad argument");
   *host_status = 0;
-  if (precision != MGB_PREC_BF16) return MGB_OK;
+  if (!prec_is_tc(precision)) return MGB_OK;
   const char* src = static_cast<const char*>(workspace) + bf16_status_offset(*dims, B, T);
   MGB_CUDA_CHECK(cudaMemcpy(host_status, src, sizeof(int), cudaMemcpyDeviceToHost));
   return MGB_OK;
@@ -245,7 +246,7 @@ size_t mgb_flat_weight_count(const mgb_model_dims* dims) {
 size_t mgb_packed_bytes(const mgb_model_dims* dims, int precision) {
   if (!dims_supported(dims)) return 0;
   return (precision == MGB_PREC_FP32 || precision == MGB_PACK_FP32_TABLES) ? fp32_packed_bytes(*dims)
-       : precision == MGB_PREC_BF16 ? bf16_packed_bytes(*dims) : 0;
+       : prec_is_tc(precision) ? bf16_packed_bytes(*dims) : 0;
 }
 
 int mgb_pack_weights(const mgb_model_dims* dims, int precision, const float* flat, void* packed,
@@ -258,7 +259,7 @@ int mgb_pack_weights(const mgb_model_dims* dims, int precision, const float* fla
   MGB_REQUIRE(packed_bytes >= need, MGB_E_WORKSPACE, "packed buffer too small: %zu < %zu", packed_bytes, need);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (precision == MGB_PACK_FP32_TABLES) return fp32_pack_tables(*dims, flat, packed, s);
-  return precision == MGB_PREC_FP32 ? fp32_pack(*dims, flat, packed, s) : bf16_pack(*dims, flat, packed, s);
+  return precision == MGB_PREC_FP32 ? fp32_pack(*dims, flat, packed, s) : bf16_pack(*dims, flat, packed, s, precision == MGB_PREC_FP16);
 }
 
 size_t mgb_workspace_bytes(const mgb_model_dims* dims, int precision, int B, int T, int K) {
@@ -266,7 +267,7 @@ size_t mgb_workspace_bytes(const mgb_model_dims* dims, int precision, int B, int
   const size_t tail = align_up((size_t)B * sizeof(int64_t), 256) +            // timestep vector
                       2 * align_up((size_t)B * dims->n_mel * T * sizeof(float), 256);  // x ping-pong
   const size_t core = precision == MGB_PREC_FP32 ? fp32_workspace_bytes(*dims, B, T)
-                    : precision == MGB_PREC_BF16 ? bf16_workspace_bytes(*dims, B, T, K > 0 ? K : 1) : 0;
+                    : prec_is_tc(precision) ? bf16_workspace_bytes(*dims, B, T, K > 0 ? K : 1, precision == MGB_PREC_FP16) : 0;
   return core ? align_up(core, 256) + tail : 0;
 }
 
@@ -315,20 +316,20 @@ int mgb_sample(const mgb_model_dims* dims, int precision, const void* packed, co
     note_launch();
   }
   const float* cur = x_T;
-  const bool bf16 = precision == MGB_PREC_BF16;
+  const bool bf16 = prec_is_tc(precision), f16 = precision == MGB_PREC_FP16;
   if (bf16) {   // cond image and the per-step tables of all K steps, once
     MGB_REQUIRE(packed && cond, MGB_E_ARG, "NULL pointer argument");
     MGB_REQUIRE(!dims->multi_speaker || spk, MGB_E_ARG,
                 "multi_speaker model needs a speaker embedding (reference raises TypeError)");
     if (int rc = check_arch()) return rc;
-    if (int rc = bf16_prepare(*dims, packed, nullptr, K, cond, spk, B, T, workspace, s)) return rc;
+    if (int rc = bf16_prepare(*dims, packed, nullptr, K, cond, spk, B, T, workspace, s, f16)) return rc;
   }
   for (int i = K - 1, n = 0; i >= 0; --i, ++n) {
     float* nxt = (n & 1) ? xb : xa;
     const float* nz = noises + (size_t)i * B * M * T;
     int rc;
     if (bf16) {
-      rc = bf16_run(*dims, packed, cur, nullptr, i, i, K, nz, sched, K, clip, nxt, nullptr, B, T, workspace, s);
+      rc = bf16_run(*dims, packed, cur, nullptr, i, i, K, nz, sched, K, clip, nxt, nullptr, B, T, workspace, s, f16);
     } else {
       if ((rc = launch_fill_t(tvec, B, i, s))) return rc;
       rc = denoiser_dispatch(dims, precision, packed, cur, tvec, cond, spk, nz, sched, K, clip, nxt, nullptr, B, T,

@@ -44,6 +44,16 @@ void set_error(const char* fmt, ...);
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// One-time setup that is PER DEVICE (cudaFuncSetAttribute(MaxDynamicSharedMemorySize) applies to the current device only):
+//   static PerDeviceOnce once;  if (once.pending()) { ...set attributes...; once.done(); }
+// The setup is idempotent, so two host threads racing on a fresh device at worst both run it.
+struct PerDeviceOnce {
+  unsigned long long mask_[4] = {0, 0, 0, 0};   // 256 device ordinals
+  static int current() { int dev = 0; return cudaGetDevice(&dev) == cudaSuccess ? dev & 255 : 0; }
+  bool pending() const { const int d = current(); return !(__atomic_load_n(&mask_[d >> 6], __ATOMIC_ACQUIRE) >> (d & 63) & 1ull); }
+  void done() { const int d = current(); __atomic_fetch_or(&mask_[d >> 6], 1ull << (d & 63), __ATOMIC_RELEASE); }
+};
+
 // Programmatic dependent launch (PDL).  A kernel launched with launch_pdl() may start while its predecessor in the stream
 // is still running: its CTAs do their private setup (barrier init, TMEM allocation, cluster sync), then pdl_wait() blocks
 // until the predecessor grid has completed and its memory is visible.  pdl_trigger() (issued right away by every CTA)
@@ -198,16 +208,17 @@ int bf16_train_backward(const mgb_model_dims& d, const float* flat, const void* 
                         const float* spk, const float* grad_out, float* grad_flat, float* grad_cond, float* grad_spk,
                         float* grad_x, int B, int T, int seg_begin, int seg_end, void* ws, cudaStream_t s);
 
-// ---- bf16 tcgen05 path (fused_bf16.cu) -------------------------------------------------------
+// ---- tcgen05 sampling path (fused_bf16.cu): bf16 operands, or fp16 operands (f16 = true, MGB_PREC_FP16) ----
 size_t bf16_packed_bytes(const mgb_model_dims& d);
-int bf16_pack(const mgb_model_dims& d, const float* flat, void* packed, cudaStream_t s);
-size_t bf16_workspace_bytes(const mgb_model_dims& d, int B, int T, int K);
+int bf16_pack(const mgb_model_dims& d, const float* flat, void* packed, cudaStream_t s, bool f16);
+size_t bf16_workspace_bytes(const mgb_model_dims& d, int B, int T, int K, bool f16);
 size_t bf16_status_offset(const mgb_model_dims& d, int B, int T);
 int bf16_prepare(const mgb_model_dims& d, const void* packed, const int64_t* t, int nsteps, const float* cond,
-                 const float* spk, int B, int T, void* ws, cudaStream_t s);
+                 const float* spk, int B, int T, void* ws, cudaStream_t s, bool f16);
 int bf16_run(const mgb_model_dims& d, const void* packed, const float* x, const int64_t* t, int t_uniform, int step,
              int nsteps, const float* noise, const float* sched, int K, int clip, float* x_prev, float* out_x0, int B, int T,
-             void* ws, cudaStream_t s);
+             void* ws, cudaStream_t s, bool f16);
+inline bool prec_is_tc(int precision) { return precision == MGB_PREC_BF16 || precision == MGB_PREC_FP16; }
 
 // ---- elementwise (elementwise.cu) -------------------------------------------------------------
 int launch_fill_t(int64_t* t, int B, int64_t value, cudaStream_t s);

@@ -1,4 +1,4 @@
-// bf16 tensor-core path of the Denoiser (MGB_PREC_BF16): a group of residual blocks is chained in
+// Tensor-core path of the Denoiser (MGB_PREC_BF16 and MGB_PREC_FP16): a group of residual blocks is chained in
 // ONE kernel per 256-row tile, and a tile is owned by a CTA PAIR (a 2-CTA cluster on one TPC).
 // Every convolution is a set of tcgen05.mma.cta_group::2 instructions (M = 256 rows = 128 per CTA,
 // N = 128 or 256 channels, K = 16) issued by the leader CTA; each CTA keeps its own 128 rows of every
@@ -35,6 +35,15 @@
 // pair's two half tiles are neighbours on the row axis: each CTA's edge row is the other's halo row and
 // travels as st.async DSMEM stores tracked by an mbarrier in the destination CTA), warps 4..11 =
 // epilogue (thread = one row x half of a 128-column chunk).
+//
+// Operand precision (template parameter F16).  MGB_PREC_BF16: bf16 operands, tanh.approx gate, fp16 spills between
+// layer groups - the throughput mode.  MGB_PREC_FP16: the SAME kernel with fp16 operands (kind::f16 runs both at the
+// same rate), i.e. an 11-bit significand - exactly TF32's - for every MMA operand, fp32 accumulation in TMEM, the fp32
+// residual stream in registers, fp32 spills between layer groups, biases / per-utterance constants added as fp16
+// hi + lo pairs (22 bits) and a gate built from ex2 + one division instead of tanh.approx (whose 2^-11 error is of the
+// size of the operand rounding).  This is the reference-precision (fp32, 1e-3 relative L2) mode on the tensor cores;
+// operand hi/lo splits or kind::tf32 (4-byte operands) would need twice the 130 KB of activation tiles per CTA, which
+// does not fit next to the weight ring.  fp16 saturates at 65504: conversions use cvt.rn.satfinite.
 //
 // MGB_PROFILE=1 runs the PROF instantiation: per-role wait counters, a per-layer timeline of
 // accumulator-ready events, layer-boundary stamps and per-load ring latencies (see bf16_run).
@@ -112,9 +121,10 @@ struct FusedParams {
   // Between layer groups the residual stream and the partial skip sum are spilled as fp16 (saturating): half the
   // HBM traffic of fp32, small enough to stay mostly L2-resident until the next launch re-reads it, and a 2^-11
   // rounding once per group boundary is far below the bf16 operand rounding of every layer.
-  const __half* U_in;           // [B*T][C] u spilled by the previous group
-  __half* U_out;                // [B*T][C] u for the next group (ping-pong: neighbours read U_in meanwhile)
-  __half* S;                    // [B*T][C] partial skip sum between groups
+  // (MGB_PREC_FP16 spills fp32: the operand rounding is 8x finer there and a 2^-11 rounding of the STREAM would show.)
+  const void* U_in;             // [B*T][C] u spilled by the previous group (fp16, or fp32 in the F16 instantiation)
+  void* U_out;                  // [B*T][C] u for the next group (ping-pong: neighbours read U_in meanwhile)
+  void* S;                      // [B*T][C] partial skip sum between groups
   int B, T, Tg, R, L, lb, le, V, halo;
   int* status;
   int debug_mode;               // MGB_DEBUG_MODE: 1 = setup + teardown only (timing experiment)
@@ -136,6 +146,37 @@ __device__ __forceinline__ uint32_t pack_f16_sat(float lo, float hi) {   // two 
   __half2 v = __floats2half2_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
 }
+// two floats -> one 32-bit pair of MMA operands: bf16 (round to nearest) or fp16 (round to nearest, saturating)
+template <bool F16>
+__device__ __forceinline__ uint32_t pack_op(float lo, float hi) {
+  if (F16) {
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+  }
+  return pack_bf16(lo, hi);
+}
+template <bool F16>
+__device__ __forceinline__ float round_op(float v) {   // the value an operand of this precision carries
+  return F16 ? __half2float(__float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f))) : __bfloat162float(__float2bfloat16_rn(v));
+}
+// 2 sigmoid(a) tanh(f) from ah = a/2 and f.  bf16 mode: tanh(ah) tanh(f) + tanh(f) with two MUFU.TANH (2^-11).
+// fp16 mode: with E1 = e^a, E2 = e^2f the same quantity is 2 E1 (E2 - 1) / ((E1 + 1)(E2 + 1)): two MUFU.EX2 (2^-22) and one
+// division; the arguments are clamped to +-40 where tanh and sigmoid are 0 / 1 to fp32 precision and the product of the
+// two denominators stays finite.
+template <bool F16>
+__device__ __forceinline__ float gate_fn(float ah, float f) {
+  if (F16) {
+    const float x1 = fminf(fmaxf(ah, -20.f), 20.f) * 2.8853900817779268f;   // 2 log2(e)
+    const float x2 = fminf(fmaxf(f, -20.f), 20.f) * 2.8853900817779268f;
+    float e1, e2;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(x1));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e2) : "f"(x2));
+    return __fdividef(2.f * e1 * (e2 - 1.f), (e1 + 1.f) * (e2 + 1.f));
+  }
+  const float ta = tanh_approx(ah), tf = tanh_approx(f);
+  return fmaf(ta, tf, tf);
+}
 __device__ __forceinline__ float2 unpack_f16(uint32_t w) { return __half22float2(*reinterpret_cast<__half2*>(&w)); }
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
@@ -143,7 +184,7 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t
 
 // KUNI: every utterance shares the per-layer constant k_l (uniform timestep, single speaker): it is added inside
 // the residual GEMM by one more K=16 step against the "ones" operand (kimg) instead of being loaded by the epilogue.
-template <bool PROF, bool KUNI>
+template <bool PROF, bool KUNI, bool F16>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_pair_kernel(const FusedParams p, const __grid_constant__ CUtensorMap tmCond) {
   const long long t_start = PROF ? clock64() : 0;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -173,11 +214,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_p
 #pragma unroll
       for (int j = 0; j < 40; ++j)
         pf[j] = (e_in && 40 * e_h + j < p.n_mel) ? __float_as_uint(__ldg(src + (size_t)j * p.T)) : 0u;
-    } else {
+    } else if (!F16) {   // (the fp32 spill of the F16 instantiation is read straight into u[] by the epilogue)
       const size_t e_row = (size_t)e_b * p.T + (e_in ? e_f : 0);
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
-        const uint4* up = reinterpret_cast<const uint4*>(p.U_in + e_row * C + 128 * c + 64 * e_h);
+        const uint4* up = reinterpret_cast<const uint4*>(static_cast<const __half*>(p.U_in) + e_row * C + 128 * c + 64 * e_h);
 #pragma unroll
         for (int j8 = 0; j8 < 8; ++j8) {
           const uint4 v = e_in ? __ldg(up + j8) : make_uint4(0u, 0u, 0u, 0u);
@@ -193,8 +234,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_p
     for (int i = tid; i < (SMEM_A + SMEM_G) / 16; i += NTHREADS) z[i] = make_uint4(0u, 0u, 0u, 0u);
   }
   if (warp == 2) tc::tmem_alloc_2cta<512>(tmem_slot);
-  if (tid >= 32 && tid < 40)   // the "ones" operand: 8 rows of [1, 1, 0, 0, 0, 0, 0, 0] bf16
-    *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(bars) + ONES_OFF + (tid - 32) * 16) = make_uint4(0x3F803F80u, 0u, 0u, 0u);
+  if (tid >= 32 && tid < 40)   // the "ones" operand: 8 rows of [1, 1, 0, 0, 0, 0, 0, 0] (bf16 or fp16)
+    *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(bars) + ONES_OFF + (tid - 32) * 16) = make_uint4(F16 ? 0x3C003C00u : 0x3F803F80u, 0u, 0u, 0u);
   if (tid == 0) {
     for (int i = 0; i < NSLOTS; ++i) {
       tc::mbar_init(&bars[B_FULL + i], rank == 0 ? 2 : 1);   // leader: own TMA + the peer's relay
@@ -370,7 +411,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_p
     } else if (warp == 1) {
       // =========================== MMA ISSUER (leader CTA) ===========================
       uint32_t slot = 0, phase = 0;
-      const uint32_t idesc128 = tc::make_idesc_bf16(256, 128), idesc256 = tc::make_idesc_bf16(256, 256);
+      const uint32_t idesc128 = tc::make_idesc_16(256, 128, F16), idesc256 = tc::make_idesc_16(256, 256, F16);
       // descriptor templates; a byte offset is added to the 14-bit start-address field (>> 4)
       const uint64_t dA = tc::make_smem_desc(tc::smem_u32(sA), A_LBO, SBO);
       const uint64_t dG = tc::make_smem_desc(tc::smem_u32(sG), G_LBO, SBO);
@@ -695,7 +736,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_p
       for (int jj = 0; jj < 8; ++jj) {
         uint32_t w[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) w[e] = in_seq ? pack_bf16(v[jj * 8 + 2 * e], v[jj * 8 + 2 * e + 1]) : 0u;
+        for (int e = 0; e < 4; ++e) w[e] = in_seq ? pack_op<F16>(v[jj * 8 + 2 * e], v[jj * 8 + 2 * e + 1]) : 0u;
         const uint32_t chunk_off = (uint32_t)(16 * c + 8 * h + jj) * A_LBO;
         st_shared_v4(aA + chunk_off + (uint32_t)(r + 1) * 16, w[0], w[1], w[2], w[3]);
         if (halo_src) tc::st_async_v4(peer_halo + chunk_off, w[0], w[1], w[2], w[3], peer_halo_bar + (uint32_t)c * 8);
@@ -709,8 +750,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_p
       for (int jj = 0; jj < 5; ++jj) {
         const uint32_t* xv = &pf[8 * jj];
         st_shared_v4(aA + (uint32_t)(5 * h + jj) * A_LBO + (uint32_t)(r + 1) * 16,
-                     pack_bf16(__uint_as_float(xv[0]), __uint_as_float(xv[1])), pack_bf16(__uint_as_float(xv[2]), __uint_as_float(xv[3])),
-                     pack_bf16(__uint_as_float(xv[4]), __uint_as_float(xv[5])), pack_bf16(__uint_as_float(xv[6]), __uint_as_float(xv[7])));
+                     pack_op<F16>(__uint_as_float(xv[0]), __uint_as_float(xv[1])), pack_op<F16>(__uint_as_float(xv[2]), __uint_as_float(xv[3])),
+                     pack_op<F16>(__uint_as_float(xv[4]), __uint_as_float(xv[5])), pack_op<F16>(__uint_as_float(xv[6]), __uint_as_float(xv[7])));
       }
       publish_a(-1);
       MGB_STAMP(warp == 4 && lane == 0, 8);             // x_t published
@@ -757,11 +798,23 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_p
       }
       publish_a(-1);
     } else {
-      // u_lb spilled by the previous group (fp16, fetched before the setup)
+      // u_lb spilled by the previous group (fp16, fetched before the setup; fp32 in the F16 instantiation, read here)
+      if (F16) {
 #pragma unroll
-      for (int i = 0; i < 64; ++i) {
-        const float2 f2 = unpack_f16(pf[i]);
-        u[2 * i] = f2.x; u[2 * i + 1] = f2.y;
+        for (int c = 0; c < 2; ++c) {
+          const float4* up = reinterpret_cast<const float4*>(static_cast<const float*>(p.U_in) + row_g * C + 128 * c + 64 * h);
+#pragma unroll
+          for (int j4 = 0; j4 < 16; ++j4) {
+            const float4 v = in_seq ? __ldg(up + j4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            u[64 * c + 4 * j4 + 0] = v.x; u[64 * c + 4 * j4 + 1] = v.y; u[64 * c + 4 * j4 + 2] = v.z; u[64 * c + 4 * j4 + 3] = v.w;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 64; ++i) {
+          const float2 f2 = unpack_f16(pf[i]);
+          u[2 * i] = f2.x; u[2 * i + 1] = f2.y;
+        }
       }
       write_A(0, &u[0]);
       write_A(1, &u[64]);
@@ -787,13 +840,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_p
         for (int jj = 0; jj < 4; ++jj) {
           float gv[8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const float ta = tanh_approx(__uint_as_float(ga[jj * 8 + e]));
-            const float tf = tanh_approx(__uint_as_float(fa[jj * 8 + e]));
-            gv[e] = fmaf(ta, tf, tf);
-          }
-          st_shared_v4(aG + (uint32_t)(8 * i + 4 * h + jj) * G_LBO + (uint32_t)r * 16, pack_bf16(gv[0], gv[1]),
-                       pack_bf16(gv[2], gv[3]), pack_bf16(gv[4], gv[5]), pack_bf16(gv[6], gv[7]));
+          for (int e = 0; e < 8; ++e) gv[e] = gate_fn<F16>(__uint_as_float(ga[jj * 8 + e]), __uint_as_float(fa[jj * 8 + e]));
+          st_shared_v4(aG + (uint32_t)(8 * i + 4 * h + jj) * G_LBO + (uint32_t)r * 16, pack_op<F16>(gv[0], gv[1]),
+                       pack_op<F16>(gv[2], gv[3]), pack_op<F16>(gv[4], gv[5]), pack_op<F16>(gv[6], gv[7]));
         }
         publish(B_GREADY + i);
       }
@@ -867,16 +916,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_p
       if (is_out) {                                     // spill u while the last skip GEMM is still running
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
-          uint4* up = reinterpret_cast<uint4*>(p.U_out + row_g * C + 128 * c + 64 * h);
+          if (F16) {
+            float4* up = reinterpret_cast<float4*>(static_cast<float*>(p.U_out) + row_g * C + 128 * c + 64 * h);
 #pragma unroll
-          for (int j8 = 0; j8 < 8; ++j8) {
-            const float* v = &u[64 * c + 8 * j8];
-            up[j8] = make_uint4(pack_f16_sat(v[0], v[1]), pack_f16_sat(v[2], v[3]), pack_f16_sat(v[4], v[5]), pack_f16_sat(v[6], v[7]));
+            for (int j4 = 0; j4 < 16; ++j4) up[j4] = make_float4(u[64 * c + 4 * j4], u[64 * c + 4 * j4 + 1], u[64 * c + 4 * j4 + 2], u[64 * c + 4 * j4 + 3]);
+          } else {
+            uint4* up = reinterpret_cast<uint4*>(static_cast<__half*>(p.U_out) + row_g * C + 128 * c + 64 * h);
+#pragma unroll
+            for (int j8 = 0; j8 < 8; ++j8) {
+              const float* v = &u[64 * c + 8 * j8];
+              up[j8] = make_uint4(pack_f16_sat(v[0], v[1]), pack_f16_sat(v[2], v[3]), pack_f16_sat(v[4], v[5]), pack_f16_sat(v[6], v[7]));
+            }
           }
         }
       }
-    } else if (!first_group) {                          // fetch the earlier groups' skip sum before waiting for this group's
-      const uint4* sp = reinterpret_cast<const uint4*>(p.S + row_g * C + 128 * h);
+    } else if (!first_group && !F16) {                  // fetch the earlier groups' skip sum before waiting for this group's
+      const uint4* sp = reinterpret_cast<const uint4*>(static_cast<const __half*>(p.S) + row_g * C + 128 * h);
 #pragma unroll
       for (int i = 0; i < 16; ++i) sraw[i] = in_seq ? __ldg(sp + i) : make_uint4(0u, 0u, 0u, 0u);
     }
@@ -889,8 +944,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_p
         uint32_t a[32];
         tc::tmem_ld32(TM_SKIP + lane_off + 128 * h + 32 * cc, a);
         tc::tmem_ld_wait();
-        if (is_out) {
-          uint4* sp = reinterpret_cast<uint4*>(p.S + row_g * C + 128 * h + 32 * cc);
+        if (is_out && F16) {
+          float4* sp = reinterpret_cast<float4*>(static_cast<float*>(p.S) + row_g * C + 128 * h + 32 * cc);
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            float4 v = make_float4(__uint_as_float(a[4 * j4]), __uint_as_float(a[4 * j4 + 1]), __uint_as_float(a[4 * j4 + 2]),
+                                   __uint_as_float(a[4 * j4 + 3]));
+            if (!first_group) { const float4 o = sp[j4]; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+            sp[j4] = v;
+          }
+        } else if (is_out) {
+          uint4* sp = reinterpret_cast<uint4*>(static_cast<__half*>(p.S) + row_g * C + 128 * h + 32 * cc);
 #pragma unroll
           for (int j8 = 0; j8 < 4; ++j8) {
             float v[8];
@@ -917,7 +981,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_p
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj) {
           float v[8];
-          if (!first_group) {           // + the earlier groups' skip sum (the blocks' skip biases live in the skip-projection bias)
+          if (!first_group && F16) {    // fp32 spill, read here (L2-resident: the previous launch has just written it)
+            const float4* sp = reinterpret_cast<const float4*>(static_cast<const float*>(p.S) + row_g * C + 128 * h + 32 * cc + 8 * jj);
+            const float4 o0 = in_seq ? __ldg(sp) : make_float4(0.f, 0.f, 0.f, 0.f), o1 = in_seq ? __ldg(sp + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float o[8] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = (__uint_as_float(a[jj * 8 + e]) + o[e]) * inv_sqrt_l;
+          } else if (!first_group) {    // + the earlier groups' skip sum (the blocks' skip biases live in the skip-projection bias)
             const uint4 o = sraw[4 * cc + jj];
             const uint32_t w4[4] = {o.x, o.y, o.z, o.w};
 #pragma unroll
@@ -930,8 +1000,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_p
 #pragma unroll
             for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(a[jj * 8 + e]) * inv_sqrt_l;
           }
-          st_shared_v4(aA + (uint32_t)(16 * h + 4 * cc + jj) * A_LBO + (uint32_t)(r + 1) * 16, pack_bf16(v[0], v[1]),
-                       pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+          st_shared_v4(aA + (uint32_t)(16 * h + 4 * cc + jj) * A_LBO + (uint32_t)(r + 1) * 16, pack_op<F16>(v[0], v[1]),
+                       pack_op<F16>(v[2], v[3]), pack_op<F16>(v[4], v[5]), pack_op<F16>(v[6], v[7]));
         }
       }
       publish_a(-1);
@@ -964,8 +1034,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_p
             float v[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) v[e] = fmaxf(__uint_as_float(a[jj * 8 + e]), 0.f);
-            st_shared_v4(aG + (uint32_t)(16 * c + 8 * h + 4 * hh + jj) * G_LBO + (uint32_t)r * 16, pack_bf16(v[0], v[1]),
-                         pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+            st_shared_v4(aG + (uint32_t)(16 * c + 8 * h + 4 * hh + jj) * G_LBO + (uint32_t)r * 16, pack_op<F16>(v[0], v[1]),
+                         pack_op<F16>(v[2], v[3]), pack_op<F16>(v[4], v[5]), pack_op<F16>(v[6], v[7]));
           }
         }
       }
@@ -1016,7 +1086,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_p
   if (warp == 2) tc::tmem_dealloc_2cta<512>(tmem);
 }
 
-// ---- cond [B][T][H] fp32 -> [32][Rp][8] bf16 on the batch row axis (zero rows in the gaps and pads) ----
+// ---- cond [B][T][H] fp32 -> [32][Rp][8] bf16 (or fp16) on the batch row axis (zero rows in the gaps and pads) ----
+template <bool F16>
 __global__ void cond_pack_kernel(const float* __restrict__ cond, __nv_bfloat16* __restrict__ out, int T, int Tg, int R,
                                  int Rp) {
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);   // 8 rows per block, 32 chunks per row
@@ -1029,7 +1100,7 @@ __global__ void cond_pack_kernel(const float* __restrict__ cond, __nv_bfloat16* 
     if (f < T) {
       const float4* src = reinterpret_cast<const float4*>(cond + ((size_t)b * T + f) * C + c8 * 8);
       const float4 a = __ldg(src), c = __ldg(src + 1);
-      v = make_uint4(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w), pack_bf16(c.x, c.y), pack_bf16(c.z, c.w));
+      v = make_uint4(pack_op<F16>(a.x, a.y), pack_op<F16>(a.z, a.w), pack_op<F16>(c.x, c.y), pack_op<F16>(c.z, c.w));
     }
   }
   reinterpret_cast<uint4*>(out)[(size_t)c8 * Rp + row] = v;
@@ -1054,6 +1125,7 @@ __global__ void ktab_kernel(const float* __restrict__ dtab, const float* __restr
 // KUNI: kimg[s][l][rank] = N=256 weight half ([2 k-chunks][128 rows][8 bf16]) whose K=0/1 columns hold the bf16 hi/lo
 // split of sqrt(2) * ktab[s][0][l][128 rank + row]; all other columns are zero.  Block x == L builds the image of
 // k00[s][0] (no sqrt(2): it is added to u_0 directly).
+template <bool F16>
 __global__ void kimg_kernel(const float* __restrict__ ktab, const float* __restrict__ k00, uint8_t* __restrict__ kimg,
                             uint8_t* __restrict__ k00img, int L, int B) {
   const int l = blockIdx.x, st = blockIdx.y, rank = blockIdx.z, row = threadIdx.x;   // 128 threads
@@ -1066,8 +1138,8 @@ __global__ void kimg_kernel(const float* __restrict__ ktab, const float* __restr
     v = k00[((size_t)st * B) * C + 128 * rank + row];
     dst = reinterpret_cast<uint4*>(k00img + ((size_t)st * 2 + rank) * KIMG_BYTES);
   }
-  const float hi = __bfloat162float(__float2bfloat16_rn(v));
-  dst[row] = make_uint4(pack_bf16(hi, v - hi), 0u, 0u, 0u);
+  const float hi = round_op<F16>(v);
+  dst[row] = make_uint4(pack_op<F16>(hi, v - hi), 0u, 0u, 0u);
   dst[128 + row] = make_uint4(0u, 0u, 0u, 0u);
 }
 
@@ -1104,6 +1176,7 @@ inline int num_wslots(const mgb_model_dims& d) { return W_LAYER0 + d.layers * W_
 // the 128-column tile).  Folded constants (all powers of two, exact in bf16): the gate half of the k=3 conv
 // (weights and bias) carries 0.5 so the epilogue computes tanh(a/2) without a multiply, and Wo_x / Wo_s carry the
 // 0.5 of sigmoid(a)*tanh(f) = 0.5*(tanh(a/2)*tanh(f) + tanh(f)).
+template <bool F16>
 __global__ void pack_images_kernel(const float* __restrict__ flat, const FlatOffsets f, const int L, const int n_mel,
                                    const int nslots, const float* __restrict__ b_in, const float* __restrict__ b_skipp,
                                    const float* __restrict__ b_out, __nv_bfloat16* __restrict__ img) {
@@ -1165,7 +1238,7 @@ __global__ void pack_images_kernel(const float* __restrict__ flat, const FlatOff
           if (k < 2) {
             const int oc = rank == 0 ? 64 * ci + row : C + 64 * ci + row;
             const float bv = gate_scale * fl[f.rel.conv_b + oc];
-            const float hi = __bfloat162float(__float2bfloat16_rn(bv));
+            const float hi = round_op<F16>(bv);
             x = k == 0 ? hi : bv - hi;
           }
           break;
@@ -1173,7 +1246,7 @@ __global__ void pack_images_kernel(const float* __restrict__ flat, const FlatOff
         case 10: case 11: case 12: {   // K = 16 against the "ones" operand: k=0 bf16(b), k=1 the bf16 remainder
           if (k < 2) {
             const float bv = kind == 10 ? b_in[128 * rank + row] : kind == 11 ? b_skipp[128 * rank + row] : b_out[64 * rank + row];
-            const float hi = __bfloat162float(__float2bfloat16_rn(bv));
+            const float hi = round_op<F16>(bv);
             x = k == 0 ? hi : bv - hi;
           }
           break;
@@ -1183,7 +1256,7 @@ __global__ void pack_images_kernel(const float* __restrict__ flat, const FlatOff
       v[e] = x;
     }
     reinterpret_cast<uint4*>(img)[((size_t)rank * nslots + slot) * 1024 + unit] =
-        make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+        make_uint4(pack_op<F16>(v[0], v[1]), pack_op<F16>(v[2], v[3]), pack_op<F16>(v[4], v[5]), pack_op<F16>(v[6], v[7]));
   }
 }
 
@@ -1215,7 +1288,7 @@ struct WorkBf16 {
   size_t status, condT, tsteps, d, h, dtab, ctab, ktab, k00, kimg, k00img, U, U2, S, total;
   int Tg, R, Rp;
 };
-WorkBf16 work_layout(const mgb_model_dims& d, int B, int T, int K) {
+WorkBf16 work_layout(const mgb_model_dims& d, int B, int T, int K, bool f16) {
   WorkBf16 w{};
   w.Tg = T + 1;
   w.R = B * w.Tg;
@@ -1234,9 +1307,10 @@ WorkBf16 work_layout(const mgb_model_dims& d, int B, int T, int K) {
   w.k00 = take((size_t)K * B * C * 4);
   w.kimg = take((size_t)K * d.layers * 2 * KIMG_BYTES);
   w.k00img = take((size_t)K * 2 * KIMG_BYTES);
-  w.U = take((size_t)B * T * C * 2);
-  w.U2 = take((size_t)B * T * C * 2);
-  w.S = take((size_t)B * T * C * 2);
+  const size_t spill = f16 ? 4 : 2;           // bytes per element of the group spills (fp32 in the fp16-operand mode)
+  w.U = take((size_t)B * T * C * spill);
+  w.U2 = take((size_t)B * T * C * spill);
+  w.S = take((size_t)B * T * C * spill);
   w.total = p;
   return w;
 }
@@ -1274,10 +1348,10 @@ int plan_groups(int L, int R, int pair_slots) {
 size_t bf16_packed_bytes(const mgb_model_dims& d) {
   return small_layout(d).total * sizeof(float) + (size_t)2 * num_wslots(d) * SLOT_BYTES;
 }
-size_t bf16_workspace_bytes(const mgb_model_dims& d, int B, int T, int K) { return work_layout(d, B, T, K > 0 ? K : 1).total; }
-size_t bf16_status_offset(const mgb_model_dims& d, int B, int T) { return work_layout(d, B, T, 1).status; }
+size_t bf16_workspace_bytes(const mgb_model_dims& d, int B, int T, int K, bool f16) { return work_layout(d, B, T, K > 0 ? K : 1, f16).total; }
+size_t bf16_status_offset(const mgb_model_dims& d, int B, int T) { return work_layout(d, B, T, 1, false).status; }
 
-int bf16_pack(const mgb_model_dims& d, const float* flat, void* packed, cudaStream_t s) {
+int bf16_pack(const mgb_model_dims& d, const float* flat, void* packed, cudaStream_t s, bool f16) {
   const FlatOffsets f = flat_offsets(d);
   const SmallOff o = small_layout(d);
   float* P = static_cast<float*>(packed);
@@ -1293,8 +1367,10 @@ int bf16_pack(const mgb_model_dims& d, const float* flat, void* packed, cudaStre
   pack_small_kernel<<<1, 256, 0, s>>>(flat, f, L, d.n_mel, P + o.bo_x, P + o.bsum_skip, P + o.b_in,
                                       P + o.b_skip, P + o.b_out);
   __nv_bfloat16* img = reinterpret_cast<__nv_bfloat16*>(P + o.total);
-  pack_images_kernel<<<dim3(num_wslots(d), 2), 256, 0, s>>>(flat, f, L, d.n_mel, num_wslots(d), P + o.b_in, P + o.b_skip,
-                                                            P + o.b_out, img);
+  if (f16) pack_images_kernel<true><<<dim3(num_wslots(d), 2), 256, 0, s>>>(flat, f, L, d.n_mel, num_wslots(d), P + o.b_in,
+                                                                           P + o.b_skip, P + o.b_out, img);
+  else pack_images_kernel<false><<<dim3(num_wslots(d), 2), 256, 0, s>>>(flat, f, L, d.n_mel, num_wslots(d), P + o.b_in,
+                                                                        P + o.b_skip, P + o.b_out, img);
   MGB_LAUNCH_CHECK();
   return MGB_OK;
 }
@@ -1304,10 +1380,10 @@ int bf16_pack(const mgb_model_dims& d, const float* flat, void* packed, cudaStre
 //   t == nullptr : `nsteps` steps, step s runs every utterance at timestep s (the sampling loop); the step-embedding
 //                  MLP and the 20 diffusion projections are evaluated once per STEP, not per utterance.
 int bf16_prepare(const mgb_model_dims& d, const void* packed, const int64_t* t, int nsteps, const float* cond,
-                 const float* spk, int B, int T, void* ws, cudaStream_t s) {
-  MGB_REQUIRE(d.n_mel == 80, MGB_E_UNSUPPORTED, "the bf16 path is built for n_mel == 80 (got %d)", d.n_mel);
+                 const float* spk, int B, int T, void* ws, cudaStream_t s, bool f16) {
+  MGB_REQUIRE(d.n_mel == 80, MGB_E_UNSUPPORTED, "the tensor-core path is built for n_mel == 80 (got %d)", d.n_mel);
   const SmallOff o = small_layout(d);
-  const WorkBf16 w = work_layout(d, B, T, nsteps);
+  const WorkBf16 w = work_layout(d, B, T, nsteps, f16);
   const float* P = static_cast<const float*>(packed);
   uint8_t* W = static_cast<uint8_t*>(ws);
   const int L = d.layers, H = d.d_encoder;
@@ -1318,7 +1394,8 @@ int bf16_prepare(const mgb_model_dims& d, const void* packed, const int64_t* t, 
   const int U = uniform ? nsteps : B;
   {
     dim3 grid((w.Rp + 7) / 8);
-    cond_pack_kernel<<<grid, 256, 0, s>>>(cond, reinterpret_cast<__nv_bfloat16*>(W + w.condT), T, w.Tg, w.R, w.Rp);
+    if (f16) cond_pack_kernel<true><<<grid, 256, 0, s>>>(cond, reinterpret_cast<__nv_bfloat16*>(W + w.condT), T, w.Tg, w.R, w.Rp);
+    else cond_pack_kernel<false><<<grid, 256, 0, s>>>(cond, reinterpret_cast<__nv_bfloat16*>(W + w.condT), T, w.Tg, w.R, w.Rp);
     MGB_CUDA_CHECK(cudaMemsetAsync(W + w.status, 0, sizeof(int), s));
     note_launch();
   }
@@ -1339,77 +1416,29 @@ int bf16_prepare(const mgb_model_dims& d, const void* packed, const int64_t* t, 
                                                                reinterpret_cast<float*>(W + w.k00), L, B, uniform ? 1 : 0);
   note_launch(5);   // step MLP (2), two projection tables, ktab
   if (uniform && !d.multi_speaker) {   // k_l is the same for every utterance: hand it to the residual GEMM (KUNI kernels)
-    kimg_kernel<<<dim3(L + 1, nsteps, 2), 128, 0, s>>>(reinterpret_cast<const float*>(W + w.ktab),
-                                                       reinterpret_cast<const float*>(W + w.k00), W + w.kimg, W + w.k00img, L, B);
+    if (f16) kimg_kernel<true><<<dim3(L + 1, nsteps, 2), 128, 0, s>>>(reinterpret_cast<const float*>(W + w.ktab),
+                                                                      reinterpret_cast<const float*>(W + w.k00), W + w.kimg, W + w.k00img, L, B);
+    else kimg_kernel<false><<<dim3(L + 1, nsteps, 2), 128, 0, s>>>(reinterpret_cast<const float*>(W + w.ktab),
+                                                                   reinterpret_cast<const float*>(W + w.k00), W + w.kimg, W + w.k00img, L, B);
     note_launch();
   }
   MGB_LAUNCH_CHECK();
   return MGB_OK;
 }
 
-// One Denoiser call (+ fused posterior update when sched != nullptr) on a workspace prepared by bf16_prepare with
-// the same (B, T, nsteps).  step = which prepared table to use; t_uniform >= 0 replaces t[b] in the posterior.
-int bf16_run(const mgb_model_dims& d, const void* packed, const float* x, const int64_t* t, int t_uniform, int step,
-             int nsteps, const float* noise, const float* sched, int K, int clip, float* x_prev, float* out_x0, int B, int T,
-             void* ws, cudaStream_t s) {
-  const SmallOff o = small_layout(d);
-  const WorkBf16 w = work_layout(d, B, T, nsteps);
-  const float* P = static_cast<const float*>(packed);
-  uint8_t* W = static_cast<uint8_t*>(ws);
-  const int L = d.layers;
-
-  static int pair_slots = 0;
-  if (!pair_slots) {
-    int dev = 0, sms = 0;
-    MGB_CUDA_CHECK(cudaGetDevice(&dev));
-    MGB_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    MGB_CUDA_CHECK(cudaFuncSetAttribute(fused_pair_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
-    MGB_CUDA_CHECK(cudaFuncSetAttribute(fused_pair_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
-    pair_slots = sms / 2 > 0 ? sms / 2 : 1;
-  }
-  CUtensorMap tm_cond;   // cond image [32 chunks][Rp rows][8]: boxes of 128 rows x 8 chunks
-  if (int rc = make_image_map(&tm_cond, W + w.condT, 32, w.Rp, 8)) return rc;
-  FusedParams p{};
-  p.wimg = reinterpret_cast<const uint8_t*>(P + o.total);
-  p.wimg_rank_stride = (size_t)num_wslots(d) * SLOT_BYTES;
-  p.condT = reinterpret_cast<const __nv_bfloat16*>(W + w.condT); p.Rp = w.Rp;
-  p.x_t = x; p.noise = noise; p.x_prev = x_prev; p.x0_out = out_x0; p.sched = sched; p.t = t; p.t_uniform = t_uniform;
-  p.K = K; p.clip = clip; p.n_mel = d.n_mel;
-  p.ktab = reinterpret_cast<const float*>(W + w.ktab) + (size_t)step * B * L * C;
-  p.k00 = reinterpret_cast<const float*>(W + w.k00) + (size_t)step * B * C;
-  const bool kuni = t_uniform >= 0 && !d.multi_speaker;   // bf16_prepare built kimg for exactly this case
-  p.kimg = W + w.kimg + (size_t)step * L * 2 * KIMG_BYTES;
-  p.k00img = W + w.k00img + (size_t)step * 2 * KIMG_BYTES;
-  __half* Ubuf[2] = {reinterpret_cast<__half*>(W + w.U), reinterpret_cast<__half*>(W + w.U2)};
-  p.S = reinterpret_cast<__half*>(W + w.S);
-  p.B = B; p.T = T; p.Tg = w.Tg; p.R = w.R; p.L = L; p.status = reinterpret_cast<int*>(W + w.status);
-  static const int debug_mode = getenv("MGB_DEBUG_MODE") ? atoi(getenv("MGB_DEBUG_MODE")) : 0;
-  p.debug_mode = debug_mode;
-  const int ngroups = plan_groups(L, w.R, pair_slots);
-  for (int g = 0; g < ngroups; ++g) {
-    p.lb = g * L / ngroups;
-    p.le = (g + 1) * L / ngroups;
-    p.halo = p.le - p.lb;
-    p.V = TILE_ROWS - 2 * p.halo;
-    const int npairs = (w.R + p.V - 1) / p.V;
-    p.U_in = Ubuf[g & 1];
-    p.U_out = Ubuf[(g + 1) & 1];
-    // timing experiments (MGB_DEBUG_MODE bit mask): 1 = setup + teardown only, 2 = prologue + ending without layers,
-    // 4 = skip the first group's launch, 8 = skip the later groups' launches.  Results are garbage in every mode.
-    if (debug_mode & 2) { if (g == 0) p.le = p.lb; else p.lb = p.le; }
-    if (((debug_mode & 4) && g == 0) || ((debug_mode & 8) && g > 0)) continue;
-    prof_begin(s);
-    static const bool do_prof = getenv("MGB_PROFILE") != nullptr;
-    if (do_prof) {
+#ifdef MGB_DEBUG_BUILD
+// Debug library only (libmixgan_b200_dbg.so): MGB_PROFILE=1 runs the PROF instantiation of the bf16 kernel and prints the
+// per-role wait counters; it allocates and synchronises, which the product library never does.
+static int run_profiled(FusedParams& p, const CUtensorMap& tm_cond, bool kuni, int npairs, cudaStream_t s) {
       const int ncta = 2 * npairs;
       long long* dprof = nullptr;
       cudaMalloc(&dprof, (size_t)ncta * 320 * sizeof(long long));
       cudaMemset(dprof, 0, (size_t)ncta * 320 * sizeof(long long));
       p.prof = dprof;
-      cudaFuncSetAttribute(fused_pair_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL);
-      cudaFuncSetAttribute(fused_pair_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL);
-      if (kuni) fused_pair_kernel<true, true><<<ncta, NTHREADS, SMEM_TOTAL, s>>>(p, tm_cond);
-      else fused_pair_kernel<true, false><<<ncta, NTHREADS, SMEM_TOTAL, s>>>(p, tm_cond);
+      cudaFuncSetAttribute(fused_pair_kernel<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL);
+      cudaFuncSetAttribute(fused_pair_kernel<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL);
+      if (kuni) fused_pair_kernel<true, true, false><<<ncta, NTHREADS, SMEM_TOTAL, s>>>(p, tm_cond);
+      else fused_pair_kernel<true, false, false><<<ncta, NTHREADS, SMEM_TOTAL, s>>>(p, tm_cond);
       cudaStreamSynchronize(s);
       long long* h = (long long*)malloc((size_t)ncta * 320 * sizeof(long long));
       cudaMemcpy(h, dprof, (size_t)ncta * 320 * sizeof(long long), cudaMemcpyDeviceToHost);
@@ -1460,9 +1489,92 @@ int bf16_run(const mgb_model_dims& d, const void* packed, const float* x, const 
       for (int k = 1; k < 16; ++k) fprintf(stderr, " %.0f", a[32 + k] - a[32 + k - 1]);
       fprintf(stderr, "\n");
       free(h); cudaFree(dprof); p.prof = nullptr;
+  return MGB_OK;
+}
+#endif
+
+// Per-device one-time setup: the opt-in to > 48 KB of dynamic shared memory is a per-device function attribute, so a
+// process that drives several GPUs (nn.DataParallel replicas, or a host thread per device) must set it on each of them.
+static int pair_slots_for_current_device(int* out) {
+  static PerDeviceOnce once;
+  if (once.pending()) {
+    MGB_CUDA_CHECK(cudaFuncSetAttribute(fused_pair_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+    MGB_CUDA_CHECK(cudaFuncSetAttribute(fused_pair_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+    MGB_CUDA_CHECK(cudaFuncSetAttribute(fused_pair_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+    MGB_CUDA_CHECK(cudaFuncSetAttribute(fused_pair_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+    once.done();
+  }
+  int dev = 0, sms = 0;
+  MGB_CUDA_CHECK(cudaGetDevice(&dev));
+  MGB_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  *out = sms / 2 > 0 ? sms / 2 : 1;
+  return MGB_OK;
+}
+
+// One Denoiser call (+ fused posterior update when sched != nullptr) on a workspace prepared by bf16_prepare with
+// the same (B, T, nsteps, f16).  step = which prepared table to use; t_uniform >= 0 replaces t[b] in the posterior.
+int bf16_run(const mgb_model_dims& d, const void* packed, const float* x, const int64_t* t, int t_uniform, int step,
+             int nsteps, const float* noise, const float* sched, int K, int clip, float* x_prev, float* out_x0, int B, int T,
+             void* ws, cudaStream_t s, bool f16) {
+  const SmallOff o = small_layout(d);
+  const WorkBf16 w = work_layout(d, B, T, nsteps, f16);
+  const float* P = static_cast<const float*>(packed);
+  uint8_t* W = static_cast<uint8_t*>(ws);
+  const int L = d.layers;
+
+  int pair_slots = 0;
+  if (int rc = pair_slots_for_current_device(&pair_slots)) return rc;
+  CUtensorMap tm_cond;   // cond image [32 chunks][Rp rows][8]: boxes of 128 rows x 8 chunks
+  if (int rc = make_image_map(&tm_cond, W + w.condT, 32, w.Rp, 8)) return rc;
+  FusedParams p{};
+  p.wimg = reinterpret_cast<const uint8_t*>(P + o.total);
+  p.wimg_rank_stride = (size_t)num_wslots(d) * SLOT_BYTES;
+  p.condT = reinterpret_cast<const __nv_bfloat16*>(W + w.condT); p.Rp = w.Rp;
+  p.x_t = x; p.noise = noise; p.x_prev = x_prev; p.x0_out = out_x0; p.sched = sched; p.t = t; p.t_uniform = t_uniform;
+  p.K = K; p.clip = clip; p.n_mel = d.n_mel;
+  p.ktab = reinterpret_cast<const float*>(W + w.ktab) + (size_t)step * B * L * C;
+  p.k00 = reinterpret_cast<const float*>(W + w.k00) + (size_t)step * B * C;
+  const bool kuni = t_uniform >= 0 && !d.multi_speaker;   // bf16_prepare built kimg for exactly this case
+  p.kimg = W + w.kimg + (size_t)step * L * 2 * KIMG_BYTES;
+  p.k00img = W + w.k00img + (size_t)step * 2 * KIMG_BYTES;
+  void* Ubuf[2] = {W + w.U, W + w.U2};
+  p.S = W + w.S;
+  p.B = B; p.T = T; p.Tg = w.Tg; p.R = w.R; p.L = L; p.status = reinterpret_cast<int*>(W + w.status);
+#ifdef MGB_DEBUG_BUILD
+  // timing experiments (MGB_DEBUG_MODE bit mask): 1 = setup + teardown only, 2 = prologue + ending without layers,
+  // 4 = skip the first group's launch, 8 = skip the later groups' launches.  Results are garbage in every mode.
+  static const int debug_mode = getenv("MGB_DEBUG_MODE") ? atoi(getenv("MGB_DEBUG_MODE")) : 0;
+  static const bool do_prof = getenv("MGB_PROFILE") != nullptr;
+#else
+  constexpr int debug_mode = 0;
+#endif
+  p.debug_mode = debug_mode;
+  const int ngroups = plan_groups(L, w.R, pair_slots);
+  for (int g = 0; g < ngroups; ++g) {
+    p.lb = g * L / ngroups;
+    p.le = (g + 1) * L / ngroups;
+    p.halo = p.le - p.lb;
+    p.V = TILE_ROWS - 2 * p.halo;
+    const int npairs = (w.R + p.V - 1) / p.V;
+    p.U_in = Ubuf[g & 1];
+    p.U_out = Ubuf[(g + 1) & 1];
+#ifdef MGB_DEBUG_BUILD
+    if (debug_mode & 2) { if (g == 0) p.le = p.lb; else p.lb = p.le; }
+    if (((debug_mode & 4) && g == 0) || ((debug_mode & 8) && g > 0)) continue;
+    if (do_prof && !f16) {
+      if (int rc = run_profiled(p, tm_cond, kuni, npairs, s)) return rc;
+      note_launch();
+      continue;
+    }
+#endif
+    prof_begin(s);
+    const dim3 grid(2 * npairs);
+    if (f16) {
+      if (kuni) fused_pair_kernel<false, true, true><<<grid, NTHREADS, SMEM_TOTAL, s>>>(p, tm_cond);
+      else fused_pair_kernel<false, false, true><<<grid, NTHREADS, SMEM_TOTAL, s>>>(p, tm_cond);
     } else {
-      if (kuni) fused_pair_kernel<false, true><<<2 * npairs, NTHREADS, SMEM_TOTAL, s>>>(p, tm_cond);
-      else fused_pair_kernel<false, false><<<2 * npairs, NTHREADS, SMEM_TOTAL, s>>>(p, tm_cond);
+      if (kuni) fused_pair_kernel<false, true, false><<<grid, NTHREADS, SMEM_TOTAL, s>>>(p, tm_cond);
+      else fused_pair_kernel<false, false, false><<<grid, NTHREADS, SMEM_TOTAL, s>>>(p, tm_cond);
     }
     prof_end(s);
     note_launch();

@@ -236,6 +236,13 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
          | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
 }
 
+// kind::f16 with both operands fp16 (format 0) or bf16 (format 1): same instruction, same rate; fp16 carries an 11-bit
+// significand (TF32's), bf16 an 8-bit one.
+__host__ __device__ constexpr uint32_t make_idesc_16(int M, int N, bool fp16) {
+  return (1u << 4) | ((fp16 ? 0u : 1u) << 7) | ((fp16 ? 0u : 1u) << 10)
+         | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
+}
+
 }  // namespace tc
 
 // =====================================================================================================

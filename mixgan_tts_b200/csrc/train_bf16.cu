@@ -35,18 +35,26 @@ constexpr int FCL = 4;            // frames-GEMM cluster: 4 row tiles share ever
 constexpr long long kTimeout = 200000000LL;    // ~0.1 s of SM cycles: a protocol bug traps instead of hanging
 constexpr float RSQRT2 = 0.70710678118654752440f;
 
-// MGB_TRAIN_TRACE=1: name every launch on stderr and synchronise after it (debug aid; never set in production)
+// Debug library only (MGB_DEBUG_BUILD): MGB_TRAIN_TRACE=1 names every launch on stderr and synchronises after it
+#ifdef MGB_DEBUG_BUILD
 bool trace_on() {
   static const bool on = [] { const char* e = getenv("MGB_TRAIN_TRACE"); return e && *e == '1'; }();
   return on;
 }
+#else
+constexpr bool trace_on() { return false; }   // the product library never synchronises
+#endif
 void trace(const char* what, cudaStream_t s) {
+#ifdef MGB_DEBUG_BUILD
   if (!trace_on()) return;
   fprintf(stderr, "[mgb train] %s ...", what);
   fflush(stderr);
   const cudaError_t e = cudaStreamSynchronize(s);
   fprintf(stderr, " %s\n", cudaGetErrorString(e));
   fflush(stderr);
+#else
+  (void)what; (void)s;
+#endif
 }
 
 struct RowSpace { int T, Tg, R, ntiles, Rp; };
@@ -468,11 +476,11 @@ cudaError_t launch_cluster(K kernel, dim3 grid, int cluster_x, size_t smem, cuda
 template <int NT, int MODE>
 int launch_fgemm(const FArgs& a, int ntiles, int n_tiles_n, cudaStream_t s) {
   constexpr int CL = (MODE == F_GATE || MODE == F_OUT) ? 2 : FCL;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce once;
+  if (once.pending()) {
     MGB_CUDA_CHECK(cudaFuncSetAttribute(fgemm_kernel<NT, MODE, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         FSmem<NT>::TOTAL));
-    configured = true;
+    once.done();
   }
   CUtensorMap m0, m1;
   if (int rc = make_image_map(&m0, a.A0, a.steps0 * 8, a.Rp, 8)) return rc;
@@ -661,10 +669,10 @@ struct WgSpec {                   // one weight-gradient problem: dst (flat grad
 };
 template <int NT>
 int launch_wg_multi(const WgSpec* sp, int n, const RowSpace& rs, float* part, int* status, cudaStream_t s) {
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce once;
+  if (once.pending()) {
     MGB_CUDA_CHECK(cudaFuncSetAttribute(wgemm_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, WSmem<NT>::TOTAL));
-    configured = true;
+    once.done();
   }
   WgArgs a{};
   WgMaps maps{};

@@ -3,6 +3,7 @@
 // tests/test_umma_probe.py uses it to pin the shared-memory descriptor conventions of tc05.cuh
 // (LBO/SBO meaning, +16 B row shift of the start address, K advance) against a host matmul.
 #include "common.cuh"
+#include "../../include/mixgan_b200_probe.h"
 #include "tc05.cuh"
 
 namespace mgb {

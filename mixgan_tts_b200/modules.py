@@ -22,7 +22,9 @@ from torch import nn
 
 from . import _lib
 
-PRECISIONS = {"fp32": _lib.PREC_FP32, "bf16": _lib.PREC_BF16}
+# "fp16": the reference-precision (fp32, 1e-3) mode on the tensor cores - fp16 operands (TF32's 11-bit significand),
+# fp32 accumulation and streams; inference entry points only (training uses "bf16" or "fp32").
+PRECISIONS = {"fp32": _lib.PREC_FP32, "bf16": _lib.PREC_BF16, "fp16": _lib.PREC_FP16}
 _PACK_KINDS = dict(PRECISIONS, fp32_tables=_lib.PACK_FP32_TABLES)
 
 # Fused optimizers (torch.optim.Adam(fused=True) ...) update parameters in place WITHOUT bumping Tensor._version, so the
@@ -229,14 +231,20 @@ class Denoiser(nn.Module):
         return out
 
     # ---------------------------------------------------------------- training (autograd)
+    @property
+    def train_precision(self) -> str:
+        """Arithmetic of the autograd path: "bf16" trains on tcgen05; the two reference-precision modes ("fp32", and
+        "fp16" whose tensor-core kernel is inference-only) train in exact fp32."""
+        return "bf16" if self.precision == "bf16" else "fp32"
+
     def flat_weights(self, params=None) -> torch.Tensor:
         """The parameters as one fp32 vector in the canonical order (built together with a weight pack)."""
-        self.packed_weights("fp32" if self.precision == "fp32" else "fp32_tables", params)
+        self.packed_weights("fp32" if self.train_precision == "fp32" else "fp32_tables", params)
         return self._flat[1]
 
     def train_workspace(self, B: int, T: int, device) -> torch.Tensor:
         lib = _lib.load()
-        n = lib.mgb_train_workspace_bytes(C.byref(self.dims), PRECISIONS[self.precision], B, T)
+        n = lib.mgb_train_workspace_bytes(C.byref(self.dims), PRECISIONS[self.train_precision], B, T)
         if n == 0:
             raise ValueError(f"unsupported shape B={B} T={T}")
         return self._train_ws.get(n, device)
@@ -333,7 +341,7 @@ class _DenoiserGradFn(torch.autograd.Function):
         lib = _lib.load()
         dev = x.device
         B, _, M, T = x.shape
-        prec = PRECISIONS[den.precision]
+        prec = PRECISIONS[den.train_precision]
         tg = None
         if den.use_cuda_graphs:
             key = (B, T, prec, dev)
@@ -378,7 +386,7 @@ class _DenoiserGradFn(torch.autograd.Function):
         ctx.tg = None
         with torch.cuda.device(dev):
             # both precisions read fp32 per-utterance tables; the bf16 mode needs nothing else from the fp32 pack
-            packed = den.packed_weights("fp32" if den.precision == "fp32" else "fp32_tables", params)
+            packed = den.packed_weights("fp32" if den.train_precision == "fp32" else "fp32_tables", params)
             flat = den._flat[1]                       # built by the call above (same fingerprint)
             tt = t.detach().to(torch.int64).contiguous()
             out = torch.empty_like(x)

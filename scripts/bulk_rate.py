@@ -3,7 +3,7 @@ import ctypes as C, sys
 sys.path.insert(0, ".")
 import torch
 from mixgan_tts_b200 import _lib
-lib = _lib.load()
+lib = _lib.load_debug()
 src = torch.zeros(32 << 20, dtype=torch.uint8, device="cuda")      # 32 MB: L2-resident after the first pass
 st = torch.zeros(1, dtype=torch.int32, device="cuda")
 stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)

@@ -1,7 +1,7 @@
 #!/bin/bash
 # In-kernel role profile (MGB_PROFILE=1) of one full sampling call (KUNI kernels) at B=64, T=800.
 set -u
-MGB_PROFILE=1 timeout 300 python - <<'PY' 2>&1 | grep -E "mgb profile|mgb timeline|mgb boundary|mgb ring|mgb tile|Error|error" | tail -${LINES_OUT:-6}
+MIXGAN_B200_USE_DEBUG_LIB=1 MGB_PROFILE=1 timeout 300 python - <<'PY' 2>&1 | grep -E "mgb profile|mgb timeline|mgb boundary|mgb ring|mgb tile|Error|error" | tail -${LINES_OUT:-6}
 import sys, torch
 sys.path.insert(0, '.'); sys.path.insert(0, 'tests')
 from helpers import Case

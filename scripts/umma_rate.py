@@ -2,7 +2,7 @@
 import ctypes as C, sys, torch
 sys.path.insert(0, '.')
 from mixgan_tts_b200 import _lib
-lib = _lib.load()
+lib = _lib.load_debug()
 torch.cuda.set_device(0)
 
 def run(name, cta2, grid, n, ksteps, reps, nacc, a_lbo, a_kadv, b_lbo, b_kadv, b_off=96 * 1024):

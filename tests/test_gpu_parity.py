@@ -3,8 +3,10 @@ reference-made golden vectors, on identical inputs and identical injected noise.
 
 Tolerances (relative L2, checked on the NORMALISED x0 as well as on the returned mel, because the
 denormalised mel has a large DC offset that flatters the ratio — SURVEY.md §7):
-  fp32 mode: north_star bar 1e-3; this suite asserts 1e-4.
-  bf16 mode: stated tolerance 2e-2 on normalised x0, 3e-3 on the denormalised mel.
+  fp32 mode (CUDA cores, exact fp32 operands): north_star bar 1e-3; this suite asserts 1e-4.
+  fp16 mode (the reference-precision mode ON THE TENSOR CORES: fp16 operands = TF32's significand, fp32 accumulate and
+             streams): asserts the north_star fp32 bar, 1e-3 on normalised x0 (measured 2.5-4.5e-4), 1e-4 on the mel.
+  bf16 mode: stated tolerance 8e-3 on normalised x0 (measured 3.4e-3), 1e-3 on the denormalised mel (measured 2.8e-4).
 """
 import ctypes as C
 
@@ -19,13 +21,13 @@ from helpers import GOLDEN_CASES, TRAIN_CASES, TRAIN_KEYS, Case, golden_case, lo
 
 pytestmark = pytest.mark.gpu
 
-TOL = {"fp32": dict(norm=1e-4, mel=1e-4), "bf16": dict(norm=2e-2, mel=3e-3)}
+TOL = {"fp32": dict(norm=1e-4, mel=1e-4), "fp16": dict(norm=1e-3, mel=1e-4), "bf16": dict(norm=8e-3, mel=1e-3)}
 
 
 def available_precisions():
     lib = _lib.load()
     dims = _lib.ModelDims(80, 256, 256, 20, 0)
-    return [p for p, code in (("fp32", 0), ("bf16", 1)) if lib.mgb_packed_bytes(C.byref(dims), code) > 0]
+    return [p for p, code in (("fp32", 0), ("bf16", 1), ("fp16", 3)) if lib.mgb_packed_bytes(C.byref(dims), code) > 0]
 
 
 PRECS = available_precisions()
@@ -47,9 +49,14 @@ def test_denoiser_forward_vs_golden_and_oracle(name, precision):
     g, c = load_golden(name), golden_case(name)
     gd = build(c, precision)
     t = torch.from_numpy(g["denoiser_t"]).cuda()
-    out = gd.denoise_fn(cu(c.t("x_T")), t, cu(c.t("cond")).transpose(1, 2), cu(c.t("spk")))
+    with torch.no_grad():            # the inference kernels of this precision
+        out = gd.denoise_fn(cu(c.t("x_T")), t, cu(c.t("cond")).transpose(1, 2), cu(c.t("spk")))
     assert out.shape == g["denoiser_out"].shape
     assert rel_l2(out, g["denoiser_out"]) < TOL[precision]["norm"]
+    # with autograd on (parameters require grad) the same call is the training forward (stash-keeping kernels)
+    out_t = gd.denoise_fn(cu(c.t("x_T")), t, cu(c.t("cond")).transpose(1, 2), cu(c.t("spk")))
+    assert out_t.requires_grad
+    assert rel_l2(out_t, g["denoiser_out"]) < TOL[gd.denoise_fn.train_precision]["norm"]
 
 
 @pytest.mark.parametrize("precision", PRECS)
@@ -183,7 +190,7 @@ def test_sampling_loop_matches_step_by_step_p_sample(precision):
         t = torch.full((c.B,), i, dtype=torch.long, device="cuda")
         x = gd.p_sample(x, t, cond.transpose(1, 2), None, noise=noises[i])
     ref = gd.denorm_spec(x[:, 0].transpose(1, 2)) * (~pad).unsqueeze(-1)
-    assert rel_l2(mel, ref) < (1e-5 if precision == "fp32" else 2e-3)
+    assert rel_l2(mel, ref) < {"fp32": 1e-5, "fp16": 1e-4, "bf16": 2e-3}[precision]
 
 
 @pytest.mark.parametrize("precision", PRECS)

@@ -20,7 +20,7 @@ def _image(mat: torch.Tensor) -> torch.Tensor:
 
 def run_probe(A, Bm, *, n, ksteps, shift=0, swap=False, bulk=True, a_rows=None):
     """A [rows,K] bf16 (rows >= 128+shift), Bm [n,K] bf16.  Returns D [128,n] fp32 and status."""
-    lib = _lib.load()
+    lib = _lib.load_debug()
     dev = A.device
     rows = A.shape[0]
     a_img, b_img = _image(A), _image(Bm)
@@ -86,7 +86,7 @@ def test_row_shift_by_start_address(shift):
 def test_two_cta_pair_conventions(n, ksteps):
     """cta_group::2: M = 256 split by rows across the CTA pair, B split by rows in halves (n/2 each),
     each CTA reads its accumulator rows from its own TMEM; commit multicast reaches both CTAs."""
-    lib = _lib.load()
+    lib = _lib.load_debug()
     K = 16 * ksteps
     g = torch.Generator(device="cpu").manual_seed(n + ksteps)
     A = (torch.randn(256, K, generator=g) * 0.5).bfloat16().cuda()
@@ -113,7 +113,7 @@ def test_aliased_operand_lbo0_sbo0(n):
     """LBO = SBO = 0 makes every 8-row group and both k-chunks of the A operand read the SAME 128-byte core
     matrix: A[r][k] = block[r % 8][k % 8].  The fused kernel uses this as a 128-byte "ones" operand that adds the
     convolution bias inside the MMA."""
-    lib = _lib.load()
+    lib = _lib.load_debug()
     g = torch.Generator(device="cpu").manual_seed(n)
     block = (torch.randn(8, 8, generator=g) * 0.5).bfloat16().cuda()
     Bm = (torch.randn(n, 16, generator=g) * 0.5).bfloat16().cuda()
@@ -146,7 +146,7 @@ def test_mn_major_operands(which, n, ksteps, shift):
     """MN-major (no swizzle) operands as the weight-gradient GEMMs of the training path read them: the activation image
     [C/8][frames][8] with the FRAME axis as K.  Convention pinned here: LBO = 128 B (next 8-frame group), SBO = byte
     stride between 8-channel chunks, K advance of one MMA (16 frames) = 256 B, a +16 B start = one frame later."""
-    lib = _lib.load()
+    lib = _lib.load_debug()
     K = 16 * ksteps
     Kp = K + 8                                  # room for the shifted read
     g = torch.Generator(device="cpu").manual_seed(n + ksteps + shift)
@@ -175,7 +175,7 @@ def test_mn_major_operands(which, n, ksteps, shift):
 def test_bulk_copy_size_sets_the_shared_memory_fill_rate():
     """The finding behind the tensor-map TMA boxes: one cp.async.bulk costs ~60-110 cycles of TMA-engine time
     whatever its size, so a ring refilled with 2 KB copies fills at a fraction of the rate of one refilled with 32 KB copies."""
-    lib = _lib.load()
+    lib = _lib.load_debug()
     src = torch.zeros(32 << 20, dtype=torch.uint8, device="cuda")
     st = torch.zeros(1, dtype=torch.int32, device="cuda")
     stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)

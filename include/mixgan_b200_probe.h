@@ -40,6 +40,12 @@ int mgb_probe_umma_rate(int cta2, int grid, int n, int ksteps, int reps, int nac
                         int a_kadv, int b_lbo, int b_sbo, int b_kadv, int b_off, long long* cycles_out,
                         int* status_out, void* stream);
 
+/* mgb_probe_umma_rate with a choice of operand contents (fill: 0 = zeros, 1 = pseudo-random values in (-1, 1)) and operand
+ * format (fp16: 0 = bf16, 1 = fp16). */
+int mgb_probe_umma_rate_data(int cta2, int grid, int n, int ksteps, int reps, int nacc, int a_lbo, int a_sbo,
+                             int a_kadv, int b_lbo, int b_sbo, int b_kadv, int b_off, int fill, int fp16,
+                             long long* cycles_out, int* status_out, void* stream);
+
 /* Bulk-copy ingest-rate probe (scripts/bulk_rate.py): `grid` CTAs each stream iters * copies_per_slot copies of copy_bytes
  * from `src` (device, src_bytes long, L2-resident when small) into a `slots`-deep shared-memory ring; cycles_out[i] = SM
  * cycles CTA i needed.  Measures how the per-SM shared-memory fill rate depends on the size of one cp.async.bulk. */

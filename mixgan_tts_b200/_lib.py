@@ -59,6 +59,7 @@ PROBE_SIGNATURES = {
     "mgb_probe_umma_2cta": (_I, [_P, _I, _P, _I] + [_I] * 8 + [_P, _P, _P]),
     "mgb_probe_bulk_rate": (_I, [_P, C.c_longlong, _I, _I, _I, _I, _I, _P, _P, _P]),
     "mgb_probe_umma_rate": (_I, [_I] * 13 + [_P, _P, _P]),
+    "mgb_probe_umma_rate_data": (_I, [_I] * 15 + [_P, _P, _P]),
 }
 
 _lib = None

@@ -162,17 +162,20 @@ __device__ __forceinline__ float round_op(float v) {   // the value an operand o
 }
 // 2 sigmoid(a) tanh(f) from ah = a/2 and f.  bf16 mode: tanh(ah) tanh(f) + tanh(f) with two MUFU.TANH (2^-11).
 // fp16 mode: with E1 = e^a, E2 = e^2f the same quantity is 2 E1 (E2 - 1) / ((E1 + 1)(E2 + 1)): two MUFU.EX2 (2^-22) and one
-// division; the arguments are clamped to +-40 where tanh and sigmoid are 0 / 1 to fp32 precision and the product of the
-// two denominators stays finite.
+// division; the exponents are clamped at 40 from above, where tanh and sigmoid are 1 to fp32 precision and the product of
+// the two denominators stays finite (towards -inf the exponentials flush to 0, which is the right limit).
 template <bool F16>
 __device__ __forceinline__ float gate_fn(float ah, float f) {
   if (F16) {
-    const float x1 = fminf(fmaxf(ah, -20.f), 20.f) * 2.8853900817779268f;   // 2 log2(e)
-    const float x2 = fminf(fmaxf(f, -20.f), 20.f) * 2.8853900817779268f;
+    // only the upper clamp is needed: E -> 0 is harmless, E -> inf would make inf / inf
+    const float x1 = fminf(ah * 2.8853900817779268f, 57.7f);   // 2 log2(e) ah, e^a <= e^40
+    const float x2 = fminf(f * 2.8853900817779268f, 57.7f);
     float e1, e2;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(x1));
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e2) : "f"(x2));
-    return __fdividef(2.f * e1 * (e2 - 1.f), (e1 + 1.f) * (e2 + 1.f));
+    float rden;                      // (div.approx without .ftz costs three more instructions of subnormal scaling)
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rden) : "f"((e1 + 1.f) * (e2 + 1.f)));
+    return (e1 + e1) * (e2 - 1.f) * rden;
   }
   const float ta = tanh_approx(ah), tf = tanh_approx(f);
   return fmaf(ta, tf, tf);
@@ -930,7 +933,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_p
           }
         }
       }
-    } else if (!first_group && !F16) {                  // fetch the earlier groups' skip sum before waiting for this group's
+    } else if (!first_group && F16) {                   // fp32 spill: the residual stream is dead in the tail, its registers hold it
+#pragma unroll
+      for (int j4 = 0; j4 < 32; ++j4) {
+        const float4 v = in_seq ? __ldg(reinterpret_cast<const float4*>(static_cast<const float*>(p.S) + row_g * C + 128 * h) + j4)
+                                : make_float4(0.f, 0.f, 0.f, 0.f);
+        u[4 * j4] = v.x; u[4 * j4 + 1] = v.y; u[4 * j4 + 2] = v.z; u[4 * j4 + 3] = v.w;
+      }
+    } else if (!first_group) {                          // fetch the earlier groups' skip sum before waiting for this group's
       const uint4* sp = reinterpret_cast<const uint4*>(static_cast<const __half*>(p.S) + row_g * C + 128 * h);
 #pragma unroll
       for (int i = 0; i < 16; ++i) sraw[i] = in_seq ? __ldg(sp + i) : make_uint4(0u, 0u, 0u, 0u);
@@ -981,12 +991,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_p
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj) {
           float v[8];
-          if (!first_group && F16) {    // fp32 spill, read here (L2-resident: the previous launch has just written it)
-            const float4* sp = reinterpret_cast<const float4*>(static_cast<const float*>(p.S) + row_g * C + 128 * h + 32 * cc + 8 * jj);
-            const float4 o0 = in_seq ? __ldg(sp) : make_float4(0.f, 0.f, 0.f, 0.f), o1 = in_seq ? __ldg(sp + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
-            const float o[8] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
+          if (!first_group && F16) {    // fp32 spill, fetched into u[] above
 #pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] = (__uint_as_float(a[jj * 8 + e]) + o[e]) * inv_sqrt_l;
+            for (int e = 0; e < 8; ++e) v[e] = (__uint_as_float(a[jj * 8 + e]) + u[32 * cc + 8 * jj + e]) * inv_sqrt_l;
           } else if (!first_group) {    // + the earlier groups' skip sum (the blocks' skip biases live in the skip-projection bias)
             const uint4 o = sraw[4 * cc + jj];
             const uint32_t w4[4] = {o.x, o.y, o.z, o.w};
@@ -1429,7 +1436,7 @@ int bf16_prepare(const mgb_model_dims& d, const void* packed, const int64_t* t, 
 #ifdef MGB_DEBUG_BUILD
 // Debug library only (libmixgan_b200_dbg.so): MGB_PROFILE=1 runs the PROF instantiation of the bf16 kernel and prints the
 // per-role wait counters; it allocates and synchronises, which the product library never does.
-static int run_profiled(FusedParams& p, const CUtensorMap& tm_cond, bool kuni, int npairs, cudaStream_t s) {
+static int run_profiled(FusedParams& p, const CUtensorMap& tm_cond, bool kuni, bool f16, int npairs, cudaStream_t s) {
       const int ncta = 2 * npairs;
       long long* dprof = nullptr;
       cudaMalloc(&dprof, (size_t)ncta * 320 * sizeof(long long));
@@ -1437,8 +1444,15 @@ static int run_profiled(FusedParams& p, const CUtensorMap& tm_cond, bool kuni, i
       p.prof = dprof;
       cudaFuncSetAttribute(fused_pair_kernel<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL);
       cudaFuncSetAttribute(fused_pair_kernel<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL);
-      if (kuni) fused_pair_kernel<true, true, false><<<ncta, NTHREADS, SMEM_TOTAL, s>>>(p, tm_cond);
-      else fused_pair_kernel<true, false, false><<<ncta, NTHREADS, SMEM_TOTAL, s>>>(p, tm_cond);
+      cudaFuncSetAttribute(fused_pair_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL);
+      cudaFuncSetAttribute(fused_pair_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL);
+      if (f16) {
+        if (kuni) fused_pair_kernel<true, true, true><<<ncta, NTHREADS, SMEM_TOTAL, s>>>(p, tm_cond);
+        else fused_pair_kernel<true, false, true><<<ncta, NTHREADS, SMEM_TOTAL, s>>>(p, tm_cond);
+      } else {
+        if (kuni) fused_pair_kernel<true, true, false><<<ncta, NTHREADS, SMEM_TOTAL, s>>>(p, tm_cond);
+        else fused_pair_kernel<true, false, false><<<ncta, NTHREADS, SMEM_TOTAL, s>>>(p, tm_cond);
+      }
       cudaStreamSynchronize(s);
       long long* h = (long long*)malloc((size_t)ncta * 320 * sizeof(long long));
       cudaMemcpy(h, dprof, (size_t)ncta * 320 * sizeof(long long), cudaMemcpyDeviceToHost);
@@ -1561,8 +1575,8 @@ int bf16_run(const mgb_model_dims& d, const void* packed, const float* x, const 
 #ifdef MGB_DEBUG_BUILD
     if (debug_mode & 2) { if (g == 0) p.le = p.lb; else p.lb = p.le; }
     if (((debug_mode & 4) && g == 0) || ((debug_mode & 8) && g > 0)) continue;
-    if (do_prof && !f16) {
-      if (int rc = run_profiled(p, tm_cond, kuni, npairs, s)) return rc;
+    if (do_prof) {
+      if (int rc = run_profiled(p, tm_cond, kuni, f16, npairs, s)) return rc;
       note_launch();
       continue;
     }

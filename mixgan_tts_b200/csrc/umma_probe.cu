@@ -2,6 +2,8 @@
 // tcgen05.mma (M=128, N=n, K=16, bf16 -> fp32 in TMEM), result read back with tcgen05.ld.
 // tests/test_umma_probe.py uses it to pin the shared-memory descriptor conventions of tc05.cuh
 // (LBO/SBO meaning, +16 B row shift of the start address, K advance) against a host matmul.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 #include "../../include/mixgan_b200_probe.h"
 #include "tc05.cuh"
@@ -172,6 +174,8 @@ struct RateArgs {
   int a_lbo, a_sbo, b_lbo, b_sbo, a_kadv, b_kadv, b_off, n, ksteps, reps, nacc;
   long long* cycles;   // [gridDim.x]
   int* status;
+  int fill;            // 0: zero operands; 1: pseudo-random values in (-1, 1) (operand toggling as in a real GEMM)
+  int fp16;            // operand format: 0 bf16, 1 fp16
 };
 
 template <bool CTA2>
@@ -182,6 +186,15 @@ __global__ void __launch_bounds__(128, 1) umma_rate_kernel(const RateArgs p) {
   const int tid = threadIdx.x, warp = tid >> 5;
   const uint32_t rank = CTA2 ? tc::cluster_ctarank() : 0u;
   for (int i = tid; i < (p.b_off * 2) / 16; i += 128) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
+  if (p.fill) {
+    for (int i = tid; i < p.b_off; i += 128) {     // b_off * 2 bytes = b_off 16-bit operands
+      uint32_t h = (uint32_t)i * 2654435761u + blockIdx.x * 40503u;
+      h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
+      const float v = (float)(int)(h & 0xFFFFu) * (1.f / 32768.f) - 1.f;
+      if (p.fp16) reinterpret_cast<__half*>(smem)[i] = __float2half_rn(v);
+      else reinterpret_cast<__nv_bfloat16*>(smem)[i] = __float2bfloat16_rn(v);
+    }
+  }
   if (warp == 0) { if (CTA2) tc::tmem_alloc_2cta<512>(&tmem_slot); else tc::tmem_alloc<512>(&tmem_slot); }
   if (tid == 32) { tc::mbar_init(&bar_mma, 1); tc::fence_barrier_init(); }
   tc::fence_proxy_async_smem();
@@ -192,7 +205,7 @@ __global__ void __launch_bounds__(128, 1) umma_rate_kernel(const RateArgs p) {
   const uint32_t tmem = tmem_slot;
   long long cyc = 0;
   if (rank == 0 && warp == 0) {
-    const uint32_t idesc = tc::make_idesc_bf16(CTA2 ? 256 : 128, p.n);
+    const uint32_t idesc = tc::make_idesc_16(CTA2 ? 256 : 128, p.n, p.fp16 != 0);
     const uint32_t a0 = tc::smem_u32(smem), b0 = tc::smem_u32(smem + p.b_off);
     const uint64_t ad = tc::make_smem_desc(a0, p.a_lbo, p.a_sbo), bd = tc::make_smem_desc(b0, p.b_lbo, p.b_sbo);
     const long long t0 = clock64();
@@ -274,9 +287,20 @@ extern "C" int mgb_probe_umma_2cta(const void* a_img, int a_bytes, const void* b
 // Issue-rate probe (scripts/umma_rate.py): runs `grid` CTAs (or CTA pairs when cta2) each issuing
 // reps*ksteps tcgen05.mma on zeroed operands; cycles_out[i] = SM cycles of leader CTA i from first issue to
 // commit completion.  Operand regions: A at 0, B at b_off (each b_off bytes, <= 100 KB).
+extern "C" int mgb_probe_umma_rate_data(int cta2, int grid, int n, int ksteps, int reps, int nacc, int a_lbo, int a_sbo,
+                                        int a_kadv, int b_lbo, int b_sbo, int b_kadv, int b_off, int fill, int fp16,
+                                        long long* cycles_out, int* status_out, void* stream);
 extern "C" int mgb_probe_umma_rate(int cta2, int grid, int n, int ksteps, int reps, int nacc, int a_lbo, int a_sbo,
                                    int a_kadv, int b_lbo, int b_sbo, int b_kadv, int b_off, long long* cycles_out,
                                    int* status_out, void* stream) {
+  return mgb_probe_umma_rate_data(cta2, grid, n, ksteps, reps, nacc, a_lbo, a_sbo, a_kadv, b_lbo, b_sbo, b_kadv, b_off, 0, 0,
+                                  cycles_out, status_out, stream);
+}
+// The same probe with a choice of operand contents (fill: 0 zeros, 1 pseudo-random values) and operand format (fp16: 0 bf16,
+// 1 fp16): tensor-pipe throughput on B200 depends on operand toggling once the board is power-managed.
+extern "C" int mgb_probe_umma_rate_data(int cta2, int grid, int n, int ksteps, int reps, int nacc, int a_lbo, int a_sbo,
+                                        int a_kadv, int b_lbo, int b_sbo, int b_kadv, int b_off, int fill, int fp16,
+                                        long long* cycles_out, int* status_out, void* stream) {
   MGB_REQUIRE(cycles_out && status_out, MGB_E_ARG, "NULL pointer argument");
   MGB_REQUIRE(n >= 16 && n <= 256 && n % 16 == 0 && ksteps >= 1 && reps >= 1 && nacc >= 1 && nacc * n <= 512, MGB_E_ARG,
               "bad n/ksteps/reps/nacc");
@@ -285,6 +309,7 @@ extern "C" int mgb_probe_umma_rate(int cta2, int grid, int n, int ksteps, int re
   RateArgs p{};
   p.a_lbo = a_lbo; p.a_sbo = a_sbo; p.b_lbo = b_lbo; p.b_sbo = b_sbo; p.a_kadv = a_kadv; p.b_kadv = b_kadv;
   p.b_off = b_off; p.n = n; p.ksteps = ksteps; p.reps = reps; p.nacc = nacc; p.cycles = cycles_out; p.status = status_out;
+  p.fill = fill; p.fp16 = fp16;
   const size_t smem = (size_t)2 * b_off;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(cta2 ? 2 * grid : grid);

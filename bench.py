@@ -1,17 +1,25 @@
 #!/usr/bin/env python
 """Benchmark of the reverse-diffusion hot path (BASELINE.json metric: mel frames/sec).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--precision bf16|fp32] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--precision bf16|fp16|fp32] [--impl reference]
+                    [--workload sample|c3|c4|train] [--no-sub] [--no-cpu-baseline]
 
 A "step" is one full reverse diffusion (all K_diff Denoiser calls + posterior updates + denorm/mask)
-over one synthetic batch.  Workload at any N: BASELINE configs[1] — LJSpeech `naive`, K_diff=4,
+over one synthetic batch.  Headline workload at any N: BASELINE configs[1] — LJSpeech `naive`, K_diff=4,
 B=64 utterances x T=800 frames per GPU (weak scaling: utterances shard across ranks with no
-collective on the data path).  One JSON line is printed by rank 0.
+collective on the data path).  ONE JSON line is printed by rank 0.
 
   value     mel frames/s with inputs resident in HBM (device-timed with CUDA events, max over ranks)
   e2e       the same metric through the public module API with HOST (pinned) inputs: H2D copy of
             cond + mask, on-device noise draw, D2H read of the mel, all inside the timed region
-  roofline  the dominant kernel against the measured tensor peak (MEASURED_PEAKS.json)
+  roofline  the dominant kernel against the measured tensor peak (MEASURED_PEAKS.json): its duration is measured IN SITU,
+            inside the timed region, by the kernel itself (%globaltimer, min start / max end over its CTAs per launch)
+  sub       the other BASELINE configurations on the same box, each a small record with the same meaning of value / e2e:
+              fp32_parity  configs[1] at the REFERENCE's precision bar (1e-3): the same fused tcgen05 kernel with fp16 operands
+              c3           configs[2]: 512 utterances, `shallow` K=1, STRONG scaling over the N ranks
+              c4           configs[3]: AISHELL3 shallow multi-speaker, B=32 x T=1500 per GPU
+              train        configs[4] (Denoiser part): training step, data-parallel gradient all-reduce over NCCL
+              elementwise  achieved HBM GB/s of the fused elementwise kernels against the measured copy bandwidth
   cpu_baseline  the CPU oracle port timed on this box's host cores on a bounded sample (rank 0, N=1)
 
 `--impl reference` times the reference's CPU implementation of the path (the torch-CPU oracle port;
@@ -33,31 +41,22 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 FLOPS_PER_FRAME_STEP = 23_805_952          # SURVEY.md §8d / BASELINE.md §3 (algorithmic, no halo)
-CONV_FLOPS_PER_FRAME_STEP = 786_432        # the k=3 conv alone (dominant kernel of the fp32 path)
+CONV_FLOPS_PER_FRAME_STEP = 786_432        # the k=3 conv alone (dominant kernel of the CUDA-core fp32 path)
 B_PER_GPU, T_FRAMES, K_DIFF = 64, 800, 4   # BASELINE configs[1]
 CPU_SAMPLE_B = 16                          # BASELINE configs[0] shape for the CPU legs
 METRIC, UNIT = "mel_frames_per_sec", "frames/s"
+SM_COUNT, FLOP_PER_CLK_SM = 148, 8192      # kind::f16: 128 x 256 x 16 MACs per 128 cycles per SM
 
 
-def ncu_traffic(B, T):
-    """dram bytes per launch of the dominant kernel from the committed ncu --set full capture (same workload), or None."""
-    import glob
-    if (B, T) != (B_PER_GPU, T_FRAMES):
-        return None
-    for p in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*", "ncu_traffic.json")), reverse=True):
-        try:
-            return float(json.load(open(p))["mean_bytes_per_launch"])
-        except Exception:
-            continue
-    return None
-
-
-def peaks():
+def peaks(region_s: float):
+    """Measured peaks; the tensor denominator is the burst figure for a timed region under 1 s, the sustained one above."""
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         d = json.load(open(p))
-        return {"tensor_tflops": float(d["bf16_tflops_sustained"]), "hbm_gbs": float(d["hbm_gbs"]),
-                "source": "MEASURED_PEAKS.json (bf16_tflops_sustained: kernel timed inside a long step)"}
+        burst = region_s < 1.0
+        return {"tensor_tflops": float(d["bf16_tflops"] if burst else d["bf16_tflops_sustained"]), "hbm_gbs": float(d["hbm_gbs"]),
+                "source": "MEASURED_PEAKS.json " + ("bf16_tflops (burst: timed region %.2f s < 1 s)" % region_s if burst else
+                                                    "bf16_tflops_sustained (timed region %.2f s >= 1 s)" % region_s)}
     return {"tensor_tflops": 1400.0, "hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md)"}
 
 
@@ -142,6 +141,33 @@ def cpu_oracle_throughput(repeats: int, B: int = CPU_SAMPLE_B):
                       f"best of {len(times)} after warm-up, {best:.2f} s per pass, torch {torch.__version__}"}, times
 
 
+def cpu_oracle_train_throughput(B: int):
+    """The oracle's training branch + torch autograd on all host threads, one step at the same shape."""
+    import torch
+    from mixgan_tts_b200 import configs, synth
+    from oracle.diffusion import DiffusionOracle
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    _, _, mc, _ = configs.make_configs("LJSpeech", "naive")
+    W = synth.make_denoiser_weights(0)
+    orc = DiffusionOracle(W, model="naive", denoiser_cfg=mc["denoiser"], spec_min=[configs.SPEC_MIN] * 80, spec_max=[configs.SPEC_MAX] * 80)
+    inp, ex, pr = synth.make_inputs(77, B, T_FRAMES, K_DIFF), synth.make_train_extras(78, B, T_FRAMES, K_DIFF), synth.grad_probe(79, B, T_FRAMES)
+    tt = lambda a: torch.from_numpy(a)
+    Wt = {k: tt(v).requires_grad_(True) for k, v in W.items()}
+    best = None
+    for _ in range(2):
+        t0 = time.perf_counter()
+        cond = tt(inp["cond"]).requires_grad_(True)
+        out = orc.forward_training_graph(tt(ex["mel"]), cond, None, tt(inp["pad_mask"]), t=tt(ex["t"]).clone(), noise_t=tt(ex["noise_t"]),
+                                         noise_prev=tt(ex["noise_prev"]), post_noise=tt(ex["post_noise"]), W=Wt)
+        ((out[0] * tt(pr["r0"])).sum() + (out[3] * tt(pr["r1"])).sum()).backward()
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return {"value": B * T_FRAMES / best, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"one training-branch step (forward + autograd backward, no optimizer) at B={B} x T={T_FRAMES}, fp32 torch-CPU oracle, "
+                      f"best of 2, {best:.2f} s, torch {torch.__version__}"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -173,42 +199,73 @@ def run_reference(args):
 
 
 # ---------------------------------------------------------------------------------------------
-def run_ours(args):
-    import torch
-    import torch.distributed as dist
+class Ctx:
+    """Process-wide state of one bench run: rank / device / process group."""
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        if self.world > 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("nccl", device_id=self.dev)
 
-    from mixgan_tts_b200 import GaussianDiffusion, _lib, configs, synth
-    from mixgan_tts_b200.modules import PRECISIONS
-    lib = _lib.load()
-    dims0 = _lib.ModelDims(80, 256, 256, 20, 0)
-    prec = args.precision
-    if prec == "auto":
-        prec = "bf16" if lib.mgb_packed_bytes(C.byref(dims0), _lib.PREC_BF16) > 0 else "fp32"
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
 
-    cfg = configs.make_configs("LJSpeech", "naive")
+    def timed(self, fn, steps, warmup):
+        """`warmup` untimed + exactly `steps` timed calls of fn(i), barrier + synchronize on both sides, CUDA events,
+        max over ranks.  Returns milliseconds for the `steps` calls."""
+        from mixgan_tts_b200 import shard
+        torch = self.torch
+        for i in range(warmup):
+            fn(i)
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        self.barrier()
+        return shard.max_over_ranks(e0.elapsed_time(e1), self.dev)
+
+    def close(self):
+        if self.world > 1:
+            self.dist.destroy_process_group()
+
+
+def make_gd(ctx, dataset, model, multi, prec, train=False):
+    from mixgan_tts_b200 import GaussianDiffusion, configs, synth
+    torch = ctx.torch
+    cfg = configs.make_configs(dataset, model, multi)
     gd = GaussianDiffusion(*cfg, precision=prec)
-    W = synth.make_denoiser_weights(0)
+    W = synth.make_denoiser_weights(0 if not multi else 7, multi_speaker=multi)
     gd.denoise_fn.load_state_dict({k: torch.from_numpy(v) for k, v in W.items()})
-    gd = gd.to(dev).eval()
-    B, T, K = args.batch, T_FRAMES, gd.num_timesteps
-    den = gd.denoise_fn
+    gd = gd.to(ctx.dev)
+    return gd.train() if train else gd.eval()
 
-    # Rotating input sets so that no step finds its inputs in L2 (3 x ~134 MB > 126 MB L2).
-    NSETS = 3
+
+def bench_sample(ctx, prec, steps, warmup, B, with_clocks=False):
+    """BASELINE configs[1] at one precision: resident value, in-situ kernel time, end-to-end value."""
+    from mixgan_tts_b200 import _lib, synth
+    from mixgan_tts_b200.pipeline import BatchSynthesizer
+    torch, dev, lib = ctx.torch, ctx.dev, _lib.load()
+    gd = make_gd(ctx, "LJSpeech", "naive", False, prec)
+    T, K = T_FRAMES, gd.num_timesteps
+    den = gd.denoise_fn
+    NSETS = 3       # rotating input sets so that no step finds its inputs in L2 (3 x ~134 MB > 126 MB L2)
     sets = []
     for i in range(NSETS):
-        inp = synth.make_inputs(1234 + 17 * i + 1000 * rank, B, T, K)
+        inp = synth.make_inputs(1234 + 17 * i + 1000 * ctx.rank, B, T, K)
         sets.append({"cond": torch.from_numpy(inp["cond"]).to(dev), "pad": torch.from_numpy(inp["pad_mask"]).to(dev),
                      "x_T": torch.from_numpy(inp["x_T"]).to(dev), "noises": torch.from_numpy(inp["noises"]).to(dev)})
     set_bytes = sum(v.numel() * v.element_size() for v in sets[0].values())
@@ -218,158 +275,269 @@ def run_ours(args):
         s = sets[i % NSETS]
         return gd._sample_core(s["cond"], None, s["x_T"], s["noises"], pad_u8[i % NSETS], want_states=False)[0]
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # ------------------------------------------------------------------ device-resident timing
-    for i in range(max(args.warmup, 3)):
+    tc_mode = prec in ("bf16", "fp16")
+    sampler = ClockSampler(ctx.local) if (with_clocks and ctx.rank == 0) else None
+    for i in range(warmup):
         step_resident(i)
-    barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
+    ctx.barrier()
+    if sampler:
         sampler.start()
+    lib.mgb_profile_enable(2 if tc_mode else 1)       # in-situ %globaltimer stamps (two atomics per CTA) / events for the fp32 path
     launches0 = lib.mgb_launch_count()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    ev0.record()
-    for i in range(args.steps):
-        step_resident(i)
-    ev1.record()
-    barrier()
+    ms_total = ctx.timed(step_resident, steps, 0)
     launches = lib.mgb_launch_count() - launches0
-    ms_total = ev0.elapsed_time(ev1)
-
-    # dominant-kernel duration: a short separate pass in which the library brackets every launch of the fused
-    # kernel with CUDA events on the launching stream (kept out of the pass above: the events cost a few us each)
-    prof_steps = min(args.steps, 4)
-    lib.mgb_profile_enable(1)
-    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    p0.record()
-    for i in range(prof_steps):
-        step_resident(i)
-    p1.record()
-    torch.cuda.synchronize()
-    ms_prof_pass = p0.elapsed_time(p1)
-    ktot, kcnt = C.c_float(0), C.c_int(0)
-    _lib.check(lib.mgb_profile_collect(C.byref(ktot), C.byref(kcnt)), "mgb_profile_collect")
+    ktot, kcnt, kmin, kmax, kmhz = C.c_float(0), C.c_int(0), C.c_float(0), C.c_float(0), C.c_float(0)
+    if tc_mode:   # the stamps of the first (up to) 256 launches of the timed region
+        ws = den.workspace(B, T, K, dev)
+        _lib.check(lib.mgb_profile_read_stamps(_lib.ptr(ws), C.byref(ktot), C.byref(kcnt), C.byref(kmin), C.byref(kmax), C.byref(kmhz)),
+                   "mgb_profile_read_stamps")
+        timed_calls = K * min(steps, max(kcnt.value // (2 * K), 1))
+    else:
+        _lib.check(lib.mgb_profile_collect(C.byref(ktot), C.byref(kcnt)), "mgb_profile_collect")
+        timed_calls = K * steps
     lib.mgb_profile_enable(0)
 
-    # ------------------------------------------------------------------ end-to-end timing (host buffers)
-    # The public batch-synthesis harness: pinned host cond/mask in, pinned host mel out; the H2D copy of batch i+1
-    # and the D2H copy of batch i-1 overlap the reverse diffusion of batch i.  Every step's copies are inside the
-    # timed region; the noise is drawn on the device inside GaussianDiffusion.forward, as the reference does.
-    from mixgan_tts_b200.pipeline import BatchSynthesizer
+    # end to end: the public batch-synthesis harness, pinned host cond/mask in, pinned host mel out; the H2D copy of batch
+    # i+1 and the D2H copy of batch i-1 overlap the reverse diffusion of batch i.  Every step's copies are inside the timed
+    # region; the noise is drawn on the device inside GaussianDiffusion.forward, as the reference does.
     host = [(s["cond"].cpu().pin_memory(), s["pad"].cpu().pin_memory()) for s in sets]
-    synth_pipe = BatchSynthesizer(gd, dev)
+    pipe = BatchSynthesizer(gd, dev)
 
     def run_e2e(n):
         acc = 0.0
-        for mel in synth_pipe.run(host[i % NSETS] for i in range(n)):
+        for mel in pipe.run(host[i % NSETS] for i in range(n)):
             acc += float(mel[0, 0, 0])          # touch the host result of every step
         return acc
 
     run_e2e(3)
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    run_e2e(args.steps)
-    e1.record()
-    barrier()
-    ms_e2e = e0.elapsed_time(e1)
-    clocks = sampler.stop() if rank == 0 else None
+    ms_e2e = ctx.timed(lambda i: run_e2e(steps), 1, 0)
+    clocks = sampler.stop() if sampler else None
 
-    from mixgan_tts_b200 import shard
-    ms_total = shard.max_over_ranks(ms_total, dev)
-    ms_e2e = shard.max_over_ranks(ms_e2e, dev)
-
-    if rank == 0:
-        pk = peaks()
-        frames_per_step = world * B * T
-        value = frames_per_step * args.steps / (ms_total * 1e-3)
-        e2e_val = frames_per_step * args.steps / (ms_e2e * 1e-3)
-        k_ms = ktot.value / max(kcnt.value, 1)
-        calls = prof_steps * K                      # Denoiser calls in the profiled pass
-        if prec in ("bf16", "fp16"):
-            # one Denoiser call = `launches_per_call` launches of fused_group_kernel (layer groups);
-            # algorithmic FLOPs per launch = FLOPs per call / launches per call
-            per_call = max(kcnt.value // calls, 1)
-            kern = f"fused_pair_kernel (tcgen05 cta_group::2; {per_call} launches = one Denoiser call over the batch)"
-            fl = FLOPS_PER_FRAME_STEP / per_call
-        else:
-            kern, fl = "conv_gemm_kernel<EPI_GATE> (k=3 conv + gate of one block, fp32 CUDA cores)", CONV_FLOPS_PER_FRAME_STEP
-        achieved = fl * B * T / (k_ms * 1e-3) / 1e12 if k_ms > 0 else 0.0
-        valid = float(sum(int((~s["pad"]).sum()) for s in sets)) / NSETS
-        line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": {"bf16": "bf16", "fp16": "f16"}.get(prec, "f32"), "data": "synthetic",
-            "config": {"workload": f"LJSpeech naive K={K} reverse diffusion, B={B} x T={T} per GPU (BASELINE configs[1]), "
-                                   "random-init Denoiser, fixed injected noise",
-                       "precision": prec, "l2": f"inputs rotate over {NSETS} sets of {set_bytes / 1e6:.0f} MB (> 126 MB L2)",
-                       "frames_valid_per_s": value * valid / (B * T), "frame_steps_per_s": value * K,
-                       "rtf_valid_audio": (ms_total / args.steps * 1e-3) / (world * valid * 256 / 22050)},
-            "roofline": {"bound": "tensor", "achieved": achieved, "peak": pk["tensor_tflops"], "unit": "TFLOP/s",
-                         "frac": achieved / pk["tensor_tflops"],
-                         "traffic": ncu_traffic(B, T) if prec == "bf16" else None, "kernel": kern,
-                         "kernel_ms": k_ms, "kernel_launches_timed": kcnt.value,
-                         "kernel_share_of_step": ktot.value / ms_prof_pass if ms_prof_pass > 0 else None,
-                         "whole_step_tflops": FLOPS_PER_FRAME_STEP * K * B * T * args.steps / (ms_total * 1e-3) / 1e12,
-                         "peak_source": pk["source"]},
-            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(B * T * 256 * 4 + B * T),
-                    "d2h_bytes_per_step": int(B * T * 80 * 4), "ms_per_step": ms_e2e / args.steps,
-                    "api": "BatchSynthesizer.run (GaussianDiffusion.forward per batch; pinned host cond/mask in, pinned host mel "
-                           "out; copies of neighbouring batches overlap compute on separate streams)"},
-            "gpu_launches": int(launches), "clocks": clocks,
-        }
-        if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"], _ = cpu_oracle_throughput(8)      # ~10 s of CPU work on the box's host cores
-        else:
-            line["cpu_baseline"] = None
-        print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    frames_per_step = ctx.world * B * T
+    value = frames_per_step * steps / (ms_total * 1e-3)
+    k_ms = ktot.value / max(kcnt.value, 1)
+    per_call = 2 if tc_mode else 1           # layer groups per Denoiser call at this shape (plan_groups)
+    if tc_mode and kcnt.value % (per_call * K) != 0:
+        per_call = max(kcnt.value // max(K * min(steps, 256 // (2 * K)), 1), 1)
+    if tc_mode:
+        kern = (f"fused_pair_kernel<{'fp16' if prec == 'fp16' else 'bf16'} operands> (tcgen05 cta_group::2; {per_call} launches = one "
+                f"Denoiser call over the batch)")
+        fl = FLOPS_PER_FRAME_STEP / per_call
+    else:
+        kern, fl = "conv_gemm_kernel<EPI_GATE> (k=3 conv + gate of one block, fp32 CUDA cores)", CONV_FLOPS_PER_FRAME_STEP
+    achieved = fl * B * T / (k_ms * 1e-3) / 1e12 if k_ms > 0 else 0.0
+    pk = peaks(ms_total * 1e-3)
+    valid = float(sum(int((~s["pad"]).sum()) for s in sets)) / NSETS
+    sm_mhz = kmhz.value if tc_mode and kmhz.value > 0 else None
+    roof = {"bound": "tensor", "achieved": achieved, "peak": pk["tensor_tflops"], "unit": "TFLOP/s",
+            "frac": achieved / pk["tensor_tflops"], "traffic": None,
+            "traffic_note": "not measured by this run; the ncu --set full capture of this kernel is summarised in profiles/r02/",
+            "kernel": kern, "kernel_ms": k_ms, "kernel_ms_min": kmin.value, "kernel_ms_max": kmax.value,
+            "kernel_launches_timed": kcnt.value,
+            "kernel_timing": ("in situ: min(start) / max(end) over each launch's CTAs in %globaltimer, the first "
+                              f"{kcnt.value} launches of the timed region" if tc_mode else "CUDA events around every launch on the launching stream, inside the timed region"),
+            "kernel_share_of_step": (k_ms * per_call * K) / (ms_total / steps) if tc_mode and ms_total > 0 else None,
+            "flops_per_launch": fl * B * T,
+            "whole_step_tflops": FLOPS_PER_FRAME_STEP * K * B * T * steps / (ms_total * 1e-3) / 1e12,
+            "peak_source": pk["source"] + "; kind::f16 issues fp16 and bf16 operands at the same rate (profiles/r02/umma_rate_vs_operand_data.txt)"}
+    if sm_mhz:     # the SM clock the kernel really ran at (clock64 / %globaltimer inside the kernel): nvidia-smi's 50 ms samples
+        # cannot see the millisecond-scale clock drop of a power-managed B200 under tensor load
+        roof["sm_mhz_in_kernel"] = sm_mhz
+        roof["frac_of_cycle_peak_at_kernel_clock"] = achieved * 1e12 / (SM_COUNT * FLOP_PER_CLK_SM * sm_mhz * 1e6)
+    return {
+        "value": value, "ms_per_step": ms_total / steps, "dtype": {"bf16": "bf16", "fp16": "f16"}.get(prec, "f32"),
+        "precision": prec, "K": K, "B": B, "T": T,
+        "l2": f"inputs rotate over {NSETS} sets of {set_bytes / 1e6:.0f} MB (> 126 MB L2)",
+        "frames_valid_per_s": value * valid / (B * T), "frame_steps_per_s": value * K,
+        "rtf_valid_audio": (ms_total / steps * 1e-3) / (ctx.world * valid * 256 / 22050),
+        "roofline": roof,
+        "e2e": {"value": frames_per_step * steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(B * T * 256 * 4 + B * T),
+                "d2h_bytes_per_step": int(B * T * 80 * 4), "ms_per_step": ms_e2e / steps,
+                "api": "BatchSynthesizer.run (GaussianDiffusion.forward per batch; pinned host cond/mask in, pinned host mel "
+                       "out; copies of neighbouring batches overlap compute on separate streams)"},
+        "gpu_launches": int(launches), "clocks": clocks,
+    }
 
 
-# ---------------------------------------------------------------------------------------------
-def run_train(args):
-    """--workload train: BASELINE configs[4] restricted to this repo's path — the diffusion decoder's training branch
-    (GaussianDiffusion.forward with mel given: q_sample x2, Denoiser forward, clamp, posterior sample), backward through
-    the library's Denoiser backward, data-parallel gradient all-reduce (NCCL, bucketed, overlapped with the backward) and
-    a fused Adam step on the Denoiser's parameters.  Per GPU: B=8 utterances x T=800 frames (config/LJSpeech/train.yaml:6).
-    The JCU discriminator / FastSpeech2 encoder of the full training step stay the reference's torch code (out of scope)."""
-    import torch
-    import torch.distributed as dist
+def bench_elementwise(ctx, B=B_PER_GPU, T=T_FRAMES, reps=20):
+    """Achieved HBM GB/s of the fused elementwise kernels either side of the Denoiser (algorithmic bytes / CUDA-event time,
+    inputs rotated over 4 sets so that none is L2-resident), against the measured copy bandwidth."""
+    from mixgan_tts_b200 import _lib
+    torch, dev, lib = ctx.torch, ctx.dev, _lib.load()
+    gd = make_gd(ctx, "LJSpeech", "shallow", False, "bf16")
+    den, M, H = gd.denoise_fn, 80, 256
+    NS = 4
+    g = torch.Generator(device=dev).manual_seed(5)
+    coarse = [torch.randn((B, T, M), device=dev, generator=g) for _ in range(NS)]
+    noise = [torch.randn((B, 1, M, T), device=dev, generator=g) for _ in range(NS)]
+    cond = [torch.randn((B, T, H), device=dev, generator=g) for _ in range(NS)]
+    pad = torch.zeros((B, T), dtype=torch.uint8, device=dev)
+    xT = [torch.empty((B, 1, M, T), device=dev) for _ in range(NS)]
+    mel = [torch.empty((B, T, M), device=dev) for _ in range(NS)]
+    smin = gd.spec_min.detach().float().reshape(-1).contiguous()
+    smax = gd.spec_max.detach().float().reshape(-1).contiguous()
+    ws = den.workspace(B, T, 1, dev)
+    st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    pk = peaks(0.0)["hbm_gbs"]
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
-    from mixgan_tts_b200 import GaussianDiffusion, _lib, configs, synth, shard
+    def t_of(fn):
+        for i in range(3):
+            fn(i)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(reps):
+            fn(i)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    out = {}
+    frames = B * T
+    ms = t_of(lambda i: _lib.check(lib.mgb_shallow_start(_lib.ptr(coarse[i % NS]), _lib.ptr(noise[i % NS]), _lib.ptr(smin), _lib.ptr(smax),
+                                                         0.5, 0.5, _lib.ptr(pad), _lib.ptr(xT[i % NS]), B, T, M, st), "shallow_start"))
+    by = frames * (3 * M * 4 + 1)
+    out["shallow_start_kernel"] = {"bytes": by, "ms": ms, "gbs": by / ms / 1e6, "frac": by / ms / 1e6 / pk}
+    ms = t_of(lambda i: _lib.check(lib.mgb_denorm_mask(_lib.ptr(xT[i % NS]), _lib.ptr(smin), _lib.ptr(smax), _lib.ptr(pad),
+                                                       _lib.ptr(mel[i % NS]), B, T, M, st), "denorm_mask"))
+    by = frames * (2 * M * 4 + 1)
+    out["denorm_mask_kernel"] = {"bytes": by, "ms": ms, "gbs": by / ms / 1e6, "frac": by / ms / 1e6 / pk}
+    ms = t_of(lambda i: _lib.check(lib.mgb_pack_cond(C.byref(den.dims), _lib.PREC_BF16, _lib.ptr(cond[i % NS]), B, T, _lib.ptr(ws),
+                                                     ws.numel(), st), "pack_cond"))
+    by = frames * (H * 4 + H * 2)
+    out["cond_pack_kernel"] = {"bytes": by, "ms": ms, "gbs": by / ms / 1e6, "frac": by / ms / 1e6 / pk}
+    # context: a plain device copy of the same size (these kernels run ~10 us; the 6551 GB/s peak is a 4 GB copy)
+    src = [torch.empty(frames * M, device=dev) for _ in range(NS)]
+    dst = [torch.empty(frames * M, device=dev) for _ in range(NS)]
+    ms = t_of(lambda i: dst[i % NS].copy_(src[i % NS]))
+    by = frames * 2 * M * 4
+    out["torch_copy_same_size_as_denorm"] = {"bytes": by, "ms": ms, "gbs": by / ms / 1e6, "frac": by / ms / 1e6 / pk}
+    out["peak_gbs"] = pk
+    out["note"] = (f"B={B} x T={T}; bytes = algorithmic (fp32 in/out, 16-bit image, 1-byte mask); CUDA events over {reps} launches, "
+                   f"{NS} rotating input sets (> L2)")
+    return out
+
+
+def bench_c3(ctx, prec, steps, warmup):
+    """BASELINE configs[2] / SURVEY 8(d) C3 — LJSpeech `shallow` (aux-decoder mel -> K=1 shallow diffusion), 512 utterances
+    of T=800 sharded contiguously by utterance over the N ranks (STRONG scaling, no collective on the data path), every rank
+    running BatchSynthesizer on its shard with pinned HOST buffers in and out."""
+    from mixgan_tts_b200 import _lib, shard, synth
+    from mixgan_tts_b200.pipeline import BatchSynthesizer
+    torch, dev, lib = ctx.torch, ctx.dev, _lib.load()
+    N_UTT, T = 512, T_FRAMES
+    gd = make_gd(ctx, "LJSpeech", "shallow", False, prec)
+    lo, hi = shard.contiguous_shard(N_UTT, ctx.world, ctx.rank)
+    n_local = hi - lo
+    # Sub-batches: at least 4 per rank so that the pipeline overlaps copies with compute even when a rank owns only 64
+    # utterances (8 GPUs); 64 utterances per batch otherwise.
+    BATCH = max(8, min(64, n_local // 4))
+    # The conditioner crosses the host boundary in the precision the kernels consume it in (bf16 / fp16 operands): the
+    # 16-bit -> fp32 -> 16-bit round trip on the device is exact, so results are bit-identical to passing fp32, and the
+    # host link carries 512 instead of 1024 B per frame.
+    cond_dt = torch.bfloat16 if prec == "bf16" else torch.float16
+    protos = []
+    for i in range(3):   # 3 distinct synthetic 64-utterance blocks, cycled (> L2 per pass)
+        inp = synth.make_inputs(500 + 7 * i + 100 * ctx.rank, 64, T, 1, shallow=True)
+        protos.append((torch.from_numpy(inp["cond"]).to(cond_dt).pin_memory(), torch.from_numpy(inp["pad_mask"]).pin_memory(), None,
+                       torch.from_numpy(inp["coarse_mel"]).pin_memory()))
+    batches = []
+    for k, b0 in enumerate(range(0, n_local, BATCH)):
+        n = min(BATCH, n_local - b0)
+        pr = protos[k % 3]
+        o = (k // 3 * BATCH) % (64 - n + 1)
+        batches.append(tuple(None if t is None else t[o:o + n] for t in pr))
+    pipe = BatchSynthesizer(gd, dev)
+    dev_batches = [tuple(None if t is None else t.to(dev) for t in b) for b in batches]
+
+    def pass_e2e(_):
+        acc = 0.0
+        for mel in pipe.run(iter(batches)):
+            acc += float(mel[0, 0, 0])
+        return acc
+
+    def pass_resident(_):
+        for cond, pad, spk, coarse in dev_batches:
+            gd(None, cond, spk, pad, coarse_mel=coarse)
+
+    n0 = lib.mgb_launch_count()
+    ms = ctx.timed(pass_resident, steps, warmup)
+    launches = lib.mgb_launch_count() - n0
+    ms_e2e = ctx.timed(pass_e2e, steps, warmup)
+    return {"value": N_UTT * T * steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps, "scaling": "strong",
+            "workload": f"LJSpeech shallow K=1 batch synthesis, {N_UTT} utterances x T={T} sharded by utterance over {ctx.world} GPU(s) "
+                        f"in batches of {BATCH} (BASELINE configs[2]); value: inputs resident in HBM (shallow start + K=1 reverse "
+                        "diffusion + denorm per batch, noise drawn on the device)",
+            "precision": prec, "utterances_per_rank": n_local, "batch": BATCH,
+            "e2e": {"value": N_UTT * T * steps / (ms_e2e * 1e-3), "unit": UNIT,
+                    "h2d_bytes_per_step": int(N_UTT * T * (256 * 2 + 80 * 4 + 1)), "d2h_bytes_per_step": int(N_UTT * T * 80 * 4),
+                    "ms_per_step": ms_e2e / steps,
+                    "host_link_gbs_per_gpu": {"h2d": n_local * T * (256 * 2 + 80 * 4 + 1) / (ms_e2e / steps * 1e-3) / 1e9,
+                                              "d2h": n_local * T * 80 * 4 / (ms_e2e / steps * 1e-3) / 1e9},
+                    "api": f"BatchSynthesizer.run on the rank's shard: pinned host cond ({str(cond_dt).split('.')[-1]}, the operand "
+                           "precision of this mode) / mask / coarse mel in, pinned host mel out; copies of neighbouring sub-batches "
+                           "overlap compute"},
+            "gpu_launches": int(launches)}
+
+
+def bench_c4(ctx, prec, steps, warmup):
+    """BASELINE configs[3]: AISHELL3 `shallow` K=1, multi-speaker, B=32 x T=1500 per GPU (weak scaling, replicas)."""
+    from mixgan_tts_b200 import _lib, synth
+    from mixgan_tts_b200.pipeline import BatchSynthesizer
+    torch, dev, lib = ctx.torch, ctx.dev, _lib.load()
+    B, T = 32, 1500
+    gd = make_gd(ctx, "AISHELL3", "shallow", True, prec)
+    host, devb = [], []
+    for i in range(3):
+        inp = synth.make_inputs(900 + 7 * i + 100 * ctx.rank, B, T, 1, multi_speaker=True, shallow=True, min_len_frac=2.0 / 3.0)
+        hb = (torch.from_numpy(inp["cond"]).pin_memory(), torch.from_numpy(inp["pad_mask"]).pin_memory(),
+              torch.from_numpy(inp["spk"]).pin_memory(), torch.from_numpy(inp["coarse_mel"]).pin_memory())
+        host.append(hb)
+        devb.append(tuple(t.to(dev) for t in hb))
+    pipe = BatchSynthesizer(gd, dev)
+
+    def pass_resident(i):
+        cond, pad, spk, coarse = devb[i % 3]
+        gd(None, cond, spk, pad, coarse_mel=coarse)
+
+    n0 = lib.mgb_launch_count()
+    ms = ctx.timed(pass_resident, steps, warmup)
+    launches = lib.mgb_launch_count() - n0
+
+    def run_e2e(n):
+        acc = 0.0
+        for mel in pipe.run(host[i % 3] for i in range(n)):
+            acc += float(mel[0, 0, 0])
+        return acc
+
+    run_e2e(3)
+    ms_e2e = ctx.timed(lambda i: run_e2e(steps), 1, 0)
+    frames = ctx.world * B * T
+    return {"value": frames * steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps, "scaling": "weak", "precision": prec,
+            "workload": f"AISHELL3 shallow K=1, multi-speaker (speaker-embedding conditioning), B={B} x T={T} per GPU (BASELINE configs[3])",
+            "e2e": {"value": frames * steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(B * T * (256 * 4 + 80 * 4 + 1) + B * 256 * 4),
+                    "d2h_bytes_per_step": int(B * T * 80 * 4), "ms_per_step": ms_e2e / steps},
+            "gpu_launches": int(launches)}
+
+
+def bench_train(ctx, prec, steps, warmup, B):
+    """BASELINE configs[4] on this repo's path: the diffusion decoder's training branch (q_sample x2, Denoiser forward, clamp,
+    posterior sample), backward through the library, data-parallel gradient all-reduce (NCCL, bucketed, overlapped with the
+    backward) and a fused Adam step.  Per GPU: B=8 utterances x T=800 frames (config/LJSpeech/train.yaml:6)."""
+    from mixgan_tts_b200 import _lib, synth
     from mixgan_tts_b200.grad_sync import GradSync
-    lib = _lib.load()
-    B, T = args.train_batch, T_FRAMES
-    cfg = configs.make_configs("LJSpeech", "naive")
-    prec = "bf16" if args.precision == "auto" else args.precision
-    gd = GaussianDiffusion(*cfg, precision=prec)
-    gd.denoise_fn.load_state_dict({k: torch.from_numpy(v) for k, v in synth.make_denoiser_weights(0).items()})
-    gd = gd.to(dev).train()
+    torch, dev, lib = ctx.torch, ctx.dev, _lib.load()
+    T = T_FRAMES
+    gd = make_gd(ctx, "LJSpeech", "naive", False, prec, train=True)
     K = gd.num_timesteps
     opt = torch.optim.Adam(gd.denoise_fn.parameters(), lr=1e-5, fused=True)
-    sync = GradSync() if world > 1 else None
+    sync = GradSync() if ctx.world > 1 else None
     NSETS = 3
     sets = []
     for i in range(NSETS):
-        inp = synth.make_inputs(77 + 13 * i + 1000 * rank, B, T, K)
-        ex = synth.make_train_extras(78 + 13 * i + 1000 * rank, B, T, K)
-        pr = synth.grad_probe(79 + 13 * i + 1000 * rank, B, T)
+        inp = synth.make_inputs(77 + 13 * i + 1000 * ctx.rank, B, T, K)
+        ex = synth.make_train_extras(78 + 13 * i + 1000 * ctx.rank, B, T, K)
+        pr = synth.grad_probe(79 + 13 * i + 1000 * ctx.rank, B, T)
         to = lambda a: torch.from_numpy(a).to(dev)
         sets.append({"cond": to(inp["cond"]), "pad": to(inp["pad_mask"]), "mel": to(ex["mel"]), "r0": to(pr["r0"]), "r1": to(pr["r1"])})
 
@@ -384,167 +552,118 @@ def run_train(args):
         opt.step()
         return loss
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    # Data-parallel self-check, visible to the driver: with every random draw fixed, the gradient after a synchronised
+    # backward must equal the mean over the ranks of the local (unsynchronised) gradients of the same step.
+    dp_check = None
+    if ctx.world > 1:
+        fixed = dict(t=torch.arange(B, device=dev) % K, noise_t=torch.full((B, 1, 80, T), 0.25, device=dev),
+                     noise_prev=torch.full((B, 1, 80, T), -0.5, device=dev), post_noise=torch.full((B, 1, 80, T), 0.125, device=dev))
+        s = sets[0]
 
-    def timed(n, **kw):
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for i in range(n):
-            step(i, **kw)
-        e1.record()
-        barrier()
-        return shard.max_over_ranks(e0.elapsed_time(e1), dev)
+        def flat_grad(with_sync):
+            gd.denoise_fn.grad_sync = sync if with_sync else None
+            opt.zero_grad(set_to_none=True)
+            out = gd(s["mel"], s["cond"].detach().requires_grad_(True), None, s["pad"], **{k: v.clone() for k, v in fixed.items()})
+            ((out[0] * s["r0"]).sum() + (out[3] * s["r1"]).sum()).backward()
+            return torch.cat([p.grad.reshape(-1) for p in gd.denoise_fn.parameters()]).clone()
 
-    for i in range(max(args.warmup, 3)):
+        local = flat_grad(False)
+        mean = local.clone()
+        ctx.dist.all_reduce(mean)
+        mean /= ctx.world
+        synced = flat_grad(True)
+        err = float((synced - mean).norm() / mean.norm().clamp_min(1e-30))
+        differs = float((synced - local).norm() / local.norm().clamp_min(1e-30))
+        dp_check = {"synced_vs_mean_of_ranks_rel_l2": err, "synced_vs_local_rel_l2": differs, "ok": bool(err < 1e-5 and differs > 1e-3)}
+        opt.zero_grad(set_to_none=True)
+
+    for i in range(max(warmup, 3)):
         step(i)
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     n0 = lib.mgb_launch_count()
-    ms = timed(args.steps)
+    ms = ctx.timed(step, steps, 0)
     launches = lib.mgb_launch_count() - n0
-    ms_nosync = timed(args.steps, with_sync=False) if world > 1 else ms
-    clocks = sampler.stop() if rank == 0 else None
-    if rank == 0:
-        frames = world * B * T
-        flops = 3 * FLOPS_PER_FRAME_STEP * frames            # forward + data-grad + weight-grad GEMMs
-        line = {"metric": "train_frames_per_sec", "value": frames * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
-                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if prec == "bf16" else "f32", "data": "synthetic",
-                "config": {"precision": prec, "workload": f"LJSpeech naive diffusion-decoder training branch: Denoiser fwd+bwd + fused Adam, B={B} x T={T} "
-                                       "per GPU (BASELINE configs[4] restricted to the Denoiser path), gradient all-reduce over NCCL",
-                           "tflops": flops * args.steps / (ms * 1e-3) / 1e12,
-                           "allreduce_exposed_ms_per_step": (ms - ms_nosync) / args.steps,
-                           "grad_bytes": int(lib.mgb_flat_weight_count(C.byref(gd.denoise_fn.dims))) * 4},
-                "gpu_launches": int(launches), "clocks": clocks}
-        if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_oracle_train_throughput(B)
-        print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    ms_nosync = ctx.timed(lambda i: step(i, with_sync=False), steps, 0) if ctx.world > 1 else ms
+    frames = ctx.world * B * T
+    flops = 3 * FLOPS_PER_FRAME_STEP * frames            # forward + data-grad + weight-grad GEMMs
+    return {"metric": "train_frames_per_sec", "value": frames * steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps,
+            "scaling": "weak", "precision": prec,
+            "workload": f"LJSpeech naive diffusion-decoder training branch: Denoiser fwd+bwd + fused Adam, B={B} x T={T} per GPU "
+                        "(BASELINE configs[4], Denoiser part), gradient all-reduce over NCCL",
+            "tflops": flops * steps / (ms * 1e-3) / 1e12,
+            "allreduce_exposed_ms_per_step": (ms - ms_nosync) / steps,
+            "grad_bytes": int(lib.mgb_flat_weight_count(C.byref(gd.denoise_fn.dims))) * 4,
+            "dp_check": dp_check, "gpu_launches": int(launches)}
 
 
-def run_c3(args):
-    """--workload c3: BASELINE configs[2] / SURVEY 8(d) C3 — LJSpeech `shallow` (aux-decoder mel -> K=1 shallow diffusion),
-    512 utterances of T=800 sharded contiguously by utterance over the N ranks (STRONG scaling, no collective on the data
-    path), every rank running mixgan_tts_b200.pipeline.BatchSynthesizer on its shard in batches of 64 with pinned HOST
-    buffers in and out.  value = 512 * 800 frames / (max over ranks of the device-timed pass)."""
-    import torch
-    import torch.distributed as dist
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
-    from mixgan_tts_b200 import GaussianDiffusion, _lib, configs, synth, shard
-    from mixgan_tts_b200.pipeline import BatchSynthesizer
+# ---------------------------------------------------------------------------------------------
+def run_ours(args):
+    ctx = Ctx()
+    from mixgan_tts_b200 import _lib
     lib = _lib.load()
-    N_UTT, T, BATCH = 512, T_FRAMES, 64
-    cfg = configs.make_configs("LJSpeech", "shallow")
-    gd = GaussianDiffusion(*cfg, precision="bf16" if args.precision == "auto" else args.precision)
-    gd.denoise_fn.load_state_dict({k: torch.from_numpy(v) for k, v in synth.make_denoiser_weights(0).items()})
-    gd = gd.to(dev).eval()
-    lo, hi = shard.contiguous_shard(N_UTT, world, rank)
-    # the shard's utterances as pinned host batches (3 distinct synthetic batches, cycled: > L2 per pass)
-    protos = []
-    for i in range(3):
-        inp = synth.make_inputs(500 + 7 * i + 100 * rank, BATCH, T, 1, shallow=True)
-        protos.append(tuple(torch.from_numpy(inp[k]).pin_memory() for k in ("cond", "pad_mask")) + (None,)
-                      + (torch.from_numpy(inp["coarse_mel"]).pin_memory(),))
-    batches = []
-    for b0 in range(lo, hi, BATCH):
-        n = min(BATCH, hi - b0)
-        pr = protos[(b0 // BATCH) % 3]
-        batches.append(tuple(None if t is None else t[:n] for t in pr))
-    pipe = BatchSynthesizer(gd, dev)
-    dev_batches = [tuple(None if t is None else t.to(dev) for t in b) for b in batches]
+    dims0 = _lib.ModelDims(80, 256, 256, 20, 0)
+    prec = args.precision
+    if prec == "auto":
+        prec = "bf16" if lib.mgb_packed_bytes(C.byref(dims0), _lib.PREC_BF16) > 0 else "fp32"
+    warmup = max(args.warmup, 3)
+    sub_steps = max(3, min(args.steps, 20))
+    tc_prec = prec if prec in ("bf16", "fp16") else "bf16"
 
-    def pass_e2e():
-        acc = 0.0
-        for mel in pipe.run(iter(batches)):
-            acc += float(mel[0, 0, 0])
-        return acc
+    if args.workload in ("c3", "c4", "train"):
+        if args.workload == "c3":
+            r = bench_c3(ctx, tc_prec, args.steps, warmup)
+        elif args.workload == "c4":
+            r = bench_c4(ctx, tc_prec, args.steps, warmup)
+        else:
+            r = bench_train(ctx, prec if prec in ("bf16", "fp32") else "bf16", args.steps, warmup, args.train_batch)
+        if ctx.rank == 0:
+            line = {"metric": r.pop("metric", METRIC), "value": r.pop("value"), "unit": r.pop("unit"), "n_gpus": ctx.world,
+                    "steps": args.steps, "warmup": warmup, "ms_per_step": r.pop("ms_per_step"), "higher_is_better": True,
+                    "scaling": r.pop("scaling"), "vs_baseline": None,
+                    "dtype": {"bf16": "bf16", "fp16": "f16"}.get(r.get("precision"), "f32"), "data": "synthetic",
+                    "config": {"workload": r.pop("workload")}}
+            if "e2e" in r:
+                line["e2e"] = r.pop("e2e")
+            line["gpu_launches"] = r.pop("gpu_launches")
+            line["config"].update(r)
+            if args.workload == "train" and ctx.world == 1 and not args.no_cpu_baseline:
+                line["cpu_baseline"] = cpu_oracle_train_throughput(args.train_batch)
+            print(json.dumps(line))
+        ctx.close()
+        return
 
-    def pass_resident():
-        for cond, pad, spk, coarse in dev_batches:
-            gd(None, cond, spk, pad, coarse_mel=coarse)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(fn):
-        for _ in range(max(args.warmup, 3)):
-            fn()
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(args.steps):
-            fn()
-        e1.record()
-        barrier()
-        return shard.max_over_ranks(e0.elapsed_time(e1), dev)
-
-    n0 = lib.mgb_launch_count()
-    ms = timed(pass_resident)
-    launches = lib.mgb_launch_count() - n0
-    ms_e2e = timed(pass_e2e)
-    if rank == 0:
-        val = N_UTT * T * args.steps / (ms * 1e-3)
-        print(json.dumps({
-            "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16",
-            "data": "synthetic",
-            "config": {"workload": f"LJSpeech shallow K=1 batch synthesis, {N_UTT} utterances x T={T} sharded by utterance over "
-                                   f"{world} GPU(s) in batches of {BATCH} (BASELINE configs[2]); value: inputs resident in HBM "
-                                   "(shallow start + K=1 reverse diffusion + denorm per batch, noise drawn on the device)",
-                       "utterances_per_rank": hi - lo},
-            "e2e": {"value": N_UTT * T * args.steps / (ms_e2e * 1e-3), "unit": UNIT,
-                    "h2d_bytes_per_step": int(N_UTT * T * (256 * 4 + 80 * 4 + 1)), "d2h_bytes_per_step": int(N_UTT * T * 80 * 4),
-                    "ms_per_step": ms_e2e / args.steps,
-                    "api": "BatchSynthesizer.run on the rank's shard: pinned host cond / mask / coarse mel in, pinned host mel out; "
-                           "the H2D copy of a 64-utterance batch (69 MB) takes longer than its compute, so this arm is PCIe-bound"},
-            "gpu_launches": int(launches)}))
-    if world > 1:
-        dist.destroy_process_group()
-
-
-def cpu_oracle_train_throughput(B: int):
-    """The oracle's training branch + torch autograd on all host threads, one step at the same shape."""
-    import torch
-    from mixgan_tts_b200 import configs, synth
-    from oracle.diffusion import DiffusionOracle
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    _, _, mc, _ = configs.make_configs("LJSpeech", "naive")
-    W = synth.make_denoiser_weights(0)
-    orc = DiffusionOracle(W, model="naive", denoiser_cfg=mc["denoiser"], spec_min=[configs.SPEC_MIN] * 80, spec_max=[configs.SPEC_MAX] * 80)
-    inp, ex, pr = synth.make_inputs(77, B, T_FRAMES, K_DIFF), synth.make_train_extras(78, B, T_FRAMES, K_DIFF), synth.grad_probe(79, B, T_FRAMES)
-    tt = lambda a: torch.from_numpy(a)
-    Wt = {k: tt(v).requires_grad_(True) for k, v in W.items()}
-    best = None
-    for _ in range(2):
-        t0 = time.perf_counter()
-        cond = tt(inp["cond"]).requires_grad_(True)
-        out = orc.forward_training_graph(tt(ex["mel"]), cond, None, tt(inp["pad_mask"]), t=tt(ex["t"]).clone(), noise_t=tt(ex["noise_t"]),
-                                         noise_prev=tt(ex["noise_prev"]), post_noise=tt(ex["post_noise"]), W=Wt)
-        ((out[0] * tt(pr["r0"])).sum() + (out[3] * tt(pr["r1"])).sum()).backward()
-        dt = time.perf_counter() - t0
-        best = dt if best is None else min(best, dt)
-    return {"value": B * T_FRAMES / best, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"one training-branch step (forward + autograd backward, no optimizer) at B={B} x T={T_FRAMES}, fp32 torch-CPU oracle, "
-                      f"best of 2, {best:.2f} s, torch {torch.__version__}"}
+    head = bench_sample(ctx, prec, args.steps, warmup, args.batch, with_clocks=True)
+    sub = {}
+    if not args.no_sub:
+        if prec == "bf16":
+            sub["fp32_parity"] = dict(
+                bench_sample(ctx, "fp16", sub_steps, warmup, args.batch),
+                note="configs[1] at the reference's precision bar: fused tcgen05 kernel with fp16 operands (TF32's 11-bit significand), "
+                     "fp32 accumulate / streams / spills; tests/test_gpu_parity.py asserts <= 1e-3 relative L2 on the normalised x0 "
+                     "against the reference-made goldens (measured 4.3e-4; bf16 mode 3.4e-3)")
+        sub["elementwise"] = bench_elementwise(ctx)
+        ctx.barrier()
+        sub["c3"] = bench_c3(ctx, tc_prec, sub_steps, warmup)
+        sub["c4"] = bench_c4(ctx, tc_prec, sub_steps, warmup)
+        sub["train"] = bench_train(ctx, "bf16" if prec != "fp32" else "fp32", sub_steps, warmup, args.train_batch)
+    if ctx.rank == 0:
+        K, B, T = head["K"], head["B"], head["T"]
+        line = {
+            "metric": METRIC, "value": head["value"], "unit": UNIT, "n_gpus": ctx.world, "steps": args.steps,
+            "warmup": warmup, "ms_per_step": head["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": head["dtype"], "data": "synthetic",
+            "config": {"workload": f"LJSpeech naive K={K} reverse diffusion, B={B} x T={T} per GPU (BASELINE configs[1]), "
+                                   "random-init Denoiser, fixed injected noise",
+                       "precision": prec, "l2": head["l2"], "frames_valid_per_s": head["frames_valid_per_s"],
+                       "frame_steps_per_s": head["frame_steps_per_s"], "rtf_valid_audio": head["rtf_valid_audio"]},
+            "roofline": head["roofline"], "e2e": head["e2e"], "gpu_launches": head["gpu_launches"], "clocks": head["clocks"],
+            "sub": sub,
+        }
+        if ctx.world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"], _ = cpu_oracle_throughput(8)      # ~10 s of CPU work on the box's host cores
+        else:
+            line["cpu_baseline"] = None
+        print(json.dumps(line))
+    ctx.close()
 
 
 def main():
@@ -556,16 +675,13 @@ def main():
     ap.add_argument("--precision", default="auto", choices=["auto", "bf16", "fp16", "fp32"])
     ap.add_argument("--batch", type=int, default=B_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="sample", choices=["sample", "train", "c3"],
-                    help="sample = the headline reverse-diffusion benchmark; train = Denoiser training step (configs[4] path); "
-                         "c3 = 512-utterance shallow-diffusion batch synthesis, strong scaling (configs[2])")
+    ap.add_argument("--no-sub", action="store_true",
+                    help="headline record only (skip the fp32_parity / c3 / c4 / train / elementwise sub-records)")
+    ap.add_argument("--workload", default="sample", choices=["sample", "train", "c3", "c4"],
+                    help="sample = the headline reverse-diffusion benchmark (+ sub-records); train / c3 / c4 = that configuration as its own line")
     ap.add_argument("--train-batch", type=int, default=8)
     args = ap.parse_args()
-    if args.workload == "train" and args.impl == "ours":
-        run_train(args)
-    elif args.workload == "c3" and args.impl == "ours":
-        run_c3(args)
-    elif args.impl == "reference":
+    if args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)

@@ -97,6 +97,14 @@ long long mgb_launch_count(void);
 void mgb_note_launches(long long n);
 void mgb_profile_enable(int on);
 int mgb_profile_collect(float* total_ms, int* count);
+/* mgb_profile_enable(2): IN-SITU timing instead — each of the first 256 launches of the fused tensor-core kernel after the
+ * enable records min(start) / max(end) over its CTAs in %globaltimer nanoseconds, and the SM cycles / nanoseconds of its
+ * first CTA, into a fixed region of the caller's workspace (two atomics per CTA, no extra launches, no events).
+ * mgb_profile_read_stamps reads the region back from that workspace after the caller has synchronised the stream (this
+ * instrumentation call does a blocking device-to-host copy): summed launch duration, number of launches recorded, their
+ * min / max, and the SM clock the kernels really ran at (cycles / ns; each of the last three may be NULL). */
+int mgb_profile_read_stamps(const void* workspace, float* total_ms, int* count, float* min_ms, float* max_ms,
+                            float* sm_mhz);
 
 /* Debug: synchronously read the watchdog word of the bf16 path from a workspace that was used with
  * the same (B, T).  0 = every kernel completed its barrier protocol; non-zero bits name the warp
@@ -147,6 +155,12 @@ int mgb_sample(const mgb_model_dims* dims, int precision, const void* packed,
                const float* sched, int K, int clip, const float* spec_min, const float* spec_max,
                const uint8_t* pad_mask, float* states_out, float* mel_out, float* x0_norm_out,
                int B, int T, void* workspace, size_t workspace_bytes, void* stream);
+
+/* The tensor-core paths read the conditioner as a 16-bit image on the batch row axis (8-channel chunks, zero rows between
+ * utterances).  Every sampling / Denoiser call builds it itself; this entry runs only that HBM-bound conversion (fp32
+ * [B][T][d_encoder] -> image inside `workspace`), so that a host can time it — bench.py reports its GB/s. */
+int mgb_pack_cond(const mgb_model_dims* dims, int precision, const float* cond, int B, int T, void* workspace,
+                  size_t workspace_bytes, void* stream);
 
 /* x_T[B][n_mel][T] = (sqrt_acp * norm_spec(coarse)^T + sqrt_1m_acp * noise) * (1 - pad_mask). */
 int mgb_shallow_start(const float* coarse, const float* noise, const float* spec_min,

@@ -32,6 +32,8 @@ SIGNATURES = {
     "mgb_note_launches": (None, [C.c_longlong]),
     "mgb_profile_enable": (None, [_I]),
     "mgb_profile_collect": (_I, [C.POINTER(C.c_float), C.POINTER(C.c_int)]),
+    "mgb_profile_read_stamps": (_I, [_P, C.POINTER(C.c_float), C.POINTER(C.c_int), C.POINTER(C.c_float), C.POINTER(C.c_float),
+                                     C.POINTER(C.c_float)]),
     "mgb_debug_status": (_I, [_D, _I, _I, _I, _P, C.POINTER(C.c_int)]),
     "mgb_device_check": (_I, [_I]),
     "mgb_flat_weight_count": (_Z, [_D]),
@@ -48,6 +50,7 @@ SIGNATURES = {
     "mgb_train_segment_range": (_I, [_D, _I, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
     "mgb_denoiser_train_forward": (_I, [_D, _I, _P, _P, _P, _P, _P, _P, _P, _P, _Z, _I, _I, _P, _Z, _P]),
     "mgb_denoiser_backward": (_I, [_D, _I, _P, _P, _Z, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _Z, _P]),
+    "mgb_pack_cond": (_I, [_D, _I, _P, _I, _I, _P, _Z, _P]),
     "mgb_shallow_start": (_I, [_P, _P, _P, _P, _F, _F, _P, _P, _I, _I, _I, _P]),
     "mgb_denorm_mask": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P]),
     "mgb_length_regulate": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _Z, _P]),

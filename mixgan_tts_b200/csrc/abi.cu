@@ -17,8 +17,12 @@ static std::vector<cudaEvent_t> g_prof_events;  // begin/end pairs
 
 void note_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+static std::atomic<long long> g_stamp_seq{0};
+bool stamp_mode() { return g_prof_on.load(std::memory_order_relaxed) == 2; }
+long long stamp_next(int add) { return g_stamp_seq.fetch_add(add, std::memory_order_relaxed); }
+
 static void prof_record(cudaStream_t s) {
-  if (!g_prof_on.load(std::memory_order_relaxed)) return;
+  if (g_prof_on.load(std::memory_order_relaxed) != 1) return;
   cudaEvent_t e;
   if (cudaEventCreate(&e) != cudaSuccess) return;
   cudaEventRecord(e, s);
@@ -57,55 +61,124 @@ __global__ void fill_i64_kernel(int64_t* p, int n, int64_t v) {
   if (i < n) p[i] = v;
 }
 
+// The two transposing elementwise kernels are HBM-bound (2 or 3 x 320 B per frame).  One block owns TF consecutive frames
+// of one utterance over ALL mel bins: the [frames][M] side of the tile is then one contiguous run of TF * M floats (moved
+// as 16-byte vectors), the [M][frames] side is M runs of TF floats (16-byte vectors when T % 4 == 0).  The transpose goes
+// through a padded shared-memory tile.  Arithmetic is written with explicit round-to-nearest intrinsics in the reference's
+// operation order (no FMA contraction): results are bit-identical to the torch expression ((v + 1) / 2 is computed as
+// (v + 1) * 0.5, the same correctly rounded value; the division by (max - min) stays an IEEE division).
+// MT = n_mel as a compile-time constant (80: index arithmetic without integer divisions) or 0 = runtime M.
+constexpr int EW_TF = 64;        // frames per block
+constexpr int EW_MAXM = 128;     // dims_supported: n_mel <= 128
+constexpr int EW_THREADS = 256;
+
 // x_T[b][m][t] = (sa * norm(coarse[b][t][m]) + sn * noise[b][m][t]) * valid[b][t]
 // norm_spec: (x - min) / (max - min) * 2 - 1  (diffusion.py:228-229); q_sample diffusion.py:150-153
-__global__ void shallow_start_kernel(const float* __restrict__ coarse, const float* __restrict__ noise,
+template <int MT>
+__global__ void __launch_bounds__(EW_THREADS) shallow_start_kernel(const float* __restrict__ coarse, const float* __restrict__ noise,
                                      const float* __restrict__ smin, const float* __restrict__ smax,
                                      float sa, float sn, const uint8_t* __restrict__ pad,
-                                     float* __restrict__ xT, int M, int T) {
-  __shared__ float tile[32][33];
-  const int b = blockIdx.z, t0 = blockIdx.x * 32, m0 = blockIdx.y * 32;
-  for (int r = threadIdx.y; r < 32; r += blockDim.y) {  // read coarse rows t, coalesced over m
-    const int t = t0 + r, m = m0 + threadIdx.x;
-    float v = 0.f;
-    if (t < T && m < M) {
-      const float c = coarse[((size_t)b * T + t) * M + m];
-      v = __fsub_rn(__fmul_rn(__fdiv_rn(__fsub_rn(c, smin[m]), __fsub_rn(smax[m], smin[m])), 2.f), 1.f);
+                                     float* __restrict__ xT, int Mrt, int T) {
+  __shared__ float tile[MT ? MT : EW_MAXM][EW_TF + 1];     // [m][t]
+  __shared__ float s_lo[MT ? MT : EW_MAXM], s_span[MT ? MT : EW_MAXM], s_valid[EW_TF];
+  const int M = MT ? MT : Mrt;
+  const int b = blockIdx.y, t0 = blockIdx.x * EW_TF;
+  const int nt = min(EW_TF, T - t0);
+  for (int i = threadIdx.x; i < M; i += EW_THREADS) { s_lo[i] = smin[i]; s_span[i] = __fsub_rn(smax[i], smin[i]); }
+  for (int i = threadIdx.x; i < nt; i += EW_THREADS) s_valid[i] = (pad && pad[(size_t)b * T + t0 + i]) ? 0.f : 1.f;
+  __syncthreads();
+  const size_t row0 = ((size_t)b * T + t0) * M;      // contiguous run of nt * M floats of coarse
+  const int n = nt * M;
+  auto norm = [&](float c, int m) { return __fsub_rn(__fmul_rn(__fdiv_rn(__fsub_rn(c, s_lo[m]), s_span[m]), 2.f), 1.f); };
+  if ((reinterpret_cast<uintptr_t>(coarse + row0) & 15) == 0 && (M & 3) == 0) {   // a float4 never straddles two frames
+    const float4* src = reinterpret_cast<const float4*>(coarse + row0);
+    for (int i = threadIdx.x; i < n / 4; i += EW_THREADS) {
+      const float4 v = __ldg(src + i);
+      const int t = (4 * i) / M, m = 4 * i - t * M;
+      tile[m][t] = norm(v.x, m); tile[m + 1][t] = norm(v.y, m + 1); tile[m + 2][t] = norm(v.z, m + 2); tile[m + 3][t] = norm(v.w, m + 3);
     }
-    tile[r][threadIdx.x] = v;
+  } else {
+    for (int idx = threadIdx.x; idx < n; idx += EW_THREADS) {
+      const int t = idx / M, m = idx - t * M;
+      tile[m][t] = norm(coarse[row0 + idx], m);
+    }
   }
   __syncthreads();
-  for (int r = threadIdx.y; r < 32; r += blockDim.y) {  // write rows m, coalesced over t
-    const int m = m0 + r, t = t0 + threadIdx.x;
-    if (t < T && m < M) {
-      const size_t o = ((size_t)b * M + m) * T + t;
-      const float q = __fadd_rn(__fmul_rn(sa, tile[threadIdx.x][r]), __fmul_rn(sn, noise[o]));
-      const float valid = (pad && pad[(size_t)b * T + t]) ? 0.f : 1.f;
-      xT[o] = q * valid;
+  const bool vec = (T & 3) == 0 && (nt & 3) == 0 && ((reinterpret_cast<uintptr_t>(noise) | reinterpret_cast<uintptr_t>(xT)) & 15) == 0;
+  if (vec) {
+    const int q = nt / 4;
+    for (int i = threadIdx.x; i < M * q; i += EW_THREADS) {
+      const int m = i / q, tq = (i - m * q) * 4;
+      const size_t o = ((size_t)b * M + m) * T + t0 + tq;
+      const float4 nz = __ldg(reinterpret_cast<const float4*>(noise + o));
+      float4 r;
+      r.x = __fadd_rn(__fmul_rn(sa, tile[m][tq]), __fmul_rn(sn, nz.x)) * s_valid[tq];
+      r.y = __fadd_rn(__fmul_rn(sa, tile[m][tq + 1]), __fmul_rn(sn, nz.y)) * s_valid[tq + 1];
+      r.z = __fadd_rn(__fmul_rn(sa, tile[m][tq + 2]), __fmul_rn(sn, nz.z)) * s_valid[tq + 2];
+      r.w = __fadd_rn(__fmul_rn(sa, tile[m][tq + 3]), __fmul_rn(sn, nz.w)) * s_valid[tq + 3];
+      *reinterpret_cast<float4*>(xT + o) = r;
+    }
+  } else {
+    for (int i = threadIdx.x; i < M * nt; i += EW_THREADS) {
+      const int m = i / nt, t = i - m * nt;
+      const size_t o = ((size_t)b * M + m) * T + t0 + t;
+      xT[o] = __fadd_rn(__fmul_rn(sa, tile[m][t]), __fmul_rn(sn, noise[o])) * s_valid[t];
     }
   }
 }
 
 // mel[b][t][m] = ((x[b][m][t] + 1) / 2 * (max - min) + min) * valid[b][t]   (diffusion.py:231-232)
-__global__ void denorm_mask_kernel(const float* __restrict__ x, const float* __restrict__ smin,
+template <int MT>
+__global__ void __launch_bounds__(EW_THREADS) denorm_mask_kernel(const float* __restrict__ x, const float* __restrict__ smin,
                                    const float* __restrict__ smax, const uint8_t* __restrict__ pad,
-                                   float* __restrict__ mel, int M, int T) {
-  __shared__ float tile[32][33];
-  const int b = blockIdx.z, t0 = blockIdx.x * 32, m0 = blockIdx.y * 32;
-  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
-    const int m = m0 + r, t = t0 + threadIdx.x;
-    tile[r][threadIdx.x] = (m < M && t < T) ? x[((size_t)b * M + m) * T + t] : 0.f;
-  }
-  __syncthreads();
-  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
-    const int t = t0 + r, m = m0 + threadIdx.x;
-    if (t < T && m < M) {
-      const float v = tile[threadIdx.x][r];
-      const float dn = __fadd_rn(__fmul_rn(__fdiv_rn(__fadd_rn(v, 1.f), 2.f), __fsub_rn(smax[m], smin[m])), smin[m]);
-      const float valid = (pad && pad[(size_t)b * T + t]) ? 0.f : 1.f;
-      mel[((size_t)b * T + t) * M + m] = dn * valid;
+                                   float* __restrict__ mel, int Mrt, int T) {
+  __shared__ float tile[MT ? MT : EW_MAXM][EW_TF + 1];     // [m][t]
+  __shared__ float s_lo[MT ? MT : EW_MAXM], s_span[MT ? MT : EW_MAXM], s_valid[EW_TF];
+  const int M = MT ? MT : Mrt;
+  const int b = blockIdx.y, t0 = blockIdx.x * EW_TF;
+  const int nt = min(EW_TF, T - t0);
+  for (int i = threadIdx.x; i < M; i += EW_THREADS) { s_lo[i] = smin[i]; s_span[i] = __fsub_rn(smax[i], smin[i]); }
+  for (int i = threadIdx.x; i < nt; i += EW_THREADS) s_valid[i] = (pad && pad[(size_t)b * T + t0 + i]) ? 0.f : 1.f;
+  const bool vec = (T & 3) == 0 && (nt & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+  if (vec) {
+    const int q = nt / 4;
+    for (int i = threadIdx.x; i < M * q; i += EW_THREADS) {
+      const int m = i / q, tq = (i - m * q) * 4;
+      const float4 v = __ldg(reinterpret_cast<const float4*>(x + ((size_t)b * M + m) * T + t0 + tq));
+      tile[m][tq] = v.x; tile[m][tq + 1] = v.y; tile[m][tq + 2] = v.z; tile[m][tq + 3] = v.w;
+    }
+  } else {
+    for (int i = threadIdx.x; i < M * nt; i += EW_THREADS) {
+      const int m = i / nt, t = i - m * nt;
+      tile[m][t] = x[((size_t)b * M + m) * T + t0 + t];
     }
   }
+  __syncthreads();
+  const size_t row0 = ((size_t)b * T + t0) * M;
+  const int n = nt * M;
+  auto value = [&](int m, int t) {
+    return __fadd_rn(__fmul_rn(__fmul_rn(__fadd_rn(tile[m][t], 1.f), 0.5f), s_span[m]), s_lo[m]) * s_valid[t];
+  };
+  if ((reinterpret_cast<uintptr_t>(mel + row0) & 15) == 0 && (M & 3) == 0) {
+    float4* dst = reinterpret_cast<float4*>(mel + row0);
+    for (int i = threadIdx.x; i < n / 4; i += EW_THREADS) {
+      const int t = (4 * i) / M, m = 4 * i - t * M;
+      dst[i] = make_float4(value(m, t), value(m + 1, t), value(m + 2, t), value(m + 3, t));
+    }
+  } else {
+    for (int idx = threadIdx.x; idx < n; idx += EW_THREADS) {
+      const int t = idx / M, m = idx - t * M;
+      mel[row0 + idx] = value(m, t);
+    }
+  }
+}
+
+static void launch_denorm_mask(const float* x, const float* smin, const float* smax, const uint8_t* pad, float* mel, int B, int M,
+                               int T, cudaStream_t s) {
+  dim3 grid((T + EW_TF - 1) / EW_TF, B), block(EW_THREADS);
+  if (M == 80) denorm_mask_kernel<80><<<grid, block, 0, s>>>(x, smin, smax, pad, mel, M, T);
+  else denorm_mask_kernel<0><<<grid, block, 0, s>>>(x, smin, smax, pad, mel, M, T);
+  note_launch();
 }
 
 // ---- LengthRegulator: exclusive scan of clamped durations, then a gather -----------------------
@@ -192,7 +265,32 @@ void mgb_profile_enable(int on) {
   std::lock_guard<std::mutex> lk(g_prof_mu);
   for (cudaEvent_t e : g_prof_events) cudaEventDestroy(e);
   g_prof_events.clear();
-  g_prof_on.store(on ? 1 : 0);
+  g_stamp_seq.store(0);
+  g_prof_on.store(on == 2 ? 2 : on ? 1 : 0);
+}
+
+int mgb_profile_read_stamps(const void* workspace, float* total_ms, int* count, float* min_ms, float* max_ms, float* sm_mhz) {
+  MGB_REQUIRE(workspace && total_ms && count, MGB_E_ARG, "NULL pointer argument");
+  const int n = bf16_max_stamps();
+  std::vector<unsigned long long> h(4 * (size_t)n);
+  MGB_CUDA_CHECK(cudaMemcpy(h.data(), static_cast<const uint8_t*>(workspace) + bf16_stamps_offset(), h.size() * 8,
+                            cudaMemcpyDeviceToHost));
+  double total = 0, lo = 1e30, hi = 0;
+  int c = 0;
+  for (int i = 0; i < n; ++i) {
+    if (h[i] == ~0ull || h[n + i] <= h[i]) continue;       // launch slot not used by the last call
+    const double ms = (double)(h[n + i] - h[i]) * 1e-6;
+    total += ms; lo = ms < lo ? ms : lo; hi = ms > hi ? ms : hi; ++c;
+  }
+  *total_ms = (float)total; *count = c;
+  if (min_ms) *min_ms = c ? (float)lo : 0.f;
+  if (max_ms) *max_ms = (float)hi;
+  if (sm_mhz) {
+    double cyc = 0, ns = 0;
+    for (int i = 0; i < n; ++i) { cyc += (double)h[2 * (size_t)n + i]; ns += (double)h[3 * (size_t)n + i]; }
+    *sm_mhz = ns > 0 ? (float)(cyc / ns * 1e3) : 0.f;
+  }
+  return MGB_OK;
 }
 
 int mgb_profile_collect(float* total_ms, int* count) {
@@ -309,12 +407,9 @@ int mgb_sample(const mgb_model_dims* dims, int precision, const void* packed, co
   float* xa = reinterpret_cast<float*>(tail + tbytes);
   float* xb = reinterpret_cast<float*>(tail + tbytes + xbytes);
   const size_t mel_elems = (size_t)B * T * M;
-  dim3 tgrid((T + 31) / 32, (M + 31) / 32, B), tblock(32, 8);
 
-  if (states_out) {  // sampling() returns the start state too (diffusion.py:160,164)
-    denorm_mask_kernel<<<tgrid, tblock, 0, s>>>(x_T, spec_min, spec_max, nullptr, states_out, M, T);
-    note_launch();
-  }
+  if (states_out)    // sampling() returns the start state too (diffusion.py:160,164)
+    launch_denorm_mask(x_T, spec_min, spec_max, nullptr, states_out, B, M, T, s);
   const float* cur = x_T;
   const bool bf16 = prec_is_tc(precision), f16 = precision == MGB_PREC_FP16;
   if (bf16) {   // cond image and the per-step tables of all K steps, once
@@ -337,14 +432,9 @@ int mgb_sample(const mgb_model_dims* dims, int precision, const void* packed, co
     }
     if (rc) return rc;
     cur = nxt;
-    if (states_out) {
-      denorm_mask_kernel<<<tgrid, tblock, 0, s>>>(cur, spec_min, spec_max, nullptr,
-                                                  states_out + (size_t)(n + 1) * mel_elems, M, T);
-      note_launch();
-    }
+    if (states_out) launch_denorm_mask(cur, spec_min, spec_max, nullptr, states_out + (size_t)(n + 1) * mel_elems, B, M, T, s);
   }
-  denorm_mask_kernel<<<tgrid, tblock, 0, s>>>(cur, spec_min, spec_max, pad_mask, mel_out, M, T);
-  note_launch();
+  launch_denorm_mask(cur, spec_min, spec_max, pad_mask, mel_out, B, M, T, s);
   if (x0_norm_out)
     MGB_CUDA_CHECK(cudaMemcpyAsync(x0_norm_out, cur, (size_t)B * M * T * sizeof(float),
                                    cudaMemcpyDeviceToDevice, s));
@@ -429,15 +519,29 @@ int mgb_train_debug_status(const mgb_model_dims* dims, int B, int T, const void*
   return MGB_OK;
 }
 
+int mgb_pack_cond(const mgb_model_dims* dims, int precision, const float* cond, int B, int T, void* workspace,
+                  size_t workspace_bytes, void* stream) {
+  MGB_REQUIRE(dims_supported(dims) && cond && workspace && B > 0 && T > 0, MGB_E_ARG, "bad argument");
+  MGB_REQUIRE(prec_is_tc(precision), MGB_E_ARG, "mgb_pack_cond: only the tensor-core precisions keep a conditioner image");
+  MGB_REQUIRE(workspace_bytes >= mgb_workspace_bytes(dims, precision, B, T, 1), MGB_E_WORKSPACE, "workspace too small");
+  if (int rc = check_arch()) return rc;
+  return bf16_pack_cond(*dims, cond, B, T, workspace, static_cast<cudaStream_t>(stream), precision == MGB_PREC_FP16);
+}
+
 int mgb_shallow_start(const float* coarse, const float* noise, const float* spec_min, const float* spec_max,
                       float sqrt_acp, float sqrt_1m_acp, const uint8_t* pad_mask, float* x_T, int B, int T,
                       int n_mel, void* stream) {
   MGB_REQUIRE(coarse && noise && spec_min && spec_max && x_T, MGB_E_ARG, "NULL pointer argument");
   MGB_REQUIRE(B > 0 && T > 0 && n_mel > 0, MGB_E_ARG, "bad shape");
   if (int rc = check_arch()) return rc;
-  dim3 grid((T + 31) / 32, (n_mel + 31) / 32, B), block(32, 8);
-  shallow_start_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(
-      coarse, noise, spec_min, spec_max, sqrt_acp, sqrt_1m_acp, pad_mask, x_T, n_mel, T);
+  MGB_REQUIRE(n_mel <= EW_MAXM, MGB_E_UNSUPPORTED, "n_mel %d > %d", n_mel, EW_MAXM);
+  dim3 grid((T + EW_TF - 1) / EW_TF, B), block(EW_THREADS);
+  if (n_mel == 80)
+    shallow_start_kernel<80><<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(
+        coarse, noise, spec_min, spec_max, sqrt_acp, sqrt_1m_acp, pad_mask, x_T, n_mel, T);
+  else
+    shallow_start_kernel<0><<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(
+        coarse, noise, spec_min, spec_max, sqrt_acp, sqrt_1m_acp, pad_mask, x_T, n_mel, T);
   note_launch();
   MGB_LAUNCH_CHECK();
   return MGB_OK;
@@ -448,10 +552,8 @@ int mgb_denorm_mask(const float* x, const float* spec_min, const float* spec_max
   MGB_REQUIRE(x && spec_min && spec_max && mel, MGB_E_ARG, "NULL pointer argument");
   MGB_REQUIRE(B > 0 && T > 0 && n_mel > 0, MGB_E_ARG, "bad shape");
   if (int rc = check_arch()) return rc;
-  dim3 grid((T + 31) / 32, (n_mel + 31) / 32, B), block(32, 8);
-  denorm_mask_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(x, spec_min, spec_max, pad_mask,
-                                                                             mel, n_mel, T);
-  note_launch();
+  MGB_REQUIRE(n_mel <= EW_MAXM, MGB_E_UNSUPPORTED, "n_mel %d > %d", n_mel, EW_MAXM);
+  launch_denorm_mask(x, spec_min, spec_max, pad_mask, mel, B, n_mel, T, static_cast<cudaStream_t>(stream));
   MGB_LAUNCH_CHECK();
   return MGB_OK;
 }

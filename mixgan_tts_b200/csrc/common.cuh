@@ -218,6 +218,11 @@ int bf16_prepare(const mgb_model_dims& d, const void* packed, const int64_t* t, 
 int bf16_run(const mgb_model_dims& d, const void* packed, const float* x, const int64_t* t, int t_uniform, int step,
              int nsteps, const float* noise, const float* sched, int K, int clip, float* x_prev, float* out_x0, int B, int T,
              void* ws, cudaStream_t s, bool f16);
+int bf16_pack_cond(const mgb_model_dims& d, const float* cond, int B, int T, void* ws, cudaStream_t s, bool f16);
+size_t bf16_stamps_offset();   // byte offset (independent of the shape) of the in-situ launch stamps inside the workspace
+int bf16_max_stamps();
+bool stamp_mode();             // mgb_profile_enable(2): the fused kernel records its own start / end in %globaltimer
+long long stamp_next(int add); // launches stamped since mgb_profile_enable(2) (returns the value before adding)
 inline bool prec_is_tc(int precision) { return precision == MGB_PREC_BF16 || precision == MGB_PREC_FP16; }
 
 // ---- elementwise (elementwise.cu) -------------------------------------------------------------

@@ -80,6 +80,7 @@ constexpr int TILE_ROWS = 256;         // rows per CTA pair
 constexpr int MAX_GROUP_LAYERS = 24;
 constexpr int COND_PAD_LO = 32;        // zero rows in front of the cond image (>= MAX_GROUP_LAYERS)
 constexpr int COND_PAD_HI = 288;       // zero rows behind it (>= TILE_ROWS + MAX_GROUP_LAYERS)
+constexpr int MAX_STAMPS = 256;        // launches per sampling call whose in-situ duration can be recorded (steps x layer groups)
 constexpr long long WAIT_CYCLES = 400000000LL;   // ~0.2 s: a protocol bug ends the kernel, never hangs it
 
 // weight-stream slot indices (see pack_images_kernel); each CTA rank has its own image of every slot
@@ -127,10 +128,16 @@ struct FusedParams {
   void* S;                      // [B*T][C] partial skip sum between groups
   int B, T, Tg, R, L, lb, le, V, halo;
   int* status;
+  unsigned long long* tstamp;   // null, or {min over CTAs of the start, max of the end} in %globaltimer ns (mgb_profile_enable(2))
   int debug_mode;               // MGB_DEBUG_MODE: 1 = setup + teardown only (timing experiment)
   long long* prof;              // debug (MGB_PROFILE): per-CTA cycle counters, 16 per CTA
 };
 
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ float tanh_approx(float x) {
   float y;
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -190,6 +197,13 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t
 template <bool PROF, bool KUNI, bool F16>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_pair_kernel(const FusedParams p, const __grid_constant__ CUtensorMap tmCond) {
   const long long t_start = PROF ? clock64() : 0;
+  unsigned long long stamp_ns0 = 0;
+  long long stamp_clk0 = 0;
+  if (p.tstamp && threadIdx.x == 0) {
+    stamp_ns0 = globaltimer_ns();
+    stamp_clk0 = clock64();
+    atomicMin(p.tstamp, stamp_ns0);
+  }
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sA = smem;
   uint8_t* sG = smem + SMEM_A;
@@ -1091,26 +1105,44 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_p
   __syncthreads();
   tc::cluster_sync_all();
   if (warp == 2) tc::tmem_dealloc_2cta<512>(tmem);
+  if (p.tstamp && threadIdx.x == 0) {
+    const unsigned long long ns1 = globaltimer_ns();
+    atomicMax(p.tstamp + MAX_STAMPS, ns1);
+    if (blockIdx.x == 0) {   // SM cycles and wall nanoseconds of one CTA: their ratio is the SM clock this launch really ran at
+      p.tstamp[2 * MAX_STAMPS] = (unsigned long long)(clock64() - stamp_clk0);
+      p.tstamp[3 * MAX_STAMPS] = ns1 - stamp_ns0;
+    }
+  }
 }
 
 // ---- cond [B][T][H] fp32 -> [32][Rp][8] bf16 (or fp16) on the batch row axis (zero rows in the gaps and pads) ----
+// HBM-bound (1 KB read + 512 B written per frame).  A block converts 32 consecutive image rows: the reads are whole 1 KB
+// cond rows (16-byte vectors, coalesced), the writes are, per 8-channel chunk, 32 consecutive 16-byte rows = one contiguous
+// 512-byte run (lane <-> row), after a transpose through shared memory.
 template <bool F16>
-__global__ void cond_pack_kernel(const float* __restrict__ cond, __nv_bfloat16* __restrict__ out, int T, int Tg, int R,
+__global__ void __launch_bounds__(256) cond_pack_kernel(const float* __restrict__ cond, __nv_bfloat16* __restrict__ out, int T, int Tg, int R,
                                  int Rp) {
-  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);   // 8 rows per block, 32 chunks per row
-  const int c8 = threadIdx.x & 31;
-  if (row >= Rp) return;
-  const int g = row - COND_PAD_LO;
-  uint4 v = make_uint4(0u, 0u, 0u, 0u);
-  if (g >= 0 && g < R) {
-    const int b = g / Tg, f = g - b * Tg;
-    if (f < T) {
-      const float4* src = reinterpret_cast<const float4*>(cond + ((size_t)b * T + f) * C + c8 * 8);
-      const float4 a = __ldg(src), c = __ldg(src + 1);
-      v = make_uint4(pack_op<F16>(a.x, a.y), pack_op<F16>(a.z, a.w), pack_op<F16>(c.x, c.y), pack_op<F16>(c.z, c.w));
+  __shared__ uint4 tile[32][33];                         // [row][chunk], padded
+  const int row0 = blockIdx.x * 32;
+  for (int i = threadIdx.x; i < 32 * 32; i += 256) {     // i = row-in-tile * 32 + chunk: a warp reads one cond row
+    const int r = i >> 5, c8 = i & 31;
+    const int g = row0 + r - COND_PAD_LO;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (g >= 0 && g < R) {
+      const int b = g / Tg, f = g - b * Tg;
+      if (f < T) {
+        const float4* src = reinterpret_cast<const float4*>(cond + ((size_t)b * T + f) * C + c8 * 8);
+        const float4 a = __ldg(src), c = __ldg(src + 1);
+        v = make_uint4(pack_op<F16>(a.x, a.y), pack_op<F16>(a.z, a.w), pack_op<F16>(c.x, c.y), pack_op<F16>(c.z, c.w));
+      }
     }
+    tile[r][c8] = v;
   }
-  reinterpret_cast<uint4*>(out)[(size_t)c8 * Rp + row] = v;
+  __syncthreads();
+  for (int i = threadIdx.x; i < 32 * 32; i += 256) {     // i = chunk * 32 + row-in-tile: a warp writes 512 contiguous bytes
+    const int c8 = i >> 5, r = i & 31;
+    if (row0 + r < Rp) reinterpret_cast<uint4*>(out)[(size_t)c8 * Rp + row0 + r] = tile[r][c8];
+  }
 }
 
 // ---- per-utterance constants of the u recurrence ----------------------------------------------------
@@ -1292,7 +1324,7 @@ __global__ void pack_small_kernel(const float* __restrict__ flat, const FlatOffs
 }
 
 struct WorkBf16 {
-  size_t status, condT, tsteps, d, h, dtab, ctab, ktab, k00, kimg, k00img, U, U2, S, total;
+  size_t status, stamps, condT, tsteps, d, h, dtab, ctab, ktab, k00, kimg, k00img, U, U2, S, total;
   int Tg, R, Rp;
 };
 WorkBf16 work_layout(const mgb_model_dims& d, int B, int T, int K, bool f16) {
@@ -1304,6 +1336,7 @@ WorkBf16 work_layout(const mgb_model_dims& d, int B, int T, int K, bool f16) {
   size_t p = 0;
   auto take = [&](size_t bytes) { size_t r = p; p += align_up(bytes, 256); return r; };
   w.status = take(256);                       // first: its offset must not depend on K (mgb_debug_status)
+  w.stamps = take((size_t)4 * MAX_STAMPS * 8);  // second, at a fixed offset: [starts][ends] in %globaltimer ns, [SM cycles][ns] of CTA 0
   w.condT = take((size_t)32 * w.Rp * 16);
   w.tsteps = take((size_t)K * sizeof(int64_t));
   w.d = take(U * C * 4);
@@ -1357,6 +1390,8 @@ size_t bf16_packed_bytes(const mgb_model_dims& d) {
 }
 size_t bf16_workspace_bytes(const mgb_model_dims& d, int B, int T, int K, bool f16) { return work_layout(d, B, T, K > 0 ? K : 1, f16).total; }
 size_t bf16_status_offset(const mgb_model_dims& d, int B, int T) { return work_layout(d, B, T, 1, false).status; }
+size_t bf16_stamps_offset() { mgb_model_dims d{80, 256, 256, 1, 0}; return work_layout(d, 1, 1, 1, false).stamps; }
+int bf16_max_stamps() { return MAX_STAMPS; }
 
 int bf16_pack(const mgb_model_dims& d, const float* flat, void* packed, cudaStream_t s, bool f16) {
   const FlatOffsets f = flat_offsets(d);
@@ -1382,6 +1417,18 @@ int bf16_pack(const mgb_model_dims& d, const float* flat, void* packed, cudaStre
   return MGB_OK;
 }
 
+// The conditioner image alone (mgb_pack_cond: lets a host measure, or pre-run, the HBM-bound conversion by itself).
+int bf16_pack_cond(const mgb_model_dims& d, const float* cond, int B, int T, void* ws, cudaStream_t s, bool f16) {
+  const WorkBf16 w = work_layout(d, B, T, 1, f16);
+  uint8_t* W = static_cast<uint8_t*>(ws);
+  dim3 grid((w.Rp + 31) / 32);
+  if (f16) cond_pack_kernel<true><<<grid, 256, 0, s>>>(cond, reinterpret_cast<__nv_bfloat16*>(W + w.condT), T, w.Tg, w.R, w.Rp);
+  else cond_pack_kernel<false><<<grid, 256, 0, s>>>(cond, reinterpret_cast<__nv_bfloat16*>(W + w.condT), T, w.Tg, w.R, w.Rp);
+  note_launch();
+  MGB_LAUNCH_CHECK();
+  return MGB_OK;
+}
+
 // Once per sampling call (or per Denoiser call): the bf16 cond image and every per-utterance constant.
 //   t != nullptr : one step, per-utterance timesteps t[B] (Denoiser.forward / p_sample)
 //   t == nullptr : `nsteps` steps, step s runs every utterance at timestep s (the sampling loop); the step-embedding
@@ -1400,10 +1447,14 @@ int bf16_prepare(const mgb_model_dims& d, const void* packed, const int64_t* t, 
   const bool uniform = t == nullptr;
   const int U = uniform ? nsteps : B;
   {
-    dim3 grid((w.Rp + 7) / 8);
+    dim3 grid((w.Rp + 31) / 32);
     if (f16) cond_pack_kernel<true><<<grid, 256, 0, s>>>(cond, reinterpret_cast<__nv_bfloat16*>(W + w.condT), T, w.Tg, w.R, w.Rp);
     else cond_pack_kernel<false><<<grid, 256, 0, s>>>(cond, reinterpret_cast<__nv_bfloat16*>(W + w.condT), T, w.Tg, w.R, w.Rp);
     MGB_CUDA_CHECK(cudaMemsetAsync(W + w.status, 0, sizeof(int), s));
+    if (stamp_mode() && stamp_next(0) == 0) { // first call after mgb_profile_enable(2): starts = UINT64_MAX (atomicMin), rest = 0
+      MGB_CUDA_CHECK(cudaMemsetAsync(W + w.stamps, 0xFF, (size_t)MAX_STAMPS * 8, s));
+      MGB_CUDA_CHECK(cudaMemsetAsync(W + w.stamps + (size_t)MAX_STAMPS * 8, 0, (size_t)3 * MAX_STAMPS * 8, s));
+    }
     note_launch();
   }
   const int64_t* tt = t;
@@ -1572,6 +1623,11 @@ int bf16_run(const mgb_model_dims& d, const void* packed, const float* x, const 
     const int npairs = (w.R + p.V - 1) / p.V;
     p.U_in = Ubuf[g & 1];
     p.U_out = Ubuf[(g + 1) & 1];
+    p.tstamp = nullptr;
+    if (stamp_mode()) {                       // the first MAX_STAMPS launches after mgb_profile_enable(2) record themselves
+      const long long stamp_idx = stamp_next(1);
+      if (stamp_idx < MAX_STAMPS) p.tstamp = reinterpret_cast<unsigned long long*>(W + w.stamps) + stamp_idx;
+    }
 #ifdef MGB_DEBUG_BUILD
     if (debug_mode & 2) { if (g == 0) p.le = p.lb; else p.lb = p.le; }
     if (((debug_mode & 4) && g == 0) || ((debug_mode & 8) && g > 0)) continue;

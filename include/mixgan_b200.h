@@ -19,6 +19,7 @@
  *                          autograd through Denoiser.forward     model/modules.py:420-446 (train.py:126-184)
  *   mgb_length_regulate    LengthRegulator.LR / expand / pad     model/linguistic_encoder.py:383-416,
  *                          get_mask_from_lengths                 utils/tools.py:144-153,374-392
+ *   mgb_durations_from_log duration rounding at inference        model/linguistic_encoder.py:310-314
  *
  * Conventions
  *   - Plain pointers and sizes only; no torch types.  All tensors are DEVICE pointers to
@@ -51,7 +52,7 @@
 extern "C" {
 #endif
 
-#define MGB_ABI_VERSION 1
+#define MGB_ABI_VERSION 2
 
 enum {
   MGB_OK = 0,
@@ -172,15 +173,30 @@ int mgb_denorm_mask(const float* x, const float* spec_min, const float* spec_max
                     const uint8_t* pad_mask, float* mel, int B, int T, int n_mel, void* stream);
 
 /*
- * LengthRegulator (integer indexing, bit-exact): x[B][S][D] fp32, dur int64 [B][S].
- * out[B][max_len][D]: each source row s repeated max(dur[b][s],0) times, zero padded;
- * mel_len[b] = sum_s max(dur[b][s],0) (int64); frames beyond max_len are an error in the
- * reference (F.pad with a negative size truncates silently) — here they are truncated and the
- * true length is still reported.  Requires scratch of B*(S+1) int64 in `workspace`.
+ * Duration indexing of the front end (all integer results are bit-exact).
+ *
+ * mgb_durations_from_log   the word-level duration rounding of LinguisticEncoder.forward at inference
+ *                          (model/linguistic_encoder.py:310-314):
+ *                          dur[i] = (int64) max(round_half_even(exp(log_d[i]) - 1) * d_control, 0)   (.long() truncates)
+ * mgb_length_regulate      LengthRegulator.LR / expand (linguistic_encoder.py:383-416) + pad (utils/tools.py:374-392):
+ *                          x[B][S][D] fp32, dur int64 [B][S]; out[B][max_len][D]: each source row s repeated
+ *                          max(dur[b][s], 0) times, zero padded; an utterance longer than max_len is CROPPED, exactly as
+ *                          the reference (F.pad with a negative size crops); mel_len[b] = sum_s max(dur[b][s], 0) is the
+ *                          TRUE length either way (int64).  mask_valid (optional, uint8 [B][max_len]) receives
+ *                          get_mask_from_lengths(mel_len, max_len) (utils/tools.py:144-153: 1 = valid frame).
+ *                          Needs B*(S+1) int64 of scratch in `workspace`; the scratch (the exclusive scan of the
+ *                          durations) is what mgb_length_regulate_backward reads.
+ * mgb_length_regulate_backward   d/dx of the expansion (the autograd of expand + cat + pad in the reference):
+ *                          grad_x[b][s] = sum of grad_out[b][f] over the frames copied from row s, in frame order.
+ * mgb_mask_from_lengths    get_mask_from_lengths for lengths that did not come out of mgb_length_regulate.
  */
-int mgb_length_regulate(const float* x, const int64_t* dur, float* out, int64_t* mel_len,
+int mgb_durations_from_log(const float* log_d, float d_control, int64_t* dur, int n, void* stream);
+int mgb_length_regulate(const float* x, const int64_t* dur, float* out, int64_t* mel_len, uint8_t* mask_valid,
                         int B, int S, int D, int max_len, void* workspace, size_t workspace_bytes,
                         void* stream);
+int mgb_length_regulate_backward(const float* grad_out, const void* workspace, float* grad_x, int B, int S, int D,
+                                 int max_len, void* stream);
+int mgb_mask_from_lengths(const int64_t* lengths, uint8_t* mask_valid, int B, int max_len, void* stream);
 
 /*
  * Training (BASELINE configs[4]): Denoiser forward that keeps the activations its backward needs, and the

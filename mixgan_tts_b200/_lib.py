@@ -53,7 +53,10 @@ SIGNATURES = {
     "mgb_pack_cond": (_I, [_D, _I, _P, _I, _I, _P, _Z, _P]),
     "mgb_shallow_start": (_I, [_P, _P, _P, _P, _F, _F, _P, _P, _I, _I, _I, _P]),
     "mgb_denorm_mask": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P]),
-    "mgb_length_regulate": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _Z, _P]),
+    "mgb_durations_from_log": (_I, [_P, _F, _P, _I, _P]),
+    "mgb_length_regulate": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _Z, _P]),
+    "mgb_length_regulate_backward": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
+    "mgb_mask_from_lengths": (_I, [_P, _P, _I, _I, _P]),
 }
 
 # include/mixgan_b200_probe.h: exported by the test-only debug library (libmixgan_b200_dbg.so), never by the product one
@@ -100,7 +103,7 @@ def load():
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)
         fn.restype, fn.argtypes = res, args
-    if lib.mgb_abi_version() != 1:
+    if lib.mgb_abi_version() != 2:
         raise RuntimeError("libmixgan_b200.so ABI version mismatch")
     _lib = lib
     return lib

@@ -181,7 +181,17 @@ static void launch_denorm_mask(const float* x, const float* smin, const float* s
   note_launch();
 }
 
-// ---- LengthRegulator: exclusive scan of clamped durations, then a gather -----------------------
+// ---- LengthRegulator: duration rounding, exclusive scan of clamped durations, gather, mask, backward ---------------
+// dur = (int64) max(round_half_even(exp(log_d) - 1) * d_control, 0)      (linguistic_encoder.py:310-314)
+// exp is evaluated in double and rounded once to fp32 (a correctly rounded fp32 exp), the rest in fp32 as torch does.
+__global__ void lr_durations_kernel(const float* __restrict__ log_d, float d_control, int64_t* __restrict__ dur, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float e = (float)exp((double)log_d[i]);
+  const float d = __fmul_rn(rintf(__fsub_rn(e, 1.f)), d_control);
+  dur[i] = (int64_t)fmaxf(d, 0.f);                   // .long() truncates towards zero
+}
+
 __global__ void lr_scan_kernel(const int64_t* __restrict__ dur, int64_t* __restrict__ cum,
                                int64_t* __restrict__ mel_len, int S) {
   // one block per utterance; S is small (phonemes/words), a serial scan by thread 0 keeps the
@@ -199,8 +209,9 @@ __global__ void lr_scan_kernel(const int64_t* __restrict__ dur, int64_t* __restr
   }
 }
 
+// One block per output frame: binary search of the source row, then a vectorised row copy; also the frame's mask byte.
 __global__ void lr_gather_kernel(const float* __restrict__ x, const int64_t* __restrict__ cum,
-                                 float* __restrict__ out, int S, int D, int max_len) {
+                                 float* __restrict__ out, uint8_t* __restrict__ mask_valid, int S, int D, int max_len) {
   const int b = blockIdx.y, f = blockIdx.x;
   const int64_t* cb = cum + (size_t)b * (S + 1);
   // binary search: largest s with cum[s] <= f (and f < cum[s+1])
@@ -213,9 +224,38 @@ __global__ void lr_gather_kernel(const float* __restrict__ x, const int64_t* __r
     }
     src = lo;
   }
+  if (mask_valid && threadIdx.x == 0) mask_valid[(size_t)b * max_len + f] = src >= 0 ? 1 : 0;   // get_mask_from_lengths: f < mel_len
   float* o = out + ((size_t)b * max_len + f) * D;
   const float* xi = src >= 0 ? x + ((size_t)b * S + src) * D : nullptr;
-  for (int d = threadIdx.x; d < D; d += blockDim.x) o[d] = xi ? xi[d] : 0.f;
+  if ((D & 3) == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out)) & 15) == 0) {
+    float4* o4 = reinterpret_cast<float4*>(o);
+    const float4* x4 = reinterpret_cast<const float4*>(xi);
+    for (int d = threadIdx.x; d < D / 4; d += blockDim.x) o4[d] = xi ? __ldg(x4 + d) : make_float4(0.f, 0.f, 0.f, 0.f);
+  } else {
+    for (int d = threadIdx.x; d < D; d += blockDim.x) o[d] = xi ? xi[d] : 0.f;
+  }
+}
+
+// d/dx: grad_x[b][s] = sum of grad_out[b][f] over the frames f that copy source row s (cropped at max_len), summed in
+// frame order (deterministic).  One block per (s, b).
+__global__ void lr_backward_kernel(const float* __restrict__ grad_out, const int64_t* __restrict__ cum,
+                                   float* __restrict__ grad_x, int S, int D, int max_len) {
+  const int b = blockIdx.y, s = blockIdx.x;
+  const int64_t* cb = cum + (size_t)b * (S + 1);
+  const int64_t lo = cb[s] < max_len ? cb[s] : max_len, hi = cb[s + 1] < max_len ? cb[s + 1] : max_len;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    float acc = 0.f;
+    for (int64_t f = lo; f < hi; ++f) acc += grad_out[((size_t)b * max_len + f) * D + d];
+    grad_x[((size_t)b * S + s) * D + d] = acc;
+  }
+}
+
+// mask[b][f] = f < lengths[b]  (utils/tools.py:144-153, True = valid)
+__global__ void mask_from_lengths_kernel(const int64_t* __restrict__ lengths, uint8_t* __restrict__ mask, int B, int max_len) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * max_len) return;
+  const int b = i / max_len, f = i - b * max_len;
+  mask[i] = (int64_t)f < lengths[b] ? 1 : 0;
 }
 
 }  // namespace
@@ -558,8 +598,17 @@ int mgb_denorm_mask(const float* x, const float* spec_min, const float* spec_max
   return MGB_OK;
 }
 
-int mgb_length_regulate(const float* x, const int64_t* dur, float* out, int64_t* mel_len, int B, int S, int D,
-                        int max_len, void* workspace, size_t workspace_bytes, void* stream) {
+int mgb_durations_from_log(const float* log_d, float d_control, int64_t* dur, int n, void* stream) {
+  MGB_REQUIRE(log_d && dur && n > 0, MGB_E_ARG, "bad argument");
+  if (int rc = check_arch()) return rc;
+  lr_durations_kernel<<<(n + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(log_d, d_control, dur, n);
+  note_launch();
+  MGB_LAUNCH_CHECK();
+  return MGB_OK;
+}
+
+int mgb_length_regulate(const float* x, const int64_t* dur, float* out, int64_t* mel_len, uint8_t* mask_valid, int B, int S,
+                        int D, int max_len, void* workspace, size_t workspace_bytes, void* stream) {
   MGB_REQUIRE(x && dur && out && mel_len && workspace, MGB_E_ARG, "NULL pointer argument");
   MGB_REQUIRE(B > 0 && S > 0 && D > 0 && max_len > 0, MGB_E_ARG, "bad shape");
   MGB_REQUIRE(workspace_bytes >= (size_t)B * (S + 1) * sizeof(int64_t), MGB_E_WORKSPACE,
@@ -569,8 +618,31 @@ int mgb_length_regulate(const float* x, const int64_t* dur, float* out, int64_t*
   int64_t* cum = static_cast<int64_t*>(workspace);
   lr_scan_kernel<<<B, 32, 0, s>>>(dur, cum, mel_len, S);
   dim3 grid(max_len, B);
-  lr_gather_kernel<<<grid, 64, 0, s>>>(x, cum, out, S, D, max_len);
+  lr_gather_kernel<<<grid, 64, 0, s>>>(x, cum, out, mask_valid, S, D, max_len);
   note_launch(2);
+  MGB_LAUNCH_CHECK();
+  return MGB_OK;
+}
+
+int mgb_length_regulate_backward(const float* grad_out, const void* workspace, float* grad_x, int B, int S, int D,
+                                 int max_len, void* stream) {
+  MGB_REQUIRE(grad_out && workspace && grad_x, MGB_E_ARG, "NULL pointer argument");
+  MGB_REQUIRE(B > 0 && S > 0 && D > 0 && max_len > 0, MGB_E_ARG, "bad shape");
+  if (int rc = check_arch()) return rc;
+  dim3 grid(S, B);
+  lr_backward_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(grad_out, static_cast<const int64_t*>(workspace),
+                                                                           grad_x, S, D, max_len);
+  note_launch();
+  MGB_LAUNCH_CHECK();
+  return MGB_OK;
+}
+
+int mgb_mask_from_lengths(const int64_t* lengths, uint8_t* mask_valid, int B, int max_len, void* stream) {
+  MGB_REQUIRE(lengths && mask_valid && B > 0 && max_len > 0, MGB_E_ARG, "bad argument");
+  if (int rc = check_arch()) return rc;
+  const int n = B * max_len;
+  mask_from_lengths_kernel<<<(n + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(lengths, mask_valid, B, max_len);
+  note_launch();
   MGB_LAUNCH_CHECK();
   return MGB_OK;
 }

@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(NT) conv_gemm_kernel(const GemmArgs p) {
       const int t = m - b * p.T;
       float c1 = 0.f, c2 = 0.f, sg = 0.f;
       if (p.sched) {
-        const int tb = (int)p.t[b];
+        const int tb = min(max((int)p.t[b], 0), p.K - 1);   // never read outside the schedule (the host validates t)
         c1 = p.sched[tb]; c2 = p.sched[p.K + tb]; sg = p.sched[2 * p.K + tb];
       }
 #pragma unroll
@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(NT) conv_gemm_kernel(const GemmArgs p) {
         const int n = n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
         if (n >= p.n_mel) continue;
         float x0 = acc[i][j] + p.bias[n];
-        if (p.clip) x0 = fminf(fmaxf(x0, -1.f), 1.f);
+        if (p.clip && x0 == x0) x0 = fminf(fmaxf(x0, -1.f), 1.f);   // NaN propagates, as torch.clamp does
         const size_t o = ((size_t)b * p.n_mel + n) * p.T + t;
         if (p.out2) p.out2[o] = x0;
         if (p.sched) {

@@ -1065,7 +1065,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_p
       // output projection -> clamp -> posterior mean + sigma * noise (diffusion.py:104-129), bins [40h, 40h+40)
       float c1 = 0.f, c2 = 0.f, sg = 0.f;
       if (p.sched) {
-        const int tb = p.t_uniform >= 0 ? p.t_uniform : (int)p.t[b];
+        const int tb = min(max(p.t_uniform >= 0 ? p.t_uniform : (int)p.t[b], 0), p.K - 1);   // never outside the schedule
         c1 = p.sched[tb]; c2 = p.sched[p.K + tb]; sg = p.sched[2 * p.K + tb];
       }
       temp_wait(0);
@@ -1082,7 +1082,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) fused_p
             const int n = NB * h + j;
             if (n < p.n_mel) {
               float x0 = __uint_as_float(j < 32 ? a[j] : a2[j - 32]);   // b_out came with the GEMM
-              if (p.clip) x0 = fminf(fmaxf(x0, -1.f), 1.f);
+              if (p.clip && x0 == x0) x0 = fminf(fmaxf(x0, -1.f), 1.f);   // NaN propagates, as torch.clamp does
               const size_t o = o0 + (size_t)j * p.T;
               if (p.x0_out) p.x0_out[o] = x0;
               if (p.sched) {

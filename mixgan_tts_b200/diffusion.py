@@ -159,6 +159,9 @@ class GaussianDiffusion(nn.Module):
             cond_bth = self._f32c(cond.transpose(1, 2))
             spk = self._spk(spk_emb)
             tt = t.detach().to(torch.int64).contiguous()
+            # the reference's `extract` (a.gather(-1, t)) raises on a timestep outside [0, K); so does this (one host read)
+            if tt.numel() and not bool(((tt >= 0) & (tt < self.num_timesteps)).all()):
+                raise IndexError(f"p_sample: timestep outside [0, {self.num_timesteps})")
             nz = self._f32c(noise)
             out = torch.empty_like(x)
             x0 = torch.empty_like(x) if return_x0 else None

@@ -31,10 +31,20 @@ _PACK_KINDS = dict(PRECISIONS, fp32_tables=_lib.PACK_FP32_TABLES)
 # (data_ptr, _version) fingerprint alone would keep serving stale kernel-layout weights after an optimizer step.  Every
 # optimizer step therefore advances this epoch, which is part of the fingerprint.
 _PARAM_EPOCH = [0]
+_DENOISER_PARAM_IDS = set()          # id() of every parameter a live Denoiser owns (entries are removed by a finalizer)
+_OPT_TOUCHES_DENOISER = weakref.WeakKeyDictionary()   # optimizer -> does it own a Denoiser parameter? (decided once)
 
 
-def _on_optimizer_step(*_args, **_kwargs):
-    _PARAM_EPOCH[0] += 1
+def _on_optimizer_step(optimizer, *_args, **_kwargs):
+    try:
+        hit = _OPT_TOUCHES_DENOISER.get(optimizer)
+        if hit is None:
+            hit = any(id(p) in _DENOISER_PARAM_IDS for g in optimizer.param_groups for p in g["params"])
+            _OPT_TOUCHES_DENOISER[optimizer] = hit
+    except TypeError:                               # an optimizer that cannot be weakly referenced: be conservative
+        hit = True
+    if hit:                                         # e.g. the discriminator's optimizer does not force a repack
+        _PARAM_EPOCH[0] += 1
 
 
 try:
@@ -83,15 +93,22 @@ class _Block(nn.Module):
 
 
 class _Workspace:
-    """Caller-owned scratch for the library, grown on demand and reused across calls."""
+    """Caller-owned scratch for the library, grown on demand and reused across calls; one buffer PER DEVICE (replicas of
+    one module on several GPUs - nn.DataParallel - share this object through ``__dict__``)."""
 
     def __init__(self):
-        self.buf = None
+        self.bufs = {}
 
     def get(self, nbytes: int, device) -> torch.Tensor:
-        if self.buf is None or self.buf.numel() < nbytes or self.buf.device != device:
-            self.buf = torch.empty(nbytes, dtype=torch.uint8, device=device)
-        return self.buf
+        buf = self.bufs.get(device)
+        if buf is None or buf.numel() < nbytes:
+            buf = self.bufs[device] = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        return buf
+
+    @property
+    def buf(self):
+        """The buffer of the current CUDA device (diagnostics)."""
+        return self.bufs.get(torch.device("cuda", torch.cuda.current_device()))
 
 
 class Denoiser(nn.Module):
@@ -114,9 +131,12 @@ class Denoiser(nn.Module):
         self.output_projection = _Conv(channels, n_mel, 1)
         nn.init.zeros_(self.output_projection.conv.weight)   # as the reference (modules.py:418)
 
-        self._packed = {}          # precision -> (fingerprint, packed tensor)
-        self._flat = None          # (fingerprint, flat fp32 parameter vector) of the last pack
-        self._flat_store = None    # (device, persistent flat buffer, per-parameter views into it)
+        # Kernel-layout caches.  Every cache is keyed by DEVICE: nn.DataParallel replicas (the reference wraps the model
+        # in one unconditionally, train.py:43-44) share these dicts through __dict__ and run in parallel threads.
+        self._packed = {}          # (precision, device) -> (fingerprint, packed tensor)
+        self._flat = {}            # device -> (fingerprint, flat fp32 parameter vector) of the last pack
+        self._flat_store = {}      # device -> (persistent flat buffer, per-parameter views into it)
+        self._pack_epoch = 0       # bumped by invalidate_packed()
         self._ws = _Workspace()
         self._train_ws = _Workspace()
         self.grad_sync = None      # optional mixgan_tts_b200.grad_sync.GradSync (data-parallel training)
@@ -127,6 +147,9 @@ class Denoiser(nn.Module):
         # (tests/test_gpu_train.py).
         self.use_cuda_graphs = os.environ.get("MIXGAN_B200_TRAIN_GRAPHS", "0") == "1"
         self._train_graphs = {}
+        ids = [id(p) for p in self.parameters()]
+        _DENOISER_PARAM_IDS.update(ids)
+        weakref.finalize(self, _DENOISER_PARAM_IDS.difference_update, ids)
 
     # ---------------------------------------------------------------- weights
     def _ordered_params(self):
@@ -143,38 +166,62 @@ class Denoiser(nn.Module):
                self.output_projection.conv.weight, self.output_projection.conv.bias]
         return ps
 
+    def invalidate_packed(self):
+        """Forget every kernel-layout copy of the weights.  The caches notice optimizer steps, ``load_state_dict``,
+        ``.to()`` / ``.cuda()`` and ordinary in-place ops by themselves; call this after writing parameters through
+        ``.data`` (``p.data.copy_()``, EMA swaps ...), which bumps no version counter."""
+        self.__dict__["_pack_epoch"] = self.__dict__.get("_pack_epoch", 0) + 1
+        self._packed.clear()
+        self._flat.clear()
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        super()._load_from_state_dict(*args, **kwargs)
+        self.invalidate_packed()
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)
+        self.invalidate_packed()
+        return out
+
     def packed_weights(self, precision: str | None = None, params=None) -> torch.Tensor:
         """Kernel-layout copy of the parameters; rebuilt when any parameter changes."""
+        return self.packed_and_flat(precision, params)[0]
+
+    def packed_and_flat(self, precision: str | None = None, params=None):
+        """``(packed, flat)``: the kernel-layout copy and the flat fp32 parameter vector it was built from (``flat`` is None
+        when the packed copy came out of the cache and no flat vector of the same parameters is held)."""
         precision = precision or self.precision
         prec = _PACK_KINDS[precision]
         params = params if params is not None else self._ordered_params()
-        fp = _param_fingerprint(params)
-        hit = self._packed.get(precision)
-        if hit is not None and hit[0] == fp:
-            return hit[1]
+        fp = (self._pack_epoch, _param_fingerprint(params))
         dev = params[0].device
+        hit = self._packed.get((precision, dev))
+        if hit is not None and hit[0] == fp:
+            fl = self._flat.get(dev)
+            return hit[1], (fl[1] if fl is not None and fl[0] == fp else None)
         if dev.type != "cuda":
             raise RuntimeError("mixgan_tts_b200.Denoiser runs on a CUDA device only (no CPU fallback); "
                                "move the module with .cuda() first")
         lib = _lib.load()
         with torch.cuda.device(dev):
-            if self._flat is not None and self._flat[0] == fp:
-                flat = self._flat[1]
+            fl = self._flat.get(dev)
+            if fl is not None and fl[0] == fp:
+                flat = fl[1]
             else:
                 # persistent flat buffer + per-parameter views, refreshed with ONE multi-tensor copy (a torch.cat over
                 # 162 reshaped views costs ~0.4 ms of host time per training step)
-                store = self._flat_store
-                if store is None or store[0] != dev or store[1].numel() != sum(p.numel() for p in params):
+                store = self._flat_store.get(dev)
+                if store is None or store[0].numel() != sum(p.numel() for p in params):
                     buf = torch.empty(sum(p.numel() for p in params), dtype=torch.float32, device=dev)
                     views, off = [], 0
                     for p in params:
                         views.append(buf[off:off + p.numel()].view(p.shape))
                         off += p.numel()
-                    store = self._flat_store = (dev, buf, views)
+                    store = self._flat_store[dev] = (buf, views)
                 with torch.no_grad():
-                    torch._foreach_copy_(store[2], list(params))
-                flat = store[1]
-                self._flat = (fp, flat)
+                    torch._foreach_copy_(store[1], [p.detach() for p in params])
+                flat = store[0]
+                self._flat[dev] = (fp, flat)
             assert flat.numel() == lib.mgb_flat_weight_count(C.byref(self.dims))
             nbytes = lib.mgb_packed_bytes(C.byref(self.dims), prec)
             if nbytes == 0:
@@ -183,8 +230,8 @@ class Denoiser(nn.Module):
             stream = torch.cuda.current_stream(dev).cuda_stream
             _lib.check(lib.mgb_pack_weights(C.byref(self.dims), prec, _lib.ptr(flat), _lib.ptr(packed), nbytes,
                                             C.c_void_p(stream)), "mgb_pack_weights")
-        self._packed[precision] = (fp, packed)
-        return packed
+        self._packed[(precision, dev)] = (fp, packed)
+        return packed, flat
 
     def workspace(self, B: int, T: int, K: int, device, precision: str | None = None) -> torch.Tensor:
         lib = _lib.load()
@@ -239,8 +286,12 @@ class Denoiser(nn.Module):
 
     def flat_weights(self, params=None) -> torch.Tensor:
         """The parameters as one fp32 vector in the canonical order (built together with a weight pack)."""
-        self.packed_weights("fp32" if self.train_precision == "fp32" else "fp32_tables", params)
-        return self._flat[1]
+        kind = "fp32" if self.train_precision == "fp32" else "fp32_tables"
+        packed, flat = self.packed_and_flat(kind, params)
+        if flat is None:                       # packed copy cached but the flat vector was dropped: rebuild both
+            self._packed.pop((kind, (params or self._ordered_params())[0].device), None)
+            packed, flat = self.packed_and_flat(kind, params)
+        return flat
 
     def train_workspace(self, B: int, T: int, device) -> torch.Tensor:
         lib = _lib.load()
@@ -386,8 +437,15 @@ class _DenoiserGradFn(torch.autograd.Function):
         ctx.tg = None
         with torch.cuda.device(dev):
             # both precisions read fp32 per-utterance tables; the bf16 mode needs nothing else from the fp32 pack
-            packed = den.packed_weights("fp32" if den.train_precision == "fp32" else "fp32_tables", params)
-            flat = den._flat[1]                       # built by the call above (same fingerprint)
+            # The eager path hands the backward its OWN copy of the flat parameter vector: the module's persistent flat
+            # buffer is rewritten in place by the next pack, and two forwards with different parameters before the first
+            # backward (a D step and a G step sharing the Denoiser) would otherwise differentiate against the wrong weights.
+            kind = "fp32" if den.train_precision == "fp32" else "fp32_tables"
+            packed, flat = den.packed_and_flat(kind, params)
+            if flat is None:
+                den._packed.pop((kind, dev), None)
+                packed, flat = den.packed_and_flat(kind, params)
+            flat = flat.clone()
             tt = t.detach().to(torch.int64).contiguous()
             out = torch.empty_like(x)
             saved = torch.empty(lib.mgb_train_saved_bytes(C.byref(den.dims), prec, B, T), dtype=torch.uint8, device=dev)

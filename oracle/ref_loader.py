@@ -72,6 +72,22 @@ def load():
     return mod
 
 
+def load_module(name: str):
+    """Import another module of the reference tree (e.g. ``model.linguistic_encoder``, ``model.mixgantts``,
+    ``transformer.Models``, ``hifigan.models``) under the same stubs; ``CUDA_VISIBLE_DEVICES`` is restored."""
+    load()
+    saved = os.environ.get("CUDA_VISIBLE_DEVICES")
+    sys.path.insert(0, REFERENCE_ROOT)
+    try:
+        return importlib.import_module(name)
+    finally:
+        sys.path.remove(REFERENCE_ROOT)
+        if saved is None:
+            os.environ.pop("CUDA_VISIBLE_DEVICES", None)
+        else:
+            os.environ["CUDA_VISIBLE_DEVICES"] = saved
+
+
 def build_reference_diffusion(args, preprocess_config, model_config, train_config, weights: dict):
     """Construct the reference ``GaussianDiffusion`` and load ``weights`` into its Denoiser."""
     import torch

@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
     for s in syms:
         assert hasattr(lib, s), f"{s} declared in include/mixgan_b200.h but not exported"
         assert s in _lib.SIGNATURES, f"{s} has no ctypes prototype"
-    assert lib.mgb_abi_version() == 1
+    assert lib.mgb_abi_version() == 2
 
 
 def test_sizes_are_computable_without_gpu():
@@ -138,16 +138,28 @@ def test_light_helpers_match_oracle_on_cpu():
 
 def test_weight_cache_fingerprint_sees_fused_optimizer_steps():
     """torch's fused optimizers update parameters in place WITHOUT bumping Tensor._version; the kernel-layout weight
-    caches must still be invalidated (a global optimizer post-step hook advances an epoch that is part of the key)."""
+    caches must still be invalidated (an optimizer post-step hook advances an epoch that is part of the key) - but only
+    by optimizers that own a Denoiser parameter (the discriminator's optimizer must not force a repack)."""
+    from mixgan_tts_b200 import Denoiser, configs
     from mixgan_tts_b200.modules import _param_fingerprint
-    ps = [torch.nn.Parameter(torch.randn(8)) for _ in range(3)]
+    _, pc, mc, _ = configs.make_configs("LJSpeech", "naive", residual_layers=1)
+    den = Denoiser(pc, mc)
+    ps = den._ordered_params()
     for p in ps:
-        p.grad = torch.randn(8)
+        p.grad = torch.randn_like(p)
     fp0 = _param_fingerprint(ps)
     assert _param_fingerprint(ps) == fp0
+    other = [torch.nn.Parameter(torch.randn(8))]
+    other[0].grad = torch.randn(8)
+    torch.optim.SGD(other, lr=1e-2).step()
+    assert _param_fingerprint(ps) == fp0              # an unrelated optimizer leaves the caches valid
     try:
         opt = torch.optim.Adam(ps, lr=1e-2, fused=True)
     except (RuntimeError, ValueError):
         opt = torch.optim.Adam(ps, lr=1e-2)
     opt.step()
     assert _param_fingerprint(ps) != fp0
+    # writes through .data bump nothing: invalidate_packed() is the documented escape hatch
+    e0 = den._pack_epoch
+    den.invalidate_packed()
+    assert den._pack_epoch == e0 + 1 and not den._packed and not den._flat

@@ -153,6 +153,67 @@ def test_shard_equivalence_and_determinism_full_size(precision):
 
 
 @pytest.mark.parametrize("precision", PRECS)
+def test_batch_of_full_length_utterances_vs_oracle(precision):
+    """B=8 x T=800 against the oracle in one piece: 8 x 801 rows are 28 tiles of 236 output rows, most of which span two
+    utterances (the shard test above only compares the GPU with itself at this size)."""
+    c = Case("LJSpeech", "naive", False, 8, 800, wseed=0, iseed=31)
+    gd = build(c, precision)
+    mel = gd(None, cu(c.t("cond")), None, cu(c.t("pad_mask")), x_T=cu(c.t("x_T")), noises=cu(c.t("noises")))[0]
+    final, _, x0s, _ = c.oracle_forward()
+    assert rel_l2(mel, final) < TOL[precision]["mel"]
+    valid = ~c.t("pad_mask")
+    # per utterance, so that one bad tile cannot hide in the batch norm
+    for b in range(c.B):
+        x0_ref = x0s[-1][b, 0].transpose(0, 1)[valid[b]]
+        x0_gpu = gd.norm_spec(mel[b:b + 1]).cpu()[0][valid[b]]
+        assert rel_l2(x0_gpu, x0_ref) < TOL[precision]["norm"] * 2, b
+
+
+# Dynamic range: a trained checkpoint is not a random-init one.  Weights, biases and the conditioner are scaled up so that
+# the residual stream, the skip sum and the pre-activations are several times larger than at initialisation (saturated
+# gates, |u| of a few tens), which exercises the 16-bit group spills and the constants folded into the packed weights.
+# Tolerances: the same stated bars; the measured values are printed (profiles/r02/parity_report.txt).
+@pytest.mark.parametrize("precision", PRECS)
+@pytest.mark.parametrize("stress", ["weights_x4", "biases_pm8", "cond_x4", "all"])
+def test_dynamic_range_vs_oracle(stress, precision):
+    c = Case("LJSpeech", "naive", False, 2, 300, wseed=5, iseed=61)
+    rg = np.random.default_rng(3)
+    W = dict(c.W)
+    if stress in ("weights_x4", "all"):
+        for k in W:
+            if k.endswith("output_projection.conv.weight") and k.startswith("residual_layers"):
+                W[k] = W[k] * np.float32(4.0)
+            elif k.endswith("conditioner_projection.conv.weight") or k.endswith("conv_layer.conv.weight"):
+                W[k] = W[k] * np.float32(2.0)
+    if stress in ("biases_pm8", "all"):
+        for k in W:
+            if k.endswith(".bias") and k.startswith("residual_layers"):
+                W[k] = W[k] + rg.uniform(-8.0, 8.0, W[k].shape).astype(np.float32)
+    if stress in ("cond_x4", "all"):
+        c.inp = dict(c.inp)
+        c.inp["cond"] = c.inp["cond"] * np.float32(4.0)
+    c.W = W
+    from oracle.diffusion import DiffusionOracle
+    from mixgan_tts_b200 import configs
+    c.oracle = DiffusionOracle(W, model="naive", denoiser_cfg=c.mc["denoiser"], spec_min=[configs.SPEC_MIN] * 80,
+                               spec_max=[configs.SPEC_MAX] * 80)
+    gd = build(c, precision)
+    x, cond = cu(c.t("x_T")), cu(c.t("cond"))
+    t = torch.tensor([3, 1], device="cuda")
+    with torch.no_grad():
+        out = gd.denoise_fn(x, t, cond.transpose(1, 2), None)            # unclamped network output: no clip to hide behind
+    from oracle.denoiser import denoiser_forward
+    ref = denoiser_forward(c.oracle.W, c.t("x_T"), t.cpu(), c.t("cond").transpose(1, 2), None)
+    assert torch.isfinite(out).all()
+    e = rel_l2(out, ref)
+    print(f"dynamic range [{stress}] {precision}: |ref| rms {float(ref.pow(2).mean().sqrt()):.3f}  rel L2 {e:.3e}")
+    assert e < TOL[precision]["norm"], (stress, e)
+    mel = gd(None, cond, None, cu(c.t("pad_mask")), x_T=x, noises=cu(c.t("noises")))[0]
+    final = c.oracle_forward()[0]
+    assert rel_l2(mel, final) < TOL[precision]["mel"] * 2
+
+
+@pytest.mark.parametrize("precision", PRECS)
 def test_long_multispeaker_utterances_config4(precision):
     """BASELINE configs[3] shape class: AISHELL3 shallow, multi-speaker, T = 1500 (not a multiple of any tile size).
     One utterance against the oracle at full length, then size-independent properties on a batch: determinism and
@@ -247,13 +308,51 @@ def test_abi_error_codes():
 
 
 def test_length_regulator_bit_exact():
+    """mgb_length_regulate / mgb_durations_from_log / mask against (i) the golden outputs of the REAL reference
+    (tests/golden/length_regulator.npz) and (ii) the oracle on further random cases: bit for bit."""
+    import os, sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    from make_golden_lr import LR_CASES, logd_case, lr_case
+    from mixgan_tts_b200.length_regulator import durations_from_log, get_mask_from_lengths
     from oracle.length_regulator import length_regulate
-    g = np.random.default_rng(5)
-    for B, S, D, max_len in [(3, 7, 5, None), (4, 33, 256, 400), (1, 1, 8, 10), (2, 50, 256, None)]:
-        x = g.standard_normal((B, S, D)).astype(np.float32)
-        dur = g.integers(-2, 9, (B, S)).astype(np.int64)
+    g = load_golden("length_regulator")
+    lr = LengthRegulator()
+    for name in LR_CASES:
+        x, dur, max_len = lr_case(name)
+        out, mel_len, mask = lr.regulate_with_mask(torch.from_numpy(x).cuda(), torch.from_numpy(dur).cuda(), max_len)
+        assert np.array_equal(mel_len.cpu().numpy(), g[f"{name}/mel_len"]), name
+        assert tuple(out.shape) == g[f"{name}/out"].shape, name
+        assert np.array_equal(out.cpu().numpy().view(np.uint32), g[f"{name}/out"].view(np.uint32)), name
+        if f"{name}/mask_w" in g.files:
+            assert np.array_equal(mask.cpu().numpy(), g[f"{name}/mask_w"]), name
+            assert np.array_equal(get_mask_from_lengths(mel_len).cpu().numpy(), g[f"{name}/mask"]), name
+        out2, mel_len2 = lr(torch.from_numpy(x).cuda(), torch.from_numpy(dur).cuda(), max_len)     # the reference's signature
+        assert torch.equal(out2, out) and torch.equal(mel_len2, mel_len)
+    log_d, controls = logd_case()
+    for c in controls:
+        d = durations_from_log(torch.from_numpy(log_d).cuda(), c)
+        assert d.dtype == torch.int64 and np.array_equal(d.cpu().numpy(), g[f"dur_from_log/{c}"]), c
+    rg = np.random.default_rng(5)
+    for B, S, D, max_len in [(3, 7, 5, None), (4, 33, 256, 400), (1, 1, 8, 10), (2, 50, 256, None), (5, 64, 130, 97)]:
+        x = rg.standard_normal((B, S, D)).astype(np.float32)
+        dur = rg.integers(-2, 9, (B, S)).astype(np.int64)
         ref, ref_len = length_regulate(x, dur, max_len)
-        out, mel_len = LengthRegulator()(torch.from_numpy(x).cuda(), torch.from_numpy(dur).cuda(), max_len)
+        out, mel_len = lr(torch.from_numpy(x).cuda(), torch.from_numpy(dur).cuda(), max_len)
         assert np.array_equal(mel_len.cpu().numpy(), ref_len)
         assert out.shape == ref.shape
         assert np.array_equal(out.cpu().numpy().view(np.uint32), ref.view(np.uint32))
+
+
+def test_length_regulator_is_differentiable_like_the_reference():
+    """The reference's expand + cat + pad carries gradient back to the encoder; the drop-in must too (segment sum)."""
+    from oracle.length_regulator import length_regulate_backward
+    rg = np.random.default_rng(11)
+    for B, S, D, max_len in [(2, 6, 4, None), (3, 20, 256, 60), (2, 9, 16, 11)]:
+        x = torch.from_numpy(rg.standard_normal((B, S, D)).astype(np.float32)).cuda().requires_grad_(True)
+        dur = torch.from_numpy(rg.integers(-1, 7, (B, S)).astype(np.int64)).cuda()
+        out, mel_len = LengthRegulator()(x, dur, max_len)
+        assert out.requires_grad and not mel_len.requires_grad
+        w = torch.from_numpy(rg.standard_normal(tuple(out.shape)).astype(np.float32)).cuda()
+        (out * w).sum().backward()
+        ref = length_regulate_backward(w.cpu().numpy(), dur.cpu().numpy())
+        assert np.allclose(x.grad.cpu().numpy(), ref, rtol=1e-5, atol=1e-5)

@@ -184,14 +184,14 @@ def test_train_abi_errors():
 # ---------------------------------------------------------------------------------------------------------------
 # bf16 tensor-core training path.  Stated tolerances (relative L2 against fp32 torch autograd through the oracle; the
 # measured values are written to gpurun_out/train_bf16_parity.txt):
-#   outputs 2e-2 (the inference path's bf16 bar);
+#   outputs 8e-3 (the inference path's bf16 bar; measured 2.4-2.7e-3);
 #   gradients 2e-2 per tensor when the two ReLU masks are stable (biases shifted so that no pre-activation sits near 0):
 #     this isolates the arithmetic of the GEMMs/epilogues — bf16 operand rounding (2^-9 per element) through 20 blocks;
-#   gradients 1e-1 per tensor with the random-init weights: there ~0.25 % of the skip-projection / input-projection
+#   gradients 8e-2 per tensor with the random-init weights (measured 4.7-6.5e-2): there ~0.25 % of the skip-projection / input-projection
 #     pre-activations lie within the bf16 forward error of zero, their ReLU masks flip against the fp32 run, and a
 #     fraction p of flipped units moves a gradient by ~sqrt(p) = 5 % in L2 (measured 5-6 %, uniform over layers).  Any
 #     bf16 training of this network has this property; it is not an error of the kernels.
-TOL_BF16_OUT, TOL_BF16_GRAD, TOL_BF16_GRAD_RELU = 2e-2, 2e-2, 1e-1
+TOL_BF16_OUT, TOL_BF16_GRAD, TOL_BF16_GRAD_RELU = 8e-3, 2e-2, 8e-2
 
 
 def _status(gd, B, T, ws=None):

@@ -70,3 +70,44 @@ def test_two_gpu_gradient_average(tmp_path, precision):
     ok = np.load(tmp_path / "ok.npy")
     assert ok[0] == 1.0, "synchronised gradients are not the mean over ranks"
     assert ok[1] == 1.0, "the all-reduce changed a local input gradient"
+
+
+@pytest.mark.parametrize("precision", ["bf16", "fp16", "fp32"])
+def test_one_process_drives_two_devices(precision):
+    """The > 48 KB shared-memory opt-in of every kernel is a PER-DEVICE attribute and the kernel-layout weight caches are
+    per device: the same process must be able to run the module on cuda:0 and on cuda:1 (and nn.DataParallel, which the
+    reference wraps the model in, train.py:43-44, must give the single-device result)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import copy
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from helpers import Case
+    from mixgan_tts_b200 import GaussianDiffusion
+    c = Case("LJSpeech", "naive", False, 4, 160, wseed=3, iseed=70, layers=20)
+    gd0 = GaussianDiffusion(c.args, c.pc, c.mc, c.tc, precision=precision)
+    gd0.denoise_fn.load_state_dict({k: torch.from_numpy(v) for k, v in c.W.items()})
+    gd0 = gd0.eval()
+    outs = []
+    for d in (0, 1):
+        gd = copy.deepcopy(gd0).to(f"cuda:{d}")
+        to = lambda k: c.t(k).to(f"cuda:{d}")
+        with torch.no_grad():
+            outs.append(gd(None, to("cond"), None, to("pad_mask"), x_T=to("x_T"), noises=to("noises"))[0].cpu())
+    assert torch.equal(outs[0], outs[1])
+    # one module object moved from device to device: the caches must follow
+    gd = copy.deepcopy(gd0).to("cuda:0")
+    with torch.no_grad():
+        a = gd(None, c.t("cond").cuda(0), None, c.t("pad_mask").cuda(0), x_T=c.t("x_T").cuda(0), noises=c.t("noises").cuda(0))[0].cpu()
+        gd = gd.to("cuda:1")
+        b = gd(None, c.t("cond").cuda(1), None, c.t("pad_mask").cuda(1), x_T=c.t("x_T").cuda(1), noises=c.t("noises").cuda(1))[0].cpu()
+    assert torch.equal(a, outs[0]) and torch.equal(b, outs[0])
+    # nn.DataParallel over the Denoiser (inference): replicas share the module's __dict__ and run in parallel threads
+    den = copy.deepcopy(gd0.denoise_fn).to("cuda:0")
+    dp = torch.nn.DataParallel(den, device_ids=[0, 1])
+    x, cond = c.t("x_T").cuda(0), c.t("cond").transpose(1, 2).contiguous().cuda(0)
+    t = torch.tensor([3, 2, 1, 0], device="cuda:0")
+    with torch.no_grad():
+        single = den(x, t, cond, None)
+        both = dp(x, t, cond, None)
+    assert torch.equal(single.cpu(), both.cpu())

@@ -120,3 +120,29 @@ def test_oracle_gradients_vs_reference_golden(name):
     loss, _, grads, gcond, gspk = oracle_training_grads(c, ex, probe)
     assert abs(float(loss) - float(g["loss"])) < 1e-4 * max(1.0, abs(float(g["loss"])))
     check_grads_against_golden(g, grads, gcond, gspk, tol=5e-5)
+
+
+# ---- LengthRegulator / duration rounding / mask: pinned by outputs of the REAL reference -------------------------------
+def test_length_regulator_oracle_matches_reference_golden():
+    """tests/golden/length_regulator.npz was made by tests/golden/make_golden_lr.py from model.linguistic_encoder.LengthRegulator,
+    utils.tools.pad / get_mask_from_lengths and the rounding expression of linguistic_encoder.py:310-314."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    from make_golden_lr import LR_CASES, logd_case, lr_case
+    from oracle.length_regulator import durations_from_log, length_regulate, mask_from_lengths
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "length_regulator.npz"))
+    for name in LR_CASES:
+        x, dur, max_len = lr_case(name)
+        out, ml = length_regulate(x, dur, max_len)
+        assert np.array_equal(ml, g[f"{name}/mel_len"]), name
+        assert out.shape == g[f"{name}/out"].shape, name
+        assert np.array_equal(out.view(np.uint32), g[f"{name}/out"].view(np.uint32)), name
+        if f"{name}/mask" in g.files:
+            assert np.array_equal(mask_from_lengths(ml), g[f"{name}/mask"]), name
+            assert np.array_equal(mask_from_lengths(ml, out.shape[1]), g[f"{name}/mask_w"]), name
+    log_d, controls = logd_case()
+    for c in controls:
+        assert np.array_equal(durations_from_log(log_d, c), g[f"dur_from_log/{c}"]), c
+    # the cropped case really crops: some utterance is longer than max_len and keeps its true length
+    assert g["cropped/mel_len"].max() > g["cropped/out"].shape[1]

@@ -60,3 +60,33 @@ def test_training_branch_oracle_matches_live_reference(model, multi):
     for a, b in zip(out[:4], ref[:4]):
         assert rel_l2(a, b) < 1e-6
     assert torch.equal(out[4], ref[4])
+
+
+def test_length_regulator_oracle_matches_live_reference():
+    """The real LengthRegulator + pad + get_mask_from_lengths + duration rounding, run here, against the numpy restatement."""
+    import numpy as np
+    from oracle.length_regulator import durations_from_log, length_regulate, mask_from_lengths
+    le = ref_loader.load_module("model.linguistic_encoder")
+    tools = ref_loader.load_module("utils.tools")
+    lr = le.LengthRegulator()
+    g = np.random.default_rng(9)
+    for B, S, D, max_len in [(2, 5, 3, None), (3, 17, 8, 40), (2, 9, 4, 7)]:
+        x = g.standard_normal((B, S, D)).astype(np.float32)
+        dur = g.integers(-2, 7, (B, S)).astype(np.int64)
+        ref, ref_len = lr(torch.from_numpy(x), torch.from_numpy(dur), max_len)
+        out, ml = length_regulate(x, dur, max_len)
+        assert np.array_equal(ml, ref_len.numpy())
+        assert np.array_equal(out.view(np.uint32), ref.numpy().view(np.uint32))
+        assert np.array_equal(mask_from_lengths(ml), tools.get_mask_from_lengths(ref_len).numpy())
+    log_d = (g.standard_normal(2000) * 1.5 + 0.5).astype(np.float32)
+    for c in (1.0, 0.8, 1.7):
+        ref = torch.clamp((torch.round(torch.exp(torch.from_numpy(log_d)) - 1) * c), min=0).long().numpy()
+        assert np.array_equal(durations_from_log(log_d, c), ref)
+    # autograd of the reference expansion = segment sum
+    from oracle.length_regulator import length_regulate_backward
+    x = torch.randn(2, 6, 4, requires_grad=True)
+    dur = torch.tensor([[2, 0, 3, 1, -1, 2], [1, 1, 1, 0, 4, 0]])
+    o, _ = lr(x, dur, 6)
+    w = torch.randn_like(o)
+    (o * w).sum().backward()
+    assert np.allclose(length_regulate_backward(w.numpy(), dur.numpy()), x.grad.numpy(), rtol=1e-6, atol=1e-6)

@@ -20,6 +20,8 @@
  *   mgb_length_regulate    LengthRegulator.LR / expand / pad     model/linguistic_encoder.py:383-416,
  *                          get_mask_from_lengths                 utils/tools.py:144-153,374-392
  *   mgb_durations_from_log duration rounding at inference        model/linguistic_encoder.py:310-314
+ *   mgb_conv1d_forward / mgb_conv1d_backward / mgb_step_embedding
+ *                          JCUDiscriminator.forward + autograd   model/mixgantts.py:186-288 (train.py:126-184)
  *
  * Conventions
  *   - Plain pointers and sizes only; no torch types.  All tensors are DEVICE pointers to
@@ -197,6 +199,33 @@ int mgb_length_regulate(const float* x, const int64_t* dur, float* out, int64_t*
 int mgb_length_regulate_backward(const float* grad_out, const void* workspace, float* grad_x, int B, int S, int D,
                                  int max_len, void* stream);
 int mgb_mask_from_lengths(const int64_t* lengths, uint8_t* mask_valid, int B, int max_len, void* stream);
+
+/*
+ * Generic fp32 Conv1d on frames-major activations, forward and backward: the building block of the JCU discriminator
+ * (reference model/mixgantts.py:186-288 - ConvNorm model/blocks.py:326-371 with stride 1 or 2 and
+ * padding (k-1)/2, LinearNorm (k = 1), F.leaky_relu(., 0.2), Mish - driven 4x forward + 2x backward per training step by
+ * train.py:126-184).  Exact fp32 on the CUDA cores: the reference's gradients are the parity target (1e-4).
+ *   x [B][Tin][Cin], y / pre / grad_y [B][Tout][Cout] with Tout = mgb_conv1d_out_len(Tin, k, stride); one row per frame.
+ *   w       : [Cout][Cin][k], the torch layout (a Linear weight [out][in] is k = 1); bias [Cout] or NULL
+ *   rowbias : [B][Cin] or NULL - added to every EXISTING input row before the convolution (padding rows stay zero):
+ *             the discriminator's "x + diffusion_step (+ speaker)" (mixgantts.py:275-276) fused into the operand gather
+ *   act     : 0 none, 1 leaky_relu(0.2), 2 mish (needs `pre`, the pre-activation, for its backward), 3 relu
+ *   backward: grad_x [B][Tin][Cin], grad_w [Cout][Cin][k], grad_bias [Cout], grad_rowbias [B][Cin]; each may be NULL
+ *             (grad_rowbias needs grad_x).  Gradients are WRITTEN, not accumulated; the weight gradient is reduced in a
+ *             fixed order (deterministic).
+ *   workspace: mgb_conv1d_workspace_bytes(...) bytes of scratch, not kept between calls.
+ * mgb_step_embedding: DiffusionEmbedding (model/blocks.py:899-913), emb [B][dim] = [sin(t f_i) | cos(t f_i)].
+ */
+int mgb_conv1d_out_len(int Tin, int k, int stride);
+size_t mgb_conv1d_workspace_bytes(int B, int Tin, int Cin, int Cout, int k, int stride);
+int mgb_conv1d_forward(const float* x, const float* w, const float* bias, const float* rowbias, float* y, float* pre,
+                       int B, int Tin, int Cin, int Cout, int k, int stride, int act,
+                       void* workspace, size_t workspace_bytes, void* stream);
+int mgb_conv1d_backward(const float* x, const float* w, const float* rowbias, const float* y, const float* pre,
+                        const float* grad_y, float* grad_x, float* grad_w, float* grad_bias, float* grad_rowbias,
+                        int B, int Tin, int Cin, int Cout, int k, int stride, int act,
+                        void* workspace, size_t workspace_bytes, void* stream);
+int mgb_step_embedding(const int64_t* t, float* emb, int B, int dim, void* stream);
 
 /*
  * Training (BASELINE configs[4]): Denoiser forward that keeps the activations its backward needs, and the

@@ -5,5 +5,7 @@ Only the hot path lives here: the sm_100a CUDA library (``csrc/`` -> ``libmixgan
 """
 from .modules import Denoiser  # noqa: F401
 from .diffusion import GaussianDiffusion  # noqa: F401
+from .discriminator import JCUDiscriminator  # noqa: F401
+from .length_regulator import LengthRegulator  # noqa: F401
 
-__all__ = ["Denoiser", "GaussianDiffusion"]
+__all__ = ["Denoiser", "GaussianDiffusion", "JCUDiscriminator", "LengthRegulator"]

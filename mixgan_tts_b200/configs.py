@@ -44,6 +44,9 @@ def model_config(dataset: str = "LJSpeech", multi_speaker: bool | None = None) -
     cfg = {
         "transformer": {"encoder_hidden": 256},
         "denoiser": den,
+        # config/*/model.yaml:40-46 (JCU discriminator, the training config)
+        "discriminator": {"n_layer": 3, "n_uncond_layer": 2, "n_cond_layer": 2, "n_channels": [64, 128, 512, 128, 1],
+                          "kernel_sizes": [3, 5, 5, 5, 3], "strides": [1, 2, 2, 1, 1]},
         "multi_speaker": False if multi_speaker is None else bool(multi_speaker),
         "max_seq_len": 1000 if dataset == "LJSpeech" else 1500,
     }

@@ -63,6 +63,48 @@ def make_denoiser_weights(seed: int = 0, *, n_mel: int = 80, channels: int = 256
     return w
 
 
+def make_discriminator_weights(seed: int = 0, *, n_mel: int = 80, residual_channels: int = 256, multi_speaker: bool = False,
+                               cfg: dict | None = None, weight_std: float = 0.02) -> dict:
+    """``{state_dict key: float32 ndarray}`` for one ``JCUDiscriminator`` (model/mixgantts.py:189-250): xavier-uniform
+    bias-free linears, N(0, weight_std^2) conv weights (``weights_init``), PyTorch-default conv biases.  Tests use a larger
+    ``weight_std`` than the reference's 0.02 so that the logits are not dominated by the biases."""
+    cfg = cfg or {"n_layer": 3, "n_uncond_layer": 2, "n_cond_layer": 2, "n_channels": [64, 128, 512, 128, 1],
+                  "kernel_sizes": [3, 5, 5, 5, 3], "strides": [1, 2, 2, 1, 1]}
+    g = _rng(seed)
+    w = {}
+
+    def linear(name, cout, cin):
+        w[f"{name}.linear.weight"] = _uniform(g, (cout, cin), np.sqrt(6.0 / (cin + cout)))
+
+    def conv(name, cout, cin, k):
+        w[f"{name}.conv.weight"] = (g.standard_normal((cout, cin, k), dtype=np.float32) * np.float32(weight_std))
+        w[f"{name}.conv.bias"] = _uniform(g, (cout,), 1.0 / np.sqrt(cin * k))
+
+    ch, ks, nl = cfg["n_channels"], cfg["kernel_sizes"], cfg["n_layer"]
+    linear("input_projection", 2 * n_mel, 2 * n_mel)
+    linear("mlp.0", 4 * residual_channels, residual_channels)
+    linear("mlp.2", ch[nl - 1], 4 * residual_channels)
+    if multi_speaker:
+        linear("spk_mlp.0", ch[nl - 1], residual_channels)
+    for i in range(nl):
+        conv(f"conv_block.{i}", ch[i], ch[i - 1] if i else 2 * n_mel, ks[i])
+    for i in range(nl, nl + cfg["n_uncond_layer"]):
+        conv(f"uncond_conv_block.{i - nl}", ch[i], ch[i - 1], ks[i])
+    for i in range(nl, nl + cfg["n_cond_layer"]):
+        conv(f"cond_conv_block.{i - nl}", ch[i], ch[i - 1], ks[i])
+    return w
+
+
+def make_discriminator_inputs(seed: int, B: int, T: int, K: int, *, n_mel: int = 80, multi_speaker: bool = False) -> dict:
+    """``x_ts``, ``x_t_prevs``, ``x_t_prev_preds`` ``[B,T,M]`` (normalised-mel scale), ``spk [B,256]`` or None, ``t [B]``."""
+    g = _rng(seed)
+    return {"x_ts": g.standard_normal((B, T, n_mel), dtype=np.float32),
+            "x_t_prevs": g.standard_normal((B, T, n_mel), dtype=np.float32) * np.float32(0.7),
+            "x_t_prev_preds": g.standard_normal((B, T, n_mel), dtype=np.float32) * np.float32(0.7),
+            "spk": g.standard_normal((B, 256), dtype=np.float32) if multi_speaker else None,
+            "t": np.array([(K - 1 - b) % K for b in range(B)], dtype=np.int64)}
+
+
 def weights_digest(w: dict) -> str:
     h = hashlib.sha256()
     for k in sorted(w):

@@ -146,3 +146,54 @@ def test_length_regulator_oracle_matches_reference_golden():
         assert np.array_equal(durations_from_log(log_d, c), g[f"dur_from_log/{c}"]), c
     # the cropped case really crops: some utterance is longer than max_len and keeps its true length
     assert g["cropped/mel_len"].max() > g["cropped/out"].shape[1]
+
+
+# ---- JCU discriminator: oracle pinned by outputs and gradients of the REAL reference -------------------------------------
+def _jcu_oracle_run(name):
+    import os
+    import sys
+    import torch
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    from make_golden_jcu import JCU_CASES, WEIGHT_STD
+    from mixgan_tts_b200 import configs, synth
+    from oracle.discriminator import fm_loss, jcu_forward, lsgan_jcu_loss
+    multi, B, T, wseed, iseed = JCU_CASES[name]
+    mc = configs.make_configs("LJSpeech", "naive", multi)[2]
+    Wn = synth.make_discriminator_weights(wseed, multi_speaker=multi, weight_std=WEIGHT_STD)
+    W = {k: torch.from_numpy(v).requires_grad_(True) for k, v in Wn.items()}
+    inp = synth.make_discriminator_inputs(iseed, B, T, 4, multi_speaker=multi)
+    tt = lambda k: None if inp[k] is None else torch.from_numpy(inp[k])
+    preds = tt("x_t_prev_preds").requires_grad_(True)
+    run = lambda prev: jcu_forward(W, mc["discriminator"], tt("x_ts"), prev, tt("spk"), tt("t"), multi_speaker=multi)
+    fc, fu = run(preds)
+    rc, ru = run(tt("x_t_prevs"))
+    fcd, fud = run(preds.detach())
+    d_loss = lsgan_jcu_loss(rc[-1], ru[-1], 1.0) + lsgan_jcu_loss(fcd[-1], fud[-1], 0.0)
+    d_grads = dict(zip(W, torch.autograd.grad(d_loss, list(W.values()), retain_graph=True, allow_unused=True)))
+    n_layers = mc["discriminator"]["n_layer"] + mc["discriminator"]["n_cond_layer"]
+    g_loss = lsgan_jcu_loss(fc[-1], fu[-1], 1.0) + fm_loss(rc, ru, fc, fu, n_layers)
+    g_preds = torch.autograd.grad(g_loss, preds)[0]
+    return Wn, (fc, fu, rc, ru), d_loss, d_grads, g_loss, g_preds
+
+
+def test_jcu_discriminator_oracle_matches_reference_golden():
+    import os
+    import torch
+    from mixgan_tts_b200 import synth
+    from helpers import rel_l2
+    for name in ("jcu_lj_B3_T50", "jcu_spk_B2_T37"):
+        g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name + ".npz"))
+        Wn, feats, d_loss, d_grads, g_loss, g_preds = _jcu_oracle_run(name)
+        assert synth.weights_digest(Wn) == str(g["weights_sha256"])
+        for lst, key in zip(feats, ("fake_cond", "fake_uncond", "real_cond", "real_uncond")):
+            for i, f in enumerate(lst):
+                assert tuple(f.shape) == g[f"{key}/{i}"].shape
+                assert rel_l2(f.detach(), g[f"{key}/{i}"]) < 2e-5, (name, key, i)
+        assert abs(float(d_loss) - float(g["d_loss"])) < 2e-5 * abs(float(g["d_loss"]))
+        assert abs(float(g_loss) - float(g["g_loss"])) < 2e-5 * abs(float(g["g_loss"]))
+        assert rel_l2(g_preds, g["g_grad_preds"]) < 2e-5
+        for k, gr in d_grads.items():
+            flat = gr.detach().reshape(-1).double()
+            assert abs(float(flat.norm()) - float(g[f"gnorm/{k}"])) < 2e-5 * max(float(g[f"gnorm/{k}"]), 1e-6), (name, k)
+            idx = torch.from_numpy(synth.grad_sample_index(flat.numel()))
+            assert rel_l2(flat[idx], g[f"gsample/{k}"]) < 2e-5, (name, k)

@@ -22,6 +22,9 @@
  *   mgb_durations_from_log duration rounding at inference        model/linguistic_encoder.py:310-314
  *   mgb_conv1d_forward / mgb_conv1d_backward / mgb_step_embedding
  *                          JCUDiscriminator.forward + autograd   model/mixgantts.py:186-288 (train.py:126-184)
+ *   mgb_auxdec_forward     decoder + mel_linear + postnet        model/mixgantts.py:139-143
+ *                          (Decoder transformer/Models.py:103-171, PostNet transformer/Layers.py:67-137)
+ *   mgb_hifigan_forward    hifigan Generator.forward             hifigan/models.py:151-166 (utils/model.py:103-121)
  *
  * Conventions
  *   - Plain pointers and sizes only; no torch types.  All tensors are DEVICE pointers to
@@ -261,6 +264,73 @@ int mgb_denoiser_backward(const mgb_model_dims* dims, int precision, const float
                           void* workspace, size_t workspace_bytes, void* stream);
 /* Debug: synchronously read the watchdog word of the bf16 training kernels from a workspace used with (B, T). */
 int mgb_train_debug_status(const mgb_model_dims* dims, int B, int T, const void* workspace, int* host_status);
+
+/*
+ * Aux decoder (second half): the FastSpeech2 decoder + mel_linear + PostNet that produce the coarse
+ * mel the shallow reverse diffusion starts from.  Replaces, at inference (model/mixgantts.py:139-143),
+ *     coarse = mel_linear(decoder(output, mel_masks));  coarse = postnet(coarse) + coarse
+ * i.e. Decoder.forward transformer/Models.py:137-171, FFTBlock transformer/Layers.py:11-31, MultiHeadAttention /
+ * PositionwiseFeedForward transformer/SubLayers.py:8-97, ScaledDotProductAttention transformer/Modules.py:6-24,
+ * PostNet transformer/Layers.py:67-137 (BatchNorm1d in eval mode).  Every matrix product runs on tcgen05 with fp16
+ * operands and fp32 accumulation; residual sums, LayerNorm and softmax statistics are fp32.
+ *   flat   : ONE fp32 device array of the parameters in this order (state_dict order without position_enc and
+ *            num_batches_tracked):  for each FFT block: slf_attn.{w_qs,w_ks,w_vs}.{weight,bias}, slf_attn.layer_norm.{weight,
+ *            bias}, slf_attn.fc.{weight,bias}, pos_ffn.w_1.{weight,bias}, pos_ffn.w_2.{weight,bias}, pos_ffn.layer_norm.{weight,
+ *            bias};  mel_linear.{weight,bias};  for each PostNet layer: conv.{weight,bias}, batch norm {weight, bias,
+ *            running_mean, running_var}.
+ *   x      : [B][T][d_model] decoder input (the variance adaptor's output), pos : [T][d_model] position encoding rows
+ *            (Decoder.position_enc[0, :T], or the sinusoid table for T > max_seq_len as Models.py:146-153)
+ *   lens   : int32 [B] valid frames per utterance or NULL (= T): keys at or beyond it are masked, rows at or beyond it are
+ *            zero-filled after every sub-layer (the reference's mel_masks)
+ *   coarse : [B][T][n_mel] = postnet(mel) + mel;  dec_out [B][T][d_model] and mel_before [B][T][n_mel] are optional.
+ */
+typedef struct mgb_auxdec_dims {
+  int32_t n_mel;          /* 80   */
+  int32_t d_model;        /* 256  decoder_hidden */
+  int32_t n_head;         /* 2    decoder_head   */
+  int32_t d_inner;        /* 1024 conv_filter_size */
+  int32_t ffn_kernel;     /* 9    conv_kernel_size[0] (the second FFN convolution is k = 1) */
+  int32_t layers;         /* 6    decoder_layer */
+  int32_t postnet_dim;    /* 512  */
+  int32_t postnet_kernel; /* 5    */
+  int32_t postnet_layers; /* 5    */
+} mgb_auxdec_dims;
+size_t mgb_auxdec_flat_count(const mgb_auxdec_dims* dims);
+size_t mgb_auxdec_packed_bytes(const mgb_auxdec_dims* dims);
+size_t mgb_auxdec_workspace_bytes(const mgb_auxdec_dims* dims, int B, int T);
+int mgb_auxdec_pack(const mgb_auxdec_dims* dims, const float* flat, void* packed, size_t packed_bytes, void* stream);
+int mgb_auxdec_forward(const mgb_auxdec_dims* dims, const void* packed, const float* x, const float* pos, const int32_t* lens,
+                       float* coarse, float* dec_out, float* mel_before, int B, int T, void* workspace,
+                       size_t workspace_bytes, void* stream);
+int mgb_auxdec_debug_status(const mgb_auxdec_dims* dims, int B, int T, const void* workspace, int* host_status);
+
+/*
+ * HiFi-GAN generator: mel -> waveform after the diffusion decoder.  Replaces Generator.forward
+ * hifigan/models.py:151-166 (ResBlock.forward :96-103) as utils/model.py:103-121 (vocoder_infer) calls it, weight norm
+ * removed (utils/model.py:99).  tcgen05 implicit-GEMM convolutions, fp16 operands, fp32 accumulation and residual sums.
+ *   flat : fp32 parameters in state_dict order after remove_weight_norm: conv_pre.{weight,bias}, ups.i.{weight,bias} for all
+ *          i, resblocks.r.{convs1.0,convs1.1,convs1.2,convs2.0,convs2.1,convs2.2}.{weight,bias} for all r, conv_post.{weight,bias}
+ *   mel  : [B][T][n_mel] frames-major (what GaussianDiffusion.forward returns; the reference transposes to [B][n_mel][T]
+ *          before the call), wav : [B][T * mgb_hifigan_hop(dims)]
+ */
+typedef struct mgb_hifigan_dims {
+  int32_t n_mel;                /* 80  */
+  int32_t initial_channel;      /* 512 upsample_initial_channel */
+  int32_t n_up;                 /* 4   */
+  int32_t up_rates[8];          /* 8, 8, 2, 2 */
+  int32_t up_kernels[8];        /* 16, 16, 4, 4 */
+  int32_t n_res;                /* 3 resblocks per stage ("resblock": "1") */
+  int32_t res_kernels[4];       /* 3, 7, 11 */
+  int32_t res_dilations[4][3];  /* 1, 3, 5 each */
+} mgb_hifigan_dims;
+size_t mgb_hifigan_flat_count(const mgb_hifigan_dims* dims);
+size_t mgb_hifigan_packed_bytes(const mgb_hifigan_dims* dims);
+int mgb_hifigan_hop(const mgb_hifigan_dims* dims);
+size_t mgb_hifigan_workspace_bytes(const mgb_hifigan_dims* dims, int B, int T);
+int mgb_hifigan_pack(const mgb_hifigan_dims* dims, const float* flat, void* packed, size_t packed_bytes, void* stream);
+int mgb_hifigan_forward(const mgb_hifigan_dims* dims, const void* packed, const float* mel, float* wav, int B, int T,
+                        void* workspace, size_t workspace_bytes, void* stream);
+int mgb_hifigan_debug_status(const mgb_hifigan_dims* dims, int B, int T, const void* workspace, int* host_status);
 
 #ifdef __cplusplus
 }

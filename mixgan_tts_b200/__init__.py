@@ -7,5 +7,7 @@ from .modules import Denoiser  # noqa: F401
 from .diffusion import GaussianDiffusion  # noqa: F401
 from .discriminator import JCUDiscriminator  # noqa: F401
 from .length_regulator import LengthRegulator  # noqa: F401
+from .aux_decoder import AuxDecoder  # noqa: F401
+from .vocoder import Generator  # noqa: F401
 
-__all__ = ["Denoiser", "GaussianDiffusion", "JCUDiscriminator", "LengthRegulator"]
+__all__ = ["Denoiser", "GaussianDiffusion", "JCUDiscriminator", "LengthRegulator", "AuxDecoder", "Generator"]

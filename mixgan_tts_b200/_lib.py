@@ -62,6 +62,19 @@ SIGNATURES = {
     "mgb_length_regulate": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _Z, _P]),
     "mgb_length_regulate_backward": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
     "mgb_mask_from_lengths": (_I, [_P, _P, _I, _I, _P]),
+    "mgb_auxdec_flat_count": (_Z, [_P]),
+    "mgb_auxdec_packed_bytes": (_Z, [_P]),
+    "mgb_auxdec_workspace_bytes": (_Z, [_P, _I, _I]),
+    "mgb_auxdec_pack": (_I, [_P, _P, _P, _Z, _P]),
+    "mgb_auxdec_forward": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P, _Z, _P]),
+    "mgb_auxdec_debug_status": (_I, [_P, _I, _I, _P, _P]),
+    "mgb_hifigan_flat_count": (_Z, [_P]),
+    "mgb_hifigan_packed_bytes": (_Z, [_P]),
+    "mgb_hifigan_hop": (_I, [_P]),
+    "mgb_hifigan_workspace_bytes": (_Z, [_P, _I, _I]),
+    "mgb_hifigan_pack": (_I, [_P, _P, _P, _Z, _P]),
+    "mgb_hifigan_forward": (_I, [_P, _P, _P, _P, _I, _I, _P, _Z, _P]),
+    "mgb_hifigan_debug_status": (_I, [_P, _I, _I, _P, _P]),
 }
 
 # include/mixgan_b200_probe.h: exported by the test-only debug library (libmixgan_b200_dbg.so), never by the product one

@@ -42,7 +42,9 @@ def model_config(dataset: str = "LJSpeech", multi_speaker: bool | None = None) -
     elif dataset != "LJSpeech":
         raise ValueError(f"unknown dataset {dataset!r}")
     cfg = {
-        "transformer": {"encoder_hidden": 256},
+        # config/*/model.yaml:1-13 (the decoder keys are read by the aux decoder)
+        "transformer": {"encoder_hidden": 256, "decoder_layer": 6, "decoder_head": 2, "decoder_hidden": 256,
+                        "conv_filter_size": 1024, "conv_kernel_size": 9, "decoder_dropout": 0.2},
         "denoiser": den,
         # config/*/model.yaml:40-46 (JCU discriminator, the training config)
         "discriminator": {"n_layer": 3, "n_uncond_layer": 2, "n_cond_layer": 2, "n_channels": [64, 128, 512, 128, 1],

@@ -105,6 +105,117 @@ def make_discriminator_inputs(seed: int, B: int, T: int, K: int, *, n_mel: int =
             "t": np.array([(K - 1 - b) % K for b in range(B)], dtype=np.int64)}
 
 
+AUXDEC_CFG = {"n_mel": 80, "d_model": 256, "n_head": 2, "d_inner": 1024, "ffn_kernel": 9, "layers": 6,
+              "postnet_dim": 512, "postnet_kernel": 5, "postnet_layers": 5, "max_seq_len": 1000}
+
+
+def sinusoid_table(n_position: int, d_hid: int) -> np.ndarray:
+    """``get_sinusoid_encoding_table`` (transformer/Models.py:11-31), float64 numpy then one cast, as the reference does
+    through ``torch.FloatTensor``."""
+    pos = np.arange(n_position)[:, None].astype(np.float64)
+    hid = np.arange(d_hid)[None, :]
+    tab = pos / np.power(10000, 2 * (hid // 2) / d_hid)
+    tab[:, 0::2] = np.sin(tab[:, 0::2])
+    tab[:, 1::2] = np.cos(tab[:, 1::2])
+    return tab.astype(np.float32)
+
+
+def make_auxdec_weights(seed: int = 0, cfg: dict | None = None) -> dict:
+    """``{key: float32 ndarray}`` for the aux decoder with the reference's ``MixGANTTS`` state_dict keys
+    (``decoder.*`` transformer/Models.py:103-135, ``mel_linear.*`` model/mixgantts.py:59-62, ``postnet.*``
+    transformer/Layers.py:67-126).  PyTorch-default uniform init for linears / convolutions; LayerNorm and BatchNorm affine
+    parameters and the BatchNorm running statistics are perturbed so that folding them is actually tested."""
+    c = dict(AUXDEC_CFG, **(cfg or {}))
+    g = _rng(seed)
+    D, H, M, P = c["d_model"], c["d_inner"], c["n_mel"], c["postnet_dim"]
+    w = {"decoder.position_enc": sinusoid_table(c["max_seq_len"] + 1, D)[None]}
+
+    def lin(name, cout, cin, k=None):
+        fan = cin * (k or 1)
+        shape = (cout, cin) if k is None else (cout, cin, k)
+        w[f"{name}.weight"] = _uniform(g, shape, 1.0 / np.sqrt(fan))
+        w[f"{name}.bias"] = _uniform(g, (cout,), 1.0 / np.sqrt(fan))
+
+    def norm(name, n):
+        w[f"{name}.weight"] = (1.0 + 0.1 * g.standard_normal((n,), dtype=np.float32)).astype(np.float32)
+        w[f"{name}.bias"] = (0.1 * g.standard_normal((n,), dtype=np.float32)).astype(np.float32)
+
+    for i in range(c["layers"]):
+        p = f"decoder.layer_stack.{i}"
+        lin(f"{p}.slf_attn.w_qs", D, D); lin(f"{p}.slf_attn.w_ks", D, D); lin(f"{p}.slf_attn.w_vs", D, D)
+        norm(f"{p}.slf_attn.layer_norm", D)
+        lin(f"{p}.slf_attn.fc", D, D)
+        lin(f"{p}.pos_ffn.w_1", H, D, c["ffn_kernel"]); lin(f"{p}.pos_ffn.w_2", D, H, 1)
+        norm(f"{p}.pos_ffn.layer_norm", D)
+    lin("mel_linear", M, D)
+    for i in range(c["postnet_layers"]):
+        cin = M if i == 0 else P
+        cout = M if i == c["postnet_layers"] - 1 else P
+        lin(f"postnet.convolutions.{i}.0.conv", cout, cin, c["postnet_kernel"])
+        b = f"postnet.convolutions.{i}.1"
+        w[f"{b}.weight"] = (0.5 + g.random((cout,), dtype=np.float32)).astype(np.float32)
+        w[f"{b}.bias"] = (0.1 * g.standard_normal((cout,), dtype=np.float32)).astype(np.float32)
+        w[f"{b}.running_mean"] = (0.2 * g.standard_normal((cout,), dtype=np.float32)).astype(np.float32)
+        w[f"{b}.running_var"] = (0.5 + g.random((cout,), dtype=np.float32)).astype(np.float32)
+        w[f"{b}.num_batches_tracked"] = np.array(100, dtype=np.int64)
+    return w
+
+
+def make_auxdec_inputs(seed: int, B: int, T: int, *, d_model: int = 256, min_len_frac: float = 0.4) -> dict:
+    """Decoder input ``x [B,T,256]`` (zero at padded frames, as the variance adaptor's length regulator leaves it),
+    ``lens [B]`` (``lens[0] = T``) and ``pad_mask [B,T]`` (True = padding, the convention at ``self.decoder(output, mel_masks)``)."""
+    g = _rng(seed)
+    x = g.standard_normal((B, T, d_model), dtype=np.float32)
+    lens = g.integers(max(1, int(T * min_len_frac)), T + 1, size=(B,), dtype=np.int64)
+    lens[0] = T
+    pad = np.arange(T)[None, :] >= lens[:, None]
+    x[pad] = 0.0
+    return {"x": x, "lens": lens, "pad_mask": pad}
+
+
+HIFIGAN_CFG = {"resblock": "1", "upsample_rates": [8, 8, 2, 2], "upsample_kernel_sizes": [16, 16, 4, 4],
+               "upsample_initial_channel": 512, "resblock_kernel_sizes": [3, 7, 11],
+               "resblock_dilation_sizes": [[1, 3, 5], [1, 3, 5], [1, 3, 5]], "num_mels": 80}   # hifigan/config.json
+
+
+def make_hifigan_weights(seed: int = 0, cfg: dict | None = None, gain: float = 1.0) -> dict:
+    """``{key: float32 ndarray}`` for ``hifigan.Generator`` AFTER ``remove_weight_norm`` (plain ``weight`` / ``bias`` keys,
+    hifigan/models.py:112-173).  The reference's N(0, 0.01) init makes every activation vanish after two layers, so weights
+    are drawn variance-preserving (std = gain / sqrt(fan_in)) to keep the parity test meaningful at every depth."""
+    c = dict(HIFIGAN_CFG, **(cfg or {}))
+    g = _rng(seed)
+    w = {}
+
+    def conv(name, cout, cin, k, transposed=False, fan=None):
+        fan = fan or cin * k
+        shape = (cin, cout, k) if transposed else (cout, cin, k)
+        w[f"{name}.weight"] = (g.standard_normal(shape, dtype=np.float32) * np.float32(gain / np.sqrt(fan)))
+        w[f"{name}.bias"] = (0.1 * g.standard_normal((cout,), dtype=np.float32)).astype(np.float32)
+
+    C0 = c["upsample_initial_channel"]
+    conv("conv_pre", C0, c["num_mels"], 7)
+    for i, (u, k) in enumerate(zip(c["upsample_rates"], c["upsample_kernel_sizes"])):
+        conv(f"ups.{i}", C0 >> (i + 1), C0 >> i, k, transposed=True, fan=(C0 >> i) * k // u)
+    nk = len(c["resblock_kernel_sizes"])
+    for i in range(len(c["upsample_rates"])):
+        ch = C0 >> (i + 1)
+        for j, k in enumerate(c["resblock_kernel_sizes"]):
+            for m in range(3):
+                conv(f"resblocks.{i * nk + j}.convs1.{m}", ch, ch, k)
+            for m in range(3):
+                conv(f"resblocks.{i * nk + j}.convs2.{m}", ch, ch, k)
+    conv("conv_post", 1, C0 >> len(c["upsample_rates"]), 7)
+    w["conv_post.weight"] *= np.float32(0.3)       # keep the final tanh out of saturation (it would hide errors)
+    return w
+
+
+def make_mel(seed: int, B: int, T: int, n_mel: int = 80) -> np.ndarray:
+    """A log-mel-like batch ``[B, T, n_mel]`` in the range the vocoder sees."""
+    g = _rng(seed)
+    m = g.standard_normal((B, T, n_mel), dtype=np.float32) * np.float32(2.0) - np.float32(5.0)
+    return np.clip(m, -11.5129, 2.0).astype(np.float32)
+
+
 def weights_digest(w: dict) -> str:
     h = hashlib.sha256()
     for k in sorted(w):

@@ -520,6 +520,96 @@ def bench_c4(ctx, prec, steps, warmup):
             "gpu_launches": int(launches)}
 
 
+def bench_stages(ctx, prec, steps, warmup):
+    """The stages either side of the path and the chain through them: the aux decoder that makes
+    the coarse mel, `shallow` K=1 reverse diffusion started from it, and the HiFi-GAN generator; one GPU's share (replicas)."""
+    import numpy as np
+    from mixgan_tts_b200 import AuxDecoder, Generator, _lib, configs, synth
+    from mixgan_tts_b200.pipeline import BatchSynthesizer
+    torch, dev, lib = ctx.torch, ctx.dev, _lib.load()
+    T = T_FRAMES
+    _, pc, mc, _ = configs.make_configs("LJSpeech", "shallow")
+    aux = AuxDecoder(pc, mc)
+    aux.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in synth.make_auxdec_weights(0).items()})
+    aux = aux.to(dev).eval()
+    voc = Generator(synth.HIFIGAN_CFG)
+    voc.load_state_dict({k: torch.from_numpy(v) for k, v in synth.make_hifigan_weights(0).items()})
+    voc = voc.to(dev).eval()
+    gd = make_gd(ctx, "LJSpeech", "shallow", False, prec)
+    out = {}
+    # -- aux decoder alone, B = 64
+    B = B_PER_GPU
+    sets = []
+    for i in range(3):
+        inp = synth.make_auxdec_inputs(300 + i + 10 * ctx.rank, B, T, min_len_frac=0.5)
+        sets.append((torch.from_numpy(inp["x"]).to(dev), torch.from_numpy(inp["pad_mask"]).to(dev), inp["lens"]))
+    n0 = lib.mgb_launch_count()
+    ms = ctx.timed(lambda i: aux(sets[i % 3][0], sets[i % 3][1]), steps, warmup)
+    launches = (lib.mgb_launch_count() - n0) // (steps + warmup)
+    fixed = 6 * (4 * 2 * 256 * 256 + 2 * 256 * 1024 * 9 + 2 * 1024 * 256) + 2 * 256 * 80 + 2 * 5 * (80 * 512 + 3 * 512 * 512 + 512 * 80)
+    att = float(np.mean([sum(6 * 2 * 2 * 2 * 128 * float(l) ** 2 for l in s[2]) for s in sets]))
+    fl = fixed * B * T + att
+    pk = peaks(ms * 1e-3)
+    peak, psrc = pk["tensor_tflops"], pk["source"]
+    out["aux_decoder"] = {
+        "value": ctx.world * B * T * steps / (ms * 1e-3), "unit": UNIT, "ms_per_call": ms / steps, "B": B, "T": T, "dtype": "f16",
+        "gpu_launches_per_call": int(launches),
+        "roofline": {"bound": "tensor", "achieved": fl * steps / (ms * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s",
+                     "frac": fl * steps / (ms * 1e-3) / 1e12 / peak, "peak_source": psrc,
+                     "flops_per_call": fl, "flops_note": f"{fixed} FLOP per frame (linears, conv FFN, mel_linear, PostNet) + attention over valid frames"},
+        "what": "FastSpeech2 decoder (6 FFT blocks) + mel_linear + PostNet, the coarse mel of the shallow configs "
+                "(model/mixgantts.py:139-143); tcgen05 fp16 operands, parity 3e-4 against the reference-made goldens"}
+    # -- HiFi-GAN alone, B = 16
+    Bv = 16
+    mels = [torch.from_numpy(synth.make_mel(400 + i + 10 * ctx.rank, Bv, T)).to(dev) for i in range(2)]
+    vsteps = max(2, steps // 2)
+    n0 = lib.mgb_launch_count()
+    ms = ctx.timed(lambda i: voc.forward_frames(mels[i % 2]), vsteps, 2)
+    launches = (lib.mgb_launch_count() - n0) // (vsteps + 2)
+    C0, fpf, rate = 512, 2.0 * 80 * 512 * 7, 1
+    for i, (u, k) in enumerate(zip(synth.HIFIGAN_CFG["upsample_rates"], synth.HIFIGAN_CFG["upsample_kernel_sizes"])):
+        fpf += 2.0 * (C0 >> i) * (C0 >> (i + 1)) * k * rate
+        rate *= u
+        fpf += rate * sum(2.0 * (C0 >> (i + 1)) ** 2 * kk * 6 for kk in synth.HIFIGAN_CFG["resblock_kernel_sizes"])
+    fpf += rate * 2.0 * (C0 >> 4) * 7
+    pk = peaks(ms * 1e-3)
+    peak, psrc = pk["tensor_tflops"], pk["source"]
+    out["vocoder"] = {
+        "value": ctx.world * Bv * T * vsteps / (ms * 1e-3), "unit": UNIT, "ms_per_call": ms / vsteps, "B": Bv, "T": T, "dtype": "f16",
+        "audio_seconds_per_s": ctx.world * Bv * T * 256 / 22050 * vsteps / (ms * 1e-3), "gpu_launches_per_call": int(launches),
+        "roofline": {"bound": "tensor", "achieved": fpf * Bv * T * vsteps / (ms * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s",
+                     "frac": fpf * Bv * T * vsteps / (ms * 1e-3) / 1e12 / peak, "peak_source": psrc, "flops_per_frame": fpf},
+        "what": "HiFi-GAN V1 generator, mel -> 22.05 kHz waveform (hifigan/models.py:112-173); tcgen05 fp16 operands, fp32 "
+                "residual sums; parity 8.5e-4 against the reference-made goldens"}
+    # -- chain from the variance adaptor's output: aux decoder -> shallow K=1 reverse diffusion (-> vocoder), host to host
+    NB = 4
+    cond_dt = torch.bfloat16 if prec == "bf16" else torch.float16
+    batches = []
+    for i in range(NB):
+        inp = synth.make_auxdec_inputs(500 + i + 10 * ctx.rank, Bv, T, min_len_frac=0.5)
+        batches.append((torch.from_numpy(inp["x"]).to(cond_dt).pin_memory(), torch.from_numpy(inp["pad_mask"]).pin_memory(), None, None))
+    for name, v in (("mel", None), ("wav", voc)):
+        pipe = BatchSynthesizer(gd, dev, aux_decoder=aux, vocoder=v)
+
+        def run(_):
+            acc = 0.0
+            for o in pipe.run(iter(batches)):
+                acc += float(o.reshape(-1)[0])
+            return acc
+        ms = ctx.timed(run, max(2, steps // 4), 1)
+        n = max(2, steps // 4)
+        fr = ctx.world * NB * Bv * T
+        out["chain_" + name] = {
+            "value": fr * n / (ms * 1e-3), "unit": UNIT, "ms_per_pass": ms / n, "batches": NB, "B": Bv, "T": T,
+            "audio_seconds_per_s": fr * 256 / 22050 * n / (ms * 1e-3),
+            "h2d_bytes_per_pass": int(NB * Bv * T * (256 * 2 + 1)),
+            "d2h_bytes_per_pass": int(NB * Bv * T * (80 * 4 if v is None else 256 * 4)),
+            "api": "BatchSynthesizer(gd, aux_decoder=..., vocoder=...).run: pinned host decoder input (= conditioner, 16-bit) + mask in, "
+                   + ("pinned host mel out" if v is None else "pinned host waveform out")
+                   + "; aux decoder -> shallow start -> K=1 reverse diffusion" + ("" if v is None else " -> HiFi-GAN") + " on the device"}
+    return out
+
+
 def bench_train(ctx, prec, steps, warmup, B):
     """BASELINE configs[4] on this repo's path: the diffusion decoder's training branch (q_sample x2, Denoiser forward, clamp,
     posterior sample), backward through the library, data-parallel gradient all-reduce (NCCL, bucketed, overlapped with the
@@ -577,22 +667,90 @@ def bench_train(ctx, prec, steps, warmup, B):
         dp_check = {"synced_vs_mean_of_ranks_rel_l2": err, "synced_vs_local_rel_l2": differs, "ok": bool(err < 1e-5 and differs > 1e-3)}
         opt.zero_grad(set_to_none=True)
 
+    # ---- the full GAN step of train.py:126-184 restricted to this repo's modules: D phase (G forward, 2 x D forward, D backward,
+    #      clip, Adam on D) then G phase (G forward again, 2 x D forward, adversarial + mel L1 + feature-matching losses,
+    #      backward through D into the Denoiser, clip, Adam on G).  Optimizers as utils/model.py:32-38 (Adam, betas (0.5, 0.9),
+    #      lr 1e-4 / 2e-4), lambda_fm = 10 and grad_clip_thresh = 1 (config/LJSpeech/train.yaml:8-13,29).
+    from mixgan_tts_b200 import JCUDiscriminator, configs
+    from mixgan_tts_b200.discriminator import feature_matching_loss, get_lsgan_losses_fn
+    _, pc, mc, tc = configs.make_configs("LJSpeech", "naive")
+    D = JCUDiscriminator(pc, mc, tc)
+    D.load_state_dict({k: torch.from_numpy(v) for k, v in synth.make_discriminator_weights(5).items()})
+    D = D.to(dev).train()
+    g_params, d_params = list(gd.denoise_fn.parameters()), list(D.parameters())
+    optG = torch.optim.Adam(g_params, lr=1e-4, betas=(0.5, 0.9), fused=True)
+    optD = torch.optim.Adam(d_params, lr=2e-4, betas=(0.5, 0.9), fused=True)
+    d_loss_fn, g_loss_fn = get_lsgan_losses_fn()
+    n_fm = mc["discriminator"]["n_layer"] + mc["discriminator"]["n_cond_layer"]
+    LAMBDA_FM, CLIP = 10.0, 1.0
+
+    def reduce_d_grads():
+        flat = torch.cat([p.grad.reshape(-1) for p in d_params])
+        ctx.dist.all_reduce(flat)
+        flat /= ctx.world
+        torch._foreach_copy_([p.grad for p in d_params], list(flat.split([p.numel() for p in d_params])))
+
+    def gan_step(i, with_sync=True):
+        s = sets[i % NSETS]
+        valid = (~s["pad"]).unsqueeze(-1)
+        # D phase (train.py:126-146): the generator forward runs in grad mode there, as here
+        gd.denoise_fn.grad_sync = None
+        out = gd(s["mel"], s["cond"].detach().requires_grad_(True), None, s["pad"])
+        x_ts, x_prev, x_pred, t = [o.detach() for o in out[1:5]]
+        fc, fu = D(x_ts, x_pred, None, t)
+        rc, ru = D(x_ts, x_prev, None, t)
+        r_loss, f_loss = d_loss_fn(rc[-1], ru[-1], fc[-1], fu[-1])
+        (r_loss + f_loss).backward()
+        if ctx.world > 1 and with_sync:
+            reduce_d_grads()
+        torch.nn.utils.clip_grad_norm_(d_params, CLIP)
+        optD.step()
+        optD.zero_grad(set_to_none=False)
+        # G phase (train.py:148-184)
+        gd.denoise_fn.grad_sync = sync if with_sync else None
+        out = gd(s["mel"], s["cond"].detach().requires_grad_(True), None, s["pad"])
+        fc, fu = D(out[1], out[3], None, out[4])
+        rc, ru = D(out[1], out[2], None, out[4])
+        adv = g_loss_fn(fc[-1], fu[-1])
+        mel_loss = torch.nn.functional.l1_loss(gd.denorm_spec(out[0]) * valid, s["mel"] * valid)   # model/loss.py:175-176,229-234
+        fm = LAMBDA_FM * feature_matching_loss(rc, ru, fc, fu, n_fm)
+        (adv + mel_loss + fm).backward()
+        torch.nn.utils.clip_grad_norm_(g_params, CLIP)
+        optG.step()
+        optG.zero_grad(set_to_none=True)
+        return adv
+
     for i in range(max(warmup, 3)):
         step(i)
     n0 = lib.mgb_launch_count()
     ms = ctx.timed(step, steps, 0)
     launches = lib.mgb_launch_count() - n0
     ms_nosync = ctx.timed(lambda i: step(i, with_sync=False), steps, 0) if ctx.world > 1 else ms
+    for i in range(max(warmup, 3)):
+        gan_step(i)
+    n0 = lib.mgb_launch_count()
+    ms_gan = ctx.timed(gan_step, steps, 0)
+    launches_gan = lib.mgb_launch_count() - n0
+    ms_gan_nosync = ctx.timed(lambda i: gan_step(i, with_sync=False), steps, 0) if ctx.world > 1 else ms_gan
     frames = ctx.world * B * T
     flops = 3 * FLOPS_PER_FRAME_STEP * frames            # forward + data-grad + weight-grad GEMMs
-    return {"metric": "train_frames_per_sec", "value": frames * steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps,
+    # the GAN step: 2 Denoiser forwards + 1 backward (4/3 of the above) + 4 discriminator forwards and 2 backwards (0.65 MFLOP
+    # per frame and forward, csrc/conv1d_f32.cu header)
+    flops_gan = (4 * FLOPS_PER_FRAME_STEP + (4 + 2 * 2) * 0.65e6) * frames
+    return {"metric": "train_frames_per_sec", "value": frames * steps / (ms_gan * 1e-3), "unit": UNIT, "ms_per_step": ms_gan / steps,
             "scaling": "weak", "precision": prec,
-            "workload": f"LJSpeech naive diffusion-decoder training branch: Denoiser fwd+bwd + fused Adam, B={B} x T={T} per GPU "
-                        "(BASELINE configs[4], Denoiser part), gradient all-reduce over NCCL",
-            "tflops": flops * steps / (ms * 1e-3) / 1e12,
-            "allreduce_exposed_ms_per_step": (ms - ms_nosync) / steps,
-            "grad_bytes": int(lib.mgb_flat_weight_count(C.byref(gd.denoise_fn.dims))) * 4,
-            "dp_check": dp_check, "gpu_launches": int(launches)}
+            "workload": f"LJSpeech naive GAN training step of train.py:126-184 on the diffusion decoder: D phase (Denoiser forward, "
+                        f"2 x JCU discriminator forward, backward, clip, Adam) + G phase (Denoiser forward, 2 x discriminator forward, "
+                        f"adversarial + mel L1 + feature-matching losses, backward through the discriminator into the Denoiser, clip, "
+                        f"Adam), B={B} x T={T} per GPU (BASELINE configs[4]); NCCL all-reduce of the Denoiser gradient (bucketed, "
+                        "overlapped) and of the discriminator gradient",
+            "tflops": flops_gan * steps / (ms_gan * 1e-3) / 1e12,
+            "allreduce_exposed_ms_per_step": (ms_gan - ms_gan_nosync) / steps,
+            "grad_bytes": int(lib.mgb_flat_weight_count(C.byref(gd.denoise_fn.dims))) * 4 + sum(p.numel() for p in d_params) * 4,
+            "denoiser_only": {"ms_per_step": ms / steps, "value": frames * steps / (ms * 1e-3), "tflops": flops * steps / (ms * 1e-3) / 1e12,
+                              "allreduce_exposed_ms_per_step": (ms - ms_nosync) / steps, "gpu_launches": int(launches),
+                              "what": "Denoiser training branch forward + backward + fused Adam with a linear probe loss (round 1's record)"},
+            "dp_check": dp_check, "gpu_launches": int(launches_gan)}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -608,6 +766,13 @@ def run_ours(args):
     sub_steps = max(3, min(args.steps, 20))
     tc_prec = prec if prec in ("bf16", "fp16") else "bf16"
 
+    if args.workload == "stages":
+        r = bench_stages(ctx, tc_prec, args.steps, warmup)
+        if ctx.rank == 0:
+            print(json.dumps({"metric": METRIC, "n_gpus": ctx.world, "steps": args.steps, "warmup": warmup, "data": "synthetic",
+                              "stages": r}))
+        ctx.close()
+        return
     if args.workload in ("c3", "c4", "train"):
         if args.workload == "c3":
             r = bench_c3(ctx, tc_prec, args.steps, warmup)
@@ -644,6 +809,7 @@ def run_ours(args):
         ctx.barrier()
         sub["c3"] = bench_c3(ctx, tc_prec, sub_steps, warmup)
         sub["c4"] = bench_c4(ctx, tc_prec, sub_steps, warmup)
+        sub["stages"] = bench_stages(ctx, tc_prec, sub_steps, warmup)
         sub["train"] = bench_train(ctx, "bf16" if prec != "fp32" else "fp32", sub_steps, warmup, args.train_batch)
     if ctx.rank == 0:
         K, B, T = head["K"], head["B"], head["T"]
@@ -677,7 +843,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sub", action="store_true",
                     help="headline record only (skip the fp32_parity / c3 / c4 / train / elementwise sub-records)")
-    ap.add_argument("--workload", default="sample", choices=["sample", "train", "c3", "c4"],
+    ap.add_argument("--workload", default="sample", choices=["sample", "train", "c3", "c4", "stages"],
                     help="sample = the headline reverse-diffusion benchmark (+ sub-records); train / c3 / c4 = that configuration as its own line")
     ap.add_argument("--train-batch", type=int, default=8)
     args = ap.parse_args()

@@ -348,7 +348,7 @@ AuxWs aux_ws(const mgb_auxdec_dims& d, const Rows& r) {
   size_t p = 0;
   auto take = [&](size_t bytes) { size_t o = p; p += align_up(bytes, 1024); return o; };
   const size_t Rp = r.Rp, D = d.d_model, M32 = (d.n_mel + 31) / 32 * 32;
-  w.status = take(1024);
+  w.status = take(8192);
   for (int i = 0; i < 2; ++i) { w.xs[i] = take(Rp * D * 4); w.xi[i] = take(Rp * D * 2); }
   w.qkv = take(Rp * 3 * D * 2);
   w.att = take(Rp * D * 2);
@@ -435,7 +435,7 @@ int mgb_auxdec_forward(const mgb_auxdec_dims* dims, const void* packed, const fl
   const int D = dims->d_model, DC = D / 8;
   const int* lens_i = reinterpret_cast<const int*>(lens);
 
-  MGB_CUDA_CHECK(cudaMemsetAsync(status, 0, 1024, s));
+  MGB_CUDA_CHECK(cudaMemsetAsync(status, 0, 8192, s));
   // dec_output = enc_seq + position_enc[:T]   (Models.py:155-157)
   if (int rc = pack_rows(x, pos, D, r, xi[0], 1.f, xs[0], s)) return rc;
   for (size_t li = 0; li < pl.fft.size(); ++li) {

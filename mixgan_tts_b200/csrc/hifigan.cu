@@ -108,7 +108,7 @@ VocWs voc_ws(const mgb_hifigan_dims& d, const Rows& r0) {
     if (e > E) E = e;
   }
   w.E = E;
-  w.status = take(1024);
+  w.status = take(8192);
   w.meli = take((size_t)r0.Rp * d.n_mel * 2);
   w.prei = take((size_t)r0.Rp * d.initial_channel * 2);
   for (int i = 0; i < 4; ++i) w.s32[i] = take(E * 4);
@@ -178,7 +178,7 @@ int mgb_hifigan_forward(const mgb_hifigan_dims* dims, const void* packed, const 
   __half* I[2] = {reinterpret_cast<__half*>(ws + w.h16[2]), reinterpret_cast<__half*>(ws + w.h16[3])};
   constexpr float SLOPE = 0.1f;                   // LRELU_SLOPE, models.py:7
 
-  MGB_CUDA_CHECK(cudaMemsetAsync(status, 0, 1024, s));
+  MGB_CUDA_CHECK(cudaMemsetAsync(status, 0, 8192, s));
   if (int rc = pack_rows(mel, nullptr, dims->n_mel, r, meli, 1.f, nullptr, s)) return rc;
   {  // conv_pre, image of leaky_relu(x) for ups[0]   (models.py:152, 154)
     ConvIO io = conv_io(meli, dims->n_mel / 8);

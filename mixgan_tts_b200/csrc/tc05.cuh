@@ -150,6 +150,12 @@ __device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const void* tmap,
       ::"r"(smem_dst), "l"(tmap), "r"(c0), "r"(c1), "r"(bar_addr)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_3d(uint32_t smem_dst, const void* tmap, int c0, int c1, int c2, uint32_t bar_addr) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+      ::"r"(smem_dst), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(bar_addr)
+      : "memory");
+}
 __device__ __forceinline__ void tma_load_2d_multicast(uint32_t smem_dst, const void* tmap, int c0, int c1, uint32_t bar_addr,
                                                       uint16_t cta_mask) {
   asm volatile(

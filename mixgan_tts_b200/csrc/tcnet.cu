@@ -14,20 +14,6 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
   __half2 v = __floats2half2_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);
 }
-__device__ __forceinline__ void tmem_ld_f32x32(uint32_t taddr, float (&v)[32]) {
-  uint32_t r[32];
-  tc::tmem_ld32(taddr, r);
-  tc::tmem_ld_wait();
-#pragma unroll
-  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-}
-__device__ __forceinline__ void load_f32x32(const float* p, float (&v)[32]) {
-#pragma unroll
-  for (int q = 0; q < 8; ++q) {
-    const float4 a = *reinterpret_cast<const float4*>(p + q * 4);
-    v[q * 4] = a.x; v[q * 4 + 1] = a.y; v[q * 4 + 2] = a.z; v[q * 4 + 3] = a.w;
-  }
-}
 // fp32 stream [C/4][Rp][4]: a thread owns one row, so a warp's 16-byte access to chunk q is 512 contiguous bytes
 __device__ __forceinline__ void load_s32(const float* base, size_t Rp, size_t row, int ch0, float (&v)[32]) {
 #pragma unroll
@@ -43,13 +29,11 @@ __device__ __forceinline__ void store_s32(float* base, size_t Rp, size_t row, in
         make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
 }
 // fp16 image [C/8][Rp][8]
-__device__ __forceinline__ void store_img32(__half* img, size_t Rp, size_t row, int ch0, const float (&v)[32], float slope) {
+__device__ __forceinline__ void store_img32(__half* img, size_t Rp, size_t row, int ch0, const float (&v)[32]) {
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
-    float w[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) { const float x = v[q * 8 + e]; w[e] = x > 0.f ? x : x * slope; }
-    uint4 u = make_uint4(pack_h2(w[0], w[1]), pack_h2(w[2], w[3]), pack_h2(w[4], w[5]), pack_h2(w[6], w[7]));
+    uint4 u = make_uint4(pack_h2(v[q * 8], v[q * 8 + 1]), pack_h2(v[q * 8 + 2], v[q * 8 + 3]),
+                         pack_h2(v[q * 8 + 4], v[q * 8 + 5]), pack_h2(v[q * 8 + 6], v[q * 8 + 7]));
     *reinterpret_cast<uint4*>(img + ((size_t)(ch0 / 8 + q) * Rp + row) * 8) = u;
   }
 }
@@ -66,155 +50,281 @@ struct KArgs {
   float* stream_out; __half* img_out; float img_slope;
   float* user_out; int user_ld;
   int up; long long Rp_out;
+  int ntiles, ntn;             // work list: row tiles x column tiles
+  int rows, resident;          // rows of an A halo tile (128 + 2 * (taps / 2) * dil); 1 = the whole weight matrix stays in shared memory
   int* status;
+  long long* trace;            // debug library only (MGB_TC_TRACE=1): SM-cycle stamps of CTA 0's first 64 work items
 };
+#ifdef MGB_DEBUG_BUILD
+#define MGB_TC_STAMP(slot) do { if (p.trace && blockIdx.x == 0 && j < 32) p.trace[j * 16 + (slot)] = clock64(); } while (0)
+#else
+#define MGB_TC_STAMP(slot) do { } while (0)
+#endif
 
+// Shared memory of the persistent kernel: an A ring of halo tiles ((128 + 2*halo) rows x KC channels: ALL taps of a
+// convolution read the same tile through descriptors shifted by tap*dilation rows, so an input row crosses the TMA engine
+// once per k-step instead of once per tap) and a W region that either holds the layer's whole weight matrix (small layers:
+// loaded once per CTA) or a ring of per-(k-step, tap) tiles.
+constexpr int ROWS_MAX = 192;          // 128 + 2 * 32 halo rows
 template <int NT, int KC>
 struct Smem {
-  static constexpr int A_BYTES = TILE * KC * 2;
-  static constexpr int B_BYTES = NT * KC * 2;
-  static constexpr int STAGE = A_BYTES + B_BYTES;
-  static constexpr int RAW = (100 * 1024) / STAGE;
-  static constexpr int STAGES = RAW < 2 ? 2 : (RAW > 6 ? 6 : RAW);
-  static constexpr int TOTAL = STAGES * STAGE + 1024;
+  // wide tiles stream 32 KB weight tiles (each used once per work item): give them the deeper ring; narrow tiles keep
+  // whole weight matrices resident and want more A stages in flight
+  static constexpr int W_REGION = (NT == 256 ? 128 : 96) * 1024;
+  static constexpr int A_REGION = (NT == 256 ? 72 : 96) * 1024;
+  static constexpr int A_STAGE = ROWS_MAX * KC * 2;                 // 24 KB (KC = 64) / 12 KB (KC = 32)
+  static constexpr int A_STAGES = A_REGION / A_STAGE;               // 3-4 / 6-8
+  static constexpr int W_STAGE = NT * KC * 2;
+  static constexpr int W_RAW = W_REGION / W_STAGE;
+  static constexpr int W_STAGES = W_RAW > 8 ? 8 : W_RAW;            // 4 (NT = 256, KC = 64) ... 8
+  static constexpr int TOTAL = W_REGION + A_STAGES * A_STAGE + 1024;
 };
 
-__device__ __forceinline__ float apply_act(float v, int act) {
-  if (act == ACT_RELU) return fmaxf(v, 0.f);
-  if (act == ACT_TANH) return tanhf(v);
-  return v;
+// tcgen05.ld without the wait: the epilogue keeps the NEXT 32 columns in flight while it works on the current ones
+__device__ __forceinline__ void tmem_ld_issue(uint32_t taddr, uint32_t (&r)[32]) { tc::tmem_ld32(taddr, r); }
+
+// One tile row per thread.  Uniform options (activation, residuals, slope, outputs) are tested OUTSIDE the element
+// loops; the accumulator columns are software-pipelined (the tcgen05.ld of column group cg + 1 is in flight while group
+// cg is processed).
+// 32 consecutive floats of a shared-memory vector, the same address in every lane (broadcast reads)
+__device__ __forceinline__ void lds_f32x32(const float* p, float (&v)[32]) {
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const float4 a = *reinterpret_cast<const float4*>(p + q * 4);
+    v[q * 4] = a.x; v[q * 4 + 1] = a.y; v[q * 4 + 2] = a.z; v[q * 4 + 3] = a.w;
+  }
 }
 
+// s_bias: the layer's whole (padded) bias vector, s_ln: LayerNorm weight | bias, staged in shared memory once per CTA —
+// global (even L1-resident) loads of these per-column constants stalled every column group on the long scoreboard.
 template <int NT>
-__device__ __forceinline__ void epilogue(const KArgs& p, uint32_t trow, int tile, int ntile, int i) {
-  const long long row = (long long)tile * TILE + i;
-  const int b = (int)(row / p.Tg), t = (int)(row - (long long)b * p.Tg);
-  const bool inrange = b < p.B && t < p.T;
+__device__ __forceinline__ void epilogue(const KArgs& p, const float* s_bias, const float* s_ln, uint32_t trow, int tile,
+                                         int ntile, int i, long long* tr) {
+  const unsigned row = (unsigned)tile * TILE + i;
+  const unsigned b = row / (unsigned)p.Tg, t = row - b * (unsigned)p.Tg;
+  const bool inrange = b < (unsigned)p.B && t < (unsigned)p.T;
   bool valid = inrange;
-  if (valid && p.lens) valid = t < p.lens[b] * p.len_mul;
-  const long long orow = p.up > 1 ? row * p.up + ntile : row;
+  if (valid && p.lens) valid = (int)t < p.lens[b] * p.len_mul;
+  const size_t orow = p.up > 1 ? (size_t)row * p.up + ntile : (size_t)row;
   const int nbase = p.up > 1 ? 0 : ntile * NT;
-  const int bcol = ntile * NT;
+  const float* bias = s_bias + ntile * NT;
   const size_t Rp = (size_t)p.Rp_out;
   float* uo = nullptr;
-  if (p.user_out && inrange) uo = p.user_out + ((size_t)((long long)b * p.T + t) * p.up + (p.up > 1 ? ntile : 0)) * p.user_ld;
+  if (p.user_out && inrange) uo = p.user_out + ((size_t)(b * (unsigned)p.T + t) * p.up + (p.up > 1 ? ntile : 0)) * p.user_ld;
+  constexpr int NCG = NT / 32;
+  // 2 epilogue groups x 168 registers (NT = 256): room for a second accumulator buffer, so the tcgen05.ld of column group
+  // cg + 1 is in flight while group cg is processed; the narrower tiles run 4 groups and hide the latency across groups.
+  constexpr bool PIPE = NT == 256;
+  uint32_t ra[32], rb[PIPE ? 32 : 1];
 
   if (p.ln_g != nullptr) {
     if constexpr (NT == 256) {
-      // LayerNorm(acc + bias + residual) over the 256 channels of this thread's row (nn.LayerNorm: biased variance, eps 1e-5)
-      float mean = 0.f;
-#pragma unroll 1
-      for (int cg = 0; cg < 8; ++cg) {
-        float v[32], bv[32];
-        tmem_ld_f32x32(trow + cg * 32, v);
-        load_f32x32(p.bias + cg * 32, bv);
-        if (valid && p.res1) {
-          float r[32];
-          load_s32(p.res1, Rp, (size_t)orow, cg * 32, r);
+      // LayerNorm(acc + bias + residual) over the 256 channels of this thread's row (nn.LayerNorm: biased variance, eps
+      // 1e-5).  Pass A accumulates sum(x - s) and sum((x - s)^2) around a per-row shift s (the first element), which is
+      // as accurate as the two-pass form when |mean| >> std; pass B normalises and stores.
+      const bool has_res = valid && p.res1 != nullptr;
+      float s1 = 0.f, s2 = 0.f, shift = 0.f;
+      auto pass_a = [&](int cg, uint32_t (&cur)[32], uint32_t (&nxt)[32]) {
+        tc::tmem_ld_wait();
+        if (cg + 1 < NCG) tmem_ld_issue(trow + (cg + 1) * 32, nxt);
+        float x[32];
+        {
+          float bv[32];
+          lds_f32x32(bias + cg * 32, bv);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] += r[j];
+          for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(cur[j]) + bv[j];
         }
+        if (has_res) {
+          float rr[32];
+          load_s32(p.res1, Rp, orow, cg * 32, rr);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) mean += v[j] + bv[j];
-      }
-      mean *= (1.f / 256.f);
-      float var = 0.f;
-#pragma unroll 1
-      for (int cg = 0; cg < 8; ++cg) {
-        float v[32], bv[32];
-        tmem_ld_f32x32(trow + cg * 32, v);
-        load_f32x32(p.bias + cg * 32, bv);
-        if (valid && p.res1) {
-          float r[32];
-          load_s32(p.res1, Rp, (size_t)orow, cg * 32, r);
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] += r[j];
+          for (int j = 0; j < 32; ++j) x[j] += rr[j];
         }
+        if (cg == 0) shift = x[0];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) { const float d = v[j] + bv[j] - mean; var += d * d; }
-      }
-      const float rstd = rsqrtf(var * (1.f / 256.f) + 1e-5f);
+        for (int j = 0; j < 32; ++j) { const float d = x[j] - shift; s1 += d; s2 = fmaf(d, d, s2); }
+      };
+      tmem_ld_issue(trow, ra);
 #pragma unroll 1
-      for (int cg = 0; cg < 8; ++cg) {
-        float v[32], bv[32], g[32], be[32];
-        tmem_ld_f32x32(trow + cg * 32, v);
-        load_f32x32(p.bias + cg * 32, bv);
-        load_f32x32(p.ln_g + cg * 32, g);
-        load_f32x32(p.ln_b + cg * 32, be);
-        if (valid && p.res1) {
-          float r[32];
-          load_s32(p.res1, Rp, (size_t)orow, cg * 32, r);
+      for (int cg = 0; cg < NCG; cg += 2) { pass_a(cg, ra, rb); pass_a(cg + 1, rb, ra); }
+      const float dm = s1 * (1.f / 256.f);                      // mean - shift
+      const float mean = shift + dm;
+      const float var = fmaxf(s2 * (1.f / 256.f) - dm * dm, 0.f);
+      const float rstd = rsqrtf(var + 1e-5f);
+      auto pass_b = [&](int cg, uint32_t (&cur)[32], uint32_t (&nxt)[32]) {
+        tc::tmem_ld_wait();
+        if (cg + 1 < NCG) tmem_ld_issue(trow + (cg + 1) * 32, nxt);
+        float v[32];
+        {
+          float bv[32];
+          lds_f32x32(bias + cg * 32, bv);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] += r[j];
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(cur[j]) + bv[j];
         }
+        if (has_res) {
+          float rr[32];
+          load_s32(p.res1, Rp, orow, cg * 32, rr);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = valid ? (v[j] + bv[j] - mean) * rstd * g[j] + be[j] : 0.f;
-        if (p.stream_out) store_s32(p.stream_out, Rp, (size_t)orow, cg * 32, v);
-        if (p.img_out) store_img32(p.img_out, Rp, (size_t)orow, cg * 32, v, p.img_slope);
+          for (int j = 0; j < 32; ++j) v[j] += rr[j];
+        }
+        {
+          float g[32];
+          lds_f32x32(s_ln + cg * 32, g);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = (v[j] - mean) * rstd * g[j];
+        }
+        {
+          float be[32];
+          lds_f32x32(s_ln + 256 + cg * 32, be);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = valid ? v[j] + be[j] : 0.f;
+        }
+        if (p.stream_out) store_s32(p.stream_out, Rp, orow, cg * 32, v);
+        if (p.img_out) store_img32(p.img_out, Rp, orow, cg * 32, v);
         if (uo) {
 #pragma unroll
           for (int q = 0; q < 8; ++q)
             *reinterpret_cast<float4*>(uo + cg * 32 + q * 4) = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
         }
-      }
+      };
+      tmem_ld_issue(trow, ra);
+#pragma unroll 1
+      for (int cg = 0; cg < NCG; cg += 2) { pass_b(cg, ra, rb); pass_b(cg + 1, rb, ra); }
     }
     return;
   }
 
-#pragma unroll 1
-  for (int cg = 0; cg < NT / 32; ++cg) {
+  const int ncg = min(NCG, (p.Cout32 - nbase + 31) / 32);         // column groups that exist in the output tensor
+  const int act = p.act;
+  const float scale = p.scale, slope = p.img_slope;
+  const bool res1 = valid && p.res1 != nullptr, res2 = valid && p.res2 != nullptr;
+  auto body = [&](int cg, uint32_t (&cur)[32], uint32_t (&nxt)[32]) {
     const int n0 = nbase + cg * 32;
-    if (n0 >= p.Cout32) break;                       // uniform over the warp
-    float v[32], bv[32];
-    tmem_ld_f32x32(trow + cg * 32, v);
-    load_f32x32(p.bias + bcol + cg * 32, bv);
+    if (!PIPE) tmem_ld_issue(trow + cg * 32, cur);
+    tc::tmem_ld_wait();
+#ifdef MGB_DEBUG_BUILD
+    if (tr && cg < 2) tr[8 + cg * 3] = clock64();
+#endif
+    if (PIPE && cg + 1 < ncg) tmem_ld_issue(trow + (cg + 1) * 32, nxt);
+    float v[32];
+    {
+      float bv[32];
+      lds_f32x32(bias + cg * 32, bv);
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j] + bv[j], p.act);
-    if (valid && p.res1) {
-      float r[32];
-      load_s32(p.res1, Rp, (size_t)orow, n0, r);
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] += r[j];
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(cur[j]) + bv[j];
     }
-    if (valid && p.res2) {
-      float r[32];
-      load_s32(p.res2, Rp, (size_t)orow, n0, r);
+    if (act == ACT_RELU) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] += r[j];
+      for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+    } else if (act == ACT_TANH) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = tanhf(v[j]);
     }
+    if (res1) {
+      float r1[32];
+      load_s32(p.res1, Rp, orow, n0, r1);
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = valid ? v[j] * p.scale : 0.f;
-    if (p.stream_out) store_s32(p.stream_out, Rp, (size_t)orow, n0, v);
-    if (p.img_out) store_img32(p.img_out, Rp, (size_t)orow, n0, v, p.img_slope);
+      for (int j = 0; j < 32; ++j) v[j] += r1[j];
+    }
+    if (res2) {
+      float r2[32];
+      load_s32(p.res2, Rp, orow, n0, r2);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] += r2[j];
+    }
+    if (scale != 1.f) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] *= scale;
+    }
+    if (!valid) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = 0.f;
+    }
+#ifdef MGB_DEBUG_BUILD
+    if (tr && cg < 2) tr[9 + cg * 3] = clock64() + (long long)(v[0] != 12345.f ? 0 : 1);
+#endif
+    if (p.stream_out) store_s32(p.stream_out, Rp, orow, n0, v);
     if (uo) {
       if (n0 + 32 <= p.Cout && (p.user_ld & 3) == 0) {
 #pragma unroll
         for (int q = 0; q < 8; ++q)
           *reinterpret_cast<float4*>(uo + n0 + q * 4) = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
       } else {
-#pragma unroll
+#pragma unroll 1
         for (int j = 0; j < 32; ++j)
           if (n0 + j < p.Cout) uo[n0 + j] = v[j];
       }
     }
+    if (p.img_out) {
+      if (slope != 1.f) {                                          // the consumer's leaky_relu, applied once here
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f) + slope * fminf(v[j], 0.f);
+      }
+      store_img32(p.img_out, Rp, orow, n0, v);
+    }
+#ifdef MGB_DEBUG_BUILD
+    if (tr && cg < 2) tr[10 + cg * 3] = clock64();
+#endif
+  };
+  if constexpr (PIPE) {
+    tmem_ld_issue(trow, ra);
+#pragma unroll 1
+    for (int cg = 0; cg < ncg; cg += 2) {                          // ncg is even for every 256-wide tile (Cout32 % 64 == 0 there)
+      body(cg, ra, rb);
+      if (cg + 1 < ncg) body(cg + 1, rb, ra);
+    }
+  } else {
+#pragma unroll 1
+    for (int cg = 0; cg < ncg; ++cg) body(cg, ra, ra);
   }
 }
 
+// Persistent kernel: one CTA per SM walks the (row tile, column tile) work list with a stride of gridDim.x.  The TMA
+// warp and the MMA warp run ahead over work items through one shared-memory ring; the accumulator is double-buffered in
+// TMEM (2 x NT columns) and the two epilogue warpgroups take alternate work items, so a tile's epilogue (the HBM side:
+// residual reads, stream / image stores) overlaps the next tiles' loads and MMAs.  Column tiles of one row tile are
+// consecutive work items (the A box is re-read from L2 while it is hot).
+// Waits of the roles that are NOT on the critical path (epilogue groups waiting for their accumulator, the TMA warp waiting
+// for a free stage) back off with nanosleep: a dozen warps polling mbarriers at full speed took 3/4 of the issue slots of
+// the sub-partition the single MMA-issuing thread lives on (measured: ~290 cycles per tcgen05.mma issued, 160 with fewer pollers).
+__device__ __forceinline__ void wait_backoff(uint32_t bar_addr, uint32_t parity, int* status, int code) {
+  if (tc::mbar_try_wait_addr(bar_addr, parity)) return;
+  const long long t0 = clock64();
+  while (!tc::mbar_try_wait_addr(bar_addr, parity)) {
+    __nanosleep(64);
+    if (clock64() - t0 > kTimeout) {
+      if (status) atomicOr(status, code);
+      __threadfence_system();
+      __trap();
+    }
+  }
+}
+
+constexpr int MAX_BIAS = 2048;     // widest padded GEMM N: a transposed convolution with stride 8 into 256 channels
+
+template <int NT>
+struct Groups { static constexpr int NBUF = NT <= 128 ? 4 : 2; static constexpr int THREADS = 64 + NBUF * 128; };
+
 template <int NT, int KC>
-__global__ void __launch_bounds__(192) tcconv_kernel(const KArgs p, const __grid_constant__ CUtensorMap tmA) {
+__global__ void __launch_bounds__(Groups<NT>::THREADS, 1) tcconv_kernel(const KArgs p, const __grid_constant__ CUtensorMap tmA) {
   using S = Smem<NT, KC>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  __shared__ __align__(8) uint64_t bar_full[S::STAGES], bar_empty[S::STAGES], bar_acc;
+  constexpr int NBUF = Groups<NT>::NBUF;
+  __shared__ __align__(8) uint64_t a_full[S::A_STAGES], a_empty[S::A_STAGES], w_full[S::W_STAGES], w_empty[S::W_STAGES],
+      w_res, acc_full[NBUF], acc_empty[NBUF];
   __shared__ uint32_t tmem_slot;
+  __shared__ __align__(16) float s_bias[MAX_BIAS], s_ln[512];
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int tile = blockIdx.x, ntile = blockIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);       // provably warp-uniform: role code stays on the uniform datapath
 
-  if (warp == 1) tc::tmem_alloc<NT>(&tmem_slot);
+  if (warp == 1) tc::tmem_alloc<NBUF * NT>(&tmem_slot);
   if (tid == 0) {
-    for (int i = 0; i < S::STAGES; ++i) { tc::mbar_init(&bar_full[i], 1); tc::mbar_init(&bar_empty[i], 1); }
-    tc::mbar_init(&bar_acc, 1);
+    for (int i = 0; i < S::A_STAGES; ++i) { tc::mbar_init(&a_full[i], 1); tc::mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < S::W_STAGES; ++i) { tc::mbar_init(&w_full[i], 1); tc::mbar_init(&w_empty[i], 1); }
+    tc::mbar_init(&w_res, 1);
+    for (int i = 0; i < NBUF; ++i) { tc::mbar_init(&acc_full[i], 1); tc::mbar_init(&acc_empty[i], 4); }
     tc::fence_barrier_init();
   }
   tc::tc_fence_before();
@@ -223,71 +333,159 @@ __global__ void __launch_bounds__(192) tcconv_kernel(const KArgs p, const __grid
   const uint32_t tmem = tmem_slot;
   pdl_trigger();
   pdl_wait();
+  for (int k = tid; k < p.ntn * NT; k += blockDim.x) s_bias[k] = p.bias[k];
+  if (p.ln_g) for (int k = tid; k < 256; k += blockDim.x) { s_ln[k] = p.ln_g[k]; s_ln[256 + k] = p.ln_b[k]; }
+  __syncthreads();
 
-  const int nsteps = p.taps * p.kspt;
-  const uint32_t smem_base = tc::smem_u32(smem);
+  const int nsteps = p.taps * p.kspt;                    // per work item; order: k-step outer, tap inner
+  const int nwork = p.ntiles * p.ntn;
+  const uint32_t w_base = tc::smem_u32(smem);
+  const uint32_t a_base = w_base + S::W_REGION;
+  const int halo = (p.taps >> 1) * p.dil;
+  const uint32_t a_bytes = (uint32_t)p.rows * KC * 2;
 
+  // The TMA and MMA roles run with WARP-UNIFORM control flow (all 32 lanes wait on the barriers and walk the work list);
+  // only the instructions that must come from one thread are predicated with elect_one().  Ring positions and operand
+  // descriptors then live in uniform registers and a tcgen05.mma costs two 64-bit adds instead of a chain of
+  // vector-to-uniform register moves (measured: ~290 cycles per MMA issued from an `if (lane == 0)` loop).
   if (warp == 0) {
-    if (lane == 0) {
+    if (p.resident && tc::elect_one()) {                 // ntn == 1: the whole matrix, once
+      const uint32_t total = (uint32_t)nsteps * S::W_STAGE;
+      tc::mbar_arrive_expect_tx_addr(tc::smem_u32(&w_res), total);
+      for (uint32_t off = 0; off < total; off += 16384) {
+        const uint32_t n = total - off < 16384 ? total - off : 16384;
+        tc::bulk_g2s_addr(w_base + off, reinterpret_cast<const uint8_t*>(p.Wpk) + off, n, tc::smem_u32(&w_res));
+      }
+    }
+    int ia = 0, iw = 0, j = 0;
+    for (int w = blockIdx.x; w < nwork; w += gridDim.x, ++j) {
+      const int tile = w / p.ntn, ntile = w - tile * p.ntn;
+      if (lane == 0) MGB_TC_STAMP(0);
       const __half* bsrc = p.Wpk + (size_t)ntile * nsteps * (size_t)(NT * KC);
-      for (int s = 0; s < nsteps; ++s) {
-        const int stage = s % S::STAGES, ph = (s / S::STAGES) & 1;
-        tc::mbar_wait_trap(tc::smem_u32(&bar_empty[stage]), ph ^ 1, kTimeout, p.status, 1);
-        const int tap = s / p.kspt, kc = s - tap * p.kspt;
-        const int off = (tap - (p.taps >> 1)) * p.dil;
-        const uint32_t sa = smem_base + stage * S::STAGE, sb = sa + S::A_BYTES;
-        const uint32_t fb = tc::smem_u32(&bar_full[stage]);
-        tc::mbar_arrive_expect_tx_addr(fb, S::STAGE);
-        tc::tma_load_2d(sa, &tmA, 2 * (tile * TILE + off), kc * (KC / 8), fb);   // 128 rows x KC channels, zero-filled outside
-        tc::bulk_g2s_addr(sb, bsrc + (size_t)s * (NT * KC), S::B_BYTES, fb);
+      for (int kc = 0; kc < p.kspt; ++kc, ++ia) {
+        const int st = ia % S::A_STAGES, ph = (ia / S::A_STAGES) & 1;
+        wait_backoff(tc::smem_u32(&a_empty[st]), ph ^ 1, p.status, 1);
+        if (tc::elect_one()) {
+          const uint32_t fb = tc::smem_u32(&a_full[st]);
+          tc::mbar_arrive_expect_tx_addr(fb, a_bytes);
+          // (128 + 2*halo) rows x KC channels in ONE box, zero-filled outside the row axis
+          tc::tma_load_3d(a_base + st * S::A_STAGE, &tmA, 0, tile * TILE - halo, kc * (KC / 8), fb);
+        }
+        if (!p.resident) {
+          for (int tap = 0; tap < p.taps; ++tap, ++iw) {
+            const int ws = iw % S::W_STAGES, wph = (iw / S::W_STAGES) & 1;
+            wait_backoff(tc::smem_u32(&w_empty[ws]), wph ^ 1, p.status, 1);
+            if (tc::elect_one()) {
+              const uint32_t wb = tc::smem_u32(&w_full[ws]);
+              tc::mbar_arrive_expect_tx_addr(wb, S::W_STAGE);
+              tc::bulk_g2s_addr(w_base + ws * S::W_STAGE, bsrc + (size_t)(kc * p.taps + tap) * (NT * KC), S::W_STAGE, wb);
+            }
+          }
+        }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = tc::make_idesc_16(128, NT, true);
-      for (int s = 0; s < nsteps; ++s) {
-        const int stage = s % S::STAGES, ph = (s / S::STAGES) & 1;
-        tc::mbar_wait_trap(tc::smem_u32(&bar_full[stage]), ph, kTimeout, p.status, 2);
+    const uint32_t idesc = tc::make_idesc_16(128, NT, true);
+    const uint32_t lbo_a = (uint32_t)p.rows * 16;        // byte stride between 8-channel chunks of the A tile
+    const uint64_t a_desc0 = tc::make_smem_desc(a_base, lbo_a, 128);
+    const uint64_t b_desc0 = tc::make_smem_desc(w_base, NT * 16, 128);
+    const uint32_t a_kstep = (2 * lbo_a) >> 4;           // descriptor address units (16 B): one K = 16 step = 2 chunks
+    constexpr uint32_t b_kstep = (2 * NT * 16) >> 4;
+    if (p.resident) { tc::mbar_wait_trap(tc::smem_u32(&w_res), 0, kTimeout, p.status, 2); tc::tc_fence_after(); }
+    int ia = 0, iw = 0, j = 0;
+    for (int w = blockIdx.x; w < nwork; w += gridDim.x, ++j) {
+      const int buf = j % NBUF;
+      if (lane == 0) MGB_TC_STAMP(1);
+      tc::mbar_wait_trap(tc::smem_u32(&acc_empty[buf]), ((j / NBUF) & 1) ^ 1, kTimeout, p.status, 2);
+      tc::tc_fence_after();
+      if (lane == 0) MGB_TC_STAMP(2);
+      const uint32_t d_tmem = tmem + buf * NT;
+      for (int kc = 0; kc < p.kspt; ++kc, ++ia) {
+        const int st = ia % S::A_STAGES, ph = (ia / S::A_STAGES) & 1;
+        tc::mbar_wait_trap(tc::smem_u32(&a_full[st]), ph, kTimeout, p.status, 2);
         tc::tc_fence_after();
-        const uint32_t sa = smem_base + stage * S::STAGE, sb = sa + S::A_BYTES;
+        const uint64_t a_st = a_desc0 + (uint64_t)((st * S::A_STAGE) >> 4);
+        for (int tap = 0; tap < p.taps; ++tap) {
+          uint64_t b;
+          int ws = 0;
+          if (p.resident) {
+            b = b_desc0 + (uint64_t)((kc * p.taps + tap) * (S::W_STAGE >> 4));
+          } else {
+            ws = iw % S::W_STAGES;
+            tc::mbar_wait_trap(tc::smem_u32(&w_full[ws]), (iw / S::W_STAGES) & 1, kTimeout, p.status, 2);
+            tc::tc_fence_after();
+            b = b_desc0 + (uint64_t)(ws * (S::W_STAGE >> 4));
+            ++iw;
+          }
+          const uint64_t a = a_st + (uint64_t)(tap * p.dil);     // the tap: the same tile, tap*dil rows (16 B each) further
+          if (tc::elect_one()) {
 #pragma unroll
-        for (int k = 0; k < KC / 16; ++k) {
-          const uint64_t ad = tc::make_smem_desc(sa + k * 2 * (TILE * 16), TILE * 16, 128);
-          const uint64_t bd = tc::make_smem_desc(sb + k * 2 * (NT * 16), NT * 16, 128);
-          tc::umma_bf16(tmem, ad, bd, idesc, (s | k) ? 1u : 0u);
+            for (int k = 0; k < KC / 16; ++k)
+              tc::umma_bf16(d_tmem, a + (uint64_t)(k * a_kstep), b + (uint64_t)(k * b_kstep), idesc, (kc | tap | k) ? 1u : 0u);
+            if (!p.resident) tc::umma_commit(&w_empty[ws]);
+          }
         }
-        tc::umma_commit(&bar_empty[stage]);
+        if (tc::elect_one()) tc::umma_commit(&a_empty[st]);
       }
-      tc::umma_commit(&bar_acc);
+      if (tc::elect_one()) tc::umma_commit(&acc_full[buf]);
+      if (lane == 0) MGB_TC_STAMP(3);
     }
   } else {
-    tc::mbar_wait_trap(tc::smem_u32(&bar_acc), 0, kTimeout, p.status, 4);
-    tc::tc_fence_after();
+    const int g = (warp - 2) >> 2;                         // epilogue group = TMEM buffer = local work index mod NBUF
     const int i = (warp & 3) * 32 + lane;                  // TMEM lane = tile row
-    epilogue<NT>(p, tmem + ((uint32_t)((warp & 3) * 32) << 16), tile, ntile, i);
+    int j = 0;
+    for (int w = blockIdx.x; w < nwork; w += gridDim.x, ++j) {
+      if (j % NBUF != g) continue;
+      const int tile = w / p.ntn, ntile = w - tile * p.ntn;
+      if ((tid & 127) == 64) MGB_TC_STAMP(4);
+      wait_backoff(tc::smem_u32(&acc_full[g]), (j / NBUF) & 1, p.status, 4);
+      tc::tc_fence_after();
+      if ((tid & 127) == 64) MGB_TC_STAMP(5);
+      long long* tr = nullptr;
+#ifdef MGB_DEBUG_BUILD
+      if (p.trace && blockIdx.x == 0 && j < 32 && (tid & 127) == 64) tr = p.trace + j * 16;
+#endif
+      epilogue<NT>(p, s_bias, s_ln, tmem + g * NT + ((uint32_t)((warp & 3) * 32) << 16), tile, ntile, i, tr);
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&acc_empty[g]);
+      if ((tid & 127) == 64) MGB_TC_STAMP(6);
+    }
   }
   tc::tc_fence_before();
   __syncthreads();
-  if (warp == 1) tc::tmem_dealloc<NT>(tmem);
+  if (warp == 1) tc::tmem_dealloc<NBUF * NT>(tmem);
 }
 
 template <int NT, int KC>
-int launch_conv(const KArgs& a, const __half* in, int in_chunks, int Rp_in, int ntiles, int ntn, cudaStream_t s) {
+int launch_conv(KArgs a, const __half* in, int in_chunks, int Rp_in, int ntiles, int ntn, cudaStream_t s) {
   using S = Smem<NT, KC>;
   static PerDeviceOnce once;
+  static int sms[256];
   if (once.pending()) {
     MGB_CUDA_CHECK(cudaFuncSetAttribute(tcconv_kernel<NT, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+    int dev = 0, n = 0;
+    MGB_CUDA_CHECK(cudaGetDevice(&dev));
+    MGB_CUDA_CHECK(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+    sms[dev & 255] = n;
     once.done();
   }
   CUtensorMap m;
-  if (int rc = make_image_map(&m, in, in_chunks, Rp_in, KC / 8)) return rc;
-  MGB_CUDA_CHECK(launch_pdl(tcconv_kernel<NT, KC>, dim3(ntiles, ntn), dim3(192), S::TOTAL, s, 1, a, m));
+  a.rows = TILE + 2 * (a.taps >> 1) * a.dil;
+  MGB_REQUIRE(a.rows <= ROWS_MAX, MGB_E_UNSUPPORTED, "convolution padding %d exceeds %d rows", (a.rows - TILE) / 2, (ROWS_MAX - TILE) / 2);
+  if (int rc = make_image_map3(&m, in, in_chunks, Rp_in, a.rows, KC / 8)) return rc;
+  a.ntiles = ntiles; a.ntn = ntn;
+  a.resident = (ntn == 1 && (long long)a.taps * a.kspt * S::W_STAGE <= S::W_REGION) ? 1 : 0;
+  const long long nwork = (long long)ntiles * ntn;
+  const int nsm = sms[PerDeviceOnce::current()];
+  const int grid = (int)(nwork < nsm ? nwork : nsm);
+  MGB_CUDA_CHECK(launch_pdl(tcconv_kernel<NT, KC>, dim3(grid), dim3(Groups<NT>::THREADS), S::TOTAL, s, 1, a, m));
   note_launch();
   return MGB_OK;
 }
 
 // ---- weight packing: torch [Cout][Cin][k] (conv / linear) or [Cin][Cout][k] (transposed conv) -> streamed fp16 tiles
-//      wp[ntile][step = tap*kspt + kc][KC/8][NT][8] -------------------------------------------------------------------
+//      wp[ntile][step = kc*taps + tap][KC/8][NT][8] -------------------------------------------------------------------
 __global__ void pack_w_kernel(const float* __restrict__ w, const float* __restrict__ oscale, __half* __restrict__ wp,
                               int Cin, int Cout, int k, int NT, int KC, int kspt, int taps, int up, int tpad, long long total) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -299,7 +497,7 @@ __global__ void pack_w_kernel(const float* __restrict__ w, const float* __restri
   const int nsteps = taps * kspt;
   const int s = (int)((idx / per_step) % nsteps);
   const int nt = (int)(idx / (per_step * nsteps));
-  const int tap = s / kspt, kc = s - tap * kspt;
+  const int kc = s / taps, tap = s - kc * taps;        // streamed order: k-step outer, tap inner
   const int ci = kc * KC + c8 * 8 + e;
   float val = 0.f;
   if (up > 1) {
@@ -399,9 +597,20 @@ int run_conv(const Layer& l, const void* packed, const Rows& rin, const ConvIO& 
   a.user_out = io.user_out; a.user_ld = io.user_ld;
   a.up = l.up; a.Rp_out = (long long)rin.Rp * l.up;
   a.status = status;
+  a.trace = nullptr;
+#ifdef MGB_DEBUG_BUILD
+  {   // the callers' status region is 8 KB: word 0 = watchdog, bytes [1024, 1024 + 64*8*8) = trace of the LAST launch
+    // MGB_TC_TRACE=<n>: trace the n-th run_conv call of the process (0-based); MGB_TC_TRACE=all: every call (the last one stays)
+    static const int which = [] { const char* e = getenv("MGB_TC_TRACE"); return !e ? -2 : (*e == 'a' ? -1 : atoi(e)); }();
+    static int counter = 0;
+    if (which != -2 && status && (which == -1 || which == counter)) a.trace = reinterpret_cast<long long*>(reinterpret_cast<char*>(status) + 1024);
+    ++counter;
+  }
+#endif
   MGB_REQUIRE(io.ln_g == nullptr || (l.NT == 256 && l.Cout == 256 && l.up == 1), MGB_E_UNSUPPORTED,
               "the fused LayerNorm epilogue needs a 256-channel output");
   MGB_REQUIRE(io.in_chunks * 8 >= l.Cin, MGB_E_ARG, "input image narrower than the layer's input channels");
+  MGB_REQUIRE(l.ntn * l.NT <= MAX_BIAS, MGB_E_UNSUPPORTED, "layer wider than %d output columns", MAX_BIAS);
 #define MGB_TC_CASE(NT_, KC_)                                                                       \
   if (l.NT == NT_ && l.KC == KC_) return launch_conv<NT_, KC_>(a, io.in, io.in_chunks, rin.Rp, rin.ntiles, l.ntn, s);
   MGB_TC_CASE(256, 64) MGB_TC_CASE(256, 32) MGB_TC_CASE(128, 64) MGB_TC_CASE(128, 32)

@@ -60,4 +60,29 @@ inline int make_image_map(CUtensorMap* m, const void* img, int nchunks, int Rp, 
   return MGB_OK;
 }
 
+// The same image as a 3-D array of 8-byte words: dim0 = the 2 words of a row's 16 bytes, dim1 = rows, dim2 = chunks.  A box
+// of 2 x box_rows x box_chunks lands as [chunk][box_rows][16 B] like the 2-D form, but box_rows may be anything up to 256
+// (a 128-row tile plus its convolution halo) and rows outside [0, Rp) are zero-filled.  Coordinates: (0, row, chunk).
+inline int make_image_map3(CUtensorMap* m, const void* img, int nchunks, int Rp, int box_rows, int box_chunks) {
+  static thread_local std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;
+  const TmapKey key{img, nchunks, Rp, box_rows * 1024 + box_chunks};
+  auto it = cache.find(key);
+  if (it != cache.end()) { *m = it->second; return MGB_OK; }
+  if (cache.size() > 8192) cache.clear();
+  TmapEncodeFn fn = tmap_encode_fn();
+  MGB_REQUIRE(fn != nullptr, MGB_E_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+  MGB_REQUIRE(box_rows >= 1 && box_rows <= 256, MGB_E_ARG, "TMA box of %d rows", box_rows);
+  const cuuint64_t dims[3] = {2, (cuuint64_t)Rp, (cuuint64_t)nchunks};
+  const cuuint64_t strides[2] = {16, (cuuint64_t)Rp * 16};
+  const cuuint32_t box[3] = {2, (cuuint32_t)box_rows, (cuuint32_t)box_chunks};
+  const cuuint32_t es[3] = {1, 1, 1};
+  const CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, const_cast<void*>(img), dims, strides, box, es,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  MGB_REQUIRE(r == CUDA_SUCCESS, MGB_E_CUDA, "cuTensorMapEncodeTiled (3-D) failed (%d) for an image of %d chunks x %d rows", (int)r,
+              nchunks, Rp);
+  cache.emplace(key, *m);
+  return MGB_OK;
+}
+
 }  // namespace mgb

@@ -21,8 +21,12 @@ class BatchSynthesizer:
     PINNED host tensors and every yielded ``mel`` is a pinned host ``[B,T,M]`` tensor (valid until the next two
     batches have been yielded: the output buffers are recycled)."""
 
-    def __init__(self, diffusion: GaussianDiffusion, device: Optional[torch.device] = None):
+    def __init__(self, diffusion: GaussianDiffusion, device: Optional[torch.device] = None, aux_decoder=None, vocoder=None):
+        """``aux_decoder`` (``mixgan_tts_b200.AuxDecoder``): batches may then carry ``coarse_mel = None`` in `shallow` mode
+        and the coarse mel is computed on the GPU from ``cond`` (which IS the decoder's input: model/mixgantts.py:138-139).
+        ``vocoder`` (``mixgan_tts_b200.Generator``): the yielded tensors are waveforms ``[B, T * hop]`` instead of mels."""
         self.gd = diffusion
+        self.aux, self.voc = aux_decoder, vocoder
         self.device = device or next(diffusion.parameters()).device
         if self.device.type != "cuda":
             raise RuntimeError("BatchSynthesizer needs the model on a CUDA device (no CPU fallback)")
@@ -59,7 +63,11 @@ class BatchSynthesizer:
             nxt = next(it, None)
             pending = self._upload(tuple(nxt) + (None,) * (4 - len(nxt))) if nxt is not None else None
             compute.wait_event(ev_in)                # inputs of THIS batch have landed; the next upload runs meanwhile
+            if coarse is None and self.aux is not None and self.gd.model == "shallow":
+                coarse = self.aux(cond, mask)        # model/mixgantts.py:139-143, stays on the device
             mel = self.gd(None, cond, spk, mask, coarse_mel=coarse)[0]
+            if self.voc is not None:
+                mel = self.voc.forward_frames(mel)   # utils/model.py:103-110
             for t in (cond, mask, spk, coarse):      # the upload stream allocated them; the compute stream used them
                 if t is not None:
                     t.record_stream(compute)

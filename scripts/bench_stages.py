@@ -77,6 +77,15 @@ def bench_voc(B=16, T=800, steps=5, warmup=2):
 
 
 if __name__ == "__main__":
+    # usage: bench_stages.py [aux|voc|both] [steps] [warmup]
     torch.cuda.set_device(0)
-    print(json.dumps(bench_aux()), flush=True)
-    print(json.dumps(bench_voc()), flush=True)
+    what = sys.argv[1] if len(sys.argv) > 1 else "both"
+    kw = {}
+    if len(sys.argv) > 2:
+        kw["steps"] = int(sys.argv[2])
+    if len(sys.argv) > 3:
+        kw["warmup"] = int(sys.argv[3])
+    if what in ("aux", "both"):
+        print(json.dumps(bench_aux(**kw)), flush=True)
+    if what in ("voc", "both"):
+        print(json.dumps(bench_voc(**kw)), flush=True)

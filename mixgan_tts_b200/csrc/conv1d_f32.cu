@@ -47,6 +47,9 @@ __global__ void pack_w_kernel(const float* __restrict__ w, float* __restrict__ w
 // ---- forward (DGRAD = false) and data gradient (DGRAD = true): out[M][N] = A[M][K] * Bm[K][N] ----------------------
 //   forward: M = B*Tout rows, K = k*Cin, N = Cout, A(m, j*Cin + ci) = xin[b][to*s + j - pad][ci], Bm = wp
 //   dgrad  : M = B*Tin  rows, K = k*Cout, N = Cin, A(m, j*Cout + co) = dz[b][(ti + pad - j)/s][co], Bm = wq
+// The operand tiles of k-step i + 1 are fetched into registers while k-step i is multiplied out of shared memory: with
+// 50-200 CTAs on 148 SMs these GEMMs are latency-bound, and an un-prefetched loop paid one full global-memory latency
+// (~1 us) per 16-deep k-step (measured 227 us for the 512 -> 128, k = 5 layer; same accumulation order, same bits).
 template <bool DGRAD>
 __global__ void __launch_bounds__(NTHR) conv_gemm_f32_kernel(const float* __restrict__ A, const float* __restrict__ Bm,
                                                              const float* __restrict__ bias, const float* __restrict__ rowbias,
@@ -72,57 +75,59 @@ __global__ void __launch_bounds__(NTHR) conv_gemm_f32_kernel(const float* __rest
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
+  auto src_row = [&](int j, int& src) -> bool {
+    if (DGRAD) { const int q = a_t + s.pad - j; src = q / s.stride; return q >= 0 && q % s.stride == 0 && q / s.stride < s.Tout; }
+    src = a_t * s.stride + j - s.pad;
+    return src >= 0 && src < s.Tin;
+  };
+  auto load_a = [&](int k0, float (&v)[4]) {
+    v[0] = v[1] = v[2] = v[3] = 0.f;
+    const int kk = k0 + a_k4;
+    if (a_m >= M || kk >= K) return;
+    if (vecA) {
+      const int j = kk / Ca, c = kk - j * Ca;
+      int src;
+      if (src_row(j, src)) {
+        const float4 x4 = *reinterpret_cast<const float4*>(A + ((size_t)a_b * src_per_b + src) * Ca + c);
+        v[0] = x4.x; v[1] = x4.y; v[2] = x4.z; v[3] = x4.w;
+        if (!DGRAD && rowbias) {
+          const float4 r4 = *reinterpret_cast<const float4*>(rowbias + (size_t)a_b * Ca + c);
+          v[0] += r4.x; v[1] += r4.y; v[2] += r4.z; v[3] += r4.w;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int ke = kk + e;
+        if (ke >= K) break;
+        const int j = ke / Ca, c = ke - j * Ca;
+        int src;
+        if (src_row(j, src)) v[e] = A[((size_t)a_b * src_per_b + src) * Ca + c] + ((!DGRAD && rowbias) ? rowbias[(size_t)a_b * Ca + c] : 0.f);
+      }
+    }
+  };
+  auto load_b = [&](int k0, float (&v)[4]) {
+    v[0] = v[1] = v[2] = v[3] = 0.f;
+    const int kk = k0 + b_k, n = n0 + b_n4;
+    if (kk >= K) return;
+    if (vecB && n + 3 < N) {
+      const float4 w4 = *reinterpret_cast<const float4*>(Bm + (size_t)kk * N + n);
+      v[0] = w4.x; v[1] = w4.y; v[2] = w4.z; v[3] = w4.w;
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) if (n + e < N) v[e] = Bm[(size_t)kk * N + n + e];
+    }
+  };
+
+  float pa[4], pb[4];
+  load_a(0, pa);
+  load_b(0, pb);
   for (int k0 = 0; k0 < K; k0 += TK) {
-    {  // A tile
-      float v[4] = {0.f, 0.f, 0.f, 0.f};
-      const int kk = k0 + a_k4;
-      if (a_m < M && kk < K) {
-        if (vecA) {
-          const int j = kk / Ca, c = kk - j * Ca;
-          int src;
-          bool ok;
-          if (DGRAD) { const int q = a_t + s.pad - j; ok = q >= 0 && q % s.stride == 0 && q / s.stride < s.Tout; src = q / s.stride; }
-          else { src = a_t * s.stride + j - s.pad; ok = src >= 0 && src < s.Tin; }
-          if (ok) {
-            const float4 x4 = *reinterpret_cast<const float4*>(A + ((size_t)a_b * src_per_b + src) * Ca + c);
-            v[0] = x4.x; v[1] = x4.y; v[2] = x4.z; v[3] = x4.w;
-            if (!DGRAD && rowbias) {
-              const float4 r4 = *reinterpret_cast<const float4*>(rowbias + (size_t)a_b * Ca + c);
-              v[0] += r4.x; v[1] += r4.y; v[2] += r4.z; v[3] += r4.w;
-            }
-          }
-        } else {
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int ke = kk + e;
-            if (ke >= K) break;
-            const int j = ke / Ca, c = ke - j * Ca;
-            int src;
-            bool ok;
-            if (DGRAD) { const int q = a_t + s.pad - j; ok = q >= 0 && q % s.stride == 0 && q / s.stride < s.Tout; src = q / s.stride; }
-            else { src = a_t * s.stride + j - s.pad; ok = src >= 0 && src < s.Tin; }
-            if (ok) v[e] = A[((size_t)a_b * src_per_b + src) * Ca + c] + ((!DGRAD && rowbias) ? rowbias[(size_t)a_b * Ca + c] : 0.f);
-          }
-        }
-      }
-#pragma unroll
-      for (int e = 0; e < 4; ++e) As[a_k4 + e][a_r] = v[e];
-    }
-    {  // B tile
-      float v[4] = {0.f, 0.f, 0.f, 0.f};
-      const int kk = k0 + b_k, n = n0 + b_n4;
-      if (kk < K) {
-        if (vecB && n + 3 < N) {
-          const float4 w4 = *reinterpret_cast<const float4*>(Bm + (size_t)kk * N + n);
-          v[0] = w4.x; v[1] = w4.y; v[2] = w4.z; v[3] = w4.w;
-        } else {
-#pragma unroll
-          for (int e = 0; e < 4; ++e) if (n + e < N) v[e] = Bm[(size_t)kk * N + n + e];
-        }
-      }
-      *reinterpret_cast<float4*>(&Bs[b_k][b_n4]) = make_float4(v[0], v[1], v[2], v[3]);
-    }
+    for (int e = 0; e < 4; ++e) As[a_k4 + e][a_r] = pa[e];
+    *reinterpret_cast<float4*>(&Bs[b_k][b_n4]) = make_float4(pb[0], pb[1], pb[2], pb[3]);
     __syncthreads();
+    if (k0 + TK < K) { load_a(k0 + TK, pa); load_b(k0 + TK, pb); }     // in flight during the multiply
 #pragma unroll
     for (int kq = 0; kq < TK; ++kq) {
       const float4 a4 = *reinterpret_cast<const float4*>(&As[kq][ty * 4]);
@@ -188,49 +193,54 @@ __global__ void __launch_bounds__(NTHR) conv_wgrad_f32_kernel(const float* __res
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  for (int m0 = mb; m0 < me; m0 += TK) {
+  auto load_ab = [&](int m0, float (&va)[4], float (&vb)[4]) {
+    va[0] = va[1] = va[2] = va[3] = 0.f;
+    vb[0] = vb[1] = vb[2] = vb[3] = 0.f;
     const int m = m0 + l_m;
-    float va[4] = {0.f, 0.f, 0.f, 0.f}, vb[4] = {0.f, 0.f, 0.f, 0.f};
-    if (m < me) {
-      const int b = m / s.Tout, to = m - b * s.Tout;
-      const int kk = k0 + l_c4;
-      if (vecA) {                  // K = k * Cin is a multiple of 4 and a float4 never straddles two taps
-        if (kk < K) {
-          const int j = kk / s.Cin, c = kk - j * s.Cin;
-          const int ti = to * s.stride + j - s.pad;
-          if (ti >= 0 && ti < s.Tin) {
-            const float4 x4 = *reinterpret_cast<const float4*>(x + ((size_t)b * s.Tin + ti) * s.Cin + c);
-            va[0] = x4.x; va[1] = x4.y; va[2] = x4.z; va[3] = x4.w;
-            if (rowbias) {
-              const float4 r4 = *reinterpret_cast<const float4*>(rowbias + (size_t)b * s.Cin + c);
-              va[0] += r4.x; va[1] += r4.y; va[2] += r4.z; va[3] += r4.w;
-            }
-          }
-        }
-      } else {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int ke = kk + e;
-          if (ke < K) {
-            const int j = ke / s.Cin, c = ke - j * s.Cin;
-            const int ti = to * s.stride + j - s.pad;
-            if (ti >= 0 && ti < s.Tin)
-              va[e] = x[((size_t)b * s.Tin + ti) * s.Cin + c] + (rowbias ? rowbias[(size_t)b * s.Cin + c] : 0.f);
+    if (m >= me) return;
+    const int b = m / s.Tout, to = m - b * s.Tout;
+    const int kk = k0 + l_c4;
+    if (vecA) {                  // K = k * Cin is a multiple of 4 and a float4 never straddles two taps
+      if (kk < K) {
+        const int j = kk / s.Cin, c = kk - j * s.Cin;
+        const int ti = to * s.stride + j - s.pad;
+        if (ti >= 0 && ti < s.Tin) {
+          const float4 x4 = *reinterpret_cast<const float4*>(x + ((size_t)b * s.Tin + ti) * s.Cin + c);
+          va[0] = x4.x; va[1] = x4.y; va[2] = x4.z; va[3] = x4.w;
+          if (rowbias) {
+            const float4 r4 = *reinterpret_cast<const float4*>(rowbias + (size_t)b * s.Cin + c);
+            va[0] += r4.x; va[1] += r4.y; va[2] += r4.z; va[3] += r4.w;
           }
         }
       }
-      const int n = n0 + l_c4;
-      if (vecB && n + 3 < s.Cout) {
-        const float4 d4 = *reinterpret_cast<const float4*>(dz + (size_t)m * s.Cout + n);
-        vb[0] = d4.x; vb[1] = d4.y; vb[2] = d4.z; vb[3] = d4.w;
-      } else {
+    } else {
 #pragma unroll
-        for (int e = 0; e < 4; ++e) if (n + e < s.Cout) vb[e] = dz[(size_t)m * s.Cout + n + e];
+      for (int e = 0; e < 4; ++e) {
+        const int ke = kk + e;
+        if (ke < K) {
+          const int j = ke / s.Cin, c = ke - j * s.Cin;
+          const int ti = to * s.stride + j - s.pad;
+          if (ti >= 0 && ti < s.Tin)
+            va[e] = x[((size_t)b * s.Tin + ti) * s.Cin + c] + (rowbias ? rowbias[(size_t)b * s.Cin + c] : 0.f);
+        }
       }
     }
+    const int n = n0 + l_c4;
+    if (vecB && n + 3 < s.Cout) {
+      const float4 d4 = *reinterpret_cast<const float4*>(dz + (size_t)m * s.Cout + n);
+      vb[0] = d4.x; vb[1] = d4.y; vb[2] = d4.z; vb[3] = d4.w;
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) if (n + e < s.Cout) vb[e] = dz[(size_t)m * s.Cout + n + e];
+    }
+  };
+  float va[4], vb[4];
+  load_ab(mb, va, vb);
+  for (int m0 = mb; m0 < me; m0 += TK) {
     *reinterpret_cast<float4*>(&As[l_m][l_c4]) = make_float4(va[0], va[1], va[2], va[3]);
     *reinterpret_cast<float4*>(&Bs[l_m][l_c4]) = make_float4(vb[0], vb[1], vb[2], vb[3]);
     __syncthreads();
+    if (m0 + TK < me) load_ab(m0 + TK, va, vb);          // the next 16 rows are in flight during the multiply
 #pragma unroll
     for (int q = 0; q < TK; ++q) {
       const float4 a4 = *reinterpret_cast<const float4*>(&As[q][ty * 4]);
@@ -266,18 +276,51 @@ __global__ void wgrad_reduce_f32_kernel(const float* __restrict__ part, float* _
   dw[i] = a;
 }
 
-// out[g][c] = sum over the group's rows of a[row][c]   (bias gradient: one group; rowbias gradient: one group per utterance)
-__global__ void colsum_f32_kernel(const float* __restrict__ a, float* __restrict__ out, int rows_per_group, int C) {
-  const int g = blockIdx.y, c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  const float* p = a + (size_t)g * rows_per_group * C + c;
+// out[g][c] = sum over the group's rows of a[row][c]   (bias gradient: one group; rowbias gradient: one group per utterance).
+// Two deterministic stages: 256-thread blocks (32 columns x 8 row lanes, 128-byte coalesced rows) sum one row split each
+// into part[split][g][c] in a fixed order, then one thread per output adds the splits in order.  (A single 128-thread
+// block walking all 6400 rows took 100-390 us per call and a quarter of the discriminator's time.)
+constexpr int CS_MAX_SPLITS = 64;
+__global__ void __launch_bounds__(256) colsum_part_kernel(const float* __restrict__ a, float* __restrict__ part, int rows_per_group,
+                                                          int C, int rows_per_split) {
+  __shared__ float red[8][33];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx, g = blockIdx.y, sp = blockIdx.z;
+  const int r0 = sp * rows_per_split, r1 = min(rows_per_group, r0 + rows_per_split);
   float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-  int r = 0;
-  for (; r + 3 < rows_per_group; r += 4) {
-    s0 += p[(size_t)r * C]; s1 += p[(size_t)(r + 1) * C]; s2 += p[(size_t)(r + 2) * C]; s3 += p[(size_t)(r + 3) * C];
+  if (c < C) {
+    const float* p = a + (size_t)g * rows_per_group * C + c;
+    int r = r0 + ry;
+    for (; r + 24 < r1; r += 32) {
+      s0 += p[(size_t)r * C]; s1 += p[(size_t)(r + 8) * C]; s2 += p[(size_t)(r + 16) * C]; s3 += p[(size_t)(r + 24) * C];
+    }
+    for (; r < r1; r += 8) s0 += p[(size_t)r * C];
   }
-  for (; r < rows_per_group; ++r) s0 += p[(size_t)r * C];
-  out[(size_t)g * C + c] = (s0 + s1) + (s2 + s3);
+  red[ry][cx] = (s0 + s1) + (s2 + s3);
+  __syncthreads();
+  if (ry == 0 && c < C) {
+    float t = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) t += red[q][cx];
+    part[((size_t)sp * gridDim.y + g) * C + c] = t;
+  }
+}
+__global__ void colsum_final_kernel(const float* __restrict__ part, float* __restrict__ out, int GC, int nsplit) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= GC) return;
+  float t = 0.f;
+  for (int sp = 0; sp < nsplit; ++sp) t += part[(size_t)sp * GC + i];
+  out[i] = t;
+}
+inline int colsum_splits(int rows_per_group) {
+  int sp = (rows_per_group + 127) / 128;
+  return sp < 1 ? 1 : (sp > CS_MAX_SPLITS ? CS_MAX_SPLITS : sp);
+}
+inline void launch_colsum(const float* a, float* out, float* part, int groups, int rows_per_group, int C, cudaStream_t st) {
+  const int sp = colsum_splits(rows_per_group);
+  const int rps = ((rows_per_group + sp - 1) / sp + 7) / 8 * 8;
+  colsum_part_kernel<<<dim3((C + 31) / 32, groups, sp), 256, 0, st>>>(a, part, rows_per_group, C, rps);
+  colsum_final_kernel<<<(groups * C + 255) / 256, 256, 0, st>>>(part, out, groups * C, sp);
 }
 
 // emb[b] = [sin(t f_i), cos(t f_i)], f_i = exp(-i ln(1e4) / (dim/2 - 1))     (blocks.py:906-913)
@@ -309,7 +352,7 @@ int wgrad_splits(const ConvShape& s) {
   if (want > max_by_rows) want = max_by_rows;
   return want < 1 ? 1 : (want > 64 ? 64 : want);
 }
-struct Work { size_t wp, wq, dz, part, total; };
+struct Work { size_t wp, wq, dz, part, cs, total; };
 Work work_layout(const ConvShape& s) {
   Work w{};
   size_t p = 0;
@@ -318,6 +361,7 @@ Work work_layout(const ConvShape& s) {
   w.wp = take(wn); w.wq = take(wn);
   w.dz = take((size_t)s.B * s.Tout * s.Cout);
   w.part = take((size_t)wgrad_splits(s) * wn);
+  w.cs = take((size_t)CS_MAX_SPLITS * (size_t)((size_t)s.B * s.Cin > (size_t)s.Cout ? (size_t)s.B * s.Cin : (size_t)s.Cout));
   w.total = p;
   return w;
 }
@@ -396,8 +440,8 @@ int mgb_conv1d_backward(const float* x, const float* w, const float* rowbias, co
     if (grad_rowbias) {
       // d rowbias[b][ci] = sum over the rows of utterance b of grad_x: exact, because every existing input row carries
       // the bias once and grad_x is the gradient with respect to (x + rowbias)
-      colsum_f32_kernel<<<dim3((Cin + 127) / 128, B), 128, 0, st>>>(grad_x, grad_rowbias, Tin, Cin);
-      ++launches;
+      launch_colsum(grad_x, grad_rowbias, reinterpret_cast<float*>(W + wl.cs), B, Tin, Cin, st);
+      launches += 2;
     }
   }
   if (grad_w) {
@@ -410,8 +454,8 @@ int mgb_conv1d_backward(const float* x, const float* w, const float* rowbias, co
     launches += 2;
   }
   if (grad_bias) {
-    colsum_f32_kernel<<<dim3((Cout + 127) / 128, 1), 128, 0, st>>>(dz, grad_bias, B * s.Tout, Cout);
-    ++launches;
+    launch_colsum(dz, grad_bias, reinterpret_cast<float*>(W + wl.cs), 1, B * s.Tout, Cout, st);
+    launches += 2;
   }
   note_launch(launches);
   MGB_LAUNCH_CHECK();

@@ -90,11 +90,12 @@ class GaussianDiffusion(nn.Module):
 
     def diffuse_fn(self, x_start, t, noise=None):
         x_start = self.norm_spec(x_start).transpose(1, 2)[:, None, :, :]   # [B,1,M,T]
+        # diffusion.py:177-185 without its two boolean-mask index operations: those size their result on the host
+        # (a device synchronisation per call, and not capturable in a CUDA graph); masked_fill_ / where give the same values
         neg = t < 0
-        t[neg] = 0                                                         # in place, as the reference
+        t.masked_fill_(neg, 0)                                             # in place, as the reference
         out = self.q_sample(x_start=x_start, t=t, noise=noise)
-        out[neg] = x_start[neg]
-        return out
+        return torch.where(neg.reshape(-1, 1, 1, 1), x_start, out)
 
     def diffuse_trace(self, x_start, mask):
         b, device = x_start.shape[0], x_start.device

@@ -688,7 +688,8 @@ def bench_train(ctx, prec, steps, warmup, B):
         flat = torch.cat([p.grad.reshape(-1) for p in d_params])
         ctx.dist.all_reduce(flat)
         flat /= ctx.world
-        torch._foreach_copy_([p.grad for p in d_params], list(flat.split([p.numel() for p in d_params])))
+        torch._foreach_copy_([p.grad for p in d_params],
+                             [c.view_as(p) for c, p in zip(flat.split([p.numel() for p in d_params]), d_params)])
 
     def gan_step(i, with_sync=True, s=None):
         s = s if s is not None else sets[i % NSETS]

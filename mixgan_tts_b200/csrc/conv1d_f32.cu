@@ -119,26 +119,34 @@ __global__ void __launch_bounds__(NTHR) conv_gemm_f32_kernel(const float* __rest
     }
   };
 
-  float pa[4], pb[4];
-  load_a(0, pa);
-  load_b(0, pb);
-  for (int k0 = 0; k0 < K; k0 += TK) {
+  // PF k-steps of operand tiles are in flight in registers (static indices: the k loop is unrolled by PF)
+  constexpr int PF = 4;
+  float pa[PF][4], pb[PF][4];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) As[a_k4 + e][a_r] = pa[e];
-    *reinterpret_cast<float4*>(&Bs[b_k][b_n4]) = make_float4(pb[0], pb[1], pb[2], pb[3]);
-    __syncthreads();
-    if (k0 + TK < K) { load_a(k0 + TK, pa); load_b(k0 + TK, pb); }     // in flight during the multiply
+  for (int u = 0; u < PF; ++u) { load_a(u * TK, pa[u]); load_b(u * TK, pb[u]); }
+  for (int kb = 0; kb < K; kb += PF * TK) {
 #pragma unroll
-    for (int kq = 0; kq < TK; ++kq) {
-      const float4 a4 = *reinterpret_cast<const float4*>(&As[kq][ty * 4]);
-      const float4 b4 = *reinterpret_cast<const float4*>(&Bs[kq][tx * 4]);
-      const float a[4] = {a4.x, a4.y, a4.z, a4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
+    for (int u = 0; u < PF; ++u) {
+      const int k0 = kb + u * TK;
+      if (k0 >= K) break;                                             // uniform over the block
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int e = 0; e < 4; ++e) As[a_k4 + e][a_r] = pa[u][e];
+      *reinterpret_cast<float4*>(&Bs[b_k][b_n4]) = make_float4(pb[u][0], pb[u][1], pb[u][2], pb[u][3]);
+      __syncthreads();
+      load_a(k0 + PF * TK, pa[u]);                                    // zero beyond K; in flight during the next PF multiplies
+      load_b(k0 + PF * TK, pb[u]);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+      for (int kq = 0; kq < TK; ++kq) {
+        const float4 a4 = *reinterpret_cast<const float4*>(&As[kq][ty * 4]);
+        const float4 b4 = *reinterpret_cast<const float4*>(&Bs[kq][tx * 4]);
+        const float a[4] = {a4.x, a4.y, a4.z, a4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+      }
+      __syncthreads();
     }
-    __syncthreads();
   }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -234,24 +242,31 @@ __global__ void __launch_bounds__(NTHR) conv_wgrad_f32_kernel(const float* __res
       for (int e = 0; e < 4; ++e) if (n + e < s.Cout) vb[e] = dz[(size_t)m * s.Cout + n + e];
     }
   };
-  float va[4], vb[4];
-  load_ab(mb, va, vb);
-  for (int m0 = mb; m0 < me; m0 += TK) {
-    *reinterpret_cast<float4*>(&As[l_m][l_c4]) = make_float4(va[0], va[1], va[2], va[3]);
-    *reinterpret_cast<float4*>(&Bs[l_m][l_c4]) = make_float4(vb[0], vb[1], vb[2], vb[3]);
-    __syncthreads();
-    if (m0 + TK < me) load_ab(m0 + TK, va, vb);          // the next 16 rows are in flight during the multiply
+  constexpr int PF = 4;                                  // row chunks in flight in registers
+  float va[PF][4], vb[PF][4];
 #pragma unroll
-    for (int q = 0; q < TK; ++q) {
-      const float4 a4 = *reinterpret_cast<const float4*>(&As[q][ty * 4]);
-      const float4 b4 = *reinterpret_cast<const float4*>(&Bs[q][tx * 4]);
-      const float a[4] = {a4.x, a4.y, a4.z, a4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
+  for (int u = 0; u < PF; ++u) load_ab(mb + u * TK, va[u], vb[u]);
+  for (int mq = mb; mq < me; mq += PF * TK) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+    for (int u = 0; u < PF; ++u) {
+      const int m0 = mq + u * TK;
+      if (m0 >= me) break;                               // uniform over the block
+      *reinterpret_cast<float4*>(&As[l_m][l_c4]) = make_float4(va[u][0], va[u][1], va[u][2], va[u][3]);
+      *reinterpret_cast<float4*>(&Bs[l_m][l_c4]) = make_float4(vb[u][0], vb[u][1], vb[u][2], vb[u][3]);
+      __syncthreads();
+      load_ab(m0 + PF * TK, va[u], vb[u]);               // zero beyond the split
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+      for (int q = 0; q < TK; ++q) {
+        const float4 a4 = *reinterpret_cast<const float4*>(&As[q][ty * 4]);
+        const float4 b4 = *reinterpret_cast<const float4*>(&Bs[q][tx * 4]);
+        const float a[4] = {a4.x, a4.y, a4.z, a4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+      }
+      __syncthreads();
     }
-    __syncthreads();
   }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {

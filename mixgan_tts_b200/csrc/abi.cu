@@ -90,6 +90,42 @@ __global__ void __launch_bounds__(EW_THREADS) shallow_start_kernel(const float* 
   const size_t row0 = ((size_t)b * T + t0) * M;      // contiguous run of nt * M floats of coarse
   const int n = nt * M;
   auto norm = [&](float c, int m) { return __fsub_rn(__fmul_rn(__fdiv_rn(__fsub_rn(c, s_lo[m]), s_span[m]), 2.f), 1.f); };
+  if constexpr (MT > 0 && (MT * EW_TF / 4) % EW_THREADS == 0) {
+    // Full tile, all pointers 16-byte aligned: every thread moves PER float4 of each operand and issues each operand's PER
+    // independent 16-byte loads back to back — the kernel is latency-bound (13 us for 49 MB), so bytes in flight per thread
+    // are what sets its bandwidth (a plain copy of this size reaches 0.58 of the HBM peak on this box).
+    constexpr int PER = (MT * EW_TF / 4) / EW_THREADS, Q = EW_TF / 4;
+    if (nt == EW_TF && (T & 3) == 0 &&
+        ((reinterpret_cast<uintptr_t>(coarse + row0) | reinterpret_cast<uintptr_t>(noise) | reinterpret_cast<uintptr_t>(xT)) & 15) == 0) {
+      const float4* src = reinterpret_cast<const float4*>(coarse + row0);
+      float4 cv[PER], nz[PER];
+#pragma unroll
+      for (int k = 0; k < PER; ++k) cv[k] = __ldg(src + threadIdx.x + k * EW_THREADS);
+#pragma unroll
+      for (int k = 0; k < PER; ++k) {
+        const int i = threadIdx.x + k * EW_THREADS, t = (4 * i) / MT, m = 4 * i - t * MT;
+        tile[m][t] = norm(cv[k].x, m); tile[m + 1][t] = norm(cv[k].y, m + 1);
+        tile[m + 2][t] = norm(cv[k].z, m + 2); tile[m + 3][t] = norm(cv[k].w, m + 3);
+      }
+#pragma unroll
+      for (int k = 0; k < PER; ++k) {
+        const int i = threadIdx.x + k * EW_THREADS, m = i / Q, tq = (i - m * Q) * 4;
+        nz[k] = __ldg(reinterpret_cast<const float4*>(noise + ((size_t)b * MT + m) * T + t0 + tq));
+      }
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < PER; ++k) {
+        const int i = threadIdx.x + k * EW_THREADS, m = i / Q, tq = (i - m * Q) * 4;
+        float4 r;
+        r.x = __fadd_rn(__fmul_rn(sa, tile[m][tq]), __fmul_rn(sn, nz[k].x)) * s_valid[tq];
+        r.y = __fadd_rn(__fmul_rn(sa, tile[m][tq + 1]), __fmul_rn(sn, nz[k].y)) * s_valid[tq + 1];
+        r.z = __fadd_rn(__fmul_rn(sa, tile[m][tq + 2]), __fmul_rn(sn, nz[k].z)) * s_valid[tq + 2];
+        r.w = __fadd_rn(__fmul_rn(sa, tile[m][tq + 3]), __fmul_rn(sn, nz[k].w)) * s_valid[tq + 3];
+        *reinterpret_cast<float4*>(xT + ((size_t)b * MT + m) * T + t0 + tq) = r;
+      }
+      return;
+    }
+  }
   if ((reinterpret_cast<uintptr_t>(coarse + row0) & 15) == 0 && (M & 3) == 0) {   // a float4 never straddles two frames
     const float4* src = reinterpret_cast<const float4*>(coarse + row0);
     for (int i = threadIdx.x; i < n / 4; i += EW_THREADS) {
@@ -140,7 +176,26 @@ __global__ void __launch_bounds__(EW_THREADS) denorm_mask_kernel(const float* __
   for (int i = threadIdx.x; i < M; i += EW_THREADS) { s_lo[i] = smin[i]; s_span[i] = __fsub_rn(smax[i], smin[i]); }
   for (int i = threadIdx.x; i < nt; i += EW_THREADS) s_valid[i] = (pad && pad[(size_t)b * T + t0 + i]) ? 0.f : 1.f;
   const bool vec = (T & 3) == 0 && (nt & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
-  if (vec) {
+  bool loaded = false;
+  if constexpr (MT > 0 && (MT * EW_TF / 4) % EW_THREADS == 0) {
+    constexpr int PER = (MT * EW_TF / 4) / EW_THREADS, Q = EW_TF / 4;
+    if (vec && nt == EW_TF) {            // full tile: all PER loads of a thread in flight before the first use
+      float4 v[PER];
+#pragma unroll
+      for (int k = 0; k < PER; ++k) {
+        const int i = threadIdx.x + k * EW_THREADS, m = i / Q, tq = (i - m * Q) * 4;
+        v[k] = __ldg(reinterpret_cast<const float4*>(x + ((size_t)b * MT + m) * T + t0 + tq));
+      }
+#pragma unroll
+      for (int k = 0; k < PER; ++k) {
+        const int i = threadIdx.x + k * EW_THREADS, m = i / Q, tq = (i - m * Q) * 4;
+        tile[m][tq] = v[k].x; tile[m][tq + 1] = v[k].y; tile[m][tq + 2] = v[k].z; tile[m][tq + 3] = v[k].w;
+      }
+      loaded = true;
+    }
+  }
+  if (loaded) {
+  } else if (vec) {
     const int q = nt / 4;
     for (int i = threadIdx.x; i < M * q; i += EW_THREADS) {
       const int m = i / q, tq = (i - m * q) * 4;

@@ -30,13 +30,13 @@ constexpr int DK = 128;           // head width the attention kernel is written 
 
 // =====================================================================================================
 // Self-attention on the tensor cores, two passes over the keys of one utterance per 128-query tile:
-//   pass 1   S = Q K^T per 128-key block (TMEM, double-buffered) -> running row max and sum (online, registers)
-//   pass 2   S again -> P = exp(S/sqrt(d) - max) / sum as fp16 into shared memory (K-major A operand)
-//            -> O += P V with V read as an MN-major B operand straight from its image box (no transpose)
-// so O never needs rescaling and leaves TMEM once.  Keys at or beyond the utterance's length are masked (-inf, as
+//   pass 1   S = Q K^T per 128-key block (TMEM, double-buffered) -> row max (registers)
+//   pass 2   S again -> P = exp(S/sqrt(d) - max) <= 1, unnormalised, as fp16 into shared memory (K-major A operand), row
+//            sums in fp32 -> O += P V with V read as an MN-major B operand straight from its image box (no transpose)
+// so O never needs rescaling, every exponential is taken once, and O leaves TMEM once, scaled by 1 / sum.  Keys at or beyond the utterance's length are masked (-inf, as
 // SubLayers.py:47 / Modules.py:19-20) and key blocks beyond it are never loaded; query tiles beyond it are skipped
 // (FFTBlock zero-fills those rows, Layers.py:27 — the next GEMM's epilogue does that here).
-// 192 threads: TMA warp, MMA warp, 4 softmax warps (thread = query row = TMEM lane).
+// 320 threads: TMA warp, MMA warp, 8 softmax warps (thread = query row = TMEM lane x one half of a key block's columns).
 // =====================================================================================================
 constexpr int ATT_TILE_BYTES = 128 * DK * 2;     // 32 KB: 128 rows x 128 channels fp16
 constexpr int ATT_RING = 4;
@@ -50,12 +50,13 @@ struct AttArgs {
   int* status;
 };
 
-__global__ void __launch_bounds__(192, 1) attn_kernel(const AttArgs p, const __grid_constant__ CUtensorMap tm) {
+__global__ void __launch_bounds__(320, 1) attn_kernel(const AttArgs p, const __grid_constant__ CUtensorMap tm) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   __shared__ __align__(8) uint64_t bar_q, ring_full[ATT_RING], ring_empty[ATT_RING], s_full[2], s_free[2], p_full[2],
       p_free[2], o_full;
   __shared__ uint32_t tmem_slot;
+  __shared__ float s_stat[2][128];          // row max, then row sum, of the two column halves
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
@@ -69,8 +70,8 @@ __global__ void __launch_bounds__(192, 1) attn_kernel(const AttArgs p, const __g
     tc::mbar_init(&bar_q, 1);
     for (int i = 0; i < ATT_RING; ++i) { tc::mbar_init(&ring_full[i], 1); tc::mbar_init(&ring_empty[i], 1); }
     for (int i = 0; i < 2; ++i) {
-      tc::mbar_init(&s_full[i], 1); tc::mbar_init(&s_free[i], 4);
-      tc::mbar_init(&p_full[i], 4); tc::mbar_init(&p_free[i], 1);
+      tc::mbar_init(&s_full[i], 1); tc::mbar_init(&s_free[i], 8);
+      tc::mbar_init(&p_full[i], 8); tc::mbar_init(&p_free[i], 1);
     }
     tc::mbar_init(&o_full, 1);
     tc::fence_barrier_init();
@@ -151,64 +152,59 @@ __global__ void __launch_bounds__(192, 1) attn_kernel(const AttArgs p, const __g
       tc::umma_commit(&o_full);
     }
   } else {
+    // 8 softmax warps: warp w owns TMEM lanes 32*(w%4).. (= query rows) and the column half (w-2)/4 of every 128-key block
     const int i = (warp & 3) * 32 + lane;
+    const int half = (warp - 2) >> 2;
     const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     const float c2 = p.c2;
-    float m = -INFINITY, l = 0.f;
-    // pass 1: row max and sum
+    auto ex2 = [](float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; };
+    float m = -INFINITY;
+    // pass 1: row max only (the exponentials are taken once, in pass 2, relative to the final max)
     for (int c = 0; c < nblk; ++c) {
       tc::mbar_wait_trap(tc::smem_u32(&s_full[c & 1]), (c >> 1) & 1, kTimeout, p.status, 4);
       tc::tc_fence_after();
-#pragma unroll 1
-      for (int cg = 0; cg < 4; ++cg) {
+#pragma unroll
+      for (int cg = 0; cg < 2; ++cg) {
         uint32_t r[32];
-        tc::tmem_ld32(trow + (c & 1) * 128 + cg * 32, r);
+        tc::tmem_ld32(trow + (c & 1) * 128 + half * 64 + cg * 32, r);
         tc::tmem_ld_wait();
-        const int key0 = c * 128 + cg * 32;
-        float cm = -INFINITY;
+        const int key0 = c * 128 + half * 64 + cg * 32;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float s = key0 + j < len ? __uint_as_float(r[j]) : -INFINITY;
-          r[j] = __float_as_uint(s);
-          cm = fmaxf(cm, s);
-        }
-        const float mn = fmaxf(m, cm);
-        if (mn > -INFINITY) {
-          float acc = 0.f;
-          const float mc = mn * c2;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) acc += exp2f(fmaf(__uint_as_float(r[j]), c2, -mc));
-          l = l * exp2f((m - mn) * c2) + acc;
-          m = mn;
-        }
+        for (int j = 0; j < 32; ++j) m = fmaxf(m, key0 + j < len ? __uint_as_float(r[j]) : -INFINITY);
       }
       tc::tc_fence_before();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&s_free[c & 1]);
     }
-    const float inv_l = 1.f / l, mc = m * c2;
-    // pass 2: normalised probabilities -> shared memory (A operand of P V)
+    s_stat[half][i] = m;
+    asm volatile("bar.sync 1, 256;" ::: "memory");               // the 8 softmax warps only
+    m = fmaxf(s_stat[0][i], s_stat[1][i]);                       // finite: key 0 of every utterance is valid
+    const float mc = m * c2;
+    float l = 0.f;
+    // pass 2: unnormalised probabilities exp(s/sqrt(d) - max) <= 1 -> fp16 in shared memory (A operand of P V), row sums in fp32
     for (int j = 0; j < nblk; ++j) {
       const int c = nblk + j;
       tc::mbar_wait_trap(tc::smem_u32(&s_full[c & 1]), (c >> 1) & 1, kTimeout, p.status, 4);
       if (j >= 2) tc::mbar_wait_trap(tc::smem_u32(&p_free[j & 1]), ((j >> 1) - 1) & 1, kTimeout, p.status, 4);
       tc::tc_fence_after();
       uint8_t* pb = smem + ATT_TILE_BYTES * (1 + ATT_RING + (j & 1));
-#pragma unroll 1
-      for (int cg = 0; cg < 4; ++cg) {
+#pragma unroll
+      for (int cg = 0; cg < 2; ++cg) {
         uint32_t r[32];
-        tc::tmem_ld32(trow + (c & 1) * 128 + cg * 32, r);
+        tc::tmem_ld32(trow + (c & 1) * 128 + half * 64 + cg * 32, r);
         tc::tmem_ld_wait();
-        const int key0 = j * 128 + cg * 32;
+        const int key0 = j * 128 + half * 64 + cg * 32;
         float pr[32];
 #pragma unroll
-        for (int e = 0; e < 32; ++e)
-          pr[e] = key0 + e < len ? exp2f(fmaf(__uint_as_float(r[e]), c2, -mc)) * inv_l : 0.f;
+        for (int e = 0; e < 32; ++e) {
+          pr[e] = key0 + e < len ? ex2(fmaf(__uint_as_float(r[e]), c2, -mc)) : 0.f;
+          l += pr[e];
+        }
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           __half2 h0 = __floats2half2_rn(pr[q * 8], pr[q * 8 + 1]), h1 = __floats2half2_rn(pr[q * 8 + 2], pr[q * 8 + 3]);
           __half2 h2 = __floats2half2_rn(pr[q * 8 + 4], pr[q * 8 + 5]), h3 = __floats2half2_rn(pr[q * 8 + 6], pr[q * 8 + 7]);
-          *reinterpret_cast<uint4*>(pb + (cg * 4 + q) * 2048 + i * 16) =
+          *reinterpret_cast<uint4*>(pb + (half * 8 + cg * 4 + q) * 2048 + i * 16) =
               make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1),
                          *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
         }
@@ -218,24 +214,27 @@ __global__ void __launch_bounds__(192, 1) attn_kernel(const AttArgs p, const __g
       __syncwarp();
       if (lane == 0) { tc::mbar_arrive(&p_full[j & 1]); tc::mbar_arrive(&s_free[c & 1]); }
     }
-    // O -> fp16 image, channels h*128 ...
+    s_stat[half][i] = l;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    const float inv_l = 1.f / (s_stat[0][i] + s_stat[1][i]);
+    // O / l -> fp16 image, channels h*128 + half*64 ...
     tc::mbar_wait_trap(tc::smem_u32(&o_full), 0, kTimeout, p.status, 4);
     tc::tc_fence_after();
     const int tq = qt * 128 + i;
     const size_t orow = (size_t)row_u + tq;
-#pragma unroll 1
-    for (int cg = 0; cg < 4; ++cg) {
+#pragma unroll
+    for (int cg = 0; cg < 2; ++cg) {
       uint32_t r[32];
-      tc::tmem_ld32(trow + 256 + cg * 32, r);
+      tc::tmem_ld32(trow + 256 + half * 64 + cg * 32, r);
       tc::tmem_ld_wait();
       if (tq < p.T) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          __half2 h0 = __floats2half2_rn(__uint_as_float(r[q * 8]), __uint_as_float(r[q * 8 + 1]));
-          __half2 h1 = __floats2half2_rn(__uint_as_float(r[q * 8 + 2]), __uint_as_float(r[q * 8 + 3]));
-          __half2 h2 = __floats2half2_rn(__uint_as_float(r[q * 8 + 4]), __uint_as_float(r[q * 8 + 5]));
-          __half2 h3 = __floats2half2_rn(__uint_as_float(r[q * 8 + 6]), __uint_as_float(r[q * 8 + 7]));
-          *reinterpret_cast<uint4*>(p.out + ((size_t)(h * (DK / 8) + cg * 4 + q) * p.Rp + orow) * 8) =
+          __half2 h0 = __floats2half2_rn(__uint_as_float(r[q * 8]) * inv_l, __uint_as_float(r[q * 8 + 1]) * inv_l);
+          __half2 h1 = __floats2half2_rn(__uint_as_float(r[q * 8 + 2]) * inv_l, __uint_as_float(r[q * 8 + 3]) * inv_l);
+          __half2 h2 = __floats2half2_rn(__uint_as_float(r[q * 8 + 4]) * inv_l, __uint_as_float(r[q * 8 + 5]) * inv_l);
+          __half2 h3 = __floats2half2_rn(__uint_as_float(r[q * 8 + 6]) * inv_l, __uint_as_float(r[q * 8 + 7]) * inv_l);
+          *reinterpret_cast<uint4*>(p.out + ((size_t)(h * (DK / 8) + half * 8 + cg * 4 + q) * p.Rp + orow) * 8) =
               make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1),
                          *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
         }
@@ -261,7 +260,7 @@ int run_attention(const __half* qkv, int qkv_chunks, const Rows& r, int n_head, 
   a.q_chunk0 = 0; a.k_chunk0 = n_head * (DK / 8); a.v_chunk0 = 2 * n_head * (DK / 8);
   a.c2 = 1.4426950408889634f / sqrtf((float)DK);
   a.status = status;
-  MGB_CUDA_CHECK(launch_pdl(attn_kernel, dim3((r.T + 127) / 128, n_head, r.B), dim3(192), ATT_SMEM, s, 1, a, m));
+  MGB_CUDA_CHECK(launch_pdl(attn_kernel, dim3((r.T + 127) / 128, n_head, r.B), dim3(320), ATT_SMEM, s, 1, a, m));
   note_launch();
   return MGB_OK;
 }

@@ -250,7 +250,7 @@ __device__ __forceinline__ void epilogue(const KArgs& p, const float* s_bias, co
         for (int q = 0; q < 8; ++q)
           *reinterpret_cast<float4*>(uo + n0 + q * 4) = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
       } else {
-#pragma unroll 1
+#pragma unroll                                                   // static indices: a rolled loop would put v[] in local memory
         for (int j = 0; j < 32; ++j)
           if (n0 + j < p.Cout) uo[n0 + j] = v[j];
       }

@@ -51,7 +51,8 @@ struct KArgs {
   float* user_out; int user_ld;
   int up; long long Rp_out;
   int ntiles, ntn;             // work list: row tiles x column tiles
-  int rows, resident;          // rows of an A halo tile (128 + 2 * (taps / 2) * dil); 1 = the whole weight matrix stays in shared memory
+  int rows, halo8, resident;   // rows of an A halo tile (128 + 2 * halo8, halo8 = the padding rounded up to 8 rows; 128 = plain
+                               // 2-D box); 1 = the whole weight matrix stays in shared memory
   int* status;
   long long* trace;            // debug library only (MGB_TC_TRACE=1): SM-cycle stamps of CTA 0's first 64 work items
 };
@@ -342,6 +343,7 @@ __global__ void __launch_bounds__(Groups<NT>::THREADS, 1) tcconv_kernel(const KA
   const uint32_t w_base = tc::smem_u32(smem);
   const uint32_t a_base = w_base + S::W_REGION;
   const int halo = (p.taps >> 1) * p.dil;
+  const int row_shift = p.halo8 - halo;                 // the first tap's row inside the tile
   const uint32_t a_bytes = (uint32_t)p.rows * KC * 2;
 
   // The TMA and MMA roles run with WARP-UNIFORM control flow (all 32 lanes wait on the barriers and walk the work list);
@@ -368,8 +370,9 @@ __global__ void __launch_bounds__(Groups<NT>::THREADS, 1) tcconv_kernel(const KA
         if (tc::elect_one()) {
           const uint32_t fb = tc::smem_u32(&a_full[st]);
           tc::mbar_arrive_expect_tx_addr(fb, a_bytes);
-          // (128 + 2*halo) rows x KC channels in ONE box, zero-filled outside the row axis
-          tc::tma_load_3d(a_base + st * S::A_STAGE, &tmA, 0, tile * TILE - halo, kc * (KC / 8), fb);
+          // (128 + 2*halo8) rows x KC channels in ONE box, zero-filled outside the row axis
+          if (p.halo8 == 0) tc::tma_load_2d(a_base + st * S::A_STAGE, &tmA, 2 * tile * TILE, kc * (KC / 8), fb);
+          else tc::tma_load_3d(a_base + st * S::A_STAGE, &tmA, 0, (tile * TILE - p.halo8) >> 3, kc * (KC / 8), fb);
         }
         if (!p.resident) {
           for (int tap = 0; tap < p.taps; ++tap, ++iw) {
@@ -417,7 +420,7 @@ __global__ void __launch_bounds__(Groups<NT>::THREADS, 1) tcconv_kernel(const KA
             b = b_desc0 + (uint64_t)(ws * (S::W_STAGE >> 4));
             ++iw;
           }
-          const uint64_t a = a_st + (uint64_t)(tap * p.dil);     // the tap: the same tile, tap*dil rows (16 B each) further
+          const uint64_t a = a_st + (uint64_t)(row_shift + tap * p.dil);   // the tap: the same tile, tap*dil rows (16 B each) further
           if (tc::elect_one()) {
 #pragma unroll
             for (int k = 0; k < KC / 16; ++k)
@@ -471,9 +474,11 @@ int launch_conv(KArgs a, const __half* in, int in_chunks, int Rp_in, int ntiles,
     once.done();
   }
   CUtensorMap m;
-  a.rows = TILE + 2 * (a.taps >> 1) * a.dil;
-  MGB_REQUIRE(a.rows <= ROWS_MAX, MGB_E_UNSUPPORTED, "convolution padding %d exceeds %d rows", (a.rows - TILE) / 2, (ROWS_MAX - TILE) / 2);
-  if (int rc = make_image_map3(&m, in, in_chunks, Rp_in, a.rows, KC / 8)) return rc;
+  a.halo8 = ((a.taps >> 1) * a.dil + 7) / 8 * 8;
+  a.rows = TILE + 2 * a.halo8;
+  MGB_REQUIRE(a.rows <= ROWS_MAX, MGB_E_UNSUPPORTED, "convolution padding %d exceeds %d rows", (a.taps >> 1) * a.dil, (ROWS_MAX - TILE) / 2);
+  if (a.halo8 == 0) { if (int rc = make_image_map(&m, in, in_chunks, Rp_in, KC / 8)) return rc; }
+  else if (int rc = make_image_map3(&m, in, in_chunks, Rp_in, a.rows, KC / 8)) return rc;
   a.ntiles = ntiles; a.ntn = ntn;
   a.resident = (ntn == 1 && (long long)a.taps * a.kspt * S::W_STAGE <= S::W_REGION) ? 1 : 0;
   const long long nwork = (long long)ntiles * ntn;

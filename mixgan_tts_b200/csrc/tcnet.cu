@@ -123,31 +123,37 @@ __device__ __forceinline__ void epilogue(const KArgs& p, const float* s_bias, co
       // LayerNorm(acc + bias + residual) over the 256 channels of this thread's row (nn.LayerNorm: biased variance, eps
       // 1e-5).  Pass A accumulates sum(x - s) and sum((x - s)^2) around a per-row shift s (the first element), which is
       // as accurate as the two-pass form when |mean| >> std; pass B normalises and stores.
+      // Pass A also writes x = acc + bias + residual back over the accumulator (tcgen05.st), so pass B reads TMEM only; the
+      // residual of column group cg + 1 is fetched (HBM / L2 latency) while group cg is processed.
       const bool has_res = valid && p.res1 != nullptr;
       float s1 = 0.f, s2 = 0.f, shift = 0.f;
-      auto pass_a = [&](int cg, uint32_t (&cur)[32], uint32_t (&nxt)[32]) {
+      float rra[32], rrb[32];
+      auto pass_a = [&](int cg, uint32_t (&cur)[32], uint32_t (&nxt)[32], float (&rcur)[32], float (&rnxt)[32]) {
         tc::tmem_ld_wait();
-        if (cg + 1 < NCG) tmem_ld_issue(trow + (cg + 1) * 32, nxt);
-        float x[32];
+        if (cg + 1 < NCG) {
+          tmem_ld_issue(trow + (cg + 1) * 32, nxt);
+          if (has_res) load_s32(p.res1, Rp, orow, (cg + 1) * 32, rnxt);
+        }
         {
           float bv[32];
           lds_f32x32(bias + cg * 32, bv);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(cur[j]) + bv[j];
-        }
-        if (has_res) {
-          float rr[32];
-          load_s32(p.res1, Rp, orow, cg * 32, rr);
+          for (int j = 0; j < 32; ++j) bv[j] += __uint_as_float(cur[j]);
+          if (has_res) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) x[j] += rr[j];
-        }
-        if (cg == 0) shift = x[0];
+            for (int j = 0; j < 32; ++j) bv[j] += rcur[j];
+          }
+          if (cg == 0) shift = bv[0];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) { const float d = x[j] - shift; s1 += d; s2 = fmaf(d, d, s2); }
+          for (int j = 0; j < 32; ++j) { const float d = bv[j] - shift; s1 += d; s2 = fmaf(d, d, s2); cur[j] = __float_as_uint(bv[j]); }
+        }
+        tc::tmem_st32(trow + cg * 32, cur);
       };
+      if (has_res) load_s32(p.res1, Rp, orow, 0, rra);
       tmem_ld_issue(trow, ra);
 #pragma unroll 1
-      for (int cg = 0; cg < NCG; cg += 2) { pass_a(cg, ra, rb); pass_a(cg + 1, rb, ra); }
+      for (int cg = 0; cg < NCG; cg += 2) { pass_a(cg, ra, rb, rra, rrb); pass_a(cg + 1, rb, ra, rrb, rra); }
+      tc::tmem_st_wait();
       const float dm = s1 * (1.f / 256.f);                      // mean - shift
       const float mean = shift + dm;
       const float var = fmaxf(s2 * (1.f / 256.f) - dm * dm, 0.f);
@@ -157,22 +163,10 @@ __device__ __forceinline__ void epilogue(const KArgs& p, const float* s_bias, co
         if (cg + 1 < NCG) tmem_ld_issue(trow + (cg + 1) * 32, nxt);
         float v[32];
         {
-          float bv[32];
-          lds_f32x32(bias + cg * 32, bv);
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(cur[j]) + bv[j];
-        }
-        if (has_res) {
-          float rr[32];
-          load_s32(p.res1, Rp, orow, cg * 32, rr);
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] += rr[j];
-        }
-        {
           float g[32];
           lds_f32x32(s_ln + cg * 32, g);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = (v[j] - mean) * rstd * g[j];
+          for (int j = 0; j < 32; ++j) v[j] = (__uint_as_float(cur[j]) - mean) * rstd * g[j];
         }
         {
           float be[32];

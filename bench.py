@@ -429,9 +429,12 @@ def bench_c3(ctx, prec, steps, warmup):
     gd = make_gd(ctx, "LJSpeech", "shallow", False, prec)
     lo, hi = shard.contiguous_shard(N_UTT, ctx.world, ctx.rank)
     n_local = hi - lo
-    # Sub-batches: at least 4 per rank so that the pipeline overlaps copies with compute even when a rank owns only 64
-    # utterances (8 GPUs); 64 utterances per batch otherwise.
-    BATCH = max(8, min(64, n_local // 4))
+    # Batches: the device-resident arm runs the rank's shard in batches of 64 utterances (218 tiles = 2.95 waves of the 74 CTA
+    # pairs; 16- or 32-utterance calls fill 0.74 of their last wave and pay the per-call preparation 2-4 times).  The
+    # end-to-end arm needs at least two batches per rank in flight to overlap its host copies with compute, so a rank that owns
+    # only 64 utterances (8 GPUs) splits them into two batches of 32.
+    BATCH = max(8, min(64, n_local))
+    BATCH_E2E = max(8, min(64, n_local // 2))
     # The conditioner crosses the host boundary in the precision the kernels consume it in (bf16 / fp16 operands): the
     # 16-bit -> fp32 -> 16-bit round trip on the device is exact, so results are bit-identical to passing fp32, and the
     # host link carries 512 instead of 1024 B per frame.
@@ -441,14 +444,18 @@ def bench_c3(ctx, prec, steps, warmup):
         inp = synth.make_inputs(500 + 7 * i + 100 * ctx.rank, 64, T, 1, shallow=True)
         protos.append((torch.from_numpy(inp["cond"]).to(cond_dt).pin_memory(), torch.from_numpy(inp["pad_mask"]).pin_memory(), None,
                        torch.from_numpy(inp["coarse_mel"]).pin_memory()))
-    batches = []
-    for k, b0 in enumerate(range(0, n_local, BATCH)):
-        n = min(BATCH, n_local - b0)
-        pr = protos[k % 3]
-        o = (k // 3 * BATCH) % (64 - n + 1)
-        batches.append(tuple(None if t is None else t[o:o + n] for t in pr))
+    def cut(batch):
+        out = []
+        for k, b0 in enumerate(range(0, n_local, batch)):
+            n = min(batch, n_local - b0)
+            pr = protos[k % 3]
+            o = (k // 3 * batch) % (64 - n + 1)
+            out.append(tuple(None if t is None else t[o:o + n] for t in pr))
+        return out
+
+    batches = cut(BATCH_E2E)
     pipe = BatchSynthesizer(gd, dev)
-    dev_batches = [tuple(None if t is None else t.to(dev) for t in b) for b in batches]
+    dev_batches = [tuple(None if t is None else t.to(dev) for t in b) for b in cut(BATCH)]
 
     def pass_e2e(_):
         acc = 0.0
@@ -466,9 +473,9 @@ def bench_c3(ctx, prec, steps, warmup):
     ms_e2e = ctx.timed(pass_e2e, steps, warmup)
     return {"value": N_UTT * T * steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps, "scaling": "strong",
             "workload": f"LJSpeech shallow K=1 batch synthesis, {N_UTT} utterances x T={T} sharded by utterance over {ctx.world} GPU(s) "
-                        f"in batches of {BATCH} (BASELINE configs[2]); value: inputs resident in HBM (shallow start + K=1 reverse "
+                        f"in batches of {BATCH} (end to end: {BATCH_E2E}) (BASELINE configs[2]); value: inputs resident in HBM (shallow start + K=1 reverse "
                         "diffusion + denorm per batch, noise drawn on the device)",
-            "precision": prec, "utterances_per_rank": n_local, "batch": BATCH,
+            "precision": prec, "utterances_per_rank": n_local, "batch": BATCH, "batch_e2e": BATCH_E2E,
             "e2e": {"value": N_UTT * T * steps / (ms_e2e * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": int(N_UTT * T * (256 * 2 + 80 * 4 + 1)), "d2h_bytes_per_step": int(N_UTT * T * 80 * 4),
                     "ms_per_step": ms_e2e / steps,

@@ -322,6 +322,10 @@ typedef struct mgb_hifigan_dims {
   int32_t n_res;                /* 3 resblocks per stage ("resblock": "1") */
   int32_t res_kernels[4];       /* 3, 7, 11 */
   int32_t res_dilations[4][3];  /* 1, 3, 5 each */
+  int32_t split_mode;           /* operand precision: 0 = fp16 operands everywhere (2^-11 per operand);
+                                   1 = fp16 hi + lo operand pairs (three MMAs per product, ~2^-21) in conv_pre, the
+                                       transposed convolutions and conv_post (< 5 % of the FLOPs, ~40 % of the error): default;
+                                   2 = hi + lo pairs in every layer: the parity mode (about 2.5x the time)                    */
 } mgb_hifigan_dims;
 size_t mgb_hifigan_flat_count(const mgb_hifigan_dims* dims);
 size_t mgb_hifigan_packed_bytes(const mgb_hifigan_dims* dims);

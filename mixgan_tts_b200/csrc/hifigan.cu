@@ -34,6 +34,7 @@ bool voc_dims_ok(const mgb_hifigan_dims* d, const char** why) {
   if (!d) return fail("NULL dims");
   if (d->n_mel <= 0 || d->n_mel % 8 || d->n_mel > 128) return fail("n_mel must be a multiple of 8 up to 128");
   if (d->n_up < 1 || d->n_up > MAX_UP || d->n_res < 1 || d->n_res > MAX_RES) return fail("1-8 upsampling stages, 1-4 resblocks");
+  if (d->split_mode < 0 || d->split_mode > 2) return fail("split_mode must be 0, 1 or 2");
   if (d->initial_channel % 64) return fail("initial channel count must be a multiple of 64");
   long long gap = GAP0;
   for (int i = 0; i < d->n_up; ++i) {
@@ -62,7 +63,11 @@ VocPlan make_plan(const mgb_hifigan_dims& d) {
     pb = align_up(pb, 16); l.b_off = pb / 4; pb += l.b_floats() * 4;
   };
   const int C0 = d.initial_channel;
-  pl.pre = plan_layer(d.n_mel, C0, 7, 1);
+  // split_mode 1: the layers whose inputs have the widest dynamic range (conv_pre on the log-mel, the transposed
+  // convolutions on the averaged resblock sums, conv_post) run with hi + lo operand pairs: < 5 % of the FLOPs, ~40 % of the
+  // fp16 operand-rounding error.  split_mode 2: every layer (parity mode, 3 MMAs per product).
+  const int sp_edge = d.split_mode >= 1 ? 1 : 0, sp_all = d.split_mode >= 2 ? 1 : 0;
+  pl.pre = plan_layer(d.n_mel, C0, 7, 1, 1, 0, sp_edge);
   pl.f_prew = takef((size_t)C0 * d.n_mel * 7); pl.f_preb = takef(C0);
   place(pl.pre);
   pl.total_up = 1;
@@ -71,7 +76,7 @@ VocPlan make_plan(const mgb_hifigan_dims& d) {
     StagePlan& S = pl.st[i];
     const int cin = C0 >> i, ch = C0 >> (i + 1), u = d.up_rates[i], k = d.up_kernels[i];
     S.ch = ch;
-    S.up = plan_layer(cin, ch, k, 1, u, (k - u) / 2);
+    S.up = plan_layer(cin, ch, k, 1, u, (k - u) / 2, sp_edge);
     S.f_upw = takef((size_t)cin * ch * k); S.f_upb = takef(ch);
     place(S.up);
     pl.total_up *= u;
@@ -82,12 +87,12 @@ VocPlan make_plan(const mgb_hifigan_dims& d) {
     for (int j = 0; j < d.n_res; ++j) {
       ResPlan& R = S.res[j];
       const int k = d.res_kernels[j];
-      for (int m = 0; m < 3; ++m) { R.c1[m] = plan_layer(S.ch, S.ch, k, d.res_dilations[j][m]); R.f_c1w[m] = takef((size_t)S.ch * S.ch * k); R.f_c1b[m] = takef(S.ch); place(R.c1[m]); }
-      for (int m = 0; m < 3; ++m) { R.c2[m] = plan_layer(S.ch, S.ch, k, 1); R.f_c2w[m] = takef((size_t)S.ch * S.ch * k); R.f_c2b[m] = takef(S.ch); place(R.c2[m]); }
+      for (int m = 0; m < 3; ++m) { R.c1[m] = plan_layer(S.ch, S.ch, k, d.res_dilations[j][m], 1, 0, sp_all); R.f_c1w[m] = takef((size_t)S.ch * S.ch * k); R.f_c1b[m] = takef(S.ch); place(R.c1[m]); }
+      for (int m = 0; m < 3; ++m) { R.c2[m] = plan_layer(S.ch, S.ch, k, 1, 1, 0, sp_all); R.f_c2w[m] = takef((size_t)S.ch * S.ch * k); R.f_c2b[m] = takef(S.ch); place(R.c2[m]); }
     }
   }
   const int chl = C0 >> d.n_up;
-  pl.post = plan_layer(chl, 1, 7, 1);
+  pl.post = plan_layer(chl, 1, 7, 1, 1, 0, sp_edge);
   pl.f_postw = takef((size_t)chl * 7); pl.f_postb = takef(1);
   place(pl.post);
   pl.flat_total = f;
@@ -95,7 +100,7 @@ VocPlan make_plan(const mgb_hifigan_dims& d) {
   return pl;
 }
 
-struct VocWs { size_t status, meli, prei, s32[4], h16[4], total; size_t E; };
+struct VocWs { size_t status, meli, prei, meli_lo, prei_lo, s32[4], h16[4], lo16[4], total; size_t E; };
 VocWs voc_ws(const mgb_hifigan_dims& d, const Rows& r0) {
   VocWs w{};
   size_t p = 0;
@@ -113,6 +118,12 @@ VocWs voc_ws(const mgb_hifigan_dims& d, const Rows& r0) {
   w.prei = take((size_t)r0.Rp * d.initial_channel * 2);
   for (int i = 0; i < 4; ++i) w.s32[i] = take(E * 4);
   for (int i = 0; i < 4; ++i) w.h16[i] = take(E * 2);
+  if (d.split_mode >= 1) {              // low-order companions of the images a split layer reads
+    w.meli_lo = take((size_t)r0.Rp * d.n_mel * 2);
+    w.prei_lo = take((size_t)r0.Rp * d.initial_channel * 2);
+    w.lo16[2] = take(E * 2);            // of I[0], the stage output
+    if (d.split_mode >= 2) { w.lo16[0] = take(E * 2); w.lo16[1] = take(E * 2); w.lo16[3] = take(E * 2); }
+  }
   w.total = p;
   return w;
 }
@@ -176,23 +187,33 @@ int mgb_hifigan_forward(const mgb_hifigan_dims* dims, const void* packed, const 
   __half* A0 = reinterpret_cast<__half*>(ws + w.h16[0]);
   __half* T1 = reinterpret_cast<__half*>(ws + w.h16[1]);
   __half* I[2] = {reinterpret_cast<__half*>(ws + w.h16[2]), reinterpret_cast<__half*>(ws + w.h16[3])};
+  const bool sp_edge = dims->split_mode >= 1, sp_all = dims->split_mode >= 2;
+  auto lo = [&](size_t off, bool on) { return on ? reinterpret_cast<__half*>(ws + off) : nullptr; };
+  __half* meli_lo = lo(w.meli_lo, sp_edge);
+  __half* prei_lo = lo(w.prei_lo, sp_edge);
+  __half* A0_lo = lo(w.lo16[0], sp_all);
+  __half* T1_lo = lo(w.lo16[1], sp_all);
+  __half* I_lo[2] = {lo(w.lo16[2], sp_edge), lo(w.lo16[3], sp_all)};
   constexpr float SLOPE = 0.1f;                   // LRELU_SLOPE, models.py:7
 
   MGB_CUDA_CHECK(cudaMemsetAsync(status, 0, 8192, s));
-  if (int rc = pack_rows(mel, nullptr, dims->n_mel, r, meli, 1.f, nullptr, s)) return rc;
+  if (int rc = pack_rows(mel, nullptr, dims->n_mel, r, meli, 1.f, nullptr, s, meli_lo)) return rc;
   {  // conv_pre, image of leaky_relu(x) for ups[0]   (models.py:152, 154)
     ConvIO io = conv_io(meli, dims->n_mel / 8);
-    io.img_out = prei; io.img_slope = SLOPE;
+    io.in_lo = meli_lo;
+    io.img_out = prei; io.img_slope = SLOPE; io.img_lo_out = prei_lo;
     if (int rc = run_conv(pl.pre, packed, r, io, status, s)) return rc;
   }
   const __half* prev = prei;
+  const __half* prev_lo = prei_lo;
   int prev_chunks = dims->initial_channel / 8;
   for (size_t si = 0; si < pl.st.size(); ++si) {
     const StagePlan& S = pl.st[si];
     const int chunks = S.ch / 8;
     {  // x = ups[i](leaky_relu(x))   (models.py:154-155): fp32 x + image of leaky_relu(x) for the resblocks
       ConvIO io = conv_io(prev, prev_chunks);
-      io.stream_out = X; io.img_out = A0; io.img_slope = SLOPE;
+      io.in_lo = prev_lo;
+      io.stream_out = X; io.img_out = A0; io.img_slope = SLOPE; io.img_lo_out = A0_lo;
       if (int rc = run_conv(S.up, packed, r, io, status, s)) return rc;
     }
     r = upsampled(r, S.up.up);
@@ -202,32 +223,36 @@ int mgb_hifigan_forward(const mgb_hifigan_dims* dims, const void* packed, const 
       const ResPlan& R = S.res[j];
       const float* cur_s = X;
       const __half* cur_i = A0;
+      const __half* cur_lo = A0_lo;
       for (int m = 0; m < 3; ++m) {
         {  // xt = leaky_relu(c1(leaky_relu(x)))   (models.py:98-100)
           ConvIO io = conv_io(cur_i, chunks);
-          io.img_out = T1; io.img_slope = SLOPE;
+          io.in_lo = cur_lo;
+          io.img_out = T1; io.img_slope = SLOPE; io.img_lo_out = T1_lo;
           if (int rc = run_conv(R.c1[m], packed, r, io, status, s)) return rc;
         }
         ConvIO io = conv_io(T1, chunks);   // x = c2(xt) + x   (models.py:101-102)
+        io.in_lo = T1_lo;
         io.res1 = cur_s;
         if (m < 2) {
-          io.stream_out = Y[m]; io.img_out = I[m]; io.img_slope = SLOPE;
-          cur_s = Y[m]; cur_i = I[m];
+          io.stream_out = Y[m]; io.img_out = I[m]; io.img_slope = SLOPE; io.img_lo_out = sp_all ? I_lo[m] : nullptr;
+          cur_s = Y[m]; cur_i = I[m]; cur_lo = sp_all ? I_lo[m] : nullptr;
         } else {
           // the resblock's output joins xs (models.py:157-161); after the last resblock x = xs / num_kernels and only the
           // image of leaky_relu(x) is needed: slope 0.1 in front of the next ups, 0.01 (F.leaky_relu default) in front of
           // conv_post (models.py:162-163)
           if (j > 0) io.res2 = XS;
           if (j + 1 < nres) io.stream_out = XS;
-          else { io.scale = 1.f / (float)nres; io.img_out = I[0]; io.img_slope = last_stage ? 0.01f : SLOPE; }
+          else { io.scale = 1.f / (float)nres; io.img_out = I[0]; io.img_slope = last_stage ? 0.01f : SLOPE; io.img_lo_out = I_lo[0]; }
         }
         if (int rc = run_conv(R.c2[m], packed, r, io, status, s)) return rc;
       }
     }
-    prev = I[0]; prev_chunks = chunks;
+    prev = I[0]; prev_lo = I_lo[0]; prev_chunks = chunks;
   }
   {  // tanh(conv_post(.))   (models.py:163-164) -> wav [B][T * hop]
     ConvIO io = conv_io(prev, prev_chunks);
+    io.in_lo = prev_lo;
     io.act = ACT_TANH; io.user_out = wav; io.user_ld = 1;
     if (int rc = run_conv(pl.post, packed, r, io, status, s)) return rc;
   }

@@ -38,6 +38,18 @@ __device__ __forceinline__ void store_img32(__half* img, size_t Rp, size_t row, 
   }
 }
 
+// low-order halves: lo = fp16(v - float(fp16(v)))
+__device__ __forceinline__ void store_img32_lo(__half* img, size_t Rp, size_t row, int ch0, const float (&v)[32]) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    float w[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) w[e] = v[q * 8 + e] - __half2float(__float2half_rn(v[q * 8 + e]));
+    uint4 u = make_uint4(pack_h2(w[0], w[1]), pack_h2(w[2], w[3]), pack_h2(w[4], w[5]), pack_h2(w[6], w[7]));
+    *reinterpret_cast<uint4*>(img + ((size_t)(ch0 / 8 + q) * Rp + row) * 8) = u;
+  }
+}
+
 struct KArgs {
   const __half* Wpk; const float* bias;
   int taps, dil, kspt;
@@ -48,6 +60,7 @@ struct KArgs {
   const float* res1; const float* res2;
   const float* ln_g; const float* ln_b;
   float* stream_out; __half* img_out; float img_slope;
+  __half* img_lo_out; int split;
   float* user_out; int user_ld;
   int up; long long Rp_out;
   int ntiles, ntn;             // work list: row tiles x column tiles
@@ -256,6 +269,7 @@ __device__ __forceinline__ void epilogue(const KArgs& p, const float* s_bias, co
         for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f) + slope * fminf(v[j], 0.f);
       }
       store_img32(p.img_out, Rp, orow, n0, v);
+      if (p.img_lo_out) store_img32_lo(p.img_lo_out, Rp, orow, n0, v);
     }
 #ifdef MGB_DEBUG_BUILD
     if (tr && cg < 2) tr[10 + cg * 3] = clock64();
@@ -301,7 +315,8 @@ template <int NT>
 struct Groups { static constexpr int NBUF = NT <= 128 ? 4 : 2; static constexpr int THREADS = 64 + NBUF * 128; };
 
 template <int NT, int KC>
-__global__ void __launch_bounds__(Groups<NT>::THREADS, 1) tcconv_kernel(const KArgs p, const __grid_constant__ CUtensorMap tmA) {
+__global__ void __launch_bounds__(Groups<NT>::THREADS, 1) tcconv_kernel(const KArgs p, const __grid_constant__ CUtensorMap tmA,
+                                                                         const __grid_constant__ CUtensorMap tmA2) {
   using S = Smem<NT, KC>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -332,7 +347,8 @@ __global__ void __launch_bounds__(Groups<NT>::THREADS, 1) tcconv_kernel(const KA
   if (p.ln_g) for (int k = tid; k < 256; k += blockDim.x) { s_ln[k] = p.ln_g[k]; s_ln[256 + k] = p.ln_b[k]; }
   __syncthreads();
 
-  const int nsteps = p.taps * p.kspt;                    // per work item; order: k-step outer, tap inner
+  const int nparts = p.split ? 2 : 1;                    // weight tiles per (k-step, tap): hi [, lo]
+  const int nsteps = p.taps * p.kspt * nparts;           // per work item; order: k-step outer, tap, part inner
   const int nwork = p.ntiles * p.ntn;
   const uint32_t w_base = tc::smem_u32(smem);
   const uint32_t a_base = w_base + S::W_REGION;
@@ -358,24 +374,27 @@ __global__ void __launch_bounds__(Groups<NT>::THREADS, 1) tcconv_kernel(const KA
       const int tile = w / p.ntn, ntile = w - tile * p.ntn;
       if (lane == 0) MGB_TC_STAMP(0);
       const __half* bsrc = p.Wpk + (size_t)ntile * nsteps * (size_t)(NT * KC);
-      for (int kc = 0; kc < p.kspt; ++kc, ++ia) {
-        const int st = ia % S::A_STAGES, ph = (ia / S::A_STAGES) & 1;
-        wait_backoff(tc::smem_u32(&a_empty[st]), ph ^ 1, p.status, 1);
-        if (tc::elect_one()) {
-          const uint32_t fb = tc::smem_u32(&a_full[st]);
-          tc::mbar_arrive_expect_tx_addr(fb, a_bytes);
-          // (128 + 2*halo8) rows x KC channels in ONE box, zero-filled outside the row axis
-          if (p.halo8 == 0) tc::tma_load_2d(a_base + st * S::A_STAGE, &tmA, 2 * tile * TILE, kc * (KC / 8), fb);
-          else tc::tma_load_3d(a_base + st * S::A_STAGE, &tmA, 0, (tile * TILE - p.halo8) >> 3, kc * (KC / 8), fb);
+      for (int kc = 0; kc < p.kspt; ++kc) {
+        for (int part = 0; part < nparts; ++part, ++ia) {       // the hi tile [and the lo tile] of this k-step
+          const int st = ia % S::A_STAGES, ph = (ia / S::A_STAGES) & 1;
+          wait_backoff(tc::smem_u32(&a_empty[st]), ph ^ 1, p.status, 1);
+          if (tc::elect_one()) {
+            const uint32_t fb = tc::smem_u32(&a_full[st]);
+            const void* tm = part ? &tmA2 : &tmA;
+            tc::mbar_arrive_expect_tx_addr(fb, a_bytes);
+            // (128 + 2*halo8) rows x KC channels in ONE box, zero-filled outside the row axis
+            if (p.halo8 == 0) tc::tma_load_2d(a_base + st * S::A_STAGE, tm, 2 * tile * TILE, kc * (KC / 8), fb);
+            else tc::tma_load_3d(a_base + st * S::A_STAGE, tm, 0, (tile * TILE - p.halo8) >> 3, kc * (KC / 8), fb);
+          }
         }
         if (!p.resident) {
-          for (int tap = 0; tap < p.taps; ++tap, ++iw) {
+          for (int t2 = 0; t2 < p.taps * nparts; ++t2, ++iw) {
             const int ws = iw % S::W_STAGES, wph = (iw / S::W_STAGES) & 1;
             wait_backoff(tc::smem_u32(&w_empty[ws]), wph ^ 1, p.status, 1);
             if (tc::elect_one()) {
               const uint32_t wb = tc::smem_u32(&w_full[ws]);
               tc::mbar_arrive_expect_tx_addr(wb, S::W_STAGE);
-              tc::bulk_g2s_addr(w_base + ws * S::W_STAGE, bsrc + (size_t)(kc * p.taps + tap) * (NT * KC), S::W_STAGE, wb);
+              tc::bulk_g2s_addr(w_base + ws * S::W_STAGE, bsrc + (size_t)(kc * p.taps * nparts + t2) * (NT * KC), S::W_STAGE, wb);
             }
           }
         }
@@ -397,32 +416,55 @@ __global__ void __launch_bounds__(Groups<NT>::THREADS, 1) tcconv_kernel(const KA
       tc::tc_fence_after();
       if (lane == 0) MGB_TC_STAMP(2);
       const uint32_t d_tmem = tmem + buf * NT;
-      for (int kc = 0; kc < p.kspt; ++kc, ++ia) {
+      for (int kc = 0; kc < p.kspt; ++kc) {
         const int st = ia % S::A_STAGES, ph = (ia / S::A_STAGES) & 1;
         tc::mbar_wait_trap(tc::smem_u32(&a_full[st]), ph, kTimeout, p.status, 2);
+        int st2 = st;
+        if (p.split) {
+          st2 = (ia + 1) % S::A_STAGES;
+          tc::mbar_wait_trap(tc::smem_u32(&a_full[st2]), ((ia + 1) / S::A_STAGES) & 1, kTimeout, p.status, 2);
+        }
+        ia += nparts;
         tc::tc_fence_after();
         const uint64_t a_st = a_desc0 + (uint64_t)((st * S::A_STAGE) >> 4);
+        const uint64_t a_st2 = a_desc0 + (uint64_t)((st2 * S::A_STAGE) >> 4);
         for (int tap = 0; tap < p.taps; ++tap) {
-          uint64_t b;
-          int ws = 0;
+          uint64_t b, b2 = 0;
+          int ws = 0, ws2 = 0;
           if (p.resident) {
-            b = b_desc0 + (uint64_t)((kc * p.taps + tap) * (S::W_STAGE >> 4));
+            b = b_desc0 + (uint64_t)(((kc * p.taps + tap) * nparts) * (S::W_STAGE >> 4));
+            b2 = b + (S::W_STAGE >> 4);
           } else {
             ws = iw % S::W_STAGES;
             tc::mbar_wait_trap(tc::smem_u32(&w_full[ws]), (iw / S::W_STAGES) & 1, kTimeout, p.status, 2);
-            tc::tc_fence_after();
             b = b_desc0 + (uint64_t)(ws * (S::W_STAGE >> 4));
             ++iw;
+            if (p.split) {
+              ws2 = iw % S::W_STAGES;
+              tc::mbar_wait_trap(tc::smem_u32(&w_full[ws2]), (iw / S::W_STAGES) & 1, kTimeout, p.status, 2);
+              b2 = b_desc0 + (uint64_t)(ws2 * (S::W_STAGE >> 4));
+              ++iw;
+            }
+            tc::tc_fence_after();
           }
-          const uint64_t a = a_st + (uint64_t)(row_shift + tap * p.dil);   // the tap: the same tile, tap*dil rows (16 B each) further
+          const uint32_t roff = row_shift + tap * p.dil;               // the tap: the same tile, tap*dil rows (16 B each) further
+          const uint64_t a = a_st + (uint64_t)roff, a2 = a_st2 + (uint64_t)roff;
           if (tc::elect_one()) {
 #pragma unroll
             for (int k = 0; k < KC / 16; ++k)
               tc::umma_bf16(d_tmem, a + (uint64_t)(k * a_kstep), b + (uint64_t)(k * b_kstep), idesc, (kc | tap | k) ? 1u : 0u);
-            if (!p.resident) tc::umma_commit(&w_empty[ws]);
+            if (p.split) {                                             // + a_hi w_lo + a_lo w_hi
+#pragma unroll
+              for (int k = 0; k < KC / 16; ++k)
+                tc::umma_bf16(d_tmem, a + (uint64_t)(k * a_kstep), b2 + (uint64_t)(k * b_kstep), idesc, 1u);
+#pragma unroll
+              for (int k = 0; k < KC / 16; ++k)
+                tc::umma_bf16(d_tmem, a2 + (uint64_t)(k * a_kstep), b + (uint64_t)(k * b_kstep), idesc, 1u);
+            }
+            if (!p.resident) { tc::umma_commit(&w_empty[ws]); if (p.split) tc::umma_commit(&w_empty[ws2]); }
           }
         }
-        if (tc::elect_one()) tc::umma_commit(&a_empty[st]);
+        if (tc::elect_one()) { tc::umma_commit(&a_empty[st]); if (p.split) tc::umma_commit(&a_empty[st2]); }
       }
       if (tc::elect_one()) tc::umma_commit(&acc_full[buf]);
       if (lane == 0) MGB_TC_STAMP(3);
@@ -455,7 +497,7 @@ __global__ void __launch_bounds__(Groups<NT>::THREADS, 1) tcconv_kernel(const KA
 }
 
 template <int NT, int KC>
-int launch_conv(KArgs a, const __half* in, int in_chunks, int Rp_in, int ntiles, int ntn, cudaStream_t s) {
+int launch_conv(KArgs a, const __half* in, const __half* in_lo, int in_chunks, int Rp_in, int ntiles, int ntn, cudaStream_t s) {
   using S = Smem<NT, KC>;
   static PerDeviceOnce once;
   static int sms[256];
@@ -467,36 +509,44 @@ int launch_conv(KArgs a, const __half* in, int in_chunks, int Rp_in, int ntiles,
     sms[dev & 255] = n;
     once.done();
   }
-  CUtensorMap m;
+  CUtensorMap m, m2;
   a.halo8 = ((a.taps >> 1) * a.dil + 7) / 8 * 8;
   a.rows = TILE + 2 * a.halo8;
   MGB_REQUIRE(a.rows <= ROWS_MAX, MGB_E_UNSUPPORTED, "convolution padding %d exceeds %d rows", (a.taps >> 1) * a.dil, (ROWS_MAX - TILE) / 2);
   if (a.halo8 == 0) { if (int rc = make_image_map(&m, in, in_chunks, Rp_in, KC / 8)) return rc; }
   else if (int rc = make_image_map3(&m, in, in_chunks, Rp_in, a.rows, KC / 8)) return rc;
+  m2 = m;
+  if (a.split) {
+    MGB_REQUIRE(in_lo != nullptr, MGB_E_ARG, "a split-precision layer needs the low-order image of its input");
+    if (a.halo8 == 0) { if (int rc = make_image_map(&m2, in_lo, in_chunks, Rp_in, KC / 8)) return rc; }
+    else if (int rc = make_image_map3(&m2, in_lo, in_chunks, Rp_in, a.rows, KC / 8)) return rc;
+  }
   a.ntiles = ntiles; a.ntn = ntn;
-  a.resident = (ntn == 1 && (long long)a.taps * a.kspt * S::W_STAGE <= S::W_REGION) ? 1 : 0;
+  a.resident = (ntn == 1 && (long long)a.taps * a.kspt * (a.split ? 2 : 1) * S::W_STAGE <= S::W_REGION) ? 1 : 0;
   const long long nwork = (long long)ntiles * ntn;
   const int nsm = sms[PerDeviceOnce::current()];
   const int grid = (int)(nwork < nsm ? nwork : nsm);
-  MGB_CUDA_CHECK(launch_pdl(tcconv_kernel<NT, KC>, dim3(grid), dim3(Groups<NT>::THREADS), S::TOTAL, s, 1, a, m));
+  MGB_CUDA_CHECK(launch_pdl(tcconv_kernel<NT, KC>, dim3(grid), dim3(Groups<NT>::THREADS), S::TOTAL, s, 1, a, m, m2));
   note_launch();
   return MGB_OK;
 }
 
 // ---- weight packing: torch [Cout][Cin][k] (conv / linear) or [Cin][Cout][k] (transposed conv) -> streamed fp16 tiles
-//      wp[ntile][step = kc*taps + tap][KC/8][NT][8] -------------------------------------------------------------------
+//      wp[ntile][step = kc*taps + tap][part: hi [, lo]][KC/8][NT][8] -------------------------------------------------------------------
 __global__ void pack_w_kernel(const float* __restrict__ w, const float* __restrict__ oscale, __half* __restrict__ wp,
-                              int Cin, int Cout, int k, int NT, int KC, int kspt, int taps, int up, int tpad, long long total) {
+                              int Cin, int Cout, int k, int NT, int KC, int kspt, int taps, int up, int tpad, int nparts,
+                              long long total) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   const int e = (int)(idx % 8);
   const int nl = (int)((idx / 8) % NT);
   const int c8 = (int)((idx / (8LL * NT)) % (KC / 8));
   const long long per_step = (long long)NT * KC;
-  const int nsteps = taps * kspt;
-  const int s = (int)((idx / per_step) % nsteps);
+  const int nsteps = taps * kspt * nparts;
+  const int s2 = (int)((idx / per_step) % nsteps);
   const int nt = (int)(idx / (per_step * nsteps));
-  const int kc = s / taps, tap = s - kc * taps;        // streamed order: k-step outer, tap inner
+  const int part = s2 % nparts, s = s2 / nparts;       // part 0 = fp16(w), part 1 = fp16(w - float(fp16(w)))
+  const int kc = s / taps, tap = s - kc * taps;        // streamed order: k-step outer, tap, part inner
   const int ci = kc * KC + c8 * 8 + e;
   float val = 0.f;
   if (up > 1) {
@@ -506,7 +556,8 @@ __global__ void pack_w_kernel(const float* __restrict__ w, const float* __restri
     const int co = nt * NT + nl;
     if (ci < Cin && co < Cout) val = w[((size_t)co * Cin + ci) * k + tap] * (oscale ? oscale[co] : 1.f);
   }
-  wp[idx] = __float2half_rn(val);
+  const __half hi = __float2half_rn(val);
+  wp[idx] = part ? __float2half_rn(val - __half2float(hi)) : hi;
 }
 __global__ void pack_b_kernel(const float* __restrict__ bias, const float* __restrict__ oscale, const float* __restrict__ oshift,
                               float* __restrict__ bp, int Cout, int NT, int ntn, int up) {
@@ -524,7 +575,8 @@ __global__ void pack_b_kernel(const float* __restrict__ bias, const float* __res
 // thread = (8-channel chunk, row), rows fastest: a warp writes 512 contiguous bytes of one image chunk and reads one
 // full 32-byte sector per thread
 __global__ void pack_rows_kernel(const float* __restrict__ user, const float* __restrict__ pos, int C, int B, int T, int Tg,
-                                 long long Rp, __half* __restrict__ img, float slope, float* __restrict__ stream) {
+                                 long long Rp, __half* __restrict__ img, float slope, float* __restrict__ stream,
+                                 __half* __restrict__ img_lo) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int nch = C / 8;
   if (idx >= Rp * nch) return;
@@ -552,16 +604,22 @@ __global__ void pack_rows_kernel(const float* __restrict__ user, const float* __
     for (int e = 0; e < 8; ++e) w[e] = v[e] > 0.f ? v[e] : v[e] * slope;
     *reinterpret_cast<uint4*>(img + ((size_t)ch * Rp + row) * 8) =
         make_uint4(pack_h2(w[0], w[1]), pack_h2(w[2], w[3]), pack_h2(w[4], w[5]), pack_h2(w[6], w[7]));
+    if (img_lo) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) w[e] -= __half2float(__float2half_rn(w[e]));
+      *reinterpret_cast<uint4*>(img_lo + ((size_t)ch * Rp + row) * 8) =
+          make_uint4(pack_h2(w[0], w[1]), pack_h2(w[2], w[3]), pack_h2(w[4], w[5]), pack_h2(w[6], w[7]));
+    }
   }
 }
 
 }  // namespace
 
 int pack_rows(const float* user, const float* pos, int C, const Rows& r, __half* img, float img_slope, float* stream,
-              cudaStream_t s) {
+              cudaStream_t s, __half* img_lo) {
   MGB_REQUIRE(C % 8 == 0, MGB_E_UNSUPPORTED, "pack_rows: channels must be a multiple of 8");
   const long long total = (long long)r.Rp * (C / 8);
-  pack_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(user, pos, C, r.B, r.T, r.Tg, r.Rp, img, img_slope, stream);
+  pack_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(user, pos, C, r.B, r.T, r.Tg, r.Rp, img, img_slope, stream, img_lo);
   note_launch();
   MGB_LAUNCH_CHECK();
   return MGB_OK;
@@ -569,12 +627,13 @@ int pack_rows(const float* user, const float* pos, int C, const Rows& r, __half*
 
 int pack_conv(const Layer& l, void* packed, const float* w, const float* bias, const float* oscale, const float* oshift,
               int ntile0, int Cout_part, cudaStream_t s) {
-  const int nsteps = l.taps * l.kspt;
+  const int nparts = l.split ? 2 : 1;
+  const int nsteps = l.taps * l.kspt * nparts;
   const int ntn = l.up > 1 ? l.ntn : (Cout_part + l.NT - 1) / l.NT;
   const long long total = (long long)ntn * nsteps * l.NT * l.KC;
   __half* wp = static_cast<__half*>(packed) + l.w_off + (size_t)ntile0 * nsteps * l.NT * l.KC;
   pack_w_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(w, oscale, wp, l.Cin, Cout_part, l.k, l.NT, l.KC, l.kspt,
-                                                                 l.taps, l.up, l.tpad, total);
+                                                                 l.taps, l.up, l.tpad, nparts, total);
   float* bp = reinterpret_cast<float*>(packed) + l.b_off + (size_t)ntile0 * l.NT;
   pack_b_kernel<<<(ntn * l.NT + 255) / 256, 256, 0, s>>>(bias, oscale, oshift, bp, Cout_part, l.NT, ntn, l.up);
   note_launch(2);
@@ -593,6 +652,7 @@ int run_conv(const Layer& l, const void* packed, const Rows& rin, const ConvIO& 
   a.act = io.act; a.scale = io.scale;
   a.res1 = io.res1; a.res2 = io.res2; a.ln_g = io.ln_g; a.ln_b = io.ln_b;
   a.stream_out = io.stream_out; a.img_out = io.img_out; a.img_slope = io.img_slope;
+  a.img_lo_out = io.img_lo_out; a.split = l.split;
   a.user_out = io.user_out; a.user_ld = io.user_ld;
   a.up = l.up; a.Rp_out = (long long)rin.Rp * l.up;
   a.status = status;
@@ -611,7 +671,7 @@ int run_conv(const Layer& l, const void* packed, const Rows& rin, const ConvIO& 
   MGB_REQUIRE(io.in_chunks * 8 >= l.Cin, MGB_E_ARG, "input image narrower than the layer's input channels");
   MGB_REQUIRE(l.ntn * l.NT <= MAX_BIAS, MGB_E_UNSUPPORTED, "layer wider than %d output columns", MAX_BIAS);
 #define MGB_TC_CASE(NT_, KC_)                                                                       \
-  if (l.NT == NT_ && l.KC == KC_) return launch_conv<NT_, KC_>(a, io.in, io.in_chunks, rin.Rp, rin.ntiles, l.ntn, s);
+  if (l.NT == NT_ && l.KC == KC_) return launch_conv<NT_, KC_>(a, io.in, io.in_lo, io.in_chunks, rin.Rp, rin.ntiles, l.ntn, s);
   MGB_TC_CASE(256, 64) MGB_TC_CASE(256, 32) MGB_TC_CASE(128, 64) MGB_TC_CASE(128, 32)
   MGB_TC_CASE(64, 64) MGB_TC_CASE(64, 32) MGB_TC_CASE(32, 64) MGB_TC_CASE(32, 32)
 #undef MGB_TC_CASE

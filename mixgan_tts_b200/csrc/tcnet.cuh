@@ -51,13 +51,15 @@ struct Layer {
   int Cin, Cout, k, dil;       // Cout = channels of the OUTPUT tensor (per phase for a transposed convolution)
   int up, tpad;                // transposed convolution: stride and padding (up == 1: ordinary convolution)
   int NT, KC, taps, kspt, ntn; // column tile, channels per k-step, GEMM taps, k-steps per tap, column tiles
+  int split;                   // 1 = split precision: operands as fp16 hi + lo pairs, three MMAs per product
+                               //     (a_hi w_hi + a_hi w_lo + a_lo w_hi: ~2^-21 relative instead of 2^-11)
   size_t w_off, b_off;         // offsets into the packed buffer: fp16 tiles (in halves), fp32 bias (in floats)
-  size_t w_halves() const { return (size_t)ntn * taps * kspt * NT * KC; }
+  size_t w_halves() const { return (size_t)ntn * taps * kspt * NT * KC * (split ? 2 : 1); }
   size_t b_floats() const { return (size_t)ntn * NT; }
 };
-inline Layer plan_layer(int Cin, int Cout, int k, int dil, int up = 1, int tpad = 0) {
+inline Layer plan_layer(int Cin, int Cout, int k, int dil, int up = 1, int tpad = 0, int split = 0) {
   Layer l{};
-  l.Cin = Cin; l.Cout = Cout; l.k = k; l.dil = dil; l.up = up; l.tpad = tpad;
+  l.Cin = Cin; l.Cout = Cout; l.k = k; l.dil = dil; l.up = up; l.tpad = tpad; l.split = split;
   if (up > 1) { l.NT = Cout; l.ntn = up; l.taps = 3; l.dil = 1; }
   else {
     l.NT = Cout > 128 ? 256 : Cout > 64 ? 128 : Cout > 32 ? 64 : 32;
@@ -71,6 +73,8 @@ inline Layer plan_layer(int Cin, int Cout, int k, int dil, int up = 1, int tpad 
 
 struct ConvIO {                      // per-launch operands of run_conv
   const __half* in; int in_chunks;   // input image and its channel chunks (Cin rounded up to 8)
+  const __half* in_lo;               // split layers: the low-order image of the input (same geometry)
+  __half* img_lo_out;                // low-order companion of img_out (for a split consumer), or NULL
   int act; float scale;
   const float* res1; const float* res2;        // fp32 streams (output row space) added after the activation
   const float* ln_g; const float* ln_b;        // LayerNorm over the row (NT == Cout == 256 only)
@@ -88,7 +92,7 @@ inline ConvIO conv_io(const __half* in, int in_chunks) {
 // user [B][T][C] fp32 (+ pos [T][C]) -> fp16 image (leaky_relu slope applied; 1 = identity) and/or fp32 stream, every
 // one of the Rp rows written (zeros outside the utterances).  C % 8 == 0.
 int pack_rows(const float* user, const float* pos, int C, const Rows& r, __half* img, float img_slope, float* stream,
-              cudaStream_t s);
+              cudaStream_t s, __half* img_lo = nullptr);
 int run_conv(const Layer& l, const void* packed, const Rows& rin, const ConvIO& io, int* status, cudaStream_t s);
 int pack_conv(const Layer& l, void* packed, const float* w, const float* bias, const float* oscale, const float* oshift,
               int ntile0, int Cout_part, cudaStream_t s);

@@ -19,7 +19,10 @@ from make_golden_aux import AUX_CASES, VOC_CASES  # noqa: E402
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-3          # aux decoder (measured 3e-4)
-TOL_VOC = 2e-3      # HiFi-GAN, ~75 fp16-operand convolutions deep (measured 8.5e-4; fp16 rounding of operands only)
+# HiFi-GAN, ~75 convolutions deep, by operand precision of the tcgen05 GEMMs (measured over the cases of this file):
+TOL_VOC = {"mixed": 1e-3,     # default: fp16 operands, hi + lo pairs in conv_pre / transposed convs / conv_post: 2.5e-4 .. 6.5e-4
+           "fp16": 2e-3,      # fp16 operands everywhere: 4.6e-4 .. 1.2e-3 (an fp16-rounding emulation of the oracle gives the same)
+           "fp16x3": 1e-4}    # hi + lo pairs everywhere, the parity mode: 1.0e-5 .. 1.7e-5
 
 
 def build_aux(dataset, wseed):
@@ -89,8 +92,8 @@ def test_aux_decoder_shard_equivalence_and_errors():
         m(x, pad)
 
 
-def build_voc(wseed):
-    gen = Generator(synth.HIFIGAN_CFG)
+def build_voc(wseed, precision="mixed"):
+    gen = Generator(synth.HIFIGAN_CFG, precision=precision)
     W = synth.make_hifigan_weights(wseed)
     gen.load_state_dict({k: torch.from_numpy(v) for k, v in W.items()}, strict=True)
     return gen.cuda().eval(), W
@@ -104,28 +107,30 @@ def voc_status(gen, B, T):
     return st.value
 
 
+@pytest.mark.parametrize("precision", ["mixed", "fp16", "fp16x3"])
 @pytest.mark.parametrize("name", list(VOC_CASES))
-def test_hifigan_vs_reference_golden(name):
+def test_hifigan_vs_reference_golden(name, precision):
     B, T, wseed, iseed = VOC_CASES[name]
     g = load_golden(name)
-    gen, W = build_voc(wseed)
+    gen, W = build_voc(wseed, precision)
     mel = torch.from_numpy(synth.make_mel(iseed, B, T)).cuda()
     wav = gen(mel.transpose(1, 2))                     # the reference's [B, n_mel, T] signature
     assert voc_status(gen, B, T) == 0
     assert tuple(wav.shape) == (B, 1, T * 256)
-    assert rel_l2(wav.squeeze(1), g["wav"]) < TOL_VOC
+    assert rel_l2(wav.squeeze(1), g["wav"]) < TOL_VOC[precision]
     assert torch.equal(gen.forward_frames(mel), wav.squeeze(1))
 
 
+@pytest.mark.parametrize("precision", ["mixed", "fp16x3"])
 @pytest.mark.parametrize("B,T", [(1, 1), (3, 7), (2, 64), (1, 130)])
-def test_hifigan_edge_shapes_vs_oracle(B, T):
-    gen, W = build_voc(70 + T % 5)
+def test_hifigan_edge_shapes_vs_oracle(B, T, precision):
+    gen, W = build_voc(70 + T % 5, precision)
     Wt = {k: torch.from_numpy(v) for k, v in W.items()}
     mel = torch.from_numpy(synth.make_mel(80 + T, B, T))
     want = oh.generator_forward(Wt, mel.transpose(1, 2), synth.HIFIGAN_CFG).squeeze(1)
     got = gen.forward_frames(mel.cuda())
     assert voc_status(gen, B, T) == 0
-    assert rel_l2(got, want) < TOL_VOC, (B, T)
+    assert rel_l2(got, want) < TOL_VOC[precision], (B, T)
 
 
 def test_hifigan_shard_equivalence():

@@ -698,15 +698,34 @@ def bench_train(ctx, prec, steps, warmup, B):
         torch._foreach_copy_([p.grad for p in d_params],
                              [c.view_as(p) for c, p in zip(flat.split([p.numel() for p in d_params]), d_params)])
 
+    # The two discriminator calls of a phase (fake and real pairs, train.py:137-138 / :159-160) share x_ts, t and the weights:
+    # they run as ONE call on the 2B-utterance batch [fake | real] and the feature lists are split afterwards — the same
+    # losses and gradients (utterances are independent in every layer), half the launches and twice the CTAs per launch.
+    # In the D phase every output of the generator forward is detached (train.py:133-135), so that forward keeps no
+    # activation stash: it runs with autograd off, i.e. through the fused inference kernel.
+    UNBATCHED = bool(os.environ.get("MIXGAN_B200_BENCH_GAN_UNBATCHED"))
+
+    def d_pair(x_ts, x_fake_prev, x_real_prev, t):
+        if UNBATCHED:
+            fc, fu = D(x_ts, x_fake_prev, None, t)
+            rc, ru = D(x_ts, x_real_prev, None, t)
+            return fc, fu, rc, ru
+        n = x_ts.shape[0]
+        c, u = D(torch.cat([x_ts, x_ts]), torch.cat([x_fake_prev, x_real_prev]), None, torch.cat([t, t]))
+        return [f[:n] for f in c], [f[:n] for f in u], [f[n:] for f in c], [f[n:] for f in u]
+
     def gan_step(i, with_sync=True, s=None):
         s = s if s is not None else sets[i % NSETS]
         valid = (~s["pad"]).unsqueeze(-1)
-        # D phase (train.py:126-146): the generator forward runs in grad mode there, as here
+        # D phase (train.py:126-146)
         gd.denoise_fn.grad_sync = None
-        out = gd(s["mel"], s["cond"].detach().requires_grad_(True), None, s["pad"])
+        if UNBATCHED:
+            out = gd(s["mel"], s["cond"].detach().requires_grad_(True), None, s["pad"])
+        else:
+            with torch.no_grad():
+                out = gd(s["mel"], s["cond"], None, s["pad"])
         x_ts, x_prev, x_pred, t = [o.detach() for o in out[1:5]]
-        fc, fu = D(x_ts, x_pred, None, t)
-        rc, ru = D(x_ts, x_prev, None, t)
+        fc, fu, rc, ru = d_pair(x_ts, x_pred, x_prev, t)
         r_loss, f_loss = d_loss_fn(rc[-1], ru[-1], fc[-1], fu[-1])
         (r_loss + f_loss).backward()
         if ctx.world > 1 and with_sync:
@@ -717,8 +736,7 @@ def bench_train(ctx, prec, steps, warmup, B):
         # G phase (train.py:148-184)
         gd.denoise_fn.grad_sync = sync if with_sync else None
         out = gd(s["mel"], s["cond"].detach().requires_grad_(True), None, s["pad"])
-        fc, fu = D(out[1], out[3], None, out[4])
-        rc, ru = D(out[1], out[2], None, out[4])
+        fc, fu, rc, ru = d_pair(out[1], out[3], out[2], out[4])
         adv = g_loss_fn(fc[-1], fu[-1])
         mel_loss = torch.nn.functional.l1_loss(gd.denorm_spec(out[0]) * valid, s["mel"] * valid)   # model/loss.py:175-176,229-234
         fm = LAMBDA_FM * feature_matching_loss(rc, ru, fc, fu, n_fm)

@@ -18,7 +18,8 @@
 namespace mgb {
 namespace {
 
-constexpr int TM = 64, TN = 64, TK = 16, NTHR = 256;
+constexpr int TM = 128, TN = 64, TK = 16, NTHR = 256;      // CTA tile; every thread owns an 8 x 4 block of it
+constexpr int LDA = TM + 4, LDB = TN + 4;
 
 enum { ACT_NONE = 0, ACT_LEAKY = 1, ACT_MISH = 2, ACT_RELU = 3 };
 
@@ -44,17 +45,41 @@ __global__ void pack_w_kernel(const float* __restrict__ w, float* __restrict__ w
   if (wq) wq[((size_t)j * Cout + co) * Cin + ci] = v;
 }
 
+// One 16-deep step of the register-tiled product: thread (tx = tid & 15, ty = tid >> 4) owns rows {4 ty .. 4 ty + 3} and
+// {64 + 4 ty ..} x columns {4 tx .. 4 tx + 3} of the 128 x 64 CTA tile: 3 shared-memory float4 loads per 32 FFMA, 8 warps
+// per CTA.  (History, ncu on the 128 -> 512 k = 5 stride-2 data gradient: 4 x 4 blocks — 2 loads per 16 FFMA — were bound
+// by shared-memory bandwidth; 8 x 8 blocks with 4 warps per CTA left one warp per scheduler, which stalled 2.8 cycles per
+// issued instruction on shared-memory and FFMA latencies.)
+__device__ __forceinline__ void tile_fma(const float (*__restrict__ As)[LDA], const float (*__restrict__ Bs)[LDB], int tx, int ty,
+                                         float (&acc)[8][4]) {
+#pragma unroll
+  for (int q = 0; q < TK; ++q) {
+    const float4 a0 = *reinterpret_cast<const float4*>(&As[q][ty * 4]);
+    const float4 a1 = *reinterpret_cast<const float4*>(&As[q][64 + ty * 4]);
+    const float4 b0 = *reinterpret_cast<const float4*>(&Bs[q][tx * 4]);
+    const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+    const float b[4] = {b0.x, b0.y, b0.z, b0.w};
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+  }
+}
+
 // ---- forward (DGRAD = false) and data gradient (DGRAD = true): out[M][N] = A[M][K] * Bm[K][N] ----------------------
 //   forward: M = B*Tout rows, K = k*Cin, N = Cout, A(m, j*Cin + ci) = xin[b][to*s + j - pad][ci], Bm = wp
 //   dgrad  : M = B*Tin  rows, K = k*Cout, N = Cin, A(m, j*Cout + co) = dz[b][(ti + pad - j)/s][co], Bm = wq
-// The operand tiles of k-step i + 1 are fetched into registers while k-step i is multiplied out of shared memory: with
-// 50-200 CTAs on 148 SMs these GEMMs are latency-bound, and an un-prefetched loop paid one full global-memory latency
-// (~1 us) per 16-deep k-step (measured 227 us for the 512 -> 128, k = 5 layer; same accumulation order, same bits).
+// Double-buffered shared-memory tiles: the operands of k-step i + 1 travel from global memory into registers while
+// k-step i is multiplied.  gridDim.z > 1 = split K: CTA z accumulates k-steps [z * steps_per_split, ...) and writes raw
+// partial sums to `part[z][M][N]`; splitk_epilogue_kernel adds them in a fixed order and applies bias / activation (the
+// discriminator's deep layers are 25-100 tiles of K = 2560: without the split two thirds of the SMs idle).
 template <bool DGRAD>
-__global__ void __launch_bounds__(NTHR) conv_gemm_f32_kernel(const float* __restrict__ A, const float* __restrict__ Bm,
+__global__ void __launch_bounds__(NTHR, 2) conv_gemm_f32_kernel(const float* __restrict__ A, const float* __restrict__ Bm,
                                                              const float* __restrict__ bias, const float* __restrict__ rowbias,
-                                                             float* __restrict__ out, float* __restrict__ pre, ConvShape s, int act) {
-  __shared__ float As[TK][TM + 4], Bs[TK][TN + 4];
+                                                             float* __restrict__ out, float* __restrict__ pre,
+                                                             float* __restrict__ part, ConvShape s, int act, int steps_per_split) {
+  __shared__ __align__(16) float As[2][TK][LDA];
+  __shared__ __align__(16) float Bs[2][TK][LDB];
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const int m0 = blockIdx.x * TM, n0 = blockIdx.y * TN;
   const int rows_per_b = DGRAD ? s.Tin : s.Tout;       // rows of `out` per utterance
@@ -62,109 +87,141 @@ __global__ void __launch_bounds__(NTHR) conv_gemm_f32_kernel(const float* __rest
   const int Ca = DGRAD ? s.Cout : s.Cin;               // channels of A
   const int N = DGRAD ? s.Cin : s.Cout;
   const int M = s.B * rows_per_b, K = s.k * Ca;
-  // A-tile loader: thread -> (row a_r, 4 consecutive k)
-  const int a_r = tid >> 2, a_k4 = (tid & 3) * 4;
-  const int a_m = m0 + a_r;
-  const int a_b = a_m < M ? a_m / rows_per_b : 0, a_t = a_m - a_b * rows_per_b;
-  // B-tile loader: thread -> (k row b_k, 4 consecutive n)
-  const int b_k = tid >> 4, b_n4 = (tid & 15) * 4;
+  const int nks_all = (K + TK - 1) / TK;
+  const int ks0 = blockIdx.z * steps_per_split;
+  const int nks = min(steps_per_split, nks_all - ks0);
   const bool vecA = (Ca & 3) == 0, vecB = (N & 3) == 0;
-  float acc[4][4];
+  // A loader: thread -> rows a_r + 64 i (i < 2), 4 consecutive k at a_k4; B loader: k row b_k, 4 n at b_n4
+  const int a_r = tid >> 2, a_k4 = (tid & 3) * 4;
+  const int b_k = tid >> 4, b_n4 = (tid & 15) * 4;
+  int a_b[2], a_t[2];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int i = 0; i < 2; ++i) {
+    const int m = m0 + a_r + 64 * i;
+    a_b[i] = m < M ? m / rows_per_b : -1;
+    a_t[i] = m < M ? m - a_b[i] * rows_per_b : 0;
+  }
+  // (tap j, channel c) of this thread's first k of the current step, advanced by TK per step
+  int kj = (ks0 * TK + a_k4) / Ca, kc = (ks0 * TK + a_k4) - kj * Ca;
 
-  auto src_row = [&](int j, int& src) -> bool {
-    if (DGRAD) { const int q = a_t + s.pad - j; src = q / s.stride; return q >= 0 && q % s.stride == 0 && q / s.stride < s.Tout; }
-    src = a_t * s.stride + j - s.pad;
+  auto src_row = [&](int t, int j, int& src) -> bool {
+    if (DGRAD) { const int q = t + s.pad - j; src = q / s.stride; return q >= 0 && q % s.stride == 0 && src < s.Tout; }
+    src = t * s.stride + j - s.pad;
     return src >= 0 && src < s.Tin;
   };
-  auto load_a = [&](int k0, float (&v)[4]) {
-    v[0] = v[1] = v[2] = v[3] = 0.f;
-    const int kk = k0 + a_k4;
-    if (a_m >= M || kk >= K) return;
-    if (vecA) {
-      const int j = kk / Ca, c = kk - j * Ca;
-      int src;
-      if (src_row(j, src)) {
-        const float4 x4 = *reinterpret_cast<const float4*>(A + ((size_t)a_b * src_per_b + src) * Ca + c);
-        v[0] = x4.x; v[1] = x4.y; v[2] = x4.z; v[3] = x4.w;
-        if (!DGRAD && rowbias) {
-          const float4 r4 = *reinterpret_cast<const float4*>(rowbias + (size_t)a_b * Ca + c);
-          v[0] += r4.x; v[1] += r4.y; v[2] += r4.z; v[3] += r4.w;
+  float4 pa[2], pb;
+  auto load_g = [&](int ks) {
+    const int kk = ks * TK + a_k4;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (a_b[i] >= 0 && kk < K) {
+        if (vecA) {
+          int src;
+          if (src_row(a_t[i], kj, src)) {
+            v = *reinterpret_cast<const float4*>(A + ((size_t)a_b[i] * src_per_b + src) * Ca + kc);
+            if (!DGRAD && rowbias) {
+              const float4 r4 = *reinterpret_cast<const float4*>(rowbias + (size_t)a_b[i] * Ca + kc);
+              v.x += r4.x; v.y += r4.y; v.z += r4.z; v.w += r4.w;
+            }
+          }
+        } else {
+          float e4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int ke = kk + e;
+            if (ke >= K) break;
+            const int j = ke / Ca, c = ke - j * Ca;
+            int src;
+            if (src_row(a_t[i], j, src))
+              e4[e] = A[((size_t)a_b[i] * src_per_b + src) * Ca + c] + ((!DGRAD && rowbias) ? rowbias[(size_t)a_b[i] * Ca + c] : 0.f);
+          }
+          v = make_float4(e4[0], e4[1], e4[2], e4[3]);
         }
       }
-    } else {
+      pa[i] = v;
+    }
+    {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      const int kr = ks * TK + b_k, n = n0 + b_n4;
+      if (kr < K) {
+        if (vecB && n + 3 < N) v = *reinterpret_cast<const float4*>(Bm + (size_t)kr * N + n);
+        else {
+          float e4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int ke = kk + e;
-        if (ke >= K) break;
-        const int j = ke / Ca, c = ke - j * Ca;
-        int src;
-        if (src_row(j, src)) v[e] = A[((size_t)a_b * src_per_b + src) * Ca + c] + ((!DGRAD && rowbias) ? rowbias[(size_t)a_b * Ca + c] : 0.f);
+          for (int e = 0; e < 4; ++e) if (n + e < N) e4[e] = Bm[(size_t)kr * N + n + e];
+          v = make_float4(e4[0], e4[1], e4[2], e4[3]);
+        }
       }
+      pb = v;
     }
+    kc += TK;
+    while (kc >= Ca) { kc -= Ca; ++kj; }
   };
-  auto load_b = [&](int k0, float (&v)[4]) {
-    v[0] = v[1] = v[2] = v[3] = 0.f;
-    const int kk = k0 + b_k, n = n0 + b_n4;
-    if (kk >= K) return;
-    if (vecB && n + 3 < N) {
-      const float4 w4 = *reinterpret_cast<const float4*>(Bm + (size_t)kk * N + n);
-      v[0] = w4.x; v[1] = w4.y; v[2] = w4.z; v[3] = w4.w;
-    } else {
+  auto store_s = [&](int buf) {
 #pragma unroll
-      for (int e = 0; e < 4; ++e) if (n + e < N) v[e] = Bm[(size_t)kk * N + n + e];
+    for (int i = 0; i < 2; ++i) {
+      As[buf][a_k4 + 0][a_r + 64 * i] = pa[i].x; As[buf][a_k4 + 1][a_r + 64 * i] = pa[i].y;
+      As[buf][a_k4 + 2][a_r + 64 * i] = pa[i].z; As[buf][a_k4 + 3][a_r + 64 * i] = pa[i].w;
     }
+    *reinterpret_cast<float4*>(&Bs[buf][b_k][b_n4]) = pb;
   };
 
-  // PF k-steps of operand tiles are in flight in registers (static indices: the k loop is unrolled by PF)
-  constexpr int PF = 4;
-  float pa[PF][4], pb[PF][4];
+  float acc[8][4];
 #pragma unroll
-  for (int u = 0; u < PF; ++u) { load_a(u * TK, pa[u]); load_b(u * TK, pb[u]); }
-  for (int kb = 0; kb < K; kb += PF * TK) {
+  for (int i = 0; i < 8; ++i)
 #pragma unroll
-    for (int u = 0; u < PF; ++u) {
-      const int k0 = kb + u * TK;
-      if (k0 >= K) break;                                             // uniform over the block
-#pragma unroll
-      for (int e = 0; e < 4; ++e) As[a_k4 + e][a_r] = pa[u][e];
-      *reinterpret_cast<float4*>(&Bs[b_k][b_n4]) = make_float4(pb[u][0], pb[u][1], pb[u][2], pb[u][3]);
-      __syncthreads();
-      load_a(k0 + PF * TK, pa[u]);                                    // zero beyond K; in flight during the next PF multiplies
-      load_b(k0 + PF * TK, pb[u]);
-#pragma unroll
-      for (int kq = 0; kq < TK; ++kq) {
-        const float4 a4 = *reinterpret_cast<const float4*>(&As[kq][ty * 4]);
-        const float4 b4 = *reinterpret_cast<const float4*>(&Bs[kq][tx * 4]);
-        const float a[4] = {a4.x, a4.y, a4.z, a4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
-      }
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  if (nks > 0) {
+    load_g(ks0);
+    store_s(0);
+    __syncthreads();
+    for (int it = 0; it < nks; ++it) {
+      const int buf = it & 1;
+      if (it + 1 < nks) load_g(ks0 + it + 1);
+      tile_fma(As[buf], Bs[buf], tx, ty, acc);
+      if (it + 1 < nks) store_s(buf ^ 1);
       __syncthreads();
     }
   }
+  const bool split = gridDim.z > 1;
+  float* dst = split ? part + (size_t)blockIdx.z * M * N : out;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int m = m0 + ty * 4 + i;
+  for (int i = 0; i < 8; ++i) {
+    const int m = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
     if (m >= M) continue;
+    {
+      const int n = n0 + tx * 4;
+      float v[4] = {acc[i][0], acc[i][1], acc[i][2], acc[i][3]};
+      if (!split && !DGRAD) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int n = n0 + tx * 4 + j;
-      if (n >= N) continue;
-      float v = acc[i][j];
-      if (!DGRAD) {
-        if (bias) v += bias[n];
-        if (pre) pre[(size_t)m * N + n] = v;
-        v = act_fwd(v, act);
+        for (int e = 0; e < 4; ++e) if (bias && n + e < N) v[e] += bias[n + e];
+        if (pre) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) if (n + e < N) pre[(size_t)m * N + n + e] = v[e];
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) v[e] = act_fwd(v[e], act);
       }
-      out[(size_t)m * N + n] = v;
+      if (vecB && n + 3 < N) *reinterpret_cast<float4*>(dst + (size_t)m * N + n) = make_float4(v[0], v[1], v[2], v[3]);
+      else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) if (n + e < N) dst[(size_t)m * N + n + e] = v[e];
+      }
     }
   }
+}
+
+// out = act(bias + sum_z part[z]) in a fixed order (the epilogue of a split-K conv_gemm_f32_kernel)
+__global__ void splitk_epilogue_kernel(const float* __restrict__ part, const float* __restrict__ bias, float* __restrict__ out,
+                                       float* __restrict__ pre, size_t MN, int N, int nsplit, int act) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= MN) return;
+  float v = 0.f;
+  for (int z = 0; z < nsplit; ++z) v += part[(size_t)z * MN + i];
+  if (bias) v += bias[i % N];
+  if (pre) pre[i] = v;
+  out[i] = act_fwd(v, act);
 }
 
 // ---- dz = dy * act'(.)  (leaky / relu from the sign of y, mish from the stored pre-activation) ----
@@ -186,96 +243,105 @@ __global__ void act_bwd_kernel(const float* __restrict__ dy, const float* __rest
 }
 
 // ---- weight gradient partials: part[split][K][Cout] = sum over the split's rows of xin(row, kk) * dz(row, co) ----
-__global__ void __launch_bounds__(NTHR) conv_wgrad_f32_kernel(const float* __restrict__ x, const float* __restrict__ rowbias,
+// The same 128 x 64 register-tiled product with the frame axis as the reduction: As[q][kk] = xin(row q, kk) and
+// Bs[q][co] = dz(row q, co) are both contiguous along their tile axis, so the tiles are stored as they are loaded.
+__global__ void __launch_bounds__(NTHR, 2) conv_wgrad_f32_kernel(const float* __restrict__ x, const float* __restrict__ rowbias,
                                                               const float* __restrict__ dz, float* __restrict__ part, ConvShape s,
                                                               int rows_per_split) {
-  __shared__ float As[TK][TM + 4], Bs[TK][TN + 4];     // As[m][kk], Bs[m][co]
+  __shared__ __align__(16) float As[2][TK][LDA];
+  __shared__ __align__(16) float Bs[2][TK][LDB];
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const int k0 = blockIdx.x * TM, n0 = blockIdx.y * TN, split = blockIdx.z;
   const int K = s.k * s.Cin, M = s.B * s.Tout;
   const int mb = split * rows_per_split, me = min(M, mb + rows_per_split);
-  const int l_m = tid >> 4, l_c4 = (tid & 15) * 4;    // loader: (row within the 16-row chunk, 4 consecutive columns)
   const bool vecA = (s.Cin & 3) == 0, vecB = (s.Cout & 3) == 0;
-  float acc[4][4];
+  // A loader: rows a_q + 8 i (i < 2), 4 consecutive kk at a_k4 (fixed for the whole kernel, so is its tap / channel)
+  const int a_q = tid >> 5, a_k4 = (tid & 31) * 4;
+  const int b_q = tid >> 4, b_n4 = (tid & 15) * 4;
+  const int kk = k0 + a_k4;
+  const int kj = kk / s.Cin, kc = kk - kj * s.Cin;
+  float4 pa[2], pb;
+  auto load_g = [&](int mq) {
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  auto load_ab = [&](int m0, float (&va)[4], float (&vb)[4]) {
-    va[0] = va[1] = va[2] = va[3] = 0.f;
-    vb[0] = vb[1] = vb[2] = vb[3] = 0.f;
-    const int m = m0 + l_m;
-    if (m >= me) return;
-    const int b = m / s.Tout, to = m - b * s.Tout;
-    const int kk = k0 + l_c4;
-    if (vecA) {                  // K = k * Cin is a multiple of 4 and a float4 never straddles two taps
-      if (kk < K) {
-        const int j = kk / s.Cin, c = kk - j * s.Cin;
-        const int ti = to * s.stride + j - s.pad;
-        if (ti >= 0 && ti < s.Tin) {
-          const float4 x4 = *reinterpret_cast<const float4*>(x + ((size_t)b * s.Tin + ti) * s.Cin + c);
-          va[0] = x4.x; va[1] = x4.y; va[2] = x4.z; va[3] = x4.w;
-          if (rowbias) {
-            const float4 r4 = *reinterpret_cast<const float4*>(rowbias + (size_t)b * s.Cin + c);
-            va[0] += r4.x; va[1] += r4.y; va[2] += r4.z; va[3] += r4.w;
+    for (int i = 0; i < 2; ++i) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      const int m = mq + a_q + 8 * i;
+      if (m < me && kk < K) {
+        const int b = m / s.Tout, to = m - b * s.Tout;
+        if (vecA) {
+          const int ti = to * s.stride + kj - s.pad;
+          if (ti >= 0 && ti < s.Tin) {
+            v = *reinterpret_cast<const float4*>(x + ((size_t)b * s.Tin + ti) * s.Cin + kc);
+            if (rowbias) {
+              const float4 r4 = *reinterpret_cast<const float4*>(rowbias + (size_t)b * s.Cin + kc);
+              v.x += r4.x; v.y += r4.y; v.z += r4.z; v.w += r4.w;
+            }
           }
-        }
-      }
-    } else {
+        } else {
+          float e4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int ke = kk + e;
-        if (ke < K) {
-          const int j = ke / s.Cin, c = ke - j * s.Cin;
-          const int ti = to * s.stride + j - s.pad;
-          if (ti >= 0 && ti < s.Tin)
-            va[e] = x[((size_t)b * s.Tin + ti) * s.Cin + c] + (rowbias ? rowbias[(size_t)b * s.Cin + c] : 0.f);
+          for (int e = 0; e < 4; ++e) {
+            const int ke = kk + e;
+            if (ke >= K) break;
+            const int j = ke / s.Cin, c = ke - j * s.Cin;
+            const int ti = to * s.stride + j - s.pad;
+            if (ti >= 0 && ti < s.Tin) e4[e] = x[((size_t)b * s.Tin + ti) * s.Cin + c] + (rowbias ? rowbias[(size_t)b * s.Cin + c] : 0.f);
+          }
+          v = make_float4(e4[0], e4[1], e4[2], e4[3]);
         }
       }
+      pa[i] = v;
     }
-    const int n = n0 + l_c4;
-    if (vecB && n + 3 < s.Cout) {
-      const float4 d4 = *reinterpret_cast<const float4*>(dz + (size_t)m * s.Cout + n);
-      vb[0] = d4.x; vb[1] = d4.y; vb[2] = d4.z; vb[3] = d4.w;
-    } else {
+    {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      const int m = mq + b_q, n = n0 + b_n4;
+      if (m < me) {
+        if (vecB && n + 3 < s.Cout) v = *reinterpret_cast<const float4*>(dz + (size_t)m * s.Cout + n);
+        else {
+          float e4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int e = 0; e < 4; ++e) if (n + e < s.Cout) vb[e] = dz[(size_t)m * s.Cout + n + e];
+          for (int e = 0; e < 4; ++e) if (n + e < s.Cout) e4[e] = dz[(size_t)m * s.Cout + n + e];
+          v = make_float4(e4[0], e4[1], e4[2], e4[3]);
+        }
+      }
+      pb = v;
     }
   };
-  constexpr int PF = 4;                                  // row chunks in flight in registers
-  float va[PF][4], vb[PF][4];
+  auto store_s = [&](int buf) {
 #pragma unroll
-  for (int u = 0; u < PF; ++u) load_ab(mb + u * TK, va[u], vb[u]);
-  for (int mq = mb; mq < me; mq += PF * TK) {
+    for (int i = 0; i < 2; ++i) *reinterpret_cast<float4*>(&As[buf][a_q + 8 * i][a_k4]) = pa[i];
+    *reinterpret_cast<float4*>(&Bs[buf][b_q][b_n4]) = pb;
+  };
+  float acc[8][4];
 #pragma unroll
-    for (int u = 0; u < PF; ++u) {
-      const int m0 = mq + u * TK;
-      if (m0 >= me) break;                               // uniform over the block
-      *reinterpret_cast<float4*>(&As[l_m][l_c4]) = make_float4(va[u][0], va[u][1], va[u][2], va[u][3]);
-      *reinterpret_cast<float4*>(&Bs[l_m][l_c4]) = make_float4(vb[u][0], vb[u][1], vb[u][2], vb[u][3]);
-      __syncthreads();
-      load_ab(m0 + PF * TK, va[u], vb[u]);               // zero beyond the split
+  for (int i = 0; i < 8; ++i)
 #pragma unroll
-      for (int q = 0; q < TK; ++q) {
-        const float4 a4 = *reinterpret_cast<const float4*>(&As[q][ty * 4]);
-        const float4 b4 = *reinterpret_cast<const float4*>(&Bs[q][tx * 4]);
-        const float a[4] = {a4.x, a4.y, a4.z, a4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
-      }
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  const int nch = (me - mb + TK - 1) / TK;
+  if (nch > 0) {
+    load_g(mb);
+    store_s(0);
+    __syncthreads();
+    for (int it = 0; it < nch; ++it) {
+      const int buf = it & 1;
+      if (it + 1 < nch) load_g(mb + (it + 1) * TK);
+      tile_fma(As[buf], Bs[buf], tx, ty, acc);
+      if (it + 1 < nch) store_s(buf ^ 1);
       __syncthreads();
     }
   }
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int kk = k0 + ty * 4 + i;
-    if (kk >= K) continue;
+  for (int i = 0; i < 8; ++i) {
+    const int kr = k0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+    if (kr >= K) continue;
+    {
+      const int n = n0 + tx * 4;
+      float* d = part + ((size_t)split * K + kr) * s.Cout + n;
+      if (vecB && n + 3 < s.Cout) *reinterpret_cast<float4*>(d) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+      else {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int n = n0 + tx * 4 + j;
-      if (n < s.Cout) part[((size_t)split * K + kk) * s.Cout + n] = acc[i][j];
+        for (int e = 0; e < 4; ++e) if (n + e < s.Cout) d[e] = acc[i][e];
+      }
     }
   }
 }
@@ -362,12 +428,20 @@ ConvShape make_shape(int B, int Tin, int Cin, int Cout, int k, int stride) {
 int wgrad_splits(const ConvShape& s) {
   const int M = s.B * s.Tout;
   const int tiles = ((s.k * s.Cin + TM - 1) / TM) * ((s.Cout + TN - 1) / TN);
-  int want = (296 + tiles - 1) / tiles;                  // about two CTAs per SM in total
+  int want = 296 / tiles;                                // at most two CTAs per SM in total: one wave
   const int max_by_rows = (M + 127) / 128;               // at least 128 rows per split
   if (want > max_by_rows) want = max_by_rows;
   return want < 1 ? 1 : (want > 64 ? 64 : want);
 }
-struct Work { size_t wp, wq, dz, part, cs, total; };
+// split K of the forward / data-gradient GEMM: up to two CTAs per SM in total, at least 8 k-steps (128 deep) per split
+int gemm_splits(int M, int N, int K) {
+  const int tiles = ((M + TM - 1) / TM) * ((N + TN - 1) / TN), nks = (K + TK - 1) / TK;
+  int want = 296 / tiles;                                // never more CTAs than fit at once (2 per SM): a 300-CTA grid
+                                                         // ran 4 of them alone, after the rest, for twice the time
+  if (want > nks / 8) want = nks / 8;
+  return want < 1 ? 1 : (want > 16 ? 16 : want);
+}
+struct Work { size_t wp, wq, dz, part, cs, gpart, total; };
 Work work_layout(const ConvShape& s) {
   Work w{};
   size_t p = 0;
@@ -377,8 +451,29 @@ Work work_layout(const ConvShape& s) {
   w.dz = take((size_t)s.B * s.Tout * s.Cout);
   w.part = take((size_t)wgrad_splits(s) * wn);
   w.cs = take((size_t)CS_MAX_SPLITS * (size_t)((size_t)s.B * s.Cin > (size_t)s.Cout ? (size_t)s.B * s.Cin : (size_t)s.Cout));
+  const int sf = gemm_splits(s.B * s.Tout, s.Cout, s.k * s.Cin), sd = gemm_splits(s.B * s.Tin, s.Cin, s.k * s.Cout);
+  const size_t gf = sf > 1 ? (size_t)sf * s.B * s.Tout * s.Cout : 0, gd = sd > 1 ? (size_t)sd * s.B * s.Tin * s.Cin : 0;
+  w.gpart = take(gf > gd ? gf : gd);
   w.total = p;
   return w;
+}
+
+// forward (DGRAD = false) or data gradient; returns the number of launches
+template <bool DGRAD>
+int launch_conv_gemm(const float* A, const float* Bm, const float* bias, const float* rowbias, float* out, float* pre, float* gpart,
+                     const ConvShape& s, int act, cudaStream_t st) {
+  const int M = DGRAD ? s.B * s.Tin : s.B * s.Tout, N = DGRAD ? s.Cin : s.Cout, K = s.k * (DGRAD ? s.Cout : s.Cin);
+  const int nks = (K + TK - 1) / TK;
+  int splits = gemm_splits(M, N, K);
+  const int sps = (nks + splits - 1) / splits;
+  splits = (nks + sps - 1) / sps;                              // no empty split
+  dim3 grid((M + TM - 1) / TM, (N + TN - 1) / TN, splits);
+  conv_gemm_f32_kernel<DGRAD><<<grid, NTHR, 0, st>>>(A, Bm, bias, rowbias, out, pre, gpart, s, act, sps);
+  if (splits == 1) return 1;
+  const size_t MN = (size_t)M * N;
+  splitk_epilogue_kernel<<<(unsigned)((MN + 255) / 256), 256, 0, st>>>(gpart, DGRAD ? nullptr : bias, out, DGRAD ? nullptr : pre, MN, N,
+                                                                        splits, DGRAD ? ACT_NONE : act);
+  return 2;
 }
 
 }  // namespace
@@ -411,9 +506,7 @@ int mgb_conv1d_forward(const float* x, const float* w, const float* bias, const 
   float* wp = reinterpret_cast<float*>(W + wl.wp);
   const int wn = Cout * Cin * k;
   pack_w_kernel<<<(wn + 255) / 256, 256, 0, st>>>(w, wp, nullptr, Cin, Cout, k);
-  dim3 grid((B * s.Tout + TM - 1) / TM, (Cout + TN - 1) / TN);
-  conv_gemm_f32_kernel<false><<<grid, NTHR, 0, st>>>(x, wp, bias, rowbias, y, pre, s, act);
-  note_launch(2);
+  note_launch(1 + launch_conv_gemm<false>(x, wp, bias, rowbias, y, pre, reinterpret_cast<float*>(W + wl.gpart), s, act, st));
   MGB_LAUNCH_CHECK();
   return MGB_OK;
 }
@@ -449,9 +542,7 @@ int mgb_conv1d_backward(const float* x, const float* w, const float* rowbias, co
   const int wn = Cout * Cin * k;
   if (grad_x) {
     pack_w_kernel<<<(wn + 255) / 256, 256, 0, st>>>(w, wp, wq, Cin, Cout, k);
-    dim3 grid((B * Tin + TM - 1) / TM, (Cin + TN - 1) / TN);
-    conv_gemm_f32_kernel<true><<<grid, NTHR, 0, st>>>(dz, wq, nullptr, nullptr, grad_x, nullptr, s, ACT_NONE);
-    launches += 2;
+    launches += 1 + launch_conv_gemm<true>(dz, wq, nullptr, nullptr, grad_x, nullptr, reinterpret_cast<float*>(W + wl.gpart), s, ACT_NONE, st);
     if (grad_rowbias) {
       // d rowbias[b][ci] = sum over the rows of utterance b of grad_x: exact, because every existing input row carries
       // the bias once and grad_x is the gradient with respect to (x + rowbias)

@@ -97,6 +97,9 @@ def test_edge_lengths_vs_oracle(B, T):
 @pytest.mark.parametrize("B,T,Cin,Cout,k,stride,act", [
     (2, 17, 8, 12, 3, 1, 0), (1, 40, 160, 64, 3, 1, 1), (3, 33, 64, 128, 5, 2, 1), (2, 9, 6, 1, 3, 1, 1),
     (1, 64, 128, 512, 5, 2, 1), (2, 31, 12, 20, 7, 3, 3), (4, 1, 256, 1024, 1, 1, 2), (2, 50, 512, 128, 5, 1, 1),
+    # split-K forward / data-gradient plans (few output tiles, deep K) and a many-tile plan, at the training step's shapes
+    (16, 200, 512, 128, 5, 1, 1), (4, 401, 128, 512, 5, 2, 1), (16, 1, 1024, 512, 1, 1, 0), (8, 200, 128, 1, 3, 1, 0),
+    (6, 333, 160, 64, 3, 1, 1),
 ])
 def test_generic_conv1d_forward_and_backward_vs_torch(B, T, Cin, Cout, k, stride, act):
     """The library Conv1d against F.conv1d + autograd (fp32, channels-first), incl. the fused row bias."""

@@ -178,6 +178,28 @@ int mgb_denorm_mask(const float* x, const float* spec_min, const float* spec_max
                     const uint8_t* pad_mask, float* mel, int B, int T, int n_mel, void* stream);
 
 /*
+ * The elementwise steps of GaussianDiffusion.forward's training branch around the Denoiser call (model/diffusion.py:201-225),
+ * fused (the torch composition is ~56 launches per call).  All states are fp32 [B][n_mel][T]; `t` int64 [B] in [0, K).
+ *
+ * mgb_train_diffuse             :206-207  x_t = diffuse_fn(mel, t) * valid and x_t_prev = diffuse_fn(mel, t - 1) * valid, with
+ *                               diffuse_fn = norm_spec + transpose + q_sample and x_start itself where t - 1 < 0 (:177-185);
+ *                               mel [B][T][n_mel]; sqrt_acp / sqrt_1m_acp = the two q_sample tables, float [K]
+ * mgb_train_posterior           :210-212, :220 of the 'naive' model: x0_pred = clamp(denoiser_out * valid) (clamp if `clip`),
+ *                               x_t_prev_pred = (coef1[t] x0_pred + coef2[t] x_t + sigma[t] noise) * valid; `sched` as in
+ *                               mgb_reverse_step (float [3][K]: coef1 | coef2 | sigma)
+ * mgb_train_posterior_backward  d/d denoiser_out of both outputs (either incoming gradient may be NULL = zero)
+ */
+int mgb_train_diffuse(const float* mel, const float* noise_t, const float* noise_prev, const float* spec_min,
+                      const float* spec_max, const float* sqrt_acp, const float* sqrt_1m_acp, const int64_t* t,
+                      const uint8_t* pad_mask, float* x_t, float* x_t_prev, int B, int T, int n_mel, int K, void* stream);
+int mgb_train_posterior(const float* denoiser_out, const float* x_t, const float* noise, const float* sched, const int64_t* t,
+                        const uint8_t* pad_mask, int clip, float* x0_pred, float* x_t_prev_pred, int B, int T, int n_mel,
+                        int K, void* stream);
+int mgb_train_posterior_backward(const float* grad_x0_pred, const float* grad_x_t_prev_pred, const float* denoiser_out,
+                                 const float* sched, const int64_t* t, const uint8_t* pad_mask, int clip,
+                                 float* grad_denoiser_out, int B, int T, int n_mel, int K, void* stream);
+
+/*
  * Duration indexing of the front end (all integer results are bit-exact).
  *
  * mgb_durations_from_log   the word-level duration rounding of LinguisticEncoder.forward at inference

@@ -53,6 +53,9 @@ SIGNATURES = {
     "mgb_pack_cond": (_I, [_D, _I, _P, _I, _I, _P, _Z, _P]),
     "mgb_shallow_start": (_I, [_P, _P, _P, _P, _F, _F, _P, _P, _I, _I, _I, _P]),
     "mgb_denorm_mask": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P]),
+    "mgb_train_diffuse": (_I, [_P] * 11 + [_I] * 4 + [_P]),
+    "mgb_train_posterior": (_I, [_P] * 6 + [_I] + [_P, _P] + [_I] * 4 + [_P]),
+    "mgb_train_posterior_backward": (_I, [_P] * 6 + [_I] + [_P] + [_I] * 4 + [_P]),
     "mgb_conv1d_out_len": (_I, [_I, _I, _I]),
     "mgb_conv1d_workspace_bytes": (_Z, [_I] * 6),
     "mgb_conv1d_forward": (_I, [_P] * 6 + [_I] * 7 + [_P, _Z, _P]),

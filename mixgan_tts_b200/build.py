@@ -19,7 +19,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmixgan_b200.so")
 LIB_DBG = os.path.join(HERE, "libmixgan_b200_dbg.so")
-SOURCES = ["abi.cu", "fp32_path.cu", "train_fp32.cu", "train_bf16.cu", "fused_bf16.cu", "conv1d_f32.cu", "tcnet.cu", "auxdec.cu", "hifigan.cu"]
+SOURCES = ["abi.cu", "fp32_path.cu", "train_fp32.cu", "train_bf16.cu", "fused_bf16.cu", "conv1d_f32.cu", "train_branch.cu", "tcnet.cu", "auxdec.cu", "hifigan.cu"]
 DBG_ONLY_SOURCES = ["umma_probe.cu"]
 HEADERS = ["common.cuh", "tc05.cuh", "small_ops.cuh", "gemm_fp32.cuh", "train_small.cuh", "tmap.cuh", "tcnet.cuh",
            os.path.join("..", "..", "include", "mixgan_b200.h"), os.path.join("..", "..", "include", "mixgan_b200_probe.h")]

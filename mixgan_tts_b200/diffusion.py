@@ -32,6 +32,42 @@ def _extract(a, t, x_shape):
     return a.gather(-1, t).reshape(b, *((1,) * (len(x_shape) - 1)))
 
 
+class _PosteriorFn(torch.autograd.Function):
+    """``x_0_pred = clamp(denoiser_out * valid)``, ``x_t_prev_pred = q_posterior_sample(x_0_pred, x_t, t) * valid`` of the
+    'naive' training branch (diffusion.py:210-212, :220) as one library kernel, and one more for d/d denoiser_out."""
+
+    @staticmethod
+    def forward(ctx, den_out, x_t, noise, sched, t, pad, clip, K):
+        lib = _lib.load()
+        den = den_out.detach().float().contiguous()
+        B, _, M, T = den.shape
+        x0, prev = torch.empty_like(den), torch.empty_like(den)
+        st = C.c_void_p(torch.cuda.current_stream(den.device).cuda_stream)
+        with torch.cuda.device(den.device):
+            _lib.check(lib.mgb_train_posterior(_lib.ptr(den), _lib.ptr(x_t), _lib.ptr(noise), _lib.ptr(sched), _lib.ptr(t),
+                                               _lib.ptr(pad), int(clip), _lib.ptr(x0), _lib.ptr(prev), B, T, M, K, st),
+                       "mgb_train_posterior")
+        ctx.save_for_backward(den, sched, t, pad)
+        ctx.cfg = (int(clip), K)
+        return x0, prev
+
+    @staticmethod
+    def backward(ctx, g_x0, g_prev):
+        den, sched, t, pad = ctx.saved_tensors
+        clip, K = ctx.cfg
+        lib = _lib.load()
+        B, _, M, T = den.shape
+        g0 = None if g_x0 is None else g_x0.float().contiguous()
+        g1 = None if g_prev is None else g_prev.float().contiguous()
+        g = torch.empty_like(den)
+        st = C.c_void_p(torch.cuda.current_stream(den.device).cuda_stream)
+        with torch.cuda.device(den.device):
+            _lib.check(lib.mgb_train_posterior_backward(_lib.ptr(g0), _lib.ptr(g1), _lib.ptr(den), _lib.ptr(sched), _lib.ptr(t),
+                                                        _lib.ptr(pad), clip, _lib.ptr(g), B, T, M, K, st),
+                       "mgb_train_posterior_backward")
+        return g, None, None, None, None, None, None, None
+
+
 class GaussianDiffusion(nn.Module):
     def __init__(self, args, preprocess_config, model_config, train_config, precision: str | None = None):
         super().__init__()
@@ -127,6 +163,16 @@ class GaussianDiffusion(nn.Module):
                     self.sqrt_one_minus_alphas_cumprod.detach().float().cpu().tolist())
             self._sched_cache = (key, torch.stack([c1, c2, sig]).contiguous().to(device), host)
         return self._sched_cache[1]
+
+    def _train_tables(self, device):
+        """(sqrt_alphas_cumprod, sqrt_one_minus_alphas_cumprod) as contiguous fp32 device tensors (the q_sample tables)."""
+        key = (device, self.sqrt_alphas_cumprod._version, self.sqrt_alphas_cumprod.data_ptr())
+        c = getattr(self, "_train_tab_cache", None)
+        if c is None or c[0] != key:
+            c = (key, self.sqrt_alphas_cumprod.detach().float().contiguous().to(device),
+                 self.sqrt_one_minus_alphas_cumprod.detach().float().contiguous().to(device))
+            self._train_tab_cache = c
+        return c[1], c[2]
 
     def _call_ctx(self, ref):
         if ref.device.type != "cuda":
@@ -271,17 +317,53 @@ class GaussianDiffusion(nn.Module):
     def _forward_training(self, mel, cond, spk_emb, mel_mask, coarse_mel, clip_denoised, t, noise_t, noise_prev,
                           post_noise):
         """diffusion.py:201-225.  The Denoiser call runs in the library (per-utterance timesteps; with autograd
-        enabled its backward runs there too, see ``modules._DenoiserGradFn``), the light elementwise steps around it
-        are torch on the registered buffers, so torch autograd chains through them as in the reference."""
+        enabled its backward runs there too, see ``modules._DenoiserGradFn``).  The elementwise steps around it are two
+        library kernels (``mgb_train_diffuse`` before, ``mgb_train_posterior`` + its backward after: ``_PosteriorFn``)
+        when ``mel`` and the noises carry no gradient; otherwise — and for the 'shallow' model's posterior, which starts
+        from the coarse mel — the torch composition on the registered buffers, through which torch autograd chains."""
         b, device = cond.shape[0], cond.device
         with torch.cuda.device(device):
-            valid = (~mel_mask)[:, None, None, :]                                   # :190, :202
+            t_given = t is not None
             if t is None:
                 t = torch.randint(0, self.num_timesteps, (b,), device=device)       # :203
             t = t.long()
-            x_t = self.diffuse_fn(mel, t.clone(), noise=noise_t) * valid             # :206
-            x_t_prev = self.diffuse_fn(mel, t - 1, noise=noise_prev) * valid         # :207
-            x_0_pred = self.denoise_fn(x_t, t, cond.transpose(1, 2), spk_emb) * valid   # :210
+            tr = lambda x: x[:, 0].transpose(1, 2)
+            fused = (mel.dtype == torch.float32 and not mel.requires_grad and mel_mask is not None
+                     and all(n is None or not n.requires_grad for n in (noise_t, noise_prev, post_noise)))
+            if fused:
+                # :206-207 in one library kernel (norm_spec, transpose, both q_samples, the t - 1 < 0 rule, the mask); the
+                # draws happen in the reference's order and shapes, so the random stream is the reference's
+                lib = _lib.load()
+                K, M, T = self.num_timesteps, self.mel_bins, mel.shape[1]
+                # a caller-supplied timestep outside [0, K) raises as the reference's gather does (one host read; skipped
+                # for the internal draw and under graph capture, where the kernels clamp the table index instead)
+                if t_given and not torch.cuda.is_current_stream_capturing() and not bool(((t >= 0) & (t < K)).all()):
+                    raise IndexError(f"forward: timestep outside [0, {K})")
+                shape = (b, 1, M, T)
+                noise_t = torch.randn(shape, device=device) if noise_t is None else self._f32c(noise_t)
+                noise_prev = torch.randn(shape, device=device) if noise_prev is None else self._f32c(noise_prev)
+                pad = mel_mask.detach().to(torch.uint8).contiguous()
+                x_t, x_t_prev = torch.empty(shape, device=device), torch.empty(shape, device=device)
+                sched = self._sched(device)
+                sa, sn = self._train_tables(device)
+                st = C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+                _lib.check(lib.mgb_train_diffuse(
+                    _lib.ptr(self._f32c(mel)), _lib.ptr(noise_t), _lib.ptr(noise_prev),
+                    _lib.ptr(self.spec_min.detach().float().reshape(-1).contiguous()),
+                    _lib.ptr(self.spec_max.detach().float().reshape(-1).contiguous()), _lib.ptr(sa), _lib.ptr(sn), _lib.ptr(t),
+                    _lib.ptr(pad), _lib.ptr(x_t), _lib.ptr(x_t_prev), b, T, M, K, st), "mgb_train_diffuse")
+                den_out = self.denoise_fn(x_t, t, cond.transpose(1, 2), spk_emb)    # :210
+                if self.model != "shallow":
+                    post_noise = torch.randn(shape, device=device) if post_noise is None else self._f32c(post_noise)
+                    x_0_pred, x_t_prev_pred = _PosteriorFn.apply(den_out, x_t, post_noise, sched, t, pad, bool(clip_denoised), K)
+                    return tr(x_0_pred), tr(x_t), tr(x_t_prev), tr(x_t_prev_pred), t
+                valid = (~mel_mask)[:, None, None, :]
+                x_0_pred = den_out * valid
+            else:
+                valid = (~mel_mask)[:, None, None, :]                                   # :190, :202
+                x_t = self.diffuse_fn(mel, t.clone(), noise=noise_t) * valid             # :206
+                x_t_prev = self.diffuse_fn(mel, t - 1, noise=noise_prev) * valid         # :207
+                x_0_pred = self.denoise_fn(x_t, t, cond.transpose(1, 2), spk_emb) * valid   # :210
             if clip_denoised:
                 x_0_pred = x_0_pred.clamp(-1., 1.)                                  # :211-212
             if self.model != "shallow":
@@ -289,5 +371,4 @@ class GaussianDiffusion(nn.Module):
             else:
                 x_start = self.norm_spec(coarse_mel).transpose(1, 2)[:, None, :, :]  # :218-219
             x_t_prev_pred = self.q_posterior_sample(x_start=x_start, x_t=x_t, t=t, noise=post_noise) * valid   # :220
-            tr = lambda x: x[:, 0].transpose(1, 2)
         return tr(x_0_pred), tr(x_t), tr(x_t_prev), tr(x_t_prev_pred), t

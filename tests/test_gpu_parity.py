@@ -277,6 +277,46 @@ def test_training_branch_forward_values_vs_golden(name, precision):
         assert rel_l2(v, g[k]) < tol, k
 
 
+@pytest.mark.parametrize("B,T", [(3, 48), (2, 131), (1, 1)])
+def test_training_branch_fused_kernels_vs_torch_composition(B, T):
+    """mgb_train_diffuse / mgb_train_posterior(+backward) against the torch composition of diffusion.py:206-220 they replace:
+    the two diffused states bit for bit, the posterior outputs and d/d denoiser_out to fp32 rounding (the sigma table is
+    exponentiated on the host), with t = 0 rows (x_t_prev = x_start, no posterior noise), padding and clamped values."""
+    from mixgan_tts_b200.diffusion import _PosteriorFn
+    c, _ = train_case("train_naive_lj_B3_T48")
+    gd = build(c, "fp32")
+    K, M = gd.num_timesteps, gd.mel_bins
+    g = torch.Generator().manual_seed(B * 100 + T)
+    mel = (torch.randn(B, T, M, generator=g) * 2 - 5).cuda()
+    t = (torch.arange(B) % K).cuda()                       # includes t = 0
+    pad = (torch.arange(T)[None, :] >= torch.tensor([max(1, T - 3 * i) for i in range(B)])[:, None]).cuda()
+    nt, npv, pn = (torch.randn(B, 1, M, T, generator=g).cuda() for _ in range(3))
+    valid = (~pad)[:, None, None, :]
+    ref_xt = gd.diffuse_fn(mel, t.clone(), noise=nt) * valid
+    ref_prev = gd.diffuse_fn(mel, t - 1, noise=npv) * valid
+    lib = _lib.load()
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    x_t, x_prev = torch.empty_like(nt), torch.empty_like(nt)
+    sa, sn = gd._train_tables(mel.device)
+    _lib.check(lib.mgb_train_diffuse(_lib.ptr(mel), _lib.ptr(nt), _lib.ptr(npv), _lib.ptr(gd.spec_min.float().reshape(-1).contiguous()),
+                                     _lib.ptr(gd.spec_max.float().reshape(-1).contiguous()), _lib.ptr(sa), _lib.ptr(sn), _lib.ptr(t),
+                                     _lib.ptr(pad.to(torch.uint8)), _lib.ptr(x_t), _lib.ptr(x_prev), B, T, M, K, st), "train_diffuse")
+    assert torch.equal(x_t, ref_xt) and torch.equal(x_prev, ref_prev)
+    # posterior + clamp, forward and backward
+    den = (torch.randn(B, 1, M, T, generator=g) * 1.2).cuda()
+    d1, d2 = den.clone().requires_grad_(True), den.clone().requires_grad_(True)
+    x0_ref = (d1 * valid).clamp(-1., 1.)
+    prev_ref = gd.q_posterior_sample(x_start=x0_ref, x_t=ref_xt, t=t, noise=pn) * valid
+    x0, prev = _PosteriorFn.apply(d2, x_t, pn, gd._sched(mel.device), t, pad.to(torch.uint8), True, K)
+    assert torch.equal(x0, x0_ref)
+    assert torch.allclose(prev, prev_ref, rtol=1e-6, atol=1e-6)
+    r0, r1 = (torch.randn(B, 1, M, T, generator=g).cuda() for _ in range(2))
+    ((x0_ref * r0).sum() + (prev_ref * r1).sum()).backward()
+    ((x0 * r0).sum() + (prev * r1).sum()).backward()
+    assert torch.allclose(d2.grad, d1.grad, rtol=1e-6, atol=1e-6)
+    assert float(d1.grad.abs().sum()) > 0
+
+
 def test_shallow_start_and_denorm_elementwise_exact():
     c = golden_case("shallow_lj_B2_T130")
     lib = _lib.load()

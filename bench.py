@@ -377,44 +377,67 @@ def bench_elementwise(ctx, B=B_PER_GPU, T=T_FRAMES, reps=20):
     smin = gd.spec_min.detach().float().reshape(-1).contiguous()
     smax = gd.spec_max.detach().float().reshape(-1).contiguous()
     ws = den.workspace(B, T, 1, dev)
-    st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
     pk = peaks(0.0)["hbm_gbs"]
+    cur = lambda: C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    how = []
 
     def t_of(fn):
+        """ms per launch: `reps` launches replayed as ONE CUDA graph between two events (these kernels run ~10 us, about
+        what the host needs to enqueue one through ctypes: an eager loop times the host, not the kernel); eager loop as the
+        fallback."""
         for i in range(3):
-            fn(i)
+            fn(i, cur())
+        torch.cuda.synchronize()
+        run = None
+        try:
+            side = torch.cuda.Stream(dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                fn(0, cur())
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                for i in range(reps):
+                    fn(i, cur())
+            graph.replay()
+            run = graph.replay
+            how.append("graph")
+        except Exception:
+            torch.cuda.synchronize()
+            run = lambda: [fn(i, cur()) for i in range(reps)]
+            how.append("eager")
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for i in range(reps):
-            fn(i)
+        run()
         e1.record()
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) / reps
 
     out = {}
     frames = B * T
-    ms = t_of(lambda i: _lib.check(lib.mgb_shallow_start(_lib.ptr(coarse[i % NS]), _lib.ptr(noise[i % NS]), _lib.ptr(smin), _lib.ptr(smax),
-                                                         0.5, 0.5, _lib.ptr(pad), _lib.ptr(xT[i % NS]), B, T, M, st), "shallow_start"))
+    ms = t_of(lambda i, st: _lib.check(lib.mgb_shallow_start(_lib.ptr(coarse[i % NS]), _lib.ptr(noise[i % NS]), _lib.ptr(smin), _lib.ptr(smax),
+                                                             0.5, 0.5, _lib.ptr(pad), _lib.ptr(xT[i % NS]), B, T, M, st), "shallow_start"))
     by = frames * (3 * M * 4 + 1)
     out["shallow_start_kernel"] = {"bytes": by, "ms": ms, "gbs": by / ms / 1e6, "frac": by / ms / 1e6 / pk}
-    ms = t_of(lambda i: _lib.check(lib.mgb_denorm_mask(_lib.ptr(xT[i % NS]), _lib.ptr(smin), _lib.ptr(smax), _lib.ptr(pad),
-                                                       _lib.ptr(mel[i % NS]), B, T, M, st), "denorm_mask"))
+    ms = t_of(lambda i, st: _lib.check(lib.mgb_denorm_mask(_lib.ptr(xT[i % NS]), _lib.ptr(smin), _lib.ptr(smax), _lib.ptr(pad),
+                                                           _lib.ptr(mel[i % NS]), B, T, M, st), "denorm_mask"))
     by = frames * (2 * M * 4 + 1)
     out["denorm_mask_kernel"] = {"bytes": by, "ms": ms, "gbs": by / ms / 1e6, "frac": by / ms / 1e6 / pk}
-    ms = t_of(lambda i: _lib.check(lib.mgb_pack_cond(C.byref(den.dims), _lib.PREC_BF16, _lib.ptr(cond[i % NS]), B, T, _lib.ptr(ws),
-                                                     ws.numel(), st), "pack_cond"))
+    ms = t_of(lambda i, st: _lib.check(lib.mgb_pack_cond(C.byref(den.dims), _lib.PREC_BF16, _lib.ptr(cond[i % NS]), B, T, _lib.ptr(ws),
+                                                         ws.numel(), st), "pack_cond"))
     by = frames * (H * 4 + H * 2)
     out["cond_pack_kernel"] = {"bytes": by, "ms": ms, "gbs": by / ms / 1e6, "frac": by / ms / 1e6 / pk}
     # context: a plain device copy of the same size (these kernels run ~10 us; the 6551 GB/s peak is a 4 GB copy)
     src = [torch.empty(frames * M, device=dev) for _ in range(NS)]
     dst = [torch.empty(frames * M, device=dev) for _ in range(NS)]
-    ms = t_of(lambda i: dst[i % NS].copy_(src[i % NS]))
+    ms = t_of(lambda i, st: dst[i % NS].copy_(src[i % NS]))
     by = frames * 2 * M * 4
     out["torch_copy_same_size_as_denorm"] = {"bytes": by, "ms": ms, "gbs": by / ms / 1e6, "frac": by / ms / 1e6 / pk}
     out["peak_gbs"] = pk
-    out["note"] = (f"B={B} x T={T}; bytes = algorithmic (fp32 in/out, 16-bit image, 1-byte mask); CUDA events over {reps} launches, "
-                   f"{NS} rotating input sets (> L2)")
+    out["note"] = (f"B={B} x T={T}; bytes = algorithmic (fp32 in/out, 16-bit image, 1-byte mask); CUDA events around {reps} launches "
+                   f"replayed as one CUDA graph ({'/'.join(sorted(set(how)))}), {NS} rotating input sets (> L2)")
     return out
 
 

@@ -649,8 +649,8 @@ __global__ void __launch_bounds__(256) wgrad_reduce_multi_kernel(const WRedArgs 
 }
 
 struct WPlan { int S, blocks_per_split; };
-WPlan plan_wg(int nblocks, int tiles) {
-  int S = 148 / tiles;                                         // one wave: at most one CTA per SM ...
+WPlan plan_wg(int nblocks, int tiles, int sm_budget = 148) {
+  int S = sm_budget / tiles;                                   // one wave: at most one CTA per SM ...
   const int cap = (nblocks + 1) / 2;                           // ... but at least 2 frame blocks per CTA: every split costs a
   if (S > cap) S = cap;                                        // 128 x NT fp32 partial that the reduction has to read back
   if (S > nblocks) S = nblocks;
@@ -668,7 +668,7 @@ struct WgSpec {                   // one weight-gradient problem: dst (flat grad
   const bf16* P0; const bf16* P1; int mtiles0; int Mo; const bf16* Q; int Kin; int taps; float* dst;
 };
 template <int NT>
-int launch_wg_multi(const WgSpec* sp, int n, const RowSpace& rs, float* part, int* status, cudaStream_t s) {
+int launch_wg_multi(const WgSpec* sp, int n, const RowSpace& rs, float* part, int* status, cudaStream_t s, int sm_budget = 148) {
   static PerDeviceOnce once;
   if (once.pending()) {
     MGB_CUDA_CHECK(cudaFuncSetAttribute(wgemm_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, WSmem<NT>::TOTAL));
@@ -691,7 +691,7 @@ int launch_wg_multi(const WgSpec* sp, int n, const RowSpace& rs, float* part, in
     if (int rc = make_image_map(&maps.Q[k], sp[k].Q, q.ntiles_per_tap * (NT / 8), rs.Rp, NT / 8)) return rc;
   }
   for (int k = n; k < WPROB_MAX; ++k) { maps.P0[k] = maps.P0[0]; maps.P1[k] = maps.P0[0]; maps.Q[k] = maps.Q[0]; }
-  const WPlan pl = plan_wg(rs.ntiles, tiles);
+  const WPlan pl = plan_wg(rs.ntiles, tiles, sm_budget);
   a.blocks_per_split = pl.blocks_per_split;
   long long off = 0, begin = 0;
   for (int k = 0; k < n; ++k) {
@@ -942,8 +942,8 @@ Work16 work16_layout(const mgb_model_dims& d, int B, int T) {
   w.dPre = take(32 * Rp * 16);
   w.dS = take(32 * Rp * 16);
   w.E = take(Rp * C * 4);
-  w.Eimg = take(2 * 32 * Rp * 16);   // e_l / e_{l-1} ping-pong: the block's dWo still needs e_l after dx has produced e_{l-1}
-  w.dZ = take(64 * Rp * 16);
+  w.Eimg = take(3 * 32 * Rp * 16);   // e images rotate over three buffers and dZ over two: the weight-gradient work of block
+  w.dZ = take(2 * 64 * Rp * 16);     // l (side stream) still reads e_l / dZ_l while blocks l-1, l-2 run their data-gradient chain
   w.dY = take((size_t)d.layers * 32 * Rp * 16);   // every layer's dY image: d loss / d cond is ONE GEMM over K = 256 L at the head
   w.part = take(wg_part_floats_max(rs.ntiles) * 4);
   w.usumE = take((size_t)B * C * 4);
@@ -1086,6 +1086,43 @@ int bf16_train_forward(const mgb_model_dims& d, const void* packed_fp32, const f
   return MGB_OK;
 }
 
+// The backward of one block is a data-gradient chain (gate backward -> conv^T: what the NEXT block waits for) plus weight
+// gradients, column sums and small per-utterance terms that nothing downstream needs before the head.  The second group
+// runs on a library-owned side stream, one block behind the chain: events fork it after the block's conv^T GEMM and join
+// it back before the buffers it reads are overwritten (dZ two blocks later, the e image three blocks later), before the
+// head segment, and at the end of every call (so a caller — eager, graph capture, bucketed all-reduce — sees a finished
+// gradient slice on its own stream).  The weight-gradient GEMM is planned for 96 SMs there, so that the 52-CTA chain
+// kernels of the next block find free SMs beside it.  One stream + 8 events per device, created at first use.
+struct SideStream { cudaStream_t s = nullptr; cudaEvent_t main_ev[4] = {}, side_ev[4] = {}; };
+SideStream* side_stream() {
+  static SideStream ctx[256];
+  static PerDeviceOnce once;
+  const int dev = PerDeviceOnce::current();
+  if (once.pending()) {
+    SideStream& c = ctx[dev];
+    if (cudaStreamCreateWithFlags(&c.s, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    for (int i = 0; i < 4; ++i) {
+      if (cudaEventCreateWithFlags(&c.main_ev[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+      if (cudaEventCreateWithFlags(&c.side_ev[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    }
+    once.done();
+  }
+  return &ctx[dev];
+}
+#ifdef MGB_DEBUG_BUILD
+bool overlap_enabled() {                          // debug library only: MGB_TRAIN_NO_OVERLAP=1 keeps everything on one stream (A/B)
+  static const bool on = [] { const char* e = getenv("MGB_TRAIN_NO_OVERLAP"); return !(e && e[0] == '1'); }();
+  return on;
+}
+int side_wg_sms() {                               // debug library only: MGB_TRAIN_WG_SMS overrides the weight-gradient SM budget
+  static const int v = [] { const char* e = getenv("MGB_TRAIN_WG_SMS"); return e ? atoi(e) : 96; }();
+  return v;
+}
+#else
+constexpr bool overlap_enabled() { return true; }
+constexpr int side_wg_sms() { return 96; }
+#endif
+
 int bf16_train_backward(const mgb_model_dims& d, const float* flat, const void* saved, const int64_t* t, const float* cond,
                         const float* spk, const float* grad_out, float* grad_flat, float* grad_cond, float* grad_spk,
                         float* grad_x, int B, int T, int seg_begin, int seg_end, void* ws, cudaStream_t s) {
@@ -1109,10 +1146,20 @@ int bf16_train_backward(const mgb_model_dims& d, const float* flat, const void* 
   FArgs base{};
   base.Rp = rs.Rp; base.B = B; base.T = T; base.L = L; base.status = status; base.taps = 1; base.n_mel = M;
 
+  SideStream* side = overlap_enabled() ? side_stream() : nullptr;
+  cudaStream_t ss = side ? side->s : s;           // stream of the off-chain work
+  int first_side_seg = -1, last_side_seg = -1;    // blocks whose off-chain work was issued by THIS call
+  auto join_side = [&]() -> int {
+    if (side && last_side_seg >= 0) MGB_CUDA_CHECK(cudaStreamWaitEvent(s, side->side_ev[last_side_seg & 3], 0));
+    first_side_seg = last_side_seg = -1;
+    return MGB_OK;
+  };
+  const size_t dz_bytes = (size_t)64 * rs.Rp * 16, eimg_bytes = (size_t)32 * rs.Rp * 16;
+
   for (int seg = seg_begin; seg < seg_end; ++seg) {
     if (seg == 0) {
       bmt_to_image_kernel<<<dim3((rs.Rp + 255) / 256, 16), 256, 0, s>>>(grad_out, img(W + w.dout), M, 16, B, T, rs.Rp);
-      zero_margins_kernel<<<dim3(64, 1), 16, 0, s>>>(img(W + w.dZ), 0, 64, rs.Rp);
+      zero_margins_kernel<<<dim3(64, 2), 16, 0, s>>>(img(W + w.dZ), dz_bytes / 2, 64, rs.Rp);
       note_launch(2);
       // dWout = dout^T P, dbout
       if (int rc = launch_wg<256>(cimg(W + w.dout), nullptr, 1, M, cimg(SV + sv.P), C, 1, rs, part, grad_flat + f.out_w,
@@ -1146,38 +1193,47 @@ int bf16_train_backward(const mgb_model_dims& d, const float* flat, const void* 
       const float* fl = flat + f.layer0 + (size_t)l * f.layer_stride;
       float* gl = grad_flat + f.layer0 + (size_t)l * f.layer_stride;
       bf16* dYl = img(W + w.dY) + (size_t)l * 32 * rs.Rp * 8;
-      // e images ping-pong between blocks: e_cur = e_l (input of this block), e_new = e_{l-1} (written by this block)
-      const size_t eimg_bytes = (size_t)32 * rs.Rp * 16;
-      bf16* e_cur = img(W + w.Eimg + ((seg & 1) ? 0 : eimg_bytes));
-      bf16* e_new = img(W + w.Eimg + ((seg & 1) ? eimg_bytes : 0));
+      // e images rotate over three buffers: e_cur = e_l (input of this block, written by the previous one), e_new = e_{l-1};
+      // dZ alternates between two
+      bf16* e_cur = img(W + w.Eimg + (size_t)((seg + 2) % 3) * eimg_bytes);
+      bf16* e_new = img(W + w.Eimg + (size_t)(seg % 3) * eimg_bytes);
+      bf16* dZl = img(W + w.dZ + (size_t)(seg & 1) * dz_bytes);
+      // the off-chain work of block seg - 2 read the dZ buffer this block overwrites (and the e buffer the NEXT chain step
+      // of this block's successor overwrites): wait for it, if this call issued it (an earlier call joined before returning)
+      if (side && seg - 2 >= first_side_seg && first_side_seg >= 0 && seg - 2 <= last_side_seg)
+        MGB_CUDA_CHECK(cudaStreamWaitEvent(s, side->side_ev[(seg - 2) & 3], 0));
       {
         FArgs a = base;                                 // dG = [e | dS] Wo; gate backward -> dZ
         if (top) { a.A0 = cimg(W + w.dS); a.steps0 = 4; a.kstep_b0 = 4; }
         else { a.A0 = e_cur; a.steps0 = 4; a.A1 = cimg(W + w.dS); a.steps1 = 4; }
         a.Bpk = wl + o.r_oproj_b; a.ksteps_b = 8;
-        a.sgth_in = reinterpret_cast<const uint32_t*>(sl + sv.rSGTH); a.img = img(W + w.dZ);
+        a.sgth_in = reinterpret_cast<const uint32_t*>(sl + sv.rSGTH); a.img = dZl;
         if (int rc = launch_fgemm<256, B_GATE>(a, rs.ntiles, 1, s)) return rc;
       }
       {
         FArgs a = base;                                 // dY = conv3^T(dZ); dx = e + dY; e' = dx / sqrt(2)
-        a.A0 = cimg(W + w.dZ); a.steps0 = 8; a.taps = 3; a.Bpk = wl + o.r_conv_b; a.ksteps_b = 24;
+        a.A0 = dZl; a.steps0 = 8; a.taps = 3; a.Bpk = wl + o.r_conv_b; a.ksteps_b = 24;
         a.fout = f32(W + w.E); a.fin = cf32(SV + sv.X0); a.img = dYl; a.img2 = e_new;
         a.first = top ? 1 : 0; a.relu0 = (l == 0) ? 1 : 0;
         if (int rc = launch_fgemm<256, B_DX>(a, rs.ntiles, 1, s)) return rc;
+      }
+      if (side) {                                       // fork: everything below runs behind the chain
+        MGB_CUDA_CHECK(cudaEventRecord(side->main_ev[seg & 3], s));
+        MGB_CUDA_CHECK(cudaStreamWaitEvent(ss, side->main_ev[seg & 3], 0));
       }
       {
         // the block's three weight gradients in ONE launch (18 output tiles x 8 frame splits = one wave) + one reduction:
         //   dWo = [e_l | dS]^T g_l (top block: e = 0, only the skip half), dW3 = dZ^T shift(y_l), dWc = dY^T cond
         WgSpec sp[3];
         if (top) {
-          MGB_CUDA_CHECK(cudaMemsetAsync(gl + f.rel.oproj_w, 0, sizeof(float) * (size_t)C * C, s));
+          MGB_CUDA_CHECK(cudaMemsetAsync(gl + f.rel.oproj_w, 0, sizeof(float) * (size_t)C * C, ss));
           sp[0] = WgSpec{cimg(W + w.dS), nullptr, 2, C, cimg(sl + sv.rG), C, 1, gl + f.rel.oproj_w + (size_t)C * C};
         } else {
           sp[0] = WgSpec{e_cur, cimg(W + w.dS), 2, 2 * C, cimg(sl + sv.rG), C, 1, gl + f.rel.oproj_w};
         }
-        sp[1] = WgSpec{cimg(W + w.dZ), nullptr, 4, 2 * C, cimg(sl + sv.rY), C, 3, gl + f.rel.conv_w};
+        sp[1] = WgSpec{dZl, nullptr, 4, 2 * C, cimg(sl + sv.rY), C, 3, gl + f.rel.conv_w};
         sp[2] = WgSpec{dYl, nullptr, 2, C, cimg(SV + sv.cond), H, 1, gl + f.rel.cproj_w};
-        if (int rc = launch_wg_multi<256>(sp, 3, rs, part, status, s)) return rc;
+        if (int rc = launch_wg_multi<256>(sp, 3, rs, part, status, ss, side ? side_wg_sms() : 148)) return rc;
       }
       // per-utterance column sums of dZ_l, dY_l and of the NEW e image (= e_{l-1}, used by the next block's small terms):
       // one launch; the two e-sum buffers alternate between blocks
@@ -1185,12 +1241,12 @@ int bf16_train_backward(const mgb_model_dims& d, const float* flat, const void* 
       float* usumE_next = f32(W + ((seg & 1) ? w.usumE2 : w.usumE));
       {
         Colsum3 c3{};
-        c3.img[0] = cimg(W + w.dZ); c3.nchunks[0] = 64; c3.out[0] = f32(W + w.usumZ); c3.ldo[0] = 2 * C;
+        c3.img[0] = dZl; c3.nchunks[0] = 64; c3.out[0] = f32(W + w.usumZ); c3.ldo[0] = 2 * C;
         c3.img[1] = dYl; c3.nchunks[1] = 32; c3.out[1] = f32(W + w.usumY); c3.ldo[1] = C;
         c3.img[2] = e_new; c3.nchunks[2] = 32; c3.out[2] = usumE_next; c3.ldo[2] = C;
-        launch_pdl(img_colsum3_kernel, dim3(128, B), dim3(256), 0, s, 1, c3, rs.Rp, rs.T);
+        launch_pdl(img_colsum3_kernel, dim3(128, B), dim3(256), 0, ss, 1, c3, rs.Rp, rs.T);
         note_launch();
-        trace("img_colsum3", s);
+        trace("img_colsum3", ss);
       }
       LayerSmallArgs q{};
       q.usumE = top ? nullptr : usumE_cur; q.usumZ = f32(W + w.usumZ); q.usumY = f32(W + w.usumY);
@@ -1200,11 +1256,17 @@ int bf16_train_backward(const mgb_model_dims& d, const float* flat, const void* 
       q.g_dproj_w = gl + f.rel.dproj_w; q.g_sproj_w = d.multi_speaker ? gl + f.rel.sproj_w : nullptr;
       q.dd_l = f32(W + w.dd_all) + (size_t)l * B * C; q.ds_l = d.multi_speaker ? f32(W + w.ds_all) + (size_t)l * B * C : nullptr;
       q.B = B; q.C = C; q.H = H;
-      launch_pdl(layer_small_kernel, dim3(C + B + 1), dim3(256), 0, s, 1, q);
+      launch_pdl(layer_small_kernel, dim3(C + B + 1), dim3(256), 0, ss, 1, q);
       note_launch();
+      if (side) {
+        MGB_CUDA_CHECK(cudaEventRecord(side->side_ev[seg & 3], ss));
+        if (first_side_seg < 0) first_side_seg = seg;
+        last_side_seg = seg;
+      }
     } else if (seg == L + 1) {
+      if (int rc = join_side()) return rc;
       // head: E and the e image written by block 0 hold the ReLU-masked gradient of the input projection's pre-activation
-      const bf16* e_last = cimg(W + w.Eimg + ((L & 1) ? (size_t)32 * rs.Rp * 16 : 0));
+      const bf16* e_last = cimg(W + w.Eimg + (size_t)(L % 3) * eimg_bytes);
       if (int rc = launch_wg<128>(e_last, nullptr, 2, C, cimg(SV + sv.xt), M, 1, rs, part, grad_flat + f.in_w,
                                   status, s)) return rc;
       launch_colsum_img(e_last, 32, rs, B, f32(W + w.usumT), C, s);
@@ -1235,6 +1297,7 @@ int bf16_train_backward(const mgb_model_dims& d, const float* flat, const void* 
         MGB_CUDA_CHECK(cudaMemcpyAsync(grad_spk, W + w.dspk, sizeof(float) * (size_t)B * H, cudaMemcpyDeviceToDevice, s));
     }
   }
+  if (int rc = join_side()) return rc;
   MGB_LAUNCH_CHECK();
   return MGB_OK;
 }

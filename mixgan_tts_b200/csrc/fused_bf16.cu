@@ -1400,11 +1400,11 @@ int bf16_pack(const mgb_model_dims& d, const float* flat, void* packed, cudaStre
   const int H = d.d_encoder, L = d.layers;
   launch_pack(flat + f.mlp0_w, P + o.mlp0_wt, 4 * C, C, 1, 4 * C, 0, 0, s);
   launch_pack(flat + f.mlp2_w, P + o.mlp2_wt, C, 4 * C, 1, C, 0, 0, s);
-  for (int l = 0; l < L; ++l) {
-    const float* fl = flat + f.layer0 + (size_t)l * f.layer_stride;
-    launch_pack(fl + f.rel.dproj_w, P + o.dproj_wt + (size_t)l * C * C, C, C, 1, C, 0, 0, s);
-    if (d.multi_speaker) launch_pack(fl + f.rel.sproj_w, P + o.sproj_wt + (size_t)l * H * C, C, H, 1, C, 0, 0, s);
-    pack_bias_kernel<<<2, 128, 0, s>>>(fl + f.rel.cproj_b, P + o.cproj_b + (size_t)l * C, C, C, 0, 0);
+  {   // the per-block tables of all L residual blocks: one launch per kind (a training step re-packs after every update)
+    const float* fl = flat + f.layer0;
+    launch_pack(fl + f.rel.dproj_w, P + o.dproj_wt, C, C, 1, C, 0, 0, s, L, f.layer_stride, (size_t)C * C);
+    if (d.multi_speaker) launch_pack(fl + f.rel.sproj_w, P + o.sproj_wt, C, H, 1, C, 0, 0, s, L, f.layer_stride, (size_t)H * C);
+    pack_bias_kernel<<<dim3(2, L), 128, 0, s>>>(fl + f.rel.cproj_b, P + o.cproj_b, C, C, 0, 0, f.layer_stride, (size_t)C);
   }
   pack_small_kernel<<<1, 256, 0, s>>>(flat, f, L, d.n_mel, P + o.bo_x, P + o.bsum_skip, P + o.b_in,
                                       P + o.b_skip, P + o.b_out);

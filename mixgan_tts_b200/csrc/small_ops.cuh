@@ -11,11 +11,14 @@ namespace smallops {
 // ---- weight packing: dst[k][n'] = src[orig(n')][k] -------------------------------------------
 // src is [n_src][Kin][taps] (state_dict layout); dst is [taps*Kin][ldd], k = tap*Kin + ci.
 // perm: 128-wide column tiles hold 64 first-half then 64 second-half output channels.
+// blockIdx.z walks `gridDim.z` matrices of the same shape (one per residual block), src_zs / dst_zs floats apart.
 static __global__ void pack_wt_kernel(const float* __restrict__ src, float* __restrict__ dst, int n_src,
-                               int Kin, int taps, int ldd, int perm, int half_n) {
+                               int Kin, int taps, int ldd, int perm, int half_n, size_t src_zs, size_t dst_zs) {
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   const int k = blockIdx.y;
   if (n >= ldd) return;
+  src += blockIdx.z * src_zs;
+  dst += blockIdx.z * dst_zs;
   int orig = n;
   if (perm) {
     const int tile = n >> 7, pos = n & 127;
@@ -28,9 +31,11 @@ static __global__ void pack_wt_kernel(const float* __restrict__ src, float* __re
 }
 
 static __global__ void pack_bias_kernel(const float* __restrict__ src, float* __restrict__ dst, int n_src,
-                                 int n_dst, int perm, int half_n) {
+                                 int n_dst, int perm, int half_n, size_t src_zs = 0, size_t dst_zs = 0) {
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= n_dst) return;
+  src += blockIdx.y * src_zs;
+  dst += blockIdx.y * dst_zs;
   int orig = n;
   if (perm) {
     const int tile = n >> 7, pos = n & 127;
@@ -189,9 +194,9 @@ static __global__ void __launch_bounds__(256) proj_table_kernel(const float* __r
 
 
 static inline void launch_pack(const float* src, float* dst, int n_src, int Kin, int taps, int ldd, int perm,
-                 int half_n, cudaStream_t s) {
-  dim3 grid((ldd + 127) / 128, taps * Kin);
-  pack_wt_kernel<<<grid, 128, 0, s>>>(src, dst, n_src, Kin, taps, ldd, perm, half_n);
+                 int half_n, cudaStream_t s, int nmat = 1, size_t src_zs = 0, size_t dst_zs = 0) {
+  dim3 grid((ldd + 127) / 128, taps * Kin, nmat);
+  pack_wt_kernel<<<grid, 128, 0, s>>>(src, dst, n_src, Kin, taps, ldd, perm, half_n, src_zs, dst_zs);
 }
 
 

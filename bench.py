@@ -816,7 +816,7 @@ def bench_train(ctx, prec, steps, warmup, B):
     launches_gan = (lib.mgb_launch_count() - n0) // max(steps, 1)
     ms_gan_nosync = ctx.timed(lambda i: gan_step(i, with_sync=False), steps, 0) if ctx.world > 1 else ms_gan_eager
     # The whole step as ONE CUDA graph (fixed shapes: the training loader pads every batch to max_seq_len): the step has
-    # ~500 library launches + ~350 torch kernels and its eager form is bound by the host enqueueing them, not by the GPU.
+    # ~400 library launches + ~330 torch kernels and its eager form is bound by the host enqueueing them, not by the GPU.
     # Inputs are copied into static buffers; every launch of the library, the random draws of the training branch, the
     # all-reduces and both fused Adam steps replay from the graph.
     graph_note, ms_gan = None, ms_gan_eager
@@ -837,10 +837,14 @@ def bench_train(ctx, prec, steps, warmup, B):
     return {"metric": "train_frames_per_sec", "value": frames * steps / (ms_gan * 1e-3), "unit": UNIT, "ms_per_step": ms_gan / steps,
             "scaling": "weak", "precision": prec,
             "workload": f"LJSpeech naive GAN training step of train.py:126-184 on the diffusion decoder: D phase (Denoiser forward, "
-                        f"2 x JCU discriminator forward, backward, clip, Adam) + G phase (Denoiser forward, 2 x discriminator forward, "
-                        f"adversarial + mel L1 + feature-matching losses, backward through the discriminator into the Denoiser, clip, "
-                        f"Adam), B={B} x T={T} per GPU (BASELINE configs[4]); NCCL all-reduce of the Denoiser gradient (bucketed, "
-                        "overlapped) and of the discriminator gradient",
+                        f"JCU discriminator forward on the fake and the real pair, backward, clip, Adam) + G phase (Denoiser forward, "
+                        f"discriminator forward on both pairs, adversarial + mel L1 + feature-matching losses, backward through the "
+                        f"discriminator into the Denoiser, clip, Adam), B={B} x T={T} per GPU (BASELINE configs[4]); NCCL all-reduce of "
+                        "the Denoiser gradient (bucketed, overlapped) and of the discriminator gradient; "
+                        + ("the two discriminator calls of a phase run separately and the D-phase generator forward keeps its stash"
+                           if UNBATCHED else
+                           "the two discriminator calls of a phase run as one call on the 2B-utterance batch [fake | real] (same losses and "
+                           "gradients) and the D-phase generator forward, whose outputs train.py detaches, runs with autograd off"),
             "tflops": flops_gan * steps / (ms_gan * 1e-3) / 1e12,
             "allreduce_exposed_ms_per_step": (ms_gan_eager - ms_gan_nosync) / steps,
             "eager_ms_per_step": ms_gan_eager / steps, "cuda_graph": graph_note,

@@ -346,15 +346,18 @@ __global__ void __launch_bounds__(NTHR, 2) conv_wgrad_f32_kernel(const float* __
   }
 }
 
-// dw[co][ci][j] (torch layout) = sum over splits (fixed order) of part[split][j*Cin + ci][co]
+// dw[co][ci][j] (torch layout) = sum over splits (fixed order) of part[split][j*Cin + ci][co].  Thread = one (kk, co) element
+// of the partial layout: the nsplit reads of a warp are 128 contiguous bytes each, only the single write is scattered
+// (indexing by the torch layout instead made every one of the nsplit reads a 4-byte access Cin * Cout floats apart).
 __global__ void wgrad_reduce_f32_kernel(const float* __restrict__ part, float* __restrict__ dw, int Cin, int Cout, int k, int nsplit) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= Cout * Cin * k) return;
-  const int j = i % k, ci = (i / k) % Cin, co = i / (k * Cin);
-  const size_t K = (size_t)k * Cin, kk = (size_t)j * Cin + ci;
+  const int n = Cout * Cin * k;
+  if (i >= n) return;
+  const int co = i % Cout, kk = i / Cout;
+  const int j = kk / Cin, ci = kk - j * Cin;
   float a = 0.f;
-  for (int s = 0; s < nsplit; ++s) a += part[((size_t)s * K + kk) * Cout + co];
-  dw[i] = a;
+  for (int s = 0; s < nsplit; ++s) a += part[(size_t)s * n + i];
+  dw[((size_t)co * Cin + ci) * k + j] = a;
 }
 
 // out[g][c] = sum over the group's rows of a[row][c]   (bias gradient: one group; rowbias gradient: one group per utterance).

@@ -17,3 +17,6 @@ for n in 0 1 2 3; do MIXGAN_B200_USE_DEBUG_LIB=1 MGB_TC_TRACE=$n timeout 200 pyt
 MIXGAN_B200_USE_DEBUG_LIB=1 MGB_TC_TRACE=all timeout 200 python scripts/tc_trace.py 2>&1 | tail -1 > gpurun_out/tc_trace_voc.txt
 cat gpurun_out/tc_trace_aux.txt gpurun_out/tc_trace_voc.txt | cut -c1-260
 ls gpurun_out | head -60
+echo "== discriminator Conv1d layers (warm-L2 per-kernel durations)"
+timeout 300 ncu --cache-control none --metrics gpu__time_duration.sum --clock-control none -k regex:"conv_gemm|conv_wgrad|splitk|wgrad_reduce|colsum|act_bwd|pack_w" --csv --log-file gpurun_out/conv1d_launches.csv python scripts/bench_conv1d.py 16 > gpurun_out/conv1d_ncu.log 2>&1; tail -1 gpurun_out/conv1d_ncu.log
+echo "== elementwise kernels"; timeout 200 python scripts/bench_elementwise.py > gpurun_out/elementwise.txt 2>&1; tail -3 gpurun_out/elementwise.txt | cut -c1-200

@@ -22,6 +22,10 @@ for path in sys.argv[1:]:
                 for kk, vv in v.items():
                     if isinstance(vv, dict):
                         print(f"  elementwise {kk}: {vv['ms'] * 1e3:.1f} us, {vv['gbs']:.0f} GB/s, frac {vv['frac']:.2f}")
+            elif "value" not in v:           # a record of records (stages)
+                for kk, vv in v.items():
+                    if isinstance(vv, dict) and "value" in vv:
+                        print(f"  sub {k}.{kk}: value {int(vv['value'])} {vv.get('unit', '')} frac {(vv.get('roofline') or {}).get('frac')}")
             else:
                 rr = v.get("roofline", {})
                 print(f"  sub {k}: value {int(v['value'])} ms {v['ms_per_step']:.3f} e2e {int(v['e2e']['value']) if 'e2e' in v else None} "

@@ -66,13 +66,22 @@ if os.path.exists(p):
             write_agg(f, L[voc[-1]:voc[-1] + 79], by_grid=True)
 p = os.path.join(G, "launches_train_gan.csv")
 if os.path.exists(p):
-    L = read_launches(p)
-    se = [i for i, r in enumerate(L) if "step_emb" in r[0]]
-    if len(se) >= 8:
+    txt = subprocess.run([sys.executable, "scripts/gan_step_summary.py", p, "60"], capture_output=True, text=True).stdout
+    if txt.strip():
         with open(os.path.join(out, "launches_train_gan_summary.txt"), "w") as f:
             f.write("ncu --metrics gpu__time_duration.sum --clock-control none python bench.py --workload train --steps 1 --warmup 3 (eager)\n"
-                    "(one period of the GAN training step of train.py:126-184, B=8 x T=800; cold-cache, serialised)\n\n")
-            write_agg(f, L[se[-8]:se[-4]])
+                    "(the last eager GAN training step of train.py:126-184, B=8 x T=800; cold-cache, serialised: compare SHARES)\n\n" + txt)
+p = os.path.join(G, "conv1d_launches.csv")
+if os.path.exists(p):
+    txt = subprocess.run([sys.executable, "scripts/conv1d_ncu_summary.py", p], capture_output=True, text=True).stdout
+    if txt.strip():
+        with open(os.path.join(out, "conv1d_f32_layers_summary.txt"), "w") as f:
+            f.write("ncu --cache-control none --metrics gpu__time_duration.sum --clock-control none python scripts/bench_conv1d.py 16\n"
+                    "(forward + backward of every JCU-discriminator layer at the batched training shape, 16 utterances x T=800; warm L2;\n"
+                    " per layer: total kernel time, then every kernel above 8 us with its grid)\n\n" + txt)
+p = os.path.join(G, "elementwise.txt")
+if os.path.exists(p):
+    shutil.copy(p, os.path.join(out, "elementwise_hbm.txt"))
 
 # ---- ncu --set full captures
 def ncu_summary(rep, dst, header):

@@ -69,6 +69,44 @@ def test_features_and_gradients_vs_reference_golden(name):
     assert rel_l2(preds.grad, g["g_grad_preds"]) < TOL
 
 
+@pytest.mark.parametrize("multi", [False, True])
+def test_one_call_on_the_concatenated_batch_equals_two_calls(multi):
+    """bench.py's GAN step runs the fake and the real pair of a phase as ONE call on the 2B-utterance batch (train.py calls
+    the discriminator twice): same features, same losses, same parameter and input gradients (utterances are independent
+    in every layer; only fp32 summation orders differ)."""
+    B, T = 3, 96
+    D, mc = build(multi, 2)
+    inp = synth.make_discriminator_inputs(31, B, T, 4, multi_speaker=multi)
+    cu = lambda k: None if inp[k] is None else torch.from_numpy(inp[k]).cuda()
+    x_ts, prevs, spk, t = cu("x_ts"), cu("x_t_prevs"), cu("spk"), cu("t")
+    n_layers = mc["discriminator"]["n_layer"] + mc["discriminator"]["n_cond_layer"]
+    d_loss_fn, g_loss_fn = get_lsgan_losses_fn()
+
+    def losses(fc, fu, rc, ru):
+        r, f = d_loss_fn(rc[-1], ru[-1], fc[-1], fu[-1])
+        return r + f + g_loss_fn(fc[-1], fu[-1]) + feature_matching_loss(rc, ru, fc, fu, n_layers)
+
+    p1 = cu("x_t_prev_preds").requires_grad_(True)
+    fc, fu = D(x_ts, p1, spk, t)
+    rc, ru = D(x_ts, prevs, spk, t)
+    D.zero_grad(set_to_none=True)
+    l1 = losses(fc, fu, rc, ru)
+    l1.backward()
+    g1 = {k: p.grad.clone() for k, p in D.named_parameters()}
+    p2 = cu("x_t_prev_preds").requires_grad_(True)
+    D.zero_grad(set_to_none=True)
+    c, u = D(torch.cat([x_ts, x_ts]), torch.cat([p2, prevs]), None if spk is None else torch.cat([spk, spk]), torch.cat([t, t]))
+    fc2, fu2, rc2, ru2 = [f[:B] for f in c], [f[:B] for f in u], [f[B:] for f in c], [f[B:] for f in u]
+    for a, b in zip(fc + fu + rc + ru, fc2 + fu2 + rc2 + ru2):
+        assert rel_l2(b.detach(), a.detach()) < 1e-6
+    l2 = losses(fc2, fu2, rc2, ru2)
+    l2.backward()
+    assert abs(float(l1) - float(l2)) < 1e-6 * abs(float(l1))
+    assert rel_l2(p2.grad, p1.grad) < 1e-5
+    for k, p in D.named_parameters():
+        assert rel_l2(p.grad, g1[k]) < 1e-5, k
+
+
 def test_state_dict_keys_match_the_reference_layout():
     for multi in (False, True):
         D, _ = build(multi, 1)

@@ -13,7 +13,10 @@
 //   wgrad     dw[co][ci][j] = sum_{b,to} xin[b][to*s + j - pad][ci] * dz[b][to][co]          (frames split over CTAs, partial
 //             sums reduced in a fixed order: deterministic, no atomics)
 // dz = dy * act'(.) is formed by a small elementwise kernel first; bias and rowbias gradients are column sums.
+#include <algorithm>
+
 #include "common.cuh"
+#include "tc05.cuh"
 
 namespace mgb {
 namespace {
@@ -41,7 +44,7 @@ __global__ void pack_w_kernel(const float* __restrict__ w, float* __restrict__ w
   if (i >= Cout * Cin * k) return;
   const int j = i % k, ci = (i / k) % Cin, co = i / (k * Cin);
   const float v = w[i];
-  wp[((size_t)j * Cin + ci) * Cout + co] = v;
+  if (wp) wp[((size_t)j * Cin + ci) * Cout + co] = v;
   if (wq) wq[((size_t)j * Cout + co) * Cin + ci] = v;
 }
 
@@ -222,6 +225,257 @@ __global__ void splitk_epilogue_kernel(const float* __restrict__ part, const flo
   if (bias) v += bias[i % N];
   if (pre) pre[i] = v;
   out[i] = act_fwd(v, act);
+}
+
+// ---- the same GEMM on the tensor cores at fp32 accuracy: 3 x TF32 ------------------------------------------------------
+// out[128 x 64 tile] = sum over 32-deep k-blocks of A B with every fp32 operand split as x = hi + lo, hi = x with the low 13
+// mantissa bits cleared (exactly what kind::tf32 reads), lo = x - hi (exact in fp32): three tcgen05.mma.kind::tf32 per
+// k8-step, lo*hi + hi*lo + hi*hi, fp32 accumulation in TMEM; the dropped terms are below 2^-21 of a product, so the result is
+// fp32-grade (the parity tests hold it to the same 1e-5 as the CUDA-core kernels).
+//   A operand: gathered by the CTA's own threads, not by TMA — it is the implicit-convolution gather (tap shift, stride,
+//     padding rows, "+ rowbias") of conv_gemm_f32_kernel, 32 channels (128 contiguous bytes) of a row per k-block, split and
+//     stored as K-major core matrices (8 rows x 16 bytes; per 4-channel group the 128 rows are one dense [128][16 B] array,
+//     SBO = 128 B, LBO = 2 KB + 16 B).
+//   B operand: the weights, split and tiled ONCE per call by pack_w_tc_kernel into exactly the shared-memory image of a
+//     (64-column tile, k-block) pair — hi then lo, 16 KB — so one cp.async.bulk per k-block brings it (3-slot ring, issued
+//     one k-block ahead by thread 0, completion on the slot's mbarrier).  (Staging B with the threads as well took 480
+//     instructions per warp and k-block at 7.5 stall cycles each: ncu, profiles/r02.)
+// Warp-specialised, no CTA-wide barrier in the loop: 128 staging threads (their global loads run two k-blocks ahead in
+// registers) publish an A stage through an mbarrier; one thread of a fifth warp issues the B copies and the MMAs as soon as
+// both operands of a k-block have landed, and tcgen05.commit on the stage's mbarrier hands it back.  (The first version —
+// one __syncthreads per k-block, MMAs issued by staging thread 0 — spent 4 400 cycles per k-block on that serial chain.)  Needs Ca % 32 == 0 (a k-block inside one tap) and N % 4 == 0; other
+// shapes take the CUDA-core kernel.  Split K as there (blockIdx.z), same epilogue kernel.
+constexpr int TC_BM = 128, TC_BK = 32, TC_THREADS = 160;    // 4 staging / epilogue warps + 1 warp issuing MMAs and B copies
+constexpr int TC_A_LBO = TC_BM * 16 + 16;                   // + 16 B, so the 8 channel groups of a row hit 8 bank groups
+constexpr int TC_A_BYTES = 8 * TC_A_LBO;                    // one of hi / lo: 16.1 KB
+constexpr int TC_A_STAGE = 2 * TC_A_BYTES;                  // hi + lo
+constexpr int TC_NA = 2, TC_NB = 3;
+// column tile BN = 128 (64 for narrow outputs): a tcgen05.mma costs the issuing thread ~300 cycles whatever its size (twelve
+// N = 64 MMAs per k-block were 3 800 cycles, the whole loop time), so the tile is as wide as shared memory allows
+template <int BN> struct TcCfg {
+  static constexpr int B_LBO = BN * 16, B_BYTES = 8 * B_LBO, B_STAGE = 2 * B_BYTES;      // BN = 128: 32 KB per slot
+  static constexpr int SMEM = TC_NA * TC_A_STAGE + TC_NB * B_STAGE + 128;                // 162 KB (BN = 128), 113 KB (64)
+};
+constexpr long long TC_TIMEOUT = 400000000LL;
+
+__device__ __forceinline__ float cut_tf32(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+__device__ __forceinline__ void split_tf32(const float4 v, float4& hi, float4& lo) {
+  hi = make_float4(cut_tf32(v.x), cut_tf32(v.y), cut_tf32(v.z), cut_tf32(v.w));
+  lo = make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w);     // the tensor core reads its top 19 bits
+}
+
+// B[kk][n] (forward: kk = j*Cin + ci, n = co; data gradient: kk = j*Cout + co, n = ci) = w[co][ci][j], split and written as
+// tiles [n / BN][kk / 32] of {hi, lo} x [kc = (kk % 32) / 4][n % BN][kk % 4]; columns beyond N are zero
+__global__ void pack_w_tc_kernel(const float* __restrict__ w, float* __restrict__ dst, int Cin, int Cout, int k, int dgrad, int BN) {
+  const int Ca = dgrad ? Cout : Cin, N = dgrad ? Cin : Cout;
+  const int K = k * Ca, Npad = (N + BN - 1) / BN * BN, nkb = K / TC_BK;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= K * Npad) return;
+  // the fastest thread index walks w with the smaller stride: ci (stride k floats) — that is kk forward, n in the data gradient
+  const int n = dgrad ? i % Npad : i / K, kk = dgrad ? i / Npad : i % K;
+  const int j = kk / Ca, c = kk - j * Ca;
+  float v = 0.f;
+  if (n < N) v = dgrad ? w[((size_t)c * Cin + n) * k + j] : w[((size_t)n * Cin + c) * k + j];
+  const float hi = cut_tf32(v), lo = v - hi;
+  const int nt = n / BN, kb = kk / TC_BK, kc = (kk % TC_BK) / 4, e = kk & 3, nn = n % BN;
+  const int half = 8 * BN * 4;                                 // floats of one of hi / lo
+  float* t = dst + ((size_t)nt * nkb + kb) * (2 * half);
+  t[kc * (BN * 4) + nn * 4 + e] = hi;
+  t[half + kc * (BN * 4) + nn * 4 + e] = lo;
+}
+
+template <bool DGRAD, int BN>
+__global__ void __launch_bounds__(TC_THREADS) conv_gemm_tc_kernel(const float* __restrict__ A, const float* __restrict__ Bt,
+                                                                  const float* __restrict__ bias, const float* __restrict__ rowbias,
+                                                                  float* __restrict__ out, float* __restrict__ pre,
+                                                                  float* __restrict__ part, ConvShape s, int act, int blocks_per_split) {
+  using Cfg = TcCfg<BN>;
+  constexpr int TC_BN = BN, TC_B_LBO = Cfg::B_LBO, TC_B_BYTES = Cfg::B_BYTES, TC_B_STAGE = Cfg::B_STAGE;
+  extern __shared__ __align__(1024) uint8_t tc_smem[];
+  uint8_t* smA = tc_smem;
+  uint8_t* smB = tc_smem + TC_NA * TC_A_STAGE;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tc_smem + TC_NA * TC_A_STAGE + TC_NB * TC_B_STAGE);
+  uint64_t* bar_free = bars;               // [2] the tensor core has read A stage i (and the B slot used with it)
+  uint64_t* bar_afull = bars + 2;          // [2] all 128 staging threads have written A stage i
+  uint64_t* bar_bfull = bars + 4;          // [3] B slot landed
+  uint64_t* bar_done = bars + 7;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int m0 = blockIdx.x * TC_BM, n0 = blockIdx.y * TC_BN;
+  const int rows_per_b = DGRAD ? s.Tin : s.Tout, src_per_b = DGRAD ? s.Tout : s.Tin;
+  const int Ca = DGRAD ? s.Cout : s.Cin, N = DGRAD ? s.Cin : s.Cout;
+  const int M = s.B * rows_per_b, K = s.k * Ca;
+  const int nkb_all = K / TC_BK;
+  const int kb0 = blockIdx.z * blocks_per_split;
+  const int nkb = min(blocks_per_split, nkb_all - kb0);
+
+  if (tid == 0) {
+    tc::mbar_init(&bar_free[0], 1); tc::mbar_init(&bar_free[1], 1);
+    tc::mbar_init(&bar_afull[0], 128); tc::mbar_init(&bar_afull[1], 128);
+    for (int i = 0; i < TC_NB; ++i) tc::mbar_init(&bar_bfull[i], 1);
+    tc::mbar_init(bar_done, 1);
+    tc::fence_barrier_init();
+  }
+  if (warp == 4) tc::tmem_alloc<TC_BN>(tmem_slot);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 4) {
+    // ---- one elected thread of this warp: B copies one k-block ahead, MMAs as soon as both operands of a k-block are in
+    // shared memory.  The whole warp walks the loop (uniform control flow, elect-predicated issue): the descriptors stay
+    // in uniform registers.
+    if (nkb > 0) {
+      const float* btile = Bt + ((size_t)blockIdx.y * nkb_all + kb0) * (TC_B_STAGE / 4);
+      constexpr uint32_t IDESC = tc::make_idesc_tf32(TC_BM, TC_BN);
+      const uint32_t smA_u = tc::smem_u32(smA), smB_u = tc::smem_u32(smB);
+      if (tc::elect_one()) {
+        tc::mbar_arrive_expect_tx(&bar_bfull[0], TC_B_STAGE);
+        tc::bulk_g2s(smB, btile, TC_B_STAGE, &bar_bfull[0]);
+      }
+      for (int it = 0; it < nkb; ++it) {
+        const int stage = it & 1, slot = it % TC_NB;
+        if (it + 1 < nkb) {
+          // B slot (it + 1) % 3 was read by the MMAs of k-block it - 2
+          if (it >= 2 && !tc::mbar_wait(&bar_free[stage], ((it >> 1) + 1) & 1, TC_TIMEOUT)) __trap();
+          const int ns = (it + 1) % TC_NB;
+          if (tc::elect_one()) {
+            tc::mbar_arrive_expect_tx(&bar_bfull[ns], TC_B_STAGE);
+            tc::bulk_g2s(smB + ns * TC_B_STAGE, btile + (size_t)(it + 1) * (TC_B_STAGE / 4), TC_B_STAGE, &bar_bfull[ns]);
+          }
+        }
+        if (!tc::mbar_wait(&bar_afull[stage], (it >> 1) & 1, TC_TIMEOUT)) __trap();
+        if (!tc::mbar_wait(&bar_bfull[slot], (it / TC_NB) & 1, TC_TIMEOUT)) __trap();
+        tc::tc_fence_after();
+        const uint32_t abase = smA_u + stage * TC_A_STAGE, bbase = smB_u + slot * TC_B_STAGE;
+        // descriptors of k8-step 0; a step further is two core-matrix columns = 2 LBO bytes (>> 4 in the address field)
+        const uint64_t a_hi = tc::make_smem_desc(abase, TC_A_LBO, 128), a_lo = tc::make_smem_desc(abase + TC_A_BYTES, TC_A_LBO, 128);
+        const uint64_t b_hi = tc::make_smem_desc(bbase, TC_B_LBO, 128), b_lo = tc::make_smem_desc(bbase + TC_B_BYTES, TC_B_LBO, 128);
+        if (tc::elect_one()) {
+#pragma unroll
+          for (int ks = 0; ks < TC_BK / 8; ++ks) {
+            const uint64_t da = (uint64_t)(ks * 2 * TC_A_LBO >> 4), db = (uint64_t)(ks * 2 * TC_B_LBO >> 4);
+            tc::umma_tf32(tmem, a_lo + da, b_hi + db, IDESC, (it > 0 || ks > 0) ? 1u : 0u);      // small terms first
+            tc::umma_tf32(tmem, a_hi + da, b_lo + db, IDESC, 1u);
+            tc::umma_tf32(tmem, a_hi + da, b_hi + db, IDESC, 1u);
+          }
+          tc::umma_commit(&bar_free[stage]);
+          if (it + 1 == nkb) tc::umma_commit(bar_done);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ---- 128 staging threads.  Eight lanes read the 128 contiguous bytes (32 channels) of one A row, so a warp-wide 16-byte
+    // load touches 4 lines (one row per thread touched 32, and the loop waited on the L1 request queue: ncu long-scoreboard
+    // stalls at the first use of the loaded registers, even two k-blocks ahead).  Thread -> rows 32 warp + 4 i + lane / 8
+    // (i < 8), 4-channel group lane % 8; per row only (base offset, first source row) are kept, a k-block costs an add and
+    // two compares per row.  The global loads run two k-blocks ahead in registers.
+    const int lane = tid & 31, a_kc = lane & 7, a_r0 = warp * 32 + (lane >> 3);
+    long long a_base[8];          // element offset of (utterance, source row 0) + this thread's channel group; < 0: no such row
+    int a_q[8];                   // forward: t * stride - pad (source row = a_q + j); data gradient: t + pad (q = a_q - j)
+    int a_rb[8];                  // forward: offset of this thread's channel group in the utterance's rowbias row
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int mi = m0 + a_r0 + 4 * i;
+      if (mi < M) {
+        const int b = mi / rows_per_b, t = mi - b * rows_per_b;
+        a_base[i] = (long long)b * src_per_b * Ca + a_kc * 4;
+        a_q[i] = DGRAD ? t + s.pad : t * s.stride - s.pad;
+        a_rb[i] = b * Ca + a_kc * 4;
+      } else { a_base[i] = -1; a_q[i] = 0; a_rb[i] = 0; }
+    }
+    auto load_g = [&](int kb, float4 (&ra)[8]) {             // k-block kb of the whole K axis -> registers
+      const int kk = kb * TC_BK;
+      const int j = kk / Ca, c0 = kk - j * Ca;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        int src;
+        bool ok = a_base[i] >= 0;
+        if (DGRAD) {
+          const int q = a_q[i] - j;
+          if (s.stride == 1) src = q;
+          else if (s.stride == 2) { src = q >> 1; ok = ok && (q & 1) == 0; }
+          else { src = q / s.stride; ok = ok && q % s.stride == 0; }
+          ok = ok && q >= 0 && src < s.Tout;
+        } else {
+          src = a_q[i] + j;
+          ok = ok && src >= 0 && src < s.Tin;
+        }
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ok) {
+          v = *reinterpret_cast<const float4*>(A + a_base[i] + (long long)src * Ca + c0);
+          if (!DGRAD && rowbias) {
+            const float4 r = *reinterpret_cast<const float4*>(rowbias + a_rb[i] + c0);
+            v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+          }
+        }
+        ra[i] = v;
+      }
+    };
+    auto stage_step = [&](int it, float4 (&ra)[8]) {          // publish k-block `it` from ra, then refill ra with it + 2
+      const int stage = it & 1;
+      if (it >= 2 && !tc::mbar_wait(&bar_free[stage], ((it >> 1) + 1) & 1, TC_TIMEOUT)) __trap();
+      uint8_t* st = smA + stage * TC_A_STAGE + a_kc * TC_A_LBO + a_r0 * 16;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float4 hi, lo;
+        split_tf32(ra[i], hi, lo);
+        *reinterpret_cast<float4*>(st + i * 64) = hi;
+        *reinterpret_cast<float4*>(st + TC_A_BYTES + i * 64) = lo;
+      }
+      tc::fence_proxy_async_smem();
+      tc::mbar_arrive(&bar_afull[stage]);
+      if (it + 2 < nkb) load_g(kb0 + it + 2, ra);
+    };
+    float4 r0[8], r1[8];
+    if (nkb > 0) load_g(kb0, r0);
+    if (nkb > 1) load_g(kb0 + 1, r1);
+    for (int it = 0; it < nkb; it += 2) {
+      stage_step(it, r0);
+      if (it + 1 < nkb) stage_step(it + 1, r1);
+    }
+    const int m = m0 + tid;                               // epilogue: thread = output row = TMEM lane
+    // epilogue
+    const bool split = gridDim.z > 1;
+    float* dst = split ? part + (size_t)blockIdx.z * M * N : out;
+    if (nkb > 0 && !tc::mbar_wait(bar_done, 0, TC_TIMEOUT)) __trap();
+    tc::tc_fence_after();
+#pragma unroll
+    for (int h = 0; h < TC_BN / 32; ++h) {
+      uint32_t r[32];
+      if (nkb > 0) {
+        tc::tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + h * 32, r);
+        tc::tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) r[i] = 0u;
+      }
+      if (m < M) {
+#pragma unroll
+        for (int c4 = 0; c4 < 8; ++c4) {
+          const int n = n0 + h * 32 + c4 * 4;
+          if (n >= N) break;                                   // N % 4 == 0
+          float v[4] = {__uint_as_float(r[c4 * 4]), __uint_as_float(r[c4 * 4 + 1]), __uint_as_float(r[c4 * 4 + 2]),
+                        __uint_as_float(r[c4 * 4 + 3])};
+          if (!split && !DGRAD) {
+            if (bias) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) v[e] += bias[n + e];
+            }
+            if (pre) *reinterpret_cast<float4*>(pre + (size_t)m * N + n) = make_float4(v[0], v[1], v[2], v[3]);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) v[e] = act_fwd(v[e], act);
+          }
+          *reinterpret_cast<float4*>(dst + (size_t)m * N + n) = make_float4(v[0], v[1], v[2], v[3]);
+        }
+      }
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tc::tmem_dealloc<TC_BN>(tmem);
 }
 
 // ---- dz = dy * act'(.)  (leaky / relu from the sign of y, mish from the stored pre-activation) ----
@@ -444,17 +698,34 @@ int gemm_splits(int M, int N, int K) {
   if (want > nks / 8) want = nks / 8;
   return want < 1 ? 1 : (want > 16 ? 16 : want);
 }
+// tensor-core plan: 128 x BN tiles (BN = 128, or 64 for outputs of at most 64 columns), 32-deep k-blocks; split K until
+// about one CTA per SM exists (two for BN = 64, which fit an SM together), at least 4 k-blocks per split
+bool tc_eligible(int N, int Ca) { return Ca % TC_BK == 0 && N % 4 == 0 && N >= 16; }
+int tc_bn(int N) { return N > 64 ? 128 : 64; }
+int tc_splits(int M, int N, int K) {
+  const int bn = tc_bn(N);
+  const int tiles = ((M + TC_BM - 1) / TC_BM) * ((N + bn - 1) / bn), nkb = K / TC_BK;
+  int want = (bn == 64 ? 296 : 148) / tiles;
+  if (want > nkb / 4) want = nkb / 4;
+  return want < 1 ? 1 : (want > 16 ? 16 : want);
+}
 struct Work { size_t wp, wq, dz, part, cs, gpart, total; };
 Work work_layout(const ConvShape& s) {
   Work w{};
   size_t p = 0;
   auto take = [&](size_t n) { size_t r = p; p += align_up(n * sizeof(float), 256); return r; };
   const size_t wn = (size_t)s.k * s.Cin * s.Cout;
-  w.wp = take(wn); w.wq = take(wn);
+  size_t wbuf = wn;                                // one packing buffer: [K][N] (CUDA-core kernels) or the hi / lo tiles
+  auto padn = [](int n) { const int bn = tc_bn(n); return (size_t)((n + bn - 1) / bn * bn); };
+  if (tc_eligible(s.Cout, s.Cin)) wbuf = std::max(wbuf, 2 * (size_t)s.k * s.Cin * padn(s.Cout));
+  if (tc_eligible(s.Cin, s.Cout)) wbuf = std::max(wbuf, 2 * (size_t)s.k * s.Cout * padn(s.Cin));
+  w.wp = take(wbuf); w.wq = w.wp;
   w.dz = take((size_t)s.B * s.Tout * s.Cout);
   w.part = take((size_t)wgrad_splits(s) * wn);
   w.cs = take((size_t)CS_MAX_SPLITS * (size_t)((size_t)s.B * s.Cin > (size_t)s.Cout ? (size_t)s.B * s.Cin : (size_t)s.Cout));
-  const int sf = gemm_splits(s.B * s.Tout, s.Cout, s.k * s.Cin), sd = gemm_splits(s.B * s.Tin, s.Cin, s.k * s.Cout);
+  int sf = gemm_splits(s.B * s.Tout, s.Cout, s.k * s.Cin), sd = gemm_splits(s.B * s.Tin, s.Cin, s.k * s.Cout);
+  if (tc_eligible(s.Cout, s.Cin)) sf = tc_splits(s.B * s.Tout, s.Cout, s.k * s.Cin);
+  if (tc_eligible(s.Cin, s.Cout)) sd = tc_splits(s.B * s.Tin, s.Cin, s.k * s.Cout);
   const size_t gf = sf > 1 ? (size_t)sf * s.B * s.Tout * s.Cout : 0, gd = sd > 1 ? (size_t)sd * s.B * s.Tin * s.Cin : 0;
   w.gpart = take(gf > gd ? gf : gd);
   w.total = p;
@@ -462,21 +733,48 @@ Work work_layout(const ConvShape& s) {
 }
 
 // forward (DGRAD = false) or data gradient; returns the number of launches
+// forward (DGRAD = false) or data gradient; `w` = torch-layout weights [Cout][Cin][k], `wbuf` = the packing buffer of the
+// workspace; returns the number of launches
 template <bool DGRAD>
-int launch_conv_gemm(const float* A, const float* Bm, const float* bias, const float* rowbias, float* out, float* pre, float* gpart,
-                     const ConvShape& s, int act, cudaStream_t st) {
-  const int M = DGRAD ? s.B * s.Tin : s.B * s.Tout, N = DGRAD ? s.Cin : s.Cout, K = s.k * (DGRAD ? s.Cout : s.Cin);
+int launch_conv_gemm(const float* A, const float* w, float* wbuf, const float* bias, const float* rowbias, float* out, float* pre,
+                     float* gpart, const ConvShape& s, int act, cudaStream_t st) {
+  const int M = DGRAD ? s.B * s.Tin : s.B * s.Tout, N = DGRAD ? s.Cin : s.Cout, Ca = DGRAD ? s.Cout : s.Cin, K = s.k * Ca;
+  const size_t MN = (size_t)M * N;
+  if (tc_eligible(N, Ca)) {
+    static PerDeviceOnce once;
+    if (once.pending()) {
+      cudaFuncSetAttribute(conv_gemm_tc_kernel<DGRAD, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<64>::SMEM);
+      cudaFuncSetAttribute(conv_gemm_tc_kernel<DGRAD, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<128>::SMEM);
+      once.done();
+    }
+    const int bn = tc_bn(N), Npad = (N + bn - 1) / bn * bn;
+    pack_w_tc_kernel<<<(unsigned)(((size_t)K * Npad + 255) / 256), 256, 0, st>>>(w, wbuf, s.Cin, s.Cout, s.k, DGRAD ? 1 : 0, bn);
+    const int nkb = K / TC_BK;
+    int splits = tc_splits(M, N, K);
+    const int bps = (nkb + splits - 1) / splits;
+    splits = (nkb + bps - 1) / bps;
+    dim3 grid((M + TC_BM - 1) / TC_BM, Npad / bn, splits);
+    if (bn == 64)
+      conv_gemm_tc_kernel<DGRAD, 64><<<grid, TC_THREADS, TcCfg<64>::SMEM, st>>>(A, wbuf, bias, rowbias, out, pre, gpart, s, act, bps);
+    else
+      conv_gemm_tc_kernel<DGRAD, 128><<<grid, TC_THREADS, TcCfg<128>::SMEM, st>>>(A, wbuf, bias, rowbias, out, pre, gpart, s, act, bps);
+    if (splits == 1) return 2;
+    splitk_epilogue_kernel<<<(unsigned)((MN + 255) / 256), 256, 0, st>>>(gpart, DGRAD ? nullptr : bias, out, DGRAD ? nullptr : pre, MN, N,
+                                                                          splits, DGRAD ? ACT_NONE : act);
+    return 3;
+  }
+  const int wn = s.Cout * s.Cin * s.k;
+  pack_w_kernel<<<(wn + 255) / 256, 256, 0, st>>>(w, DGRAD ? nullptr : wbuf, DGRAD ? wbuf : nullptr, s.Cin, s.Cout, s.k);
   const int nks = (K + TK - 1) / TK;
   int splits = gemm_splits(M, N, K);
   const int sps = (nks + splits - 1) / splits;
   splits = (nks + sps - 1) / sps;                              // no empty split
   dim3 grid((M + TM - 1) / TM, (N + TN - 1) / TN, splits);
-  conv_gemm_f32_kernel<DGRAD><<<grid, NTHR, 0, st>>>(A, Bm, bias, rowbias, out, pre, gpart, s, act, sps);
-  if (splits == 1) return 1;
-  const size_t MN = (size_t)M * N;
+  conv_gemm_f32_kernel<DGRAD><<<grid, NTHR, 0, st>>>(A, wbuf, bias, rowbias, out, pre, gpart, s, act, sps);
+  if (splits == 1) return 2;
   splitk_epilogue_kernel<<<(unsigned)((MN + 255) / 256), 256, 0, st>>>(gpart, DGRAD ? nullptr : bias, out, DGRAD ? nullptr : pre, MN, N,
                                                                         splits, DGRAD ? ACT_NONE : act);
-  return 2;
+  return 3;
 }
 
 }  // namespace
@@ -507,9 +805,7 @@ int mgb_conv1d_forward(const float* x, const float* w, const float* bias, const 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   uint8_t* W = static_cast<uint8_t*>(workspace);
   float* wp = reinterpret_cast<float*>(W + wl.wp);
-  const int wn = Cout * Cin * k;
-  pack_w_kernel<<<(wn + 255) / 256, 256, 0, st>>>(w, wp, nullptr, Cin, Cout, k);
-  note_launch(1 + launch_conv_gemm<false>(x, wp, bias, rowbias, y, pre, reinterpret_cast<float*>(W + wl.gpart), s, act, st));
+  note_launch(launch_conv_gemm<false>(x, w, wp, bias, rowbias, y, pre, reinterpret_cast<float*>(W + wl.gpart), s, act, st));
   MGB_LAUNCH_CHECK();
   return MGB_OK;
 }
@@ -530,7 +826,6 @@ int mgb_conv1d_backward(const float* x, const float* w, const float* rowbias, co
   MGB_REQUIRE(workspace_bytes >= wl.total, MGB_E_WORKSPACE, "workspace too small: %zu < %zu", workspace_bytes, wl.total);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   uint8_t* W = static_cast<uint8_t*>(workspace);
-  float* wp = reinterpret_cast<float*>(W + wl.wp);
   float* wq = reinterpret_cast<float*>(W + wl.wq);
   float* dzb = reinterpret_cast<float*>(W + wl.dz);
   float* part = reinterpret_cast<float*>(W + wl.part);
@@ -544,8 +839,7 @@ int mgb_conv1d_backward(const float* x, const float* w, const float* rowbias, co
   }
   const int wn = Cout * Cin * k;
   if (grad_x) {
-    pack_w_kernel<<<(wn + 255) / 256, 256, 0, st>>>(w, wp, wq, Cin, Cout, k);
-    launches += 1 + launch_conv_gemm<true>(dz, wq, nullptr, nullptr, grad_x, nullptr, reinterpret_cast<float*>(W + wl.gpart), s, ACT_NONE, st);
+    launches += launch_conv_gemm<true>(dz, w, wq, nullptr, nullptr, grad_x, nullptr, reinterpret_cast<float*>(W + wl.gpart), s, ACT_NONE, st);
     if (grad_rowbias) {
       // d rowbias[b][ci] = sum over the rows of utterance b of grad_x: exact, because every existing input row carries
       // the bias once and grad_x is the gradient with respect to (x + rowbias)

@@ -262,6 +262,20 @@ __host__ __device__ constexpr uint32_t make_idesc_16(int M, int N, bool fp16) {
          | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
 }
 
+// kind::tf32: 4-byte operands (the tensor core reads sign, exponent and the top 10 mantissa bits), fp32 accumulate, K = 8 per
+// instruction = 32 bytes per operand row: the shared-memory descriptors are the kind::f16 ones byte for byte (a core matrix is
+// 8 rows x 16 bytes = 8 x 4 tf32).  Half the kind::f16 rate.
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 }  // namespace tc
 
 // =====================================================================================================

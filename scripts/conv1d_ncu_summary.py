@@ -2,12 +2,12 @@
 import csv, re, sys
 lines = [l for l in open(sys.argv[1]) if not l.startswith("==")]
 rows = [(r["Kernel Name"], r["Grid Size"], float(r["Metric Value"]) / 1000) for r in csv.DictReader(lines)]
-pat = re.compile(r"(conv_gemm_f32_kernel<.>|conv_wgrad_f32_kernel|wgrad_reduce_f32_kernel|splitk_epilogue_kernel|colsum_\w+|act_bwd_kernel|pack_w_kernel)")
+pat = re.compile(r"(conv_gemm_f32_kernel<.>|conv_gemm_tc_kernel<[^>]*>|conv_wgrad_f32_kernel|wgrad_reduce_f32_kernel|splitk_epilogue_kernel|colsum_\w+|act_bwd_kernel|pack_w_tc_kernel|pack_w_kernel)")
 lib = [(pat.search(n).group(1), g, t) for n, g, t in rows if pat.search(n)]
 # split into layers x iterations at every forward conv_gemm<0>
 iters, cur = [], []
 for k in lib:
-    if k[0] == "pack_w_kernel" and cur and any(c[0] == "conv_gemm_f32_kernel<0>" for c in cur) and any(c[0].startswith("conv_wgrad") for c in cur):
+    if k[0] in ("pack_w_kernel", "pack_w_tc_kernel") and cur and any((c[0] == "conv_gemm_f32_kernel<0>" or c[0].startswith("conv_gemm_tc_kernel<0")) for c in cur) and any(c[0].startswith("conv_wgrad") for c in cur):
         iters.append(cur); cur = []
     cur.append(k)
 iters.append(cur)

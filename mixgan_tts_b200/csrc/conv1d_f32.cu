@@ -237,8 +237,8 @@ __global__ void splitk_epilogue_kernel(const float* __restrict__ part, const flo
 //     stored as K-major core matrices (8 rows x 16 bytes; per 4-channel group the 128 rows are one dense [128][16 B] array,
 //     SBO = 128 B, LBO = 2 KB + 16 B).
 //   B operand: the weights, split and tiled ONCE per call by pack_w_tc_kernel into exactly the shared-memory image of a
-//     (64-column tile, k-block) pair — hi then lo, 16 KB — so one cp.async.bulk per k-block brings it (3-slot ring, issued
-//     one k-block ahead by thread 0, completion on the slot's mbarrier).  (Staging B with the threads as well took 480
+//     (64-column tile, k-block) pair — hi then lo, 16 KB — so one cp.async.bulk per k-block brings it (4-slot ring, issued
+//     two k-blocks ahead, completion on the slot's mbarrier).  (Staging B with the threads as well took 480
 //     instructions per warp and k-block at 7.5 stall cycles each: ncu, profiles/r02.)
 // Warp-specialised, no CTA-wide barrier in the loop: 128 staging threads (their global loads run two k-blocks ahead in
 // registers) publish an A stage through an mbarrier; one thread of a fifth warp issues the B copies and the MMAs as soon as
@@ -249,12 +249,13 @@ constexpr int TC_BM = 128, TC_BK = 32, TC_THREADS = 160;    // 4 staging / epilo
 constexpr int TC_A_LBO = TC_BM * 16 + 16;                   // + 16 B, so the 8 channel groups of a row hit 8 bank groups
 constexpr int TC_A_BYTES = 8 * TC_A_LBO;                    // one of hi / lo: 16.1 KB
 constexpr int TC_A_STAGE = 2 * TC_A_BYTES;                  // hi + lo
-constexpr int TC_NA = 2, TC_NB = 3;
+constexpr int TC_NA = 2, TC_NB = 4;                         // B copies run two k-blocks ahead: a 32 KB bulk copy from L2 takes
+                                                            // ~2 000 cycles; one k-block ahead it paced the whole loop (1.1 us per k-block)
 // column tile BN = 128 (64 for narrow outputs): a tcgen05.mma costs the issuing thread ~300 cycles whatever its size (twelve
 // N = 64 MMAs per k-block were 3 800 cycles, the whole loop time), so the tile is as wide as shared memory allows
 template <int BN> struct TcCfg {
   static constexpr int B_LBO = BN * 16, B_BYTES = 8 * B_LBO, B_STAGE = 2 * B_BYTES;      // BN = 128: 32 KB per slot
-  static constexpr int SMEM = TC_NA * TC_A_STAGE + TC_NB * B_STAGE + 128;                // 162 KB (BN = 128), 113 KB (64)
+  static constexpr int SMEM = TC_NA * TC_A_STAGE + TC_NB * B_STAGE + 128;                // 194 KB (BN = 128), 130 KB (64)
 };
 constexpr long long TC_TIMEOUT = 400000000LL;
 
@@ -297,9 +298,9 @@ __global__ void __launch_bounds__(TC_THREADS) conv_gemm_tc_kernel(const float* _
   uint64_t* bars = reinterpret_cast<uint64_t*>(tc_smem + TC_NA * TC_A_STAGE + TC_NB * TC_B_STAGE);
   uint64_t* bar_free = bars;               // [2] the tensor core has read A stage i (and the B slot used with it)
   uint64_t* bar_afull = bars + 2;          // [2] all 128 staging threads have written A stage i
-  uint64_t* bar_bfull = bars + 4;          // [3] B slot landed
-  uint64_t* bar_done = bars + 7;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* bar_bfull = bars + 4;          // [4] B slot landed
+  uint64_t* bar_done = bars + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
   const int tid = threadIdx.x, warp = tid >> 5;
   const int m0 = blockIdx.x * TC_BM, n0 = blockIdx.y * TC_BN;
   const int rows_per_b = DGRAD ? s.Tin : s.Tout, src_per_b = DGRAD ? s.Tout : s.Tin;
@@ -331,18 +332,20 @@ __global__ void __launch_bounds__(TC_THREADS) conv_gemm_tc_kernel(const float* _
       constexpr uint32_t IDESC = tc::make_idesc_tf32(TC_BM, TC_BN);
       const uint32_t smA_u = tc::smem_u32(smA), smB_u = tc::smem_u32(smB);
       if (tc::elect_one()) {
-        tc::mbar_arrive_expect_tx(&bar_bfull[0], TC_B_STAGE);
-        tc::bulk_g2s(smB, btile, TC_B_STAGE, &bar_bfull[0]);
+        for (int i = 0; i < 2 && i < nkb; ++i) {
+          tc::mbar_arrive_expect_tx(&bar_bfull[i], TC_B_STAGE);
+          tc::bulk_g2s(smB + i * TC_B_STAGE, btile + (size_t)i * (TC_B_STAGE / 4), TC_B_STAGE, &bar_bfull[i]);
+        }
       }
       for (int it = 0; it < nkb; ++it) {
         const int stage = it & 1, slot = it % TC_NB;
-        if (it + 1 < nkb) {
-          // B slot (it + 1) % 3 was read by the MMAs of k-block it - 2
+        if (it + 2 < nkb) {
+          // B slot (it + 2) % 4 was read by the MMAs of k-block it - 2
           if (it >= 2 && !tc::mbar_wait(&bar_free[stage], ((it >> 1) + 1) & 1, TC_TIMEOUT)) __trap();
-          const int ns = (it + 1) % TC_NB;
+          const int ns = (it + 2) % TC_NB;
           if (tc::elect_one()) {
             tc::mbar_arrive_expect_tx(&bar_bfull[ns], TC_B_STAGE);
-            tc::bulk_g2s(smB + ns * TC_B_STAGE, btile + (size_t)(it + 1) * (TC_B_STAGE / 4), TC_B_STAGE, &bar_bfull[ns]);
+            tc::bulk_g2s(smB + ns * TC_B_STAGE, btile + (size_t)(it + 2) * (TC_B_STAGE / 4), TC_B_STAGE, &bar_bfull[ns]);
           }
         }
         if (!tc::mbar_wait(&bar_afull[stage], (it >> 1) & 1, TC_TIMEOUT)) __trap();
@@ -699,13 +702,13 @@ int gemm_splits(int M, int N, int K) {
   return want < 1 ? 1 : (want > 16 ? 16 : want);
 }
 // tensor-core plan: 128 x BN tiles (BN = 128, or 64 for outputs of at most 64 columns), 32-deep k-blocks; split K until
-// about one CTA per SM exists (two for BN = 64, which fit an SM together), at least 4 k-blocks per split
+// about one CTA per SM exists, at least 4 k-blocks per split
 bool tc_eligible(int N, int Ca) { return Ca % TC_BK == 0 && N % 4 == 0 && N >= 16; }
 int tc_bn(int N) { return N > 64 ? 128 : 64; }
 int tc_splits(int M, int N, int K) {
   const int bn = tc_bn(N);
   const int tiles = ((M + TC_BM - 1) / TC_BM) * ((N + bn - 1) / bn), nkb = K / TC_BK;
-  int want = (bn == 64 ? 296 : 148) / tiles;
+  int want = 148 / tiles;
   if (want > nkb / 4) want = nkb / 4;
   return want < 1 ? 1 : (want > 16 ? 16 : want);
 }

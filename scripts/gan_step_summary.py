@@ -22,7 +22,7 @@ def short(n):
     return re.sub(r"\(.*", "", n)[:78]
 
 
-DISC = ("conv_gemm_f32", "conv_wgrad_f32", "wgrad_reduce_f32", "splitk_epilogue", "colsum_part", "colsum_final", "act_bwd", "pack_w_kernel", "step_embedding")
+DISC = ("conv_gemm_f32", "conv_gemm_tc", "pack_w_tc", "conv_wgrad_f32", "wgrad_reduce_f32", "splitk_epilogue", "colsum_part", "colsum_final", "act_bwd", "pack_w_kernel", "step_embedding")
 agg = collections.OrderedDict()
 for n, g, t in seg:
     k = short(n)

@@ -229,7 +229,9 @@ int mgb_mask_from_lengths(const int64_t* lengths, uint8_t* mask_valid, int B, in
  * Generic fp32 Conv1d on frames-major activations, forward and backward: the building block of the JCU discriminator
  * (reference model/mixgantts.py:186-288 - ConvNorm model/blocks.py:326-371 with stride 1 or 2 and
  * padding (k-1)/2, LinearNorm (k = 1), F.leaky_relu(., 0.2), Mish - driven 4x forward + 2x backward per training step by
- * train.py:126-184).  Exact fp32 on the CUDA cores: the reference's gradients are the parity target (1e-4).
+ * train.py:126-184).  fp32 accuracy throughout — the reference's gradients are the parity target (1e-4): forward and data
+ * gradient run on the tensor cores as 3 x TF32 (hi / lo operand split, fp32 accumulation; channel counts that are multiples of
+ * 32), everything else, and the weight gradient, as exact-fp32 CUDA-core kernels.
  *   x [B][Tin][Cin], y / pre / grad_y [B][Tout][Cout] with Tout = mgb_conv1d_out_len(Tin, k, stride); one row per frame.
  *   w       : [Cout][Cin][k], the torch layout (a Linear weight [out][in] is k = 1); bias [Cout] or NULL
  *   rowbias : [B][Cin] or NULL - added to every EXISTING input row before the convolution (padding rows stay zero):

@@ -9,7 +9,8 @@ Same constructor arguments, parameter names / shapes / ``state_dict`` keys and `
 Every layer (Linear or strided Conv1d + bias + leaky_relu / Mish, and the "x + diffusion_step (+ speaker)" add fused into
 the first conditional convolution's operand gather) is one ``torch.autograd.Function`` over ``mgb_conv1d_forward`` /
 ``mgb_conv1d_backward`` on frames-major ``[B, T, C]`` fp32 tensors; torch autograd only chains the nodes.  The returned
-feature lists hold ``[B, C, T']`` views, as the reference's do.  Exact fp32 (the reference's gradients are the parity target).
+feature lists hold ``[B, C, T']`` views, as the reference's do.  fp32 accuracy (3 x TF32 tensor-core or exact-fp32
+CUDA-core kernels, csrc/conv1d_f32.cu): the reference's gradients are the parity target.
 """
 from __future__ import annotations
 

@@ -722,7 +722,7 @@ int tc_splits(int M, int N, int K) {
   if (want > nkb / 4) want = nkb / 4;
   return want < 1 ? 1 : (want > 16 ? 16 : want);
 }
-struct Work { size_t wp, wq, dz, part, cs, gpart, total; };
+struct Work { size_t wp, wq, dz, part, cs, cs2, gpart, total; };
 Work work_layout(const ConvShape& s) {
   Work w{};
   size_t p = 0;
@@ -736,6 +736,7 @@ Work work_layout(const ConvShape& s) {
   w.dz = take((size_t)s.B * s.Tout * s.Cout);
   w.part = take((size_t)wgrad_splits(s) * wn);
   w.cs = take((size_t)CS_MAX_SPLITS * (size_t)((size_t)s.B * s.Cin > (size_t)s.Cout ? (size_t)s.B * s.Cin : (size_t)s.Cout));
+  w.cs2 = take((size_t)CS_MAX_SPLITS * (size_t)s.Cout);          // the bias column sum runs beside the rowbias one (side stream)
   int sf = gemm_splits(s.B * s.Tout, s.Cout, s.k * s.Cin), sd = gemm_splits(s.B * s.Tin, s.Cin, s.k * s.Cout);
   if (tc_eligible(s.Cout, s.Cin)) sf = tc_splits(s.B * s.Tout, s.Cout, s.k * s.Cin);
   if (tc_eligible(s.Cin, s.Cout)) sd = tc_splits(s.B * s.Tin, s.Cin, s.k * s.Cout);
@@ -788,6 +789,25 @@ int launch_conv_gemm(const float* A, const float* w, float* wbuf, const float* b
   splitk_epilogue_kernel<<<(unsigned)((MN + 255) / 256), 256, 0, st>>>(gpart, DGRAD ? nullptr : bias, out, DGRAD ? nullptr : pre, MN, N,
                                                                         splits, DGRAD ? ACT_NONE : act);
   return 3;
+}
+
+// The backward of a layer is two independent halves once dz exists: the data gradient (tensor cores, what the previous layer's
+// backward waits for) and the weight / bias gradients (CUDA cores).  With both requested, the second half runs on a
+// library-owned side stream (one per device, created at first use), forked and joined by events inside the call — the caller's
+// stream sees finished gradients when the call's work completes, and inside a CUDA-graph capture the fork/join become edges.
+struct ConvSide { cudaStream_t s = nullptr; cudaEvent_t fork = nullptr, join = nullptr; };
+ConvSide* conv_side() {
+  static ConvSide ctx[256];
+  static PerDeviceOnce once;
+  const int dev = PerDeviceOnce::current();
+  if (once.pending()) {
+    ConvSide& c = ctx[dev];
+    if (cudaStreamCreateWithFlags(&c.s, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&c.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&c.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    once.done();
+  }
+  return &ctx[dev];
 }
 
 }  // namespace
@@ -851,6 +871,25 @@ int mgb_conv1d_backward(const float* x, const float* w, const float* rowbias, co
     ++launches;
   }
   const int wn = Cout * Cin * k;
+  ConvSide* side = (grad_x && (grad_w || grad_bias)) ? conv_side() : nullptr;
+  cudaStream_t ss = side ? side->s : st;                    // stream of the weight / bias gradient half
+  if (side) {
+    MGB_CUDA_CHECK(cudaEventRecord(side->fork, st));
+    MGB_CUDA_CHECK(cudaStreamWaitEvent(ss, side->fork, 0));
+  }
+  if (grad_w) {
+    const int splits = wgrad_splits(s);
+    const int M = B * s.Tout;
+    const int rows_per_split = ((M + splits - 1) / splits + TK - 1) / TK * TK;
+    dim3 grid((k * Cin + TM - 1) / TM, (Cout + TN - 1) / TN, splits);
+    conv_wgrad_f32_kernel<<<grid, NTHR, 0, ss>>>(x, rowbias, dz, part, s, rows_per_split);
+    wgrad_reduce_f32_kernel<<<(wn + 255) / 256, 256, 0, ss>>>(part, grad_w, Cin, Cout, k, splits);
+    launches += 2;
+  }
+  if (grad_bias) {
+    launch_colsum(dz, grad_bias, reinterpret_cast<float*>(W + wl.cs2), 1, B * s.Tout, Cout, ss);
+    launches += 2;
+  }
   if (grad_x) {
     launches += launch_conv_gemm<true>(dz, w, wq, nullptr, nullptr, grad_x, nullptr, reinterpret_cast<float*>(W + wl.gpart), s, ACT_NONE, st);
     if (grad_rowbias) {
@@ -860,18 +899,9 @@ int mgb_conv1d_backward(const float* x, const float* w, const float* rowbias, co
       launches += 2;
     }
   }
-  if (grad_w) {
-    const int splits = wgrad_splits(s);
-    const int M = B * s.Tout;
-    const int rows_per_split = ((M + splits - 1) / splits + TK - 1) / TK * TK;
-    dim3 grid((k * Cin + TM - 1) / TM, (Cout + TN - 1) / TN, splits);
-    conv_wgrad_f32_kernel<<<grid, NTHR, 0, st>>>(x, rowbias, dz, part, s, rows_per_split);
-    wgrad_reduce_f32_kernel<<<(wn + 255) / 256, 256, 0, st>>>(part, grad_w, Cin, Cout, k, splits);
-    launches += 2;
-  }
-  if (grad_bias) {
-    launch_colsum(dz, grad_bias, reinterpret_cast<float*>(W + wl.cs), 1, B * s.Tout, Cout, st);
-    launches += 2;
+  if (side) {
+    MGB_CUDA_CHECK(cudaEventRecord(side->join, ss));
+    MGB_CUDA_CHECK(cudaStreamWaitEvent(st, side->join, 0));
   }
   note_launch(launches);
   MGB_LAUNCH_CHECK();

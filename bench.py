@@ -650,6 +650,7 @@ def bench_train(ctx, prec, steps, warmup, B):
     T = T_FRAMES
     gd = make_gd(ctx, "LJSpeech", "naive", False, prec, train=True)
     K = gd.num_timesteps
+    torch.manual_seed(1234 + ctx.rank)          # the training branch draws t and three noises per call: reproducible runs
     opt = torch.optim.Adam(gd.denoise_fn.parameters(), lr=1e-5, fused=True, capturable=True)
     sync = GradSync() if ctx.world > 1 else None
     NSETS = 3
@@ -737,9 +738,16 @@ def bench_train(ctx, prec, steps, warmup, B):
         c, u = D(torch.cat([x_ts, x_ts]), torch.cat([x_fake_prev, x_real_prev]), None, torch.cat([t, t]))
         return [f[:n] for f in c], [f[:n] for f in u], [f[n:] for f in c], [f[n:] for f in u]
 
+    # The G phase's generator forward depends on nothing the D phase's discriminator work produces (same generator weights,
+    # its own random draws, which follow the D-phase forward's in the reference's order too): it is enqueued on a second
+    # stream beside the D phase's discriminator forward / backward / Adam and joined before the G phase's discriminator call.
+    OVERLAP = not UNBATCHED and not os.environ.get("MIXGAN_B200_BENCH_GAN_NO_OVERLAP")
+    g_stream = torch.cuda.Stream(dev) if OVERLAP else None
+
     def gan_step(i, with_sync=True, s=None):
         s = s if s is not None else sets[i % NSETS]
         valid = (~s["pad"]).unsqueeze(-1)
+        cur = torch.cuda.current_stream(dev)
         # D phase (train.py:126-146)
         gd.denoise_fn.grad_sync = None
         if UNBATCHED:
@@ -748,6 +756,12 @@ def bench_train(ctx, prec, steps, warmup, B):
             with torch.no_grad():
                 out = gd(s["mel"], s["cond"], None, s["pad"])
         x_ts, x_prev, x_pred, t = [o.detach() for o in out[1:5]]
+        out_g = None
+        if OVERLAP:
+            gd.denoise_fn.grad_sync = sync if with_sync else None
+            g_stream.wait_stream(cur)
+            with torch.cuda.stream(g_stream):
+                out_g = gd(s["mel"], s["cond"].detach().requires_grad_(True), None, s["pad"])
         fc, fu, rc, ru = d_pair(x_ts, x_pred, x_prev, t)
         r_loss, f_loss = d_loss_fn(rc[-1], ru[-1], fc[-1], fu[-1])
         (r_loss + f_loss).backward()
@@ -758,7 +772,11 @@ def bench_train(ctx, prec, steps, warmup, B):
         optD.zero_grad(set_to_none=False)
         # G phase (train.py:148-184)
         gd.denoise_fn.grad_sync = sync if with_sync else None
-        out = gd(s["mel"], s["cond"].detach().requires_grad_(True), None, s["pad"])
+        if OVERLAP:
+            cur.wait_stream(g_stream)
+            out = out_g
+        else:
+            out = gd(s["mel"], s["cond"].detach().requires_grad_(True), None, s["pad"])
         fc, fu, rc, ru = d_pair(out[1], out[3], out[2], out[4])
         adv = g_loss_fn(fc[-1], fu[-1])
         mel_loss = torch.nn.functional.l1_loss(gd.denorm_spec(out[0]) * valid, s["mel"] * valid)   # model/loss.py:175-176,229-234
@@ -809,8 +827,9 @@ def bench_train(ctx, prec, steps, warmup, B):
         except Exception as e:
             den_graph_note = f"CUDA-graph capture failed ({type(e).__name__}: {str(e)[:160]}); eager step timed"
             torch.cuda.synchronize(dev)
-    for i in range(max(warmup, 3)):
-        gan_step(i)
+    # adversarial loss of the first (warm-up) steps: a fingerprint of the whole update sequence (same seeds => same values
+    # whatever the scheduling: MIXGAN_B200_BENCH_GAN_NO_OVERLAP=1 / _UNBATCHED=1 must reproduce them to fp32 rounding)
+    first_adv = [float(gan_step(i)) for i in range(max(warmup, 3))]
     n0 = lib.mgb_launch_count()
     ms_gan_eager = ctx.timed(gan_step, steps, 0)
     launches_gan = (lib.mgb_launch_count() - n0) // max(steps, 1)
@@ -844,10 +863,11 @@ def bench_train(ctx, prec, steps, warmup, B):
                         + ("the two discriminator calls of a phase run separately and the D-phase generator forward keeps its stash"
                            if UNBATCHED else
                            "the two discriminator calls of a phase run as one call on the 2B-utterance batch [fake | real] (same losses and "
-                           "gradients) and the D-phase generator forward, whose outputs train.py detaches, runs with autograd off"),
+                           "gradients) and the D-phase generator forward, whose outputs train.py detaches, runs with autograd off"
+                           + ("; the G-phase generator forward runs on a second stream beside the D phase's discriminator work" if OVERLAP else "")),
             "tflops": flops_gan * steps / (ms_gan * 1e-3) / 1e12,
             "allreduce_exposed_ms_per_step": (ms_gan_eager - ms_gan_nosync) / steps,
-            "eager_ms_per_step": ms_gan_eager / steps, "cuda_graph": graph_note,
+            "eager_ms_per_step": ms_gan_eager / steps, "cuda_graph": graph_note, "warmup_adv_losses": first_adv,
             "grad_bytes": int(lib.mgb_flat_weight_count(C.byref(gd.denoise_fn.dims))) * 4 + sum(p.numel() for p in d_params) * 4,
             "denoiser_only": {"ms_per_step": ms / steps, "value": frames * steps / (ms * 1e-3), "tflops": flops * steps / (ms * 1e-3) / 1e12,
                               "eager_ms_per_step": ms_eager / steps, "cuda_graph": den_graph_note,

@@ -31,7 +31,12 @@
  *     densely packed row-major arrays unless a parameter says "host".
  *   - The caller owns every buffer (inputs, outputs, packed weights, workspace).  The library
  *     never allocates or frees caller-visible memory and never synchronises the device; all work
- *     is enqueued on `stream` (a cudaStream_t passed as void*).
+ *     is enqueued on `stream` (a cudaStream_t passed as void*).  Two training entry points
+ *     (mgb_denoiser_backward in the bf16 mode, mgb_conv1d_backward) run the half of their work
+ *     that nothing downstream waits for on a library-owned side stream (one non-blocking stream
+ *     and a few events per device, created at first use): it is forked from and joined back to
+ *     `stream` by events INSIDE the call, so the caller still sees plain stream semantics (and a
+ *     CUDA-graph capture of `stream` records the fork / join as edges).
  *   - Return value: 0 = OK, negative = error (MGB_E_*); mgb_last_error() returns a thread-local
  *     message.  Nothing throws across the ABI.
  *   - There is no CPU fallback: on a device that is not sm_100 every compute entry point

@@ -228,8 +228,132 @@ __global__ void __launch_bounds__(EW_THREADS) denorm_mask_kernel(const float* __
   }
 }
 
+// ---- register-transpose forms of the two kernels above (T % 4 == 0, n_mel % 4 == 0, 16-byte aligned pointers) ----------
+// A thread owns a 4 (mel) x 4 (frames) block: four 16-byte loads along one axis, a transpose in registers, four 16-byte
+// stores along the other — no shared memory, no barrier, no bank conflicts.  Lane = (mb = lane & 7, tb = lane >> 3): a warp
+// covers 32 mel bins x 16 frames, so a warp-wide access on the [frames][mel] side is 4 rows x 128 contiguous bytes and on the
+// [mel][frames] side 8 rows x 64 contiguous bytes: full 32-byte sectors both ways.  A warp walks two 16-frame chunks (eight
+// independent loads in flight per thread per operand).  Same arithmetic, operation by operation, as the tiled kernels.
+constexpr int RT_THREADS = 256, RT_FRAMES = 32;       // frames per warp task
+
+// task = (utterance b, 32-frame chunk, 32-mel group); tasks are enumerated mel-group fastest
+__device__ __forceinline__ bool rt_task(int B, int T, int M, int frames, int& b, int& t_base, int& m0, int& tb) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nmg = (M + 31) / 32, nch = (T + frames - 1) / frames;
+  const long long task = (long long)blockIdx.x * (RT_THREADS / 32) + warp;
+  if (task >= (long long)B * nch * nmg) return false;
+  const int mg = (int)(task % nmg);
+  const long long r = task / nmg;
+  const int ch = (int)(r % nch);
+  b = (int)(r / nch);
+  t_base = ch * frames;
+  m0 = mg * 32 + (lane & 7) * 4;
+  tb = lane >> 3;
+  return m0 < M;
+}
+
+template <int NH>
+__global__ void __launch_bounds__(RT_THREADS) denorm_mask_rt_kernel(const float* __restrict__ x, const float* __restrict__ smin,
+                                                                    const float* __restrict__ smax, const uint8_t* __restrict__ pad,
+                                                                    float* __restrict__ mel, int B, int M, int T) {
+  int b, t_base, m0, tb;
+  if (!rt_task(B, T, M, 16 * NH, b, t_base, m0, tb)) return;
+  float4 v[NH][4];
+  int t0[NH];
+#pragma unroll
+  for (int h = 0; h < NH; ++h) {
+    t0[h] = t_base + tb * 4 * NH + h * 4;     // a thread owns 4 NH consecutive frames
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+      v[h][r] = t0[h] < T ? __ldg(reinterpret_cast<const float4*>(x + ((size_t)b * M + m0 + r) * T + t0[h])) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  const float4 lo = __ldg(reinterpret_cast<const float4*>(smin + m0)), hi = __ldg(reinterpret_cast<const float4*>(smax + m0));
+  const float span[4] = {__fsub_rn(hi.x, lo.x), __fsub_rn(hi.y, lo.y), __fsub_rn(hi.z, lo.z), __fsub_rn(hi.w, lo.w)};
+  const float lov[4] = {lo.x, lo.y, lo.z, lo.w};
+#pragma unroll
+  for (int h = 0; h < NH; ++h) {
+    if (t0[h] >= T) continue;
+    uint32_t pm = 0u;
+    if (pad) pm = *reinterpret_cast<const uint32_t*>(pad + (size_t)b * T + t0[h]);      // 4 mask bytes (T % 4 == 0)
+    const float in[4][4] = {{v[h][0].x, v[h][0].y, v[h][0].z, v[h][0].w}, {v[h][1].x, v[h][1].y, v[h][1].z, v[h][1].w},
+                            {v[h][2].x, v[h][2].y, v[h][2].z, v[h][2].w}, {v[h][3].x, v[h][3].y, v[h][3].z, v[h][3].w}};   // [r][e]
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float valid = ((pm >> (8 * e)) & 0xFFu) ? 0.f : 1.f;
+      float o[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+        o[r] = __fadd_rn(__fmul_rn(__fmul_rn(__fadd_rn(in[r][e], 1.f), 0.5f), span[r]), lov[r]) * valid;
+      *reinterpret_cast<float4*>(mel + ((size_t)b * T + t0[h] + e) * M + m0) = make_float4(o[0], o[1], o[2], o[3]);
+    }
+  }
+}
+
+template <int NH>
+__global__ void __launch_bounds__(RT_THREADS) shallow_start_rt_kernel(const float* __restrict__ coarse, const float* __restrict__ noise,
+                                                                      const float* __restrict__ smin, const float* __restrict__ smax,
+                                                                      float sa, float sn, const uint8_t* __restrict__ pad,
+                                                                      float* __restrict__ xT, int B, int M, int T) {
+  int b, t_base, m0, tb;
+  if (!rt_task(B, T, M, 16 * NH, b, t_base, m0, tb)) return;
+  float4 c[NH][4], nz[NH][4];
+  int t0[NH];
+#pragma unroll
+  for (int h = 0; h < NH; ++h) {
+    t0[h] = t_base + tb * 4 * NH + h * 4;     // a thread owns 4 NH consecutive frames
+    const bool in = t0[h] < T;
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+      c[h][e] = in ? __ldg(reinterpret_cast<const float4*>(coarse + ((size_t)b * T + t0[h] + e) * M + m0)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+      nz[h][r] = in ? __ldg(reinterpret_cast<const float4*>(noise + ((size_t)b * M + m0 + r) * T + t0[h])) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  const float4 lo = __ldg(reinterpret_cast<const float4*>(smin + m0)), hi = __ldg(reinterpret_cast<const float4*>(smax + m0));
+  const float span[4] = {__fsub_rn(hi.x, lo.x), __fsub_rn(hi.y, lo.y), __fsub_rn(hi.z, lo.z), __fsub_rn(hi.w, lo.w)};
+  const float lov[4] = {lo.x, lo.y, lo.z, lo.w};
+#pragma unroll
+  for (int h = 0; h < NH; ++h) {
+    if (t0[h] >= T) continue;
+    uint32_t pm = 0u;
+    if (pad) pm = *reinterpret_cast<const uint32_t*>(pad + (size_t)b * T + t0[h]);
+    const float cv[4][4] = {{c[h][0].x, c[h][0].y, c[h][0].z, c[h][0].w}, {c[h][1].x, c[h][1].y, c[h][1].z, c[h][1].w},
+                            {c[h][2].x, c[h][2].y, c[h][2].z, c[h][2].w}, {c[h][3].x, c[h][3].y, c[h][3].z, c[h][3].w}};   // [e][r]
+    const float nv[4][4] = {{nz[h][0].x, nz[h][0].y, nz[h][0].z, nz[h][0].w}, {nz[h][1].x, nz[h][1].y, nz[h][1].z, nz[h][1].w},
+                            {nz[h][2].x, nz[h][2].y, nz[h][2].z, nz[h][2].w}, {nz[h][3].x, nz[h][3].y, nz[h][3].z, nz[h][3].w}};   // [r][e]
+    float valid[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) valid[e] = ((pm >> (8 * e)) & 0xFFu) ? 0.f : 1.f;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      float o[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float nrm = __fsub_rn(__fmul_rn(__fdiv_rn(__fsub_rn(cv[e][r], lov[r]), span[r]), 2.f), 1.f);
+        o[e] = __fadd_rn(__fmul_rn(sa, nrm), __fmul_rn(sn, nv[r][e])) * valid[e];
+      }
+      *reinterpret_cast<float4*>(xT + ((size_t)b * M + m0 + r) * T + t0[h]) = make_float4(o[0], o[1], o[2], o[3]);
+    }
+  }
+}
+
+inline bool rt_ok(int M, int T, const void* a, const void* b2, const void* c2, const void* d, const void* e) {
+  return (M & 3) == 0 && (T & 3) == 0 &&
+         ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b2) | reinterpret_cast<uintptr_t>(c2) |
+           reinterpret_cast<uintptr_t>(d) | reinterpret_cast<uintptr_t>(e)) & 15) == 0;
+}
+inline unsigned rt_blocks(int B, int M, int T, int frames = RT_FRAMES) {
+  const long long tasks = (long long)B * ((T + frames - 1) / frames) * ((M + 31) / 32);
+  return (unsigned)((tasks + RT_THREADS / 32 - 1) / (RT_THREADS / 32));
+}
+
 static void launch_denorm_mask(const float* x, const float* smin, const float* smax, const uint8_t* pad, float* mel, int B, int M,
                                int T, cudaStream_t s) {
+  if (rt_ok(M, T, x, smin, smax, mel, pad && (reinterpret_cast<uintptr_t>(pad) & 3) ? reinterpret_cast<const void*>(1) : nullptr)) {
+    denorm_mask_rt_kernel<1><<<rt_blocks(B, M, T, 16), RT_THREADS, 0, s>>>(x, smin, smax, pad, mel, B, M, T);
+    note_launch();
+    return;
+  }
   dim3 grid((T + EW_TF - 1) / EW_TF, B), block(EW_THREADS);
   if (M == 80) denorm_mask_kernel<80><<<grid, block, 0, s>>>(x, smin, smax, pad, mel, M, T);
   else denorm_mask_kernel<0><<<grid, block, 0, s>>>(x, smin, smax, pad, mel, M, T);
@@ -630,6 +754,13 @@ int mgb_shallow_start(const float* coarse, const float* noise, const float* spec
   MGB_REQUIRE(B > 0 && T > 0 && n_mel > 0, MGB_E_ARG, "bad shape");
   if (int rc = check_arch()) return rc;
   MGB_REQUIRE(n_mel <= EW_MAXM, MGB_E_UNSUPPORTED, "n_mel %d > %d", n_mel, EW_MAXM);
+  if (rt_ok(n_mel, T, coarse, noise, x_T, spec_min, spec_max) && !(pad_mask && (reinterpret_cast<uintptr_t>(pad_mask) & 3))) {
+    shallow_start_rt_kernel<1><<<rt_blocks(B, n_mel, T, 16), RT_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
+        coarse, noise, spec_min, spec_max, sqrt_acp, sqrt_1m_acp, pad_mask, x_T, B, n_mel, T);
+    note_launch();
+    MGB_LAUNCH_CHECK();
+    return MGB_OK;
+  }
   dim3 grid((T + EW_TF - 1) / EW_TF, B), block(EW_THREADS);
   if (n_mel == 80)
     shallow_start_kernel<80><<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(

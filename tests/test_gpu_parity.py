@@ -339,6 +339,39 @@ def test_shallow_start_and_denorm_elementwise_exact():
     assert torch.allclose(mel.cpu(), ref, rtol=0, atol=2e-6)
 
 
+@pytest.mark.parametrize("B,T", [(2, 800), (3, 132), (1, 16), (2, 20), (2, 130), (1, 7)])
+def test_elementwise_kernels_bitwise_vs_torch_expressions(B, T):
+    """mgb_shallow_start / mgb_denorm_mask against the torch expressions of diffusion.py:147-153, 177-185, 228-232 evaluated
+    in fp32 on the GPU, bit for bit, on both code paths: the register-transpose kernels (T % 4 == 0) and the tiled ones
+    (ragged T), with a padding mask."""
+    lib = _lib.load()
+    M = 80
+    g = torch.Generator().manual_seed(B * 1000 + T)
+    coarse = (torch.randn(B, T, M, generator=g) * 2 - 5).cuda()
+    noise = torch.randn(B, 1, M, T, generator=g).cuda()
+    lens = torch.tensor([max(1, T - 5 * i) for i in range(B)])
+    pad = (torch.arange(T)[None, :] >= lens[:, None]).cuda()
+    smin = (torch.rand(M, generator=g) * 2 - 12).cuda()
+    smax = (torch.rand(M, generator=g) * 2 + 1).cuda()
+    sa, sn = 0.8123456, 0.5831234
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    xT = torch.empty((B, 1, M, T), device="cuda")
+    _lib.check(lib.mgb_shallow_start(_lib.ptr(coarse), _lib.ptr(noise), _lib.ptr(smin), _lib.ptr(smax), sa, sn,
+                                     _lib.ptr(pad.to(torch.uint8)), _lib.ptr(xT), B, T, M, st), "shallow_start")
+    saf, snf = torch.tensor(sa, dtype=torch.float32).cuda(), torch.tensor(sn, dtype=torch.float32).cuda()
+    norm = ((coarse - smin) / (smax - smin) * 2 - 1).transpose(1, 2)[:, None]
+    ref = (saf * norm + snf * noise) * (~pad)[:, None, None, :]
+    assert torch.equal(xT, ref)
+    mel = torch.empty((B, T, M), device="cuda")
+    _lib.check(lib.mgb_denorm_mask(_lib.ptr(xT), _lib.ptr(smin), _lib.ptr(smax), _lib.ptr(pad.to(torch.uint8)), _lib.ptr(mel),
+                                   B, T, M, st), "denorm_mask")
+    ref2 = ((xT[:, 0].transpose(1, 2) + 1) / 2 * (smax - smin) + smin) * (~pad).unsqueeze(-1)
+    assert torch.equal(mel, ref2)
+    # no mask
+    _lib.check(lib.mgb_denorm_mask(_lib.ptr(xT), _lib.ptr(smin), _lib.ptr(smax), None, _lib.ptr(mel), B, T, M, st), "denorm_mask")
+    assert torch.equal(mel, (xT[:, 0].transpose(1, 2) + 1) / 2 * (smax - smin) + smin)
+
+
 def test_abi_error_codes():
     lib = _lib.load()
     dims = _lib.ModelDims(80, 256, 256, 20, 0)

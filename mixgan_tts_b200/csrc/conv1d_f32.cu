@@ -46,6 +46,19 @@ __device__ __forceinline__ float act_fwd(float v, int act) {
   return v;
 }
 
+// Epilogue form: leaky_relu / relu / identity are one select with a slope (0.2 / 0 / 1); Mish is a call, not inlined — the
+// per-element act_fwd() switch inlined 128 times per thread made the tensor-core forward kernel 23 000 SASS lines (395 MUFU
+// sites, 360 KB of code: instruction-cache misses in every epilogue) and the forward 15 us slower than the data gradient of
+// the same shape.
+__device__ __noinline__ float mish_call(float v) {
+  const float sp = v > 20.f ? v : log1pf(expf(v));
+  return v * tanhf(sp);
+}
+__device__ __forceinline__ float act_slope(int act) { return act == ACT_LEAKY ? 0.2f : (act == ACT_RELU ? 0.f : 1.f); }
+__device__ __forceinline__ float act_apply(float v, float slope, bool mish) {
+  return mish ? mish_call(v) : (v > 0.f ? v : slope * v);
+}
+
 struct ConvShape { int B, Tin, Tout, Cin, Cout, k, stride, pad; };
 
 // ---- weights: torch [Cout][Cin][k] -> wp [k][Cin][Cout] (forward / wgrad B operand) and wq [k][Cout][Cin] (dgrad) ----
@@ -214,7 +227,7 @@ __global__ void __launch_bounds__(NTHR, 2) conv_gemm_f32_kernel(const float* __r
           for (int e = 0; e < 4; ++e) if (n + e < N) pre[(size_t)m * N + n + e] = v[e];
         }
 #pragma unroll
-        for (int e = 0; e < 4; ++e) v[e] = act_fwd(v[e], act);
+        for (int e = 0; e < 4; ++e) v[e] = act_apply(v[e], act_slope(act), act == ACT_MISH);
       }
       if (vecB && n + 3 < N) *reinterpret_cast<float4*>(dst + (size_t)m * N + n) = make_float4(v[0], v[1], v[2], v[3]);
       else {
@@ -452,6 +465,8 @@ __global__ void __launch_bounds__(TC_THREADS) conv_gemm_tc_kernel(const float* _
     const int m = m0 + tid;                               // epilogue: thread = output row = TMEM lane
     // epilogue
     const bool split = gridDim.z > 1;
+    const float slope = act_slope(act);
+    const bool mish = act == ACT_MISH;
     float* dst = split ? part + (size_t)blockIdx.z * M * N : out;
     if (nkb > 0 && !tc::mbar_wait(bar_done, 0, TC_TIMEOUT)) __trap();
     tc::tc_fence_after();
@@ -474,12 +489,12 @@ __global__ void __launch_bounds__(TC_THREADS) conv_gemm_tc_kernel(const float* _
                         __uint_as_float(r[c4 * 4 + 3])};
           if (!split && !DGRAD) {
             if (bias) {
-#pragma unroll
-              for (int e = 0; e < 4; ++e) v[e] += bias[n + e];
+              const float4 bv = *reinterpret_cast<const float4*>(bias + n);
+              v[0] += bv.x; v[1] += bv.y; v[2] += bv.z; v[3] += bv.w;
             }
             if (pre) *reinterpret_cast<float4*>(pre + (size_t)m * N + n) = make_float4(v[0], v[1], v[2], v[3]);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) v[e] = act_fwd(v[e], act);
+            for (int e = 0; e < 4; ++e) v[e] = act_apply(v[e], slope, mish);
           }
           *reinterpret_cast<float4*>(dst + (size_t)m * N + n) = make_float4(v[0], v[1], v[2], v[3]);
         }

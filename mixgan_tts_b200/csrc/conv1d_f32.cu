@@ -7,12 +7,15 @@
 //                          three tcgen05.mma.kind::tf32 per k8-step, fp32 accumulation in TMEM) for channel counts that are
 //                          multiples of 32 — every layer of the discriminator but the two logit convolutions
 //   conv_gemm_f32_kernel, conv_wgrad_f32_kernel   exact-fp32 CUDA-core kernels: every other shape, and the weight gradient
-// Ablations of conv_gemm_tc_kernel on the 128 -> 512 (k = 5, stride 2) layer at 16 utterances x T = 800, B200, ncu with warm
-// L2 (forward 62 us / data gradient 51 us as shipped): A loads skipped (zeros staged) 30 / 49 us; MMAs skipped 54 / 44 us;
-// fence.proxy.async skipped, mbarrier.test_wait spinning instead of try_wait, weight ring 3 -> 4 slots (copies one -> two
-// k-blocks ahead), one row per thread instead of eight lanes per row, B staged by the threads instead of pre-split tiles by
-// cp.async.bulk, one __syncthreads per k-block instead of the mbarrier ring: all within 10 %.  The forward kernels wait on
-// the A gather (long-scoreboard stalls at the first use of the loaded registers, tensor pipe 17 % busy).
+// History of conv_gemm_tc_kernel on the 128 -> 512 (k = 5, stride 2) layer at 16 utterances x T = 800, B200, ncu with warm
+// L2.  First versions: forward 62 us / data gradient 51 us, and nothing moved them by more than 10 % — fence.proxy.async
+// skipped, mbarrier.test_wait spinning instead of try_wait, weight ring 3 -> 4 slots, one row per thread instead of eight
+// lanes per row, B staged by the threads instead of pre-split tiles by cp.async.bulk, one __syncthreads per k-block instead
+// of the mbarrier ring; only staging zeros instead of loading A did (30 / 49 us).  The cause was one line: the forward's
+// "+ rowbias" was added inside the load function, right behind the load — also as a no-op select when there is no rowbias —
+// so the loaded registers were consumed at once and the two-k-block prefetch never existed in the forward kernels.  With the
+// rowbias values in their own prefetched registers and the add at stage-write time: forward 28 us, data gradient 50 us (the
+// stride-2 data gradient stages, and multiplies, the zero rows of the taps that do not hit an input row).
 //
 // Layout: x [B][Tin][Cin], y [B][Tout][Cout] fp32, one row per frame (channels contiguous), Tout = (Tin - 1) / stride + 1
 // for the reference's padding (k - 1) / 2.  A kernel tap is a row offset, so no im2col buffer exists anywhere:
@@ -412,7 +415,10 @@ __global__ void __launch_bounds__(TC_THREADS) conv_gemm_tc_kernel(const float* _
         a_rb[i] = b * Ca + a_kc * 4;
       } else { a_base[i] = -1; a_q[i] = 0; a_rb[i] = 0; }
     }
-    auto load_g = [&](int kb, float4 (&ra)[8]) {             // k-block kb of the whole K axis -> registers
+    const bool has_rb = !DGRAD && rowbias != nullptr;
+    // k-block kb of the whole K axis -> registers; the rowbias values travel in their own registers and are added when the
+    // stage is written (adding them here made every load's use immediate: no prefetch for the layer that has a rowbias)
+    auto load_g = [&](int kb, float4 (&ra)[8], float4 (&rb)[8]) {
       const int kk = kb * TC_BK;
       const int j = kk / Ca, c0 = kk - j * Ca;
 #pragma unroll
@@ -429,38 +435,37 @@ __global__ void __launch_bounds__(TC_THREADS) conv_gemm_tc_kernel(const float* _
           src = a_q[i] + j;
           ok = ok && src >= 0 && src < s.Tin;
         }
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f), r = make_float4(0.f, 0.f, 0.f, 0.f);
         if (ok) {
           v = *reinterpret_cast<const float4*>(A + a_base[i] + (long long)src * Ca + c0);
-          if (!DGRAD && rowbias) {
-            const float4 r = *reinterpret_cast<const float4*>(rowbias + a_rb[i] + c0);
-            v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
-          }
+          if (has_rb) r = *reinterpret_cast<const float4*>(rowbias + a_rb[i] + c0);
         }
         ra[i] = v;
+        if (!DGRAD) rb[i] = r;
       }
     };
-    auto stage_step = [&](int it, float4 (&ra)[8]) {          // publish k-block `it` from ra, then refill ra with it + 2
+    auto stage_step = [&](int it, float4 (&ra)[8], float4 (&rb)[8]) {   // publish k-block `it` from ra, then refill ra with it + 2
       const int stage = it & 1;
       if (it >= 2 && !tc::mbar_wait(&bar_free[stage], ((it >> 1) + 1) & 1, TC_TIMEOUT)) __trap();
       uint8_t* st = smA + stage * TC_A_STAGE + a_kc * TC_A_LBO + a_r0 * 16;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        float4 hi, lo;
-        split_tf32(ra[i], hi, lo);
+        float4 hi, lo, v = ra[i];
+        if (has_rb) { v.x += rb[i].x; v.y += rb[i].y; v.z += rb[i].z; v.w += rb[i].w; }
+        split_tf32(v, hi, lo);
         *reinterpret_cast<float4*>(st + i * 64) = hi;
         *reinterpret_cast<float4*>(st + TC_A_BYTES + i * 64) = lo;
       }
       tc::fence_proxy_async_smem();
       tc::mbar_arrive(&bar_afull[stage]);
-      if (it + 2 < nkb) load_g(kb0 + it + 2, ra);
+      if (it + 2 < nkb) load_g(kb0 + it + 2, ra, rb);
     };
-    float4 r0[8], r1[8];
-    if (nkb > 0) load_g(kb0, r0);
-    if (nkb > 1) load_g(kb0 + 1, r1);
+    float4 r0[8], r1[8], q0[8], q1[8];
+    if (nkb > 0) load_g(kb0, r0, q0);
+    if (nkb > 1) load_g(kb0 + 1, r1, q1);
     for (int it = 0; it < nkb; it += 2) {
-      stage_step(it, r0);
-      if (it + 1 < nkb) stage_step(it + 1, r1);
+      stage_step(it, r0, q0);
+      if (it + 1 < nkb) stage_step(it + 1, r1, q1);
     }
     const int m = m0 + tid;                               // epilogue: thread = output row = TMEM lane
     // epilogue

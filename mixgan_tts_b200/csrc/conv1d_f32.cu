@@ -138,21 +138,20 @@ __global__ void __launch_bounds__(NTHR, 2) conv_gemm_f32_kernel(const float* __r
     src = t * s.stride + j - s.pad;
     return src >= 0 && src < s.Tin;
   };
-  float4 pa[2], pb;
+  const bool has_rb = !DGRAD && rowbias != nullptr;
+  float4 pa[2], prb[2], pb;        // prb: the rowbias values, added when the tile is stored (not behind the load: see the header)
   auto load_g = [&](int ks) {
     const int kk = ks * TK + a_k4;
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      prb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (a_b[i] >= 0 && kk < K) {
         if (vecA) {
           int src;
           if (src_row(a_t[i], kj, src)) {
             v = *reinterpret_cast<const float4*>(A + ((size_t)a_b[i] * src_per_b + src) * Ca + kc);
-            if (!DGRAD && rowbias) {
-              const float4 r4 = *reinterpret_cast<const float4*>(rowbias + (size_t)a_b[i] * Ca + kc);
-              v.x += r4.x; v.y += r4.y; v.z += r4.z; v.w += r4.w;
-            }
+            if (has_rb) prb[i] = *reinterpret_cast<const float4*>(rowbias + (size_t)a_b[i] * Ca + kc);
           }
         } else {
           float e4[4] = {0.f, 0.f, 0.f, 0.f};
@@ -190,8 +189,10 @@ __global__ void __launch_bounds__(NTHR, 2) conv_gemm_f32_kernel(const float* __r
   auto store_s = [&](int buf) {
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
-      As[buf][a_k4 + 0][a_r + 64 * i] = pa[i].x; As[buf][a_k4 + 1][a_r + 64 * i] = pa[i].y;
-      As[buf][a_k4 + 2][a_r + 64 * i] = pa[i].z; As[buf][a_k4 + 3][a_r + 64 * i] = pa[i].w;
+      float4 v = pa[i];
+      if (has_rb) { v.x += prb[i].x; v.y += prb[i].y; v.z += prb[i].z; v.w += prb[i].w; }
+      As[buf][a_k4 + 0][a_r + 64 * i] = v.x; As[buf][a_k4 + 1][a_r + 64 * i] = v.y;
+      As[buf][a_k4 + 2][a_r + 64 * i] = v.z; As[buf][a_k4 + 3][a_r + 64 * i] = v.w;
     }
     *reinterpret_cast<float4*>(&Bs[buf][b_k][b_n4]) = pb;
   };
@@ -547,11 +548,14 @@ __global__ void __launch_bounds__(NTHR, 2) conv_wgrad_f32_kernel(const float* __
   const int b_q = tid >> 4, b_n4 = (tid & 15) * 4;
   const int kk = k0 + a_k4;
   const int kj = kk / s.Cin, kc = kk - kj * s.Cin;
-  float4 pa[2], pb;
+  // the rowbias values travel in their own registers (prb) and are added when the tile is stored: an add right behind the
+  // load — even predicated off — waits for the load and cancels the prefetch (see the header)
+  float4 pa[2], prb[2], pb;
   auto load_g = [&](int mq) {
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      prb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
       const int m = mq + a_q + 8 * i;
       if (m < me && kk < K) {
         const int b = m / s.Tout, to = m - b * s.Tout;
@@ -559,10 +563,7 @@ __global__ void __launch_bounds__(NTHR, 2) conv_wgrad_f32_kernel(const float* __
           const int ti = to * s.stride + kj - s.pad;
           if (ti >= 0 && ti < s.Tin) {
             v = *reinterpret_cast<const float4*>(x + ((size_t)b * s.Tin + ti) * s.Cin + kc);
-            if (rowbias) {
-              const float4 r4 = *reinterpret_cast<const float4*>(rowbias + (size_t)b * s.Cin + kc);
-              v.x += r4.x; v.y += r4.y; v.z += r4.z; v.w += r4.w;
-            }
+            if (rowbias) prb[i] = *reinterpret_cast<const float4*>(rowbias + (size_t)b * s.Cin + kc);
           }
         } else {
           float e4[4] = {0.f, 0.f, 0.f, 0.f};
@@ -596,7 +597,11 @@ __global__ void __launch_bounds__(NTHR, 2) conv_wgrad_f32_kernel(const float* __
   };
   auto store_s = [&](int buf) {
 #pragma unroll
-    for (int i = 0; i < 2; ++i) *reinterpret_cast<float4*>(&As[buf][a_q + 8 * i][a_k4]) = pa[i];
+    for (int i = 0; i < 2; ++i) {
+      float4 v = pa[i];
+      if (rowbias) { v.x += prb[i].x; v.y += prb[i].y; v.z += prb[i].z; v.w += prb[i].w; }
+      *reinterpret_cast<float4*>(&As[buf][a_q + 8 * i][a_k4]) = v;
+    }
     *reinterpret_cast<float4*>(&Bs[buf][b_q][b_n4]) = pb;
   };
   float acc[8][4];
